@@ -1,0 +1,78 @@
+/* osbli_oracle.h -- CPU restatement (plain C99) of the OpenSBLI per-timestep solver hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library; the product (opensbli_b200) never does.
+ *
+ * It restates, loop by loop and un-fused, what the reference's generated OPS-C program executes
+ * for the canonical compressible Euler / Navier-Stokes system (ideal gas, conservative variables
+ * rho, rhou_i, rhoE):
+ *   program order ............ opensbli/code_generation/algorithm/algorithm.py:384-477
+ *   constituent relations .... app scripts (strings); opensbli/equation_types/opensbliequations.py:297-321
+ *   characteristic LLF flux .. opensbli/schemes/spatial/shock_capturing.py:357-536
+ *   Roe / simple average ..... opensbli/schemes/spatial/averaging.py:31-114
+ *   eigensystems ............. opensbli/physical_models/euler_eigensystem.py:57-135
+ *   WENO-JS / WENO-Z ......... opensbli/schemes/spatial/weno.py:35-465
+ *   TENO5 / TENO6 ............ opensbli/schemes/spatial/teno.py:57-465
+ *   central-4 conv + viscous . opensbli/schemes/spatial/scheme.py:63-387, optimisations/StoreSome.py:71-161
+ *   RK3 / low-storage RK ..... opensbli/schemes/temporal/rk_sbli.py:58-133, rk_LS.py:70-166
+ *   periodic / Dirichlet ..... opensbli/core/boundary_conditions/periodic.py:42-56, dirichlet.py:28-41
+ *
+ * Parity pinning: the reference has NO tests or golden vectors of its own;
+ * this restatement is pinned against (i) outputs of the reference itself run here -- its generated
+ * C compiled against oracle/ops_seq.h into oracle/_ref/<config>/ref_seq -- and (ii) the fixtures in
+ * tests/golden/ minted from those executables by tests/golden/make_golden.py.
+ *
+ * Data layout: one padded array per variable, x fastest, halo `halo` (=5, opsc.py:707-711) on both
+ * sides of every active dimension:  idx(i,j,k) = (i+h) + px*((j+h) + py*(k+h)).
+ */
+#ifndef OSBLI_ORACLE_H
+#define OSBLI_ORACLE_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { OSBO_CONV_CENTRAL = 0, OSBO_CONV_WENO = 1, OSBO_CONV_TENO = 2 };
+enum { OSBO_AVG_SIMPLE = 0, OSBO_AVG_ROE = 1 };
+enum { OSBO_RK_SBLI = 0, OSBO_RK_LS = 1 };
+enum { OSBO_BC_PERIODIC = 0, OSBO_BC_DIRICHLET = 1 };
+
+typedef struct {
+  int ndim;
+  int np[3];
+  int halo;        /* storage halo, 5 */
+  int conv;        /* OSBO_CONV_* */
+  int order;       /* central 4 | weno 5 | teno 5,6 */
+  int weno_z;      /* 0 JS, 1 Z */
+  int averaging;   /* OSBO_AVG_* */
+  int viscous;     /* 0 Euler, 1 constant-viscosity Navier-Stokes */
+  int rk;          /* OSBO_RK_* */
+  int nstages;
+  double rk_a[8];  /* SBLI: rkold ; LS: A */
+  double rk_b[8];  /* SBLI: rknew ; LS: B */
+  double gama, Minf, Re, Pr, dt, eps, teno_ct;
+  double delta[3];
+  int bc[3][2];
+  double bc_q[3][2][5]; /* Dirichlet: conservative state imposed on boundary + halo points */
+} osbo_cfg;
+
+/* number of doubles of one padded array */
+long osbo_padded_size(const osbo_cfg *c);
+
+/* Advance nsteps full RK steps.  q[m] (m < ndim+2) point to padded arrays; rk_reg[m] are the RK
+ * register arrays (tempRK_* for LS, *_RKold for SBLI; zero-halo in the reference, padded here for
+ * simplicity -- only interior is touched).  Returns 0 on success. */
+int osbo_advance(const osbo_cfg *c, double *const *q, double *const *rk_reg, int nsteps);
+
+/* Pieces, exposed for unit tests. */
+void osbo_apply_bcs(const osbo_cfg *c, double *const *q);
+void osbo_residual(const osbo_cfg *c, double *const *q, double *const *R); /* CR + spatial kernels */
+/* one-interface reconstructions on the 6-point window f[0..5] = f(i-2..i+3):
+ * fp = 1/2(CF + lambda CS), fm = 1/2(CF - lambda CS); returns Recon (both sides summed). */
+double osbo_recon_teno5(const double *fp, const double *fm, double eps, double ct);
+double osbo_recon_teno6(const double *fp, const double *fm, double eps, double ct);
+double osbo_recon_weno5(const double *fp, const double *fm, int z);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,154 @@
+"""Test-side helpers: ctypes binding of the CPU oracle (oracle/osbli_oracle.c), runner for the
+reference executables in oracle/_ref/ and reader for their raw dumps.  Test infrastructure only."""
+import ctypes
+import os
+import subprocess
+import tempfile
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(REPO, 'oracle')
+REF_DIR = os.path.join(ORACLE_DIR, '_ref')
+
+CONV = {'central': 0, 'weno': 1, 'teno': 2}
+BC = {'periodic': 0, 'dirichlet': 1}
+
+
+class OsboCfg(ctypes.Structure):
+    _fields_ = [('ndim', ctypes.c_int), ('np', ctypes.c_int * 3), ('halo', ctypes.c_int),
+                ('conv', ctypes.c_int), ('order', ctypes.c_int), ('weno_z', ctypes.c_int),
+                ('averaging', ctypes.c_int), ('viscous', ctypes.c_int), ('rk', ctypes.c_int),
+                ('nstages', ctypes.c_int), ('rk_a', ctypes.c_double * 8), ('rk_b', ctypes.c_double * 8),
+                ('gama', ctypes.c_double), ('Minf', ctypes.c_double), ('Re', ctypes.c_double),
+                ('Pr', ctypes.c_double), ('dt', ctypes.c_double), ('eps', ctypes.c_double),
+                ('teno_ct', ctypes.c_double), ('delta', ctypes.c_double * 3),
+                ('bc', (ctypes.c_int * 2) * 3), ('bc_q', ((ctypes.c_double * 5) * 2) * 3)]
+
+
+_lib = None
+
+
+def oracle_lib():
+    global _lib
+    if _lib is None:
+        so = os.path.join(ORACLE_DIR, 'libosbli_oracle.so')
+        src = os.path.join(ORACLE_DIR, 'osbli_oracle.c')
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(['make', '-C', ORACLE_DIR, 'libosbli_oracle.so'], stdout=subprocess.DEVNULL)
+        _lib = ctypes.CDLL(so)
+        _lib.osbo_padded_size.restype = ctypes.c_long
+        for f in ('osbo_recon_teno5', 'osbo_recon_teno6', 'osbo_recon_weno5'):
+            getattr(_lib, f).restype = ctypes.c_double
+    return _lib
+
+
+def make_cfg(plan):
+    """plan: dict as produced by opensbli_b200.plan (numeric, resolved)."""
+    c = OsboCfg()
+    c.ndim = plan['ndim']
+    for d in range(3):
+        c.np[d] = plan['np'][d] if d < plan['ndim'] else 1
+        c.delta[d] = plan['delta'][d] if d < plan['ndim'] else 1.0
+    c.halo = 5
+    c.conv = CONV[plan['conv']]
+    c.order = plan['order']
+    c.weno_z = 1 if plan.get('weno_formulation', 'JS') == 'Z' else 0
+    c.averaging = 1 if plan.get('averaging', 'roe') == 'roe' else 0
+    c.viscous = 1 if plan.get('viscous') else 0
+    c.rk = 0 if plan['rk'] == 'sbli' else 1
+    c.nstages = len(plan['rk_a'])
+    for s in range(c.nstages):
+        c.rk_a[s] = plan['rk_a'][s]
+        c.rk_b[s] = plan['rk_b'][s]
+    k = plan['constants']
+    c.gama = k['gama']
+    c.Minf = k.get('Minf', 1.0)
+    c.Re = k.get('Re', 1.0)
+    c.Pr = k.get('Pr', 1.0)
+    c.dt = k['dt']
+    c.eps = k.get('eps', 1e-16)
+    c.teno_ct = k.get('TENO_CT', 1e-6)
+    for d in range(plan['ndim']):
+        for s in range(2):
+            b = plan['bc'][d][s]
+            c.bc[d][s] = BC[b['type']]
+            if b['type'] == 'dirichlet':
+                for m, v in enumerate(b['q']):
+                    c.bc_q[d][s][m] = v
+    return c
+
+
+def padded_shape(plan, halo=5):
+    nd = plan['ndim']
+    return tuple(plan['np'][d] + 2 * halo for d in reversed(range(nd)))   # numpy order (k,j,i)
+
+
+def oracle_advance(plan, q, nsteps, rk_reg=None):
+    """q: list of padded numpy arrays (C-order, x fastest), advanced in place. Returns rk registers."""
+    lib = oracle_lib()
+    cfg = make_cfg(plan)
+    nv = plan['ndim'] + 2
+    assert len(q) == nv
+    q = [np.ascontiguousarray(a, dtype=np.float64) for a in q]
+    if rk_reg is None:
+        rk_reg = [np.zeros_like(a) for a in q]
+    P = ctypes.POINTER(ctypes.c_double)
+    qa = (P * nv)(*[a.ctypes.data_as(P) for a in q])
+    ra = (P * nv)(*[a.ctypes.data_as(P) for a in rk_reg])
+    rc = lib.osbo_advance(ctypes.byref(cfg), qa, ra, ctypes.c_int(nsteps))
+    assert rc == 0
+    return q, rk_reg
+
+
+def oracle_residual(plan, q):
+    lib = oracle_lib()
+    cfg = make_cfg(plan)
+    nv = plan['ndim'] + 2
+    q = [np.ascontiguousarray(a, dtype=np.float64) for a in q]
+    R = [np.zeros_like(a) for a in q]
+    P = ctypes.POINTER(ctypes.c_double)
+    qa = (P * nv)(*[a.ctypes.data_as(P) for a in q])
+    ra = (P * nv)(*[a.ctypes.data_as(P) for a in R])
+    lib.osbo_residual(ctypes.byref(cfg), qa, ra)
+    return R
+
+
+# ---------------------------------------------------------------- reference executables
+def have_ref(config):
+    return os.path.exists(os.path.join(REF_DIR, config, 'ref_seq'))
+
+
+def read_dump(path):
+    raw = open(path, 'rb').read()
+    hdr = np.frombuffer(raw[:40], dtype=np.int32)
+    nd = int(hdr[0])
+    size, d_m, d_p = hdr[1:4], hdr[4:7], hdr[7:10]
+    pdim = [int(size[d] - d_m[d] + d_p[d]) for d in range(nd)]
+    data = np.frombuffer(raw[40:], dtype=np.float64).reshape(tuple(reversed(pdim))).copy()
+    return data
+
+
+def run_ref(config, params, fields, exe='ref_seq', dump_all=False, threads=None):
+    """Run oracle/_ref/<config>/<exe> with parameter overrides (dict of env names, e.g. block0np0, niter, dt)
+    and return {field: padded ndarray} of the final-time dump (+ wall time of the reference's own timer)."""
+    d = os.path.join(REF_DIR, config)
+    with tempfile.TemporaryDirectory() as out:
+        env = dict(os.environ, OSBLI_OUT=out)
+        if dump_all:
+            env['OSBLI_DUMP_ALL'] = '1'
+        if threads:
+            env['OMP_NUM_THREADS'] = str(threads)
+        for k, v in params.items():
+            env[k] = repr(v) if isinstance(v, float) else str(v)
+        res = subprocess.run([os.path.join(d, exe)], env=env, cwd=out, stdout=subprocess.PIPE, check=True, text=True)
+        wall = None
+        for line in res.stdout.splitlines():
+            if 'Total Wall time' in line:
+                wall = float(line.split()[-1])
+        outd = {}
+        for f in fields:
+            cand = [p for p in os.listdir(out) if p.endswith('.%s_B0.bin' % f) and (dump_all == p.startswith('all.'))]
+            assert len(cand) == 1, (f, os.listdir(out))
+            outd[f] = read_dump(os.path.join(out, cand[0]))
+        outd['_wall'] = wall
+    return outd
