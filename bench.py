@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- grid-point updates/s of the OpenSBLI solver hot path (fp64, TENO5 Taylor-Green vortex).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size S] [--impl reference]
+
+One "step" = one full RK3 time step (3 stages) of all 5 conserved variables on every grid point of the block,
+i.e. exactly the body of the reference's timed loop (algorithm.py:301-327, 440-474): BCs/exchanges, constituent
+relations, TENO5 characteristic flux sweeps in 3 directions, viscous terms, RK update.
+Workload (N=1): BASELINE.json configs[2] = TGV Re=1600, TENO5 + StoreSome(4) viscous + RungeKuttaLS(3), 512^3 fp64.
+N>1: weak scaling, 512^3 points per GPU, slab decomposition (N=8 -> 1024^3), halo exchange by peer stores over NVLink.
+
+Prints ONE JSON line (see the contract in the task statement): value = whole-job updates/s with the state resident in
+HBM; e2e = the same through the C-ABI call with HOST buffers (pinned H2D of the state + step + D2H every step);
+roofline = dominant kernel family (flux sweeps) against the measured FP64-pipe peak (and HBM for context);
+cpu_baseline = the reference's own generated C (oracle/_ref/tgv_teno5/ref_omp) on this box's host cores.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = 'grid-point updates/s (fp64, TENO5 TGV)'
+UNIT = 'updates/s'
+ALG_BYTES_PER_UPDATE = 480.0          # 3 stages x (5 q + 5 RK regs) x (read + write) x 8 B
+ALG_FLOP_PER_POINT_FLUX_SWEEP = 2836.0 + 50.0 / 3.0   # reference count_ops: one LLFTeno_reconstruction_d loop + its share of the Residual loop
+ALG_FLOP_PER_UPDATE = 27.1e3          # 3 x 9038 (reference's own operation count, opsc.py:411-418)
+LS3 = dict(rk='ls', rk_a=[0.0, -5.0 / 9.0, -153.0 / 128.0], rk_b=[1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0])
+
+
+def tgv_plan(np3):
+    dl = 2 * math.pi / 512 if max(np3) > 512 else 2 * math.pi / np3[0]
+    per = [[dict(type='periodic'), dict(type='periodic')] for _ in range(3)]
+    return dict(ndim=3, np=list(np3), delta=[dl] * 3, conv='teno', order=5, averaging='roe', viscous=True,
+                constants=dict(gama=1.4, Minf=0.1, Re=1600.0, Pr=0.71, dt=0.003385 * 64 * dl / (2 * math.pi),
+                               eps=1e-16, TENO_CT=1e-6), bc=per, **LS3)
+
+
+def global_grid(ngpus, size):
+    """weak scaling: size^3 points per GPU; N=2: (s,s,2s) N=4: (s,2s,2s) N=8: (2s,2s,2s)."""
+    f = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}[ngpus]
+    return [size * f[0], size * f[1], size * f[2]]
+
+
+def tgv_state_into(bufs, plan, k0, nk, halo=5):
+    """Analytic TGV initial condition (apps/taylor_green_vortex/taylor_green_vortex.py:87-101) for planes
+    [k0, k0+nk) of the block, written into the padded numpy arrays bufs (interior only; BCs fill the halos)."""
+    import numpy as np
+    n0, n1 = plan['np'][0], plan['np'][1]
+    d = plan['delta']
+    x = (np.arange(n0) * d[0])[None, None, :]
+    y = (np.arange(n1) * d[1])[None, :, None]
+    z = ((k0 + np.arange(nk)) * d[2])[:, None, None]
+    g, M = 1.4, 0.1
+    s = (slice(halo, halo + nk), slice(halo, halo + n1), slice(halo, halo + n0))
+    u0 = np.sin(x) * np.cos(y) * np.cos(z)
+    u1 = -np.cos(x) * np.sin(y) * np.cos(z)
+    p = 1.0 / (g * M * M) + (1.0 / 16.0) * (np.cos(2.0 * x) + np.cos(2.0 * y)) * (2.0 + np.cos(2.0 * z))
+    r = g * M * M * p
+    for b in bufs:
+        b[...] = 0.0
+    bufs[0][s] = r
+    bufs[1][s] = r * u0
+    bufs[2][s] = r * u1
+    bufs[3][s] = 0.0
+    bufs[4][s] = p / (g - 1.0) + 0.5 * r * (u0 * u0 + u1 * u1)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference
+def cpu_sample_size(cores):
+    """Bounded sample of the same workload: TGV TENO5 on n^3 points for 2 steps, ~10-20 s of CPU work."""
+    rate = 4.0e4 * max(cores, 1)              # reference generated C: ~4-6e4 updates/s per core
+    n = int(round((rate * 12.0 / 2.0) ** (1.0 / 3.0) / 8.0)) * 8
+    return max(32, min(n, 256))
+
+
+def run_reference_cpu(steps, n, threads):
+    """Times the reference's own generated C (OPS-OpenMP stand-in) with its own timer (time loop only)."""
+    exe = os.path.join(REPO, 'oracle', '_ref', 'tgv_teno5', 'ref_omp')
+    if not os.path.exists(exe):
+        return None
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), block0np0=str(n), block0np1=str(n), block0np2=str(n),
+               niter=str(steps), dt=repr(0.003385 * 64 / n))
+    env.pop('OSBLI_OUT', None)
+    out = subprocess.run([exe], env=env, stdout=subprocess.PIPE, text=True, check=True).stdout
+    for line in out.splitlines():
+        if 'Total Wall time' in line:
+            return float(line.split()[-1])
+    return None
+
+
+def run_oracle_port_cpu(steps, n):
+    """Fallback when oracle/_ref is absent: the plain-C oracle port (1 core) on a small sample."""
+    sys.path.insert(0, os.path.join(REPO, 'tests'))
+    import numpy as np
+    import oracle_util as ou
+    plan = tgv_plan([n, n, n])
+    q = [np.zeros((n + 10,) * 3) for _ in range(5)]
+    tgv_state_into(q, plan, 0, n)
+    t0 = time.perf_counter()
+    ou.oracle_advance(plan, q, steps)
+    return time.perf_counter() - t0
+
+
+def cpu_model():
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                return line.split(':', 1)[1].strip()
+    except Exception:
+        pass
+    return 'unknown'
+
+
+def reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = args.cpu_size or cpu_sample_size(cores)
+    exe = os.path.join(REPO, 'oracle', '_ref', 'tgv_teno5', 'ref_omp')
+    kind = 'reference'
+    if os.path.exists(exe):
+        if args.warmup > 0:
+            run_reference_cpu(args.warmup, n, cores)
+        wall = run_reference_cpu(args.steps, n, cores)
+        sample = 'TGV TENO5 %d^3 x %d steps (reference generated C, g++ -O3 -march=x86-64-v3 -fopenmp, OPS stand-in), %s' % (n, args.steps, cpu_model())
+    else:   # the oracle always exists: fall back to the plain-C port (scalar, 1 core)
+        kind, cores, n = 'port', 1, 40
+        wall = run_oracle_port_cpu(args.steps, n)
+        sample = 'TGV TENO5 %d^3 x %d steps (oracle/osbli_oracle.c port, 1 core), %s' % (n, args.steps, cpu_model())
+    value = n ** 3 * args.steps / wall
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * wall / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'TGV Re=1600 TENO5+StoreSome(4)+RK-LS3 512^3 fp64 (BASELINE configs[2]); CPU arm timed on a bounded %d^3 sample' % n},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--size', type=int, default=512, help='points per direction per GPU (default 512: the headline case)')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--cpu-size', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import opensbli_b200
+    from opensbli_b200.decomp import DistributedSimulation, local_extent
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the B200 back end has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    if world != args.gpus and rank == 0:
+        print('bench.py: --gpus %d but WORLD_SIZE=%d; using WORLD_SIZE' % (args.gpus, world), file=sys.stderr)
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+
+    plan = tgv_plan(global_grid(world, args.size))
+
+    class _Solo(object):
+        def get_rank(self): return 0
+        def get_world_size(self): return 1
+    dsim = DistributedSimulation(plan, dist if world > 1 else _Solo(), device=local_rank)
+    sim = dsim.sim
+    lplan = dsim.plan
+    k0, nk = local_extent(plan, rank, world)
+    shape = sim.shape
+    nbytes_state = 5 * int(np.prod(shape)) * 8
+
+    # pinned host buffers (torch only provides the pinned allocation)
+    hin = [torch.empty(shape, dtype=torch.float64, pin_memory=True) for _ in range(5)]
+    hout = [torch.empty(shape, dtype=torch.float64, pin_memory=True) for _ in range(5)]
+    q_in = [t.numpy() for t in hin]
+    q_out = [t.numpy() for t in hout]
+    tgv_state_into(q_in, lplan, k0, nk)
+    sim.set_state(q_in)
+
+    def barrier():
+        sim.sync()
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+
+    # ---- resident-state timing: W warm-up steps, then EXACTLY K steps between barriers + syncs
+    dsim.step(W)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = sim.launch_count()
+    torch.cuda.synchronize()
+    barrier()
+    sim.timer_start()                              # CUDA events on the solver's own stream (torch events would not see it)
+    dsim.step(K)
+    ms = sim.timer_stop()
+    barrier()
+    launches = sim.launch_count() - launches0
+    clocks = sampler.summary()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    points = float(np.prod(plan['np']))
+    value = points * K / (ms * 1e-3)
+
+    # ---- state sanity (no NaN) after the timed region
+    chk = sim.download('rho')
+    finite = bool(np.isfinite(chk).all())
+
+    # ---- per-kernel-family device time (events around every launch of one step) -> roofline of the dominant family
+    prof = sim.profile_step() if world == 1 else None
+    roofline = roofline_hbm = None
+    fp64_peak = opensbli_b200.measure_fp64_peak(local_rank)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    if prof:
+        fl = prof['flux']
+        per_launch_ms = fl['ms'] / max(fl['launches'], 1)
+        pts_local = float(np.prod(lplan['np']))
+        ach = ALG_FLOP_PER_POINT_FLUX_SWEEP * pts_local / (per_launch_ms * 1e-3) / 1e12
+        tot = sum(v['ms'] for v in prof.values())
+        roofline = {'bound': 'fp64', 'kernel': 'k_flux_{x,yz} (TENO5 characteristic flux sweep + flux difference)',
+                    'achieved': ach, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': ach / fp64_peak if fp64_peak else None,
+                    'traffic': None, 'launch_ms': per_launch_ms, 'share_of_step': fl['ms'] / tot if tot else None,
+                    'peak_source': 'measured in this run: DFMA micro-benchmark osb_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)',
+                    'flop_model': "reference's own count_ops: 2836 per point per LLFTeno_reconstruction loop + 50/3 Residual",
+                    'families_ms': {k: v['ms'] for k, v in prof.items()}}
+        roofline_hbm = {'bound': 'hbm', 'achieved': ALG_BYTES_PER_UPDATE * value / world / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                        'frac': ALG_BYTES_PER_UPDATE * value / world / 1e9 / hbm_peak,
+                        'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
+                        'note': 'whole step, algorithmic 480 B/update; the step is FP64-bound, shown for context'}
+
+    # ---- end to end through the C-ABI call with HOST buffers: every step = H2D state + 1 step + D2H state
+    e2e = None
+    if not args.no_e2e:
+        Ke = min(K, 5)
+        tgv_state_into(q_in, lplan, k0, nk)
+        if world == 1:
+            sim.advance_host(q_in, q_out, 1)      # warm-up of the path
+            tot_ms = 0.0
+            src, dst = q_out, q_in
+            for _ in range(Ke):
+                tot_ms += sim.advance_host(src, dst, 1)
+                src, dst = dst, src
+            e2e = {'value': points * Ke / (tot_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': nbytes_state,
+                   'd2h_bytes_per_step': nbytes_state, 'steps': Ke,
+                   'call': 'osb_advance_host(ctx, q_in, q_out, 1) per step, pinned host buffers in the reference layout'}
+        else:
+            barrier()
+            sim.timer_start()
+            for _ in range(Ke):
+                sim.set_state(q_in)
+                dsim.step(1)
+                for m, nme in enumerate(sim.q_names):
+                    q_out[m][...] = sim.download(nme)
+            t = torch.tensor([sim.timer_stop()], dtype=torch.float64, device='cuda')
+            barrier()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e = {'value': points * Ke / (float(t.item()) * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': nbytes_state * world,
+                   'd2h_bytes_per_step': nbytes_state * world, 'steps': Ke,
+                   'call': 'per step: osb_upload x5 + stage loop with halo pushes + osb_download x5 on every rank'}
+
+    # ---- CPU baseline beside it (rank 0, N=1): the reference's generated C on this box's host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n = args.cpu_size or cpu_sample_size(cores)
+        wall = run_reference_cpu(2, n, cores)
+        if wall:
+            cpu = {'value': n ** 3 * 2 / wall, 'unit': UNIT, 'cores': cores, 'kind': 'reference',
+                   'sample': 'TGV TENO5 %d^3 x 2 steps, reference generated C (OPS-OpenMP stand-in, g++ -O3 -march=x86-64-v3 -fopenmp), %s' % (n, cpu_model())}
+        else:
+            cpu = {'value': None, 'unit': UNIT, 'cores': cores, 'kind': 'reference', 'sample': 'oracle/_ref/tgv_teno5/ref_omp missing'}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+                'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+                'data': 'synthetic',
+                'config': {'workload': 'TGV Re=1600 TENO5(Roe,LLF)+StoreSome(4) viscous+RK-LS3, %s grid fp64 (BASELINE configs[%d]), %d^3 points per GPU'
+                                       % ('x'.join(str(n) for n in plan['np']), 2 if world == 1 else 4, args.size),
+                           'grid': plan['np'], 'parallelism': 'slab%d' % world,
+                           'l2_policy': 'working set %.1f GB per GPU >> 126 MB L2 (no flush needed)' % (19 * np.prod(shape) * 8 / 1e9),
+                           'finite': finite},
+                'roofline': roofline, 'roofline_hbm': roofline_hbm, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e,
+                'gpu_launches': int(launches), 'fp64_peak_tflops_measured': fp64_peak,
+                'alg_flop_per_update': ALG_FLOP_PER_UPDATE, 'achieved_alg_tflops': ALG_FLOP_PER_UPDATE * value / world / 1e12}
+        print(json.dumps(line))
+    dsim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

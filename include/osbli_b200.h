@@ -1,0 +1,93 @@
+/* osbli_b200.h -- C ABI of the B200-native execution back end for OpenSBLI.
+ *
+ * This is the drop-in boundary: everything the reference obtains today by
+ * emitting OPS-C text (opensbli/code_generation/opsc.py:250-282) and linking the external OPS
+ * runtime is reached through these entry points instead.  The caller is the Python back-end class
+ * `opensbli_b200.B200(alg)` (same call shape as `OPSC(alg)`, opsc.py:253) via ctypes; signatures
+ * carry only plain pointers and sizes.  Single-threaded host control, one context per process/GPU.
+ * Every function returns 0 on success and a non-zero code otherwise (never throws or aborts);
+ * the message is available from osb_last_error().  Device memory is owned by the context; host
+ * buffers are owned by the caller.
+ *
+ * Field arrays cross the boundary in the reference's own layout (opsc.py:693-722 ops_decl_dat,
+ * halo rule opsc.py:707-711): one array per variable, x fastest, padded by 5 halo points on both
+ * sides of every active dimension.  Field names are the reference's dataset names without the
+ * block suffix: rho, rhou0.., rhoE, u0.., p, a, T, Residual0.., tempRK_rho.. / rho_RKold..
+ */
+#ifndef OSBLI_B200_H
+#define OSBLI_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct osb_ctx osb_ctx;
+
+/* Create a solver context from a plan (text, "osbli_plan 1" format written by
+ * opensbli_b200.plan.to_text).  Replaces: OPSC.__init__ code emission + ops_init / ops_decl_block /
+ * ops_decl_dat / ops_decl_stencil / ops_decl_halo / ops_partition (opsc.py:435-593, 693-722).
+ * device < 0 selects the current CUDA device. */
+int osb_create(const char *plan_text, int device, osb_ctx **ctx);
+int osb_destroy(osb_ctx *ctx);
+/* ctx may be NULL (error of a failed osb_create). */
+const char *osb_last_error(const osb_ctx *ctx);
+
+/* Runtime constants; replaces ops_decl_const + the `name=Input;` substitution
+ * (opsc.py:625-654, utilities/helperfunctions.py:130-149). */
+int osb_set_const_f64(osb_ctx *ctx, const char *name, double value);
+int osb_get_const_f64(const osb_ctx *ctx, const char *name, double *value);
+
+/* Field access; replaces ops_decl_dat(_hdf5) initial values and ops_fetch_dat_hdf5_file
+ * (opsc.py:693-722, core/io_hdf5.py:99-127).  dims/halo_m/halo_p have 3 entries. */
+int osb_num_fields(const osb_ctx *ctx);
+const char *osb_field_name(const osb_ctx *ctx, int index);
+int osb_field_info(const osb_ctx *ctx, const char *name, int *dims, int *halo_m, int *halo_p);
+int osb_upload(osb_ctx *ctx, const char *name, const double *host_padded);
+int osb_download(osb_ctx *ctx, const char *name, double *host_padded);
+int osb_device_ptr(osb_ctx *ctx, const char *name, double **device_ptr);
+
+/* The time loop body, in the reference's program order (algorithm.py:440-474):
+ *   per iteration: BCs ; [save] ; per stage: constituent relations, spatial kernels, RK update, BCs.
+ * osb_step enqueues nsteps iterations on the context's stream and returns without synchronising. */
+int osb_step(osb_ctx *ctx, int nsteps);
+int osb_sync(osb_ctx *ctx);
+/* Pieces of the loop, for parity tests: boundary conditions on q; residual of the current q
+ * (constituent relations + all spatial kernels) left in Residual0.. */
+int osb_apply_bcs(osb_ctx *ctx);
+int osb_residual(osb_ctx *ctx);
+
+/* Stage-level control for a decomposed run (one context per rank): osb_step_begin = the iteration-start
+ * BCs (+ rk_sbli save); osb_stage(s) = constituent relations, spatial kernels, RK update and the rank-local
+ * BCs of stage s.  Between stages the caller exchanges halos with osb_halo_push. */
+int osb_step_begin(osb_ctx *ctx);
+int osb_stage(osb_ctx *ctx, int stage);
+
+/* Same as osb_step, timed on the device with CUDA events on the context's stream (includes a sync). */
+int osb_step_timed(osb_ctx *ctx, int nsteps, double *elapsed_ms);
+/* Device-side stopwatch on the context's stream (CUDA events): start records an event, stop records a second
+ * one, synchronises on it and returns the elapsed device time; host-driven gaps between launches are included. */
+int osb_timer_start(osb_ctx *ctx);
+int osb_timer_stop(osb_ctx *ctx, double *elapsed_ms);
+/* End-to-end: copy the conserved arrays from host (pinned or pageable, reference layout), advance
+ * nsteps, copy them back.  q_in/q_out hold ndim+2 pointers.  elapsed_ms covers H2D + steps + D2H. */
+int osb_advance_host(osb_ctx *ctx, const double *const *q_in, double *const *q_out, int nsteps, double *elapsed_ms);
+
+/* Instrumentation: number of kernels launched by this context so far; per-family device time of
+ * one profiled step (events around each launch).  Families: see OSB_FAM_*. */
+enum { OSB_FAM_PRIM = 0, OSB_FAM_FLUX = 1, OSB_FAM_CENTRAL = 2, OSB_FAM_VISCOUS = 3, OSB_FAM_RK = 4, OSB_FAM_BC = 5, OSB_NFAM = 6 };
+int osb_launch_count(const osb_ctx *ctx, long long *count);
+int osb_profile_step(osb_ctx *ctx, double *family_ms /* [OSB_NFAM] */, long long *family_launches /* [OSB_NFAM] */);
+
+/* Multi-GPU (slab decomposition along the slowest axis): direct peer access to a neighbour's
+ * arrays through CUDA IPC.  See INTEGRATION.md. */
+int osb_ipc_export(osb_ctx *ctx, void *handles /* nq * 64 bytes */, int *nbytes);
+int osb_ipc_import(osb_ctx *ctx, int side /* 0 = low neighbour, 1 = high neighbour */, const void *handles, int nbytes);
+/* push this rank's boundary planes of q into the neighbours' halo planes (peer stores over NVLink) */
+int osb_halo_push(osb_ctx *ctx);
+
+/* FP64 pipe micro-benchmark (dependent-free DFMA chains); used by bench.py for the roofline peak. */
+int osb_measure_fp64_peak(int device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

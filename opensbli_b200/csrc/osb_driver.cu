@@ -1,0 +1,640 @@
+// osb_driver.cu -- context, plan parser, launch orchestration and the C ABI (include/osbli_b200.h).
+//
+// The step order reproduces TraditionalAlgorithmRK.generate_solution
+// (opensbli/code_generation/algorithm/algorithm.py:440-474):
+//   per iteration: BC kernels/exchanges (dir0 side0, dir0 side1, dir1 side0, ...) ; [rk_sbli: save]
+//   per stage:     constituent relations ; spatial kernels ; RK update ; BC kernels/exchanges
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+#include "../../include/osbli_b200.h"
+#include "osb_kernels.cuh"
+
+using namespace osb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum ConvKind { CONV_CENTRAL = 0, CONV_WENO = 1, CONV_TENO = 2 };
+enum RkKind { RK_SBLI = 0, RK_LS = 1 };
+enum BcKind { BC_PERIODIC = 0, BC_DIRICHLET = 1, BC_EXCHANGE = 2 /* neighbour rank owns the halo */ };
+
+struct BcSpec {
+  int kind = BC_PERIODIC;
+  double q[5] = {0, 0, 0, 0, 0};
+};
+
+struct Plan {
+  int nd = 0;
+  int np[3] = {1, 1, 1};
+  double delta[3] = {1, 1, 1};
+  int conv = CONV_TENO, order = 5;
+  bool weno_z = false;
+  int averaging = AVG_ROE;
+  bool viscous = false;
+  int rk = RK_LS;
+  std::vector<double> rk_a, rk_b;
+  std::map<std::string, double> consts;
+  BcSpec bc[3][2];
+};
+
+struct Field {
+  std::string name;
+  double *dev = nullptr;
+};
+
+}  // namespace
+
+struct osb_ctx {
+  Plan plan;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  GridDev grid{};
+  FieldPtrs fp{};
+  PhysConst pc{};
+  SchemeParams sp{};
+  std::vector<Field> fields;
+  std::string error;
+  long long launches = 0;
+  // profiling
+  bool profiling = false;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
+  // peers (slab decomposition)
+  cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+  double *peer_q[2][5] = {{nullptr}};
+  bool peer_open[2] = {false, false};
+};
+
+namespace {
+
+#define OSB_CUDA(ctx, call)                                                                 \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      (ctx)->error = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+      return 1;                                                                             \
+    }                                                                                       \
+  } while (0)
+
+int fail(osb_ctx *ctx, const std::string &msg) {
+  ctx->error = msg;
+  return 1;
+}
+
+bool parse_plan(const std::string &text, Plan &P, std::string &err) {
+  std::istringstream in(text);
+  std::string line;
+  bool header = false;
+  while (std::getline(in, line)) {
+    std::istringstream ls(line);
+    std::string key;
+    if (!(ls >> key) || key[0] == '#') continue;
+    if (key == "osbli_plan") { int v; ls >> v; if (v != 1) { err = "unsupported plan version"; return false; } header = true; }
+    else if (key == "ndim") ls >> P.nd;
+    else if (key == "np") { for (int d = 0; d < P.nd; d++) ls >> P.np[d]; }
+    else if (key == "delta") { for (int d = 0; d < P.nd; d++) ls >> P.delta[d]; }
+    else if (key == "conv") { std::string v; ls >> v; P.conv = v == "central" ? CONV_CENTRAL : v == "weno" ? CONV_WENO : v == "teno" ? CONV_TENO : -1; if (P.conv < 0) { err = "unknown conv scheme " + v; return false; } }
+    else if (key == "order") ls >> P.order;
+    else if (key == "weno_formulation") { std::string v; ls >> v; P.weno_z = (v == "Z"); }
+    else if (key == "averaging") { std::string v; ls >> v; P.averaging = v == "roe" ? AVG_ROE : AVG_SIMPLE; }
+    else if (key == "viscous") { int v; ls >> v; P.viscous = v != 0; }
+    else if (key == "rk") { std::string v; ls >> v; P.rk = v == "sbli" ? RK_SBLI : RK_LS; }
+    else if (key == "rk_a") { double v; while (ls >> v) P.rk_a.push_back(v); }
+    else if (key == "rk_b") { double v; while (ls >> v) P.rk_b.push_back(v); }
+    else if (key == "const") { std::string n; double v; ls >> n >> v; P.consts[n] = v; }
+    else if (key == "bc") {
+      int d, s; std::string kind; ls >> d >> s >> kind;
+      if (d < 0 || d > 2 || s < 0 || s > 1) { err = "bad bc line: " + line; return false; }
+      if (kind == "periodic") P.bc[d][s].kind = BC_PERIODIC;
+      else if (kind == "exchange") P.bc[d][s].kind = BC_EXCHANGE;
+      else if (kind == "dirichlet") { P.bc[d][s].kind = BC_DIRICHLET; for (int m = 0; m < P.nd + 2; m++) ls >> P.bc[d][s].q[m]; }
+      else { err = "unsupported boundary condition '" + kind + "'"; return false; }
+    } else { err = "unknown plan key '" + key + "'"; return false; }
+    if (ls.fail() && !ls.eof()) { err = "malformed plan line: " + line; return false; }
+  }
+  if (!header) { err = "missing 'osbli_plan 1' header"; return false; }
+  if (P.nd < 1 || P.nd > 3) { err = "ndim must be 1, 2 or 3"; return false; }
+  for (int d = 0; d < P.nd; d++) if (P.np[d] < 6) { err = "np must be >= 6 in every direction"; return false; }
+  if (P.rk_a.empty() || P.rk_a.size() != P.rk_b.size()) { err = "rk_a / rk_b missing or of different length"; return false; }
+  if (P.conv == CONV_CENTRAL && P.order != 4) { err = "central scheme: only order 4 is implemented"; return false; }
+  if (P.conv == CONV_WENO && P.order != 5) { err = "WENO: only order 5 (k=3) is implemented"; return false; }
+  if (P.conv == CONV_TENO && P.order != 5 && P.order != 6) { err = "TENO: only orders 5 and 6 are implemented"; return false; }
+  for (const char *k : {"gama", "dt"}) if (!P.consts.count(k)) { err = std::string("missing constant ") + k; return false; }
+  if (P.viscous) for (const char *k : {"Re", "Pr", "Minf"}) if (!P.consts.count(k)) { err = std::string("missing constant ") + k; return false; }
+  return true;
+}
+
+void scheme_halos(const Plan &P, int &hm, int &hp) {
+  if (P.conv == CONV_CENTRAL) { hm = 2; hp = 2; } else { hm = 3; hp = 4; }
+}
+
+void refresh_constants(osb_ctx *c) {
+  const Plan &P = c->plan;
+  auto get = [&](const char *k, double d) { auto it = P.consts.find(k); return it == P.consts.end() ? d : it->second; };
+  c->pc.gama = get("gama", 1.4); c->pc.Minf = get("Minf", 1.0); c->pc.Re = get("Re", 1.0); c->pc.Pr = get("Pr", 1.0);
+  c->pc.dt = get("dt", 0.0);
+  for (int d = 0; d < 3; d++) { c->pc.inv[d] = 1.0 / P.delta[d]; c->pc.inv2[d] = pow(P.delta[d], -2); }
+  c->sp.eps = get("eps", 1e-16); c->sp.teno_ct = get("TENO_CT", 1e-6);
+}
+
+Field *find_field(osb_ctx *c, const char *name) {
+  std::string n(name);
+  if (n.size() > 3 && n.compare(n.size() - 3, 3, "_B0") == 0) n.resize(n.size() - 3);
+  for (auto &f : c->fields) if (f.name == n) return &f;
+  return nullptr;
+}
+
+// ---- launch helpers ----------------------------------------------------------------------------
+struct Launcher {
+  osb_ctx *c;
+  int fam;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  Launcher(osb_ctx *ctx, int family) : c(ctx), fam(family) {
+    if (c->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream); }
+  }
+  ~Launcher() {
+    c->launches++;
+    if (c->profiling) { cudaEventRecord(e1, c->stream); c->prof_events.push_back({fam, {e0, e1}}); }
+  }
+};
+
+dim3 grid3(int n0, int n1, int n2, dim3 b) { return dim3((n0 + b.x - 1) / b.x, (n1 + b.y - 1) / b.y, (n2 + b.z - 1) / b.z); }
+
+template <int ND>
+void launch_prim(osb_ctx *c) {
+  int hm, hp; scheme_halos(c->plan, hm, hp);
+  int lo[3] = {0, 0, 0}, n[3] = {1, 1, 1};
+  for (int d = 0; d < ND; d++) { lo[d] = -hm; n[d] = c->grid.np[d] + hm + hp; }
+  dim3 b(128, 2, 1);
+  Launcher L(c, OSB_FAM_PRIM);
+  k_prim<ND><<<grid3(n[0], n[1], n[2], b), b, 0, c->stream>>>(c->grid, c->fp, c->pc, lo[0], lo[1], lo[2], n[0], n[1], n[2]);
+}
+
+template <int ND, int RECON, int AVG>
+void launch_flux(osb_ctx *c) {
+  const GridDev &g = c->grid;
+  {
+    const long long E = (long long)(g.np[0] + 1) * g.np[1] * g.np[2];
+    const long long nb = (E - 1 + FLUX_BT - 2) / (FLUX_BT - 1);
+    Launcher L(c, OSB_FAM_FLUX);
+    k_flux_x<ND, RECON, AVG, false><<<(unsigned)nb, FLUX_BT, 0, c->stream>>>(g, c->fp, c->pc, c->sp);
+  }
+  if (ND >= 2) {
+    const long long ER = (long long)(g.np[1] + 1) * (ND > 2 ? g.np[2] : 1);
+    dim3 b(32, FLUX_TY, 1), gr((unsigned)((ER - 1 + FLUX_RB - 2) / (FLUX_RB - 1)), (g.np[0] + 31) / 32, 1);
+    Launcher L(c, OSB_FAM_FLUX);
+    k_flux_yz<(ND >= 2 ? ND : 2), 1, RECON, AVG, true><<<gr, b, 0, c->stream>>>(g, c->fp, c->pc, c->sp);
+  }
+  if (ND >= 3) {
+    const long long ER = (long long)(g.np[2] + 1) * g.np[1];
+    dim3 b(32, FLUX_TY, 1), gr((unsigned)((ER - 1 + FLUX_RB - 2) / (FLUX_RB - 1)), (g.np[0] + 31) / 32, 1);
+    Launcher L(c, OSB_FAM_FLUX);
+    k_flux_yz<3, 2, RECON, AVG, true><<<gr, b, 0, c->stream>>>(g, c->fp, c->pc, c->sp);
+  }
+}
+
+template <int ND>
+void launch_flux_scheme(osb_ctx *c) {
+  const Plan &P = c->plan;
+  const bool roe = P.averaging == AVG_ROE;
+  if (P.conv == CONV_TENO && P.order == 5) { roe ? launch_flux<ND, RECON_TENO5, AVG_ROE>(c) : launch_flux<ND, RECON_TENO5, AVG_SIMPLE>(c); }
+  else if (P.conv == CONV_TENO) { roe ? launch_flux<ND, RECON_TENO6, AVG_ROE>(c) : launch_flux<ND, RECON_TENO6, AVG_SIMPLE>(c); }
+  else if (P.weno_z) { roe ? launch_flux<ND, RECON_WENO5_Z, AVG_ROE>(c) : launch_flux<ND, RECON_WENO5_Z, AVG_SIMPLE>(c); }
+  else { roe ? launch_flux<ND, RECON_WENO5_JS, AVG_ROE>(c) : launch_flux<ND, RECON_WENO5_JS, AVG_SIMPLE>(c); }
+}
+
+template <int ND>
+void launch_residual(osb_ctx *c) {
+  const GridDev &g = c->grid;
+  launch_prim<ND>(c);
+  if (c->plan.conv == CONV_CENTRAL) {
+    dim3 b(64, 2, 2);
+    Launcher L(c, OSB_FAM_CENTRAL);
+    k_central<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc);
+  } else {
+    launch_flux_scheme<ND>(c);
+  }
+  if (c->plan.viscous) {
+    dim3 b(64, 2, 2);
+    Launcher L(c, OSB_FAM_VISCOUS);
+    k_viscous<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc);
+  }
+}
+
+void box_launch_cfg(const Box &b, int nv, unsigned &blocks) {
+  const long long cnt = (long long)b.n[0] * b.n[1] * b.n[2] * nv;
+  long long nb = (cnt + 255) / 256;
+  if (nb > 148 * 16) nb = 148 * 16;
+  if (nb < 1) nb = 1;
+  blocks = (unsigned)nb;
+}
+
+void launch_bcs(osb_ctx *c) {
+  const Plan &P = c->plan;
+  const GridDev &g = c->grid;
+  const int nv = P.nd + 2;
+  int hm, hp; scheme_halos(P, hm, hp);
+  for (int d = 0; d < P.nd; d++)
+    for (int s = 0; s < 2; s++) {
+      const BcSpec &b = P.bc[d][s];
+      if (b.kind == BC_EXCHANGE) continue;   // filled by the neighbour rank (osb_halo_push)
+      Box full;
+      for (int e = 0; e < 3; e++) { full.lo[e] = e < P.nd ? -hm : 0; full.n[e] = e < P.nd ? g.np[e] + hm + hp : 1; }
+      unsigned blocks;
+      if (b.kind == BC_PERIODIC) {
+        // periodic.py:42-56: side 0 copies [0,hm) -> [np,np+hm); side 1 copies [np-hm, np-hm+hp) -> [-hm, -hm+hp)
+        Box src = full, dst = full;
+        if (s == 0) { src.lo[d] = 0; dst.lo[d] = g.np[d]; src.n[d] = dst.n[d] = hm; }
+        else { src.lo[d] = g.np[d] - hm; dst.lo[d] = -hm; src.n[d] = dst.n[d] = hp; }
+        box_launch_cfg(src, nv, blocks);
+        Launcher L(c, OSB_FAM_BC);
+        k_copy_box<<<blocks, 256, 0, c->stream>>>(g, c->fp, nv, src, dst);
+      } else if (b.kind == BC_DIRICHLET) {
+        // dirichlet.py:28-41: boundary plane + halo planes of that side
+        Box dst = full;
+        if (s == 0) { dst.lo[d] = -hm; dst.n[d] = hm + 1; } else { dst.lo[d] = g.np[d] - 1; dst.n[d] = hp + 1; }
+        DirichletState st;
+        for (int m = 0; m < 5; m++) st.q[m] = b.q[m];
+        box_launch_cfg(dst, nv, blocks);
+        Launcher L(c, OSB_FAM_BC);
+        k_fill_box<<<blocks, 256, 0, c->stream>>>(g, c->fp, nv, dst, st);
+      }
+    }
+}
+
+template <int ND>
+void launch_rk(osb_ctx *c, int stage) {
+  const GridDev &g = c->grid;
+  dim3 b(128, 2, 1);
+  Launcher L(c, OSB_FAM_RK);
+  if (c->plan.rk == RK_LS)
+    k_rk_ls<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc.dt, c->plan.rk_a[stage], c->plan.rk_b[stage]);
+  else
+    k_rk_sbli<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc.dt, c->plan.rk_a[stage], c->plan.rk_b[stage]);
+}
+
+template <int ND>
+void launch_save(osb_ctx *c) {
+  const GridDev &g = c->grid;
+  dim3 b(128, 2, 1);
+  Launcher L(c, OSB_FAM_RK);
+  k_rk_save<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp);
+}
+
+template <int ND>
+int step_nd(osb_ctx *c, int nsteps) {
+  const int nstages = (int)c->plan.rk_a.size();
+  for (int it = 0; it < nsteps; it++) {
+    launch_bcs(c);
+    if (c->plan.rk == RK_SBLI) launch_save<ND>(c);
+    for (int s = 0; s < nstages; s++) {
+      launch_residual<ND>(c);
+      launch_rk<ND>(c, s);
+      launch_bcs(c);
+    }
+  }
+  OSB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+template <int ND>
+int stage_nd(osb_ctx *c, int s) {
+  if (s < 0) { launch_bcs(c); if (c->plan.rk == RK_SBLI) launch_save<ND>(c); }
+  else { launch_residual<ND>(c); launch_rk<ND>(c, s); launch_bcs(c); }
+  OSB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+int do_stage(osb_ctx *c, int s) {
+  if (s >= (int)c->plan.rk_a.size()) return fail(c, "stage index out of range");
+  switch (c->plan.nd) {
+    case 1: return stage_nd<1>(c, s);
+    case 2: return stage_nd<2>(c, s);
+    default: return stage_nd<3>(c, s);
+  }
+}
+
+int do_step(osb_ctx *c, int nsteps) {
+  switch (c->plan.nd) {
+    case 1: return step_nd<1>(c, nsteps);
+    case 2: return step_nd<2>(c, nsteps);
+    default: return step_nd<3>(c, nsteps);
+  }
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char *osb_last_error(const osb_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int osb_create(const char *plan_text, int device, osb_ctx **out) {
+  if (!plan_text || !out) { g_create_error = "null argument"; return 1; }
+  *out = nullptr;
+  osb_ctx *c = new osb_ctx();
+  std::string err;
+  if (!parse_plan(plan_text, c->plan, err)) { g_create_error = "plan: " + err; delete c; return 1; }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(ce) + "): the B200 back end has no CPU fallback";
+    delete c; return 2;
+  }
+  if (device >= 0) { ce = cudaSetDevice(device); if (ce != cudaSuccess) { g_create_error = cudaGetErrorString(ce); delete c; return 2; } }
+  cudaGetDevice(&c->device);
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; delete c; return 2; }
+  const Plan &P = c->plan;
+  GridDev &g = c->grid;
+  g.nd = P.nd; g.h = 5;
+  long long n = 1; g.off = 0;
+  for (int d = 0; d < 3; d++) {
+    g.np[d] = d < P.nd ? P.np[d] : 1;
+    g.pd[d] = d < P.nd ? P.np[d] + 2 * g.h : 1;
+    g.s[d] = n;
+    if (d < P.nd) g.off += g.h * n;
+    n *= g.pd[d];
+  }
+  g.n = n;
+  refresh_constants(c);
+  // fields (names = reference dataset names without the _B0 suffix)
+  const int nv = P.nd + 2;
+  std::vector<std::string> qn = {"rho"};
+  for (int d = 0; d < P.nd; d++) qn.push_back("rhou" + std::to_string(d));
+  qn.push_back("rhoE");
+  auto add = [&](const std::string &name, double **slot) -> bool {
+    Field f; f.name = name;
+    if (cudaMalloc(&f.dev, sizeof(double) * g.n) != cudaSuccess) return false;
+    cudaMemsetAsync(f.dev, 0, sizeof(double) * g.n, c->stream);   // OPS semantics: zero-initialised dats
+    *slot = f.dev;
+    c->fields.push_back(f);
+    return true;
+  };
+  bool ok = true;
+  for (int m = 0; m < nv && ok; m++) ok = add(qn[m], &c->fp.q[m]);
+  for (int d = 0; d < P.nd && ok; d++) ok = add("u" + std::to_string(d), &c->fp.u[d]);
+  ok = ok && add("p", &c->fp.p) && add("a", &c->fp.a) && add("T", &c->fp.T);
+  for (int m = 0; m < nv && ok; m++) ok = add("Residual" + std::to_string(m), &c->fp.R[m]);
+  for (int m = 0; m < nv && ok; m++) ok = add(P.rk == RK_LS ? "tempRK_" + qn[m] : qn[m] + "_RKold", &c->fp.rk[m]);
+  if (!ok) { g_create_error = "cudaMalloc failed (out of device memory)"; osb_destroy(c); return 3; }
+  cudaStreamSynchronize(c->stream);
+  *out = c;
+  return 0;
+}
+
+int osb_destroy(osb_ctx *c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  for (int s = 0; s < 2; s++)
+    if (c->peer_open[s]) for (int m = 0; m < 5; m++) if (c->peer_q[s][m]) cudaIpcCloseMemHandle(c->peer_q[s][m]);
+  for (auto &f : c->fields) cudaFree(f.dev);
+  if (c->timer0) { cudaEventDestroy(c->timer0); cudaEventDestroy(c->timer1); }
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int osb_set_const_f64(osb_ctx *c, const char *name, double v) {
+  if (!c || !name) return 1;
+  c->plan.consts[name] = v;
+  refresh_constants(c);
+  return 0;
+}
+int osb_get_const_f64(const osb_ctx *c, const char *name, double *v) {
+  if (!c || !name || !v) return 1;
+  auto it = c->plan.consts.find(name);
+  if (it == c->plan.consts.end()) return 1;
+  *v = it->second;
+  return 0;
+}
+
+int osb_num_fields(const osb_ctx *c) { return c ? (int)c->fields.size() : 0; }
+const char *osb_field_name(const osb_ctx *c, int i) { return (c && i >= 0 && i < (int)c->fields.size()) ? c->fields[i].name.c_str() : nullptr; }
+
+int osb_field_info(const osb_ctx *c, const char *name, int *dims, int *halo_m, int *halo_p) {
+  if (!c || !name) return 1;
+  if (!find_field(const_cast<osb_ctx *>(c), name)) return fail(const_cast<osb_ctx *>(c), std::string("unknown field ") + name);
+  for (int d = 0; d < 3; d++) {
+    if (dims) dims[d] = c->grid.np[d];
+    if (halo_m) halo_m[d] = d < c->grid.nd ? -c->grid.h : 0;
+    if (halo_p) halo_p[d] = d < c->grid.nd ? c->grid.h : 0;
+  }
+  return 0;
+}
+
+int osb_upload(osb_ctx *c, const char *name, const double *host) {
+  if (!c || !name || !host) return 1;
+  Field *f = find_field(c, name);
+  if (!f) return fail(c, std::string("unknown field ") + name);
+  OSB_CUDA(c, cudaMemcpyAsync(f->dev, host, sizeof(double) * c->grid.n, cudaMemcpyHostToDevice, c->stream));
+  OSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int osb_download(osb_ctx *c, const char *name, double *host) {
+  if (!c || !name || !host) return 1;
+  Field *f = find_field(c, name);
+  if (!f) return fail(c, std::string("unknown field ") + name);
+  OSB_CUDA(c, cudaMemcpyAsync(host, f->dev, sizeof(double) * c->grid.n, cudaMemcpyDeviceToHost, c->stream));
+  OSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int osb_device_ptr(osb_ctx *c, const char *name, double **p) {
+  if (!c || !name || !p) return 1;
+  Field *f = find_field(c, name);
+  if (!f) return fail(c, std::string("unknown field ") + name);
+  *p = f->dev;
+  return 0;
+}
+
+int osb_step(osb_ctx *c, int nsteps) {
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  return do_step(c, nsteps);
+}
+int osb_step_begin(osb_ctx *c) {
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  return do_stage(c, -1);
+}
+int osb_stage(osb_ctx *c, int stage) {
+  if (!c || stage < 0) return 1;
+  cudaSetDevice(c->device);
+  return do_stage(c, stage);
+}
+int osb_sync(osb_ctx *c) {
+  if (!c) return 1;
+  OSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int osb_apply_bcs(osb_ctx *c) {
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  launch_bcs(c);
+  OSB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+int osb_residual(osb_ctx *c) {
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  switch (c->plan.nd) { case 1: launch_residual<1>(c); break; case 2: launch_residual<2>(c); break; default: launch_residual<3>(c); }
+  OSB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int osb_step_timed(osb_ctx *c, int nsteps, double *ms) {
+  if (!c || !ms) return 1;
+  cudaSetDevice(c->device);
+  cudaEvent_t e0, e1;
+  OSB_CUDA(c, cudaEventCreate(&e0)); OSB_CUDA(c, cudaEventCreate(&e1));
+  OSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  OSB_CUDA(c, cudaEventRecord(e0, c->stream));
+  int rc = do_step(c, nsteps);
+  OSB_CUDA(c, cudaEventRecord(e1, c->stream));
+  OSB_CUDA(c, cudaEventSynchronize(e1));
+  float t = 0; cudaEventElapsedTime(&t, e0, e1);
+  *ms = t;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return rc;
+}
+
+int osb_timer_start(osb_ctx *c) {
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  if (!c->timer0) { OSB_CUDA(c, cudaEventCreate(&c->timer0)); OSB_CUDA(c, cudaEventCreate(&c->timer1)); }
+  OSB_CUDA(c, cudaEventRecord(c->timer0, c->stream));
+  return 0;
+}
+int osb_timer_stop(osb_ctx *c, double *ms) {
+  if (!c || !ms || !c->timer0) return 1;
+  cudaSetDevice(c->device);
+  OSB_CUDA(c, cudaEventRecord(c->timer1, c->stream));
+  OSB_CUDA(c, cudaEventSynchronize(c->timer1));
+  float t = 0; OSB_CUDA(c, cudaEventElapsedTime(&t, c->timer0, c->timer1));
+  *ms = t;
+  return 0;
+}
+
+int osb_advance_host(osb_ctx *c, const double *const *q_in, double *const *q_out, int nsteps, double *ms) {
+  if (!c || !q_in || !q_out) return 1;
+  cudaSetDevice(c->device);
+  const int nv = c->plan.nd + 2;
+  const size_t bytes = sizeof(double) * c->grid.n;
+  cudaEvent_t e0, e1;
+  OSB_CUDA(c, cudaEventCreate(&e0)); OSB_CUDA(c, cudaEventCreate(&e1));
+  OSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  OSB_CUDA(c, cudaEventRecord(e0, c->stream));
+  for (int m = 0; m < nv; m++) OSB_CUDA(c, cudaMemcpyAsync(c->fp.q[m], q_in[m], bytes, cudaMemcpyHostToDevice, c->stream));
+  int rc = do_step(c, nsteps);
+  for (int m = 0; m < nv; m++) OSB_CUDA(c, cudaMemcpyAsync(q_out[m], c->fp.q[m], bytes, cudaMemcpyDeviceToHost, c->stream));
+  OSB_CUDA(c, cudaEventRecord(e1, c->stream));
+  OSB_CUDA(c, cudaEventSynchronize(e1));
+  float t = 0; cudaEventElapsedTime(&t, e0, e1);
+  if (ms) *ms = t;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return rc;
+}
+
+int osb_launch_count(const osb_ctx *c, long long *n) { if (!c || !n) return 1; *n = c->launches; return 0; }
+
+int osb_profile_step(osb_ctx *c, double *fam_ms, long long *fam_n) {
+  if (!c || !fam_ms) return 1;
+  cudaSetDevice(c->device);
+  OSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->profiling = true; c->prof_events.clear();
+  int rc = do_step(c, 1);
+  c->profiling = false;
+  OSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < OSB_NFAM; i++) { fam_ms[i] = 0.0; if (fam_n) fam_n[i] = 0; }
+  for (auto &pe : c->prof_events) {
+    float t = 0; cudaEventElapsedTime(&t, pe.second.first, pe.second.second);
+    fam_ms[pe.first] += t; if (fam_n) fam_n[pe.first]++;
+    cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second);
+  }
+  c->prof_events.clear();
+  return rc;
+}
+
+// ---- slab decomposition: CUDA IPC peer access -----------------------------------------------------
+int osb_ipc_export(osb_ctx *c, void *handles, int *nbytes) {
+  if (!c || !handles || !nbytes) return 1;
+  cudaSetDevice(c->device);
+  const int nv = c->plan.nd + 2;
+  for (int m = 0; m < nv; m++) {
+    cudaIpcMemHandle_t h;
+    OSB_CUDA(c, cudaIpcGetMemHandle(&h, c->fp.q[m]));
+    memcpy((char *)handles + m * sizeof(h), &h, sizeof(h));
+  }
+  *nbytes = nv * (int)sizeof(cudaIpcMemHandle_t);
+  return 0;
+}
+int osb_ipc_import(osb_ctx *c, int side, const void *handles, int nbytes) {
+  if (!c || !handles || side < 0 || side > 1) return 1;
+  cudaSetDevice(c->device);
+  const int nv = c->plan.nd + 2;
+  if (nbytes != nv * (int)sizeof(cudaIpcMemHandle_t)) return fail(c, "osb_ipc_import: wrong handle size");
+  for (int m = 0; m < nv; m++) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + m * sizeof(h), sizeof(h));
+    void *p = nullptr;
+    OSB_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_q[side][m] = (double *)p;
+  }
+  c->peer_open[side] = true;
+  return 0;
+}
+int osb_halo_push(osb_ctx *c) {
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  const Plan &P = c->plan;
+  const GridDev &g = c->grid;
+  const int d = P.nd - 1;   // slabs along the slowest axis
+  const int nv = P.nd + 2;
+  int hm, hp; scheme_halos(P, hm, hp);
+  // planes along the slowest axis are contiguous: [plane index] * s[d], each s[d] doubles
+  const size_t plane = sizeof(double) * g.s[d];
+  for (int m = 0; m < nv; m++) {
+    if (P.bc[d][1].kind == BC_EXCHANGE && c->peer_open[1]) {
+      // my top hm planes [np-hm, np) -> high neighbour's low halo [-hm, 0)
+      OSB_CUDA(c, cudaMemcpyAsync(c->peer_q[1][m] + (g.h - hm) * g.s[d], c->fp.q[m] + (g.h + g.np[d] - hm) * g.s[d], plane * hm, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (P.bc[d][0].kind == BC_EXCHANGE && c->peer_open[0]) {
+      // my bottom hp planes [0, hp) -> low neighbour's high halo [np, np+hp); neighbour has the same np
+      OSB_CUDA(c, cudaMemcpyAsync(c->peer_q[0][m] + (g.h + g.np[d]) * g.s[d], c->fp.q[m] + g.h * g.s[d], plane * hp, cudaMemcpyDeviceToDevice, c->stream));
+    }
+  }
+  c->launches += 0;
+  return 0;
+}
+
+int osb_measure_fp64_peak(int device, double *tflops) {
+  if (!tflops) return 1;
+  if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return 2;
+  cudaDeviceProp prop; int dev = 0; cudaGetDevice(&dev);
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 2;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+  double *out = nullptr;
+  if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return 3;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0);
+    k_dfma_peak<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *tflops = best;
+  return cudaGetLastError() == cudaSuccess ? 0 : 4;
+}
+
+}  // extern "C"

@@ -1,0 +1,353 @@
+// osb_kernels.cuh -- sm_100a kernels of the per-timestep solver loop (fp64).
+//
+// Kernel families (OSB_FAM_* in include/osbli_b200.h) and the reference loops they replace
+// (SURVEY.md section 2b / appendix A):
+//   k_prim      CRu_i, CRp, CRa, CRT                       (constituent relations, one fused pass)
+//   k_flux      LLF{Weno,Teno}_reconstruction_d + Residual (flux sweep + flux difference, fused)
+//   k_central   Convective terms group / CD / residual     (4th-order skew-symmetric, fused)
+//   k_viscous   Derivative evaluation CD + Viscous terms   (fused, mixed derivatives on the fly)
+//   k_rk_*      Save equations / Sub stage / Temporal solution advancement
+//   k_periodic  exchange{n}_block0 ; k_dirichlet  Dirichlet boundary dir d side s
+#pragma once
+#include "osb_math.cuh"
+
+namespace osb {
+
+struct GridDev {
+  int nd;
+  int np[3];          // interior points
+  int pd[3];          // padded dims (np + 2h in active dims)
+  long long s[3];     // strides
+  long long off;      // linear index of point (0,0,0)
+  int h;              // storage halo
+  long long n;        // padded size
+};
+
+struct FieldPtrs {
+  double *q[5];       // rho, rhou0.., rhoE
+  double *u[3];       // velocities
+  double *p, *a, *T;
+  double *R[5];       // Residual
+  double *rk[5];      // RK register (tempRK_* or *_RKold)
+};
+
+struct PhysConst {
+  double gama, Minf, Re, Pr, dt;
+  double inv[3], inv2[3];   // 1/Delta_d, 1/Delta_d^2
+};
+
+// -------------------------------------------------------------------------------------------------
+// constituent relations over [lo, hi) (grid + scheme halos)
+// -------------------------------------------------------------------------------------------------
+template <int ND>
+__global__ void __launch_bounds__(256) k_prim(GridDev g, FieldPtrs f, PhysConst c, int lo0, int lo1, int lo2, int n0, int n1, int n2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= n0 || j >= n1 || k >= n2) return;
+  const long long x = g.off + (lo0 + i) + (ND > 1 ? (lo1 + j) * g.s[1] : 0) + (ND > 2 ? (lo2 + k) * g.s[2] : 0);
+  const double rho = f.q[0][x];
+  double ke = 0.0;
+#pragma unroll
+  for (int d = 0; d < ND; d++) {
+    const double u = f.q[1 + d][x] / rho;
+    f.u[d][x] = u;
+    ke += 0.5 * rho * u * u;
+  }
+  const double p = (c.gama - 1.0) * (f.q[ND + 1][x] - ke);
+  f.p[x] = p;
+  f.a[x] = sqrt(c.gama * p / rho);
+  f.T[x] = c.Minf * c.Minf * c.gama * p / rho;
+}
+
+// -------------------------------------------------------------------------------------------------
+// characteristic flux sweep, direction DIR, fused with the flux difference.
+// Interfaces of one pencil are numbered e = 0..np_DIR (interface e sits between points e-1 and e);
+// pencils are concatenated, so neighbours e-1, e are adjacent unless e % (np_DIR+1) == 0.
+// A block evaluates BT consecutive interfaces (x-sweep) or 32 lanes x RB consecutive interface rows
+// (y/z sweeps), parks the fluxes in shared memory and differences them; consecutive blocks overlap by one.
+// -------------------------------------------------------------------------------------------------
+template <int ND>
+__device__ __forceinline__ void load_point(const FieldPtrs &f, long long x, Point<ND> &P) {
+  P.rho = __ldg(f.q[0] + x);
+#pragma unroll
+  for (int d = 0; d < ND; d++) { P.m[d] = __ldg(f.q[1 + d] + x); P.u[d] = __ldg(f.u[d] + x); }
+  P.E = __ldg(f.q[ND + 1] + x);
+  P.pr = __ldg(f.p + x);
+  P.a = __ldg(f.a + x);
+}
+
+constexpr int FLUX_BT = 256;   // x-sweep: interfaces per block
+constexpr int FLUX_RB = 32;    // y/z sweeps: interface rows per block
+constexpr int FLUX_TY = 8;     // y/z sweeps: thread rows
+
+template <int ND, int RECON, int AVG, bool ACCUM>
+__global__ void __launch_bounds__(FLUX_BT) k_flux_x(GridDev g, FieldPtrs f, PhysConst c, SchemeParams sp) {
+  constexpr int NV = ND + 2;
+  __shared__ double sF[NV][FLUX_BT];
+  const int t = threadIdx.x;
+  const long long NI = g.np[0] + 1;
+  const long long E = NI * g.np[1] * g.np[2];
+  const long long e = (long long)blockIdx.x * (FLUX_BT - 1) + t;
+  const bool valid = e < E;
+  long long x = 0;
+  int ie = 0;
+  if (valid) {
+    ie = (int)(e % NI);
+    const long long row = e / NI;
+    const int j = (int)(row % g.np[1]), k = (int)(row / g.np[1]);
+    x = g.off + (ie - 1) + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
+    Point<ND> pt[6];
+#pragma unroll
+    for (int p = 0; p < 6; p++) load_point<ND>(f, x + (p - 2), pt[p]);
+    double fl[NV];
+    interface_flux<ND, 0, RECON, AVG>(pt, c.gama, sp, fl);
+#pragma unroll
+    for (int m = 0; m < NV; m++) sF[m][t] = fl[m];
+  }
+  __syncthreads();
+  if (valid && t > 0 && ie != 0) {
+    // interface ie lies between points ie-1 and ie, interface ie-1 between ie-2 and ie-1: together they
+    // bound point ie-1, which is the left point x of this thread's interface.
+#pragma unroll
+    for (int m = 0; m < NV; m++) {
+      const double r = -c.inv[0] * (sF[m][t] - sF[m][t - 1]);
+      if (ACCUM) f.R[m][x] += r; else f.R[m][x] = r;
+    }
+  }
+}
+
+template <int ND, int DIR, int RECON, int AVG, bool ACCUM>
+__global__ void __launch_bounds__(32 * FLUX_TY) k_flux_yz(GridDev g, FieldPtrs f, PhysConst c, SchemeParams sp) {
+  constexpr int NV = ND + 2;
+  constexpr int OTH = (DIR == 1) ? 2 : 1;            // the other non-x direction
+  __shared__ double sF[FLUX_RB][NV][32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i = blockIdx.y * 32 + tx;
+  const long long NJ = g.np[DIR] + 1;
+  const long long nother = (ND > 2) ? g.np[OTH] : 1;
+  const long long ER = NJ * nother;
+  const long long r0 = (long long)blockIdx.x * (FLUX_RB - 1);
+  const bool xin = i < g.np[0];
+#pragma unroll 1
+  for (int it = 0; it < FLUX_RB / FLUX_TY; it++) {
+    const int r = ty + FLUX_TY * it;
+    const long long er = r0 + r;
+    if (xin && er < ER) {
+      const int je = (int)(er % NJ);
+      const int o = (int)(er / NJ);
+      const long long x = g.off + i + (long long)(je - 1) * g.s[DIR] + (ND > 2 ? o * g.s[OTH] : 0);
+      Point<ND> pt[6];
+#pragma unroll
+      for (int p = 0; p < 6; p++) load_point<ND>(f, x + (p - 2) * g.s[DIR], pt[p]);
+      double fl[NV];
+      interface_flux<ND, DIR, RECON, AVG>(pt, c.gama, sp, fl);
+#pragma unroll
+      for (int m = 0; m < NV; m++) sF[r][m][tx] = fl[m];
+    }
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int it = 0; it < FLUX_RB / FLUX_TY; it++) {
+    const int r = ty + FLUX_TY * it;
+    const long long er = r0 + r;
+    if (xin && r > 0 && er < ER) {
+      const int je = (int)(er % NJ);
+      if (je != 0) {
+        const int o = (int)(er / NJ);
+        const long long x = g.off + i + (long long)(je - 1) * g.s[DIR] + (ND > 2 ? o * g.s[OTH] : 0);
+#pragma unroll
+        for (int m = 0; m < NV; m++) {
+          const double rr = -c.inv[DIR] * (sF[r][m][tx] - sF[r - 1][m][tx]);
+          if (ACCUM) f.R[m][x] += rr; else f.R[m][x] = rr;
+        }
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Central(4) skew-symmetric convective residual (scheme.py:187-271, parsing.py:75-111); R = conv
+// -------------------------------------------------------------------------------------------------
+template <int ND>
+__global__ void __launch_bounds__(256) k_central(GridDev g, FieldPtrs f, PhysConst c) {
+  constexpr int NV = ND + 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z * blockDim.z + threadIdx.z;
+  if (i >= g.np[0] || j >= g.np[1] || k >= g.np[2]) return;
+  const long long x = g.off + i + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
+  double r[NV], q0[NV], u0[ND], div = 0.0;
+#pragma unroll
+  for (int m = 0; m < NV; m++) { r[m] = 0.0; q0[m] = f.q[m][x]; }
+#pragma unroll
+  for (int d = 0; d < ND; d++) u0[d] = f.u[d][x];
+#pragma unroll
+  for (int d = 0; d < ND; d++) {
+    const long long s = g.s[d];
+    const double um2 = __ldg(f.u[d] + x - 2 * s), um1 = __ldg(f.u[d] + x - s), up1 = __ldg(f.u[d] + x + s), up2 = __ldg(f.u[d] + x + 2 * s);
+    div += d1c(um2, um1, up1, up2, c.inv[d]);
+#pragma unroll
+    for (int m = 0; m < NV; m++) {
+      const double qm2 = __ldg(f.q[m] + x - 2 * s), qm1 = __ldg(f.q[m] + x - s), qp1 = __ldg(f.q[m] + x + s), qp2 = __ldg(f.q[m] + x + 2 * s);
+      // conservative part d(q_m u_d)/dx_d and advective part u_d dq_m/dx_d
+      r[m] += d1c(qm2 * um2, qm1 * um1, qp1 * up1, qp2 * up2, c.inv[d]) + u0[d] * d1c(qm2, qm1, qp1, qp2, c.inv[d]);
+    }
+    const double pm2 = __ldg(f.p + x - 2 * s), pm1 = __ldg(f.p + x - s), pp1 = __ldg(f.p + x + s), pp2 = __ldg(f.p + x + 2 * s);
+    // pressure gradient (momentum d) and pressure work (energy), carried with weight 2 to share the -1/2 below
+    r[1 + d] += 2.0 * d1c(pm2, pm1, pp1, pp2, c.inv[d]);
+    r[ND + 1] += 2.0 * d1c(pm2 * um2, pm1 * um1, pp1 * up1, pp2 * up2, c.inv[d]);
+  }
+#pragma unroll
+  for (int m = 0; m < NV; m++) f.R[m][x] = -0.5 * (r[m] + q0[m] * div);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Viscous terms, constant viscosity (StoreSome.py:71-161 / scheme.py:256-327); R += visc
+//   tau_ij = (1/Re)(du_i/dx_j + du_j/dx_i - 2/3 delta_ij div u) ; q_j = dT/dx_j /((g-1) Minf^2 Pr Re)
+// Mixed derivatives: derivative along the higher direction of the derivative along the lower one.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dev_d1(const double *a, long long x, long long s, double inv) {
+  return d1c(__ldg(a + x - 2 * s), __ldg(a + x - s), __ldg(a + x + s), __ldg(a + x + 2 * s), inv);
+}
+__device__ __forceinline__ double dev_d2(const double *a, long long x, long long s, double inv2) {
+  return d2c(__ldg(a + x - 2 * s), __ldg(a + x - s), __ldg(a + x), __ldg(a + x + s), __ldg(a + x + 2 * s), inv2);
+}
+// d/dx_out ( d a / dx_in )
+__device__ __forceinline__ double dev_dmix(const double *a, long long x, long long sin_, double invin, long long sout, double invout) {
+  return d1c(dev_d1(a, x - 2 * sout, sin_, invin), dev_d1(a, x - sout, sin_, invin),
+             dev_d1(a, x + sout, sin_, invin), dev_d1(a, x + 2 * sout, sin_, invin), invout);
+}
+
+template <int ND>
+__global__ void __launch_bounds__(256) k_viscous(GridDev g, FieldPtrs f, PhysConst c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z * blockDim.z + threadIdx.z;
+  if (i >= g.np[0] || j >= g.np[1] || k >= g.np[2]) return;
+  const long long x = g.off + i + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
+  const double iRe = 1.0 / c.Re;
+  const double kq = iRe * (1.0 / (c.gama - 1.0)) * (1.0 / (c.Minf * c.Minf)) * (1.0 / c.Pr);
+  double dv[ND][ND];   // dv[a][b] = d u_a / d x_b
+#pragma unroll
+  for (int a = 0; a < ND; a++)
+#pragma unroll
+    for (int b = 0; b < ND; b++) dv[a][b] = dev_d1(f.u[a], x, g.s[b], c.inv[b]);
+  double vis[ND], e = 0.0, div = 0.0;
+#pragma unroll
+  for (int a = 0; a < ND; a++) div += dv[a][a];
+#pragma unroll
+  for (int a = 0; a < ND; a++) {
+    double s = 0.0;
+#pragma unroll
+    for (int b = 0; b < ND; b++) {
+      if (b == a) s += (4.0 / 3.0) * dev_d2(f.u[a], x, g.s[a], c.inv2[a]);
+      else {
+        s += dev_d2(f.u[a], x, g.s[b], c.inv2[b]);
+        const int in = a < b ? a : b, out = a < b ? b : a;
+        s += (1.0 / 3.0) * dev_dmix(f.u[b], x, g.s[in], c.inv[in], g.s[out], c.inv[out]);
+      }
+    }
+    vis[a] = iRe * s;
+    f.R[1 + a][x] += vis[a];
+  }
+  double lapT = 0.0;
+#pragma unroll
+  for (int d = 0; d < ND; d++) lapT += dev_d2(f.T, x, g.s[d], c.inv2[d]);
+  e = kq * lapT;
+#pragma unroll
+  for (int a = 0; a < ND; a++) {
+#pragma unroll
+    for (int b = a + 1; b < ND; b++) { const double sab = dv[a][b] + dv[b][a]; e += iRe * sab * sab; }
+    e += iRe * (2.0 * dv[a][a] - (2.0 / 3.0) * div) * dv[a][a];
+    e += vis[a] * f.u[a][x];
+  }
+  f.R[ND + 1][x] += e;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Runge-Kutta updates (rk_sbli.py:102-133, rk_LS.py:139-166)
+// -------------------------------------------------------------------------------------------------
+template <int ND>
+__global__ void __launch_bounds__(256) k_rk_ls(GridDev g, FieldPtrs f, double dt, double A, double B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= g.np[0] || j >= g.np[1] || k >= g.np[2]) return;
+  const long long x = g.off + i + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
+#pragma unroll
+  for (int m = 0; m < ND + 2; m++) {
+    const double t = dt * f.R[m][x] + A * f.rk[m][x];
+    f.rk[m][x] = t;
+    f.q[m][x] = B * t + f.q[m][x];
+  }
+}
+template <int ND>
+__global__ void __launch_bounds__(256) k_rk_sbli(GridDev g, FieldPtrs f, double dt, double rkold, double rknew) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= g.np[0] || j >= g.np[1] || k >= g.np[2]) return;
+  const long long x = g.off + i + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
+#pragma unroll
+  for (int m = 0; m < ND + 2; m++) {
+    const double r = f.R[m][x], o = f.rk[m][x];
+    f.q[m][x] = dt * rknew * r + o;
+    f.rk[m][x] = dt * rkold * r + o;
+  }
+}
+template <int ND>
+__global__ void __launch_bounds__(256) k_rk_save(GridDev g, FieldPtrs f) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z;
+  if (i >= g.np[0] || j >= g.np[1] || k >= g.np[2]) return;
+  const long long x = g.off + i + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
+#pragma unroll
+  for (int m = 0; m < ND + 2; m++) f.rk[m][x] = f.q[m][x];
+}
+
+// -------------------------------------------------------------------------------------------------
+// Boundary conditions
+// -------------------------------------------------------------------------------------------------
+struct Box { int lo[3], n[3]; };   // start index and extent per dimension (inactive dims: lo 0, n 1)
+
+// periodic slab copy (periodic.py:42-56): dst box <- src box, same extents, nv arrays
+__global__ void __launch_bounds__(256) k_copy_box(GridDev g, FieldPtrs f, int nv, Box src, Box dst) {
+  const long long cnt = (long long)src.n[0] * src.n[1] * src.n[2];
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cnt * nv; e += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(e / cnt);
+    long long r = e % cnt;
+    const int i = (int)(r % src.n[0]); r /= src.n[0];
+    const int j = (int)(r % src.n[1]);
+    const int k = (int)(r / src.n[1]);
+    const long long xs = g.off + (src.lo[0] + i) + (src.lo[1] + j) * g.s[1] * (g.nd > 1) + (src.lo[2] + k) * g.s[2] * (g.nd > 2);
+    const long long xd = g.off + (dst.lo[0] + i) + (dst.lo[1] + j) * g.s[1] * (g.nd > 1) + (dst.lo[2] + k) * g.s[2] * (g.nd > 2);
+    f.q[m][xd] = f.q[m][xs];
+  }
+}
+struct DirichletState { double q[5]; };
+__global__ void __launch_bounds__(256) k_fill_box(GridDev g, FieldPtrs f, int nv, Box dst, DirichletState st) {
+  const long long cnt = (long long)dst.n[0] * dst.n[1] * dst.n[2];
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cnt * nv; e += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(e / cnt);
+    long long r = e % cnt;
+    const int i = (int)(r % dst.n[0]); r /= dst.n[0];
+    const int j = (int)(r % dst.n[1]);
+    const int k = (int)(r / dst.n[1]);
+    const long long xd = g.off + (dst.lo[0] + i) + (dst.lo[1] + j) * g.s[1] * (g.nd > 1) + (dst.lo[2] + k) * g.s[2] * (g.nd > 2);
+    f.q[m][xd] = st.q[m];
+  }
+}
+
+// FP64 pipe micro-benchmark: 8 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+}  // namespace osb

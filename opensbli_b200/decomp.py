@@ -1,0 +1,128 @@
+"""Slab decomposition of the single structured block over the GPUs of one node.
+
+The reference delegates decomposition to OPS (`ops_partition("")`, opensbli/code_generation/opsc.py:540-545); here
+the block is cut into equal slabs along its slowest axis, one rank (process) per GPU.  Faces along that axis are
+contiguous planes, so a halo exchange is a plain plane copy.  Only the conserved arrays are exchanged -- primitives are
+recomputed in the halos, as the reference does (constituent-relation kernels run over grid + halos).
+
+Exchange protocol per RK stage (the place where the reference has its `ops_halo_transfer`s, algorithm.py:440-442):
+    stage kernels + rank-local BCs -> barrier -> peer stores of boundary planes over NVLink (CUDA IPC) -> barrier
+The pure functions in this module (extents, neighbours, plane indices) are shared by the GPU driver and by the
+CPU (gloo) tests of the N>1 path.
+"""
+import copy
+
+from . import plan as _plan
+
+
+def scheme_halos(plan):
+    """(halo_m, halo_p) of the spatial scheme: WENO/TENO 3/4 (weno.py:17-32, teno.py:18-36), central 2/2."""
+    return (2, 2) if plan['conv'] == 'central' else (3, 4)
+
+
+def slab_axis(plan):
+    return plan['ndim'] - 1
+
+
+def local_extent(plan, rank, world):
+    ax = slab_axis(plan)
+    n = plan['np'][ax]
+    if n % world:
+        raise _plan.PlanError('np[%d]=%d is not divisible by %d ranks' % (ax, n, world))
+    loc = n // world
+    return rank * loc, loc
+
+
+def neighbours(plan, rank, world):
+    """(low, high) neighbour ranks along the slab axis, None at a physical (non-periodic) boundary."""
+    ax = slab_axis(plan)
+    periodic = plan['bc'][ax][0]['type'] == 'periodic'
+    low = rank - 1 if rank > 0 else (world - 1 if periodic else None)
+    high = rank + 1 if rank < world - 1 else (0 if periodic else None)
+    if world == 1:
+        return None, None
+    return low, high
+
+
+def local_plan(plan, rank, world):
+    """Plan of one rank: its slab of the block; faces shared with a neighbour become 'exchange' BCs."""
+    if world == 1:
+        return copy.deepcopy(plan)
+    ax = slab_axis(plan)
+    _, loc = local_extent(plan, rank, world)
+    hm, hp = scheme_halos(plan)
+    if loc < max(hm, hp):
+        raise _plan.PlanError('slab of %d planes is thinner than the halo depth' % loc)
+    p = copy.deepcopy(plan)
+    p['np'][ax] = loc
+    low, high = neighbours(plan, rank, world)
+    if low is not None:
+        p['bc'][ax][0] = {'type': 'exchange'}
+    if high is not None:
+        p['bc'][ax][1] = {'type': 'exchange'}
+    return _plan.validate(p)
+
+
+def push_planes(plan_local, halo=5):
+    """Plane index ranges (in the padded array, along the slab axis) of the two pushes of one rank:
+    'up'   : my top hm planes    [np-hm, np) -> high neighbour's low halo  [-hm, 0)
+    'down' : my bottom hp planes [0, hp)     -> low neighbour's high halo  [np, np+hp)   (same np on every rank)"""
+    ax = slab_axis(plan_local)
+    n = plan_local['np'][ax]
+    hm, hp = scheme_halos(plan_local)
+    return {'up': ((halo + n - hm, halo + n), (halo - hm, halo)),
+            'down': ((halo, halo + hp), (halo + n, halo + n + hp))}
+
+
+class DistributedSimulation(object):
+    """One rank of a slab-decomposed run on GPUs: a Simulation plus the per-stage halo exchange.
+    `dist` is torch.distributed (already initialised, one rank per GPU)."""
+
+    def __init__(self, plan_global, dist, device):
+        from .runtime import Simulation
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.plan_global = _plan.validate(plan_global)
+        self.plan = local_plan(plan_global, self.rank, self.world)
+        self.offset, self.nloc = local_extent(plan_global, self.rank, self.world)
+        self.sim = Simulation(self.plan, device=device)
+        self.device = device
+        self.nstages = len(self.plan['rk_a'])
+        self.low, self.high = neighbours(plan_global, self.rank, self.world)
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.sim.ipc_export())
+            if self.low is not None:
+                self.sim.ipc_import(0, handles[self.low])
+            if self.high is not None:
+                self.sim.ipc_import(1, handles[self.high])
+            self.barrier()
+
+    def barrier(self):
+        import torch
+        if self.world > 1:
+            self.sim.sync()
+            if self.dist.get_backend() == 'nccl':
+                self.dist.barrier(device_ids=[torch.cuda.current_device()])
+            else:
+                self.dist.barrier()
+
+    def exchange(self):
+        if self.world > 1:
+            self.barrier()          # everyone has finished reading its halos / writing its boundary planes
+            self.sim.halo_push()
+            self.barrier()          # all pushes have landed
+
+    def step(self, nsteps=1):
+        if self.world == 1:
+            self.sim.step(nsteps)
+            return
+        for _ in range(nsteps):
+            self.sim.step_begin()
+            self.exchange()
+            for s in range(self.nstages):
+                self.sim.stage(s)
+                self.exchange()
+
+    def close(self):
+        self.sim.close()

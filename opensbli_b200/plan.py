@@ -1,0 +1,116 @@
+"""Execution plan of the B200 back end.
+
+A *plan* is what `B200(alg)` (backend.py) distils from an OpenSBLI algorithm object -- the same
+information the reference's OPSC back end turns into OPS-C text (opensbli/code_generation/opsc.py:250-282):
+dimensions, grid sizes, which spatial/temporal schemes act on the canonical compressible
+Euler / Navier-Stokes system, boundary conditions per side, and the numerical constants.  It is a plain
+JSON-able dict; `to_text` serialises it to the line format parsed by the C ABI (`osb_create`).
+
+    ndim            1 | 2 | 3
+    np              [n0, n1, n2][:ndim]           block0np{d}
+    delta           [d0, ...]                     Delta{d}block0
+    conv            'central' | 'weno' | 'teno'   Central / LLFWeno / LLFTeno
+    order           4 | 5 | 6
+    weno_formulation 'JS' | 'Z'
+    averaging       'roe' | 'simple'              RoeAverage / SimpleAverage
+    viscous         bool                          constant-viscosity Navier-Stokes terms (Central / StoreSome)
+    rk              'ls' | 'sbli'                 RungeKuttaLS / RungeKutta
+    rk_a, rk_b      stage coefficients            LS: A, B ; SBLI: rkold, rknew
+    constants       {name: float}                 gama, Minf, Re, Pr, dt, eps, TENO_CT, ...
+    bc              [[side0, side1] per direction] each {'type': 'periodic'} | {'type': 'dirichlet', 'q': [...]}
+                    | {'type': 'exchange'} (halo owned by the neighbouring rank of a slab decomposition)
+    init            optional list of [lhs, rhs] assignment strings (numpy syntax) for the cold initialisation
+    niter           optional int
+"""
+import copy
+import json
+
+CONV = ('central', 'weno', 'teno')
+
+
+class PlanError(ValueError):
+    pass
+
+
+def validate(plan):
+    nd = plan.get('ndim')
+    if nd not in (1, 2, 3):
+        raise PlanError('ndim must be 1, 2 or 3')
+    for k in ('np', 'delta'):
+        if len(plan.get(k, ())) < nd:
+            raise PlanError('%s needs %d entries' % (k, nd))
+    if plan.get('conv') not in CONV:
+        raise PlanError('conv must be one of %s' % (CONV,))
+    order = plan.get('order')
+    ok = {'central': (4,), 'weno': (5,), 'teno': (5, 6)}[plan['conv']]
+    if order not in ok:
+        raise PlanError('%s scheme: order %r is not implemented by the B200 back end (supported: %s)' % (plan['conv'], order, ok))
+    if plan.get('rk') not in ('ls', 'sbli'):
+        raise PlanError("rk must be 'ls' or 'sbli'")
+    if not plan.get('rk_a') or len(plan['rk_a']) != len(plan.get('rk_b', ())):
+        raise PlanError('rk_a / rk_b missing or of different length')
+    if len(plan.get('bc', ())) < nd:
+        raise PlanError('bc needs one [side0, side1] pair per direction')
+    for d in range(nd):
+        for s in range(2):
+            b = plan['bc'][d][s]
+            if b['type'] not in ('periodic', 'dirichlet', 'exchange'):
+                raise PlanError("boundary condition '%s' is not implemented by the B200 back end" % b['type'])
+            if b['type'] == 'dirichlet' and len(b.get('q', ())) != nd + 2:
+                raise PlanError('dirichlet bc needs %d conservative values' % (nd + 2))
+    c = plan.get('constants', {})
+    need = ['gama', 'dt'] + (['Re', 'Pr', 'Minf'] if plan.get('viscous') else [])
+    for k in need:
+        if k not in c:
+            raise PlanError('missing constant %s' % k)
+    return plan
+
+
+def _f(x):
+    return repr(float(x))
+
+
+def to_text(plan):
+    """Serialise for osb_create (see include/osbli_b200.h)."""
+    validate(plan)
+    nd = plan['ndim']
+    L = ['osbli_plan 1', 'ndim %d' % nd,
+         'np ' + ' '.join(str(int(n)) for n in plan['np'][:nd]),
+         'delta ' + ' '.join(_f(d) for d in plan['delta'][:nd]),
+         'conv %s' % plan['conv'], 'order %d' % plan['order'],
+         'weno_formulation %s' % plan.get('weno_formulation', 'JS'),
+         'averaging %s' % plan.get('averaging', 'roe'),
+         'viscous %d' % (1 if plan.get('viscous') else 0),
+         'rk %s' % plan['rk'],
+         'rk_a ' + ' '.join(_f(v) for v in plan['rk_a']),
+         'rk_b ' + ' '.join(_f(v) for v in plan['rk_b'])]
+    for k, v in sorted(plan['constants'].items()):
+        L.append('const %s %s' % (k, _f(v)))
+    for d in range(nd):
+        for s in range(2):
+            b = plan['bc'][d][s]
+            if b['type'] == 'dirichlet':
+                L.append('bc %d %d dirichlet %s' % (d, s, ' '.join(_f(v) for v in b['q'])))
+            else:
+                L.append('bc %d %d %s' % (d, s, b['type']))
+    return '\n'.join(L) + '\n'
+
+
+def save(plan, path):
+    with open(path, 'w') as f:
+        json.dump(plan, f, indent=1, sort_keys=True)
+
+
+def load(path):
+    with open(path) as f:
+        return validate(json.load(f))
+
+
+def with_size(plan, np_, delta=None, **constants):
+    """Copy of a plan on another grid / with other constants."""
+    p = copy.deepcopy(plan)
+    p['np'] = list(np_)
+    if delta is not None:
+        p['delta'] = list(delta)
+    p['constants'].update(constants)
+    return validate(p)

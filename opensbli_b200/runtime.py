@@ -1,0 +1,215 @@
+"""ctypes binding of the C ABI (include/osbli_b200.h) and the `Simulation` driver object.
+
+There is no CPU fallback: if the CUDA library is missing or no GPU is present, construction fails loudly.
+"""
+import ctypes
+import os
+import numpy as np
+
+from . import plan as _plan
+from .build import LIB
+
+_P = ctypes.POINTER(ctypes.c_double)
+_lib = None
+
+FAMILIES = ('prim', 'flux', 'central', 'viscous', 'rk', 'bc')
+
+SYMBOLS = ('osb_create', 'osb_destroy', 'osb_last_error', 'osb_set_const_f64', 'osb_get_const_f64',
+           'osb_num_fields', 'osb_field_name', 'osb_field_info', 'osb_upload', 'osb_download', 'osb_device_ptr',
+           'osb_step', 'osb_step_begin', 'osb_stage', 'osb_sync', 'osb_apply_bcs', 'osb_residual', 'osb_step_timed', 'osb_timer_start', 'osb_timer_stop', 'osb_advance_host',
+           'osb_launch_count', 'osb_profile_step', 'osb_ipc_export', 'osb_ipc_import', 'osb_halo_push',
+           'osb_measure_fp64_peak')
+
+
+class BackendError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """Load libosbli_b200.so (built in-tree by opensbli_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB
+    if not os.path.exists(path):
+        raise BackendError('%s not found: build it with `python -m opensbli_b200.build` '
+                           '(the B200 back end has no CPU fallback)' % path)
+    lib = ctypes.CDLL(path)
+    lib.osb_last_error.restype = ctypes.c_char_p
+    lib.osb_last_error.argtypes = [ctypes.c_void_p]
+    lib.osb_field_name.restype = ctypes.c_char_p
+    lib.osb_field_name.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.osb_create.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    lib.osb_destroy.argtypes = [ctypes.c_void_p]
+    lib.osb_set_const_f64.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_double]
+    lib.osb_get_const_f64.argtypes = [ctypes.c_void_p, ctypes.c_char_p, _P]
+    lib.osb_num_fields.argtypes = [ctypes.c_void_p]
+    lib.osb_field_info.argtypes = [ctypes.c_void_p, ctypes.c_char_p] + [ctypes.POINTER(ctypes.c_int)] * 3
+    lib.osb_upload.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
+    lib.osb_download.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
+    lib.osb_device_ptr.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+    lib.osb_step.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.osb_sync.argtypes = [ctypes.c_void_p]
+    lib.osb_step_begin.argtypes = [ctypes.c_void_p]
+    lib.osb_stage.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.osb_apply_bcs.argtypes = [ctypes.c_void_p]
+    lib.osb_residual.argtypes = [ctypes.c_void_p]
+    lib.osb_step_timed.argtypes = [ctypes.c_void_p, ctypes.c_int, _P]
+    lib.osb_timer_start.argtypes = [ctypes.c_void_p]
+    lib.osb_timer_stop.argtypes = [ctypes.c_void_p, _P]
+    lib.osb_advance_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _P]
+    lib.osb_launch_count.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
+    lib.osb_profile_step.argtypes = [ctypes.c_void_p, _P, ctypes.POINTER(ctypes.c_longlong)]
+    lib.osb_ipc_export.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
+    lib.osb_ipc_import.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    lib.osb_halo_push.argtypes = [ctypes.c_void_p]
+    lib.osb_measure_fp64_peak.argtypes = [ctypes.c_int, _P]
+    _lib = lib
+    return lib
+
+
+def measure_fp64_peak(device=-1):
+    v = ctypes.c_double()
+    rc = load_library().osb_measure_fp64_peak(device, ctypes.byref(v))
+    if rc:
+        raise BackendError('osb_measure_fp64_peak failed (%d)' % rc)
+    return v.value
+
+
+class Simulation(object):
+    """One solver context on one GPU.  Field arrays are numpy arrays in the reference layout:
+    shape (np2+10, np1+10, np0+10)[-ndim:], C order (x fastest), halo 5."""
+
+    HALO = 5
+
+    def __init__(self, plan, device=-1):
+        self.plan = _plan.validate(plan)
+        self.lib = load_library()
+        self.ctx = ctypes.c_void_p()
+        rc = self.lib.osb_create(_plan.to_text(plan).encode(), int(device), ctypes.byref(self.ctx))
+        if rc:
+            raise BackendError('osb_create failed (%d): %s' % (rc, self.lib.osb_last_error(None).decode()))
+        self.ndim = plan['ndim']
+        self.nv = self.ndim + 2
+        self.shape = tuple(int(plan['np'][d]) + 2 * self.HALO for d in reversed(range(self.ndim)))
+        self.q_names = ['rho'] + ['rhou%d' % d for d in range(self.ndim)] + ['rhoE']
+
+    # -- plumbing
+    def _check(self, rc, what):
+        if rc:
+            raise BackendError('%s failed (%d): %s' % (what, rc, self.lib.osb_last_error(self.ctx).decode()))
+
+    def close(self):
+        if self.ctx:
+            self.lib.osb_destroy(self.ctx)
+            self.ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- fields
+    def field_names(self):
+        return [self.lib.osb_field_name(self.ctx, i).decode() for i in range(self.lib.osb_num_fields(self.ctx))]
+
+    def upload(self, name, array):
+        a = np.ascontiguousarray(array, dtype=np.float64)
+        if a.shape != self.shape:
+            raise ValueError('field %s: expected padded shape %s, got %s' % (name, self.shape, a.shape))
+        self._check(self.lib.osb_upload(self.ctx, name.encode(), a.ctypes.data), 'osb_upload')
+
+    def download(self, name):
+        a = np.empty(self.shape, dtype=np.float64)
+        self._check(self.lib.osb_download(self.ctx, name.encode(), a.ctypes.data), 'osb_download')
+        return a
+
+    def set_state(self, q):
+        for n, a in zip(self.q_names, q):
+            self.upload(n, a)
+
+    def get_state(self):
+        return [self.download(n) for n in self.q_names]
+
+    def device_ptr(self, name):
+        p = ctypes.c_void_p()
+        self._check(self.lib.osb_device_ptr(self.ctx, name.encode(), ctypes.byref(p)), 'osb_device_ptr')
+        return p.value
+
+    def set_const(self, name, value):
+        self._check(self.lib.osb_set_const_f64(self.ctx, name.encode(), float(value)), 'osb_set_const_f64')
+
+    # -- the time loop
+    def step(self, nsteps=1, sync=True):
+        self._check(self.lib.osb_step(self.ctx, int(nsteps)), 'osb_step')
+        if sync:
+            self.sync()
+
+    def step_begin(self):
+        self._check(self.lib.osb_step_begin(self.ctx), 'osb_step_begin')
+
+    def stage(self, s):
+        self._check(self.lib.osb_stage(self.ctx, int(s)), 'osb_stage')
+
+    def halo_push(self):
+        self._check(self.lib.osb_halo_push(self.ctx), 'osb_halo_push')
+
+    def ipc_export(self):
+        buf = ctypes.create_string_buffer(64 * 8)
+        n = ctypes.c_int()
+        self._check(self.lib.osb_ipc_export(self.ctx, buf, ctypes.byref(n)), 'osb_ipc_export')
+        return buf.raw[:n.value]
+
+    def ipc_import(self, side, handles):
+        self._check(self.lib.osb_ipc_import(self.ctx, int(side), handles, len(handles)), 'osb_ipc_import')
+
+    def sync(self):
+        self._check(self.lib.osb_sync(self.ctx), 'osb_sync')
+
+    def apply_bcs(self):
+        self._check(self.lib.osb_apply_bcs(self.ctx), 'osb_apply_bcs')
+        self.sync()
+
+    def residual(self):
+        self._check(self.lib.osb_residual(self.ctx), 'osb_residual')
+        self.sync()
+        return [self.download('Residual%d' % m) for m in range(self.nv)]
+
+    def step_timed(self, nsteps=1):
+        ms = ctypes.c_double()
+        self._check(self.lib.osb_step_timed(self.ctx, int(nsteps), ctypes.byref(ms)), 'osb_step_timed')
+        return ms.value
+
+    def timer_start(self):
+        self._check(self.lib.osb_timer_start(self.ctx), 'osb_timer_start')
+
+    def timer_stop(self):
+        ms = ctypes.c_double()
+        self._check(self.lib.osb_timer_stop(self.ctx, ctypes.byref(ms)), 'osb_timer_stop')
+        return ms.value
+
+    def advance_host(self, q_in, q_out, nsteps=1):
+        """End-to-end call with HOST buffers (lists of nv padded float64 arrays, ideally pinned)."""
+        pin = (ctypes.c_void_p * self.nv)(*[a.ctypes.data for a in q_in])
+        pout = (ctypes.c_void_p * self.nv)(*[a.ctypes.data for a in q_out])
+        ms = ctypes.c_double()
+        self._check(self.lib.osb_advance_host(self.ctx, pin, pout, int(nsteps), ctypes.byref(ms)), 'osb_advance_host')
+        return ms.value
+
+    def launch_count(self):
+        n = ctypes.c_longlong()
+        self._check(self.lib.osb_launch_count(self.ctx, ctypes.byref(n)), 'osb_launch_count')
+        return n.value
+
+    def profile_step(self):
+        ms = (ctypes.c_double * len(FAMILIES))()
+        n = (ctypes.c_longlong * len(FAMILIES))()
+        self._check(self.lib.osb_profile_step(self.ctx, ms, n), 'osb_profile_step')
+        return {f: {'ms': ms[i], 'launches': n[i]} for i, f in enumerate(FAMILIES)}

@@ -267,60 +267,88 @@ static inline double eigenvalue(int nd, int j, double ud, double a) {
  * interfaces i+1/2, i = -1 .. np_d-1 (the reference also evaluates i = np_d, which nothing consumes).
  * Output wk[m] = flux component m at interface i+1/2 stored at point i.
  * ------------------------------------------------------------------------------------------- */
+/* one interface: stencil data for the 6 points p = 0..5 <-> offsets -2..3 */
+static void interface_flux(const osbo_cfg *c, int nd, int dir, double qs[6][5], double us[6][3],
+                           const double *ps, const double *as, double *flux) {
+  const int nv = nd + 2;
+  const double gm1 = c->gama - 1.0;
+  /* interface state between points 2 and 3 (averaging.py:31-59 simple, :62-114 Roe) */
+  double rho, u[3] = {0, 0, 0}, a;
+  if (c->averaging == OSBO_AVG_ROE) {
+    double sl = sqrt(qs[2][0]), sr = sqrt(qs[3][0]);
+    rho = sqrt(qs[2][0] * qs[3][0]);
+    double w = 1.0 / (sr + sl), ke = 0.0;
+    for (int d = 0; d < nd; d++) { u[d] = w * (sr * us[3][d] + sl * us[2][d]); ke += u[d] * u[d]; }
+    double Hh = w * ((ps[2] + qs[2][nd + 1]) / sl + (ps[3] + qs[3][nd + 1]) / sr);
+    a = sqrt(gm1 * (Hh - 0.5 * ke));
+  } else {
+    rho = 0.5 * (qs[2][0] + qs[3][0]);
+    for (int d = 0; d < nd; d++) u[d] = 0.5 * (us[2][d] + us[3][d]);
+    a = 0.5 * (as[2] + as[3]);
+  }
+  double L[5][5], Rm[5][5];
+  eigensystem(nd, dir, c->gama, rho, u, a, L, Rm);
+  /* characteristic flux / solution over the 6 stencil points and max |lambda| */
+  double CF[5][6], CS[5][6], lam[5] = {0, 0, 0, 0, 0};
+  for (int p = 0; p < 6; p++) {
+    double F[5], ud = us[p][dir], pr = ps[p];
+    const double *qv = qs[p];
+    F[0] = qv[1 + dir];
+    for (int d = 0; d < nd; d++) F[1 + d] = qv[1 + d] * ud + (d == dir ? pr : 0.0);
+    F[nd + 1] = (pr + qv[nd + 1]) * ud;
+    for (int jj = 0; jj < nv; jj++) {
+      double cf = 0.0, cs = 0.0;
+      for (int m = 0; m < nv; m++) { cf += L[jj][m] * F[m]; cs += L[jj][m] * qv[m]; }
+      CF[jj][p] = cf; CS[jj][p] = cs;
+      double l = fabs(eigenvalue(nd, jj, ud, as[p]));
+      if (l > lam[jj]) lam[jj] = l;
+    }
+  }
+  double rec[5];
+  for (int jj = 0; jj < nv; jj++) {
+    double fp[6], fm[6];
+    for (int p = 0; p < 6; p++) { fp[p] = 0.5 * (CF[jj][p] + lam[jj] * CS[jj][p]); fm[p] = 0.5 * (CF[jj][p] - lam[jj] * CS[jj][p]); }
+    if (c->conv == OSBO_CONV_TENO) rec[jj] = c->order == 6 ? osbo_recon_teno6(fp, fm, c->eps, c->teno_ct) : osbo_recon_teno5(fp, fm, c->eps, c->teno_ct);
+    else rec[jj] = osbo_recon_weno5(fp, fm, c->weno_z);
+  }
+  for (int m = 0; m < nv; m++) {
+    double f = 0.0;
+    for (int jj = 0; jj < nv; jj++) f += Rm[m][jj] * rec[jj];
+    flux[m] = f;
+  }
+}
+
+/* test hook: flux of one interface from 6 conservative states q6[p][m] (constituent relations applied here) */
+void osbo_interface_flux(const osbo_cfg *c, int dir, const double *q6, double *flux) {
+  const int nd = c->ndim, nv = nd + 2;
+  double qs[6][5], us[6][3], ps[6], as[6];
+  for (int p = 0; p < 6; p++) {
+    double ke = 0.0;
+    for (int m = 0; m < nv; m++) qs[p][m] = q6[p * nv + m];
+    for (int d = 0; d < nd; d++) { us[p][d] = qs[p][1 + d] / qs[p][0]; ke += 0.5 * qs[p][0] * us[p][d] * us[p][d]; }
+    ps[p] = (c->gama - 1.0) * (qs[p][nd + 1] - ke);
+    as[p] = sqrt(c->gama * ps[p] / qs[p][0]);
+  }
+  interface_flux(c, nd, dir, qs, us, ps, as, flux);
+}
+
 static void llf_flux(const osbo_cfg *c, const grid_t *g, int dir, double *const *q, const prim_t *P, double **wk) {
   const int nd = g->ndim, nv = g->nv;
   int lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
   for (int d = 0; d < nd; d++) { lo[d] = 0; hi[d] = g->np[d]; }
   lo[dir] = -1;
   const long sd = g->s[dir];
-  const double gm1 = c->gama - 1.0;
   for (int k = lo[2]; k < hi[2]; k++) for (int j = lo[1]; j < hi[1]; j++) for (int i = lo[0]; i < hi[0]; i++) {
-    const long x = gidx(g, i, j, k), x1 = x + sd;
-    /* interface state (averaging.py:31-59 simple, :62-114 Roe) */
-    double rho, u[3] = {0, 0, 0}, a;
-    if (c->averaging == OSBO_AVG_ROE) {
-      double sl = sqrt(q[0][x]), sr = sqrt(q[0][x1]);
-      rho = sqrt(q[0][x] * q[0][x1]);
-      double w = 1.0 / (sr + sl), ke = 0.0;
-      for (int d = 0; d < nd; d++) { u[d] = w * (sr * P->u[d][x1] + sl * P->u[d][x]); ke += u[d] * u[d]; }
-      double Hh = w * ((P->p[x] + q[nd + 1][x]) / sl + (P->p[x1] + q[nd + 1][x1]) / sr);
-      a = sqrt(gm1 * (Hh - 0.5 * ke));
-    } else {
-      rho = 0.5 * (q[0][x] + q[0][x1]);
-      for (int d = 0; d < nd; d++) u[d] = 0.5 * (P->u[d][x] + P->u[d][x1]);
-      a = 0.5 * (P->a[x] + P->a[x1]);
-    }
-    double L[5][5], Rm[5][5];
-    eigensystem(nd, dir, c->gama, rho, u, a, L, Rm);
-    /* characteristic flux / solution over the 6 stencil points and max |lambda| */
-    double CF[5][6], CS[5][6], lam[5] = {0, 0, 0, 0, 0};
+    const long x = gidx(g, i, j, k);
+    double qs[6][5], us[6][3], ps[6], as[6], fl[5];
     for (int p = 0; p < 6; p++) {
       const long xp = x + (p - 2) * sd;
-      double qv[5], F[5], ud = P->u[dir][xp], pr = P->p[xp];
-      for (int m = 0; m < nv; m++) qv[m] = q[m][xp];
-      F[0] = qv[1 + dir];
-      for (int d = 0; d < nd; d++) F[1 + d] = qv[1 + d] * ud + (d == dir ? pr : 0.0);
-      F[nd + 1] = (pr + qv[nd + 1]) * ud;
-      for (int jj = 0; jj < nv; jj++) {
-        double cf = 0.0, cs = 0.0;
-        for (int m = 0; m < nv; m++) { cf += L[jj][m] * F[m]; cs += L[jj][m] * qv[m]; }
-        CF[jj][p] = cf; CS[jj][p] = cs;
-        double l = fabs(eigenvalue(nd, jj, ud, P->a[xp]));
-        if (l > lam[jj]) lam[jj] = l;
-      }
+      for (int m = 0; m < nv; m++) qs[p][m] = q[m][xp];
+      for (int d = 0; d < nd; d++) us[p][d] = P->u[d][xp];
+      ps[p] = P->p[xp]; as[p] = P->a[xp];
     }
-    double rec[5];
-    for (int jj = 0; jj < nv; jj++) {
-      double fp[6], fm[6];
-      for (int p = 0; p < 6; p++) { fp[p] = 0.5 * (CF[jj][p] + lam[jj] * CS[jj][p]); fm[p] = 0.5 * (CF[jj][p] - lam[jj] * CS[jj][p]); }
-      if (c->conv == OSBO_CONV_TENO) rec[jj] = c->order == 6 ? osbo_recon_teno6(fp, fm, c->eps, c->teno_ct) : osbo_recon_teno5(fp, fm, c->eps, c->teno_ct);
-      else rec[jj] = osbo_recon_weno5(fp, fm, c->weno_z);
-    }
-    for (int m = 0; m < nv; m++) {
-      double f = 0.0;
-      for (int jj = 0; jj < nv; jj++) f += Rm[m][jj] * rec[jj];
-      wk[m][x] = f;
-    }
+    interface_flux(c, nd, dir, qs, us, ps, as, fl);
+    for (int m = 0; m < nv; m++) wk[m][x] = fl[m];
   }
 }
 

@@ -71,6 +71,8 @@ void osbo_residual(const osbo_cfg *c, double *const *q, double *const *R); /* CR
 double osbo_recon_teno5(const double *fp, const double *fm, double eps, double ct);
 double osbo_recon_teno6(const double *fp, const double *fm, double eps, double ct);
 double osbo_recon_weno5(const double *fp, const double *fm, int z);
+/* flux of one interface (direction dir) from the 6 conservative stencil states q6[p*nv+m], p <-> offsets -2..3 */
+void osbo_interface_flux(const osbo_cfg *c, int dir, const double *q6, double *flux);
 
 #ifdef __cplusplus
 }
