@@ -1,0 +1,129 @@
+"""CPU tests of the drop-in boundary: the reference front end (only importable in the build container, where
+/root/reference exists) drives `B200(alg)`; the plans it distils must equal the hand-written plans of the golden
+fixtures.  The committed plan fixtures under tests/golden/plans/ make the same check possible without the reference."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from common import load_fixture
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PLANS = os.path.join(REPO, 'tests', 'golden', 'plans')
+REF = '/root/reference'
+
+APPS = {
+    'tgv_teno5': (os.path.join(REPO, 'apps', 'tgv_teno5.py'), [], 'tgv_teno5_16'),
+    'tgv_central4': (REF + '/apps/taylor_green_vortex/taylor_green_vortex.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'tgv_central4_16'),
+    'sod_teno5': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'sod_teno5_n200'),
+}
+
+DRIVER = r'''
+import sys, os
+sys.path.insert(0, %(oracle)r); sys.path.insert(0, %(repo)r)
+import refshim; refshim.install(%(ref)r)
+os.environ['OSBLI_BACKEND'] = 'b200'
+src = open(%(app)r).read()
+for old, new in %(edits)r:
+    assert old in src
+    src = src.replace(old, new)
+exec(compile(src, %(app)r, 'exec'), {'__name__': '__main__'})
+'''
+
+
+def run_app(name, workdir):
+    app, edits, _ = APPS[name]
+    code = DRIVER % dict(oracle=os.path.join(REPO, 'oracle'), repo=REPO, ref=REF, app=app, edits=edits)
+    env = dict(os.environ, PYTHONHASHSEED='0')
+    subprocess.run([sys.executable, '-W', 'ignore', '-c', code], cwd=workdir, env=env, check=True, stdout=subprocess.DEVNULL)
+
+
+def comparable(plan):
+    keys = ('ndim', 'np', 'conv', 'order', 'averaging', 'viscous', 'rk', 'rk_a', 'rk_b', 'bc')
+    p = {k: plan[k] for k in keys}
+    if plan['conv'] == 'weno':
+        p['weno_formulation'] = plan.get('weno_formulation', 'JS')
+    return p
+
+
+@pytest.mark.parametrize('name', sorted(APPS))
+def test_b200_backend_distils_expected_plan(name, tmp_path):
+    from opensbli_b200 import run as R
+    if os.path.isdir(REF):
+        run_app(name, str(tmp_path))
+        workdir = str(tmp_path)
+        os.makedirs(os.path.join(PLANS, name), exist_ok=True)      # refresh the committed fixtures
+        for f in ('opensbli_b200.plan.json', 'opensbli.cpp'):
+            open(os.path.join(PLANS, name, f), 'w').write(open(os.path.join(workdir, f)).read())
+    else:
+        workdir = os.path.join(PLANS, name)
+        if not os.path.exists(os.path.join(workdir, 'opensbli.cpp')):
+            pytest.skip('no committed plan fixture for %s' % name)
+    plan_sym, env, plan_num = R.load_case(workdir)
+    want, _ = load_fixture(APPS[name][2])
+    got = comparable(plan_num)
+    exp = comparable(want)
+    # the app's own grid size may differ from the fixture's
+    got['np'] = exp['np']
+    assert json.loads(json.dumps(got)) == json.loads(json.dumps(exp))
+    for k in ('gama',):
+        assert plan_num['constants'][k] == want['constants'][k]
+    # the stub keeps the reference's contract: every parameter was substituted, `int iter=0;` is present
+    stub = open(os.path.join(workdir, 'opensbli.cpp')).read()
+    assert '=Input;' not in stub and 'int iter=0;' in stub
+
+
+def test_initial_state_from_cold_kernel_matches_reference_init():
+    """numpy evaluation of the Grid_based_initialisation statements == the reference's own init kernel output."""
+    import numpy as np
+    from opensbli_b200 import run as R
+    workdir = os.path.join(PLANS, 'tgv_teno5')
+    if not os.path.exists(os.path.join(workdir, 'opensbli.cpp')):
+        pytest.skip('plan fixture missing')
+    plan_sym, env, plan_num = R.load_case(workdir)
+    want, states = load_fixture('tgv_teno5_16')
+    env = dict(env, block0np0=16, block0np1=16, block0np2=16, Delta0block0=want['delta'][0], Delta1block0=want['delta'][1], Delta2block0=want['delta'][2])
+    plan_num = R.resolve(plan_sym, env)
+    q0 = R.initial_state(plan_sym, plan_num, env)
+    s = (slice(5, -5),) * 3
+    for m in range(5):
+        assert np.abs(q0[m][s] - states[0][m]).max() <= 1e-13 * max(1.0, np.abs(states[0][m]).max())
+
+
+def test_sod_initial_state_and_dirichlet_states():
+    """Piecewise initial condition and the Dirichlet boundary states, evaluated from the plan fixture."""
+    import numpy as np
+    from opensbli_b200 import run as R
+    workdir = os.path.join(PLANS, 'sod_teno5')
+    if not os.path.exists(os.path.join(workdir, 'opensbli.cpp')):
+        pytest.skip('plan fixture missing')
+    plan_sym, env, plan_num = R.load_case(workdir)
+    want, states = load_fixture('sod_teno5_n200')
+    assert plan_num['niter'] == 1000 and plan_num['np'] == [200]
+    q0 = R.initial_state(plan_sym, plan_num, env)
+    for m in range(3):
+        assert np.abs(q0[m][5:-5] - states[0][m]).max() <= 1e-15
+    for s in range(2):
+        assert np.allclose(plan_num['bc'][0][s]['q'], want['bc'][0][s]['q'], rtol=1e-15, atol=0)
+
+
+def test_c_expression_semantics():
+    from opensbli_b200.run import c_eval
+    assert c_eval('ceil(0.2/0.0002)', {}) == 1000.0
+    assert c_eval('2*M_PI/block0np0', {'block0np0': 64}) == 2 * 3.141592653589793 / 64
+    assert c_eval('7/2', {}) == 3 and c_eval('7/2.0', {}) == 3.5 and c_eval('1.0/(n-1)', {'n': 200}) == 1.0 / 199
+    assert c_eval('1.0e-16', {}) == 1e-16
+
+
+def test_unsupported_features_fail_loudly(tmp_path):
+    """An app outside the accelerated path must raise, never silently fall back."""
+    if not os.path.isdir(REF):
+        pytest.skip('needs the reference front end')
+    app = REF + '/apps/katzer_SBLI/katzer_SBLI.py'
+    code = DRIVER % dict(oracle=os.path.join(REPO, 'oracle'), repo=REPO, ref=REF, app=app,
+                         edits=[("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")])
+    r = subprocess.run([sys.executable, '-W', 'ignore', '-c', code], cwd=str(tmp_path), env=dict(os.environ, PYTHONHASHSEED='0'),
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode != 0 and 'UnsupportedByB200' in r.stderr
