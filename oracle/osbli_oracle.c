@@ -482,6 +482,40 @@ void osbo_residual(const osbo_cfg *c, double *const *q, double *const *R) {
  * RK SBLI (rk_sbli.py:102-133): q = q_old + dt*rknew[s]*R ; q_old += dt*rkold[s]*R.
  * RK LS  (rk_LS.py:139-166):    tmp = dt*R + A[s]*tmp ; q += B[s]*tmp.
  * ------------------------------------------------------------------------------------------- */
+/* One stage of the loop for a decomposed run: stage < 0 = iteration start (BCs + rk_sbli save),
+ * otherwise residual + RK update + BCs of that stage.  Faces marked OSBO_BC_EXCHANGE are left to the caller. */
+int osbo_stage(const osbo_cfg *c, double *const *q, double *const *rk_reg, int stage) {
+  grid_t g; grid_init(c, &g);
+  const int nv = g.nv;
+  if (stage < 0) {
+    osbo_apply_bcs(c, q);
+    if (c->rk == OSBO_RK_SBLI)
+      for (int m = 0; m < nv; m++)
+        for (int k = 0; k < g.np[2]; k++) for (int j = 0; j < g.np[1]; j++) for (int i = 0; i < g.np[0]; i++) {
+          long x = gidx(&g, i, j, k); rk_reg[m][x] = q[m][x];
+        }
+    return 0;
+  }
+  double *Rbuf = (double *)calloc((size_t)g.n * nv, sizeof(double));
+  if (!Rbuf) return 1;
+  double *R[5]; for (int m = 0; m < nv; m++) R[m] = Rbuf + (size_t)m * g.n;
+  osbo_residual(c, q, R);
+  for (int m = 0; m < nv; m++)
+    for (int k = 0; k < g.np[2]; k++) for (int j = 0; j < g.np[1]; j++) for (int i = 0; i < g.np[0]; i++) {
+      long x = gidx(&g, i, j, k);
+      if (c->rk == OSBO_RK_SBLI) {
+        q[m][x] = c->dt * c->rk_b[stage] * R[m][x] + rk_reg[m][x];
+        rk_reg[m][x] = c->dt * c->rk_a[stage] * R[m][x] + rk_reg[m][x];
+      } else {
+        rk_reg[m][x] = c->dt * R[m][x] + c->rk_a[stage] * rk_reg[m][x];
+        q[m][x] = c->rk_b[stage] * rk_reg[m][x] + q[m][x];
+      }
+    }
+  osbo_apply_bcs(c, q);
+  free(Rbuf);
+  return 0;
+}
+
 int osbo_advance(const osbo_cfg *c, double *const *q, double *const *rk_reg, int nsteps) {
   grid_t g; grid_init(c, &g);
   const int nv = g.nv;

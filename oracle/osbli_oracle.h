@@ -34,7 +34,7 @@ extern "C" {
 enum { OSBO_CONV_CENTRAL = 0, OSBO_CONV_WENO = 1, OSBO_CONV_TENO = 2 };
 enum { OSBO_AVG_SIMPLE = 0, OSBO_AVG_ROE = 1 };
 enum { OSBO_RK_SBLI = 0, OSBO_RK_LS = 1 };
-enum { OSBO_BC_PERIODIC = 0, OSBO_BC_DIRICHLET = 1 };
+enum { OSBO_BC_PERIODIC = 0, OSBO_BC_DIRICHLET = 1, OSBO_BC_EXCHANGE = 2 /* halo filled by the caller (decomposed run) */ };
 
 typedef struct {
   int ndim;
@@ -63,6 +63,8 @@ long osbo_padded_size(const osbo_cfg *c);
  * simplicity -- only interior is touched).  Returns 0 on success. */
 int osbo_advance(const osbo_cfg *c, double *const *q, double *const *rk_reg, int nsteps);
 
+/* stage < 0: iteration start (BCs, save); else one RK stage incl. its BCs (for decomposed runs) */
+int osbo_stage(const osbo_cfg *c, double *const *q, double *const *rk_reg, int stage);
 /* Pieces, exposed for unit tests. */
 void osbo_apply_bcs(const osbo_cfg *c, double *const *q);
 void osbo_residual(const osbo_cfg *c, double *const *q, double *const *R); /* CR + spatial kernels */

@@ -11,7 +11,7 @@ ORACLE_DIR = os.path.join(REPO, 'oracle')
 REF_DIR = os.path.join(ORACLE_DIR, '_ref')
 
 CONV = {'central': 0, 'weno': 1, 'teno': 2}
-BC = {'periodic': 0, 'dirichlet': 1}
+BC = {'periodic': 0, 'dirichlet': 1, 'exchange': 2}
 
 
 class OsboCfg(ctypes.Structure):
@@ -98,6 +98,17 @@ def oracle_advance(plan, q, nsteps, rk_reg=None):
     rc = lib.osbo_advance(ctypes.byref(cfg), qa, ra, ctypes.c_int(nsteps))
     assert rc == 0
     return q, rk_reg
+
+
+def oracle_stage(plan, q, rk_reg, stage):
+    """In-place: stage < 0 = iteration start, else one RK stage (arrays must be C-contiguous float64)."""
+    lib = oracle_lib()
+    cfg = make_cfg(plan)
+    nv = plan['ndim'] + 2
+    P = ctypes.POINTER(ctypes.c_double)
+    qa = (P * nv)(*[a.ctypes.data_as(P) for a in q])
+    ra = (P * nv)(*[a.ctypes.data_as(P) for a in rk_reg])
+    assert lib.osbo_stage(ctypes.byref(cfg), qa, ra, ctypes.c_int(stage)) == 0
 
 
 def oracle_residual(plan, q):
