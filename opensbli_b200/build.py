@@ -4,7 +4,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'osb_driver.cu')
-DEPS = [SRC, os.path.join(HERE, 'csrc', 'osb_kernels.cuh'), os.path.join(HERE, 'csrc', 'osb_math.cuh'),
+DEPS = [SRC, os.path.join(HERE, 'csrc', 'osb_kernels.cuh'), os.path.join(HERE, 'csrc', 'osb_math.cuh'), os.path.join(HERE, 'csrc', 'osb_flux.cuh'),
         os.path.join(os.path.dirname(HERE), 'include', 'osbli_b200.h')]
 LIB = os.path.join(HERE, 'libosbli_b200.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

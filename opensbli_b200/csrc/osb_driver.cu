@@ -140,7 +140,7 @@ void refresh_constants(osb_ctx *c) {
   c->pc.gama = get("gama", 1.4); c->pc.Minf = get("Minf", 1.0); c->pc.Re = get("Re", 1.0); c->pc.Pr = get("Pr", 1.0);
   c->pc.dt = get("dt", 0.0);
   for (int d = 0; d < 3; d++) { c->pc.inv[d] = 1.0 / P.delta[d]; c->pc.inv2[d] = pow(P.delta[d], -2); }
-  c->sp.eps = get("eps", 1e-16); c->sp.teno_ct = get("TENO_CT", 1e-6);
+  c->sp = make_scheme_params(get("eps", 1e-16), get("TENO_CT", 1e-6));
 }
 
 Field *find_field(osb_ctx *c, const char *name) {
@@ -180,22 +180,29 @@ template <int ND, int RECON, int AVG>
 void launch_flux(osb_ctx *c) {
   const GridDev &g = c->grid;
   {
-    const long long E = (long long)(g.np[0] + 1) * g.np[1] * g.np[2];
-    const long long nb = (E - 1 + FLUX_BT - 2) / (FLUX_BT - 1);
+    const long long T = (long long)(g.np[0] + 6) * g.np[1] * g.np[2];
+    const long long nb = (T + F2_BT - 7) / (F2_BT - 6);
     Launcher L(c, OSB_FAM_FLUX);
-    k_flux_x<ND, RECON, AVG, false><<<(unsigned)nb, FLUX_BT, 0, c->stream>>>(g, c->fp, c->pc, c->sp);
+    k_flux2_x<ND, RECON, AVG, false><<<(unsigned)nb, F2_BT, 0, c->stream>>>(g, c->fp, c->pc, c->sp);
   }
   if (ND >= 2) {
-    const long long ER = (long long)(g.np[1] + 1) * (ND > 2 ? g.np[2] : 1);
-    dim3 b(32, FLUX_TY, 1), gr((unsigned)((ER - 1 + FLUX_RB - 2) / (FLUX_RB - 1)), (g.np[0] + 31) / 32, 1);
+    const long long TR = (long long)(g.np[1] + 6) * (ND > 2 ? g.np[2] : 1);
+    dim3 b(32, F2_TY, 1), gr((unsigned)((TR + F2_RT - 7) / (F2_RT - 6)), (g.np[0] + 31) / 32, 1);
     Launcher L(c, OSB_FAM_FLUX);
-    k_flux_yz<(ND >= 2 ? ND : 2), 1, RECON, AVG, true><<<gr, b, 0, c->stream>>>(g, c->fp, c->pc, c->sp);
+    constexpr int N2 = (ND >= 2 ? ND : 2);
+    auto kern = k_flux2_yz<N2, 1, RECON, AVG, true>;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_yz_smem_bytes<N2>()); attr_set = true; }
+    kern<<<gr, b, f2_yz_smem_bytes<N2>(), c->stream>>>(g, c->fp, c->pc, c->sp);
   }
   if (ND >= 3) {
-    const long long ER = (long long)(g.np[2] + 1) * g.np[1];
-    dim3 b(32, FLUX_TY, 1), gr((unsigned)((ER - 1 + FLUX_RB - 2) / (FLUX_RB - 1)), (g.np[0] + 31) / 32, 1);
+    const long long TR = (long long)(g.np[2] + 6) * g.np[1];
+    dim3 b(32, F2_TY, 1), gr((unsigned)((TR + F2_RT - 7) / (F2_RT - 6)), (g.np[0] + 31) / 32, 1);
     Launcher L(c, OSB_FAM_FLUX);
-    k_flux_yz<3, 2, RECON, AVG, true><<<gr, b, 0, c->stream>>>(g, c->fp, c->pc, c->sp);
+    auto kern = k_flux2_yz<3, 2, RECON, AVG, true>;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_yz_smem_bytes<3>()); attr_set = true; }
+    kern<<<gr, b, f2_yz_smem_bytes<3>(), c->stream>>>(g, c->fp, c->pc, c->sp);
   }
 }
 

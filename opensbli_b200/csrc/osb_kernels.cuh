@@ -10,6 +10,7 @@
 //   k_periodic  exchange{n}_block0 ; k_dirichlet  Dirichlet boundary dir d side s
 #pragma once
 #include "osb_math.cuh"
+#include "osb_flux.cuh"
 
 namespace osb {
 
@@ -46,15 +47,20 @@ __global__ void __launch_bounds__(256) k_prim(GridDev g, FieldPtrs f, PhysConst 
   const int k = blockIdx.z;
   if (i >= n0 || j >= n1 || k >= n2) return;
   const long long x = g.off + (lo0 + i) + (ND > 1 ? (lo1 + j) * g.s[1] : 0) + (ND > 2 ? (lo2 + k) * g.s[2] : 0);
-  const double rho = f.q[0][x];
-  double ke = 0.0;
+  // all loads first: the output arrays may alias the inputs as far as the compiler knows
+  double q[ND + 2];
+#pragma unroll
+  for (int m = 0; m < ND + 2; m++) q[m] = __ldg(f.q[m] + x);
+  const double rho = q[0];
+  double ke = 0.0, u[ND];
 #pragma unroll
   for (int d = 0; d < ND; d++) {
-    const double u = f.q[1 + d][x] / rho;
-    f.u[d][x] = u;
-    ke += 0.5 * rho * u * u;
+    u[d] = q[1 + d] / rho;
+    ke += 0.5 * rho * u[d] * u[d];
   }
-  const double p = (c.gama - 1.0) * (f.q[ND + 1][x] - ke);
+  const double p = (c.gama - 1.0) * (q[ND + 1] - ke);
+#pragma unroll
+  for (int d = 0; d < ND; d++) f.u[d][x] = u[d];
   f.p[x] = p;
   f.a[x] = sqrt(c.gama * p / rho);
   f.T[x] = c.Minf * c.Minf * c.gama * p / rho;
@@ -167,6 +173,180 @@ __global__ void __launch_bounds__(32 * FLUX_TY) k_flux_yz(GridDev g, FieldPtrs f
 }
 
 // -------------------------------------------------------------------------------------------------
+// v2 flux sweeps: the block first stages its points (conserved variables + constituent relations evaluated once
+// per point: 1/rho, p, a) in shared memory, then every thread evaluates interface fluxes from the staged window,
+// parks them in shared memory and differences them.  Points are numbered along the sweep direction including 3
+// halo points on both sides (-3 .. np+2) and pencils are concatenated, so a block is simply a run of consecutive
+// staged points (x) or staged rows (y/z); consecutive blocks overlap by 6.
+// -------------------------------------------------------------------------------------------------
+template <int ND>
+__device__ __forceinline__ void stage_values(const double *q, double gama, double *sv, int VS) {
+  typedef SV<ND> V;
+  const double rho = q[0], E = q[ND + 1];
+  const double irho = 1.0 / rho;
+  double ke = 0.0;
+#pragma unroll
+  for (int d = 0; d < ND; d++) {
+    const double m = q[1 + d];
+    sv[(V::M0 + d) * VS] = m;
+    const double u = m * irho;
+    ke += 0.5 * rho * u * u;
+  }
+  const double p = (gama - 1.0) * (E - ke);
+  sv[V::RHO * VS] = rho; sv[V::IRHO * VS] = irho; sv[V::E * VS] = E; sv[V::P * VS] = p;
+  sv[V::A * VS] = sqrt(gama * p * irho);
+}
+
+template <int ND>
+__device__ __forceinline__ void stage_point(const FieldPtrs &f, long long x, double gama, double *sv, int VS) {
+  double q[ND + 2];
+#pragma unroll
+  for (int m = 0; m < ND + 2; m++) q[m] = __ldg(f.q[m] + x);
+  stage_values<ND>(q, gama, sv, VS);
+}
+
+constexpr int F2_BT = 128;            // x-sweep: staged points per block (BT-6 residual points)
+constexpr int F2_TY = 4;              // y/z sweeps: thread rows
+constexpr int F2_RT = 21;             // y/z sweeps: staged rows per block (RT-5 = 16 interface rows, RT-6 = 15 point rows)
+template <int ND> constexpr size_t f2_yz_smem_bytes() { return sizeof(double) * (SV<ND>::N + ND + 2) * F2_RT * 32; }
+
+template <int ND, int RECON, int AVG, bool ACCUM>
+__global__ void __launch_bounds__(F2_BT, 3) k_flux2_x(GridDev g, FieldPtrs f, PhysConst c, SchemeParams sp) {
+  constexpr int NV = ND + 2, NVAL = SV<ND>::N;
+  __shared__ double sP[NVAL][F2_BT];
+  __shared__ double sF[NV][F2_BT];
+  const int t = threadIdx.x;
+  const long long NPR = g.np[0] + 6;
+  const long long T = NPR * g.np[1] * g.np[2];
+  const long long fidx = (long long)blockIdx.x * (F2_BT - 6) + t;
+  const bool inside = fidx < T;
+  int ip = 0;
+  long long x = 0;
+  if (inside) {
+    ip = (int)(fidx % NPR) - 3;
+    const long long row = fidx / NPR;
+    const int j = (int)(row % g.np[1]), k = (int)(row / g.np[1]);
+    x = g.off + ip + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
+    stage_point<ND>(f, x, c.gama, &sP[0][t], F2_BT);
+  }
+  __syncthreads();
+  const bool iface = inside && t >= 2 && t <= F2_BT - 4 && ip >= -1 && ip <= g.np[0] - 1;
+  if (iface) {
+    double fl[NV];
+    interface_flux_staged<ND, 0, RECON, AVG>(&sP[0][t - 2], 1, F2_BT, c.gama, sp, fl);
+#pragma unroll
+    for (int m = 0; m < NV; m++) sF[m][t] = fl[m];
+  }
+  __syncthreads();
+  if (iface && t >= 3 && ip >= 0) {
+    double old[NV];
+    if (ACCUM) {
+#pragma unroll
+      for (int m = 0; m < NV; m++) old[m] = f.R[m][x];
+    }
+#pragma unroll
+    for (int m = 0; m < NV; m++) {
+      const double r = -c.inv[0] * (sF[m][t] - sF[m][t - 1]);
+      f.R[m][x] = ACCUM ? old[m] + r : r;
+    }
+  }
+}
+
+template <int ND, int DIR, int RECON, int AVG, bool ACCUM>
+__global__ void __launch_bounds__(32 * F2_TY, 3) k_flux2_yz(GridDev g, FieldPtrs f, PhysConst c, SchemeParams sp) {
+  constexpr int NV = ND + 2, NVAL = SV<ND>::N;
+  constexpr int OTH = (DIR == 1) ? 2 : 1;
+  extern __shared__ double f2_smem[];                       // dynamic: more than the 48 KB static limit
+  double (*sP)[F2_RT][32] = reinterpret_cast<double (*)[F2_RT][32]>(f2_smem);
+  double (*sF)[F2_RT][32] = reinterpret_cast<double (*)[F2_RT][32]>(f2_smem + NVAL * F2_RT * 32);
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i = blockIdx.y * 32 + tx;
+  const bool xin = i < g.np[0];
+  const long long NJR = g.np[DIR] + 6;
+  const long long nother = (ND > 2) ? g.np[OTH] : 1;
+  const long long TR = NJR * nother;
+  const long long r0 = (long long)blockIdx.x * (F2_RT - 6);
+  // stage RT rows: all loads are issued before the first use so their latencies overlap
+  {
+    constexpr int NIT = (F2_RT + F2_TY - 1) / F2_TY;
+    double raw[NIT][NV];
+    bool ok[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int r = ty + it * F2_TY;
+      const long long fr = r0 + r;
+      ok[it] = xin && r < F2_RT && fr < TR;
+      if (ok[it]) {
+        const int jp = (int)(fr % NJR) - 3;
+        const int o = (int)(fr / NJR);
+        const long long x = g.off + i + (long long)jp * g.s[DIR] + (ND > 2 ? o * g.s[OTH] : 0);
+#pragma unroll
+        for (int m = 0; m < NV; m++) raw[it][m] = __ldg(f.q[m] + x);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int r = ty + it * F2_TY;
+      if (ok[it]) stage_values<ND>(raw[it], c.gama, &sP[0][r][tx], F2_RT * 32);
+    }
+  }
+  __syncthreads();
+  // interface rows r = 2 .. RT-4
+#pragma unroll 1
+  for (int r = 2 + ty; r <= F2_RT - 4; r += F2_TY) {
+    const long long fr = r0 + r;
+    if (xin && fr < TR) {
+      const int jp = (int)(fr % NJR) - 3;
+      if (jp >= -1 && jp <= g.np[DIR] - 1) {
+        double fl[NV];
+        interface_flux_staged<ND, DIR, RECON, AVG>(&sP[0][r - 2][tx], 32, F2_RT * 32, c.gama, sp, fl);
+#pragma unroll
+        for (int m = 0; m < NV; m++) sF[m][r][tx] = fl[m];
+      }
+    }
+  }
+  __syncthreads();
+  // flux differences; when accumulating, all old residual values are fetched before the first store
+  // (the compiler must assume the Residual arrays alias and would otherwise serialise load-add-store chains)
+  {
+    constexpr int NIT = (F2_RT - 6 + F2_TY - 1) / F2_TY;
+    double old[NIT][NV];
+    long long xs[NIT];
+    bool ok[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int r = 3 + ty + it * F2_TY;
+      const long long fr = r0 + r;
+      ok[it] = false;
+      xs[it] = 0;
+      if (xin && r <= F2_RT - 4 && fr < TR) {
+        const int jp = (int)(fr % NJR) - 3;
+        if (jp >= 0 && jp <= g.np[DIR] - 1) {
+          const int o = (int)(fr / NJR);
+          xs[it] = g.off + i + (long long)jp * g.s[DIR] + (ND > 2 ? o * g.s[OTH] : 0);
+          ok[it] = true;
+          if (ACCUM) {
+#pragma unroll
+            for (int m = 0; m < NV; m++) old[it][m] = f.R[m][xs[it]];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int r = 3 + ty + it * F2_TY;
+      if (ok[it]) {
+#pragma unroll
+        for (int m = 0; m < NV; m++) {
+          const double rr = -c.inv[DIR] * (sF[m][r][tx] - sF[m][r - 1][tx]);
+          f.R[m][xs[it]] = ACCUM ? old[it][m] + rr : rr;
+        }
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // Central(4) skew-symmetric convective residual (scheme.py:187-271, parsing.py:75-111); R = conv
 // -------------------------------------------------------------------------------------------------
 template <int ND>
@@ -220,7 +400,7 @@ __device__ __forceinline__ double dev_dmix(const double *a, long long x, long lo
 }
 
 template <int ND>
-__global__ void __launch_bounds__(256) k_viscous(GridDev g, FieldPtrs f, PhysConst c) {
+__global__ void __launch_bounds__(256, 2) k_viscous(GridDev g, FieldPtrs f, PhysConst c) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const int k = blockIdx.z * blockDim.z + threadIdx.z;
@@ -249,7 +429,6 @@ __global__ void __launch_bounds__(256) k_viscous(GridDev g, FieldPtrs f, PhysCon
       }
     }
     vis[a] = iRe * s;
-    f.R[1 + a][x] += vis[a];
   }
   double lapT = 0.0;
 #pragma unroll
@@ -260,9 +439,14 @@ __global__ void __launch_bounds__(256) k_viscous(GridDev g, FieldPtrs f, PhysCon
 #pragma unroll
     for (int b = a + 1; b < ND; b++) { const double sab = dv[a][b] + dv[b][a]; e += iRe * sab * sab; }
     e += iRe * (2.0 * dv[a][a] - (2.0 / 3.0) * div) * dv[a][a];
-    e += vis[a] * f.u[a][x];
+    e += vis[a] * __ldg(f.u[a] + x);
   }
-  f.R[ND + 1][x] += e;
+  double old[ND + 1];
+#pragma unroll
+  for (int a = 0; a < ND + 1; a++) old[a] = f.R[1 + a][x];
+#pragma unroll
+  for (int a = 0; a < ND; a++) f.R[1 + a][x] = old[a] + vis[a];
+  f.R[ND + 1][x] = old[ND] + e;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -275,11 +459,14 @@ __global__ void __launch_bounds__(256) k_rk_ls(GridDev g, FieldPtrs f, double dt
   const int k = blockIdx.z;
   if (i >= g.np[0] || j >= g.np[1] || k >= g.np[2]) return;
   const long long x = g.off + i + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
+  double r[ND + 2], k_[ND + 2], q[ND + 2];
+#pragma unroll
+  for (int m = 0; m < ND + 2; m++) { r[m] = __ldg(f.R[m] + x); k_[m] = f.rk[m][x]; q[m] = f.q[m][x]; }
 #pragma unroll
   for (int m = 0; m < ND + 2; m++) {
-    const double t = dt * f.R[m][x] + A * f.rk[m][x];
+    const double t = dt * r[m] + A * k_[m];
     f.rk[m][x] = t;
-    f.q[m][x] = B * t + f.q[m][x];
+    f.q[m][x] = B * t + q[m];
   }
 }
 template <int ND>
@@ -289,11 +476,13 @@ __global__ void __launch_bounds__(256) k_rk_sbli(GridDev g, FieldPtrs f, double 
   const int k = blockIdx.z;
   if (i >= g.np[0] || j >= g.np[1] || k >= g.np[2]) return;
   const long long x = g.off + i + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
+  double r[ND + 2], o[ND + 2];
+#pragma unroll
+  for (int m = 0; m < ND + 2; m++) { r[m] = __ldg(f.R[m] + x); o[m] = f.rk[m][x]; }
 #pragma unroll
   for (int m = 0; m < ND + 2; m++) {
-    const double r = f.R[m][x], o = f.rk[m][x];
-    f.q[m][x] = dt * rknew * r + o;
-    f.rk[m][x] = dt * rkold * r + o;
+    f.q[m][x] = dt * rknew * r[m] + o[m];
+    f.rk[m][x] = dt * rkold * r[m] + o[m];
   }
 }
 template <int ND>
@@ -303,8 +492,11 @@ __global__ void __launch_bounds__(256) k_rk_save(GridDev g, FieldPtrs f) {
   const int k = blockIdx.z;
   if (i >= g.np[0] || j >= g.np[1] || k >= g.np[2]) return;
   const long long x = g.off + i + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
+  double q[ND + 2];
 #pragma unroll
-  for (int m = 0; m < ND + 2; m++) f.rk[m][x] = f.q[m][x];
+  for (int m = 0; m < ND + 2; m++) q[m] = f.q[m][x];
+#pragma unroll
+  for (int m = 0; m < ND + 2; m++) f.rk[m][x] = q[m];
 }
 
 // -------------------------------------------------------------------------------------------------

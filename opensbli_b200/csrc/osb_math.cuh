@@ -32,7 +32,19 @@ enum Averaging : int { AVG_SIMPLE = 0, AVG_ROE = 1 };
 struct SchemeParams {
   double eps;      // TENO eps (runtime constant `eps`, teno.py:358-365)
   double teno_ct;  // TENO cut-off C_T
+  // derived on the host by make_scheme_params():
+  double eps16;    // 16*eps: TENO5 works on g = 2f with beta'' = 16 beta(f)
+  double kfast5;   // 0.98 (3 C_T)^(-1/6): if 1 + tau/D_min <= kfast every TENO5 stencil passes the cut-off
+  double kfast6;   // 0.98 (4 C_T)^(-1/6): same for the 4 stencils of TENO6
 };
+
+inline SchemeParams make_scheme_params(double eps, double ct) {
+  SchemeParams s;
+  s.eps = eps; s.teno_ct = ct; s.eps16 = 16.0 * eps;
+  s.kfast5 = 0.98 * pow(3.0 * ct, -1.0 / 6.0);
+  s.kfast6 = 0.98 * pow(4.0 * ct, -1.0 / 6.0);
+  return s;
+}
 
 OSB_HD double sq(double x) { return x * x; }
 OSB_HD double pow6(double x) { double x2 = x * x; return x2 * x2 * x2; }
@@ -55,27 +67,63 @@ OSB_HD double inv_pow2(double m) {
 // side calls the same function on the mirrored window (p -> 1-p).  The value returned is the
 // reconstruction of 2*f (the 1/2 of the LLF splitting is applied by the caller through `half`).
 // ------------------------------------------------------------------------------------------------
-OSB_HD double teno5_side(double fm2, double fm1, double f0, double f1, double f2, const SchemeParams &sp) {
-  // smoothness indicators, teno.py:159-177
-  const double b0 = 0.25 * sq(fm1 - f1) + (13.0 / 12.0) * sq(fm1 - 2.0 * f0 + f1);
-  const double b1 = 0.25 * sq(3.0 * f0 - 4.0 * f1 + f2) + (13.0 / 12.0) * sq(f0 - 2.0 * f1 + f2);
-  const double b2 = 0.25 * sq(fm2 - 4.0 * fm1 + 3.0 * f0) + (13.0 / 12.0) * sq(fm2 - 2.0 * fm1 + f0);
-  const double tau = fabs(b0 - b2);                                   // teno.py:209
-  const double D0 = sp.eps + b0, D1 = sp.eps + b1, D2 = sp.eps + b2;
+// TENO5 on g = 2f (doubled split flux); the contribution of one side to Recon is the reconstruction of f = g/2,
+// sum_r omega_r q_r(f).  Split in a branch-free "front" (smoothness indicators, candidate polynomials, the cheap
+// sufficient test for "every stencil passes the cut-off") and a "resolve" step, so that the two sides of a wave are
+// scheduled together and share one branch.
+//   beta''_r = 16 beta_r(f) = A_r^2 + 13/3 B_r^2   (teno.py:159-177 scaled; eps scaled alike, so tau/(eps+beta) is unchanged)
+//   fast test: alpha_r >= 1 and sum(alpha) <= 3 alpha_max with alpha_max = (1 + tau/D_min)^6, hence
+//   alpha_r/sum >= 1/(3 alpha_max) >= C_T whenever 1 + tau/D_min <= (3 C_T)^(-1/6)  (2 % margin in kfast5).
+struct Teno5Side {
+  double D0, D1, D2, tau, Q0, Q1, Q2;
+  bool all_pass;
+};
+OSB_HD Teno5Side teno5_front(double gm2, double gm1, double g0, double g1, double g2, const SchemeParams &sp) {
+  Teno5Side t;
+  const double e0 = gm1 - gm2, e1 = g0 - gm1, e2 = g1 - g0, e3 = g2 - g1;        // first differences
+  const double A0 = e1 + e2, A1 = e3 - 3.0 * e2, A2 = 3.0 * e1 - e0;             // 2x first-derivative terms
+  const double B0 = e2 - e1, B1 = e3 - e2, B2 = e1 - e0;                          // second differences
+  const double c = 13.0 / 3.0;
+  const double b0 = (c * B0) * B0 + A0 * A0, b1 = (c * B1) * B1 + A1 * A1, b2 = (c * B2) * B2 + A2 * A2;
+  t.tau = fabs(b0 - b2);                                                          // teno.py:209
+  t.D0 = sp.eps16 + b0; t.D1 = sp.eps16 + b1; t.D2 = sp.eps16 + b2;
+  // 12 x candidate reconstructions (teno.py:113-114 times 6, times 2 for g = 2f)
+  t.Q0 = 5.0 * g0 + (2.0 * g1 - gm1);
+  t.Q1 = 5.0 * g1 + (2.0 * g0 - g2);
+  t.Q2 = 11.0 * g0 + (2.0 * gm2 - 7.0 * gm1);
+  const double Dmin = fmin(t.D0, fmin(t.D1, t.D2));
+  t.all_pass = (Dmin + t.tau <= sp.kfast5 * Dmin);
+  return t;
+}
+namespace teno5c {
+constexpr double d0 = 11.0 / 20.0, d1 = 2.0 / 5.0, d2 = 1.0 / 20.0;               // teno.py:133
+// 1/sum(d_r delta_r) takes one of 7 values (all-zero cannot happen: the largest alpha_r/sum is >= 1/3 > C_T);
+// evaluated in the order of the run-time sum, hence bit-identical to the division.
+constexpr double i111 = 1.0 / ((d0 + d1) + d2), i110 = 1.0 / ((d0 + d1) + 0.0), i101 = 1.0 / ((d0 + 0.0) + d2), i100 = 1.0 / ((d0 + 0.0) + 0.0);
+constexpr double i011 = 1.0 / ((0.0 + d1) + d2), i010 = 1.0 / ((0.0 + d1) + 0.0), i001 = 1.0 / ((0.0 + 0.0) + d2);
+}
+OSB_HD double teno5_linear(const Teno5Side &t) {
+  using namespace teno5c;
+  return i111 * ((d0 / 12.0) * t.Q0 + (d1 / 12.0) * t.Q1 + (d2 / 12.0) * t.Q2);
+}
+OSB_HD double teno5_resolve(const Teno5Side &t, const SchemeParams &sp) {
+  using namespace teno5c;
   // P_r = (D_r + tau) * prod_{s != r} D_s ; alpha_r = (P_r / (D0 D1 D2))^6   (teno.py:207-212, C=1, q=6)
-  const double P0 = (D0 + tau) * (D1 * D2), P1 = (D1 + tau) * (D0 * D2), P2 = (D2 + tau) * (D0 * D1);
+  const double P0 = (t.D0 + t.tau) * (t.D1 * t.D2), P1 = (t.D1 + t.tau) * (t.D0 * t.D2), P2 = (t.D2 + t.tau) * (t.D0 * t.D1);
   const double sc = inv_pow2(fmax(P0, fmax(P1, P2)));
-  const double A0 = pow6(P0 * sc), A1 = pow6(P1 * sc), A2 = pow6(P2 * sc);
-  const double thr = sp.teno_ct * (A0 + A1 + A2);                     // teno.py:445-465
-  const bool k0 = !(thr > A0), k1 = !(thr > A1), k2 = !(thr > A2);
-  // candidate (ENO) reconstructions, teno.py:113-114
-  const double q0 = (1.0 / 6.0) * (-fm1 + 5.0 * f0 + 2.0 * f1);
-  const double q1 = (1.0 / 6.0) * (2.0 * f0 + 5.0 * f1 - f2);
-  const double q2 = (1.0 / 6.0) * (2.0 * fm2 - 7.0 * fm1 + 11.0 * f0);
-  // omega_r = d_r delta_r / sum(d_s delta_s), d = (11/20, 4/10, 1/20)  (teno.py:133, 413-418)
-  const double w0 = k0 ? (11.0 / 20.0) : 0.0, w1 = k1 ? (2.0 / 5.0) : 0.0, w2 = k2 ? (1.0 / 20.0) : 0.0;
-  const double inv = 1.0 / (w0 + w1 + w2);
-  return inv * (w0 * q0 + w1 * q1 + w2 * q2);
+  const double a0 = pow6(P0 * sc), a1 = pow6(P1 * sc), a2 = pow6(P2 * sc);
+  const double thr = sp.teno_ct * (a0 + a1 + a2);                                 // teno.py:445-465
+  const bool k0 = !(thr > a0), k1 = !(thr > a1), k2 = !(thr > a2);
+  const double w0 = k0 ? (d0 / 12.0) : 0.0, w1 = k1 ? (d1 / 12.0) : 0.0, w2 = k2 ? (d2 / 12.0) : 0.0;
+  const double inv = k0 ? (k1 ? (k2 ? i111 : i110) : (k2 ? i101 : i100)) : (k1 ? (k2 ? i011 : i010) : i001);
+  return inv * (w0 * t.Q0 + w1 * t.Q1 + w2 * t.Q2);
+}
+// both sides of one characteristic wave: gp = CF + lam CS (right-biased), gm = CF - lam CS (left-biased, mirrored)
+OSB_HD double teno5_wave(const double *gp, const double *gm, const SchemeParams &sp) {
+  const Teno5Side tp = teno5_front(gp[0], gp[1], gp[2], gp[3], gp[4], sp);
+  const Teno5Side tm = teno5_front(gm[5], gm[4], gm[3], gm[2], gm[1], sp);
+  if (tp.all_pass && tm.all_pass) return teno5_linear(tp) + teno5_linear(tm);
+  return teno5_resolve(tp, sp) + teno5_resolve(tm, sp);
 }
 
 // TENO6 (teno.py:85-136, 165-177, 216-234).  `square_last` reproduces the reference's right-biased
@@ -141,10 +189,7 @@ OSB_HD double reconstruct(const double *cf, const double *cs, double lam, const 
   for (int p = 0; p < 6; p++) { gp[p] = cf[p] + lam * cs[p]; gm[p] = cf[p] - lam * cs[p]; }
   double r;
   if (RECON == RECON_TENO5) {
-    // TENO5 smoothness indicators act on f = g/2: beta(f) = beta(g)/4, tau likewise, so the ratio
-    // tau/(eps+beta) needs eps scaled by 4 when working with g.
-    SchemeParams s4 = sp; s4.eps = 4.0 * sp.eps;
-    r = teno5_side(gp[0], gp[1], gp[2], gp[3], gp[4], s4) + teno5_side(gm[5], gm[4], gm[3], gm[2], gm[1], s4);
+    return teno5_wave(gp, gm, sp);
   } else if (RECON == RECON_TENO6) {
     // beta_3 of the right-biased side is not homogeneous (linear last term): evaluate on f itself.
     double fp[6], fm[6];
@@ -158,6 +203,24 @@ OSB_HD double reconstruct(const double *cf, const double *cs, double lam, const 
     r = weno5_side<false>(gp[0], gp[1], gp[2], gp[3], gp[4]) + weno5_side<false>(gm[5], gm[4], gm[3], gm[2], gm[1]);
   }
   return 0.5 * r;
+}
+
+// Same, from the doubled split fluxes gp = CF + lam CS, gm = CF - lam CS already formed by the caller.
+template <int RECON>
+OSB_HD double reconstruct_g(const double *gp, const double *gm, const SchemeParams &sp) {
+  if (RECON == RECON_TENO5) {
+    return teno5_wave(gp, gm, sp);
+  } else if (RECON == RECON_TENO6) {
+    double fp[6], fm[6];
+#pragma unroll
+    for (int p = 0; p < 6; p++) { fp[p] = 0.5 * gp[p]; fm[p] = 0.5 * gm[p]; }
+    return teno6_side(fp[0], fp[1], fp[2], fp[3], fp[4], fp[5], sp, false) +
+           teno6_side(fm[5], fm[4], fm[3], fm[2], fm[1], fm[0], sp, true);
+  } else if (RECON == RECON_WENO5_Z) {
+    return 0.5 * (weno5_side<true>(gp[0], gp[1], gp[2], gp[3], gp[4]) + weno5_side<true>(gm[5], gm[4], gm[3], gm[2], gm[1]));
+  } else {
+    return 0.5 * (weno5_side<false>(gp[0], gp[1], gp[2], gp[3], gp[4]) + weno5_side<false>(gm[5], gm[4], gm[3], gm[2], gm[1]));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

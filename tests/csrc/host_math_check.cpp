@@ -2,6 +2,7 @@
 // inlines) for the HOST, so the restructured eigen-projections / division-free TENO cut-off can be checked
 // against the CPU oracle without a GPU.  Test infrastructure only; never loaded by the product.
 #include "../../opensbli_b200/csrc/osb_math.cuh"
+#include "../../opensbli_b200/csrc/osb_flux.cuh"
 
 using namespace osb;
 
@@ -21,6 +22,44 @@ static void run(const double *q6, double gama, double Minf, const SchemeParams &
   interface_flux<ND, DIR, RECON, AVG>(pt, gama, sp, flux);
 }
 
+// v2: staged layout [value][point], constituent relations evaluated while staging (as the sweep kernels do)
+template <int ND, int DIR, int RECON, int AVG>
+static void run_staged(const double *q6, double gama, const SchemeParams &sp, double *flux) {
+  typedef SV<ND> V;
+  double st[V::N * 6];
+  for (int p = 0; p < 6; p++) {
+    const double *q = q6 + p * (ND + 2);
+    const double irho = 1.0 / q[0];
+    double ke = 0.0;
+    for (int d = 0; d < ND; d++) { st[(V::M0 + d) * 6 + p] = q[1 + d]; const double u = q[1 + d] * irho; ke += 0.5 * q[0] * u * u; }
+    const double pr = (gama - 1.0) * (q[ND + 1] - ke);
+    st[V::RHO * 6 + p] = q[0]; st[V::IRHO * 6 + p] = irho; st[V::E * 6 + p] = q[ND + 1];
+    st[V::P * 6 + p] = pr; st[V::A * 6 + p] = sqrt(gama * pr * irho);
+  }
+  interface_flux_staged<ND, DIR, RECON, AVG>(st, 1, 6, gama, sp, flux);
+}
+
+template <int ND, int DIR>
+static int dispatch_staged(int recon, int avg, const double *q6, double gama, const SchemeParams &sp, double *flux) {
+#define CASE(R, A) if (recon == R && avg == A) { run_staged<ND, DIR, R, A>(q6, gama, sp, flux); return 0; }
+  CASE(RECON_WENO5_JS, AVG_SIMPLE) CASE(RECON_WENO5_JS, AVG_ROE) CASE(RECON_WENO5_Z, AVG_SIMPLE) CASE(RECON_WENO5_Z, AVG_ROE)
+  CASE(RECON_TENO5, AVG_SIMPLE) CASE(RECON_TENO5, AVG_ROE) CASE(RECON_TENO6, AVG_SIMPLE) CASE(RECON_TENO6, AVG_ROE)
+#undef CASE
+  return 1;
+}
+
+extern "C" int hostcheck_interface_flux_staged(int nd, int dir, int recon, int avg, const double *q6, double gama,
+                                               double eps, double ct, double *flux) {
+  SchemeParams sp = make_scheme_params(eps, ct);
+  if (nd == 1 && dir == 0) return dispatch_staged<1, 0>(recon, avg, q6, gama, sp, flux);
+  if (nd == 2 && dir == 0) return dispatch_staged<2, 0>(recon, avg, q6, gama, sp, flux);
+  if (nd == 2 && dir == 1) return dispatch_staged<2, 1>(recon, avg, q6, gama, sp, flux);
+  if (nd == 3 && dir == 0) return dispatch_staged<3, 0>(recon, avg, q6, gama, sp, flux);
+  if (nd == 3 && dir == 1) return dispatch_staged<3, 1>(recon, avg, q6, gama, sp, flux);
+  if (nd == 3 && dir == 2) return dispatch_staged<3, 2>(recon, avg, q6, gama, sp, flux);
+  return 1;
+}
+
 template <int ND, int DIR>
 static int dispatch(int recon, int avg, const double *q6, double gama, const SchemeParams &sp, double *flux) {
 #define CASE(R, A) if (recon == R && avg == A) { run<ND, DIR, R, A>(q6, gama, 0.0, sp, flux); return 0; }
@@ -32,7 +71,7 @@ static int dispatch(int recon, int avg, const double *q6, double gama, const Sch
 
 extern "C" int hostcheck_interface_flux(int nd, int dir, int recon, int avg, const double *q6, double gama,
                                         double eps, double ct, double *flux) {
-  SchemeParams sp; sp.eps = eps; sp.teno_ct = ct;
+  SchemeParams sp = make_scheme_params(eps, ct);
   if (nd == 1 && dir == 0) return dispatch<1, 0>(recon, avg, q6, gama, sp, flux);
   if (nd == 2 && dir == 0) return dispatch<2, 0>(recon, avg, q6, gama, sp, flux);
   if (nd == 2 && dir == 1) return dispatch<2, 1>(recon, avg, q6, gama, sp, flux);
