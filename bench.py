@@ -315,7 +315,7 @@ def main():
                 sim.set_state(q_in)
                 dsim.step(1)
                 for m, nme in enumerate(sim.q_names):
-                    q_out[m][...] = sim.download(nme)
+                    sim.download_into(nme, q_out[m])
             t = torch.tensor([sim.timer_stop()], dtype=torch.float64, device='cuda')
             barrier()
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -131,6 +131,12 @@ class Simulation(object):
         self._check(self.lib.osb_download(self.ctx, name.encode(), a.ctypes.data), 'osb_download')
         return a
 
+    def download_into(self, name, array):
+        """device -> caller-owned host array (e.g. pinned memory), no intermediate allocation."""
+        if array.shape != self.shape or array.dtype != np.float64 or not array.flags['C_CONTIGUOUS']:
+            raise ValueError('download_into needs a C-contiguous float64 array of shape %s' % (self.shape,))
+        self._check(self.lib.osb_download(self.ctx, name.encode(), array.ctypes.data), 'osb_download')
+
     def set_state(self, q):
         for n, a in zip(self.q_names, q):
             self.upload(n, a)
