@@ -76,13 +76,125 @@ static void bc_dirichlet(const osbo_cfg *c, const grid_t *g, double *const *q, i
     for (int k = lo[2]; k < hi[2]; k++) for (int j = lo[1]; j < hi[1]; j++) for (int i = lo[0]; i < hi[0]; i++)
       q[m][gidx(g, i, j, k)] = c->bc_q[dir][side][m];
 }
+/* plane loop helper: boundary plane of (dir, side), tangential range = block + scheme halos (bc_core.py:158-198) */
+#define PLANE_LOOP(c, g, dir, side, ...)                                                               \
+  {                                                                                                    \
+    int hm_, hp_; scheme_halos(c, &hm_, &hp_);                                                         \
+    int lo_[3] = {0, 0, 0}, hi_[3] = {1, 1, 1};                                                        \
+    for (int d_ = 0; d_ < (g)->ndim; d_++) { lo_[d_] = -hm_; hi_[d_] = (g)->np[d_] + hp_; }            \
+    lo_[dir] = (side) == 0 ? 0 : (g)->np[dir] - 1; hi_[dir] = lo_[dir] + 1;                            \
+    for (int k = lo_[2]; k < hi_[2]; k++) for (int j = lo_[1]; j < hi_[1]; j++) for (int i = lo_[0]; i < hi_[0]; i++) { \
+      const long x = gidx(g, i, j, k); (void)x; __VA_ARGS__                                                   \
+    }                                                                                                  \
+  }
+
+/* dirichlet.py:28-41 with equations that depend on the tangential position (e.g. the shock generator of
+ * apps/katzer_SBLI/katzer_SBLI.py:101-106): values come from a per-face table [nv][padded tangential extent]. */
+static void bc_dirichlet_field(const osbo_cfg *c, const grid_t *g, double *const *q, int dir, int side) {
+  int hm, hp; scheme_halos(c, &hm, &hp);
+  const int n = side == 0 ? hm : hp;
+  const long sd = g->s[dir];
+  /* tangential linear index = padded index with dimension dir removed */
+  long ts[3] = {0, 0, 0}, acc = 1;
+  for (int d = 0; d < g->ndim; d++) if (d != dir) { ts[d] = acc; acc *= g->pd[d]; }
+  const double *tab = c->bc_face[dir][side];
+  PLANE_LOOP(c, g, dir, side, {
+    int id[3] = {i, j, k};
+    long t = 0;
+    for (int d = 0; d < g->ndim; d++) if (d != dir) t += ts[d] * (id[d] + g->h);
+    for (int m = 0; m < g->nv; m++)
+      for (int h = 0; h <= n; h++) q[m][x + (side == 0 ? -h : h) * sd] = tab[m * acc + t];
+  })
+}
+/* extrapolation.py:29-58 */
+static void bc_extrapolation(const osbo_cfg *c, const grid_t *g, double *const *q, int dir, int side) {
+  int hm, hp; scheme_halos(c, &hm, &hp);
+  const int n = side == 0 ? hm : hp;
+  const long out = (side == 0 ? -1 : 1) * g->s[dir], in = -out;
+  PLANE_LOOP(c, g, dir, side, {
+    for (int m = 0; m < g->nv; m++) {
+      if (c->extrap_order[dir][side] == 0) {
+        for (int h = 0; h <= n; h++) q[m][x + h * out] = q[m][x + in];
+      } else {
+        for (int h = 1; h <= n; h++) q[m][x + h * out] = 2.0 * q[m][x + (h - 1) * out] - q[m][x + (h - 2) * out];
+      }
+    }
+  })
+}
+/* inlet_pressure_extrapolate.py:32-66 (side 0 only) */
+static void bc_inlet_pressure(const osbo_cfg *c, const grid_t *g, double *const *q, int dir, int side) {
+  int hm, hp; scheme_halos(c, &hm, &hp);
+  const int nd = g->ndim;
+  const long sd = g->s[dir];
+  (void)side; (void)hp;
+  PLANE_LOOP(c, g, dir, 0, {
+    double rhob = q[0][x], ub[3] = {0, 0, 0}, ke = 0.0;
+    for (int d = 0; d < nd; d++) { ub[d] = fabs(q[1 + d][x] / q[0][x]); ke += ub[d] * ub[d]; }
+    double pb = (c->gama - 1.0) * (-0.5 * rhob * ke + q[nd + 1][x]);
+    double ab = sqrt(c->gama * pb / rhob);
+    int sup = ub[dir] >= ab;
+    for (int m = 0; m < g->nv; m++) q[m][x] = sup ? q[m][x - sd] : q[m][x];
+    for (int h = 1; h <= hm; h++) q[nd + 1][x - h * sd] = sup ? q[nd + 1][x - h * sd] : q[nd + 1][x];
+  })
+}
+/* isothermal_wall.py:32-88: no-slip wall at fixed temperature; halo states from wall pressure and a linearly
+ * extrapolated temperature, velocities reflected. */
+static void bc_isothermal_wall(const osbo_cfg *c, const grid_t *g, double *const *q, int dir, int side) {
+  int hm, hp; scheme_halos(c, &hm, &hp);
+  const int nd = g->ndim, n = side == 0 ? hm : hp;
+  const long out = (side == 0 ? -1 : 1) * g->s[dir], in = -out;
+  const double gm = c->gama, M2 = c->Minf * c->Minf;
+  PLANE_LOOP(c, g, dir, side, {
+    for (int d = 0; d < nd; d++) q[1 + d][x] = 0.0;
+    q[nd + 1][x] = q[0][x] * c->Twall / (gm * (gm - 1.0) * M2);
+    double ke = 0.0;
+    for (int d = 0; d < nd; d++) ke += 0.5 * q[1 + d][x] * q[1 + d][x];
+    const double Pw = (gm - 1.0) * (-ke / q[0][x] + q[nd + 1][x]);
+    const long xa = x + in;
+    double kea = 0.0;
+    for (int d = 0; d < nd; d++) kea += 0.5 * q[1 + d][xa] * q[1 + d][xa];
+    const double Ta = M2 * gm * (gm - 1.0) * (-kea / q[0][xa] + q[nd + 1][xa]) / q[0][xa];
+    for (int h = 1; h <= n; h++) {
+      const long xi = x + h * in, xo = x + h * out;
+      const double Th = (h + 1) * c->Twall - h * Ta;
+      const double rh = M2 * gm * Pw / Th;
+      double u2 = 0.0;
+      double uu[3];
+      for (int d = 0; d < nd; d++) { uu[d] = q[1 + d][xi] / q[0][xi]; u2 += uu[d] * uu[d]; }
+      q[0][xo] = rh;
+      for (int d = 0; d < nd; d++) q[1 + d][xo] = -rh * uu[d];
+      q[nd + 1][xo] = Pw / (gm - 1.0) + 0.5 * rh * u2;
+    }
+  })
+}
+/* symmetry.py:23-50 (cartesian: unit normal e_dir): halos mirror the interior with the normal momentum reversed */
+static void bc_symmetry(const osbo_cfg *c, const grid_t *g, double *const *q, int dir, int side) {
+  int hm, hp; scheme_halos(c, &hm, &hp);
+  const int n = side == 0 ? hm : hp;
+  const long out = (side == 0 ? -1 : 1) * g->s[dir], in = -out;
+  PLANE_LOOP(c, g, dir, side, {
+    for (int h = 1; h <= n; h++)
+      for (int m = 0; m < g->nv; m++) {
+        const double v = q[m][x + h * in];
+        q[m][x + h * out] = (m == 1 + dir) ? v - 2.0 * v : v;
+      }
+  })
+}
 /* order: dir0 side0, dir0 side1, dir1 side0 ...  (block.py:199-210, algorithm.py:440-442) */
 void osbo_apply_bcs(const osbo_cfg *c, double *const *q) {
   grid_t g; grid_init(c, &g);
   for (int d = 0; d < c->ndim; d++)
     for (int s = 0; s < 2; s++) {
-      if (c->bc[d][s] == OSBO_BC_PERIODIC) bc_periodic(c, &g, q, d, s);
-      else if (c->bc[d][s] == OSBO_BC_DIRICHLET) bc_dirichlet(c, &g, q, d, s);
+      switch (c->bc[d][s]) {
+        case OSBO_BC_PERIODIC: bc_periodic(c, &g, q, d, s); break;
+        case OSBO_BC_DIRICHLET: bc_dirichlet(c, &g, q, d, s); break;
+        case OSBO_BC_DIRICHLET_FIELD: bc_dirichlet_field(c, &g, q, d, s); break;
+        case OSBO_BC_EXTRAPOLATION: bc_extrapolation(c, &g, q, d, s); break;
+        case OSBO_BC_INLET_PRESSURE_EXTRAPOLATE: bc_inlet_pressure(c, &g, q, d, s); break;
+        case OSBO_BC_ISOTHERMAL_WALL: bc_isothermal_wall(c, &g, q, d, s); break;
+        case OSBO_BC_SYMMETRY: bc_symmetry(c, &g, q, d, s); break;
+        default: break;
+      }
     }
 }
 
@@ -91,7 +203,7 @@ void osbo_apply_bcs(const osbo_cfg *c, double *const *q) {
  *   u_i = rhou_i/rho ; p = (gama-1)(rhoE - 1/2 rho u_i u_i) ; a = sqrt(gama p/rho) ; T = gama Minf^2 p/rho
  * evaluated over grid + scheme halos (opensbliequations.py:297-321).
  * ------------------------------------------------------------------------------------------- */
-typedef struct { double *u[3], *p, *a, *T; } prim_t;
+typedef struct { double *u[3], *p, *a, *T, *mu; } prim_t;
 
 static void constituent(const osbo_cfg *c, const grid_t *g, double *const *q, prim_t *P) {
   int hm, hp; scheme_halos(c, &hm, &hp);
@@ -106,6 +218,10 @@ static void constituent(const osbo_cfg *c, const grid_t *g, double *const *q, pr
     P->p[x] = p;
     P->a[x] = sqrt(c->gama * p / rho);
     P->T[x] = c->Minf * c->Minf * c->gama * p / rho;
+    /* viscosity laws of the apps: Sutherland katzer_SBLI.py:25, power law compressible_TCF_TENO/turbulent_channel.py:29 */
+    if (c->visc_law == OSBO_MU_SUTHERLAND) P->mu[x] = (c->SuthT / c->RefT + 1.0) * pow(P->T[x], 1.5) / (c->SuthT / c->RefT + P->T[x]);
+    else if (c->visc_law == OSBO_MU_POWER) P->mu[x] = pow(P->T[x], c->mu_exp);
+    else P->mu[x] = 1.0;
   }
 }
 
@@ -267,9 +383,15 @@ static inline double eigenvalue(int nd, int j, double ud, double a) {
  * interfaces i+1/2, i = -1 .. np_d-1 (the reference also evaluates i = np_d, which nothing consumes).
  * Output wk[m] = flux component m at interface i+1/2 stored at point i.
  * ------------------------------------------------------------------------------------------- */
+/* adaptive TENO cut-off from the sensor (teno.py:430-443): C_T = 10^-floor(a1 - a2 (1 - (1-theta)^4 (1+4 theta))) */
+static double adaptive_ct(const osbo_cfg *c, double th) {
+  double om = 1.0 - th;
+  return pow(10.0, -floor(c->teno_a1 - c->teno_a2 * (-(om * om) * (om * om) * (4.0 * th + 1.0) + 1.0)));
+}
+
 /* one interface: stencil data for the 6 points p = 0..5 <-> offsets -2..3 */
 static void interface_flux(const osbo_cfg *c, int nd, int dir, double qs[6][5], double us[6][3],
-                           const double *ps, const double *as, double *flux) {
+                           const double *ps, const double *as, double teno_ct, double *flux) {
   const int nv = nd + 2;
   const double gm1 = c->gama - 1.0;
   /* interface state between points 2 and 3 (averaging.py:31-59 simple, :62-114 Roe) */
@@ -308,7 +430,7 @@ static void interface_flux(const osbo_cfg *c, int nd, int dir, double qs[6][5], 
   for (int jj = 0; jj < nv; jj++) {
     double fp[6], fm[6];
     for (int p = 0; p < 6; p++) { fp[p] = 0.5 * (CF[jj][p] + lam[jj] * CS[jj][p]); fm[p] = 0.5 * (CF[jj][p] - lam[jj] * CS[jj][p]); }
-    if (c->conv == OSBO_CONV_TENO) rec[jj] = c->order == 6 ? osbo_recon_teno6(fp, fm, c->eps, c->teno_ct) : osbo_recon_teno5(fp, fm, c->eps, c->teno_ct);
+    if (c->conv == OSBO_CONV_TENO) rec[jj] = c->order == 6 ? osbo_recon_teno6(fp, fm, c->eps, teno_ct) : osbo_recon_teno5(fp, fm, c->eps, teno_ct);
     else rec[jj] = osbo_recon_weno5(fp, fm, c->weno_z);
   }
   for (int m = 0; m < nv; m++) {
@@ -329,7 +451,7 @@ void osbo_interface_flux(const osbo_cfg *c, int dir, const double *q6, double *f
     ps[p] = (c->gama - 1.0) * (qs[p][nd + 1] - ke);
     as[p] = sqrt(c->gama * ps[p] / qs[p][0]);
   }
-  interface_flux(c, nd, dir, qs, us, ps, as, flux);
+  interface_flux(c, nd, dir, qs, us, ps, as, c->teno_ct, flux);
 }
 
 static void llf_flux(const osbo_cfg *c, const grid_t *g, int dir, double *const *q, const prim_t *P, double **wk) {
@@ -347,7 +469,12 @@ static void llf_flux(const osbo_cfg *c, const grid_t *g, int dir, double *const 
       for (int d = 0; d < nd; d++) us[p][d] = P->u[d][xp];
       ps[p] = P->p[xp]; as[p] = P->a[xp];
     }
-    interface_flux(c, nd, dir, qs, us, ps, as, fl);
+    double ct = c->teno_ct;
+    if (c->teno_adaptive) {          /* sensor value of the interface's left point; halo points hold 0 */
+      ct = adaptive_ct(c, c->theta[x]);
+      if (dir == 0 && c->teno_store) c->teno_store[x] = ct;
+    }
+    interface_flux(c, nd, dir, qs, us, ps, as, ct, fl);
     for (int m = 0; m < nv; m++) wk[m][x] = fl[m];
   }
 }
@@ -361,22 +488,139 @@ static inline double d2c(const double *f, long x, long s, double inv2) {
   return (1.0 / 12.0) * inv2 * (-f[x - 2 * s] + 16.0 * f[x - s] - 30.0 * f[x] + 16.0 * f[x + s] - f[x + 2 * s]);
 }
 
+/* Central derivative with the one-sided boundary closure selected by the grid index along the derivative
+ * direction (opensblifunctions.py:523-534 modify_boundary_formula; reduced_access_scheme.py:36-83,
+ * Carpenter_scheme.py:38-102).  Closure tables hold, for the rows idx = 0..nr-1 next to side 0, the weights of the
+ * boundary-absolute points 0..np-1; side 1 mirrors them (sign -1 for first derivatives). */
+static double d1g(const osbo_cfg *c, const double *f, long x, long s, double inv, int dir, int idx, int n) {
+  if (c->closure[dir][0] && idx < c->c_nr1) {
+    double r = 0.0; const long x0 = x - idx * s;
+    for (int p = 0; p < c->c_np1; p++) r += c->c_d1[idx * c->c_np1 + p] * f[x0 + p * s];
+    return inv * r;
+  }
+  if (c->closure[dir][1] && n - 1 - idx < c->c_nr1) {
+    const int row = n - 1 - idx; double r = 0.0; const long x0 = x + row * s;
+    for (int p = 0; p < c->c_np1; p++) r -= c->c_d1[row * c->c_np1 + p] * f[x0 - p * s];
+    return inv * r;
+  }
+  return d1c(f, x, s, inv);
+}
+static double d2g(const osbo_cfg *c, const double *f, long x, long s, double inv2, int dir, int idx, int n) {
+  if (c->closure[dir][0] && idx < c->c_nr2) {
+    double r = 0.0; const long x0 = x - idx * s;
+    for (int p = 0; p < c->c_np2; p++) r += c->c_d2[idx * c->c_np2 + p] * f[x0 + p * s];
+    return inv2 * r;
+  }
+  if (c->closure[dir][1] && n - 1 - idx < c->c_nr2) {
+    const int row = n - 1 - idx; double r = 0.0; const long x0 = x + row * s;
+    for (int p = 0; p < c->c_np2; p++) r += c->c_d2[row * c->c_np2 + p] * f[x0 - p * s];
+    return inv2 * r;
+  }
+  return d2c(f, x, s, inv2);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * General viscous terms: variable viscosity, stretched (diagonal-metric) grid, one-sided closures.
+ * With  d_j f = D_jj delta_j f ,  d_jj f = D_jj^2 delta_jj f + D_jj SD_jjj delta_j f ,
+ *       d_ij f = D_ii D_jj delta_out(delta_in f)  (in = lower, out = higher direction; metric.py:72-135,
+ *       opensblifunctions.py:540-549) and S_ij = d_j u_i + d_i u_j - 2/3 delta_ij div u  the reference expands
+ * (app strings, e.g. katzer_SBLI.py:10-14; StoreSome.py:71-161):
+ *   momentum_i += 1/Re [ sum_j d_j mu S_ij + mu ( sum_j d_jj u_i + 1/3 sum_j d_ij u_j ) ]
+ *   energy     += kq [ sum_j d_j mu d_j T + mu sum_j d_jj T ] + sum_i u_i (momentum_i term) + mu/Re sum_ij S_ij d_j u_i
+ * ------------------------------------------------------------------------------------------- */
+static void viscous_general(const osbo_cfg *c, const grid_t *g, const prim_t *P, double *const *R,
+                            double *dv[5][3], const double *inv, const double *inv2) {
+  const int nd = g->ndim;
+  /* stored xi-derivatives of u_v (v < nd), T (v = nd): over ranges widened by +-2 in the other directions */
+  for (int v = 0; v < nd + 1; v++) {
+    const double *f = v < nd ? P->u[v] : P->T;
+    for (int d = 0; d < nd; d++) {
+      int l[3] = {0, 0, 0}, hh[3] = {1, 1, 1};
+      for (int e = 0; e < nd; e++) { l[e] = -2; hh[e] = g->np[e] + 2; }
+      l[d] = 0; hh[d] = g->np[d];
+      for (int k = l[2]; k < hh[2]; k++) for (int j = l[1]; j < hh[1]; j++) for (int i = l[0]; i < hh[0]; i++) {
+        long x = gidx(g, i, j, k);
+        int id[3] = {i, j, k};
+        dv[v][d][x] = d1g(c, f, x, g->s[d], inv[d], d, id[d], g->np[d]);
+      }
+    }
+  }
+  const double iRe = 1.0 / c->Re;
+  const double kq = iRe * (1.0 / (c->gama - 1.0)) * pow(c->Minf, -2) * (1.0 / c->Pr);
+  for (int k = 0; k < g->np[2]; k++) for (int j = 0; j < g->np[1]; j++) for (int i = 0; i < g->np[0]; i++) {
+    long x = gidx(g, i, j, k);
+    int id[3] = {i, j, k};
+    double Dm[3], SDm[3], dmu[3], du[3][3], dT[3];
+    for (int d = 0; d < nd; d++) {
+      Dm[d] = c->D[d] ? c->D[d][x] : 1.0;
+      SDm[d] = c->SD[d] ? c->SD[d][x] : 0.0;
+      dmu[d] = c->visc_law == OSBO_MU_CONSTANT ? 0.0 : Dm[d] * d1g(c, P->mu, x, g->s[d], inv[d], d, id[d], g->np[d]);
+      dT[d] = Dm[d] * dv[nd][d][x];
+      for (int a = 0; a < nd; a++) du[a][d] = Dm[d] * dv[a][d][x];
+    }
+    double div = 0.0;
+    for (int a = 0; a < nd; a++) div += du[a][a];
+    const double mu = P->mu[x];
+    double vis[3] = {0, 0, 0}, e = 0.0;
+    for (int a = 0; a < nd; a++) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int b = 0; b < nd; b++) {
+        double Sab = du[a][b] + du[b][a] - (a == b ? (2.0 / 3.0) * div : 0.0);
+        s1 += dmu[b] * Sab;
+        double lap = Dm[b] * Dm[b] * d2g(c, P->u[a], x, g->s[b], inv2[b], b, id[b], g->np[b]) + Dm[b] * SDm[b] * dv[a][b][x];
+        if (b == a) s2 += (4.0 / 3.0) * lap;
+        else {
+          s2 += lap;
+          int in = a < b ? a : b, out = a < b ? b : a;
+          s2 += (1.0 / 3.0) * Dm[a] * Dm[b] * d1g(c, dv[b][in], x, g->s[out], inv[out], out, id[out], g->np[out]);
+        }
+        e += iRe * mu * Sab * du[a][b];
+      }
+      vis[a] = iRe * (s1 + mu * s2);
+      R[1 + a][x] += vis[a];
+      e += vis[a] * P->u[a][x];
+    }
+    double hT = 0.0;
+    for (int d = 0; d < nd; d++)
+      hT += dmu[d] * dT[d] + mu * (Dm[d] * Dm[d] * d2g(c, P->T, x, g->s[d], inv2[d], d, id[d], g->np[d]) + Dm[d] * SDm[d] * dv[nd][d][x]);
+    R[nd + 1][x] += kq * hT + e;
+  }
+}
+
 /* ---------------------------------------------------------------------------------------------
  * Spatial residual = what the stage's "spatial kernels" leave in Residual_m
  * ------------------------------------------------------------------------------------------- */
 void osbo_residual(const osbo_cfg *c, double *const *q, double *const *R) {
   grid_t g; grid_init(c, &g);
   const int nd = g.ndim, nv = g.nv;
-  double *buf = (double *)calloc((size_t)g.n * (6 + 15 + 12), sizeof(double));
+  double *buf = (double *)calloc((size_t)g.n * (7 + 15 + 15), sizeof(double));
   prim_t P; double *w = buf;
   for (int d = 0; d < 3; d++) { P.u[d] = w; w += g.n; }
-  P.p = w; w += g.n; P.a = w; w += g.n; P.T = w; w += g.n;
+  P.p = w; w += g.n; P.a = w; w += g.n; P.T = w; w += g.n; P.mu = w; w += g.n;
   double *wk[3][5]; for (int d = 0; d < 3; d++) for (int m = 0; m < 5; m++) { wk[d][m] = w; w += g.n; }
-  double *dv[4][3]; for (int v = 0; v < 4; v++) for (int d = 0; d < 3; d++) { dv[v][d] = w; w += g.n; }
+  double *dv[5][3]; for (int v = 0; v < 5; v++) for (int d = 0; d < 3; d++) { dv[v][d] = w; w += g.n; }
   double inv[3], inv2[3];
   for (int d = 0; d < nd; d++) { inv[d] = 1.0 / c->delta[d]; inv2[d] = pow(c->delta[d], -2); }
 
   constituent(c, &g, q, &P);
+  int general = c->visc_law != OSBO_MU_CONSTANT;
+  for (int d = 0; d < nd; d++) if (c->D[d] || c->closure[d][0] || c->closure[d][1]) general = 1;
+
+  if (c->teno_adaptive) {
+    /* modified Ducros sensor (shock_sensors.py:12-49), evaluated on the interior only */
+    for (int k = 0; k < g.np[2]; k++) for (int j = 0; j < g.np[1]; j++) for (int i = 0; i < g.np[0]; i++) {
+      long x = gidx(&g, i, j, k);
+      int id[3] = {i, j, k};
+      double du[3][3];
+      for (int a = 0; a < nd; a++) for (int b = 0; b < nd; b++)
+        du[a][b] = d1g(c, P.u[a], x, g.s[b], inv[b], b, id[b], g.np[b]) * (c->D[b] ? c->D[b][x] : 1.0);
+      double div = 0.0, vort = 0.0;
+      for (int a = 0; a < nd; a++) div += du[a][a];
+      if (nd == 2) vort = (du[1][0] - du[0][1]) * (du[1][0] - du[0][1]);
+      else if (nd == 3) vort = (du[2][1] - du[1][2]) * (du[2][1] - du[1][2]) + (du[0][2] - du[2][0]) * (du[0][2] - du[2][0]) + (du[1][0] - du[0][1]) * (du[1][0] - du[0][1]);
+      c->theta[x] = (0.5 - 0.5 * tanh(2.5 + 250.0 * div)) * div * div / (c->sensor_eps + div * div + vort);
+    }
+  }
 
   if (c->conv != OSBO_CONV_CENTRAL) {
     for (int d = 0; d < nd; d++) llf_flux(c, &g, d, q, &P, wk[d]);
@@ -385,7 +629,7 @@ void osbo_residual(const osbo_cfg *c, double *const *q, double *const *R) {
       long x = gidx(&g, i, j, k);
       for (int m = 0; m < nv; m++) {
         double r = 0.0;
-        for (int d = 0; d < nd; d++) r -= inv[d] * (wk[d][m][x] - wk[d][m][x - g.s[d]]);
+        for (int d = 0; d < nd; d++) r -= inv[d] * (wk[d][m][x] - wk[d][m][x - g.s[d]]) * (c->D[d] ? c->D[d][x] : 1.0);
         R[m][x] = r;
       }
     }
@@ -421,7 +665,8 @@ void osbo_residual(const osbo_cfg *c, double *const *q, double *const *R) {
     }
   }
 
-  if (c->viscous) {
+  if (c->viscous && general) viscous_general(c, &g, &P, R, dv, inv, inv2);
+  if (c->viscous && !general) {
     /* Stored first derivatives d(u_v)/dx_d, d(T)/dx_d over ranges widened by +-2 in the other directions
      * (StoreSome.py:85-134 "Derivative evaluation"; scheme.py:256-267 "Viscous CD"). */
     int lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};

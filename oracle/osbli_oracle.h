@@ -34,7 +34,10 @@ extern "C" {
 enum { OSBO_CONV_CENTRAL = 0, OSBO_CONV_WENO = 1, OSBO_CONV_TENO = 2 };
 enum { OSBO_AVG_SIMPLE = 0, OSBO_AVG_ROE = 1 };
 enum { OSBO_RK_SBLI = 0, OSBO_RK_LS = 1 };
-enum { OSBO_BC_PERIODIC = 0, OSBO_BC_DIRICHLET = 1, OSBO_BC_EXCHANGE = 2 /* halo filled by the caller (decomposed run) */ };
+enum { OSBO_BC_PERIODIC = 0, OSBO_BC_DIRICHLET = 1, OSBO_BC_EXCHANGE = 2 /* halo filled by the caller (decomposed run) */,
+       OSBO_BC_ISOTHERMAL_WALL = 3, OSBO_BC_EXTRAPOLATION = 4, OSBO_BC_INLET_PRESSURE_EXTRAPOLATE = 5,
+       OSBO_BC_SYMMETRY = 6, OSBO_BC_DIRICHLET_FIELD = 7 /* imposed state varies along the face */ };
+enum { OSBO_MU_CONSTANT = 0, OSBO_MU_SUTHERLAND = 1, OSBO_MU_POWER = 2 };
 
 typedef struct {
   int ndim;
@@ -53,6 +56,22 @@ typedef struct {
   double delta[3];
   int bc[3][2];
   double bc_q[3][2][5]; /* Dirichlet: conservative state imposed on boundary + halo points */
+  /* ---- general path: stretched grids, variable viscosity, one-sided closures, wall/inflow/outflow BCs,
+   *      adaptive TENO (BASELINE config 4, apps/katzer_SBLI) ---- */
+  int visc_law;               /* OSBO_MU_*: mu = 1 | T^1.5 (1+S/Tr)/(T+S/Tr) | T^mu_exp */
+  double SuthT, RefT, mu_exp;
+  const double *D[3];         /* D_dd = d xi_d / d x_d (padded array) or NULL: direction not stretched (metric.py:137-147) */
+  const double *SD[3];        /* SD_ddd (second-derivative metric, metric.py:149-212) or NULL */
+  int closure[3][2];          /* 1: central derivatives switch to the one-sided closure near this face */
+  int c_nr1, c_np1, c_nr2, c_np2;       /* closure tables: rows x points (boundary-absolute points 0..np-1) */
+  double c_d1[4 * 6], c_d2[2 * 6];      /* ReducedAccess: 2x5, 2x5; Carpenter: 4x6, 2x5 */
+  int teno_adaptive;          /* C_T from the Ducros sensor (teno.py:430-443) */
+  double teno_a1, teno_a2, sensor_eps;
+  double *theta;              /* sensor array (padded, written by the residual evaluation) or NULL */
+  double *teno_store;         /* optional output of C_T of the direction-0 sweep ('TENO' dataset) or NULL */
+  double Twall;
+  int extrap_order[3][2];
+  const double *bc_face[3][2];/* OSBO_BC_DIRICHLET_FIELD: [nv][padded tangential extent] */
 } osbo_cfg;
 
 /* number of doubles of one padded array */

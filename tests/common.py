@@ -27,8 +27,25 @@ def fixtures():
 def load_fixture(name):
     z = np.load(os.path.join(GOLDEN, name + '.npz'))
     plan = json.loads(str(z['plan']))
-    states = {int(k[1:]): z[k] for k in z.files if k.startswith('q')}
+    states = {int(k[1:]): z[k] for k in z.files if k.startswith('q') and k[1:].isdigit()}
+    # general-path fixtures carry metric fields, a Dirichlet table and the padded initial state
+    fields = {k[6:]: z[k] for k in z.files if k.startswith('field_')}
+    if fields:
+        plan['fields'] = fields
+    for k in z.files:
+        if k.startswith('bc_table_'):
+            d, s = int(k.split('_')[2]), int(k.split('_')[3])
+            plan['bc'][d][s]['table'] = z[k]
+    if 'q0_padded' in z.files:
+        plan['q0_padded'] = z['q0_padded']
     return plan, states
+
+
+def initial_padded(plan, states):
+    """padded initial state: the stored one if the halos matter (general path), else zero-padded interior."""
+    if 'q0_padded' in plan:
+        return [np.array(a, dtype=np.float64, order='C', copy=True) for a in plan['q0_padded']]
+    return pad(plan, states[0])
 
 
 def pad(plan, q_inner, halo=5):

@@ -51,8 +51,50 @@ FIXTURES = {
 }
 
 
+def ssp_rk3():
+    """RungeKuttaLS(3, formulation='SSP') coefficients, rk_LS.py:74-89."""
+    from math import sqrt
+    c = 0.924574
+    z1 = float(sqrt(36*c**4 + 36*c**3 - 135*c**2 + 84*c - 12))
+    z2 = float(2*c**2 + c - 2)
+    z3 = float(12*c**4 - 18*c**3 + 18*c**2 - 11*c + 2)
+    z4 = float(36*c**4 - 36*c**3 + 13*c**2 - 8*c + 4)
+    z5 = float(69*c**3 - 62*c**2 + 28*c - 8)
+    z6 = float(34*c**4 - 46*c**3 + 34*c**2 - 13*c + 2)
+    B = [0.924574, (12*c*(c-1)*(3*z2-z1) - (3*z2-z1)**2)/(144*c*(3*c-2)*(c-1)**2),
+         (-24*(3*c-2)*(c-1)**2)/((3*z2-z1)**2 - 12*c*(c-1)*(3*z2-z1))]
+    A = [0.0, (-z1*(6*c**2 - 4*c + 1) + 3*z3)/((2*c+1)*z1 - 3*(c+2)*(2*c-1)**2),
+         (-z1*z4 + 108*(2*c-1)*c**5 - 3*(2*c-1)*z5)/(24*z1*c*(c-1)**4 + 72*c*z6 + 72*c**6 * (2*c-13))]
+    return A, B
+
+
+def katzer_plan(N0, N1):
+    """apps/katzer_SBLI/katzer_SBLI.py as shipped, on an N0 x N1 grid (metric fields and the Dirichlet table are
+    filled in from the reference's own cold kernels by main())."""
+    A, B = ssp_rk3()
+    ra = 'reduced_access'
+    return dict(ndim=2, np=[N0, N1], delta=[400.0 / (N0 - 1), 115.0 / (N1 - 1)], conv='teno', order=5, averaging='roe',
+                viscous=True, rk='ls', rk_a=A, rk_b=B, viscosity=dict(type='sutherland'), teno_adaptive=True,
+                metric_fields=[None, 'D11'],
+                constants=dict(gama=1.4, Minf=2.0, Pr=0.72, Re=950.0, Twall=1.67619431, dt=0.04, SuthT=110.4, RefT=288.0,
+                               eps=1e-15, TENO_CT=1e-5, teno_a1=10.5, teno_a2=4.5, epsilon=1e-30),
+                bc=[[dict(type='inlet_pressure_extrapolate', closure=ra), dict(type='extrapolation', order=0, closure=ra)],
+                    [dict(type='isothermal_wall', closure=ra), dict(type='dirichlet_field', closure=ra)]])
+
+
+def katzer_dirichlet_table(N0, halo=5):
+    x0 = (400.0 / (N0 - 1)) * np.arange(-halo, N0 + halo)
+    return np.stack([np.where(x0 > 40.0, 1.129734572, 1.00000596004), np.where(x0 > 40.0, 1.0921171, 1.00000268202),
+                     np.where(x0 > 40.0, -0.058866065, 0.00565001630205), np.where(x0 > 40.0, 1.0590824, 0.94644428042)])
+
+
+FIXTURES['katzer_60x40'] = ('katzer', katzer_plan(60, 40), [1, 10])
+
+
 def env_params(plan):
     P = {'dt': plan['constants']['dt']}
+    if 'metric_fields' in plan:      # Katzer: grid spacings follow from the sizes inside the generated program
+        P = {}
     for d in range(plan['ndim']):
         P['block0np%d' % d] = plan['np'][d]
     return P
@@ -65,7 +107,17 @@ def main():
         inner = (slice(5, -5),) * nd
         out = {'plan': np.array(json.dumps(plan, sort_keys=True)),
                'provenance': np.array(open(os.path.join(REF_DIR, config, 'provenance.json')).read())}
-        r = run_ref(config, dict(env_params(plan), niter=0), fields)
+        extra = []
+        if 'metric_fields' in plan:
+            extra = [n for d, name in enumerate(plan['metric_fields']) if name for n in ('D%d%d' % (d, d), 'SD%d%d%d' % (d, d, d))]
+        r = run_ref(config, dict(env_params(plan), niter=0), fields + extra, dump_all=bool(extra))
+        if extra:
+            # full padded arrays: the halo values of the initial state and of the metrics are part of the problem
+            # (the reference's init and metric kernels fill them once; some BCs never rewrite them)
+            out['q0_padded'] = np.stack([r[f] for f in fields])
+            for n in extra:
+                out['field_' + n] = r[n]
+            out['bc_table_1_1'] = katzer_dirichlet_table(plan['np'][0])
         out['q0'] = np.stack([r[f][inner] for f in fields])
         for n in steps:
             r = run_ref(config, dict(env_params(plan), niter=n), fields)

@@ -11,7 +11,15 @@ ORACLE_DIR = os.path.join(REPO, 'oracle')
 REF_DIR = os.path.join(ORACLE_DIR, '_ref')
 
 CONV = {'central': 0, 'weno': 1, 'teno': 2}
-BC = {'periodic': 0, 'dirichlet': 1, 'exchange': 2}
+BC = {'periodic': 0, 'dirichlet': 1, 'exchange': 2, 'isothermal_wall': 3, 'extrapolation': 4,
+      'inlet_pressure_extrapolate': 5, 'symmetry': 6, 'dirichlet_field': 7}
+MU = {'constant': 0, 'sutherland': 1, 'power': 2}
+CLOSURES = {
+    # rows idx = 0.. next to the face x weights of the boundary-absolute points 0..np-1
+    # reduced_access_scheme.py:36-43, 76-83 ; Carpenter second derivative Carpenter_scheme.py:69-76
+    'reduced_access': dict(d1=[[-25.0 / 12, 48.0 / 12, -36.0 / 12, 16.0 / 12, -3.0 / 12], [-3.0 / 12, -10.0 / 12, 18.0 / 12, -6.0 / 12, 1.0 / 12]],
+                           d2=[[35.0 / 12, -104.0 / 12, 114.0 / 12, -56.0 / 12, 11.0 / 12], [11.0 / 12, -20.0 / 12, 6.0 / 12, 4.0 / 12, -1.0 / 12]]),
+}
 
 
 class OsboCfg(ctypes.Structure):
@@ -22,7 +30,17 @@ class OsboCfg(ctypes.Structure):
                 ('gama', ctypes.c_double), ('Minf', ctypes.c_double), ('Re', ctypes.c_double),
                 ('Pr', ctypes.c_double), ('dt', ctypes.c_double), ('eps', ctypes.c_double),
                 ('teno_ct', ctypes.c_double), ('delta', ctypes.c_double * 3),
-                ('bc', (ctypes.c_int * 2) * 3), ('bc_q', ((ctypes.c_double * 5) * 2) * 3)]
+                ('bc', (ctypes.c_int * 2) * 3), ('bc_q', ((ctypes.c_double * 5) * 2) * 3),
+                # general path (keep in sync with oracle/osbli_oracle.h)
+                ('visc_law', ctypes.c_int), ('SuthT', ctypes.c_double), ('RefT', ctypes.c_double), ('mu_exp', ctypes.c_double),
+                ('D', ctypes.POINTER(ctypes.c_double) * 3), ('SD', ctypes.POINTER(ctypes.c_double) * 3),
+                ('closure', (ctypes.c_int * 2) * 3),
+                ('c_nr1', ctypes.c_int), ('c_np1', ctypes.c_int), ('c_nr2', ctypes.c_int), ('c_np2', ctypes.c_int),
+                ('c_d1', ctypes.c_double * 24), ('c_d2', ctypes.c_double * 12),
+                ('teno_adaptive', ctypes.c_int), ('teno_a1', ctypes.c_double), ('teno_a2', ctypes.c_double),
+                ('sensor_eps', ctypes.c_double), ('theta', ctypes.POINTER(ctypes.c_double)),
+                ('teno_store', ctypes.POINTER(ctypes.c_double)), ('Twall', ctypes.c_double),
+                ('extrap_order', (ctypes.c_int * 2) * 3), ('bc_face', (ctypes.POINTER(ctypes.c_double) * 2) * 3)]
 
 
 _lib = None
@@ -45,6 +63,8 @@ def oracle_lib():
 def make_cfg(plan):
     """plan: dict as produced by opensbli_b200.plan (numeric, resolved)."""
     c = OsboCfg()
+    P = ctypes.POINTER(ctypes.c_double)
+    keep = []
     c.ndim = plan['ndim']
     for d in range(3):
         c.np[d] = plan['np'][d] if d < plan['ndim'] else 1
@@ -75,6 +95,43 @@ def make_cfg(plan):
             if b['type'] == 'dirichlet':
                 for m, v in enumerate(b['q']):
                     c.bc_q[d][s][m] = v
+            if b['type'] == 'dirichlet_field':
+                a = np.ascontiguousarray(b['table'], dtype=np.float64)
+                keep.append(a)
+                c.bc_face[d][s] = a.ctypes.data_as(P)
+            if b['type'] == 'extrapolation':
+                c.extrap_order[d][s] = int(b.get('order', 0))
+            if b.get('closure'):
+                c.closure[d][s] = 1
+                cl = plan['closures'][b['closure']] if 'closures' in plan else CLOSURES[b['closure']]
+                d1, d2 = np.asarray(cl['d1'], dtype=np.float64), np.asarray(cl['d2'], dtype=np.float64)
+                c.c_nr1, c.c_np1 = d1.shape
+                c.c_nr2, c.c_np2 = d2.shape
+                for i, v in enumerate(d1.ravel()):
+                    c.c_d1[i] = v
+                for i, v in enumerate(d2.ravel()):
+                    c.c_d2[i] = v
+    visc = plan.get('viscosity', {'type': 'constant'})
+    c.visc_law = MU[visc['type']]
+    c.SuthT, c.RefT, c.mu_exp = k.get('SuthT', 0.0), k.get('RefT', 1.0), visc.get('exponent', 0.0)
+    c.Twall = k.get('Twall', 1.0)
+    shape = padded_shape(plan)
+    for d, name in enumerate(plan.get('metric_fields', [None] * plan['ndim'])):
+        if name:
+            for arr, fld in ((c.D, 'D%d%d' % (d, d)), (c.SD, 'SD%d%d%d' % (d, d, d))):
+                a = np.ascontiguousarray(plan['fields'][fld], dtype=np.float64)
+                assert a.shape == shape
+                keep.append(a)
+                arr[d] = a.ctypes.data_as(P)
+    ad = plan.get('teno_adaptive')
+    if ad:
+        c.teno_adaptive = 1
+        c.teno_a1, c.teno_a2, c.sensor_eps = k['teno_a1'], k['teno_a2'], k.get('epsilon', 1e-12)
+        th, ts = np.zeros(shape), np.zeros(shape)
+        keep += [th, ts]
+        c.theta, c.teno_store = th.ctypes.data_as(P), ts.ctypes.data_as(P)
+        c._theta, c._teno_store = th, ts
+    c._keep = keep
     return c
 
 

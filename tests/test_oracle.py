@@ -3,7 +3,7 @@ reference's own generated C, and -- when oracle/_ref is present -- against the r
 import numpy as np
 import pytest
 
-from common import fixtures, load_fixture, pad, inner, field_errors, tol_for
+from common import fixtures, load_fixture, pad, inner, field_errors, tol_for, initial_padded
 import oracle_util as ou
 
 
@@ -13,7 +13,7 @@ def test_oracle_matches_golden(name):
     for n in sorted(k for k in states if k > 0):
         if n > 200:
             continue
-        q, _ = ou.oracle_advance(plan, pad(plan, states[0]), n)
+        q, _ = ou.oracle_advance(plan, initial_padded(plan, states), n)
         err = field_errors(plan, inner(plan, q), states[n])
         assert max(err) < tol_for(plan, n), (name, n, err)
 
