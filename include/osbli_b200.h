@@ -44,6 +44,9 @@ int osb_field_info(const osb_ctx *ctx, const char *name, int *dims, int *halo_m,
 int osb_upload(osb_ctx *ctx, const char *name, const double *host_padded);
 int osb_download(osb_ctx *ctx, const char *name, double *host_padded);
 int osb_device_ptr(osb_ctx *ctx, const char *name, double **device_ptr);
+/* State imposed by a `dirichlet_field` boundary (equations of a DirichletBC that depend on the position along the face,
+ * dirichlet.py:28-41): table[m][t], m < ndim+2, t = padded tangential index (the field index with dimension dir removed). */
+int osb_upload_face(osb_ctx *ctx, int dir, int side, const double *table);
 
 /* The time loop body, in the reference's program order (algorithm.py:440-474):
  *   per iteration: BCs ; [save] ; per stage: constituent relations, spatial kernels, RK update, BCs.

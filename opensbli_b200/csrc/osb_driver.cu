@@ -23,11 +23,14 @@ thread_local std::string g_create_error;
 
 enum ConvKind { CONV_CENTRAL = 0, CONV_WENO = 1, CONV_TENO = 2 };
 enum RkKind { RK_SBLI = 0, RK_LS = 1 };
-enum BcKind { BC_PERIODIC = 0, BC_DIRICHLET = 1, BC_EXCHANGE = 2 /* neighbour rank owns the halo */ };
+enum BcKind { BC_PERIODIC = 0, BC_DIRICHLET = 1, BC_EXCHANGE = 2 /* neighbour rank owns the halo */, BC_ISOTHERMAL_WALL = 3,
+              BC_EXTRAPOLATION = 4, BC_INLET_PRESSURE = 5, BC_SYMMETRY = 6, BC_DIRICHLET_FIELD = 7 };
 
 struct BcSpec {
   int kind = BC_PERIODIC;
   double q[5] = {0, 0, 0, 0, 0};
+  int order = 0;            // extrapolation order
+  bool closure = false;     // central derivatives use the one-sided closure next to this face
 };
 
 struct Plan {
@@ -42,6 +45,12 @@ struct Plan {
   std::vector<double> rk_a, rk_b;
   std::map<std::string, double> consts;
   BcSpec bc[3][2];
+  // general path
+  int visc_law = 0;
+  double mu_exp = 0.0;
+  bool metric[3] = {false, false, false};
+  bool teno_adaptive = false;
+  Closures cl{};
 };
 
 struct Field {
@@ -67,6 +76,11 @@ struct osb_ctx {
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
   // peers (slab decomposition)
   cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+  GeneralPtrs gp{};
+  AdaptiveCT ad{};
+  bool general = false;
+  double *face_table[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  long long face_size[3] = {0, 0, 0};
   double *peer_q[2][5] = {{nullptr}};
   bool peer_open[2] = {false, false};
 };
@@ -111,10 +125,32 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
     else if (key == "bc") {
       int d, s; std::string kind; ls >> d >> s >> kind;
       if (d < 0 || d > 2 || s < 0 || s > 1) { err = "bad bc line: " + line; return false; }
-      if (kind == "periodic") P.bc[d][s].kind = BC_PERIODIC;
-      else if (kind == "exchange") P.bc[d][s].kind = BC_EXCHANGE;
-      else if (kind == "dirichlet") { P.bc[d][s].kind = BC_DIRICHLET; for (int m = 0; m < P.nd + 2; m++) ls >> P.bc[d][s].q[m]; }
+      BcSpec &b = P.bc[d][s];
+      if (kind == "periodic") b.kind = BC_PERIODIC;
+      else if (kind == "exchange") b.kind = BC_EXCHANGE;
+      else if (kind == "dirichlet") { b.kind = BC_DIRICHLET; for (int m = 0; m < P.nd + 2; m++) ls >> b.q[m]; }
+      else if (kind == "dirichlet_field") b.kind = BC_DIRICHLET_FIELD;
+      else if (kind == "isothermal_wall") b.kind = BC_ISOTHERMAL_WALL;
+      else if (kind == "extrapolation") { b.kind = BC_EXTRAPOLATION; ls >> b.order; }
+      else if (kind == "inlet_pressure_extrapolate") { b.kind = BC_INLET_PRESSURE; if (s != 0) { err = "inlet_pressure_extrapolate is defined for side 0 only"; return false; } }
+      else if (kind == "symmetry") b.kind = BC_SYMMETRY;
       else { err = "unsupported boundary condition '" + kind + "'"; return false; }
+      std::string tok;
+      if (ls >> tok) { if (tok == "closure") b.closure = true; else { err = "bad bc line: " + line; return false; } }
+    }
+    else if (key == "viscosity") {
+      std::string v; ls >> v;
+      if (v == "constant") P.visc_law = 0; else if (v == "sutherland") P.visc_law = 1;
+      else if (v == "power") { P.visc_law = 2; ls >> P.mu_exp; } else { err = "unknown viscosity law " + v; return false; }
+    }
+    else if (key == "metric") { int d2, on; ls >> d2 >> on; if (d2 < 0 || d2 > 2) { err = "bad metric line"; return false; } P.metric[d2] = on != 0; }
+    else if (key == "teno_adaptive") { int v; ls >> v; P.teno_adaptive = v != 0; }
+    else if (key == "closure_d1" || key == "closure_d2") {
+      int nr, np; ls >> nr >> np;
+      if (nr < 1 || np < 1 || nr > (key == "closure_d1" ? 4 : 2) || np > 6) { err = "closure table too large: " + line; return false; }
+      double *dst = key == "closure_d1" ? P.cl.d1 : P.cl.d2;
+      for (int i = 0; i < nr * np; i++) ls >> dst[i];
+      if (key == "closure_d1") { P.cl.nr1 = nr; P.cl.np1 = np; } else { P.cl.nr2 = nr; P.cl.np2 = np; }
     } else { err = "unknown plan key '" + key + "'"; return false; }
     if (ls.fail() && !ls.eof()) { err = "malformed plan line: " + line; return false; }
   }
@@ -127,6 +163,16 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
   if (P.conv == CONV_TENO && P.order != 5 && P.order != 6) { err = "TENO: only orders 5 and 6 are implemented"; return false; }
   for (const char *k : {"gama", "dt"}) if (!P.consts.count(k)) { err = std::string("missing constant ") + k; return false; }
   if (P.viscous) for (const char *k : {"Re", "Pr", "Minf"}) if (!P.consts.count(k)) { err = std::string("missing constant ") + k; return false; }
+  bool any_closure = false;
+  for (int d = 0; d < P.nd; d++) for (int s = 0; s < 2; s++) { P.cl.on[d][s] = P.bc[d][s].closure ? 1 : 0; any_closure |= P.bc[d][s].closure; }
+  if (any_closure && (P.cl.nr1 == 0 || P.cl.nr2 == 0)) { err = "a face requests a derivative closure but closure_d1/closure_d2 tables are missing"; return false; }
+  if (P.teno_adaptive) {
+    if (P.conv != CONV_TENO) { err = "teno_adaptive needs a TENO scheme"; return false; }
+    for (const char *k : {"teno_a1", "teno_a2"}) if (!P.consts.count(k)) { err = std::string("missing constant ") + k; return false; }
+  }
+  if (P.visc_law == 1) for (const char *k : {"SuthT", "RefT"}) if (!P.consts.count(k)) { err = std::string("missing constant ") + k; return false; }
+  for (int d = 0; d < P.nd; d++) for (int s = 0; s < 2; s++)
+    if (P.bc[d][s].kind == BC_ISOTHERMAL_WALL && !P.consts.count("Twall")) { err = "missing constant Twall"; return false; }
   return true;
 }
 
@@ -141,6 +187,10 @@ void refresh_constants(osb_ctx *c) {
   c->pc.dt = get("dt", 0.0);
   for (int d = 0; d < 3; d++) { c->pc.inv[d] = 1.0 / P.delta[d]; c->pc.inv2[d] = pow(P.delta[d], -2); }
   c->sp = make_scheme_params(get("eps", 1e-16), get("TENO_CT", 1e-6));
+  c->ad = make_adaptive_ct(P.teno_adaptive, get("teno_a1", 0.0), get("teno_a2", 0.0));
+  c->pc.visc_law = P.visc_law; c->pc.mu_exp = P.mu_exp;
+  c->pc.SuthT = get("SuthT", 0.0); c->pc.RefT = get("RefT", 1.0); c->pc.Twall = get("Twall", 1.0);
+  c->pc.sensor_eps = get("epsilon", 1e-12);
 }
 
 Field *find_field(osb_ctx *c, const char *name) {
@@ -173,7 +223,7 @@ void launch_prim(osb_ctx *c) {
   for (int d = 0; d < ND; d++) { lo[d] = -hm; n[d] = c->grid.np[d] + hm + hp; }
   dim3 b(128, 2, 1);
   Launcher L(c, OSB_FAM_PRIM);
-  k_prim<ND><<<grid3(n[0], n[1], n[2], b), b, 0, c->stream>>>(c->grid, c->fp, c->pc, lo[0], lo[1], lo[2], n[0], n[1], n[2]);
+  k_prim<ND><<<grid3(n[0], n[1], n[2], b), b, 0, c->stream>>>(c->grid, c->fp, c->pc, c->gp.mu, lo[0], lo[1], lo[2], n[0], n[1], n[2]);
 }
 
 template <int ND, int RECON, int AVG>
@@ -183,7 +233,7 @@ void launch_flux(osb_ctx *c) {
     const long long T = (long long)(g.np[0] + 6) * g.np[1] * g.np[2];
     const long long nb = (T + F2_BT - 7) / (F2_BT - 6);
     Launcher L(c, OSB_FAM_FLUX);
-    k_flux2_x<ND, RECON, AVG, false><<<(unsigned)nb, F2_BT, 0, c->stream>>>(g, c->fp, c->pc, c->sp);
+    k_flux2_x<ND, RECON, AVG, false><<<(unsigned)nb, F2_BT, 0, c->stream>>>(g, c->fp, c->pc, c->sp, c->ad, c->gp);
   }
   if (ND >= 2) {
     const long long TR = (long long)(g.np[1] + 6) * (ND > 2 ? g.np[2] : 1);
@@ -193,7 +243,7 @@ void launch_flux(osb_ctx *c) {
     auto kern = k_flux2_yz<N2, 1, RECON, AVG, true>;
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_yz_smem_bytes<N2>()); attr_set = true; }
-    kern<<<gr, b, f2_yz_smem_bytes<N2>(), c->stream>>>(g, c->fp, c->pc, c->sp);
+    kern<<<gr, b, f2_yz_smem_bytes<N2>(), c->stream>>>(g, c->fp, c->pc, c->sp, c->ad, c->gp);
   }
   if (ND >= 3) {
     const long long TR = (long long)(g.np[2] + 6) * g.np[1];
@@ -202,7 +252,7 @@ void launch_flux(osb_ctx *c) {
     auto kern = k_flux2_yz<3, 2, RECON, AVG, true>;
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_yz_smem_bytes<3>()); attr_set = true; }
-    kern<<<gr, b, f2_yz_smem_bytes<3>(), c->stream>>>(g, c->fp, c->pc, c->sp);
+    kern<<<gr, b, f2_yz_smem_bytes<3>(), c->stream>>>(g, c->fp, c->pc, c->sp, c->ad, c->gp);
   }
 }
 
@@ -220,6 +270,11 @@ template <int ND>
 void launch_residual(osb_ctx *c) {
   const GridDev &g = c->grid;
   launch_prim<ND>(c);
+  if (c->plan.teno_adaptive) {
+    dim3 b(64, 2, 2);
+    Launcher L(c, OSB_FAM_PRIM);
+    k_theta<(ND > 1 ? ND : 2)><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc, c->plan.cl, c->gp);
+  }
   if (c->plan.conv == CONV_CENTRAL) {
     dim3 b(64, 2, 2);
     Launcher L(c, OSB_FAM_CENTRAL);
@@ -230,7 +285,8 @@ void launch_residual(osb_ctx *c) {
   if (c->plan.viscous) {
     dim3 b(64, 2, 2);
     Launcher L(c, OSB_FAM_VISCOUS);
-    k_viscous<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc);
+    if (c->general) k_viscous_general<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc, c->plan.cl, c->gp);
+    else k_viscous<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc);
   }
 }
 
@@ -271,6 +327,31 @@ void launch_bcs(osb_ctx *c) {
         box_launch_cfg(dst, nv, blocks);
         Launcher L(c, OSB_FAM_BC);
         k_fill_box<<<blocks, 256, 0, c->stream>>>(g, c->fp, nv, dst, st);
+      } else {
+        // plane kernels: boundary plane of (d, s), tangential range incl. the scheme halos
+        PlaneSpec ps;
+        ps.dir = d; ps.side = s; ps.nh = s == 0 ? hm : hp;
+        for (int e = 0; e < 3; e++) { ps.lo[e] = full.lo[e]; ps.n[e] = full.n[e]; }
+        ps.lo[d] = s == 0 ? 0 : g.np[d] - 1; ps.n[d] = 1;
+        const long long cnt = (long long)ps.n[0] * ps.n[1] * ps.n[2];
+        const unsigned nb = (unsigned)((cnt + 127) / 128);
+        Launcher L(c, OSB_FAM_BC);
+        switch (b.kind) {
+          case BC_DIRICHLET_FIELD: k_bc_dirichlet_field<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps, c->face_table[d][s], c->face_size[d]); break;
+          case BC_EXTRAPOLATION: k_bc_extrapolation<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps, b.order); break;
+          case BC_SYMMETRY: k_bc_symmetry<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps); break;
+          case BC_INLET_PRESSURE:
+            if (P.nd == 1) k_bc_inlet_pressure<1><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+            else if (P.nd == 2) k_bc_inlet_pressure<2><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+            else k_bc_inlet_pressure<3><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+            break;
+          case BC_ISOTHERMAL_WALL:
+            if (P.nd == 1) k_bc_isothermal_wall<1><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+            else if (P.nd == 2) k_bc_isothermal_wall<2><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+            else k_bc_isothermal_wall<3><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+            break;
+          default: break;
+        }
       }
     }
 }
@@ -390,6 +471,30 @@ int osb_create(const char *plan_text, int device, osb_ctx **out) {
   ok = ok && add("p", &c->fp.p) && add("a", &c->fp.a) && add("T", &c->fp.T);
   for (int m = 0; m < nv && ok; m++) ok = add("Residual" + std::to_string(m), &c->fp.R[m]);
   for (int m = 0; m < nv && ok; m++) ok = add(P.rk == RK_LS ? "tempRK_" + qn[m] : qn[m] + "_RKold", &c->fp.rk[m]);
+  // general path: metric fields (uploaded by the caller), viscosity, sensor
+  c->general = P.visc_law != 0;
+  for (int d = 0; d < P.nd; d++) {
+    if (P.metric[d] || P.bc[d][0].closure || P.bc[d][1].closure) c->general = true;
+    if (P.metric[d] && ok) {
+      double *pD = nullptr, *pS = nullptr;
+      const std::string dd = std::to_string(d);
+      ok = add("D" + dd + dd, &pD) && add("SD" + dd + dd + dd, &pS);
+      c->gp.D[d] = pD; c->gp.SD[d] = pS;
+    }
+  }
+  if (ok && (c->general || P.visc_law != 0)) ok = add("mu", &c->gp.mu);
+  if (ok && P.teno_adaptive) ok = add("theta", &c->gp.theta) && add("TENO", &c->gp.teno_store);
+  if (P.teno_adaptive && P.nd < 2) { g_create_error = "adaptive TENO needs at least 2 dimensions (vorticity)"; osb_destroy(c); return 1; }
+  for (int d = 0; d < P.nd && ok; d++) {
+    long long ts = 1;
+    for (int e = 0; e < P.nd; e++) if (e != d) ts *= g.pd[e];
+    c->face_size[d] = ts;
+    for (int s = 0; s < 2 && ok; s++)
+      if (P.bc[d][s].kind == BC_DIRICHLET_FIELD) {
+        ok = cudaMalloc(&c->face_table[d][s], sizeof(double) * ts * nv) == cudaSuccess;
+        if (ok) cudaMemsetAsync(c->face_table[d][s], 0, sizeof(double) * ts * nv, c->stream);
+      }
+  }
   if (!ok) { g_create_error = "cudaMalloc failed (out of device memory)"; osb_destroy(c); return 3; }
   cudaStreamSynchronize(c->stream);
   *out = c;
@@ -402,6 +507,7 @@ int osb_destroy(osb_ctx *c) {
   for (int s = 0; s < 2; s++)
     if (c->peer_open[s]) for (int m = 0; m < 5; m++) if (c->peer_q[s][m]) cudaIpcCloseMemHandle(c->peer_q[s][m]);
   for (auto &f : c->fields) cudaFree(f.dev);
+  for (int d = 0; d < 3; d++) for (int s = 0; s < 2; s++) if (c->face_table[d][s]) cudaFree(c->face_table[d][s]);
   if (c->timer0) { cudaEventDestroy(c->timer0); cudaEventDestroy(c->timer1); }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -449,6 +555,14 @@ int osb_download(osb_ctx *c, const char *name, double *host) {
   Field *f = find_field(c, name);
   if (!f) return fail(c, std::string("unknown field ") + name);
   OSB_CUDA(c, cudaMemcpyAsync(host, f->dev, sizeof(double) * c->grid.n, cudaMemcpyDeviceToHost, c->stream));
+  OSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int osb_upload_face(osb_ctx *c, int dir, int side, const double *table) {
+  if (!c || !table || dir < 0 || dir >= c->plan.nd || side < 0 || side > 1) return 1;
+  if (!c->face_table[dir][side]) return fail(c, "osb_upload_face: this face has no dirichlet_field boundary condition");
+  const size_t bytes = sizeof(double) * c->face_size[dir] * (c->plan.nd + 2);
+  OSB_CUDA(c, cudaMemcpyAsync(c->face_table[dir][side], table, bytes, cudaMemcpyHostToDevice, c->stream));
   OSB_CUDA(c, cudaStreamSynchronize(c->stream));
   return 0;
 }

@@ -35,13 +35,30 @@ struct FieldPtrs {
 struct PhysConst {
   double gama, Minf, Re, Pr, dt;
   double inv[3], inv2[3];   // 1/Delta_d, 1/Delta_d^2
+  // general path
+  int visc_law;             // 0 constant, 1 Sutherland, 2 power law
+  double SuthT, RefT, mu_exp, Twall, sensor_eps;
+};
+
+// one-sided closure tables (reduced_access_scheme.py:36-83, Carpenter_scheme.py:38-102): rows idx = 0..nr-1 next to
+// side 0 x weights of the boundary-absolute points 0..np-1; side 1 mirrors them (sign -1 for first derivatives)
+struct Closures {
+  int on[3][2];
+  int nr1, np1, nr2, np2;
+  double d1[4 * 6], d2[2 * 6];
+};
+
+struct GeneralPtrs {
+  const double *D[3];       // D_dd metric (nullptr: direction not stretched)
+  const double *SD[3];      // SD_ddd
+  double *mu, *theta, *teno_store;
 };
 
 // -------------------------------------------------------------------------------------------------
 // constituent relations over [lo, hi) (grid + scheme halos)
 // -------------------------------------------------------------------------------------------------
 template <int ND>
-__global__ void __launch_bounds__(256) k_prim(GridDev g, FieldPtrs f, PhysConst c, int lo0, int lo1, int lo2, int n0, int n1, int n2) {
+__global__ void __launch_bounds__(256) k_prim(GridDev g, FieldPtrs f, PhysConst c, double *mu, int lo0, int lo1, int lo2, int n0, int n1, int n2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const int k = blockIdx.z;
@@ -63,7 +80,13 @@ __global__ void __launch_bounds__(256) k_prim(GridDev g, FieldPtrs f, PhysConst 
   for (int d = 0; d < ND; d++) f.u[d][x] = u[d];
   f.p[x] = p;
   f.a[x] = sqrt(c.gama * p / rho);
-  f.T[x] = c.Minf * c.Minf * c.gama * p / rho;
+  const double T = c.Minf * c.Minf * c.gama * p / rho;
+  f.T[x] = T;
+  if (mu) {   // viscosity laws of the apps: Sutherland (katzer_SBLI.py:25), power law (turbulent_channel.py:29)
+    if (c.visc_law == 1) mu[x] = (c.SuthT / c.RefT + 1.0) * (T * sqrt(T)) / (c.SuthT / c.RefT + T);
+    else if (c.visc_law == 2) mu[x] = pow(T, c.mu_exp);
+    else mu[x] = 1.0;
+  }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -211,7 +234,7 @@ constexpr int F2_RT = 21;             // y/z sweeps: staged rows per block (RT-5
 template <int ND> constexpr size_t f2_yz_smem_bytes() { return sizeof(double) * (SV<ND>::N + ND + 2) * F2_RT * 32; }
 
 template <int ND, int RECON, int AVG, bool ACCUM>
-__global__ void __launch_bounds__(F2_BT, 3) k_flux2_x(GridDev g, FieldPtrs f, PhysConst c, SchemeParams sp) {
+__global__ void __launch_bounds__(F2_BT, 3) k_flux2_x(GridDev g, FieldPtrs f, PhysConst c, SchemeParams sp, AdaptiveCT ad, GeneralPtrs gp) {
   constexpr int NV = ND + 2, NVAL = SV<ND>::N;
   __shared__ double sP[NVAL][F2_BT];
   __shared__ double sF[NV][F2_BT];
@@ -233,6 +256,11 @@ __global__ void __launch_bounds__(F2_BT, 3) k_flux2_x(GridDev g, FieldPtrs f, Ph
   const bool iface = inside && t >= 2 && t <= F2_BT - 4 && ip >= -1 && ip <= g.np[0] - 1;
   if (iface) {
     double fl[NV];
+    if (ad.on) {                      // sensor value of the interface's left point (0 in the halos)
+      const int e = adaptive_exponent(ad, gp.theta[x]);
+      sp.teno_ct = ad.ct[e]; sp.kfast5 = ad.k5[e]; sp.kfast6 = ad.k6[e];
+      if (gp.teno_store) gp.teno_store[x] = sp.teno_ct;
+    }
     interface_flux_staged<ND, 0, RECON, AVG>(&sP[0][t - 2], 1, F2_BT, c.gama, sp, fl);
 #pragma unroll
     for (int m = 0; m < NV; m++) sF[m][t] = fl[m];
@@ -244,16 +272,17 @@ __global__ void __launch_bounds__(F2_BT, 3) k_flux2_x(GridDev g, FieldPtrs f, Ph
 #pragma unroll
       for (int m = 0; m < NV; m++) old[m] = f.R[m][x];
     }
+    const double met = gp.D[0] ? -c.inv[0] * gp.D[0][x] : -c.inv[0];
 #pragma unroll
     for (int m = 0; m < NV; m++) {
-      const double r = -c.inv[0] * (sF[m][t] - sF[m][t - 1]);
+      const double r = met * (sF[m][t] - sF[m][t - 1]);
       f.R[m][x] = ACCUM ? old[m] + r : r;
     }
   }
 }
 
 template <int ND, int DIR, int RECON, int AVG, bool ACCUM>
-__global__ void __launch_bounds__(32 * F2_TY, 3) k_flux2_yz(GridDev g, FieldPtrs f, PhysConst c, SchemeParams sp) {
+__global__ void __launch_bounds__(32 * F2_TY, 3) k_flux2_yz(GridDev g, FieldPtrs f, PhysConst c, SchemeParams sp, AdaptiveCT ad, GeneralPtrs gp) {
   constexpr int NV = ND + 2, NVAL = SV<ND>::N;
   constexpr int OTH = (DIR == 1) ? 2 : 1;
   extern __shared__ double f2_smem[];                       // dynamic: more than the 48 KB static limit
@@ -299,6 +328,12 @@ __global__ void __launch_bounds__(32 * F2_TY, 3) k_flux2_yz(GridDev g, FieldPtrs
       const int jp = (int)(fr % NJR) - 3;
       if (jp >= -1 && jp <= g.np[DIR] - 1) {
         double fl[NV];
+        if (ad.on) {
+          const int o = (int)(fr / NJR);
+          const long long x = g.off + i + (long long)jp * g.s[DIR] + (ND > 2 ? o * g.s[OTH] : 0);
+          const int e = adaptive_exponent(ad, gp.theta[x]);
+          sp.teno_ct = ad.ct[e]; sp.kfast5 = ad.k5[e]; sp.kfast6 = ad.k6[e];
+        }
         interface_flux_staged<ND, DIR, RECON, AVG>(&sP[0][r - 2][tx], 32, F2_RT * 32, c.gama, sp, fl);
 #pragma unroll
         for (int m = 0; m < NV; m++) sF[m][r][tx] = fl[m];
@@ -336,9 +371,10 @@ __global__ void __launch_bounds__(32 * F2_TY, 3) k_flux2_yz(GridDev g, FieldPtrs
     for (int it = 0; it < NIT; it++) {
       const int r = 3 + ty + it * F2_TY;
       if (ok[it]) {
+        const double met = gp.D[DIR] ? -c.inv[DIR] * gp.D[DIR][xs[it]] : -c.inv[DIR];
 #pragma unroll
         for (int m = 0; m < NV; m++) {
-          const double rr = -c.inv[DIR] * (sF[m][r][tx] - sF[m][r - 1][tx]);
+          const double rr = met * (sF[m][r][tx] - sF[m][r - 1][tx]);
           f.R[m][xs[it]] = ACCUM ? old[it][m] + rr : rr;
         }
       }
@@ -500,6 +536,139 @@ __global__ void __launch_bounds__(256) k_rk_save(GridDev g, FieldPtrs f) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// General path: one-sided closures, stretched-grid metrics, variable viscosity (BASELINE config 4)
+// -------------------------------------------------------------------------------------------------
+// first / second xi-derivative along direction dir at linear index x, grid index idx of n points
+__device__ __forceinline__ double gd1(const Closures &cl, const double *a, long long x, long long s, double inv, int dir, int idx, int n) {
+  if (cl.on[dir][0] && idx < cl.nr1) {
+    double r = 0.0; const long long x0 = x - idx * s;
+    for (int p = 0; p < cl.np1; p++) r += cl.d1[idx * cl.np1 + p] * __ldg(a + x0 + p * s);
+    return inv * r;
+  }
+  if (cl.on[dir][1] && n - 1 - idx < cl.nr1) {
+    const int row = n - 1 - idx; double r = 0.0; const long long x0 = x + row * s;
+    for (int p = 0; p < cl.np1; p++) r -= cl.d1[row * cl.np1 + p] * __ldg(a + x0 - p * s);
+    return inv * r;
+  }
+  return d1c(__ldg(a + x - 2 * s), __ldg(a + x - s), __ldg(a + x + s), __ldg(a + x + 2 * s), inv);
+}
+__device__ __forceinline__ double gd2(const Closures &cl, const double *a, long long x, long long s, double inv2, int dir, int idx, int n) {
+  if (cl.on[dir][0] && idx < cl.nr2) {
+    double r = 0.0; const long long x0 = x - idx * s;
+    for (int p = 0; p < cl.np2; p++) r += cl.d2[idx * cl.np2 + p] * __ldg(a + x0 + p * s);
+    return inv2 * r;
+  }
+  if (cl.on[dir][1] && n - 1 - idx < cl.nr2) {
+    const int row = n - 1 - idx; double r = 0.0; const long long x0 = x + row * s;
+    for (int p = 0; p < cl.np2; p++) r += cl.d2[row * cl.np2 + p] * __ldg(a + x0 - p * s);
+    return inv2 * r;
+  }
+  return d2c(__ldg(a + x - 2 * s), __ldg(a + x - s), __ldg(a + x), __ldg(a + x + s), __ldg(a + x + 2 * s), inv2);
+}
+// d/dxi_out ( d a / dxi_in ): the outer formula (central or closure by idx_out) applied to inner derivatives
+__device__ __forceinline__ double gdmix(const Closures &cl, const double *a, long long x, long long sin_, double invin, int in, int idxin, int nin,
+                                        long long sout, double invout, int out, int idxout, int nout) {
+  if (cl.on[out][0] && idxout < cl.nr1) {
+    double r = 0.0; const long long x0 = x - idxout * sout;
+    for (int p = 0; p < cl.np1; p++) r += cl.d1[idxout * cl.np1 + p] * gd1(cl, a, x0 + p * sout, sin_, invin, in, idxin, nin);
+    return invout * r;
+  }
+  if (cl.on[out][1] && nout - 1 - idxout < cl.nr1) {
+    const int row = nout - 1 - idxout; double r = 0.0; const long long x0 = x + row * sout;
+    for (int p = 0; p < cl.np1; p++) r -= cl.d1[row * cl.np1 + p] * gd1(cl, a, x0 - p * sout, sin_, invin, in, idxin, nin);
+    return invout * r;
+  }
+  return d1c(gd1(cl, a, x - 2 * sout, sin_, invin, in, idxin, nin), gd1(cl, a, x - sout, sin_, invin, in, idxin, nin),
+             gd1(cl, a, x + sout, sin_, invin, in, idxin, nin), gd1(cl, a, x + 2 * sout, sin_, invin, in, idxin, nin), invout);
+}
+
+// modified Ducros sensor (shock_sensors.py:12-49) on the interior
+template <int ND>
+__global__ void __launch_bounds__(256) k_theta(GridDev g, FieldPtrs f, PhysConst c, Closures cl, GeneralPtrs gp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z * blockDim.z + threadIdx.z;
+  if (i >= g.np[0] || j >= g.np[1] || k >= g.np[2]) return;
+  const long long x = g.off + i + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
+  const int id[3] = {i, j, k};
+  double du[ND][ND];
+#pragma unroll
+  for (int a = 0; a < ND; a++)
+#pragma unroll
+    for (int b = 0; b < ND; b++)
+      du[a][b] = gd1(cl, f.u[a], x, g.s[b], c.inv[b], b, id[b], g.np[b]) * (gp.D[b] ? gp.D[b][x] : 1.0);
+  double div = 0.0, vort = 0.0;
+#pragma unroll
+  for (int a = 0; a < ND; a++) div += du[a][a];
+  if (ND == 2) vort = sq(du[1][0] - du[0][1]);
+  if (ND == 3) vort = sq(du[2 % ND][1] - du[1][2 % ND]) + sq(du[0][2 % ND] - du[2 % ND][0]) + sq(du[1][0] - du[0][1]);
+  gp.theta[x] = (0.5 - 0.5 * tanh(2.5 + 250.0 * div)) * div * div / (c.sensor_eps + div * div + vort);
+}
+
+// General viscous terms: variable viscosity, stretched (diagonal-metric) grid, one-sided closures.
+// With  d_j f = D_jj delta_j f ,  d_jj f = D_jj^2 delta_jj f + D_jj SD_jjj delta_j f ,  d_ij f = D_ii D_jj delta_out(delta_in f)
+// (metric.py:72-135, opensblifunctions.py:540-549) and  S_ij = d_j u_i + d_i u_j - 2/3 delta_ij div u  (app strings, e.g.
+// katzer_SBLI.py:10-14, expanded by StoreSome.py:71-161):
+//   momentum_i += 1/Re [ sum_j d_j mu S_ij + mu ( sum_j d_jj u_i + 1/3 sum_j d_ij u_j ) ]
+//   energy     += kq [ sum_j d_j mu d_j T + mu sum_j d_jj T ] + sum_i u_i (momentum_i term) + mu/Re sum_ij S_ij d_j u_i
+template <int ND>
+__global__ void __launch_bounds__(256) k_viscous_general(GridDev g, FieldPtrs f, PhysConst c, Closures cl, GeneralPtrs gp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z * blockDim.z + threadIdx.z;
+  if (i >= g.np[0] || j >= g.np[1] || k >= g.np[2]) return;
+  const long long x = g.off + i + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
+  const int id[3] = {i, j, k};
+  const double iRe = 1.0 / c.Re;
+  const double kq = iRe * (1.0 / (c.gama - 1.0)) * (1.0 / (c.Minf * c.Minf)) * (1.0 / c.Pr);
+  double Dm[ND], SDm[ND], dmu[ND], dT[ND], dxi[ND + 1][ND], du[ND][ND];
+#pragma unroll
+  for (int d = 0; d < ND; d++) {
+    Dm[d] = gp.D[d] ? gp.D[d][x] : 1.0;
+    SDm[d] = gp.SD[d] ? gp.SD[d][x] : 0.0;
+    dmu[d] = c.visc_law == 0 ? 0.0 : Dm[d] * gd1(cl, gp.mu, x, g.s[d], c.inv[d], d, id[d], g.np[d]);
+#pragma unroll
+    for (int a = 0; a < ND; a++) { dxi[a][d] = gd1(cl, f.u[a], x, g.s[d], c.inv[d], d, id[d], g.np[d]); du[a][d] = Dm[d] * dxi[a][d]; }
+    dxi[ND][d] = gd1(cl, f.T, x, g.s[d], c.inv[d], d, id[d], g.np[d]);
+    dT[d] = Dm[d] * dxi[ND][d];
+  }
+  double div = 0.0;
+#pragma unroll
+  for (int a = 0; a < ND; a++) div += du[a][a];
+  const double mu = gp.mu[x];
+  double vis[ND], e = 0.0;
+#pragma unroll
+  for (int a = 0; a < ND; a++) {
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int b = 0; b < ND; b++) {
+      const double Sab = du[a][b] + du[b][a] - (a == b ? (2.0 / 3.0) * div : 0.0);
+      s1 += dmu[b] * Sab;
+      const double lap = Dm[b] * Dm[b] * gd2(cl, f.u[a], x, g.s[b], c.inv2[b], b, id[b], g.np[b]) + Dm[b] * SDm[b] * dxi[a][b];
+      if (b == a) s2 += (4.0 / 3.0) * lap;
+      else {
+        s2 += lap;
+        const int in = a < b ? a : b, out = a < b ? b : a;
+        s2 += (1.0 / 3.0) * Dm[a] * Dm[b] * gdmix(cl, f.u[b], x, g.s[in], c.inv[in], in, id[in], g.np[in], g.s[out], c.inv[out], out, id[out], g.np[out]);
+      }
+      e += iRe * mu * Sab * du[a][b];
+    }
+    vis[a] = iRe * (s1 + mu * s2);
+    e += vis[a] * __ldg(f.u[a] + x);
+  }
+  double hT = 0.0;
+#pragma unroll
+  for (int d = 0; d < ND; d++)
+    hT += dmu[d] * dT[d] + mu * (Dm[d] * Dm[d] * gd2(cl, f.T, x, g.s[d], c.inv2[d], d, id[d], g.np[d]) + Dm[d] * SDm[d] * dxi[ND][d]);
+  double old[ND + 1];
+#pragma unroll
+  for (int a = 0; a < ND + 1; a++) old[a] = f.R[1 + a][x];
+#pragma unroll
+  for (int a = 0; a < ND; a++) f.R[1 + a][x] = old[a] + vis[a];
+  f.R[ND + 1][x] = old[ND] + (kq * hT + e);
+}
+
+// -------------------------------------------------------------------------------------------------
 // Boundary conditions
 // -------------------------------------------------------------------------------------------------
 struct Box { int lo[3], n[3]; };   // start index and extent per dimension (inactive dims: lo 0, n 1)
@@ -530,6 +699,121 @@ __global__ void __launch_bounds__(256) k_fill_box(GridDev g, FieldPtrs f, int nv
     const long long xd = g.off + (dst.lo[0] + i) + (dst.lo[1] + j) * g.s[1] * (g.nd > 1) + (dst.lo[2] + k) * g.s[2] * (g.nd > 2);
     f.q[m][xd] = st.q[m];
   }
+}
+
+
+// Plane boundary kernels: one thread per point of the boundary plane of (dir, side); the tangential range covers the
+// scheme halos, as in the reference (bc_core.py:158-198).  `lo`/`n` = tangential start and extents (n[dir] = 1).
+struct PlaneSpec { int dir, side, lo[3], n[3], nh; };   // nh = number of halo planes on that side
+
+__device__ __forceinline__ bool plane_point(const GridDev &g, const PlaneSpec &ps, long long &x, long long &tlin) {
+  const long long cnt = (long long)ps.n[0] * ps.n[1] * ps.n[2];
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= cnt) return false;
+  long long r = e;
+  int id[3];
+  id[0] = ps.lo[0] + (int)(r % ps.n[0]); r /= ps.n[0];
+  id[1] = ps.lo[1] + (int)(r % ps.n[1]);
+  id[2] = ps.lo[2] + (int)(r / ps.n[1]);
+  x = g.off + id[0] + (g.nd > 1 ? id[1] * g.s[1] : 0) + (g.nd > 2 ? id[2] * g.s[2] : 0);
+  // tangential linear index into a face table: padded index with dimension dir removed
+  long long acc = 1; tlin = 0;
+  for (int d = 0; d < g.nd; d++) if (d != ps.dir) { tlin += acc * (id[d] + g.h); acc *= g.pd[d]; }
+  return true;
+}
+
+// dirichlet.py:28-41 with a state that varies along the face: table[m * tsize + tlin]
+__global__ void __launch_bounds__(128) k_bc_dirichlet_field(GridDev g, FieldPtrs f, int nv, PlaneSpec ps, const double *table, long long tsize) {
+  long long x, t;
+  if (!plane_point(g, ps, x, t)) return;
+  const long long out = (ps.side == 0 ? -1 : 1) * g.s[ps.dir];
+  for (int m = 0; m < nv; m++) {
+    const double v = table[m * tsize + t];
+    for (int h = 0; h <= ps.nh; h++) f.q[m][x + h * out] = v;
+  }
+}
+// extrapolation.py:29-58
+__global__ void __launch_bounds__(128) k_bc_extrapolation(GridDev g, FieldPtrs f, int nv, PlaneSpec ps, int order) {
+  long long x, t;
+  if (!plane_point(g, ps, x, t)) return;
+  const long long out = (ps.side == 0 ? -1 : 1) * g.s[ps.dir], in = -out;
+  for (int m = 0; m < nv; m++) {
+    if (order == 0) {
+      const double v = f.q[m][x + in];
+      for (int h = 0; h <= ps.nh; h++) f.q[m][x + h * out] = v;
+    } else {
+      double a = f.q[m][x - out], b = f.q[m][x];
+      for (int h = 1; h <= ps.nh; h++) { const double v = 2.0 * b - a; f.q[m][x + h * out] = v; a = b; b = v; }
+    }
+  }
+}
+// inlet_pressure_extrapolate.py:32-66 (side 0)
+template <int ND>
+__global__ void __launch_bounds__(128) k_bc_inlet_pressure(GridDev g, FieldPtrs f, PhysConst c, PlaneSpec ps) {
+  long long x, t;
+  if (!plane_point(g, ps, x, t)) return;
+  const long long sd = g.s[ps.dir];
+  const double rhob = f.q[0][x];
+  double ub[ND], ke = 0.0;
+#pragma unroll
+  for (int d = 0; d < ND; d++) { ub[d] = fabs(f.q[1 + d][x] / rhob); ke += ub[d] * ub[d]; }
+  const double pb = (c.gama - 1.0) * (-0.5 * rhob * ke + f.q[ND + 1][x]);
+  const double ab = sqrt(c.gama * pb / rhob);
+  double un = ub[0];
+#pragma unroll
+  for (int d = 0; d < ND; d++) if (d == ps.dir) un = ub[d];
+  const bool sup = un >= ab;
+  if (sup) {
+#pragma unroll
+    for (int m = 0; m < ND + 2; m++) f.q[m][x] = f.q[m][x - sd];
+  } else {
+    const double E = f.q[ND + 1][x];
+    for (int h = 1; h <= ps.nh; h++) f.q[ND + 1][x - h * sd] = E;
+  }
+}
+// isothermal_wall.py:32-88
+template <int ND>
+__global__ void __launch_bounds__(128) k_bc_isothermal_wall(GridDev g, FieldPtrs f, PhysConst c, PlaneSpec ps) {
+  long long x, t;
+  if (!plane_point(g, ps, x, t)) return;
+  const long long out = (ps.side == 0 ? -1 : 1) * g.s[ps.dir], in = -out;
+  const double gm = c.gama, M2 = c.Minf * c.Minf;
+  const double rw = f.q[0][x];
+#pragma unroll
+  for (int d = 0; d < ND; d++) f.q[1 + d][x] = 0.0;
+  const double Ew = rw * c.Twall / (gm * (gm - 1.0) * M2);
+  f.q[ND + 1][x] = Ew;
+  const double Pw = (gm - 1.0) * (-0.0 / rw + Ew);
+  const long long xa = x + in;
+  double kea = 0.0;
+  const double ra = f.q[0][xa];
+#pragma unroll
+  for (int d = 0; d < ND; d++) { const double m = f.q[1 + d][xa]; kea += 0.5 * m * m; }
+  const double Ta = M2 * gm * (gm - 1.0) * (-kea / ra + f.q[ND + 1][xa]) / ra;
+  for (int h = 1; h <= ps.nh; h++) {
+    const long long xi = x + h * in, xo = x + h * out;
+    const double Th = (h + 1) * c.Twall - h * Ta;
+    const double rh = M2 * gm * Pw / Th;
+    const double ri = f.q[0][xi];
+    double u2 = 0.0, uu[ND];
+#pragma unroll
+    for (int d = 0; d < ND; d++) { uu[d] = f.q[1 + d][xi] / ri; u2 += uu[d] * uu[d]; }
+    f.q[0][xo] = rh;
+#pragma unroll
+    for (int d = 0; d < ND; d++) f.q[1 + d][xo] = -rh * uu[d];
+    f.q[ND + 1][xo] = Pw / (gm - 1.0) + 0.5 * rh * u2;
+  }
+}
+// symmetry.py:23-50 (cartesian normal)
+__global__ void __launch_bounds__(128) k_bc_symmetry(GridDev g, FieldPtrs f, int nv, PlaneSpec ps) {
+  long long x, t;
+  if (!plane_point(g, ps, x, t)) return;
+  const long long out = (ps.side == 0 ? -1 : 1) * g.s[ps.dir], in = -out;
+  for (int h = 1; h <= ps.nh; h++)
+    for (int m = 0; m < nv; m++) {
+      const double v = f.q[m][x + h * in];
+      f.q[m][x + h * out] = (m == 1 + ps.dir) ? v - 2.0 * v : v;
+    }
 }
 
 // FP64 pipe micro-benchmark: 8 independent DFMA chains per thread

@@ -38,6 +38,30 @@ struct SchemeParams {
   double kfast6;   // 0.98 (4 C_T)^(-1/6): same for the 4 stencils of TENO6
 };
 
+// adaptive TENO (teno.py:430-443): C_T = 10^-e, e = floor(a1 - a2 (1 - (1-theta)^4 (1+4 theta))) from the Ducros sensor.
+// e is a small integer, so C_T and the derived constants come from tables built on the host with the same pow().
+struct AdaptiveCT {
+  int on;
+  double a1, a2;
+  double ct[16], k5[16], k6[16];
+};
+OSB_HD int adaptive_exponent(const AdaptiveCT &ad, double theta) {
+  const double om = 1.0 - theta;
+  const double e = floor(ad.a1 - ad.a2 * (-(om * om) * (om * om) * (4.0 * theta + 1.0) + 1.0));
+  const int i = (int)e;
+  return i < 0 ? 0 : (i > 15 ? 15 : i);
+}
+inline AdaptiveCT make_adaptive_ct(bool on, double a1, double a2) {
+  AdaptiveCT ad;
+  ad.on = on ? 1 : 0; ad.a1 = a1; ad.a2 = a2;
+  for (int e = 0; e < 16; e++) {
+    ad.ct[e] = pow(10.0, -(double)e);
+    ad.k5[e] = 0.98 * pow(3.0 * ad.ct[e], -1.0 / 6.0);
+    ad.k6[e] = 0.98 * pow(4.0 * ad.ct[e], -1.0 / 6.0);
+  }
+  return ad;
+}
+
 inline SchemeParams make_scheme_params(double eps, double ct) {
   SchemeParams s;
   s.eps = eps; s.teno_ct = ct; s.eps16 = 16.0 * eps;

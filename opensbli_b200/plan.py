@@ -19,6 +19,12 @@ JSON-able dict; `to_text` serialises it to the line format parsed by the C ABI (
     constants       {name: float}                 gama, Minf, Re, Pr, dt, eps, TENO_CT, ...
     bc              [[side0, side1] per direction] each {'type': 'periodic'} | {'type': 'dirichlet', 'q': [...]}
                     | {'type': 'exchange'} (halo owned by the neighbouring rank of a slab decomposition)
+                    | {'type': 'isothermal_wall'} | {'type': 'extrapolation', 'order': 0|1} | {'type': 'symmetry'}
+                    | {'type': 'inlet_pressure_extrapolate'} | {'type': 'dirichlet_field', 'table': ndarray [nv, tangential]}
+                    every non-periodic face may carry 'closure': 'reduced_access' | 'carpenter' (one-sided derivative rows)
+    viscosity       {'type': 'constant'} | {'type': 'sutherland'} | {'type': 'power', 'exponent': e}
+    metric_fields   per direction None | 'D11'...: stretched direction; fields['D11'], fields['SD111'] hold the metric arrays
+    teno_adaptive   bool: C_T from the Ducros sensor (constants teno_a1, teno_a2, epsilon)
     init            optional list of [lhs, rhs] assignment strings (numpy syntax) for the cold initialisation
     niter           optional int
 """
@@ -26,6 +32,15 @@ import copy
 import json
 
 CONV = ('central', 'weno', 'teno')
+BC_TYPES = ('periodic', 'dirichlet', 'exchange', 'isothermal_wall', 'extrapolation', 'inlet_pressure_extrapolate', 'symmetry',
+            'dirichlet_field')
+
+# one-sided derivative closures: rows idx = 0.. next to the face x weights of the boundary-absolute points 0..np-1
+# (reduced_access_scheme.py:36-43,76-83; Carpenter's first-derivative rows are taken from the scheme object by the back end)
+CLOSURES = {
+    'reduced_access': {'d1': [[-25.0 / 12, 48.0 / 12, -36.0 / 12, 16.0 / 12, -3.0 / 12], [-3.0 / 12, -10.0 / 12, 18.0 / 12, -6.0 / 12, 1.0 / 12]],
+                       'd2': [[35.0 / 12, -104.0 / 12, 114.0 / 12, -56.0 / 12, 11.0 / 12], [11.0 / 12, -20.0 / 12, 6.0 / 12, 4.0 / 12, -1.0 / 12]]},
+}
 
 
 class PlanError(ValueError):
@@ -54,7 +69,7 @@ def validate(plan):
     for d in range(nd):
         for s in range(2):
             b = plan['bc'][d][s]
-            if b['type'] not in ('periodic', 'dirichlet', 'exchange'):
+            if b['type'] not in BC_TYPES:
                 raise PlanError("boundary condition '%s' is not implemented by the B200 back end" % b['type'])
             if b['type'] == 'dirichlet' and len(b.get('q', ())) != nd + 2:
                 raise PlanError('dirichlet bc needs %d conservative values' % (nd + 2))
@@ -86,13 +101,35 @@ def to_text(plan):
          'rk_b ' + ' '.join(_f(v) for v in plan['rk_b'])]
     for k, v in sorted(plan['constants'].items()):
         L.append('const %s %s' % (k, _f(v)))
+    closures = set()
     for d in range(nd):
         for s in range(2):
             b = plan['bc'][d][s]
+            cl = ' closure' if b.get('closure') else ''
+            if b.get('closure'):
+                closures.add(b['closure'])
             if b['type'] == 'dirichlet':
-                L.append('bc %d %d dirichlet %s' % (d, s, ' '.join(_f(v) for v in b['q'])))
+                L.append('bc %d %d dirichlet %s%s' % (d, s, ' '.join(_f(v) for v in b['q']), cl))
+            elif b['type'] == 'extrapolation':
+                L.append('bc %d %d extrapolation %d%s' % (d, s, int(b.get('order', 0)), cl))
             else:
-                L.append('bc %d %d %s' % (d, s, b['type']))
+                L.append('bc %d %d %s%s' % (d, s, b['type'], cl))
+    if len(closures) > 1:
+        raise PlanError('only one closure scheme per block is implemented (got %s)' % sorted(closures))
+    for name in closures:
+        tab = plan.get('closures', CLOSURES).get(name) or CLOSURES.get(name)
+        if tab is None:
+            raise PlanError("no coefficient table for closure '%s'" % name)
+        for key in ('d1', 'd2'):
+            rows = tab[key]
+            L.append('closure_%s %d %d %s' % (key, len(rows), len(rows[0]), ' '.join(_f(v) for r in rows for v in r)))
+    visc = plan.get('viscosity', {'type': 'constant'})
+    L.append('viscosity %s%s' % (visc['type'], ' ' + _f(visc['exponent']) if visc['type'] == 'power' else ''))
+    for d, name in enumerate(plan.get('metric_fields', [None] * nd)):
+        if name:
+            L.append('metric %d 1' % d)
+    if plan.get('teno_adaptive'):
+        L.append('teno_adaptive 1')
     return '\n'.join(L) + '\n'
 
 

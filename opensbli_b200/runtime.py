@@ -15,7 +15,7 @@ _lib = None
 FAMILIES = ('prim', 'flux', 'central', 'viscous', 'rk', 'bc')
 
 SYMBOLS = ('osb_create', 'osb_destroy', 'osb_last_error', 'osb_set_const_f64', 'osb_get_const_f64',
-           'osb_num_fields', 'osb_field_name', 'osb_field_info', 'osb_upload', 'osb_download', 'osb_device_ptr',
+           'osb_num_fields', 'osb_field_name', 'osb_field_info', 'osb_upload', 'osb_download', 'osb_device_ptr', 'osb_upload_face',
            'osb_step', 'osb_step_begin', 'osb_stage', 'osb_sync', 'osb_apply_bcs', 'osb_residual', 'osb_step_timed', 'osb_timer_start', 'osb_timer_stop', 'osb_advance_host',
            'osb_launch_count', 'osb_profile_step', 'osb_ipc_export', 'osb_ipc_import', 'osb_halo_push',
            'osb_measure_fp64_peak')
@@ -48,6 +48,7 @@ def load_library(path=None):
     lib.osb_upload.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
     lib.osb_download.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
     lib.osb_device_ptr.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+    lib.osb_upload_face.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.osb_step.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.osb_sync.argtypes = [ctypes.c_void_p]
     lib.osb_step_begin.argtypes = [ctypes.c_void_p]
@@ -93,6 +94,15 @@ class Simulation(object):
         self.nv = self.ndim + 2
         self.shape = tuple(int(plan['np'][d]) + 2 * self.HALO for d in reversed(range(self.ndim)))
         self.q_names = ['rho'] + ['rhou%d' % d for d in range(self.ndim)] + ['rhoE']
+        # cold-path inputs carried by the plan: metric fields and tabulated Dirichlet states
+        for name, arr in plan.get('fields', {}).items():
+            self.upload(name, arr)
+        for d in range(self.ndim):
+            for s in range(2):
+                b = plan['bc'][d][s]
+                if b['type'] == 'dirichlet_field':
+                    t = np.ascontiguousarray(b['table'], dtype=np.float64)
+                    self._check(self.lib.osb_upload_face(self.ctx, d, s, t.ctypes.data), 'osb_upload_face')
 
     # -- plumbing
     def _check(self, rc, what):
