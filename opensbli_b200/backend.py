@@ -58,7 +58,10 @@ class _Printer(object):
 
         class P(NumPyPrinter):
             def _print_DataSet(s, e):
-                return _strip(e.base)
+                off = tuple(int(i) for i in e.indices)
+                if any(off):
+                    return "_A('%s', %r)" % (_strip(e.base), off)
+                return "_A('%s')" % _strip(e.base)
 
             def _print_Grididx(s, e):
                 return 'idx%d' % int(e.number)
@@ -67,7 +70,7 @@ class _Printer(object):
                 if type(e).__name__ == 'Grididx':
                     return 'idx%d' % int(e.number)
                 if type(e).__name__ == 'DataSet':
-                    return _strip(e.base)
+                    return s._print_DataSet(e)
                 return str(e)
 
             def _print_Piecewise(s, e):
@@ -95,24 +98,35 @@ class _Printer(object):
         return self.p.doprint(expr)
 
 
-def _cold_statements(kernel):
+def _cold_kernel(kernel):
+    """A cold (one-off or boundary-value) kernel as data: its iteration range (C expressions in block0np{d}) and an
+    ordered list of assignments  [lhs name, lhs offset or None for a kernel-local variable, rhs in numpy syntax]."""
+    from sympy.printing.c import ccode
     pr = _Printer()
     out = []
     for e in kernel.equations:
         if not hasattr(e, 'lhs'):
             raise UnsupportedByB200('cold kernel %s: unsupported equation %r' % (_name(kernel), e))
-        out.append([pr(e.lhs), pr(e.rhs)])
-    return out
+        if type(e.lhs).__name__ == 'DataSet':
+            lhs, off = _strip(e.lhs.base), [int(i) for i in e.lhs.indices]
+        else:
+            lhs, off = str(e.lhs), None
+        out.append([lhs, off, pr(e.rhs)])
+    rng = [ccode(r) for r in kernel.total_range()]
+    return {'name': _name(kernel), 'range': rng, 'statements': out}
 
 
 def _lambdify_check(eq, canonical, names, ntry=8, tol=1e-12):
     """numerically compare eq.rhs with canonical(**values) on random positive inputs."""
     from sympy import lambdify, Symbol
-    from opensbli.core.opensbliobjects import DataSet, ConstantObject
-    atoms = list(eq.rhs.atoms(DataSet)) + list(eq.rhs.atoms(ConstantObject))
-    rep = {a: Symbol('v_' + (_strip(a.base) if type(a).__name__ == 'DataSet' else str(a))) for a in atoms}
-    syms = sorted(set(rep.values()), key=str)
-    f = lambdify(syms, eq.rhs.xreplace(rep), 'math')
+    from opensbli.core.opensbliobjects import DataSet
+    rep = {a: Symbol('v_' + _strip(a.base)) for a in eq.rhs.atoms(DataSet)}
+    expr = eq.rhs.xreplace(rep)
+    # constants may be ConstantObjects or plain Symbols (apps build BC equations with parse_expr): go by name
+    rep2 = {a: Symbol('v_' + str(a)) for a in expr.free_symbols if not str(a).startswith('v_')}
+    expr = expr.xreplace(rep2)
+    syms = sorted(expr.free_symbols, key=str)
+    f = lambdify(syms, expr, 'math')
     rng = np.random.default_rng(0)
     for _ in range(ntry):
         vals = {str(s)[2:]: float(0.5 + rng.random()) for s in syms}
@@ -132,17 +146,34 @@ def _check_constituent(kernels, ndim):
     }
     for d in range(ndim):
         canon['u%d' % d] = (lambda d: (lambda v: v['rhou%d' % d] / v['rho']))(d)
-    seen = []
+    info = {'viscosity': {'type': 'constant'}, 'sensor': False}
     for k in kernels:
+        lhs_names = [(_strip(e.lhs.base) if hasattr(e.lhs, 'base') else str(e.lhs)) for e in k.equations if hasattr(e, 'lhs')]
+        if 'theta' in lhs_names:          # modified Ducros sensor (shock_sensors.py:12-49), recognised by its output array
+            from sympy import tanh
+            if not any(e.rhs.has(tanh) for e in k.equations if hasattr(e, 'rhs')):
+                raise UnsupportedByB200('shock sensor %s is not the modified Ducros sensor' % _name(k))
+            info['sensor'] = True
+            continue
         for e in k.equations:
             lhs = _strip(e.lhs.base) if hasattr(e.lhs, 'base') else str(e.lhs)
+            if lhs == 'mu':
+                suth = lambda v: v['T'] ** 1.5 * (1.0 + v['SuthT'] / v['RefT']) / (v['T'] + v['SuthT'] / v['RefT'])
+                if _lambdify_check(e, suth, None):
+                    info['viscosity'] = {'type': 'sutherland'}
+                    continue
+                from sympy import Pow
+                pw = [a for a in e.rhs.atoms(Pow)]
+                if len(pw) == 1 and e.rhs == pw[0] and pw[0].exp.is_number:
+                    info['viscosity'] = {'type': 'power', 'exponent': float(pw[0].exp)}
+                    continue
+                raise UnsupportedByB200('viscosity law mu = %s is not implemented (Sutherland and T**n are)' % e.rhs)
             if lhs not in canon:
-                raise UnsupportedByB200("constituent relation for '%s' (kernel %s) is outside the canonical ideal-gas set "
-                                        "{u_i, p, a, T} the B200 kernels implement" % (lhs, _name(k)))
+                raise UnsupportedByB200("constituent relation for '%s' (kernel %s) is outside the set {u_i, p, a, T, mu, theta} "
+                                        "the B200 kernels implement" % (lhs, _name(k)))
             if not _lambdify_check(e, canon[lhs], None):
                 raise UnsupportedByB200("constituent relation %s = %s differs from the canonical form" % (lhs, e.rhs))
-            seen.append(lhs)
-    return seen
+    return info
 
 
 def _datasets_used(kernels):
@@ -165,8 +196,7 @@ def _recon_info(k):
         info['order'] = {3: 5, 4: 6}.get(nst)
         if info['order'] is None:
             raise UnsupportedByB200('TENO with %d candidate stencils is not implemented' % nst)
-        if 'TENO_CT' in names:
-            raise UnsupportedByB200('adaptive TENO (shock-sensor controlled C_T) is not implemented yet')
+        info['teno_adaptive'] = 'TENO_CT' in names
         info['weno_formulation'] = 'JS'
     else:
         nst = len(set(n for n in names if re.match(r'omega_\d+$', n)))
@@ -180,9 +210,71 @@ def _recon_info(k):
     info['averaging'] = 'roe' if ('AVG_%d_inv_rho' % d) in names else 'simple'
     used = _datasets_used([k])
     extra = [u for u in used if re.match(r'(D\d\d|detJ|SD\d+)$', u)]
-    if extra:
+    if extra:   # full curvilinear eigensystems (metric direction cosines, euler_eigensystem.py:18-54) are not implemented
         raise UnsupportedByB200('curvilinear metric terms %s in %s are not implemented yet' % (sorted(extra), _name(k)))
+    info.setdefault('teno_adaptive', False)
     return info
+
+
+def _metric_directions(kernels, ndim):
+    """Stretched directions from the metric arrays the residual / viscous loops read: only diagonal metrics D_dd
+    (+ SD_ddd) are implemented, i.e. grids stretched along their own coordinate (metric.py:137-147)."""
+    used = _datasets_used(kernels)
+    out = [None] * ndim
+    for u in used:
+        m = re.match(r'S?D(\d)(\d)(\d?)$', u)
+        if m:
+            idx = [int(x) for x in m.groups() if x != '']
+            if len(set(idx)) != 1:
+                raise UnsupportedByB200('off-diagonal metric term %s: general curvilinear grids are not implemented yet' % u)
+            out[idx[0]] = 'D%d%d' % (idx[0], idx[0])
+        elif u == 'detJ':
+            raise UnsupportedByB200('detJ in the hot loops (strong-conservation curvilinear form) is not implemented yet')
+    return out
+
+
+def _closure_tables(kernels, ndim):
+    """One-sided closure rows from the idx-conditional formulas of the first-derivative loops
+    (opensblifunctions.py:523-534).  Returns ({(dir, side): nrows}, d1 table) with the table read off the equations:
+    row r = weights of the boundary-absolute points 0..np-1."""
+    from sympy import Piecewise, Eq
+    from opensbli.core.opensbliobjects import DataSet, Grididx
+    faces, table = {}, None
+    for k in kernels:
+        for e in k.equations:
+            for pw in e.rhs.atoms(Piecewise):
+                rows0 = {}
+                for expr, cond in pw.args:
+                    if cond is True or cond == True or not isinstance(cond, Eq):  # noqa: E712
+                        continue
+                    idxs = list(cond.lhs.atoms(Grididx))
+                    if len(idxs) != 1:
+                        continue
+                    d = int(idxs[0].number)
+                    side = 0 if cond.lhs == idxs[0] else 1
+                    row = int(cond.rhs) if side == 0 else int(cond.rhs) - 1
+                    faces[(d, side)] = max(faces.get((d, side), 0), row + 1)
+                    if side == 0:
+                        rows0[row] = (expr, d)
+                if rows0 and table is None and len(e.rhs.atoms(DataSet)) and all(len(x.atoms(DataSet)) >= 4 for x, _ in rows0.values()):
+                    # only first-derivative formulas of a plain dataset are used to read the weights
+                    bases = set(ds.base for x, _ in rows0.values() for ds in x.atoms(DataSet))
+                    if len(bases) != 1:
+                        continue
+                    tab = []
+                    for r in sorted(rows0):
+                        expr, d = rows0[r]
+                        w = {}
+                        ex = expr.expand()
+                        for ds in ex.atoms(DataSet):
+                            cf = ex.coeff(ds)
+                            syms = [a for a in cf.free_symbols]
+                            cf = cf.subs({a: 1 for a in syms})      # strip the 1/Delta factor
+                            w[int(ds.indices[d]) + r] = float(cf)
+                        tab.append([w.get(p, 0.0) for p in range(max(w) + 1)])
+                    n = max(len(t) for t in tab)
+                    table = [t + [0.0] * (n - len(t)) for t in tab]
+    return faces, table
 
 
 def _const_value(c):
@@ -214,19 +306,19 @@ def extract_plan(algorithm):
     q_names = ['rho'] + ['rhou%d' % d for d in range(ndim)] + ['rhoE']
 
     # ---- stage loop: classify every kernel
-    cr, recon, central_conv, viscous, rk_kernels, stage_bcs, unknown = [], [], [], [], [], [], []
+    cr, recon, resid, central_conv, viscous, rk_kernels, stage_bcs, unknown = [], [], [], [], [], [], [], []
     for c in in_stage:
         t, n = type(c).__name__, _name(c)
         if t == 'ExchangeSelf' or ' boundary dir' in n:
             stage_bcs.append(c)
         elif t != 'Kernel':
             unknown.append(c)
-        elif n.startswith('CR'):
+        elif n.startswith('CR') or n == 'ConstituentRelations evaluation':
             cr.append(c)
         elif re.match(r'LLF(Teno|Weno)_reconstruction_\d_direction', n):
             recon.append(c)
         elif re.match(r'LLF(Teno|Weno) Residual', n):
-            pass
+            resid.append(c)
         elif n.startswith('Convective'):
             central_conv.append(c)
         elif n.startswith('Viscous') or n.startswith('Derivative evaluation'):
@@ -237,31 +329,42 @@ def extract_plan(algorithm):
             unknown.append(c)
     if unknown:
         raise UnsupportedByB200('loops outside the accelerated hot path: %s' % sorted(set(_name(c) for c in unknown)))
-    _check_constituent(cr, ndim)
+    crinfo = _check_constituent(cr, ndim)
+    plan['viscosity'] = crinfo['viscosity']
     if recon and central_conv:
         raise UnsupportedByB200('mixed shock-capturing and central convective terms are not implemented')
     if recon:
         infos = [_recon_info(k) for k in recon]
         if sorted(i['direction'] for i in infos) != list(range(ndim)):
             raise UnsupportedByB200('reconstruction kernels do not cover every direction once')
-        for key in ('conv', 'order', 'weno_formulation', 'averaging'):
+        for key in ('conv', 'order', 'weno_formulation', 'averaging', 'teno_adaptive'):
             if len(set(i[key] for i in infos)) != 1:
                 raise UnsupportedByB200('direction-dependent %s is not implemented' % key)
             plan[key] = infos[0][key]
+        if plan['teno_adaptive'] and not crinfo['sensor']:
+            raise UnsupportedByB200('adaptive TENO without the Ducros sensor relation is not implemented')
     elif central_conv:
-        plan.update(conv='central', order=4)
-        if len([k for k in central_conv if 'CD' in _name(k)]) != {1: 6, 2: 18, 3: 39}.get(ndim, -1) and ndim == 3:
+        plan.update(conv='central', order=4, teno_adaptive=False)
+        if ndim == 3 and len([k for k in central_conv if 'CD' in _name(k)]) != 39:
             raise UnsupportedByB200('unexpected set of central convective derivative loops (only the skew-symmetric '
                                     'Navier-Stokes form of apps/taylor_green_vortex is implemented)')
     else:
         raise UnsupportedByB200('no convective discretisation found in the stage loop')
-    if viscous:
-        plan['viscous'] = True
-        used = _datasets_used(viscous)
-        if 'mu' in used:
-            raise UnsupportedByB200('variable viscosity (mu as a constituent relation) is not implemented yet')
-        if any(re.match(r'(D\d\d|detJ|SD\d+)$', u) for u in used):
-            raise UnsupportedByB200('curvilinear metric terms in the viscous loops are not implemented yet')
+    plan['viscous'] = bool(viscous)
+    if plan['viscosity']['type'] != 'constant' and not viscous:
+        plan['viscosity'] = {'type': 'constant'}
+    plan['metric_fields'] = _metric_directions(resid + viscous + [k for k in cr if _name(k) == 'ConstituentRelations evaluation'], ndim)
+    faces, d1tab = _closure_tables([k for k in viscous + cr if _name(k).startswith('Derivative evaluation') or _name(k) == 'ConstituentRelations evaluation'], ndim)
+    closure_name = None
+    if faces:
+        nrows = set(faces.values())
+        if len(nrows) != 1 or d1tab is None:
+            raise UnsupportedByB200('could not read the one-sided derivative closure from the derivative loops')
+        closure_name = {2: 'reduced_access', 4: 'carpenter'}.get(nrows.pop(), 'custom')
+        # second-derivative rows are the same in both of the reference's schemes (reduced_access_scheme.py:76-83,
+        # Carpenter_scheme.py:69-76); first-derivative rows were read off the equations
+        plan['closures'] = {closure_name: {'d1': d1tab, 'd2': [[35.0 / 12, -104.0 / 12, 114.0 / 12, -56.0 / 12, 11.0 / 12],
+                                                                 [11.0 / 12, -20.0 / 12, 6.0 / 12, 4.0 / 12, -1.0 / 12]]}}
 
     # ---- Runge-Kutta kind and coefficients (rk_LS.py:70-102, rk_sbli.py:58-61)
     consts = {}
@@ -277,7 +380,6 @@ def extract_plan(algorithm):
 
     # ---- boundary conditions, from the iteration-start list (algorithm.py:442)
     bc = [[None, None] for _ in range(ndim)]
-    cold_pr = _Printer()
     for c in [c for c in in_iter if type(c).__name__ == 'ExchangeSelf' or ' boundary dir' in _name(c)]:
         if type(c).__name__ == 'ExchangeSelf':
             arrays = [_strip(a) for a in c.transfer_arrays]
@@ -287,22 +389,44 @@ def extract_plan(algorithm):
             bc[int(c.direction)][int(side)] = {'type': 'periodic'}
             continue
         m = re.match(r'(\w+) boundary dir(\d) side(\d)', _name(c))
-        kind, d, s = m.group(1), int(m.group(2)), int(m.group(3))
-        if kind != 'Dirichlet':
+        kind, d, sd = m.group(1), int(m.group(2)), int(m.group(3))
+        entry = None
+        if kind == 'Dirichlet':
+            # imposed state = whatever the BC equations evaluate to on the face (constants or functions of the position)
+            entry = {'type': 'dirichlet_field', 'kernel': _cold_kernel(c)}
+        elif kind == 'Extrapolation':
+            # order 0 copies one interior value into boundary + halos; order 1 extrapolates linearly (extrapolation.py:37-55)
+            lin = any(e.rhs.is_Add for e in c.equations if hasattr(e, 'rhs'))
+            entry = {'type': 'extrapolation', 'order': 1 if lin else 0}
+        elif kind == 'InletPressureExtrapolate':
+            entry = {'type': 'inlet_pressure_extrapolate'}
+        elif kind == 'Symmetry':
+            entry = {'type': 'symmetry'}
+        elif kind == 'IsothermalWall':
+            # the wall-energy equation must be the canonical rhoE = rho Twall/(gama (gama-1) Minf^2) (isothermal_wall.py:40-45)
+            walls = [e for e in c.equations if hasattr(e.lhs, 'base') and _strip(e.lhs.base) == 'rhoE' and not any(e.lhs.indices)]
+            canon = lambda v: v['rho'] * v['Twall'] / (v['gama'] * (v['gama'] - 1.0) * v['Minf'] ** 2)
+            if not walls or not _lambdify_check(walls[0], canon, None):
+                raise UnsupportedByB200('isothermal wall with a non-canonical wall-energy equation is not implemented')
+            entry = {'type': 'isothermal_wall'}
+        else:
             raise UnsupportedByB200("boundary condition '%s' is not implemented yet" % kind)
-        bc[d][s] = {'type': 'dirichlet', 'statements': _cold_statements(c)}
+        if (d, sd) in faces:
+            entry['closure'] = closure_name
+        bc[d][sd] = entry
     if any(b is None for pair in bc for b in pair):
         raise UnsupportedByB200('a block face has no recognised boundary condition')
     plan['bc'] = bc
 
-    # ---- cold kernels before the time loop
-    init = []
+    # ---- cold kernels before the time loop (initialisation, metric evaluation, metric boundaries), in program order
+    cold = []
     for c in before:
         if type(c).__name__ == 'Kernel':
-            if not _name(c).startswith('Grid_based_initialisation'):
-                raise UnsupportedByB200('cold kernel %s is not implemented yet' % _name(c))
-            init += _cold_statements(c)
-    plan['init'] = init
+            n = _name(c)
+            if not (n.startswith('Grid_based_initialisation') or n.startswith('MetricsEquation evaluation') or n.startswith('Metric boundary')):
+                raise UnsupportedByB200('cold kernel %s is not implemented yet' % n)
+            cold.append(_cold_kernel(c))
+    plan['cold'] = cold
     plan['q_names'] = q_names
 
     # ---- constants, in declaration order (opsc.py:625-654)

@@ -71,60 +71,109 @@ def read_stub(text, decls):
     return env
 
 
-def _exec_statements(statements, ns):
-    for lhs, rhs in statements:
-        ns[lhs] = eval(rhs, {'numpy': np, 'math': math}, ns)
-    return ns
+class ColdRunner(object):
+    """numpy interpreter of the cold kernels distilled by the back end (initialisation, metric evaluation, metric
+    boundaries, Dirichlet states): every kernel is a range plus ordered assignments whose right-hand sides read
+    datasets at relative offsets through `_A(name, offset)`.  Vectorised over the kernel's range, which is valid
+    because no cold kernel reads, at another point, a value it has itself written."""
+
+    def __init__(self, nd, np_, env, halo=5):
+        self.nd, self.np_, self.env, self.h = nd, list(np_), dict(env), halo
+        self.shape = tuple(n + 2 * halo for n in reversed(self.np_))
+        self.arrays = {}
+
+    def array(self, name):
+        if name not in self.arrays:
+            self.arrays[name] = np.zeros(self.shape)       # OPS semantics: datasets start zeroed
+        return self.arrays[name]
+
+    def _slices(self, lo, hi, off):
+        return tuple(slice(lo[d] + off[d] + self.h, hi[d] + off[d] + self.h) for d in reversed(range(self.nd)))
+
+    def run(self, kernel):
+        rng = [int(c_eval(r, self.env)) for r in kernel['range']]
+        lo, hi = rng[0::2], rng[1::2]
+        ax = [np.arange(lo[d], hi[d]) for d in range(self.nd)]
+        grids = np.meshgrid(*reversed(ax), indexing='ij')[::-1]
+        zero = (0,) * self.nd
+
+        def _A(name, off=zero):
+            return self.array(name)[self._slices(lo, hi, off)]
+        ns = dict(self.env)
+        ns.update({'idx%d' % d: grids[d] for d in range(self.nd)})
+        g = {'numpy': np, 'math': math, '_A': _A}
+        for lhs, off, rhs in kernel['statements']:
+            val = eval(rhs, g, ns)
+            if off is None:
+                ns[lhs] = val
+            else:
+                self.array(lhs)[self._slices(lo, hi, off)] = val
+        return lo, hi
 
 
 def resolve(plan_sym, env):
-    """symbolic plan + parameter values -> numeric plan accepted by opensbli_b200.Simulation."""
+    """symbolic plan + parameter values -> numeric plan accepted by opensbli_b200.Simulation (cold kernels evaluated:
+    metric fields, tabulated Dirichlet states); returns (plan, ColdRunner holding every cold dataset)."""
     nd = plan_sym['ndim']
     p = {k: plan_sym[k] for k in ('ndim', 'conv', 'order', 'weno_formulation', 'averaging', 'viscous', 'rk', 'rk_a', 'rk_b')}
+    for k in ('viscosity', 'metric_fields', 'teno_adaptive', 'closures'):
+        if k in plan_sym:
+            p[k] = plan_sym[k]
     p['np'] = [int(env['block0np%d' % d]) for d in range(nd)]
     p['delta'] = [float(env['Delta%dblock0' % d]) for d in range(nd)]
     p['constants'] = {k: float(v) for k, v in env.items() if not k.startswith(('block0np', 'Delta', 'niter'))}
     p['niter'] = int(env.get('niter', 0))
+    cold = ColdRunner(nd, p['np'], env)
+    for k in plan_sym.get('cold', []):
+        cold.run(k)
+    p['fields'] = {}
+    for d, name in enumerate(p.get('metric_fields') or []):
+        if name:
+            for f in (name, 'S' + name + str(d)):
+                p['fields'][f] = cold.array(f).copy()
     bc = []
     for d in range(nd):
         pair = []
         for s in range(2):
-            b = plan_sym['bc'][d][s]
-            if b['type'] == 'dirichlet':
-                ns = _exec_statements(b['statements'], dict(env))
-                pair.append({'type': 'dirichlet', 'q': [float(ns[n]) for n in plan_sym['q_names']]})
-            else:
-                pair.append({'type': b['type']})
+            b = dict(plan_sym['bc'][d][s])
+            if b['type'] == 'dirichlet_field':
+                # evaluate the BC equations on a scratch copy of the datasets, read the imposed state off the boundary plane
+                scratch = ColdRunner(nd, p['np'], env)
+                scratch.arrays = {k: v.copy() for k, v in cold.arrays.items()}
+                scratch.run(b.pop('kernel'))
+                plane = p['np'][d] - 1 + scratch.h if s == 1 else scratch.h
+                tabs = []
+                for n in plan_sym['q_names']:
+                    a = np.moveaxis(scratch.array(n), nd - 1 - d, 0)
+                    tabs.append(a[plane].reshape(-1))
+                table = np.stack(tabs)
+                if all(np.all(t == t[0]) for t in table):        # constant state: plain Dirichlet
+                    b = {'type': 'dirichlet', 'q': [float(t[0]) for t in table], **({'closure': b['closure']} if b.get('closure') else {})}
+                else:
+                    b['table'] = table
+            pair.append(b)
         bc.append(pair)
     p['bc'] = bc
-    return _plan.validate(p)
+    return _plan.validate(p), cold
 
 
-def initial_state(plan_sym, plan_num, env, halo=5):
-    """Evaluate the Grid_based_initialisation statements over the padded block (gridbasedinit.py:46-57)."""
-    nd = plan_num['ndim']
-    ax = [np.arange(-halo, n + halo) for n in plan_num['np']]
-    grids = np.meshgrid(*reversed(ax), indexing='ij')[::-1]
-    ns = dict(env)
-    for d in range(nd):
-        ns['idx%d' % d] = grids[d]
-    _exec_statements(plan_sym['init'], ns)
-    shape = grids[0].shape
-    return [np.ascontiguousarray(np.broadcast_to(np.asarray(ns[n], dtype=np.float64), shape)) for n in plan_sym['q_names']]
+def initial_state(plan_sym, cold):
+    return [np.ascontiguousarray(cold.array(n)) for n in plan_sym['q_names']]
 
 
 def load_case(workdir='.'):
     plan_sym = json.load(open(os.path.join(workdir, PLAN_FILE)))
     env = read_stub(open(os.path.join(workdir, STUB_FILE)).read(), plan_sym['constant_decls'])
-    return plan_sym, env, resolve(plan_sym, env)
+    plan_num, cold = resolve(plan_sym, env)
+    return plan_sym, env, plan_num, cold
 
 
 def main(argv=None):
     argv = sys.argv[1:] if argv is None else argv
     workdir = argv[0] if argv else '.'
     from .runtime import Simulation
-    plan_sym, env, plan_num = load_case(workdir)
-    q0 = initial_state(plan_sym, plan_num, env)
+    plan_sym, env, plan_num, cold = load_case(workdir)
+    q0 = initial_state(plan_sym, cold)
     niter = plan_num.get('niter', 0)
     with Simulation(plan_num) as sim:
         sim.set_state(q0)

@@ -17,6 +17,7 @@ REF = '/root/reference'
 APPS = {
     'tgv_teno5': (os.path.join(REPO, 'apps', 'tgv_teno5.py'), [], 'tgv_teno5_16'),
     'tgv_central4': (REF + '/apps/taylor_green_vortex/taylor_green_vortex.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'tgv_central4_16'),
+    'katzer': (REF + '/apps/katzer_SBLI/katzer_SBLI.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'katzer_60x40'),
     'sod_teno5': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'sod_teno5_n200'),
 }
 
@@ -41,8 +42,12 @@ def run_app(name, workdir):
 
 
 def comparable(plan):
-    keys = ('ndim', 'np', 'conv', 'order', 'averaging', 'viscous', 'rk', 'rk_a', 'rk_b', 'bc')
+    keys = ('ndim', 'np', 'conv', 'order', 'averaging', 'viscous', 'rk', 'rk_a', 'rk_b')
     p = {k: plan[k] for k in keys}
+    p['bc'] = [[{k: v for k, v in b.items() if k != 'table'} for b in pair] for pair in plan['bc']]
+    p['viscosity'] = plan.get('viscosity', {'type': 'constant'})
+    p['teno_adaptive'] = bool(plan.get('teno_adaptive'))
+    p['metric_fields'] = plan.get('metric_fields') or [None] * plan['ndim']
     if plan['conv'] == 'weno':
         p['weno_formulation'] = plan.get('weno_formulation', 'JS')
     return p
@@ -61,15 +66,17 @@ def test_b200_backend_distils_expected_plan(name, tmp_path):
         workdir = os.path.join(PLANS, name)
         if not os.path.exists(os.path.join(workdir, 'opensbli.cpp')):
             pytest.skip('no committed plan fixture for %s' % name)
-    plan_sym, env, plan_num = R.load_case(workdir)
+    plan_sym, env, plan_num, _cold = R.load_case(workdir)
     want, _ = load_fixture(APPS[name][2])
     got = comparable(plan_num)
     exp = comparable(want)
     # the app's own grid size may differ from the fixture's
     got['np'] = exp['np']
     assert json.loads(json.dumps(got)) == json.loads(json.dumps(exp))
-    for k in ('gama',):
-        assert plan_num['constants'][k] == want['constants'][k]
+    for k in want['constants']:
+        if k not in ('dt',) and k in plan_num['constants']:
+            assert plan_num['constants'][k] == want['constants'][k], k
+    assert 'gama' in plan_num['constants']
     # the stub keeps the reference's contract: every parameter was substituted, `int iter=0;` is present
     stub = open(os.path.join(workdir, 'opensbli.cpp')).read()
     assert '=Input;' not in stub and 'int iter=0;' in stub
@@ -82,11 +89,11 @@ def test_initial_state_from_cold_kernel_matches_reference_init():
     workdir = os.path.join(PLANS, 'tgv_teno5')
     if not os.path.exists(os.path.join(workdir, 'opensbli.cpp')):
         pytest.skip('plan fixture missing')
-    plan_sym, env, plan_num = R.load_case(workdir)
+    plan_sym, env, plan_num, _cold = R.load_case(workdir)
     want, states = load_fixture('tgv_teno5_16')
     env = dict(env, block0np0=16, block0np1=16, block0np2=16, Delta0block0=want['delta'][0], Delta1block0=want['delta'][1], Delta2block0=want['delta'][2])
-    plan_num = R.resolve(plan_sym, env)
-    q0 = R.initial_state(plan_sym, plan_num, env)
+    plan_num, cold = R.resolve(plan_sym, env)
+    q0 = R.initial_state(plan_sym, cold)
     s = (slice(5, -5),) * 3
     for m in range(5):
         assert np.abs(q0[m][s] - states[0][m]).max() <= 1e-13 * max(1.0, np.abs(states[0][m]).max())
@@ -99,10 +106,10 @@ def test_sod_initial_state_and_dirichlet_states():
     workdir = os.path.join(PLANS, 'sod_teno5')
     if not os.path.exists(os.path.join(workdir, 'opensbli.cpp')):
         pytest.skip('plan fixture missing')
-    plan_sym, env, plan_num = R.load_case(workdir)
+    plan_sym, env, plan_num, cold = R.load_case(workdir)
     want, states = load_fixture('sod_teno5_n200')
     assert plan_num['niter'] == 1000 and plan_num['np'] == [200]
-    q0 = R.initial_state(plan_sym, plan_num, env)
+    q0 = R.initial_state(plan_sym, cold)
     for m in range(3):
         assert np.abs(q0[m][5:-5] - states[0][m]).max() <= 1e-15
     for s in range(2):
@@ -121,7 +128,7 @@ def test_unsupported_features_fail_loudly(tmp_path):
     """An app outside the accelerated path must raise, never silently fall back."""
     if not os.path.isdir(REF):
         pytest.skip('needs the reference front end')
-    app = REF + '/apps/katzer_SBLI/katzer_SBLI.py'
+    app = REF + '/apps/euler_wave_curvilinear/euler_wave.py'
     code = DRIVER % dict(oracle=os.path.join(REPO, 'oracle'), repo=REPO, ref=REF, app=app,
                          edits=[("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")])
     r = subprocess.run([sys.executable, '-W', 'ignore', '-c', code], cwd=str(tmp_path), env=dict(os.environ, PYTHONHASHSEED='0'),
