@@ -216,6 +216,54 @@ def _recon_info(k):
     return info
 
 
+KNOWN_CONSTANTS = re.compile(r'^(gama|gamma_m1|Minf|Re|Pr|dt|eps|TENO_CT|teno_a1|teno_a2|epsilon|SuthT|RefT|Twall|niter|'
+                             r'block0np\d|Delta\dblock0|inv_\d+|rc\d+|rcinv\d+|inv_rfact\d*_block0)$')
+
+
+def _check_constants_used(components):
+    """Every runtime constant the hot loops read must be one the hand-written kernels account for; anything else
+    (body-force constants c_j of the channel apps, user constants of custom terms) means the equations are not the
+    canonical system and must not be silently dropped."""
+    from opensbli.core.opensbliobjects import ConstantObject
+    bad = set()
+    for c in components:
+        if type(c).__name__ != 'Kernel':
+            continue
+        for e in c.equations:
+            if hasattr(e, 'rhs'):
+                for a in e.rhs.atoms(ConstantObject):
+                    if not KNOWN_CONSTANTS.match(str(a)):
+                        bad.add('%s (in %s)' % (a, _name(c)))
+    if bad:
+        raise UnsupportedByB200('the hot loops use constants outside the implemented canonical system: %s' % sorted(bad))
+
+
+def _check_central_form(kernels, ndim, q_names):
+    """Central(4): only the Blaisdell skew-symmetric form of apps/taylor_green_vortex, discretised by
+    Central.sbli_rhs_discretisation into one work array per derivative (scheme.py:187-271), on periodic boxes, is
+    implemented.  The set of derivative loops identifies it."""
+    got = set()
+    for k in kernels:
+        m = re.match(r'Convective CD (.+) x(\d) $', _name(k))
+        if m:
+            got.add((frozenset(m.group(1).replace('_B0', '').split('*')), int(m.group(2))))
+    want = set()
+    for d in range(ndim):
+        want.add((frozenset(['u%d' % d]), d))
+        want.add((frozenset(['p']), d))
+        want.add((frozenset(['p', 'u%d' % d]), d))
+        for q in q_names:
+            want.add((frozenset([q]), d))
+            want.add((frozenset([q, 'u%d' % d]), d))
+    if got != want:
+        raise UnsupportedByB200('central convective terms are not in the skew-symmetric form of apps/taylor_green_vortex '
+                                '(derivative loops differ: %s)' % sorted((sorted(a), b) for a, b in got ^ want)[:6])
+    for k in kernels:
+        from sympy import Piecewise
+        if any(e.rhs.has(Piecewise) for e in k.equations if hasattr(e, 'rhs')):
+            raise UnsupportedByB200('central convective derivatives with one-sided boundary closures are not implemented yet')
+
+
 def _metric_directions(kernels, ndim):
     """Stretched directions from the metric arrays the residual / viscous loops read: only diagonal metrics D_dd
     (+ SD_ddd) are implemented, i.e. grids stretched along their own coordinate (metric.py:137-147)."""
@@ -329,6 +377,7 @@ def extract_plan(algorithm):
             unknown.append(c)
     if unknown:
         raise UnsupportedByB200('loops outside the accelerated hot path: %s' % sorted(set(_name(c) for c in unknown)))
+    _check_constants_used(in_stage + in_iter)
     crinfo = _check_constituent(cr, ndim)
     plan['viscosity'] = crinfo['viscosity']
     if recon and central_conv:
@@ -345,9 +394,7 @@ def extract_plan(algorithm):
             raise UnsupportedByB200('adaptive TENO without the Ducros sensor relation is not implemented')
     elif central_conv:
         plan.update(conv='central', order=4, teno_adaptive=False)
-        if ndim == 3 and len([k for k in central_conv if 'CD' in _name(k)]) != 39:
-            raise UnsupportedByB200('unexpected set of central convective derivative loops (only the skew-symmetric '
-                                    'Navier-Stokes form of apps/taylor_green_vortex is implemented)')
+        _check_central_form(central_conv, ndim, q_names)
     else:
         raise UnsupportedByB200('no convective discretisation found in the stage loop')
     plan['viscous'] = bool(viscous)
