@@ -266,8 +266,20 @@ void launch_flux_scheme(osb_ctx *c) {
   else { roe ? launch_flux<ND, RECON_WENO5_JS, AVG_ROE>(c) : launch_flux<ND, RECON_WENO5_JS, AVG_SIMPLE>(c); }
 }
 
+template <int RK>
+void launch_viscous_tiled(osb_ctx *c, double a, double b) {
+  const GridDev &g = c->grid;
+  auto kern = k_viscous3d_tiled<RK>;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vt_smem_bytes()); attr_set = true; }
+  dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + VT_ZC - 1) / VT_ZC);
+  Launcher L(c, OSB_FAM_VISCOUS);
+  kern<<<gr, bl, vt_smem_bytes(), c->stream>>>(g, c->fp, c->pc, a, b);
+}
+
+// stage >= 0: fuse the RK update of that stage into the last spatial kernel where possible (returns true if fused)
 template <int ND>
-void launch_residual(osb_ctx *c) {
+bool launch_residual(osb_ctx *c, int stage = -1) {
   const GridDev &g = c->grid;
   launch_prim<ND>(c);
   if (c->plan.teno_adaptive) {
@@ -283,11 +295,18 @@ void launch_residual(osb_ctx *c) {
     launch_flux_scheme<ND>(c);
   }
   if (c->plan.viscous) {
+    if (ND == 3 && !c->general) {
+      if (stage < 0) launch_viscous_tiled<0>(c, 0.0, 0.0);
+      else if (c->plan.rk == RK_LS) launch_viscous_tiled<1>(c, c->plan.rk_a[stage], c->plan.rk_b[stage]);
+      else launch_viscous_tiled<2>(c, c->plan.rk_a[stage], c->plan.rk_b[stage]);
+      return stage >= 0;
+    }
     dim3 b(64, 2, 2);
     Launcher L(c, OSB_FAM_VISCOUS);
     if (c->general) k_viscous_general<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc, c->plan.cl, c->gp);
     else k_viscous<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc);
   }
+  return false;
 }
 
 void box_launch_cfg(const Box &b, int nv, unsigned &blocks) {
@@ -382,8 +401,7 @@ int step_nd(osb_ctx *c, int nsteps) {
     launch_bcs(c);
     if (c->plan.rk == RK_SBLI) launch_save<ND>(c);
     for (int s = 0; s < nstages; s++) {
-      launch_residual<ND>(c);
-      launch_rk<ND>(c, s);
+      if (!launch_residual<ND>(c, s)) launch_rk<ND>(c, s);
       launch_bcs(c);
     }
   }
@@ -394,7 +412,7 @@ int step_nd(osb_ctx *c, int nsteps) {
 template <int ND>
 int stage_nd(osb_ctx *c, int s) {
   if (s < 0) { launch_bcs(c); if (c->plan.rk == RK_SBLI) launch_save<ND>(c); }
-  else { launch_residual<ND>(c); launch_rk<ND>(c, s); launch_bcs(c); }
+  else { if (!launch_residual<ND>(c, s)) launch_rk<ND>(c, s); launch_bcs(c); }
   OSB_CUDA(c, cudaGetLastError());
   return 0;
 }

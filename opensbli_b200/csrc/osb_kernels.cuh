@@ -486,6 +486,156 @@ __global__ void __launch_bounds__(256, 2) k_viscous(GridDev g, FieldPtrs f, Phys
 }
 
 // -------------------------------------------------------------------------------------------------
+// 3-D viscous terms, shared-memory version (constant viscosity, uniform periodic grid) with the RK update fused in.
+// A block owns a 32 x 8 column in (x, y) and marches along z keeping the 5 planes k-2..k+2 of (u0, u1, u2, T) incl. a
+// halo of 2 in shared memory (ring buffer), so every stencil value is read from HBM once per column chunk.
+// With FUSE_RK the kernel finishes the stage: Residual (flux sweeps) + viscous terms -> low-storage / SBLI RK update of
+// q and the RK register; otherwise it leaves Residual += viscous (parity entry point osb_residual).
+// -------------------------------------------------------------------------------------------------
+constexpr int VT_X = 32, VT_Y = 8, VT_HX = VT_X + 4, VT_HY = VT_Y + 4, VT_PLANE = VT_HX * VT_HY, VT_ZC = 32;
+constexpr size_t vt_smem_bytes() { return sizeof(double) * 5 * 4 * VT_PLANE; }
+
+template <int RK>   // RK: 0 = residual only, 1 = low-storage update (rk_LS.py:139-166), 2 = SBLI update (rk_sbli.py:102-133)
+__global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled(GridDev g, FieldPtrs f, PhysConst c, double rkA, double rkB) {
+  extern __shared__ double vt_smem[];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * VT_X + tx;
+  const int i0 = blockIdx.x * VT_X, j0 = blockIdx.y * VT_Y, k0 = blockIdx.z * VT_ZC;
+  const int i = i0 + tx, j = j0 + ty;
+  const int kend = min(k0 + VT_ZC, g.np[2]);
+  const double *src[4] = {f.u[0], f.u[1], f.u[2], f.T};
+  auto S = [&](int slot, int v) -> double * { return vt_smem + (size_t)(slot * 4 + v) * VT_PLANE; };
+  auto load_plane = [&](int kk) {
+    const int slot = (kk + 10) % 5;
+    for (int e = tid; e < VT_PLANE; e += VT_X * VT_Y) {
+      const int yy = e / VT_HX, xx = e % VT_HX;
+      const int gi = i0 + xx - 2, gj = j0 + yy - 2;
+      if (gi < g.np[0] + 2 && gj < g.np[1] + 2) {
+        const long long x = g.off + gi + gj * g.s[1] + (long long)kk * g.s[2];
+#pragma unroll
+        for (int v = 0; v < 4; v++) S(slot, v)[e] = __ldg(src[v] + x);
+      }
+    }
+  };
+  for (int kk = k0 - 2; kk <= k0 + 2; kk++) load_plane(kk);
+  const double iRe = 1.0 / c.Re;
+  const double kq = iRe * (1.0 / (c.gama - 1.0)) * (1.0 / (c.Minf * c.Minf)) * (1.0 / c.Pr);
+  const int ce = (ty + 2) * VT_HX + tx + 2;
+  constexpr int NPF = (VT_PLANE + VT_X * VT_Y - 1) / (VT_X * VT_Y);
+  const bool active = i < g.np[0] && j < g.np[1];
+  __syncthreads();
+  for (int k = k0; k < kend; k++) {
+    // software pipeline: fetch plane k+3 and this point's Residual / RK register / q while plane k is computed
+    double pf[NPF][4];
+    const bool more = k + 1 < kend;
+    if (more) {
+#pragma unroll
+      for (int it = 0; it < NPF; it++) {
+        const int e = tid + it * VT_X * VT_Y;
+        const int yy = e / VT_HX, xx = e % VT_HX;
+        const int gi = i0 + xx - 2, gj = j0 + yy - 2;
+        if (e < VT_PLANE && gi < g.np[0] + 2 && gj < g.np[1] + 2) {
+          const long long xg = g.off + gi + gj * g.s[1] + (long long)(k + 3) * g.s[2];
+#pragma unroll
+          for (int v = 0; v < 4; v++) pf[it][v] = __ldg(src[v] + xg);
+        }
+      }
+    }
+    const long long x = g.off + i + j * g.s[1] + (long long)k * g.s[2];
+    double R[5], q[5], o[5];
+    if (active) {
+#pragma unroll
+      for (int m = 0; m < 5; m++) R[m] = f.R[m][x];
+      if (RK != 0) {
+#pragma unroll
+        for (int m = 0; m < 5; m++) { o[m] = f.rk[m][x]; q[m] = f.q[m][x]; }
+      }
+    }
+    if (active) {
+      const double *P[5][4];
+#pragma unroll
+      for (int dz = 0; dz < 5; dz++)
+#pragma unroll
+        for (int v = 0; v < 4; v++) P[dz][v] = S((k + dz - 2 + 10) % 5, v) + ce;
+      // first derivatives d u_a / d x_b and the Laplacian-like second derivatives at the point
+      double dv[3][3], d2[4][3];
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        const double *p = P[2][v];
+        const double fx = d1c(p[-2], p[-1], p[1], p[2], c.inv[0]);
+        const double fy = d1c(p[-2 * VT_HX], p[-VT_HX], p[VT_HX], p[2 * VT_HX], c.inv[1]);
+        const double fz = d1c(P[0][v][0], P[1][v][0], P[3][v][0], P[4][v][0], c.inv[2]);
+        if (v < 3) { dv[v][0] = fx; dv[v][1] = fy; dv[v][2] = fz; }
+        d2[v][0] = d2c(p[-2], p[-1], p[0], p[1], p[2], c.inv2[0]);
+        d2[v][1] = d2c(p[-2 * VT_HX], p[-VT_HX], p[0], p[VT_HX], p[2 * VT_HX], c.inv2[1]);
+        d2[v][2] = d2c(P[0][v][0], P[1][v][0], p[0], P[3][v][0], P[4][v][0], c.inv2[2]);
+      }
+      // mixed derivatives: derivative along the higher direction of the derivative along the lower one
+      auto dxy = [&](int v) {        // d/dy ( d/dx )
+        const double *p = P[2][v];
+        double r[4];
+        const int oy[4] = {-2 * VT_HX, -VT_HX, VT_HX, 2 * VT_HX};
+#pragma unroll
+        for (int q = 0; q < 4; q++) r[q] = d1c(p[oy[q] - 2], p[oy[q] - 1], p[oy[q] + 1], p[oy[q] + 2], c.inv[0]);
+        return d1c(r[0], r[1], r[2], r[3], c.inv[1]);
+      };
+      auto dxz = [&](int v) {        // d/dz ( d/dx )
+        double r[4];
+        const int pz[4] = {0, 1, 3, 4};
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const double *p = P[pz[q]][v]; r[q] = d1c(p[-2], p[-1], p[1], p[2], c.inv[0]); }
+        return d1c(r[0], r[1], r[2], r[3], c.inv[2]);
+      };
+      auto dyz = [&](int v) {        // d/dz ( d/dy )
+        double r[4];
+        const int pz[4] = {0, 1, 3, 4};
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const double *p = P[pz[q]][v]; r[q] = d1c(p[-2 * VT_HX], p[-VT_HX], p[VT_HX], p[2 * VT_HX], c.inv[1]); }
+        return d1c(r[0], r[1], r[2], r[3], c.inv[2]);
+      };
+      double vis[3];
+      vis[0] = iRe * ((4.0 / 3.0) * d2[0][0] + d2[0][1] + d2[0][2] + (1.0 / 3.0) * (dxy(1) + dxz(2)));
+      vis[1] = iRe * (d2[1][0] + (4.0 / 3.0) * d2[1][1] + d2[1][2] + (1.0 / 3.0) * (dxy(0) + dyz(2)));
+      vis[2] = iRe * (d2[2][0] + d2[2][1] + (4.0 / 3.0) * d2[2][2] + (1.0 / 3.0) * (dxz(0) + dyz(1)));
+      const double div = dv[0][0] + dv[1][1] + dv[2][2];
+      double e = kq * (d2[3][0] + d2[3][1] + d2[3][2]);
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int b = a + 1; b < 3; b++) { const double sab = dv[a][b] + dv[b][a]; e += iRe * sab * sab; }
+        e += iRe * (2.0 * dv[a][a] - (2.0 / 3.0) * div) * dv[a][a];
+        e += vis[a] * P[2][a][0];
+      }
+      R[1] += vis[0]; R[2] += vis[1]; R[3] += vis[2]; R[4] += e;
+      if (RK == 0) {
+#pragma unroll
+        for (int m = 1; m < 5; m++) f.R[m][x] = R[m];
+      } else {
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+          if (RK == 1) { const double t = c.dt * R[m] + rkA * o[m]; f.rk[m][x] = t; f.q[m][x] = rkB * t + q[m]; }
+          else { f.q[m][x] = c.dt * rkB * R[m] + o[m]; f.rk[m][x] = c.dt * rkA * R[m] + o[m]; }
+        }
+      }
+    }
+    __syncthreads();                 // every thread is done reading the slot of plane k-2
+    if (more) {
+      const int slot = (k + 3 + 10) % 5;
+#pragma unroll
+      for (int it = 0; it < NPF; it++) {
+        const int e = tid + it * VT_X * VT_Y;
+        const int yy = e / VT_HX, xx = e % VT_HX;
+        const int gi = i0 + xx - 2, gj = j0 + yy - 2;
+        if (e < VT_PLANE && gi < g.np[0] + 2 && gj < g.np[1] + 2) {
+#pragma unroll
+          for (int v = 0; v < 4; v++) S(slot, v)[e] = pf[it][v];
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // Runge-Kutta updates (rk_sbli.py:102-133, rk_LS.py:139-166)
 // -------------------------------------------------------------------------------------------------
 template <int ND>

@@ -6,7 +6,7 @@ timeout 1200 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider -x
 echo "pytest exit $?" >> gpurun_out/${TAG}_tests.log
 timeout 600 python bench.py --size 256 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_bench256.json 2> gpurun_out/${TAG}_bench256.err
 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench512.json 2> gpurun_out/${TAG}_bench512.err
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_viscous|k_rk_ls|k_prim" -s 6 -c 3 -o gpurun_out/${TAG}_flux python bench.py --size 256 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_flux|k_viscous3d" -s 8 -c 4 -o gpurun_out/${TAG}_flux python bench.py --size 256 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -4 gpurun_out/${TAG}_tests.log; python - <<PY
 import json
 for f in ('gpurun_out/${TAG}_bench256.json','gpurun_out/${TAG}_bench512.json'):
