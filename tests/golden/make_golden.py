@@ -92,10 +92,44 @@ def katzer_dirichlet_table(N0, halo=5):
 FIXTURES['katzer_60x40'] = ('katzer', katzer_plan(60, 40), [1, 10])
 
 
+def carpenter_tables():
+    """First-derivative rows of the reference's Carpenter closure, taken from the scheme object itself
+    (Carpenter_scheme.py:78-102, a 4x6 matrix al4^-1 ar4 evaluated by SymPy); second-derivative rows :69-76."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), 'oracle'))
+    import refshim
+    refshim.install()
+    from opensbli.core.boundary_conditions.Carpenter_scheme import Carpenter
+    c = Carpenter()
+    d1 = [[float(c.bc4_coefficients[i, j]) for j in range(6)] for i in range(4)]
+    d2 = [[float(c.bc4_2_coefficients[i, j]) for j in range(5)] for i in range(2)]
+    return {'d1': d1, 'd2': d2}
+
+
+def katzer_carpenter_plan(N0, N1):
+    p = katzer_plan(N0, N1)
+    for pair in p['bc']:
+        for b in pair:
+            b['closure'] = 'carpenter'
+    p['closures'] = {'carpenter': carpenter_tables()}
+    return p
+
+
+def tgv_sym_plan(N):
+    """apps/taylor_green_vortex/TGsym/TGsym.py: 1/8-domain TGV, Central(4) + RungeKutta(3), SymmetryBC on all faces."""
+    sym = [[dict(type='symmetry'), dict(type='symmetry')] for _ in range(3)]
+    return dict(ndim=3, np=[N, N, N], delta=[math.pi / (N - 1)] * 3, conv='central', order=4, averaging='roe', viscous=True,
+                constants=dict(gama=1.4, Minf=0.1, Re=800.0, Pr=0.71, dt=0.005), bc=sym, **SBLI3)
+
+
+if os.path.isdir('/root/reference'):
+    FIXTURES['katzer_carpenter_60x40'] = ('katzer_carpenter', katzer_carpenter_plan(60, 40), [1, 10])
+FIXTURES['tgv_sym_17'] = ('tgv_sym', tgv_sym_plan(17), [1, 3])
+
+
 def env_params(plan):
     P = {'dt': plan['constants']['dt']}
-    if 'metric_fields' in plan:      # Katzer: grid spacings follow from the sizes inside the generated program
-        P = {}
+    if 'metric_fields' in plan or plan['bc'][0][0]['type'] == 'symmetry':
+        P = {}                        # grid spacings follow from the sizes inside the generated program
     for d in range(plan['ndim']):
         P['block0np%d' % d] = plan['np'][d]
     return P
