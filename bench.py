@@ -267,7 +267,7 @@ def main():
     finite = bool(np.isfinite(chk).all())
 
     # ---- per-kernel-family device time (events around every launch of one step) -> roofline of the dominant family
-    prof = sim.profile_step() if world == 1 else None
+    prof = sim.profile_step()          # every rank takes part (the stage sequence contains the neighbour handshakes)
     roofline = roofline_hbm = None
     fp64_peak = opensbli_b200.measure_fp64_peak(local_rank)
     peaks = {}
@@ -346,6 +346,7 @@ def main():
                            'finite': finite},
                 'roofline': roofline, 'roofline_hbm': roofline_hbm, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e,
                 'gpu_launches': int(launches), 'fp64_peak_tflops_measured': fp64_peak,
+                'families_ms_rank0': {k: v['ms'] for k, v in prof.items()} if prof else None,
                 'alg_flop_per_update': ALG_FLOP_PER_UPDATE, 'achieved_alg_tflops': ALG_FLOP_PER_UPDATE * value / world / 1e12}
         print(json.dumps(line))
     dsim.close()

@@ -76,7 +76,8 @@ int osb_advance_host(osb_ctx *ctx, const double *const *q_in, double *const *q_o
 
 /* Instrumentation: number of kernels launched by this context so far; per-family device time of
  * one profiled step (events around each launch).  Families: see OSB_FAM_*. */
-enum { OSB_FAM_PRIM = 0, OSB_FAM_FLUX = 1, OSB_FAM_CENTRAL = 2, OSB_FAM_VISCOUS = 3, OSB_FAM_RK = 4, OSB_FAM_BC = 5, OSB_NFAM = 6 };
+enum { OSB_FAM_PRIM = 0, OSB_FAM_FLUX = 1, OSB_FAM_CENTRAL = 2, OSB_FAM_VISCOUS = 3, OSB_FAM_RK = 4, OSB_FAM_BC = 5,
+       OSB_FAM_SYNC = 6 /* waiting for neighbour ranks */, OSB_NFAM = 7 };
 int osb_launch_count(const osb_ctx *ctx, long long *count);
 int osb_profile_step(osb_ctx *ctx, double *family_ms /* [OSB_NFAM] */, long long *family_launches /* [OSB_NFAM] */);
 

@@ -83,6 +83,10 @@ struct osb_ctx {
   long long face_size[3] = {0, 0, 0};
   double *peer_q[2][5] = {{nullptr}};
   bool peer_open[2] = {false, false};
+  // stream-ordered neighbour synchronisation (flag words written by the neighbours through peer pointers)
+  unsigned long long *flags = nullptr;          // [0] low nbr read-done, [1] low nbr pushed, [2] high nbr read-done, [3] high nbr pushed, [7] error
+  unsigned long long *peer_flags[2] = {nullptr, nullptr};
+  unsigned long long epoch_sig[2] = {0, 0}, epoch_wait[2] = {0, 0};
 };
 
 namespace {
@@ -226,34 +230,40 @@ void launch_prim(osb_ctx *c) {
   k_prim<ND><<<grid3(n[0], n[1], n[2], b), b, 0, c->stream>>>(c->grid, c->fp, c->pc, c->gp.mu, lo[0], lo[1], lo[2], n[0], n[1], n[2]);
 }
 
+void neighbour_signal(osb_ctx *c, int kind);
+
+// Sweep order: in 3-D the z sweep (the only one that reads the halos owned by neighbour ranks of a slab decomposition)
+// goes first, so that the "read done" notification overlaps with the x and y sweeps.
 template <int ND, int RECON, int AVG>
 void launch_flux(osb_ctx *c) {
   const GridDev &g = c->grid;
+  if (ND >= 3) {
+    const long long TR = (long long)(g.np[2] + 6) * g.np[1];
+    dim3 b(32, F2_TY, 1), gr((unsigned)((TR + F2_RT - 7) / (F2_RT - 6)), (g.np[0] + 31) / 32, 1);
+    auto kern = k_flux2_yz<3, 2, RECON, AVG, false>;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_yz_smem_bytes<3>()); attr_set = true; }
+    { Launcher L(c, OSB_FAM_FLUX); kern<<<gr, b, f2_yz_smem_bytes<3>(), c->stream>>>(g, c->fp, c->pc, c->sp, c->ad, c->gp); }
+    neighbour_signal(c, 0);
+  }
   {
     const long long T = (long long)(g.np[0] + 6) * g.np[1] * g.np[2];
     const long long nb = (T + F2_BT - 7) / (F2_BT - 6);
     Launcher L(c, OSB_FAM_FLUX);
-    k_flux2_x<ND, RECON, AVG, false><<<(unsigned)nb, F2_BT, 0, c->stream>>>(g, c->fp, c->pc, c->sp, c->ad, c->gp);
+    if (ND >= 3) k_flux2_x<ND, RECON, AVG, true><<<(unsigned)nb, F2_BT, 0, c->stream>>>(g, c->fp, c->pc, c->sp, c->ad, c->gp);
+    else k_flux2_x<ND, RECON, AVG, false><<<(unsigned)nb, F2_BT, 0, c->stream>>>(g, c->fp, c->pc, c->sp, c->ad, c->gp);
   }
   if (ND >= 2) {
     const long long TR = (long long)(g.np[1] + 6) * (ND > 2 ? g.np[2] : 1);
     dim3 b(32, F2_TY, 1), gr((unsigned)((TR + F2_RT - 7) / (F2_RT - 6)), (g.np[0] + 31) / 32, 1);
-    Launcher L(c, OSB_FAM_FLUX);
     constexpr int N2 = (ND >= 2 ? ND : 2);
     auto kern = k_flux2_yz<N2, 1, RECON, AVG, true>;
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_yz_smem_bytes<N2>()); attr_set = true; }
+    Launcher L(c, OSB_FAM_FLUX);
     kern<<<gr, b, f2_yz_smem_bytes<N2>(), c->stream>>>(g, c->fp, c->pc, c->sp, c->ad, c->gp);
   }
-  if (ND >= 3) {
-    const long long TR = (long long)(g.np[2] + 6) * g.np[1];
-    dim3 b(32, F2_TY, 1), gr((unsigned)((TR + F2_RT - 7) / (F2_RT - 6)), (g.np[0] + 31) / 32, 1);
-    Launcher L(c, OSB_FAM_FLUX);
-    auto kern = k_flux2_yz<3, 2, RECON, AVG, true>;
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_yz_smem_bytes<3>()); attr_set = true; }
-    kern<<<gr, b, f2_yz_smem_bytes<3>(), c->stream>>>(g, c->fp, c->pc, c->sp, c->ad, c->gp);
-  }
+  if (ND < 3) neighbour_signal(c, 0);
 }
 
 template <int ND>
@@ -266,6 +276,51 @@ void launch_flux_scheme(osb_ctx *c) {
   else { roe ? launch_flux<ND, RECON_WENO5_JS, AVG_ROE>(c) : launch_flux<ND, RECON_WENO5_JS, AVG_SIMPLE>(c); }
 }
 
+bool has_exchange(const osb_ctx *c) {
+  const int d = c->plan.nd - 1;
+  return (c->plan.bc[d][0].kind == BC_EXCHANGE && c->peer_open[0]) || (c->plan.bc[d][1].kind == BC_EXCHANGE && c->peer_open[1]);
+}
+
+bool fused_push_enabled() {
+  static const bool on = getenv("OSB_NO_FUSED_PUSH") == nullptr;
+  return on;
+}
+
+PeerPush peer_push(const osb_ctx *c) {
+  PeerPush pp;
+  if (!fused_push_enabled()) return PeerPush{};
+  const int d = c->plan.nd - 1;
+  int hm, hp; scheme_halos(c->plan, hm, hp);
+  pp.hm = hm; pp.hp = hp;
+  for (int m = 0; m < 5; m++) {
+    pp.lo[m] = (c->plan.bc[d][0].kind == BC_EXCHANGE && c->peer_open[0]) ? c->peer_q[0][m] : nullptr;
+    pp.hi[m] = (c->plan.bc[d][1].kind == BC_EXCHANGE && c->peer_open[1]) ? c->peer_q[1][m] : nullptr;
+  }
+  return pp;
+}
+
+// kind 0: "I have finished reading my halos", kind 1: "my pushes into your halos have landed".
+// Flag slots of a rank: [0] low neighbour read-done, [1] low neighbour pushed, [2] high neighbour read-done, [3] high pushed.
+// A rank is the HIGH neighbour of its low neighbour (writes that rank's slots 2,3) and the LOW neighbour of its high one.
+void neighbour_signal(osb_ctx *c, int kind) {
+  if (!has_exchange(c)) return;
+  const int d = c->plan.nd - 1;
+  const bool lo = c->plan.bc[d][0].kind == BC_EXCHANGE && c->peer_open[0], hi = c->plan.bc[d][1].kind == BC_EXCHANGE && c->peer_open[1];
+  const unsigned long long e = ++c->epoch_sig[kind];
+  k_signal<<<1, 1, 0, c->stream>>>(lo ? c->peer_flags[0] + 2 + kind : nullptr, hi ? c->peer_flags[1] + 0 + kind : nullptr, e);
+  c->launches++;
+}
+void neighbour_wait(osb_ctx *c, int kind) {
+  if (!has_exchange(c)) return;
+  const int d = c->plan.nd - 1;
+  const bool lo = c->plan.bc[d][0].kind == BC_EXCHANGE && c->peer_open[0], hi = c->plan.bc[d][1].kind == BC_EXCHANGE && c->peer_open[1];
+  const unsigned long long e = ++c->epoch_wait[kind];
+  Launcher L(c, OSB_FAM_SYNC);
+  k_wait<<<1, 1, 0, c->stream>>>(lo ? c->flags + 0 + kind : nullptr, hi ? c->flags + 2 + kind : nullptr, e, c->flags + 7);
+}
+
+int push_planes_memcpy(osb_ctx *c);
+
 template <int RK>
 void launch_viscous_tiled(osb_ctx *c, double a, double b) {
   const GridDev &g = c->grid;
@@ -274,12 +329,12 @@ void launch_viscous_tiled(osb_ctx *c, double a, double b) {
   if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vt_smem_bytes()); attr_set = true; }
   dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + VT_ZC - 1) / VT_ZC);
   Launcher L(c, OSB_FAM_VISCOUS);
-  kern<<<gr, bl, vt_smem_bytes(), c->stream>>>(g, c->fp, c->pc, a, b);
+  kern<<<gr, bl, vt_smem_bytes(), c->stream>>>(g, c->fp, c->pc, a, b, RK == 0 ? PeerPush{} : peer_push(c));
 }
 
-// stage >= 0: fuse the RK update of that stage into the last spatial kernel where possible (returns true if fused)
+// phase A of a stage: everything that reads the halos of q (constituent relations, sensor, convective terms)
 template <int ND>
-bool launch_residual(osb_ctx *c, int stage = -1) {
+void launch_phase_a(osb_ctx *c) {
   const GridDev &g = c->grid;
   launch_prim<ND>(c);
   if (c->plan.teno_adaptive) {
@@ -291,9 +346,17 @@ bool launch_residual(osb_ctx *c, int stage = -1) {
     dim3 b(64, 2, 2);
     Launcher L(c, OSB_FAM_CENTRAL);
     k_central<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc);
+    neighbour_signal(c, 0);
   } else {
     launch_flux_scheme<ND>(c);
   }
+}
+
+// phase B: viscous terms (stencils on u, T only).  stage >= 0: fuse the RK update (and the halo push of a decomposed run)
+// of that stage into the kernel where possible; returns true if the RK update was fused.
+template <int ND>
+bool launch_phase_b(osb_ctx *c, int stage) {
+  const GridDev &g = c->grid;
   if (c->plan.viscous) {
     if (ND == 3 && !c->general) {
       if (stage < 0) launch_viscous_tiled<0>(c, 0.0, 0.0);
@@ -395,14 +458,32 @@ void launch_save(osb_ctx *c) {
 }
 
 template <int ND>
-int step_nd(osb_ctx *c, int nsteps) {
-  const int nstages = (int)c->plan.rk_a.size();
-  for (int it = 0; it < nsteps; it++) {
+void launch_residual(osb_ctx *c) {
+  launch_phase_a<ND>(c);
+  launch_phase_b<ND>(c, -1);
+}
+
+// One stage of the loop (s < 0: iteration start).  In a decomposed run the neighbour exchange is part of the stage and is
+// ordered on the stream by flag words, so a whole run can be enqueued without host synchronisation:
+//   phase A (reads halos) -> "read done" handshake -> phase B + RK (+ fused peer push) -> "pushed" handshake -> local BCs
+template <int ND>
+int stage_nd(osb_ctx *c, int s) {
+  const bool ex = has_exchange(c);
+  if (s < 0) {
     launch_bcs(c);
+    if (ex) { if (push_planes_memcpy(c)) return 1; neighbour_signal(c, 1); neighbour_wait(c, 1); }
     if (c->plan.rk == RK_SBLI) launch_save<ND>(c);
-    for (int s = 0; s < nstages; s++) {
-      if (!launch_residual<ND>(c, s)) launch_rk<ND>(c, s);
+  } else {
+    launch_phase_a<ND>(c);        // sends the "read done" notification as soon as the halo-reading kernels are enqueued
+    neighbour_wait(c, 0);
+    const bool fused = launch_phase_b<ND>(c, s);
+    if (!fused) launch_rk<ND>(c, s);
+    if (ex && fused && fused_push_enabled()) {            // planes were pushed by the kernel: interior part; the receiver's own BCs complete the halos
+      neighbour_signal(c, 1); neighbour_wait(c, 1);
       launch_bcs(c);
+    } else {
+      launch_bcs(c);
+      if (ex) { if (push_planes_memcpy(c)) return 1; neighbour_signal(c, 1); neighbour_wait(c, 1); }
     }
   }
   OSB_CUDA(c, cudaGetLastError());
@@ -410,10 +491,12 @@ int step_nd(osb_ctx *c, int nsteps) {
 }
 
 template <int ND>
-int stage_nd(osb_ctx *c, int s) {
-  if (s < 0) { launch_bcs(c); if (c->plan.rk == RK_SBLI) launch_save<ND>(c); }
-  else { if (!launch_residual<ND>(c, s)) launch_rk<ND>(c, s); launch_bcs(c); }
-  OSB_CUDA(c, cudaGetLastError());
+int step_nd(osb_ctx *c, int nsteps) {
+  const int nstages = (int)c->plan.rk_a.size();
+  for (int it = 0; it < nsteps; it++) {
+    if (stage_nd<ND>(c, -1)) return 1;
+    for (int s = 0; s < nstages; s++) if (stage_nd<ND>(c, s)) return 1;
+  }
   return 0;
 }
 int do_stage(osb_ctx *c, int s) {
@@ -514,6 +597,8 @@ int osb_create(const char *plan_text, int device, osb_ctx **out) {
       }
   }
   if (!ok) { g_create_error = "cudaMalloc failed (out of device memory)"; osb_destroy(c); return 3; }
+  if (cudaMalloc(&c->flags, 8 * sizeof(unsigned long long)) != cudaSuccess) { g_create_error = "cudaMalloc failed"; osb_destroy(c); return 3; }
+  cudaMemsetAsync(c->flags, 0, 8 * sizeof(unsigned long long), c->stream);
   cudaStreamSynchronize(c->stream);
   *out = c;
   return 0;
@@ -523,7 +608,11 @@ int osb_destroy(osb_ctx *c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   for (int s = 0; s < 2; s++)
-    if (c->peer_open[s]) for (int m = 0; m < 5; m++) if (c->peer_q[s][m]) cudaIpcCloseMemHandle(c->peer_q[s][m]);
+    if (c->peer_open[s]) {
+      for (int m = 0; m < 5; m++) if (c->peer_q[s][m]) cudaIpcCloseMemHandle(c->peer_q[s][m]);
+      if (c->peer_flags[s]) cudaIpcCloseMemHandle(c->peer_flags[s]);
+    }
+  if (c->flags) cudaFree(c->flags);
   for (auto &f : c->fields) cudaFree(f.dev);
   for (int d = 0; d < 3; d++) for (int s = 0; s < 2; s++) if (c->face_table[d][s]) cudaFree(c->face_table[d][s]);
   if (c->timer0) { cudaEventDestroy(c->timer0); cudaEventDestroy(c->timer1); }
@@ -610,6 +699,11 @@ int osb_stage(osb_ctx *c, int stage) {
 int osb_sync(osb_ctx *c) {
   if (!c) return 1;
   OSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->epoch_wait[0] || c->epoch_wait[1]) {
+    unsigned long long err = 0;
+    OSB_CUDA(c, cudaMemcpy(&err, c->flags + 7, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err) return fail(c, "timed out waiting for a neighbour rank (halo exchange epoch " + std::to_string(err) + ")");
+  }
   return 0;
 }
 int osb_apply_bcs(osb_ctx *c) {
@@ -710,14 +804,19 @@ int osb_ipc_export(osb_ctx *c, void *handles, int *nbytes) {
     OSB_CUDA(c, cudaIpcGetMemHandle(&h, c->fp.q[m]));
     memcpy((char *)handles + m * sizeof(h), &h, sizeof(h));
   }
-  *nbytes = nv * (int)sizeof(cudaIpcMemHandle_t);
+  {
+    cudaIpcMemHandle_t h;
+    OSB_CUDA(c, cudaIpcGetMemHandle(&h, c->flags));
+    memcpy((char *)handles + nv * sizeof(h), &h, sizeof(h));
+  }
+  *nbytes = (nv + 1) * (int)sizeof(cudaIpcMemHandle_t);
   return 0;
 }
 int osb_ipc_import(osb_ctx *c, int side, const void *handles, int nbytes) {
   if (!c || !handles || side < 0 || side > 1) return 1;
   cudaSetDevice(c->device);
   const int nv = c->plan.nd + 2;
-  if (nbytes != nv * (int)sizeof(cudaIpcMemHandle_t)) return fail(c, "osb_ipc_import: wrong handle size");
+  if (nbytes != (nv + 1) * (int)sizeof(cudaIpcMemHandle_t)) return fail(c, "osb_ipc_import: wrong handle size");
   for (int m = 0; m < nv; m++) {
     cudaIpcMemHandle_t h;
     memcpy(&h, (const char *)handles + m * sizeof(h), sizeof(h));
@@ -725,12 +824,24 @@ int osb_ipc_import(osb_ctx *c, int side, const void *handles, int nbytes) {
     OSB_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     c->peer_q[side][m] = (double *)p;
   }
+  {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + nv * sizeof(h), sizeof(h));
+    void *p = nullptr;
+    OSB_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_flags[side] = (unsigned long long *)p;
+  }
   c->peer_open[side] = true;
   return 0;
 }
 int osb_halo_push(osb_ctx *c) {
   if (!c) return 1;
   cudaSetDevice(c->device);
+  return push_planes_memcpy(c);
+}
+}  // extern "C"
+namespace {
+int push_planes_memcpy(osb_ctx *c) {
   const Plan &P = c->plan;
   const GridDev &g = c->grid;
   const int d = P.nd - 1;   // slabs along the slowest axis
@@ -748,9 +859,10 @@ int osb_halo_push(osb_ctx *c) {
       OSB_CUDA(c, cudaMemcpyAsync(c->peer_q[0][m] + (g.h + g.np[d]) * g.s[d], c->fp.q[m] + g.h * g.s[d], plane * hp, cudaMemcpyDeviceToDevice, c->stream));
     }
   }
-  c->launches += 0;
   return 0;
 }
+}  // namespace
+extern "C" {
 
 int osb_measure_fp64_peak(int device, double *tflops) {
   if (!tflops) return 1;

@@ -492,14 +492,42 @@ __global__ void __launch_bounds__(256, 2) k_viscous(GridDev g, FieldPtrs f, Phys
 // With FUSE_RK the kernel finishes the stage: Residual (flux sweeps) + viscous terms -> low-storage / SBLI RK update of
 // q and the RK register; otherwise it leaves Residual += viscous (parity entry point osb_residual).
 // -------------------------------------------------------------------------------------------------
+// Slab decomposition: the kernel that finishes a stage also delivers the new boundary planes to the neighbour ranks by
+// peer stores over NVLink (pointers obtained through CUDA IPC): plane k >= np2-hm goes to the high neighbour's low halo,
+// plane k < hp to the low neighbour's high halo (same slab thickness on every rank).
+struct PeerPush {
+  double *lo[5], *hi[5];     // neighbour's conserved arrays (nullptr: no neighbour on that side)
+  int hm, hp;
+};
+
+// Stream-ordered cross-GPU synchronisation without the host: a rank publishes an epoch number in its neighbours' flag
+// words and waits for theirs.  The wait gives up after ~10 s and reports through *err instead of hanging the GPU.
+__global__ void k_signal(unsigned long long *a, unsigned long long *b, unsigned long long e) {
+  __threadfence_system();
+  if (a) *(volatile unsigned long long *)a = e;
+  if (b) *(volatile unsigned long long *)b = e;
+  __threadfence_system();
+}
+__global__ void k_wait(const unsigned long long *a, const unsigned long long *b, unsigned long long e, unsigned long long *err) {
+  const long long t0 = clock64();
+  while ((a && *(const volatile unsigned long long *)a < e) || (b && *(const volatile unsigned long long *)b < e)) {
+    __nanosleep(500);
+    if (clock64() - t0 > (20LL << 30)) { *err = e; break; }
+  }
+  __threadfence_system();
+}
+
 constexpr int VT_X = 32, VT_Y = 8, VT_HX = VT_X + 4, VT_HY = VT_Y + 4, VT_PLANE = VT_HX * VT_HY, VT_ZC = 32;
 constexpr size_t vt_smem_bytes() { return sizeof(double) * 5 * 4 * VT_PLANE; }
 
 template <int RK>   // RK: 0 = residual only, 1 = low-storage update (rk_LS.py:139-166), 2 = SBLI update (rk_sbli.py:102-133)
-__global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled(GridDev g, FieldPtrs f, PhysConst c, double rkA, double rkB) {
+__global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled(GridDev g, FieldPtrs f, PhysConst c, double rkA, double rkB, PeerPush pp) {
   extern __shared__ double vt_smem[];
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * VT_X + tx;
-  const int i0 = blockIdx.x * VT_X, j0 = blockIdx.y * VT_Y, k0 = blockIdx.z * VT_ZC;
+  // z-chunks are scheduled with the two boundary chunks first: they also perform the peer stores of a decomposed run,
+  // which are slower than local stores and would otherwise form the tail of the launch
+  const int nzc = gridDim.z, zc = blockIdx.z == 0 ? 0 : (blockIdx.z == 1 ? nzc - 1 : (int)blockIdx.z - 1);
+  const int i0 = blockIdx.x * VT_X, j0 = blockIdx.y * VT_Y, k0 = zc * VT_ZC;
   const int i = i0 + tx, j = j0 + ty;
   const int kend = min(k0 + VT_ZC, g.np[2]);
   const double *src[4] = {f.u[0], f.u[1], f.u[2], f.T};
@@ -612,8 +640,13 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled(GridDev g, F
       } else {
 #pragma unroll
         for (int m = 0; m < 5; m++) {
-          if (RK == 1) { const double t = c.dt * R[m] + rkA * o[m]; f.rk[m][x] = t; f.q[m][x] = rkB * t + q[m]; }
-          else { f.q[m][x] = c.dt * rkB * R[m] + o[m]; f.rk[m][x] = c.dt * rkA * R[m] + o[m]; }
+          double qn;
+          if (RK == 1) { const double t = c.dt * R[m] + rkA * o[m]; f.rk[m][x] = t; qn = rkB * t + q[m]; }
+          else { qn = c.dt * rkB * R[m] + o[m]; f.rk[m][x] = c.dt * rkA * R[m] + o[m]; }
+          f.q[m][x] = qn;
+          // fused halo exchange: peer stores of the new boundary planes
+          if (pp.hi[m] && k >= g.np[2] - pp.hm) pp.hi[m][x - (long long)g.np[2] * g.s[2]] = qn;
+          if (pp.lo[m] && k < pp.hp) pp.lo[m][x + (long long)g.np[2] * g.s[2]] = qn;
         }
       }
     }

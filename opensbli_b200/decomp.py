@@ -5,8 +5,10 @@ the block is cut into equal slabs along its slowest axis, one rank (process) per
 contiguous planes, so a halo exchange is a plain plane copy.  Only the conserved arrays are exchanged -- primitives are
 recomputed in the halos, as the reference does (constituent-relation kernels run over grid + halos).
 
-Exchange protocol per RK stage (the place where the reference has its `ops_halo_transfer`s, algorithm.py:440-442):
-    stage kernels + rank-local BCs -> barrier -> peer stores of boundary planes over NVLink (CUDA IPC) -> barrier
+Exchange protocol per RK stage (the place where the reference has its `ops_halo_transfer`s, algorithm.py:440-442), all
+ordered on each rank's CUDA stream by flag words the neighbours write through peer pointers -- no host synchronisation:
+    kernels that read the halos -> "read done" handshake -> viscous + RK kernel, which also stores the new boundary
+    planes straight into the neighbours' halos over NVLink (CUDA IPC peer pointers) -> "pushed" handshake -> rank-local BCs
 The pure functions in this module (extents, neighbours, plane indices) are shared by the GPU driver and by the
 CPU (gloo) tests of the N>1 path.
 """
@@ -107,22 +109,9 @@ class DistributedSimulation(object):
             else:
                 self.dist.barrier()
 
-    def exchange(self):
-        if self.world > 1:
-            self.barrier()          # everyone has finished reading its halos / writing its boundary planes
-            self.sim.halo_push()
-            self.barrier()          # all pushes have landed
-
-    def step(self, nsteps=1):
-        if self.world == 1:
-            self.sim.step(nsteps)
-            return
-        for _ in range(nsteps):
-            self.sim.step_begin()
-            self.exchange()
-            for s in range(self.nstages):
-                self.sim.stage(s)
-                self.exchange()
+    def step(self, nsteps=1, sync=True):
+        """Enqueue nsteps iterations; the neighbour exchange is part of the stream-ordered stage sequence."""
+        self.sim.step(nsteps, sync=sync)
 
     def close(self):
         self.sim.close()

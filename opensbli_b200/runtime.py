@@ -12,7 +12,7 @@ from .build import LIB
 _P = ctypes.POINTER(ctypes.c_double)
 _lib = None
 
-FAMILIES = ('prim', 'flux', 'central', 'viscous', 'rk', 'bc')
+FAMILIES = ('prim', 'flux', 'central', 'viscous', 'rk', 'bc', 'sync')
 
 SYMBOLS = ('osb_create', 'osb_destroy', 'osb_last_error', 'osb_set_const_f64', 'osb_get_const_f64',
            'osb_num_fields', 'osb_field_name', 'osb_field_info', 'osb_upload', 'osb_download', 'osb_device_ptr', 'osb_upload_face',
