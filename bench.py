@@ -34,12 +34,18 @@ ALG_FLOP_PER_UPDATE = 27.1e3          # 3 x 9038 (reference's own operation coun
 LS3 = dict(rk='ls', rk_a=[0.0, -5.0 / 9.0, -153.0 / 128.0], rk_b=[1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0])
 
 
-def tgv_plan(np3):
+SBLI3 = dict(rk='sbli', rk_a=[1.0 / 4.0, 3.0 / 20.0, 3.0 / 5.0], rk_b=[2.0 / 3.0, 5.0 / 12.0, 3.0 / 5.0])
+
+
+def tgv_plan(np3, workload='teno5'):
     dl = 2 * math.pi / 512 if max(np3) > 512 else 2 * math.pi / np3[0]
     per = [[dict(type='periodic'), dict(type='periodic')] for _ in range(3)]
+    consts = dict(gama=1.4, Minf=0.1, Re=1600.0, Pr=0.71, dt=0.003385 * 64 * dl / (2 * math.pi), eps=1e-16, TENO_CT=1e-6)
+    if workload == 'central4':      # BASELINE configs[1]: the shipped taylor_green_vortex app, Central(4) + RungeKutta(3)
+        return dict(ndim=3, np=list(np3), delta=[dl] * 3, conv='central', order=4, averaging='roe', viscous=True,
+                    constants=consts, bc=per, **SBLI3)
     return dict(ndim=3, np=list(np3), delta=[dl] * 3, conv='teno', order=5, averaging='roe', viscous=True,
-                constants=dict(gama=1.4, Minf=0.1, Re=1600.0, Pr=0.71, dt=0.003385 * 64 * dl / (2 * math.pi),
-                               eps=1e-16, TENO_CT=1e-6), bc=per, **LS3)
+                constants=consts, bc=per, **LS3)
 
 
 def global_grid(ngpus, size):
@@ -188,6 +194,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--size', type=int, default=512, help='points per direction per GPU (default 512: the headline case)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='teno5', choices=['teno5', 'central4'], help='teno5 = headline (BASELINE configs[2]); central4 = configs[1] at --size')
     ap.add_argument('--cpu-size', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -216,7 +223,7 @@ def main():
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
 
-    plan = tgv_plan(global_grid(world, args.size))
+    plan = tgv_plan(global_grid(world, args.size), args.workload)
 
     class _Solo(object):
         def get_rank(self): return 0
@@ -276,7 +283,13 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
-    if prof:
+    if prof and args.workload == 'central4':
+        tot = sum(v['ms'] for v in prof.values())
+        roofline = {'bound': 'hbm', 'kernel': 'whole step (k_prim, k_central, k_viscous3d_tiled+RK)', 'achieved': ALG_BYTES_PER_UPDATE * value / world / 1e9,
+                    'peak': hbm_peak, 'unit': 'GB/s', 'frac': ALG_BYTES_PER_UPDATE * value / world / 1e9 / hbm_peak, 'traffic': None,
+                    'families_ms': {k: v['ms'] for k, v in prof.items()}, 'share_of_step': 1.0,
+                    'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'}
+    elif prof:
         fl = prof['flux']
         per_launch_ms = fl['ms'] / max(fl['launches'], 1)
         pts_local = float(np.prod(lplan['np']))
@@ -339,8 +352,9 @@ def main():
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
                 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
                 'data': 'synthetic',
-                'config': {'workload': 'TGV Re=1600 TENO5(Roe,LLF)+StoreSome(4) viscous+RK-LS3, %s grid fp64 (BASELINE configs[%d]), %d^3 points per GPU'
-                                       % ('x'.join(str(n) for n in plan['np']), 2 if world == 1 else 4, args.size),
+                'config': {'workload': ('TGV Re=1600 TENO5(Roe,LLF)+StoreSome(4) viscous+RK-LS3, %s grid fp64 (BASELINE configs[%d]), %d^3 points per GPU'
+                                        % ('x'.join(str(n) for n in plan['np']), 2 if world == 1 else 4, args.size)) if args.workload == 'teno5' else
+                                       'TGV Re=1600 Central(4) skew-symmetric + RungeKutta(3), %s grid fp64 (BASELINE configs[1] at this size)' % 'x'.join(str(n) for n in plan['np']),
                            'grid': plan['np'], 'parallelism': 'slab%d' % world,
                            'l2_policy': 'working set %.1f GB per GPU >> 126 MB L2 (no flush needed)' % (19 * np.prod(shape) * 8 / 1e9),
                            'finite': finite},
