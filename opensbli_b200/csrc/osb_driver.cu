@@ -87,6 +87,10 @@ struct osb_ctx {
   unsigned long long *flags = nullptr;          // [0] low nbr read-done, [1] low nbr pushed, [2] high nbr read-done, [3] high nbr pushed, [7] error
   unsigned long long *peer_flags[2] = {nullptr, nullptr};
   unsigned long long epoch_sig[2] = {0, 0}, epoch_wait[2] = {0, 0};
+  // one time step captured as a CUDA graph (launch-bound small grids): invalidated when a constant changes
+  cudaGraphExec_t step_graph = nullptr;
+  long long graph_launches = 0;
+  bool use_graph = true;
 };
 
 namespace {
@@ -508,12 +512,41 @@ int do_stage(osb_ctx *c, int s) {
   }
 }
 
-int do_step(osb_ctx *c, int nsteps) {
+int step_dispatch(osb_ctx *c, int nsteps) {
   switch (c->plan.nd) {
     case 1: return step_nd<1>(c, nsteps);
     case 2: return step_nd<2>(c, nsteps);
     default: return step_nd<3>(c, nsteps);
   }
+}
+
+void drop_graph(osb_ctx *c) {
+  if (c->step_graph) { cudaGraphExecDestroy(c->step_graph); c->step_graph = nullptr; }
+}
+
+// Small grids are launch-bound (a Sod step is ~20 kernels of a few microseconds): one time step is captured once as a
+// CUDA graph and replayed.  Not used while profiling (events between launches) nor in decomposed runs (the handshake
+// kernels carry a new epoch number every stage).
+int do_step(osb_ctx *c, int nsteps) {
+  const long long pts = (long long)c->grid.np[0] * c->grid.np[1] * c->grid.np[2];
+  if (!c->use_graph || c->profiling || has_exchange(c) || pts > (1LL << 22) || nsteps < 2) return step_dispatch(c, nsteps);
+  if (!c->step_graph) {
+    cudaGraph_t graph = nullptr;
+    const long long l0 = c->launches;
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return step_dispatch(c, nsteps); }
+    const int rc = step_dispatch(c, 1);
+    const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    c->graph_launches = c->launches - l0;
+    c->launches = l0;
+    if (rc || e != cudaSuccess || !graph) { cudaGetLastError(); if (graph) cudaGraphDestroy(graph); c->use_graph = false; return step_dispatch(c, nsteps); }
+    if (cudaGraphInstantiate(&c->step_graph, graph, 0) != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(graph); c->use_graph = false; return step_dispatch(c, nsteps); }
+    cudaGraphDestroy(graph);
+  }
+  for (int it = 0; it < nsteps; it++) {
+    OSB_CUDA(c, cudaGraphLaunch(c->step_graph, c->stream));
+    c->launches += c->graph_launches;
+  }
+  return 0;
 }
 
 }  // namespace
@@ -612,6 +645,7 @@ int osb_destroy(osb_ctx *c) {
       for (int m = 0; m < 5; m++) if (c->peer_q[s][m]) cudaIpcCloseMemHandle(c->peer_q[s][m]);
       if (c->peer_flags[s]) cudaIpcCloseMemHandle(c->peer_flags[s]);
     }
+  drop_graph(c);
   if (c->flags) cudaFree(c->flags);
   for (auto &f : c->fields) cudaFree(f.dev);
   for (int d = 0; d < 3; d++) for (int s = 0; s < 2; s++) if (c->face_table[d][s]) cudaFree(c->face_table[d][s]);
@@ -625,6 +659,7 @@ int osb_set_const_f64(osb_ctx *c, const char *name, double v) {
   if (!c || !name) return 1;
   c->plan.consts[name] = v;
   refresh_constants(c);
+  drop_graph(c);          // constants are baked into the captured kernel arguments
   return 0;
 }
 int osb_get_const_f64(const osb_ctx *c, const char *name, double *v) {
@@ -832,6 +867,7 @@ int osb_ipc_import(osb_ctx *c, int side, const void *handles, int nbytes) {
     c->peer_flags[side] = (unsigned long long *)p;
   }
   c->peer_open[side] = true;
+  drop_graph(c);
   return 0;
 }
 int osb_halo_push(osb_ctx *c) {
