@@ -31,6 +31,10 @@ UNIT = 'updates/s'
 ALG_BYTES_PER_UPDATE = 480.0          # 3 stages x (5 q + 5 RK regs) x (read + write) x 8 B
 ALG_FLOP_PER_POINT_FLUX_SWEEP = 2836.0 + 50.0 / 3.0   # reference count_ops: one LLFTeno_reconstruction_d loop + its share of the Residual loop
 ALG_FLOP_PER_UPDATE = 27.1e3          # 3 x 9038 (reference's own operation count, opsc.py:411-418)
+# dram__bytes_read.sum + dram__bytes_write.sum per flux-sweep launch at 512^3 from the `ncu --set full` capture
+# profiles/r01_final_ncu_top_kernels_512.md: z 15.55 GB, x 16.32 GB, y 22.50 GB -> mean of the three launches of a stage
+# (algorithmic: 5 q read + 5 residual read + 5 residual write = 16.1 GB for the accumulating sweeps, 10.7 GB for the first)
+NCU_DRAM_BYTES_PER_FLUX_LAUNCH_512 = 18.12e9
 LS3 = dict(rk='ls', rk_a=[0.0, -5.0 / 9.0, -153.0 / 128.0], rk_b=[1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0])
 
 
@@ -297,7 +301,8 @@ def main():
         tot = sum(v['ms'] for v in prof.values())
         roofline = {'bound': 'fp64', 'kernel': 'k_flux_{x,yz} (TENO5 characteristic flux sweep + flux difference)',
                     'achieved': ach, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': ach / fp64_peak if fp64_peak else None,
-                    'traffic': None, 'launch_ms': per_launch_ms, 'share_of_step': fl['ms'] / tot if tot else None,
+                    'traffic': NCU_DRAM_BYTES_PER_FLUX_LAUNCH_512 if (world == 1 and args.size == 512) else None,
+                    'traffic_source': 'profiles/r01_final_ncu_top_kernels_512.md (bytes per launch, ncu --set full)', 'launch_ms': per_launch_ms, 'share_of_step': fl['ms'] / tot if tot else None,
                     'peak_source': 'measured in this run: DFMA micro-benchmark osb_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)',
                     'flop_model': "reference's own count_ops: 2836 per point per LLFTeno_reconstruction loop + 50/3 Residual",
                     'families_ms': {k: v['ms'] for k, v in prof.items()}}
