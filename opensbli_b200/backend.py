@@ -131,7 +131,10 @@ def _lambdify_check(eq, canonical, names, ntry=8, tol=1e-12):
     for _ in range(ntry):
         vals = {str(s)[2:]: float(0.5 + rng.random()) for s in syms}
         got = f(*[vals[str(s)[2:]] for s in syms])
-        want = canonical(vals)
+        try:
+            want = canonical(vals)
+        except KeyError:          # the canonical form needs a symbol the equation does not have
+            return False
         if abs(got - want) > tol * max(1.0, abs(want)):
             return False
     return True
@@ -216,7 +219,7 @@ def _recon_info(k):
     return info
 
 
-KNOWN_CONSTANTS = re.compile(r'^(gama|gamma_m1|Minf|Re|Pr|dt|eps|TENO_CT|teno_a1|teno_a2|epsilon|SuthT|RefT|Twall|niter|'
+KNOWN_CONSTANTS = re.compile(r'^(gama|gamma_m1|Minf|Re|Pr|dt|eps|TENO_CT|teno_a1|teno_a2|epsilon|SuthT|RefT|Twall|niter|c[0-2]|'
                              r'block0np\d|Delta\dblock0|inv_\d+|rc\d+|rcinv\d+|inv_rfact\d*_block0)$')
 
 
@@ -236,6 +239,35 @@ def _check_constants_used(components):
                         bad.add('%s (in %s)' % (a, _name(c)))
     if bad:
         raise UnsupportedByB200('the hot loops use constants outside the implemented canonical system: %s' % sorted(bad))
+
+
+def _check_forcing(kernels, ndim):
+    """Constant body force of the channel apps (turbulent_channel.py:15-16): momentum_i gets -c_i, the energy equation
+    -c_j u_j.  Verified on the residual equations: d Residual_i / d c_i = -1 and d Residual_E / d c_j = -u_j."""
+    from sympy import diff, simplify, Symbol
+    from opensbli.core.opensbliobjects import ConstantObject, DataSet
+    found = False
+    for k in kernels:
+        for e in k.equations:
+            cs = [a for a in e.rhs.atoms(ConstantObject) if re.match(r'c[0-2]$', str(a))] if hasattr(e, 'rhs') else []
+            if not cs:
+                continue
+            found = True
+            m = re.match(r'Residual(\d)$', _strip(e.lhs.base) if hasattr(e.lhs, 'base') else '')
+            if not m:
+                raise UnsupportedByB200('body-force constant outside a residual equation (%s)' % _name(k))
+            eq = int(m.group(1))
+            for cst in cs:
+                j = int(str(cst)[1])
+                dd = diff(e.rhs, cst)
+                if 1 <= eq <= ndim:
+                    ok = (eq - 1 == j) and dd == -1
+                else:
+                    us = [a for a in dd.atoms(DataSet)]
+                    ok = eq == ndim + 1 and len(us) == 1 and _strip(us[0].base) == 'u%d' % j and simplify(dd + us[0]) == 0
+                if not ok:
+                    raise UnsupportedByB200('forcing term of %s in Residual%d is not the canonical constant body force' % (cst, eq))
+    return found
 
 
 def _check_central_form(kernels, ndim, q_names):
@@ -398,6 +430,7 @@ def extract_plan(algorithm):
     else:
         raise UnsupportedByB200('no convective discretisation found in the stage loop')
     plan['viscous'] = bool(viscous)
+    plan['forcing'] = _check_forcing(resid + viscous + central_conv, ndim)
     if plan['viscosity']['type'] != 'constant' and not viscous:
         plan['viscosity'] = {'type': 'constant'}
     plan['metric_fields'] = _metric_directions(resid + viscous + [k for k in cr if _name(k) == 'ConstituentRelations evaluation'], ndim)

@@ -50,6 +50,7 @@ struct Plan {
   double mu_exp = 0.0;
   bool metric[3] = {false, false, false};
   bool teno_adaptive = false;
+  bool forcing = false;
   Closures cl{};
 };
 
@@ -153,6 +154,7 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
     }
     else if (key == "metric") { int d2, on; ls >> d2 >> on; if (d2 < 0 || d2 > 2) { err = "bad metric line"; return false; } P.metric[d2] = on != 0; }
     else if (key == "teno_adaptive") { int v; ls >> v; P.teno_adaptive = v != 0; }
+    else if (key == "forcing") { int v; ls >> v; P.forcing = v != 0; }
     else if (key == "closure_d1" || key == "closure_d2") {
       int nr, np; ls >> nr >> np;
       if (nr < 1 || np < 1 || nr > (key == "closure_d1" ? 4 : 2) || np > 6) { err = "closure table too large: " + line; return false; }
@@ -178,6 +180,7 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
     if (P.conv != CONV_TENO) { err = "teno_adaptive needs a TENO scheme"; return false; }
     for (const char *k : {"teno_a1", "teno_a2"}) if (!P.consts.count(k)) { err = std::string("missing constant ") + k; return false; }
   }
+  if (P.forcing && !P.viscous) { err = "body forcing is implemented together with the viscous terms only"; return false; }
   if (P.visc_law == 1) for (const char *k : {"SuthT", "RefT"}) if (!P.consts.count(k)) { err = std::string("missing constant ") + k; return false; }
   for (int d = 0; d < P.nd; d++) for (int s = 0; s < 2; s++)
     if (P.bc[d][s].kind == BC_ISOTHERMAL_WALL && !P.consts.count("Twall")) { err = "missing constant Twall"; return false; }
@@ -199,6 +202,7 @@ void refresh_constants(osb_ctx *c) {
   c->pc.visc_law = P.visc_law; c->pc.mu_exp = P.mu_exp;
   c->pc.SuthT = get("SuthT", 0.0); c->pc.RefT = get("RefT", 1.0); c->pc.Twall = get("Twall", 1.0);
   c->pc.sensor_eps = get("epsilon", 1e-12);
+  for (int d = 0; d < 3; d++) c->pc.force[d] = P.forcing ? get(("c" + std::to_string(d)).c_str(), 0.0) : 0.0;
 }
 
 Field *find_field(osb_ctx *c, const char *name) {
@@ -606,7 +610,7 @@ int osb_create(const char *plan_text, int device, osb_ctx **out) {
   for (int m = 0; m < nv && ok; m++) ok = add("Residual" + std::to_string(m), &c->fp.R[m]);
   for (int m = 0; m < nv && ok; m++) ok = add(P.rk == RK_LS ? "tempRK_" + qn[m] : qn[m] + "_RKold", &c->fp.rk[m]);
   // general path: metric fields (uploaded by the caller), viscosity, sensor
-  c->general = P.visc_law != 0;
+  c->general = P.visc_law != 0 || P.forcing;
   for (int d = 0; d < P.nd; d++) {
     if (P.metric[d] || P.bc[d][0].closure || P.bc[d][1].closure) c->general = true;
     if (P.metric[d] && ok) {

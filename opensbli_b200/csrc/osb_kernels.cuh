@@ -38,6 +38,7 @@ struct PhysConst {
   // general path
   int visc_law;             // 0 constant, 1 Sutherland, 2 power law
   double SuthT, RefT, mu_exp, Twall, sensor_eps;
+  double force[3];          // constant body force c_j (channel apps): momentum_i -= c_i, energy -= c_j u_j
 };
 
 // one-sided closure tables (reduced_access_scheme.py:36-83, Carpenter_scheme.py:38-102): rows idx = 0..nr-1 next to
@@ -837,7 +838,9 @@ __global__ void __launch_bounds__(256) k_viscous_general(GridDev g, FieldPtrs f,
       e += iRe * mu * Sab * du[a][b];
     }
     vis[a] = iRe * (s1 + mu * s2);
-    e += vis[a] * __ldg(f.u[a] + x);
+    const double ua = __ldg(f.u[a] + x);
+    e += vis[a] * ua - c.force[a] * ua;
+    vis[a] -= c.force[a];
   }
   double hT = 0.0;
 #pragma unroll

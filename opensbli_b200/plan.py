@@ -25,6 +25,7 @@ JSON-able dict; `to_text` serialises it to the line format parsed by the C ABI (
     viscosity       {'type': 'constant'} | {'type': 'sutherland'} | {'type': 'power', 'exponent': e}
     metric_fields   per direction None | 'D11'...: stretched direction; fields['D11'], fields['SD111'] hold the metric arrays
     teno_adaptive   bool: C_T from the Ducros sensor (constants teno_a1, teno_a2, epsilon)
+    forcing         bool: constant body force c0, c1, c2 (constants): momentum_i -= c_i, energy -= c_j u_j
     init            optional list of [lhs, rhs] assignment strings (numpy syntax) for the cold initialisation
     niter           optional int
 """
@@ -130,6 +131,8 @@ def to_text(plan):
             L.append('metric %d 1' % d)
     if plan.get('teno_adaptive'):
         L.append('teno_adaptive 1')
+    if plan.get('forcing'):
+        L.append('forcing 1')
     return '\n'.join(L) + '\n'
 
 

@@ -116,7 +116,7 @@ def resolve(plan_sym, env):
     metric fields, tabulated Dirichlet states); returns (plan, ColdRunner holding every cold dataset)."""
     nd = plan_sym['ndim']
     p = {k: plan_sym[k] for k in ('ndim', 'conv', 'order', 'weno_formulation', 'averaging', 'viscous', 'rk', 'rk_a', 'rk_b')}
-    for k in ('viscosity', 'metric_fields', 'teno_adaptive', 'closures'):
+    for k in ('viscosity', 'metric_fields', 'teno_adaptive', 'closures', 'forcing'):
         if k in plan_sym:
             p[k] = plan_sym[k]
     p['np'] = [int(env['block0np%d' % d]) for d in range(nd)]

@@ -577,8 +577,8 @@ static void viscous_general(const osbo_cfg *c, const grid_t *g, const prim_t *P,
         e += iRe * mu * Sab * du[a][b];
       }
       vis[a] = iRe * (s1 + mu * s2);
-      R[1 + a][x] += vis[a];
-      e += vis[a] * P->u[a][x];
+      R[1 + a][x] += vis[a] - c->force[a];
+      e += vis[a] * P->u[a][x] - c->force[a] * P->u[a][x];
     }
     double hT = 0.0;
     for (int d = 0; d < nd; d++)
@@ -603,7 +603,7 @@ void osbo_residual(const osbo_cfg *c, double *const *q, double *const *R) {
   for (int d = 0; d < nd; d++) { inv[d] = 1.0 / c->delta[d]; inv2[d] = pow(c->delta[d], -2); }
 
   constituent(c, &g, q, &P);
-  int general = c->visc_law != OSBO_MU_CONSTANT;
+  int general = c->visc_law != OSBO_MU_CONSTANT || c->force[0] != 0.0 || c->force[1] != 0.0 || c->force[2] != 0.0;
   for (int d = 0; d < nd; d++) if (c->D[d] || c->closure[d][0] || c->closure[d][1]) general = 1;
 
   if (c->teno_adaptive) {

@@ -72,6 +72,7 @@ typedef struct {
   double Twall;
   int extrap_order[3][2];
   const double *bc_face[3][2];/* OSBO_BC_DIRICHLET_FIELD: [nv][padded tangential extent] */
+  double force[3];            /* constant body force c_j: momentum_i -= c_i, energy -= c_j u_j (turbulent_channel.py:15-16) */
 } osbo_cfg;
 
 /* number of doubles of one padded array */

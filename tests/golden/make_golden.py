@@ -121,7 +121,22 @@ def tgv_sym_plan(N):
                 constants=dict(gama=1.4, Minf=0.1, Re=800.0, Pr=0.71, dt=0.005), bc=sym, **SBLI3)
 
 
+def tcf_teno6_plan(N0, N1, N2):
+    """apps/channel_flow/compressible_TCF_TENO/turbulent_channel.py (statistics off): TENO6, Carpenter closures at the
+    isothermal walls, wall-normal stretching, T^0.7 viscosity, body force c0 = -1, SSP-RK3, periodic in x and z."""
+    A, B = ssp_rk3()
+    per = lambda: dict(type='periodic')
+    wall = lambda: dict(type='isothermal_wall', closure='carpenter')
+    return dict(ndim=3, np=[N0, N1, N2], delta=[4.0 * math.pi / N0, 2.0 / (N1 - 1), (4.0 * math.pi / 3.0) / N2], conv='teno', order=6,
+                averaging='roe', viscous=True, rk='ls', rk_a=A, rk_b=B, viscosity=dict(type='power', exponent=0.7),
+                metric_fields=[None, 'D11', None], forcing=True, closures={'carpenter': carpenter_tables()},
+                constants=dict(gama=1.4, Minf=0.0955, Pr=0.7, Re=190.71, Twall=1.0, dt=0.0002, eps=1e-15, TENO_CT=1e-7,
+                               c0=-1.0, c1=0.0, c2=0.0),
+                bc=[[per(), per()], [wall(), wall()], [per(), per()]])
+
+
 if os.path.isdir('/root/reference'):
+    FIXTURES['tcf_teno6_16x24x12'] = ('tcf_teno6', tcf_teno6_plan(16, 24, 12), [1, 5])
     FIXTURES['katzer_carpenter_60x40'] = ('katzer_carpenter', katzer_carpenter_plan(60, 40), [1, 10])
 FIXTURES['tgv_sym_17'] = ('tgv_sym', tgv_sym_plan(17), [1, 3])
 

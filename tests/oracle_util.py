@@ -40,7 +40,8 @@ class OsboCfg(ctypes.Structure):
                 ('teno_adaptive', ctypes.c_int), ('teno_a1', ctypes.c_double), ('teno_a2', ctypes.c_double),
                 ('sensor_eps', ctypes.c_double), ('theta', ctypes.POINTER(ctypes.c_double)),
                 ('teno_store', ctypes.POINTER(ctypes.c_double)), ('Twall', ctypes.c_double),
-                ('extrap_order', (ctypes.c_int * 2) * 3), ('bc_face', (ctypes.POINTER(ctypes.c_double) * 2) * 3)]
+                ('extrap_order', (ctypes.c_int * 2) * 3), ('bc_face', (ctypes.POINTER(ctypes.c_double) * 2) * 3),
+                ('force', ctypes.c_double * 3)]
 
 
 _lib = None
@@ -115,6 +116,9 @@ def make_cfg(plan):
     c.visc_law = MU[visc['type']]
     c.SuthT, c.RefT, c.mu_exp = k.get('SuthT', 0.0), k.get('RefT', 1.0), visc.get('exponent', 0.0)
     c.Twall = k.get('Twall', 1.0)
+    if plan.get('forcing'):
+        for d in range(plan['ndim']):
+            c.force[d] = k.get('c%d' % d, 0.0)
     shape = padded_shape(plan)
     for d, name in enumerate(plan.get('metric_fields', [None] * plan['ndim'])):
         if name:

@@ -18,6 +18,8 @@ APPS = {
     'tgv_teno5': (os.path.join(REPO, 'apps', 'tgv_teno5.py'), [], 'tgv_teno5_16'),
     'tgv_central4': (REF + '/apps/taylor_green_vortex/taylor_green_vortex.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'tgv_central4_16'),
     'katzer': (REF + '/apps/katzer_SBLI/katzer_SBLI.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'katzer_60x40'),
+    'tcf_teno6': (REF + '/apps/channel_flow/compressible_TCF_TENO/turbulent_channel.py',
+                  [("stats = True", "stats = False"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'tcf_teno6_16x24x12'),
     'sod_teno5': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'sod_teno5_n200'),
 }
 
@@ -48,6 +50,7 @@ def comparable(plan):
     p['viscosity'] = plan.get('viscosity', {'type': 'constant'})
     p['teno_adaptive'] = bool(plan.get('teno_adaptive'))
     p['metric_fields'] = plan.get('metric_fields') or [None] * plan['ndim']
+    p['forcing'] = bool(plan.get('forcing'))
     if plan['conv'] == 'weno':
         p['weno_formulation'] = plan.get('weno_formulation', 'JS')
     return p
@@ -77,6 +80,11 @@ def test_b200_backend_distils_expected_plan(name, tmp_path):
         if k not in ('dt',) and k in plan_num['constants']:
             assert plan_num['constants'][k] == want['constants'][k], k
     assert 'gama' in plan_num['constants']
+    # one-sided closure rows read off the IR equal the tables of the reference's scheme objects
+    import numpy as np
+    for name, tab in want.get('closures', {}).items():
+        for key in ('d1', 'd2'):
+            assert np.allclose(np.array(plan_num['closures'][name][key]), np.array(tab[key]), rtol=1e-12, atol=1e-14), (name, key)
     # the stub keeps the reference's contract: every parameter was substituted, `int iter=0;` is present
     stub = open(os.path.join(workdir, 'opensbli.cpp')).read()
     assert '=Input;' not in stub and 'int iter=0;' in stub

@@ -77,6 +77,13 @@ CASES = [
     (3, 13, 'teno', 6, 'JS', 'roe', True, 'ls'),
     (3, 14, 'weno', 5, 'JS', 'roe', False, 'sbli'),
     (3, 12, 'teno', 5, 'JS', 'simple', True, 'sbli'),
+    # smallest grids the halo logic admits (np >= 6 per direction: periodic copies of depth 3/4 must not overlap)
+    (1, 6, 'teno', 5, 'JS', 'roe', False, 'ls'),
+    (2, 6, 'weno', 5, 'Z', 'roe', True, 'ls'),
+    (3, 6, 'teno', 5, 'JS', 'roe', True, 'ls'),
+    (3, 6, 'central', 4, 'JS', 'roe', True, 'sbli'),
+    # x extent spanning several 128-point staging blocks and 32-wide tiles with a ragged tail
+    (2, 300, 'teno', 5, 'JS', 'roe', True, 'ls'),
 ]
 
 
@@ -84,7 +91,7 @@ def synthetic_plan(nd, N, conv, order, form, avg, visc, rk):
     per = [[dict(type='periodic'), dict(type='periodic')] for _ in range(nd)]
     coeff = (dict(rk='ls', rk_a=[0.0, -5.0 / 9.0, -153.0 / 128.0], rk_b=[1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0]) if rk == 'ls' else
              dict(rk='sbli', rk_a=[0.25, 3.0 / 20.0, 0.6], rk_b=[2.0 / 3.0, 5.0 / 12.0, 0.6]))
-    np_ = [N, N + 3, N + 1][:nd]
+    np_ = [N, N + 3, N + 1][:nd] if N > 6 and N < 100 else ([N, N, N][:nd] if N <= 6 else [N, 37, 1][:nd])
     return dict(ndim=nd, np=np_, delta=[2 * math.pi / n for n in np_], conv=conv, order=order, weno_formulation=form,
                 averaging=avg, viscous=visc, constants=dict(gama=1.4, Minf=0.5, Re=200.0, Pr=0.71, dt=2e-3, eps=1e-16, TENO_CT=1e-5),
                 bc=per, **coeff)
