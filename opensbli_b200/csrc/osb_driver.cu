@@ -92,6 +92,7 @@ struct osb_ctx {
   cudaGraphExec_t step_graph = nullptr;
   long long graph_launches = 0;
   bool use_graph = true;
+  int swap_parity = 0;                          // fused central path: q and Residual buffers exchange roles every stage
 };
 
 namespace {
@@ -471,12 +472,51 @@ void launch_residual(osb_ctx *c) {
   launch_phase_b<ND>(c, -1);
 }
 
+// Central(4) + viscous + RK in one out-of-place kernel (3-D, constant viscosity, uniform grid, single GPU): the new state is
+// written into the Residual buffers, which then exchange roles with the q buffers (the field table follows).
+bool fused_central_ok(const osb_ctx *c) {
+  static const bool on = getenv("OSB_NO_FUSED_CENTRAL") == nullptr;
+  const Plan &P = c->plan;
+  if (!on || P.nd != 3 || P.conv != CONV_CENTRAL || !P.viscous || c->general) return false;
+  for (int s = 0; s < 2; s++) if (P.bc[2][s].kind == BC_EXCHANGE) return false;
+  return true;
+}
+
+void launch_central_fused(osb_ctx *c, int stage) {
+  const GridDev &g = c->grid;
+  QPtrs qi, qo, rk;
+  for (int m = 0; m < 5; m++) { qi.q[m] = c->fp.q[m]; qo.q[m] = c->fp.R[m]; rk.q[m] = c->fp.rk[m]; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_central3d_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_smem_bytes());
+    cudaFuncSetAttribute(k_central3d_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_smem_bytes());
+    attr_set = true;
+  }
+  dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + VT_ZC - 1) / VT_ZC);
+  {
+    Launcher L(c, OSB_FAM_CENTRAL);
+    if (c->plan.rk == RK_LS) k_central3d_fused<1><<<gr, bl, ct_smem_bytes(), c->stream>>>(g, qi, qo, rk, c->pc, c->plan.rk_a[stage], c->plan.rk_b[stage], 0);
+    else k_central3d_fused<2><<<gr, bl, ct_smem_bytes(), c->stream>>>(g, qi, qo, rk, c->pc, c->plan.rk_a[stage], c->plan.rk_b[stage], stage == 0);
+  }
+  for (int m = 0; m < 5; m++) {
+    for (auto &f : c->fields) { if (f.dev == c->fp.q[m]) f.dev = c->fp.R[m]; else if (f.dev == c->fp.R[m]) f.dev = c->fp.q[m]; }
+    std::swap(c->fp.q[m], c->fp.R[m]);
+  }
+  c->swap_parity ^= 1;
+}
+
 // One stage of the loop (s < 0: iteration start).  In a decomposed run the neighbour exchange is part of the stage and is
 // ordered on the stream by flag words, so a whole run can be enqueued without host synchronisation:
 //   phase A (reads halos) -> "read done" handshake -> phase B + RK (+ fused peer push) -> "pushed" handshake -> local BCs
 template <int ND>
 int stage_nd(osb_ctx *c, int s) {
   const bool ex = has_exchange(c);
+  if (ND == 3 && fused_central_ok(c)) {
+    if (s >= 0) launch_central_fused(c, s);
+    launch_bcs(c);
+    OSB_CUDA(c, cudaGetLastError());
+    return 0;
+  }
   if (s < 0) {
     launch_bcs(c);
     if (ex) { if (push_planes_memcpy(c)) return 1; neighbour_signal(c, 1); neighbour_wait(c, 1); }
@@ -534,11 +574,16 @@ void drop_graph(osb_ctx *c) {
 int do_step(osb_ctx *c, int nsteps) {
   const long long pts = (long long)c->grid.np[0] * c->grid.np[1] * c->grid.np[2];
   if (!c->use_graph || c->profiling || has_exchange(c) || pts > (1LL << 22) || nsteps < 2) return step_dispatch(c, nsteps);
+  // the fused central path exchanges buffer roles every stage: the captured unit must bring them back (two steps if the
+  // number of stages is odd) and may only be replayed from the parity it was captured at (0)
+  const int unit = (fused_central_ok(c) && (c->plan.rk_a.size() % 2)) ? 2 : 1;
+  if (c->swap_parity) { if (step_dispatch(c, 1)) return 1; nsteps--; }
+  if (nsteps < unit) return step_dispatch(c, nsteps);
   if (!c->step_graph) {
     cudaGraph_t graph = nullptr;
     const long long l0 = c->launches;
     if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return step_dispatch(c, nsteps); }
-    const int rc = step_dispatch(c, 1);
+    const int rc = step_dispatch(c, unit);
     const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
     c->graph_launches = c->launches - l0;
     c->launches = l0;
@@ -546,11 +591,11 @@ int do_step(osb_ctx *c, int nsteps) {
     if (cudaGraphInstantiate(&c->step_graph, graph, 0) != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(graph); c->use_graph = false; return step_dispatch(c, nsteps); }
     cudaGraphDestroy(graph);
   }
-  for (int it = 0; it < nsteps; it++) {
+  for (int it = 0; it + unit <= nsteps; it += unit) {
     OSB_CUDA(c, cudaGraphLaunch(c->step_graph, c->stream));
     c->launches += c->graph_launches;
   }
-  return 0;
+  return step_dispatch(c, nsteps % unit);
 }
 
 }  // namespace

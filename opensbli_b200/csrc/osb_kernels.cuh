@@ -670,6 +670,185 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled(GridDev g, F
 }
 
 // -------------------------------------------------------------------------------------------------
+// Central(4) Navier-Stokes stage in ONE kernel (3-D, constant viscosity, uniform grid; BASELINE config 2):
+// constituent relations + skew-symmetric convective terms + viscous terms + RK update.  A block marches along z over a
+// 32 x 8 column with the planes k-2..k+2 of (rho, E, u0, u1, u2, p, T) in shared memory (computed from q while staging),
+// so per stage q is read once (plus tile halos) and q, RK register are written once.  The update is out of place
+// (q_in -> q_out): neighbouring blocks still read the old values of the points this block updates.
+// -------------------------------------------------------------------------------------------------
+constexpr int CT_NV = 7, CT_RHO = 0, CT_E = 1, CT_U = 2, CT_P = 5, CT_T = 6;
+constexpr size_t ct_smem_bytes() { return sizeof(double) * 5 * CT_NV * VT_PLANE; }
+struct QPtrs { double *q[5]; };
+
+template <int RK>   // 1 = low-storage update, 2 = SBLI update (first_stage folds the "Save equations" loop: old = q)
+__global__ void __launch_bounds__(VT_X * VT_Y, 1) k_central3d_fused(GridDev g, QPtrs qin, QPtrs qout, QPtrs rkreg, PhysConst c,
+                                                                   double rkA, double rkB, int first_stage) {
+  extern __shared__ double ct_smem[];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * VT_X + tx;
+  const int i0 = blockIdx.x * VT_X, j0 = blockIdx.y * VT_Y, k0 = blockIdx.z * VT_ZC;
+  const int i = i0 + tx, j = j0 + ty;
+  const int kend = min(k0 + VT_ZC, g.np[2]);
+  constexpr int NPF = (VT_PLANE + VT_X * VT_Y - 1) / (VT_X * VT_Y);
+  auto S = [&](int slot, int v) -> double * { return ct_smem + (size_t)(slot * CT_NV + v) * VT_PLANE; };
+  auto in_tile = [&](int e, long long &xg, int kk) -> bool {
+    const int yy = e / VT_HX, xx = e % VT_HX;
+    const int gi = i0 + xx - 2, gj = j0 + yy - 2;
+    xg = g.off + gi + gj * g.s[1] + (long long)kk * g.s[2];
+    return e < VT_PLANE && gi < g.np[0] + 2 && gj < g.np[1] + 2;
+  };
+  auto stage = [&](int slot, int e, const double *q) {     // constituent relations of one staged point
+    const double rho = q[0], irho = 1.0 / rho;
+    const double u0 = q[1] * irho, u1 = q[2] * irho, u2 = q[3] * irho;
+    const double p = (c.gama - 1.0) * (q[4] - 0.5 * rho * (u0 * u0 + u1 * u1 + u2 * u2));
+    S(slot, CT_RHO)[e] = rho; S(slot, CT_E)[e] = q[4];
+    S(slot, CT_U)[e] = u0; S(slot, CT_U + 1)[e] = u1; S(slot, CT_U + 2)[e] = u2;
+    S(slot, CT_P)[e] = p; S(slot, CT_T)[e] = c.Minf * c.Minf * c.gama * p * irho;
+  };
+  for (int kk = k0 - 2; kk <= k0 + 2; kk++)
+    for (int it = 0; it < NPF; it++) {
+      long long xg;
+      const int e = tid + it * VT_X * VT_Y;
+      if (in_tile(e, xg, kk)) {
+        double q[5];
+#pragma unroll
+        for (int m = 0; m < 5; m++) q[m] = __ldg(qin.q[m] + xg);
+        stage((kk + 10) % 5, e, q);
+      }
+    }
+  const double iRe = 1.0 / c.Re;
+  const double kq = iRe * (1.0 / (c.gama - 1.0)) * (1.0 / (c.Minf * c.Minf)) * (1.0 / c.Pr);
+  const int ce = (ty + 2) * VT_HX + tx + 2;
+  const bool active = i < g.np[0] && j < g.np[1];
+  __syncthreads();
+  for (int k = k0; k < kend; k++) {
+    // software pipeline: raw q of plane k+3 and this point's RK register travel while plane k is computed
+    double pf[NPF][5];
+    const bool more = k + 1 < kend;
+    if (more) {
+#pragma unroll
+      for (int it = 0; it < NPF; it++) {
+        long long xg;
+        if (in_tile(tid + it * VT_X * VT_Y, xg, k + 3)) {
+#pragma unroll
+          for (int m = 0; m < 5; m++) pf[it][m] = __ldg(qin.q[m] + xg);
+        }
+      }
+    }
+    const long long x = g.off + i + j * g.s[1] + (long long)k * g.s[2];
+    double o[5];
+    if (active && !(RK == 2 && first_stage)) {
+#pragma unroll
+      for (int m = 0; m < 5; m++) o[m] = rkreg.q[m][x];
+    }
+    if (active) {
+      const double *P[5][CT_NV];
+#pragma unroll
+      for (int dz = 0; dz < 5; dz++)
+#pragma unroll
+        for (int v = 0; v < CT_NV; v++) P[dz][v] = S((k + dz - 2 + 10) % 5, v) + ce;
+      const double rho0 = P[2][CT_RHO][0], E0 = P[2][CT_E][0];
+      const double uc[3] = {P[2][CT_U][0], P[2][CT_U + 1][0], P[2][CT_U + 2][0]};
+      const double qc[5] = {rho0, rho0 * uc[0], rho0 * uc[1], rho0 * uc[2], E0};
+      // ---- skew-symmetric convective terms (parsing.py:75-111, scheme.py:187-271)
+      double cons[5] = {0, 0, 0, 0, 0}, adv[5] = {0, 0, 0, 0, 0}, div = 0.0, dp[3], dpu = 0.0;
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        double qn[4][5], un[4], pn[4];
+#pragma unroll
+        for (int n = 0; n < 4; n++) {
+          const int s = n < 2 ? n - 2 : n - 1;                    // -2, -1, +1, +2
+          const int off = d == 0 ? s : (d == 1 ? s * VT_HX : 0);
+          const int dz = d == 2 ? 2 + s : 2;
+          const double r = P[dz][CT_RHO][off];
+          const double v0 = P[dz][CT_U][off], v1 = P[dz][CT_U + 1][off], v2 = P[dz][CT_U + 2][off];
+          un[n] = d == 0 ? v0 : (d == 1 ? v1 : v2);
+          pn[n] = P[dz][CT_P][off];
+          qn[n][0] = r; qn[n][1] = r * v0; qn[n][2] = r * v1; qn[n][3] = r * v2; qn[n][4] = P[dz][CT_E][off];
+        }
+        div += d1c(un[0], un[1], un[2], un[3], c.inv[d]);
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+          cons[m] += d1c(qn[0][m] * un[0], qn[1][m] * un[1], qn[2][m] * un[2], qn[3][m] * un[3], c.inv[d]);
+          adv[m] += uc[d] * d1c(qn[0][m], qn[1][m], qn[2][m], qn[3][m], c.inv[d]);
+        }
+        dp[d] = d1c(pn[0], pn[1], pn[2], pn[3], c.inv[d]);
+        dpu += d1c(pn[0] * un[0], pn[1] * un[1], pn[2] * un[2], pn[3] * un[3], c.inv[d]);
+      }
+      double R[5];
+#pragma unroll
+      for (int m = 0; m < 5; m++) R[m] = -0.5 * (cons[m] + adv[m] + qc[m] * div);
+      R[1] -= dp[0]; R[2] -= dp[1]; R[3] -= dp[2]; R[4] -= dpu;
+      // ---- viscous terms (same arithmetic as k_viscous3d_tiled)
+      const int VI[4] = {CT_U, CT_U + 1, CT_U + 2, CT_T};
+      double dv[3][3], d2[4][3];
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        const double *p = P[2][VI[v]];
+        const double fx = d1c(p[-2], p[-1], p[1], p[2], c.inv[0]);
+        const double fy = d1c(p[-2 * VT_HX], p[-VT_HX], p[VT_HX], p[2 * VT_HX], c.inv[1]);
+        const double fz = d1c(P[0][VI[v]][0], P[1][VI[v]][0], P[3][VI[v]][0], P[4][VI[v]][0], c.inv[2]);
+        if (v < 3) { dv[v][0] = fx; dv[v][1] = fy; dv[v][2] = fz; }
+        d2[v][0] = d2c(p[-2], p[-1], p[0], p[1], p[2], c.inv2[0]);
+        d2[v][1] = d2c(p[-2 * VT_HX], p[-VT_HX], p[0], p[VT_HX], p[2 * VT_HX], c.inv2[1]);
+        d2[v][2] = d2c(P[0][VI[v]][0], P[1][VI[v]][0], p[0], P[3][VI[v]][0], P[4][VI[v]][0], c.inv2[2]);
+      }
+      auto dxy = [&](int v) {
+        const double *p = P[2][VI[v]];
+        double r[4];
+        const int oy[4] = {-2 * VT_HX, -VT_HX, VT_HX, 2 * VT_HX};
+#pragma unroll
+        for (int q = 0; q < 4; q++) r[q] = d1c(p[oy[q] - 2], p[oy[q] - 1], p[oy[q] + 1], p[oy[q] + 2], c.inv[0]);
+        return d1c(r[0], r[1], r[2], r[3], c.inv[1]);
+      };
+      auto dxz = [&](int v) {
+        double r[4];
+        const int pz[4] = {0, 1, 3, 4};
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const double *p = P[pz[q]][VI[v]]; r[q] = d1c(p[-2], p[-1], p[1], p[2], c.inv[0]); }
+        return d1c(r[0], r[1], r[2], r[3], c.inv[2]);
+      };
+      auto dyz = [&](int v) {
+        double r[4];
+        const int pz[4] = {0, 1, 3, 4};
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const double *p = P[pz[q]][VI[v]]; r[q] = d1c(p[-2 * VT_HX], p[-VT_HX], p[VT_HX], p[2 * VT_HX], c.inv[1]); }
+        return d1c(r[0], r[1], r[2], r[3], c.inv[2]);
+      };
+      double vis[3];
+      vis[0] = iRe * ((4.0 / 3.0) * d2[0][0] + d2[0][1] + d2[0][2] + (1.0 / 3.0) * (dxy(1) + dxz(2)));
+      vis[1] = iRe * (d2[1][0] + (4.0 / 3.0) * d2[1][1] + d2[1][2] + (1.0 / 3.0) * (dxy(0) + dyz(2)));
+      vis[2] = iRe * (d2[2][0] + d2[2][1] + (4.0 / 3.0) * d2[2][2] + (1.0 / 3.0) * (dxz(0) + dyz(1)));
+      const double dvg = dv[0][0] + dv[1][1] + dv[2][2];
+      double e = kq * (d2[3][0] + d2[3][1] + d2[3][2]);
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int b = a + 1; b < 3; b++) { const double sab = dv[a][b] + dv[b][a]; e += iRe * sab * sab; }
+        e += iRe * (2.0 * dv[a][a] - (2.0 / 3.0) * dvg) * dv[a][a];
+        e += vis[a] * uc[a];
+      }
+      R[1] += vis[0]; R[2] += vis[1]; R[3] += vis[2]; R[4] += e;
+      // ---- RK update, out of place
+#pragma unroll
+      for (int m = 0; m < 5; m++) {
+        if (RK == 1) { const double t = c.dt * R[m] + rkA * o[m]; rkreg.q[m][x] = t; qout.q[m][x] = rkB * t + qc[m]; }
+        else { const double old = first_stage ? qc[m] : o[m]; qout.q[m][x] = c.dt * rkB * R[m] + old; rkreg.q[m][x] = c.dt * rkA * R[m] + old; }
+      }
+    }
+    __syncthreads();
+    if (more) {
+#pragma unroll
+      for (int it = 0; it < NPF; it++) {
+        long long xg;
+        const int e = tid + it * VT_X * VT_Y;
+        if (in_tile(e, xg, k + 3)) stage((k + 3 + 10) % 5, e, pf[it]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // Runge-Kutta updates (rk_sbli.py:102-133, rk_LS.py:139-166)
 // -------------------------------------------------------------------------------------------------
 template <int ND>

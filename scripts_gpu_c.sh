@@ -1,5 +1,7 @@
 #!/bin/bash
+# central-4 workload (BASELINE config 2): parity tests touching the central path, bench at three sizes, ncu of the stage kernel
 mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q -k "central or sym or tgv or matrix or graph or e2e" > gpurun_out/c_tests.log 2>&1; tail -3 gpurun_out/c_tests.log
 for s in 64 256 512; do
 timeout 600 python bench.py --workload central4 --size $s --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/c_bench$s.json 2> gpurun_out/c_bench$s.err
 python - <<PY
