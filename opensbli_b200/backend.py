@@ -270,30 +270,141 @@ def _check_forcing(kernels, ndim):
     return found
 
 
-def _check_central_form(kernels, ndim, q_names):
-    """Central(4): only the Blaisdell skew-symmetric form of apps/taylor_green_vortex, discretised by
-    Central.sbli_rhs_discretisation into one work array per derivative (scheme.py:187-271), on periodic boxes, is
-    implemented.  The set of derivative loops identifies it."""
-    got = set()
+def _central_form(kernels, ndim, q_names):
+    """Central(4) convective terms: which splitting do the loops evaluate?  The convective loops (in program order: product
+    work arrays, first-derivative loops or local evaluations, residual equations; scheme.py:187-271, StoreSome.py:71-161)
+    are interpreted numerically on random data:
+      * every derivative loop must be the 4th-order central difference of one of the functions the kernels implement
+        (q_m, u_a, p, q_m u_d, p u_d, rhoE/rho) along one direction;
+      * the residual equations must equal the Blaisdell skew form (parsing.py:75-111; taylor_green_vortex.py:8-11,
+        laminar_channel.py:7-9) or the Feiereisen quadratic split (compressible_TCF_Central/turbulent_channel.py:12-20),
+        with diagonal metric factors D_dd and the constant body force where present.
+    Returns 'blaisdell' or 'feiereisen'."""
+    import random
+    from sympy import Piecewise
+    from opensbli.core.opensbliobjects import DataSet
+    rnd = random.Random(20240607)
+    W = {-2: 1.0 / 12, -1: -8.0 / 12, 1: 8.0 / 12, 2: -1.0 / 12}
+    unames = ['u%d' % d for d in range(ndim)]
+    vals, tvals, Dv, cv = {}, {}, {}, {}
+
+    def v(name, s):
+        return vals.setdefault((name, s), rnd.uniform(1.0, 2.0))
+
+    def default_branch(ex):
+        for _ in range(4):
+            pws = list(ex.atoms(Piecewise))
+            if not pws:
+                break
+            ex = ex.xreplace({pw: pw.args[-1][0] for pw in pws})
+        return ex
+
+    def numeric(ex, mapping):
+        ex = ex.xreplace(mapping)
+        return float(ex.subs({s: 1.0 for s in ex.free_symbols}))
+
+    point_defs, terms = {}, {}
+
+    def field_value(name, s):
+        """value of dataset `name` at shift s along the current direction: a field, or a pointwise product work array"""
+        if name in point_defs:
+            ex = point_defs[name]
+            return numeric(ex, {ds: field_value(_strip(ds.base), s) for ds in ex.atoms(DataSet)})
+        if name in q_names or name in unames or name in ('p', 'T', 'mu'):
+            return v(name, s)
+        raise UnsupportedByB200('central convective loops read %s, which is outside the canonical system' % name)
+
+    def expected(form, m, forced):
+        D = lambda d: Dv.get(d, 1.0)
+        T = lambda f, d: tvals[(f, d)]
+        r = 0.0
+        for d in range(ndim):
+            ud, q = v('u%d' % d, 0), v(q_names[m], 0)
+            if form == 'blaisdell':
+                r -= 0.5 * D(d) * (T('%s*u%d' % (q_names[m], d), d) + ud * T(q_names[m], d) + q * T('u%d' % d, d))
+            elif m == 0:
+                r -= D(d) * T('rhou%d' % d, d)
+            elif m <= ndim:
+                r -= 0.5 * D(d) * (T('rhou%d*u%d' % (m - 1, d), d) + v('rhou%d' % d, 0) * T('u%d' % (m - 1), d) + v('u%d' % (m - 1), 0) * T('rhou%d' % d, d))
+            else:
+                r -= 0.5 * D(d) * (T('rhoE*u%d' % d, d) + v('rhou%d' % d, 0) * T('rhoE/rho', d) + (v('rhoE', 0) / v('rho', 0)) * T('rhou%d' % d, d))
+            if m == ndim + 1:
+                r -= D(d) * T('p*u%d' % d, d)
+        if 1 <= m <= ndim:
+            r -= D(m - 1) * T('p', m - 1)
+            if forced:
+                r -= cv[m - 1]
+        if m == ndim + 1 and forced:
+            r -= sum(cv[j] * v('u%d' % j, 0) for j in range(ndim))
+        return r
+
+    forms = set()
     for k in kernels:
-        m = re.match(r'Convective CD (.+) x(\d) $', _name(k))
-        if m:
-            got.add((frozenset(m.group(1).replace('_B0', '').split('*')), int(m.group(2))))
-    want = set()
-    for d in range(ndim):
-        want.add((frozenset(['u%d' % d]), d))
-        want.add((frozenset(['p']), d))
-        want.add((frozenset(['p', 'u%d' % d]), d))
-        for q in q_names:
-            want.add((frozenset([q]), d))
-            want.add((frozenset([q, 'u%d' % d]), d))
-    if got != want:
-        raise UnsupportedByB200('central convective terms are not in the skew-symmetric form of apps/taylor_green_vortex '
-                                '(derivative loops differ: %s)' % sorted((sorted(a), b) for a, b in got ^ want)[:6])
-    for k in kernels:
-        from sympy import Piecewise
-        if any(e.rhs.has(Piecewise) for e in k.equations if hasattr(e, 'rhs')):
-            raise UnsupportedByB200('central convective derivatives with one-sided boundary closures are not implemented yet')
+        for e in k.equations:
+            if not hasattr(e, 'rhs'):
+                continue
+            lname = _strip(e.lhs.base) if hasattr(e.lhs, 'base') else str(e.lhs)
+            ex = default_branch(e.rhs)
+            dss = list(ex.atoms(DataSet))
+            m = re.match(r'Residual(\d)$', lname)
+            if m:
+                # ---- a residual equation: evaluate it on random term / field / metric values
+                mapping, forced = {}, False
+                for ds in dss:
+                    n = _strip(ds.base)
+                    if any(int(i) != 0 for i in ds.indices[:ndim]):
+                        raise UnsupportedByB200('stencil access inside the convective residual equation of %s' % _name(k))
+                    if n in terms:
+                        mapping[ds] = tvals.setdefault(terms[n], rnd.uniform(1.0, 2.0))
+                    elif re.match(r'D(\d)\1$', n):
+                        mapping[ds] = Dv.setdefault(int(n[1]), rnd.uniform(1.0, 2.0))
+                    else:
+                        mapping[ds] = field_value(n, 0)
+                for s in ex.free_symbols:
+                    n = str(s)
+                    if n in terms:
+                        mapping[s] = tvals.setdefault(terms[n], rnd.uniform(1.0, 2.0))
+                    elif re.match(r'c[0-2]$', n):
+                        mapping[s] = cv.setdefault(int(n[1]), rnd.uniform(1.0, 2.0)); forced = True
+                for j in range(ndim):
+                    cv.setdefault(j, rnd.uniform(1.0, 2.0))
+                got = numeric(ex, mapping)
+                ok = []
+                for form in ('blaisdell', 'feiereisen'):
+                    try:
+                        if abs(expected(form, int(m.group(1)), forced) - got) < 1e-11 * max(1.0, abs(got)):
+                            ok.append(form)
+                    except KeyError:
+                        pass
+                if not ok:
+                    raise UnsupportedByB200('central convective terms of %s are neither the Blaisdell skew form nor the Feiereisen split '
+                                            'the B200 kernels implement' % lname)
+                forms.add(frozenset(ok))
+                continue
+            dirs = set(d for ds in dss for d in range(ndim) if int(ds.indices[d]) != 0)
+            if not dirs:
+                point_defs[lname] = ex                   # pointwise product work array ("Convective terms group d")
+                terms.pop(lname, None)
+                continue
+            if len(dirs) != 1:
+                raise UnsupportedByB200('derivative loop %s differentiates along more than one direction' % _name(k))
+            d = dirs.pop()
+            got = numeric(ex, {ds: field_value(_strip(ds.base), int(ds.indices[d])) for ds in dss})
+            cands = {n: (lambda s, n=n: v(n, s)) for n in q_names + unames + ['p', 'T', 'mu']}
+            cands.update({'%s*u%d' % (n, d): (lambda s, n=n: v(n, s) * v('u%d' % d, s)) for n in q_names + ['p']})
+            cands['rhoE/rho'] = lambda s: v('rhoE', s) / v('rho', s)
+            match = [c for c, f in cands.items() if abs(sum(W[s] * f(s) for s in W) - got) < 1e-12]
+            if len(match) != 1:
+                raise UnsupportedByB200('derivative loop %s (%s) is not a 4th-order central difference of a function the B200 '
+                                        'kernels implement' % (_name(k), lname))
+            terms[lname] = (match[0], d)
+            point_defs.pop(lname, None)
+    common = set(['blaisdell', 'feiereisen'])
+    for f in forms:
+        common &= f
+    if not forms or not common:
+        raise UnsupportedByB200('central convective residual equations do not agree on one splitting')
+    return 'blaisdell' if 'blaisdell' in common else 'feiereisen'
 
 
 def _metric_directions(kernels, ndim):
@@ -331,12 +442,21 @@ def _closure_tables(kernels, ndim):
                     if len(idxs) != 1:
                         continue
                     d = int(idxs[0].number)
-                    side = 0 if cond.lhs == idxs[0] else 1
-                    row = int(cond.rhs) if side == 0 else int(cond.rhs) - 1
+                    # Eq(idx, r) | Eq(np - idx, r + 1) | Eq(idx, np - 1 - r), whichever way SymPy canonicalised it
+                    diff = cond.lhs - cond.rhs
+                    at = -diff.subs(idxs[0], 0) / diff.coeff(idxs[0])          # the grid index the row applies to
+                    if at.is_number:
+                        side, row = 0, int(at)
+                    else:
+                        nps = [s for s in at.free_symbols]
+                        if len(nps) != 1 or not (nps[0] - at).is_number:
+                            continue
+                        side, row = 1, int(nps[0] - at) - 1
                     faces[(d, side)] = max(faces.get((d, side), 0), row + 1)
                     if side == 0:
                         rows0[row] = (expr, d)
-                if rows0 and table is None and len(e.rhs.atoms(DataSet)) and all(len(x.atoms(DataSet)) >= 4 for x, _ in rows0.values()):
+                first = not re.search(r' CD .*x\w*\d .*x\w*\d', _name(k))       # not a second / mixed derivative loop
+                if first and rows0 and table is None and len(e.rhs.atoms(DataSet)) and all(len(x.atoms(DataSet)) >= 4 for x, _ in rows0.values()):
                     # only first-derivative formulas of a plain dataset are used to read the weights
                     bases = set(ds.base for x, _ in rows0.values() for ds in x.atoms(DataSet))
                     if len(bases) != 1:
@@ -426,15 +546,16 @@ def extract_plan(algorithm):
             raise UnsupportedByB200('adaptive TENO without the Ducros sensor relation is not implemented')
     elif central_conv:
         plan.update(conv='central', order=4, teno_adaptive=False)
-        _check_central_form(central_conv, ndim, q_names)
+        plan['central_form'] = _central_form([k for k in in_stage if k in central_conv or _name(k).startswith('Derivative evaluation')], ndim, q_names)
     else:
         raise UnsupportedByB200('no convective discretisation found in the stage loop')
     plan['viscous'] = bool(viscous)
     plan['forcing'] = _check_forcing(resid + viscous + central_conv, ndim)
     if plan['viscosity']['type'] != 'constant' and not viscous:
         plan['viscosity'] = {'type': 'constant'}
-    plan['metric_fields'] = _metric_directions(resid + viscous + [k for k in cr if _name(k) == 'ConstituentRelations evaluation'], ndim)
-    faces, d1tab = _closure_tables([k for k in viscous + cr if _name(k).startswith('Derivative evaluation') or _name(k) == 'ConstituentRelations evaluation'], ndim)
+    plan['metric_fields'] = _metric_directions(resid + viscous + central_conv + [k for k in cr if _name(k) == 'ConstituentRelations evaluation'], ndim)
+    faces, d1tab = _closure_tables([k for k in viscous + cr + central_conv if _name(k).startswith(('Derivative evaluation', 'Viscous CD', 'Convective CD'))
+                                    or _name(k) == 'ConstituentRelations evaluation'], ndim)
     closure_name = None
     if faces:
         nrows = set(faces.values())
@@ -503,7 +624,7 @@ def extract_plan(algorithm):
     for c in before:
         if type(c).__name__ == 'Kernel':
             n = _name(c)
-            if not (n.startswith('Grid_based_initialisation') or n.startswith('MetricsEquation evaluation') or n.startswith('Metric boundary')):
+            if not (n.startswith('Grid_based_initialisation') or n.startswith('MetricsEquation') or n.startswith('Metric boundary')):
                 raise UnsupportedByB200('cold kernel %s is not implemented yet' % n)
             cold.append(_cold_kernel(c))
     plan['cold'] = cold

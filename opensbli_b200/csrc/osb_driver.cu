@@ -51,6 +51,7 @@ struct Plan {
   bool metric[3] = {false, false, false};
   bool teno_adaptive = false;
   bool forcing = false;
+  int central_form = 0;      // 0 Blaisdell skew form, 1 Feiereisen quadratic split
   Closures cl{};
 };
 
@@ -156,6 +157,7 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
     else if (key == "metric") { int d2, on; ls >> d2 >> on; if (d2 < 0 || d2 > 2) { err = "bad metric line"; return false; } P.metric[d2] = on != 0; }
     else if (key == "teno_adaptive") { int v; ls >> v; P.teno_adaptive = v != 0; }
     else if (key == "forcing") { int v; ls >> v; P.forcing = v != 0; }
+    else if (key == "central_form") { std::string v; ls >> v; P.central_form = v == "blaisdell" ? 0 : v == "feiereisen" ? 1 : -1; if (P.central_form < 0) { err = "unknown central_form " + v; return false; } }
     else if (key == "closure_d1" || key == "closure_d2") {
       int nr, np; ls >> nr >> np;
       if (nr < 1 || np < 1 || nr > (key == "closure_d1" ? 4 : 2) || np > 6) { err = "closure table too large: " + line; return false; }
@@ -353,8 +355,15 @@ void launch_phase_a(osb_ctx *c) {
   }
   if (c->plan.conv == CONV_CENTRAL) {
     dim3 b(64, 2, 2);
-    Launcher L(c, OSB_FAM_CENTRAL);
-    k_central<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc);
+    {
+      Launcher L(c, OSB_FAM_CENTRAL);
+      if (c->general || c->plan.central_form != 0) {
+        if (c->plan.central_form == 0) k_central_general<ND, 0><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc, c->plan.cl, c->gp);
+        else k_central_general<ND, 1><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc, c->plan.cl, c->gp);
+      } else {
+        k_central<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc);
+      }
+    }
     neighbour_signal(c, 0);
   } else {
     launch_flux_scheme<ND>(c);
@@ -477,7 +486,7 @@ void launch_residual(osb_ctx *c) {
 bool fused_central_ok(const osb_ctx *c) {
   static const bool on = getenv("OSB_NO_FUSED_CENTRAL") == nullptr;
   const Plan &P = c->plan;
-  if (!on || P.nd != 3 || P.conv != CONV_CENTRAL || !P.viscous || c->general) return false;
+  if (!on || P.nd != 3 || P.conv != CONV_CENTRAL || !P.viscous || c->general || P.central_form != 0) return false;
   for (int s = 0; s < 2; s++) if (P.bc[2][s].kind == BC_EXCHANGE) return false;
   return true;
 }

@@ -1033,6 +1033,80 @@ __global__ void __launch_bounds__(256) k_viscous_general(GridDev g, FieldPtrs f,
   f.R[ND + 1][x] = old[ND] + (kq * hT + e);
 }
 
+// General Central(4) convective terms: one-sided closures by grid index (opensblifunctions.py:523-534), diagonal
+// metrics, and the two splittings of the shipped apps: FORM 0 Blaisdell skew form (parsing.py:75-111), FORM 1 Feiereisen
+// quadratic split (compressible_TCF_Central/turbulent_channel.py:12-20).  Writes Residual (first spatial kernel of a stage).
+__device__ __forceinline__ int gd1_stencil(const Closures &cl, int dir, int idx, int n, double *w, int *off) {
+  if (cl.on[dir][0] && idx < cl.nr1) {
+    for (int p = 0; p < cl.np1; p++) { w[p] = cl.d1[idx * cl.np1 + p]; off[p] = p - idx; }
+    return cl.np1;
+  }
+  if (cl.on[dir][1] && n - 1 - idx < cl.nr1) {
+    const int row = n - 1 - idx;
+    for (int p = 0; p < cl.np1; p++) { w[p] = -cl.d1[row * cl.np1 + p]; off[p] = row - p; }
+    return cl.np1;
+  }
+  w[0] = 1.0 / 12.0; w[1] = -8.0 / 12.0; w[2] = 8.0 / 12.0; w[3] = -1.0 / 12.0;
+  off[0] = -2; off[1] = -1; off[2] = 1; off[3] = 2;
+  return 4;
+}
+
+template <int ND, int FORM>
+__global__ void __launch_bounds__(256) k_central_general(GridDev g, FieldPtrs f, PhysConst c, Closures cl, GeneralPtrs gp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z * blockDim.z + threadIdx.z;
+  if (i >= g.np[0] || j >= g.np[1] || k >= g.np[2]) return;
+  const long long x = g.off + i + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
+  const int id[3] = {i, j, k};
+  constexpr int NV = ND + 2;
+  double qc[NV], uc[ND], r[NV];
+#pragma unroll
+  for (int m = 0; m < NV; m++) { qc[m] = __ldg(f.q[m] + x); r[m] = 0.0; }
+#pragma unroll
+  for (int a = 0; a < ND; a++) uc[a] = __ldg(f.u[a] + x);
+#pragma unroll
+  for (int d = 0; d < ND; d++) {
+    double w[6]; int off[6];
+    const int cnt = gd1_stencil(cl, d, id[d], g.np[d], w, off);
+    const double sc = c.inv[d] * (gp.D[d] ? gp.D[d][x] : 1.0);
+    double dqu[NV], dq[NV], du[ND], dp = 0.0, dpu = 0.0, dh = 0.0;
+#pragma unroll
+    for (int m = 0; m < NV; m++) { dqu[m] = 0.0; dq[m] = 0.0; }
+#pragma unroll
+    for (int a = 0; a < ND; a++) du[a] = 0.0;
+    for (int p = 0; p < cnt; p++) {
+      const long long xs = x + off[p] * g.s[d];
+      const double wp = w[p], ud = __ldg(f.u[d] + xs), pr = __ldg(f.p + xs);
+      double qs[NV];
+#pragma unroll
+      for (int m = 0; m < NV; m++) { qs[m] = __ldg(f.q[m] + xs); dqu[m] += wp * (qs[m] * ud); dq[m] += wp * qs[m]; }
+#pragma unroll
+      for (int a = 0; a < ND; a++) du[a] += wp * __ldg(f.u[a] + xs);
+      dp += wp * pr; dpu += wp * (pr * ud);
+      if (FORM == 1) dh += wp * (qs[NV - 1] / qs[0]);
+    }
+#pragma unroll
+    for (int m = 0; m < NV; m++) { dqu[m] *= sc; dq[m] *= sc; }
+#pragma unroll
+    for (int a = 0; a < ND; a++) du[a] *= sc;
+    dp *= sc; dpu *= sc; dh *= sc;
+    if (FORM == 0) {
+#pragma unroll
+      for (int m = 0; m < NV; m++) r[m] -= 0.5 * (dqu[m] + uc[d] * dq[m] + qc[m] * du[d]);
+    } else {
+      r[0] -= dq[1 + d];
+#pragma unroll
+      for (int a = 0; a < ND; a++) r[1 + a] -= 0.5 * (dqu[1 + a] + qc[1 + d] * du[a] + uc[a] * dq[1 + d]);
+      r[NV - 1] -= 0.5 * (dqu[NV - 1] + qc[1 + d] * dh + (qc[NV - 1] / qc[0]) * dq[1 + d]);
+    }
+    r[1 + d] -= dp;
+    r[NV - 1] -= dpu;
+  }
+#pragma unroll
+  for (int m = 0; m < NV; m++) f.R[m][x] = r[m];
+}
+
 // -------------------------------------------------------------------------------------------------
 // Boundary conditions
 // -------------------------------------------------------------------------------------------------

@@ -26,6 +26,8 @@ JSON-able dict; `to_text` serialises it to the line format parsed by the C ABI (
     metric_fields   per direction None | 'D11'...: stretched direction; fields['D11'], fields['SD111'] hold the metric arrays
     teno_adaptive   bool: C_T from the Ducros sensor (constants teno_a1, teno_a2, epsilon)
     forcing         bool: constant body force c0, c1, c2 (constants): momentum_i -= c_i, energy -= c_j u_j
+    central_form    'blaisdell' (default; Skew() split of taylor_green_vortex / laminar_2D) | 'feiereisen' (quadratic split of
+                    compressible_TCF_Central / turbulent_3D): how Central(4) writes the convective terms
     init            optional list of [lhs, rhs] assignment strings (numpy syntax) for the cold initialisation
     niter           optional int
 """
@@ -133,6 +135,10 @@ def to_text(plan):
         L.append('teno_adaptive 1')
     if plan.get('forcing'):
         L.append('forcing 1')
+    if plan.get('central_form', 'blaisdell') != 'blaisdell':
+        if plan['central_form'] != 'feiereisen':
+            raise PlanError("central_form must be 'blaisdell' or 'feiereisen'")
+        L.append('central_form feiereisen')
     return '\n'.join(L) + '\n'
 
 

@@ -52,10 +52,12 @@ def c_eval(expr, env):
     return ev(ast.parse(expr.strip(), mode='eval'))
 
 
-def read_stub(text, decls):
-    """-> ordered {name: value} from the stub's `name = expr;` lines (declared types from the plan)."""
+def read_stub(text, decls, overrides=None):
+    """-> ordered {name: value} from the stub's `name = expr;` lines (declared types from the plan).  `overrides` replaces
+    the value of a parameter (e.g. block0np0) before the expressions that depend on it are evaluated."""
     types = {n: t for n, t, _ in decls}
     env = {}
+    overrides = overrides or {}
     for line in text.splitlines():
         line = line.strip()
         if not line.endswith(';') or '=' not in line or line.startswith(('//', 'int iter')):
@@ -66,7 +68,7 @@ def read_stub(text, decls):
             continue
         if expr == 'Input':
             raise ValueError("simulation parameter '%s' has no value: call substitute_simulation_parameters" % name)
-        v = c_eval(expr, env)
+        v = overrides[name] if name in overrides else c_eval(expr, env)
         env[name] = int(v) if types[name] == 'int' else float(v)
     return env
 
@@ -116,7 +118,7 @@ def resolve(plan_sym, env):
     metric fields, tabulated Dirichlet states); returns (plan, ColdRunner holding every cold dataset)."""
     nd = plan_sym['ndim']
     p = {k: plan_sym[k] for k in ('ndim', 'conv', 'order', 'weno_formulation', 'averaging', 'viscous', 'rk', 'rk_a', 'rk_b')}
-    for k in ('viscosity', 'metric_fields', 'teno_adaptive', 'closures', 'forcing'):
+    for k in ('viscosity', 'metric_fields', 'teno_adaptive', 'closures', 'forcing', 'central_form'):
         if k in plan_sym:
             p[k] = plan_sym[k]
     p['np'] = [int(env['block0np%d' % d]) for d in range(nd)]
@@ -161,9 +163,9 @@ def initial_state(plan_sym, cold):
     return [np.ascontiguousarray(cold.array(n)) for n in plan_sym['q_names']]
 
 
-def load_case(workdir='.'):
+def load_case(workdir='.', overrides=None):
     plan_sym = json.load(open(os.path.join(workdir, PLAN_FILE)))
-    env = read_stub(open(os.path.join(workdir, STUB_FILE)).read(), plan_sym['constant_decls'])
+    env = read_stub(open(os.path.join(workdir, STUB_FILE)).read(), plan_sym['constant_decls'], overrides)
     plan_num, cold = resolve(plan_sym, env)
     return plan_sym, env, plan_num, cold
 

@@ -588,6 +588,68 @@ static void viscous_general(const osbo_cfg *c, const grid_t *g, const prim_t *P,
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * General Central(4) convective terms: one-sided closures next to walls (every first derivative of the convective
+ * loops switches formula by grid index, opensblifunctions.py:523-534), diagonal metrics D_dd (metric.py:137-147) and the
+ * two splittings the shipped apps use:
+ *  form 0 (Blaisdell, Skew(), parsing.py:75-111):
+ *     q_m:  -1/2 [ d(q_m u_j) + u_j d(q_m) + q_m d(u_j) ] ,  momentum_i: - d_i p ,  energy: - d_j(p u_j)
+ *  form 1 (Feiereisen, compressible_TCF_Central/turbulent_channel.py:12-20):
+ *     mass: - d_j(rho u_j)
+ *     momentum_i: -1/2 [ d_j(rhou_i u_j) + rhou_j d_j(u_i) + u_i d_j(rhou_j) ] - d_i p
+ *     energy:     -1/2 [ d_j(rhoE u_j) + rhou_j d_j(rhoE/rho) + (rhoE/rho) d_j(rhou_j) ] - d_j(p u_j)
+ * ------------------------------------------------------------------------------------------- */
+static int d1_stencil(const osbo_cfg *c, int dir, int idx, int n, double *w, int *off) {
+  if (c->closure[dir][0] && idx < c->c_nr1) {
+    for (int p = 0; p < c->c_np1; p++) { w[p] = c->c_d1[idx * c->c_np1 + p]; off[p] = p - idx; }
+    return c->c_np1;
+  }
+  if (c->closure[dir][1] && n - 1 - idx < c->c_nr1) {
+    const int row = n - 1 - idx;
+    for (int p = 0; p < c->c_np1; p++) { w[p] = -c->c_d1[row * c->c_np1 + p]; off[p] = row - p; }
+    return c->c_np1;
+  }
+  w[0] = 1.0 / 12.0; w[1] = -8.0 / 12.0; w[2] = 8.0 / 12.0; w[3] = -1.0 / 12.0;
+  off[0] = -2; off[1] = -1; off[2] = 1; off[3] = 2;
+  return 4;
+}
+
+static void central_general(const osbo_cfg *c, const grid_t *g, double *const *q, const prim_t *P, double *const *R, const double *inv) {
+  const int nd = g->ndim, nv = g->nv;
+  for (int k = 0; k < g->np[2]; k++) for (int j = 0; j < g->np[1]; j++) for (int i = 0; i < g->np[0]; i++) {
+    const long x = gidx(g, i, j, k);
+    const int id[3] = {i, j, k};
+    double r[5] = {0, 0, 0, 0, 0};
+    for (int d = 0; d < nd; d++) {
+      double w[8]; int off[8];
+      const int cnt = d1_stencil(c, d, id[d], g->np[d], w, off);
+      const double sc = inv[d] * (c->D[d] ? c->D[d][x] : 1.0);
+      double dqu[5] = {0, 0, 0, 0, 0}, dq[5] = {0, 0, 0, 0, 0}, du[3] = {0, 0, 0}, dp = 0.0, dpu = 0.0, dh = 0.0;
+      for (int p = 0; p < cnt; p++) {
+        const long xs = x + off[p] * g->s[d];
+        const double ud = P->u[d][xs];
+        for (int m = 0; m < nv; m++) { dqu[m] += w[p] * (q[m][xs] * ud); dq[m] += w[p] * q[m][xs]; }
+        for (int a = 0; a < nd; a++) du[a] += w[p] * P->u[a][xs];
+        dp += w[p] * P->p[xs]; dpu += w[p] * (P->p[xs] * ud);
+        dh += w[p] * (q[nd + 1][xs] / q[0][xs]);
+      }
+      for (int m = 0; m < nv; m++) { dqu[m] *= sc; dq[m] *= sc; }
+      for (int a = 0; a < nd; a++) du[a] *= sc;
+      dp *= sc; dpu *= sc; dh *= sc;
+      if (c->central_form == 0) {
+        for (int m = 0; m < nv; m++) r[m] -= 0.5 * (dqu[m] + P->u[d][x] * dq[m] + q[m][x] * du[d]);
+      } else {
+        r[0] -= dq[1 + d];
+        for (int a = 0; a < nd; a++) r[1 + a] -= 0.5 * (dqu[1 + a] + q[1 + d][x] * du[a] + P->u[a][x] * dq[1 + d]);
+        r[nd + 1] -= 0.5 * (dqu[nd + 1] + q[1 + d][x] * dh + (q[nd + 1][x] / q[0][x]) * dq[1 + d]);
+      }
+      r[1 + d] -= dp;
+      r[nd + 1] -= dpu;
+    }
+    for (int m = 0; m < nv; m++) R[m][x] = r[m];
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------
  * Spatial residual = what the stage's "spatial kernels" leave in Residual_m
  * ------------------------------------------------------------------------------------------- */
 void osbo_residual(const osbo_cfg *c, double *const *q, double *const *R) {
@@ -633,6 +695,8 @@ void osbo_residual(const osbo_cfg *c, double *const *q, double *const *R) {
         R[m][x] = r;
       }
     }
+  } else if (general || c->central_form != 0) {
+    central_general(c, &g, q, &P, R, inv);
   } else {
     /* Central(4) skew-symmetric (Blaisdell) convective terms: parsing.py:75-111, scheme.py:187-271.
      *  mass:     -1/2 [ d(rho u_j)/dx_j + u_j d(rho)/dx_j + rho du_j/dx_j ]

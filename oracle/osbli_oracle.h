@@ -73,6 +73,8 @@ typedef struct {
   int extrap_order[3][2];
   const double *bc_face[3][2];/* OSBO_BC_DIRICHLET_FIELD: [nv][padded tangential extent] */
   double force[3];            /* constant body force c_j: momentum_i -= c_i, energy -= c_j u_j (turbulent_channel.py:15-16) */
+  int central_form;           /* Central(4) convective split: 0 Blaisdell skew form (taylor_green_vortex.py:8-11, laminar_channel.py:7-9),
+                               * 1 Feiereisen quadratic split (compressible_TCF_Central/turbulent_channel.py:12-20) */
 } osbo_cfg;
 
 /* number of doubles of one padded array */

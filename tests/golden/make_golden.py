@@ -135,7 +135,29 @@ def tcf_teno6_plan(N0, N1, N2):
                 bc=[[per(), per()], [wall(), wall()], [per(), per()]])
 
 
+def lam2d_plan(N0, N1):
+    """apps/channel_flow/laminar_2D/laminar_channel.py: Central(4) in the Skew() (Blaisdell) split with Carpenter closures at
+    isothermal walls, uniform grid, Sutherland viscosity, body force c0 = -1, RungeKuttaLS(3)."""
+    per = lambda: dict(type='periodic')
+    wall = lambda: dict(type='isothermal_wall', closure='carpenter')
+    return dict(ndim=2, np=[N0, N1], delta=[2.0 * math.pi / N0, 2.0 / (N1 - 1)], conv='central', order=4, averaging='roe', viscous=True,
+                viscosity=dict(type='sutherland'), forcing=True, central_form='blaisdell', closures={'carpenter': carpenter_tables()},
+                constants=dict(gama=1.4, Minf=0.1, Pr=0.72, Re=90.0, Twall=1.0, SuthT=110.4, RefT=273.0, dt=0.0002, c0=-1.0, c1=0.0),
+                bc=[[per(), per()], [wall(), wall()]], **LS3)
+
+
+def tcf_central_plan(N0, N1, N2):
+    """apps/channel_flow/compressible_TCF_Central/turbulent_channel.py (statistics off): Central(4) in the Feiereisen
+    quadratic split, Carpenter closures at the isothermal walls, wall-normal stretching, T^0.7 viscosity, body force."""
+    p = tcf_teno6_plan(N0, N1, N2)
+    p.update(conv='central', order=4, central_form='feiereisen', **LS3)
+    p['constants'] = dict(gama=1.4, Minf=0.0955, Pr=0.7, Re=190.71, Twall=1.0, dt=0.0002, c0=-1.0, c1=0.0, c2=0.0)
+    return p
+
+
 if os.path.isdir('/root/reference'):
+    FIXTURES['lam2d_16x64'] = ('lam2d', lam2d_plan(16, 64), [1, 10])
+    FIXTURES['tcf_central_16x24x12'] = ('tcf_central', tcf_central_plan(16, 24, 12), [1, 5])
     FIXTURES['tcf_teno6_16x24x12'] = ('tcf_teno6', tcf_teno6_plan(16, 24, 12), [1, 5])
     FIXTURES['katzer_carpenter_60x40'] = ('katzer_carpenter', katzer_carpenter_plan(60, 40), [1, 10])
 FIXTURES['tgv_sym_17'] = ('tgv_sym', tgv_sym_plan(17), [1, 3])
@@ -152,6 +174,8 @@ def env_params(plan):
 
 def main():
     for name, (config, plan, steps) in FIXTURES.items():
+        if sys.argv[1:] and name not in sys.argv[1:]:
+            continue
         nd = plan['ndim']
         fields = ['rho'] + ['rhou%d' % d for d in range(nd)] + ['rhoE']
         inner = (slice(5, -5),) * nd
@@ -167,7 +191,8 @@ def main():
             out['q0_padded'] = np.stack([r[f] for f in fields])
             for n in extra:
                 out['field_' + n] = r[n]
-            out['bc_table_1_1'] = katzer_dirichlet_table(plan['np'][0])
+            if config.startswith('katzer'):
+                out['bc_table_1_1'] = katzer_dirichlet_table(plan['np'][0])
         out['q0'] = np.stack([r[f][inner] for f in fields])
         for n in steps:
             r = run_ref(config, dict(env_params(plan), niter=n), fields)

@@ -41,7 +41,7 @@ class OsboCfg(ctypes.Structure):
                 ('sensor_eps', ctypes.c_double), ('theta', ctypes.POINTER(ctypes.c_double)),
                 ('teno_store', ctypes.POINTER(ctypes.c_double)), ('Twall', ctypes.c_double),
                 ('extrap_order', (ctypes.c_int * 2) * 3), ('bc_face', (ctypes.POINTER(ctypes.c_double) * 2) * 3),
-                ('force', ctypes.c_double * 3)]
+                ('force', ctypes.c_double * 3), ('central_form', ctypes.c_int)]
 
 
 _lib = None
@@ -116,6 +116,7 @@ def make_cfg(plan):
     c.visc_law = MU[visc['type']]
     c.SuthT, c.RefT, c.mu_exp = k.get('SuthT', 0.0), k.get('RefT', 1.0), visc.get('exponent', 0.0)
     c.Twall = k.get('Twall', 1.0)
+    c.central_form = {'blaisdell': 0, 'feiereisen': 1}[plan.get('central_form', 'blaisdell')]
     if plan.get('forcing'):
         for d in range(plan['ndim']):
             c.force[d] = k.get('c%d' % d, 0.0)

@@ -20,6 +20,10 @@ APPS = {
     'katzer': (REF + '/apps/katzer_SBLI/katzer_SBLI.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'katzer_60x40'),
     'tcf_teno6': (REF + '/apps/channel_flow/compressible_TCF_TENO/turbulent_channel.py',
                   [("stats = True", "stats = False"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'tcf_teno6_16x24x12'),
+    'lam2d': (REF + '/apps/channel_flow/laminar_2D/laminar_channel.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'lam2d_16x64'),
+    'tcf_central': (REF + '/apps/channel_flow/compressible_TCF_Central/turbulent_channel.py',
+                    [("stats = True", "stats = False"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)"),
+                     ("print_iteration_ops()", "")], 'tcf_central_16x24x12'),
     'sod_teno5': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'sod_teno5_n200'),
 }
 
@@ -36,11 +40,23 @@ exec(compile(src, %(app)r, 'exec'), {'__name__': '__main__'})
 '''
 
 
-def run_app(name, workdir):
+def start_app(name, workdir):
     app, edits, _ = APPS[name]
     code = DRIVER % dict(oracle=os.path.join(REPO, 'oracle'), repo=REPO, ref=REF, app=app, edits=edits)
     env = dict(os.environ, PYTHONHASHSEED='0')
-    subprocess.run([sys.executable, '-W', 'ignore', '-c', code], cwd=workdir, env=env, check=True, stdout=subprocess.DEVNULL)
+    return subprocess.Popen([sys.executable, '-W', 'ignore', '-c', code], cwd=workdir, env=env, stdout=subprocess.DEVNULL)
+
+
+@pytest.fixture(scope='module')
+def app_runs(tmp_path_factory):
+    """All app scripts run through the reference front end concurrently (each is a minute of single-threaded SymPy)."""
+    if not os.path.isdir(REF):
+        return {}
+    procs = {}
+    for name in APPS:
+        d = str(tmp_path_factory.mktemp(name))
+        procs[name] = (d, start_app(name, d))
+    return {name: (d, p.wait()) for name, (d, p) in procs.items()}
 
 
 def comparable(plan):
@@ -51,17 +67,18 @@ def comparable(plan):
     p['teno_adaptive'] = bool(plan.get('teno_adaptive'))
     p['metric_fields'] = plan.get('metric_fields') or [None] * plan['ndim']
     p['forcing'] = bool(plan.get('forcing'))
+    p['central_form'] = plan.get('central_form', 'blaisdell') if plan['conv'] == 'central' else None
     if plan['conv'] == 'weno':
         p['weno_formulation'] = plan.get('weno_formulation', 'JS')
     return p
 
 
 @pytest.mark.parametrize('name', sorted(APPS))
-def test_b200_backend_distils_expected_plan(name, tmp_path):
+def test_b200_backend_distils_expected_plan(name, app_runs):
     from opensbli_b200 import run as R
     if os.path.isdir(REF):
-        run_app(name, str(tmp_path))
-        workdir = str(tmp_path)
+        workdir, rc = app_runs[name]
+        assert rc == 0, 'B200(alg) failed on %s' % APPS[name][0]
         os.makedirs(os.path.join(PLANS, name), exist_ok=True)      # refresh the committed fixtures
         for f in ('opensbli_b200.plan.json', 'opensbli.cpp'):
             open(os.path.join(PLANS, name, f), 'w').write(open(os.path.join(workdir, f)).read())
@@ -105,6 +122,31 @@ def test_initial_state_from_cold_kernel_matches_reference_init():
     s = (slice(5, -5),) * 3
     for m in range(5):
         assert np.abs(q0[m][s] - states[0][m]).max() <= 1e-13 * max(1.0, np.abs(states[0][m]).max())
+
+
+@pytest.mark.parametrize('name,fixture,sizes', [('lam2d', 'lam2d_16x64', (16, 64)), ('tcf_central', 'tcf_central_16x24x12', (16, 24, 12)),
+                                                ('tcf_teno6', 'tcf_teno6_16x24x12', (16, 24, 12))])
+def test_channel_cold_kernels_match_reference(name, fixture, sizes):
+    """Channel apps: initial condition, stretched-grid metrics and their boundary kernels evaluated by the runner from
+    the plan fixture == the reference's own cold kernels (golden), at the fixture's grid size."""
+    import numpy as np
+    from opensbli_b200 import run as R
+    workdir = os.path.join(PLANS, name)
+    if not os.path.exists(os.path.join(workdir, 'opensbli.cpp')):
+        pytest.skip('plan fixture missing')
+    over = {'block0np%d' % d: n for d, n in enumerate(sizes)}
+    plan_sym, env, plan_num, cold = R.load_case(workdir, overrides=over)
+    want, states = load_fixture(fixture)
+    assert plan_num['np'] == list(sizes)
+    assert np.allclose(plan_num['delta'], want['delta'], rtol=1e-14)
+    q0 = R.initial_state(plan_sym, cold)
+    s = (slice(5, -5),) * len(sizes)
+    for m in range(len(q0)):
+        assert np.abs(q0[m][s] - states[0][m]).max() <= 1e-12 * max(1.0, np.abs(states[0][m]).max())
+    # metric arrays: interior points (the hot loops read D_dd / SD_ddd at the point itself only; the reference additionally
+    # copies them into the periodic halos, which nothing reads)
+    for f, a in want.get('fields', {}).items():
+        assert np.abs(plan_num['fields'][f][s] - a[s]).max() <= 1e-11 * np.abs(a).max(), f
 
 
 def test_sod_initial_state_and_dirichlet_states():

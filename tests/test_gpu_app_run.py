@@ -82,3 +82,21 @@ def test_katzer_app_from_plan_fixture():
     qo, _ = ou.oracle_advance(plan, [a.copy() for a in q0], 20)
     err = field_errors(plan, inner(plan, q), inner(plan, qo))
     assert max(err) < 1e-11, err
+
+
+@pytest.mark.parametrize('name,fixture,sizes,nsteps', [('lam2d', 'lam2d_16x64', (16, 64), 10), ('tcf_central', 'tcf_central_16x24x12', (16, 24, 12), 5),
+                                                       ('tcf_teno6', 'tcf_teno6_16x24x12', (16, 24, 12), 5)])
+def test_channel_apps_from_plan_fixture(name, fixture, sizes, nsteps):
+    """Channel apps through `B200(alg)` (laminar 2-D in the Blaisdell split, 3-D turbulent channel in the Feiereisen split and
+    with TENO6): cold kernels by the runner at the fixture's grid size, then n steps on the GPU against the reference golden."""
+    from opensbli_b200 import run as R, Simulation
+    over = {'block0np%d' % d: n for d, n in enumerate(sizes)}
+    plan_sym, env, plan, cold = R.load_case(os.path.join(PLANS, name), overrides=over)
+    want, states = load_fixture(fixture)
+    q0 = R.initial_state(plan_sym, cold)
+    with Simulation(plan) as sim:
+        sim.set_state(q0)
+        sim.step(nsteps)
+        q = sim.get_state()
+    err = field_errors(plan, inner(plan, q), states[nsteps])
+    assert max(err) < 1e-12 * nsteps, err
