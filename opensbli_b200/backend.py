@@ -140,6 +140,40 @@ def _lambdify_check(eq, canonical, names, ntry=8, tol=1e-12):
     return True
 
 
+def _check_adiabatic_wall(kernel, direction, side, ndim):
+    """adiabatic_wall.py:28-79: the wall-energy equation must be rho_wall T_wall / (gama (gama-1) Minf^2) with
+    T_wall = 6/11 (3 T_1 - 3/2 T_2 + 1/3 T_3), T_h the temperature h points above the wall; checked numerically."""
+    from opensbli.core.opensbliobjects import DataSet
+    import random
+    rnd = random.Random(7)
+    walls = [e for e in kernel.equations if hasattr(e.lhs, 'base') and _strip(e.lhs.base) == 'rhoE' and not any(int(i) != 0 for i in e.lhs.indices[:ndim])]
+    if not walls:
+        return False
+    ex = walls[0].rhs
+    inward = 1 if side == 0 else -1
+    for _ in range(4):
+        vals, mapping = {}, {}
+        for ds in ex.atoms(DataSet):
+            key = (_strip(ds.base), int(ds.indices[direction]) * inward)
+            if any(int(ds.indices[e]) != 0 for e in range(ndim) if e != direction):
+                return False
+            mapping[ds] = vals.setdefault(key, rnd.uniform(1.0, 2.0))
+        cst = {str(s): rnd.uniform(1.2, 1.6) for s in ex.free_symbols}
+        try:
+            got = float(ex.xreplace(mapping).subs({s: cst[str(s)] for s in ex.free_symbols}))
+            gm, M2 = cst['gama'], cst['Minf'] ** 2
+            T = {}
+            for h in (1, 2, 3):
+                ke = sum(0.5 * vals[('rhou%d' % d, h)] ** 2 for d in range(ndim))
+                T[h] = gm * M2 * (gm - 1.0) * (vals[('rhoE', h)] - ke / vals[('rho', h)]) / vals[('rho', h)]
+            want = vals[('rho', 0)] * (6.0 / 11.0) * (3.0 * T[1] + T[3] / 3.0 - 1.5 * T[2]) / (gm * (gm - 1.0) * M2)
+        except (KeyError, TypeError):
+            return False
+        if abs(got - want) > 1e-11 * abs(want):
+            return False
+    return True
+
+
 def _check_constituent(kernels, ndim):
     """The hand-written kernels hard-wire the ideal-gas constituent relations; make sure the app's are those."""
     canon = {
@@ -219,7 +253,7 @@ def _recon_info(k):
     return info
 
 
-KNOWN_CONSTANTS = re.compile(r'^(gama|gamma_m1|Minf|Re|Pr|dt|eps|TENO_CT|teno_a1|teno_a2|epsilon|SuthT|RefT|Twall|niter|c[0-2]|'
+KNOWN_CONSTANTS = re.compile(r'^(gama|gamma_m1|Minf|Re|Pr|mu|dt|eps|TENO_CT|teno_a1|teno_a2|epsilon|SuthT|RefT|Twall|niter|c[0-2]|'
                              r'block0np\d|Delta\dblock0|inv_\d+|rc\d+|rcinv\d+|inv_rfact\d*_block0)$')
 
 
@@ -603,6 +637,10 @@ def extract_plan(algorithm):
             entry = {'type': 'inlet_pressure_extrapolate'}
         elif kind == 'Symmetry':
             entry = {'type': 'symmetry'}
+        elif kind == 'AdiabaticWall':
+            if not _check_adiabatic_wall(c, d, sd, ndim):
+                raise UnsupportedByB200('adiabatic wall with a non-canonical wall-energy equation is not implemented')
+            entry = {'type': 'adiabatic_wall'}
         elif kind == 'IsothermalWall':
             # the wall-energy equation must be the canonical rhoE = rho Twall/(gama (gama-1) Minf^2) (isothermal_wall.py:40-45)
             walls = [e for e in c.equations if hasattr(e.lhs, 'base') and _strip(e.lhs.base) == 'rhoE' and not any(e.lhs.indices)]

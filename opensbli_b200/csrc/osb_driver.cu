@@ -24,7 +24,7 @@ thread_local std::string g_create_error;
 enum ConvKind { CONV_CENTRAL = 0, CONV_WENO = 1, CONV_TENO = 2 };
 enum RkKind { RK_SBLI = 0, RK_LS = 1 };
 enum BcKind { BC_PERIODIC = 0, BC_DIRICHLET = 1, BC_EXCHANGE = 2 /* neighbour rank owns the halo */, BC_ISOTHERMAL_WALL = 3,
-              BC_EXTRAPOLATION = 4, BC_INLET_PRESSURE = 5, BC_SYMMETRY = 6, BC_DIRICHLET_FIELD = 7 };
+              BC_EXTRAPOLATION = 4, BC_INLET_PRESSURE = 5, BC_SYMMETRY = 6, BC_DIRICHLET_FIELD = 7, BC_ADIABATIC_WALL = 8 };
 
 struct BcSpec {
   int kind = BC_PERIODIC;
@@ -142,6 +142,7 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
       else if (kind == "dirichlet") { b.kind = BC_DIRICHLET; for (int m = 0; m < P.nd + 2; m++) ls >> b.q[m]; }
       else if (kind == "dirichlet_field") b.kind = BC_DIRICHLET_FIELD;
       else if (kind == "isothermal_wall") b.kind = BC_ISOTHERMAL_WALL;
+      else if (kind == "adiabatic_wall") b.kind = BC_ADIABATIC_WALL;
       else if (kind == "extrapolation") { b.kind = BC_EXTRAPOLATION; ls >> b.order; }
       else if (kind == "inlet_pressure_extrapolate") { b.kind = BC_INLET_PRESSURE; if (s != 0) { err = "inlet_pressure_extrapolate is defined for side 0 only"; return false; } }
       else if (kind == "symmetry") b.kind = BC_SYMMETRY;
@@ -198,6 +199,7 @@ void refresh_constants(osb_ctx *c) {
   const Plan &P = c->plan;
   auto get = [&](const char *k, double d) { auto it = P.consts.find(k); return it == P.consts.end() ? d : it->second; };
   c->pc.gama = get("gama", 1.4); c->pc.Minf = get("Minf", 1.0); c->pc.Re = get("Re", 1.0); c->pc.Pr = get("Pr", 1.0);
+  if (P.visc_law == 0) c->pc.Re /= get("mu", 1.0);      // constant-viscosity apps may carry a constant `mu` in mu/Re (viscous_shock_tube.py:14-16)
   c->pc.dt = get("dt", 0.0);
   for (int d = 0; d < 3; d++) { c->pc.inv[d] = 1.0 / P.delta[d]; c->pc.inv2[d] = pow(P.delta[d], -2); }
   c->sp = make_scheme_params(get("eps", 1e-16), get("TENO_CT", 1e-6));
@@ -449,6 +451,11 @@ void launch_bcs(osb_ctx *c) {
             if (P.nd == 1) k_bc_isothermal_wall<1><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
             else if (P.nd == 2) k_bc_isothermal_wall<2><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
             else k_bc_isothermal_wall<3><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+            break;
+          case BC_ADIABATIC_WALL:
+            if (P.nd == 1) k_bc_adiabatic_wall<1><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+            else if (P.nd == 2) k_bc_adiabatic_wall<2><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+            else k_bc_adiabatic_wall<3><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
             break;
           default: break;
         }

@@ -1243,6 +1243,32 @@ __global__ void __launch_bounds__(128) k_bc_isothermal_wall(GridDev g, FieldPtrs
     f.q[ND + 1][xo] = Pw / (gm - 1.0) + 0.5 * rh * u2;
   }
 }
+// adiabatic_wall.py:28-79: dT/dn = 0 to fourth order (T_wall from the three points above the wall), mirrored halos
+template <int ND>
+__global__ void __launch_bounds__(128) k_bc_adiabatic_wall(GridDev g, FieldPtrs f, PhysConst c, PlaneSpec ps) {
+  long long x, t;
+  if (!plane_point(g, ps, x, t)) return;
+  const long long out = (ps.side == 0 ? -1 : 1) * g.s[ps.dir], in = -out;
+  const double gm = c.gama, M2 = c.Minf * c.Minf;
+  double T[4];
+  for (int h = 1; h <= ps.nh || h <= 3; h++) {
+    const long long xi = x + h * in, xo = x + h * out;
+    const double r = f.q[0][xi], E = f.q[ND + 1][xi];
+    double ke = 0.0, m[ND];
+#pragma unroll
+    for (int d = 0; d < ND; d++) { m[d] = f.q[1 + d][xi]; ke += 0.5 * m[d] * m[d]; }
+    if (h <= 3) T[h] = gm * M2 * (gm - 1.0) * (E - ke / r) / r;
+    if (h <= ps.nh) {
+      f.q[0][xo] = r; f.q[ND + 1][xo] = E;
+#pragma unroll
+      for (int d = 0; d < ND; d++) f.q[1 + d][xo] = -m[d];
+    }
+  }
+  const double Tw = (6.0 / 11.0) * (3.0 * T[1] + (1.0 / 3.0) * T[3] - 1.5 * T[2]);
+#pragma unroll
+  for (int d = 0; d < ND; d++) f.q[1 + d][x] = 0.0;
+  f.q[ND + 1][x] = f.q[0][x] * Tw / (gm * (gm - 1.0) * M2);
+}
 // symmetry.py:23-50 (cartesian normal)
 __global__ void __launch_bounds__(128) k_bc_symmetry(GridDev g, FieldPtrs f, int nv, PlaneSpec ps) {
   long long x, t;

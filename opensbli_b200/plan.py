@@ -19,10 +19,11 @@ JSON-able dict; `to_text` serialises it to the line format parsed by the C ABI (
     constants       {name: float}                 gama, Minf, Re, Pr, dt, eps, TENO_CT, ...
     bc              [[side0, side1] per direction] each {'type': 'periodic'} | {'type': 'dirichlet', 'q': [...]}
                     | {'type': 'exchange'} (halo owned by the neighbouring rank of a slab decomposition)
-                    | {'type': 'isothermal_wall'} | {'type': 'extrapolation', 'order': 0|1} | {'type': 'symmetry'}
+                    | {'type': 'isothermal_wall'} | {'type': 'adiabatic_wall'} | {'type': 'extrapolation', 'order': 0|1} | {'type': 'symmetry'}
                     | {'type': 'inlet_pressure_extrapolate'} | {'type': 'dirichlet_field', 'table': ndarray [nv, tangential]}
                     every non-periodic face may carry 'closure': 'reduced_access' | 'carpenter' (one-sided derivative rows)
     viscosity       {'type': 'constant'} | {'type': 'sutherland'} | {'type': 'power', 'exponent': e}
+                    (constant: an optional constant 'mu' scales 1/Re, e.g. viscous_shock_tube.py:14-16)
     metric_fields   per direction None | 'D11'...: stretched direction; fields['D11'], fields['SD111'] hold the metric arrays
     teno_adaptive   bool: C_T from the Ducros sensor (constants teno_a1, teno_a2, epsilon)
     forcing         bool: constant body force c0, c1, c2 (constants): momentum_i -= c_i, energy -= c_j u_j
@@ -36,7 +37,7 @@ import json
 
 CONV = ('central', 'weno', 'teno')
 BC_TYPES = ('periodic', 'dirichlet', 'exchange', 'isothermal_wall', 'extrapolation', 'inlet_pressure_extrapolate', 'symmetry',
-            'dirichlet_field')
+            'dirichlet_field', 'adiabatic_wall')
 
 # one-sided derivative closures: rows idx = 0.. next to the face x weights of the boundary-absolute points 0..np-1
 # (reduced_access_scheme.py:36-43,76-83; Carpenter's first-derivative rows are taken from the scheme object by the back end)

@@ -167,6 +167,31 @@ static void bc_isothermal_wall(const osbo_cfg *c, const grid_t *g, double *const
     }
   })
 }
+/* adiabatic_wall.py:28-79: no-slip wall with dT/dn = 0 to fourth order, T_wall = 6/11 (3 T_1 - 3/2 T_2 + 1/3 T_3) from the
+ * three points above the wall; wall energy = rho_wall T_wall / (gama (gama-1) Minf^2); halos mirror rho and rhoE and
+ * reverse every momentum component.  Statement order as in the generated kernel (density halos, wall momentum, momentum
+ * halos, wall energy, energy halos). */
+static void bc_adiabatic_wall(const osbo_cfg *c, const grid_t *g, double *const *q, int dir, int side) {
+  int hm, hp; scheme_halos(c, &hm, &hp);
+  const int nd = g->ndim, n = side == 0 ? hm : hp;
+  const long out = (side == 0 ? -1 : 1) * g->s[dir], in = -out;
+  const double gm = c->gama, M2 = c->Minf * c->Minf;
+  PLANE_LOOP(c, g, dir, side, {
+    for (int h = 1; h <= n; h++) q[0][x + h * out] = q[0][x + h * in];
+    for (int d = 0; d < nd; d++) q[1 + d][x] = 0.0;
+    for (int h = 1; h <= n; h++) for (int d = 0; d < nd; d++) q[1 + d][x + h * out] = -q[1 + d][x + h * in];
+    double T[4];
+    for (int h = 1; h <= 3; h++) {
+      const long xi = x + h * in;
+      double ke = 0.0;
+      for (int d = 0; d < nd; d++) ke += 0.5 * q[1 + d][xi] * q[1 + d][xi];
+      T[h] = gm * M2 * (gm - 1.0) * (q[nd + 1][xi] - ke / q[0][xi]) / q[0][xi];
+    }
+    const double Tw = (6.0 / 11.0) * (3.0 * T[1] + (1.0 / 3.0) * T[3] - 1.5 * T[2]);
+    q[nd + 1][x] = q[0][x] * Tw / (gm * (gm - 1.0) * M2);
+    for (int h = 1; h <= n; h++) q[nd + 1][x + h * out] = q[nd + 1][x + h * in];
+  })
+}
 /* symmetry.py:23-50 (cartesian: unit normal e_dir): halos mirror the interior with the normal momentum reversed */
 static void bc_symmetry(const osbo_cfg *c, const grid_t *g, double *const *q, int dir, int side) {
   int hm, hp; scheme_halos(c, &hm, &hp);
@@ -193,6 +218,7 @@ void osbo_apply_bcs(const osbo_cfg *c, double *const *q) {
         case OSBO_BC_INLET_PRESSURE_EXTRAPOLATE: bc_inlet_pressure(c, &g, q, d, s); break;
         case OSBO_BC_ISOTHERMAL_WALL: bc_isothermal_wall(c, &g, q, d, s); break;
         case OSBO_BC_SYMMETRY: bc_symmetry(c, &g, q, d, s); break;
+        case OSBO_BC_ADIABATIC_WALL: bc_adiabatic_wall(c, &g, q, d, s); break;
         default: break;
       }
     }

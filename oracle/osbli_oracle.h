@@ -36,7 +36,8 @@ enum { OSBO_AVG_SIMPLE = 0, OSBO_AVG_ROE = 1 };
 enum { OSBO_RK_SBLI = 0, OSBO_RK_LS = 1 };
 enum { OSBO_BC_PERIODIC = 0, OSBO_BC_DIRICHLET = 1, OSBO_BC_EXCHANGE = 2 /* halo filled by the caller (decomposed run) */,
        OSBO_BC_ISOTHERMAL_WALL = 3, OSBO_BC_EXTRAPOLATION = 4, OSBO_BC_INLET_PRESSURE_EXTRAPOLATE = 5,
-       OSBO_BC_SYMMETRY = 6, OSBO_BC_DIRICHLET_FIELD = 7 /* imposed state varies along the face */ };
+       OSBO_BC_SYMMETRY = 6, OSBO_BC_DIRICHLET_FIELD = 7 /* imposed state varies along the face */,
+       OSBO_BC_ADIABATIC_WALL = 8 };
 enum { OSBO_MU_CONSTANT = 0, OSBO_MU_SUTHERLAND = 1, OSBO_MU_POWER = 2 };
 
 typedef struct {

@@ -155,7 +155,17 @@ def tcf_central_plan(N0, N1, N2):
     return p
 
 
+def vst_plan(N0, N1):
+    """apps/viscous_shock_tube/viscous_shock_tube.py: 2-D TENO5 + StoreSome viscous terms with a constant `mu` symbol,
+    adiabatic walls on three faces and a symmetry face, ReducedAccess closures, RungeKuttaLS(3)."""
+    wall = lambda: dict(type='adiabatic_wall', closure='reduced_access')
+    return dict(ndim=2, np=[N0, N1], delta=[1.0 / (N0 - 1), 0.5 / (N1 - 1)], conv='teno', order=5, averaging='roe', viscous=True,
+                constants=dict(gama=1.4, Minf=1.0, Pr=0.73, Re=200.0, mu=1.0, dt=0.000005, eps=1e-15, TENO_CT=1e-6),
+                bc=[[wall(), wall()], [wall(), dict(type='symmetry')]], **LS3)     # SymmetryBC does not modify the derivatives
+
+
 if os.path.isdir('/root/reference'):
+    FIXTURES['vst_60x30'] = ('vst', vst_plan(60, 30), [1, 10, 200])
     FIXTURES['lam2d_16x64'] = ('lam2d', lam2d_plan(16, 64), [1, 10])
     FIXTURES['tcf_central_16x24x12'] = ('tcf_central', tcf_central_plan(16, 24, 12), [1, 5])
     FIXTURES['tcf_teno6_16x24x12'] = ('tcf_teno6', tcf_teno6_plan(16, 24, 12), [1, 5])

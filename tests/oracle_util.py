@@ -12,7 +12,7 @@ REF_DIR = os.path.join(ORACLE_DIR, '_ref')
 
 CONV = {'central': 0, 'weno': 1, 'teno': 2}
 BC = {'periodic': 0, 'dirichlet': 1, 'exchange': 2, 'isothermal_wall': 3, 'extrapolation': 4,
-      'inlet_pressure_extrapolate': 5, 'symmetry': 6, 'dirichlet_field': 7}
+      'inlet_pressure_extrapolate': 5, 'symmetry': 6, 'dirichlet_field': 7, 'adiabatic_wall': 8}
 MU = {'constant': 0, 'sutherland': 1, 'power': 2}
 CLOSURES = {
     # rows idx = 0.. next to the face x weights of the boundary-absolute points 0..np-1
@@ -84,7 +84,7 @@ def make_cfg(plan):
     k = plan['constants']
     c.gama = k['gama']
     c.Minf = k.get('Minf', 1.0)
-    c.Re = k.get('Re', 1.0)
+    c.Re = k.get('Re', 1.0) / (k.get('mu', 1.0) if plan.get('viscosity', {'type': 'constant'})['type'] == 'constant' else 1.0)
     c.Pr = k.get('Pr', 1.0)
     c.dt = k['dt']
     c.eps = k.get('eps', 1e-16)

@@ -24,6 +24,8 @@ APPS = {
     'tcf_central': (REF + '/apps/channel_flow/compressible_TCF_Central/turbulent_channel.py',
                     [("stats = True", "stats = False"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)"),
                      ("print_iteration_ops()", "")], 'tcf_central_16x24x12'),
+    'vst': (REF + '/apps/viscous_shock_tube/viscous_shock_tube.py',
+            [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)"), ("print_iteration_ops(NaN_check='rho_B0')", "")], 'vst_60x30'),
     'sod_teno5': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'sod_teno5_n200'),
 }
 
@@ -124,7 +126,7 @@ def test_initial_state_from_cold_kernel_matches_reference_init():
         assert np.abs(q0[m][s] - states[0][m]).max() <= 1e-13 * max(1.0, np.abs(states[0][m]).max())
 
 
-@pytest.mark.parametrize('name,fixture,sizes', [('lam2d', 'lam2d_16x64', (16, 64)), ('tcf_central', 'tcf_central_16x24x12', (16, 24, 12)),
+@pytest.mark.parametrize('name,fixture,sizes', [('lam2d', 'lam2d_16x64', (16, 64)), ('vst', 'vst_60x30', (60, 30)), ('tcf_central', 'tcf_central_16x24x12', (16, 24, 12)),
                                                 ('tcf_teno6', 'tcf_teno6_16x24x12', (16, 24, 12))])
 def test_channel_cold_kernels_match_reference(name, fixture, sizes):
     """Channel apps: initial condition, stretched-grid metrics and their boundary kernels evaluated by the runner from
