@@ -36,6 +36,12 @@ const char *osb_last_error(const osb_ctx *ctx);
 int osb_set_const_f64(osb_ctx *ctx, const char *name, double value);
 int osb_get_const_f64(const osb_ctx *ctx, const char *name, double *value);
 
+/* Iteration number seen by time-dependent source terms: the loop counter `iter` of the generated time loop
+ * (algorithm.py:440-474; e.g. the forcing sin(omega dt iter) of apps/transitional_SBLI/transitional_SBLI.py:77-89).
+ * Starts at the plan's iteration0 (restart_iteration_no), advances by one per completed step. */
+int osb_set_iteration(osb_ctx *ctx, long long iteration);
+long long osb_get_iteration(const osb_ctx *ctx);
+
 /* Field access; replaces ops_decl_dat(_hdf5) initial values and ops_fetch_dat_hdf5_file
  * (opsc.py:693-722, core/io_hdf5.py:99-127).  dims/halo_m/halo_p have 3 entries. */
 int osb_num_fields(const osb_ctx *ctx);

@@ -275,6 +275,76 @@ def _check_constants_used(components):
         raise UnsupportedByB200('the hot loops use constants outside the implemented canonical system: %s' % sorted(bad))
 
 
+def _dirichlet_free(kernel, ndim, q_names):
+    """Dirichlet faces that do not impose every conserved variable (transitional_SBLI.py:134-141 leaves the spanwise
+    momentum alone and adds its kinetic energy to the imposed energy): which variables are free, and whether the energy
+    equation is  E_imposed + 1/2 sum(free momentum^2)/rho  -- checked numerically."""
+    import random
+    from opensbli.core.opensbliobjects import DataSet
+    rnd = random.Random(11)
+    centre = {}
+    for e in kernel.equations:
+        if hasattr(e.lhs, 'base') and not any(int(i) != 0 for i in e.lhs.indices[:ndim]):
+            centre[_strip(e.lhs.base)] = e
+    free = [m for m, n in enumerate(q_names) if n not in centre]
+    if not free:
+        return {}
+    if any(not (1 <= m <= ndim) for m in free) or 'rhoE' not in centre:
+        raise UnsupportedByB200('Dirichlet face that leaves %s free is not implemented' % [q_names[m] for m in free])
+    ex = centre['rhoE'].rhs
+    dss = [a for a in ex.atoms(DataSet) if _strip(a.base) in q_names]
+    if not dss:
+        return {'free': free}
+    others = {s: rnd.uniform(1.0, 2.0) for s in ex.free_symbols}
+    def value(vals):
+        return float(ex.xreplace({a: vals[_strip(a.base)] for a in dss}).subs(others))
+    for _ in range(3):
+        vals = {n: rnd.uniform(1.0, 2.0) for n in q_names}
+        zero = dict(vals, **{q_names[m]: 0.0 for m in free})
+        ke = 0.5 * sum(vals[q_names[m]] ** 2 for m in free) / vals['rho']
+        if any(_strip(a.base) not in [q_names[m] for m in free] + ['rho'] for a in dss) or abs(value(vals) - value(zero) - ke) > 1e-12:
+            raise UnsupportedByB200('Dirichlet energy equation depends on the solution in a way the B200 kernels do not implement')
+    return {'free': free, 'ke_free': True}
+
+
+def _mass_source(cr, hot, ndim):
+    """Time-periodic mass source of apps/transitional_SBLI (transitional_SBLI.py:77-89): a constituent relation
+    S = f(x, constants) * sin(w * iter) that enters the continuity residual as +S.  Returns (plan entry, cold kernel that
+    evaluates f, the CR kernel) or (None, None, None)."""
+    from sympy import sin, Symbol, diff
+    from sympy.printing.c import ccode
+    from opensbli.core.opensbliobjects import DataSet
+    for k in cr:
+        for e in k.equations:
+            its = [s for s in e.rhs.free_symbols if str(s) == 'iter'] if hasattr(e, 'rhs') else []
+            if not its:
+                continue
+            it = its[0]
+            sname = _strip(e.lhs.base)
+            spatial, temporal = e.rhs.as_independent(it, as_Add=False)
+            if len(k.equations) != 1 or temporal.func != sin or (temporal.args[0] / it).has(it):
+                raise UnsupportedByB200('time-dependent constituent relation %s is not of the form f(x) sin(w iter)' % sname)
+            rate = temporal.args[0] / it
+            uses = 0
+            for h in hot:
+                for he in h.equations:
+                    if not hasattr(he, 'rhs'):
+                        continue
+                    ds = [a for a in he.rhs.atoms(DataSet) if _strip(a.base) == sname]
+                    if not ds:
+                        continue
+                    lhs = _strip(he.lhs.base) if hasattr(he.lhs, 'base') else str(he.lhs)
+                    if lhs != 'Residual0' or len(ds) != 1 or any(int(i) != 0 for i in ds[0].indices[:ndim]) or diff(he.rhs, ds[0]) != 1:
+                        raise UnsupportedByB200('source term %s enters %s in a form the B200 kernels do not implement' % (sname, lhs))
+                    uses += 1
+            if uses != 1:
+                raise UnsupportedByB200('source term %s is not added to the continuity residual exactly once' % sname)
+            cold = {'name': 'Mass source amplitude', 'range': [ccode(r) for r in k.total_range()],
+                    'statements': [['BF_amp', [0] * ndim, _Printer()(spatial)]]}
+            return {'field': 'BF_amp', 'rate': ccode(rate)}, cold, k
+    return None, None, None
+
+
 def _check_forcing(kernels, ndim):
     """Constant body force of the channel apps (turbulent_channel.py:15-16): momentum_i gets -c_i, the energy equation
     -c_j u_j.  Verified on the residual equations: d Residual_i / d c_i = -1 and d Residual_E / d c_j = -u_j."""
@@ -563,7 +633,10 @@ def extract_plan(algorithm):
             unknown.append(c)
     if unknown:
         raise UnsupportedByB200('loops outside the accelerated hot path: %s' % sorted(set(_name(c) for c in unknown)))
-    _check_constants_used(in_stage + in_iter)
+    mass_source, source_cold, source_kernel = _mass_source(cr, [c for c in in_stage if type(c).__name__ == 'Kernel' and c not in cr], ndim)
+    if source_kernel is not None:
+        cr.remove(source_kernel)
+    _check_constants_used([c for c in in_stage + in_iter if c is not source_kernel])
     crinfo = _check_constituent(cr, ndim)
     plan['viscosity'] = crinfo['viscosity']
     if recon and central_conv:
@@ -629,6 +702,7 @@ def extract_plan(algorithm):
         if kind == 'Dirichlet':
             # imposed state = whatever the BC equations evaluate to on the face (constants or functions of the position)
             entry = {'type': 'dirichlet_field', 'kernel': _cold_kernel(c)}
+            entry.update(_dirichlet_free(c, ndim, q_names))
         elif kind == 'Extrapolation':
             # order 0 copies one interior value into boundary + halos; order 1 extrapolates linearly (extrapolation.py:37-55)
             lin = any(e.rhs.is_Add for e in c.equations if hasattr(e, 'rhs'))
@@ -665,6 +739,11 @@ def extract_plan(algorithm):
             if not (n.startswith('Grid_based_initialisation') or n.startswith('MetricsEquation') or n.startswith('Metric boundary')):
                 raise UnsupportedByB200('cold kernel %s is not implemented yet' % n)
             cold.append(_cold_kernel(c))
+    if mass_source:
+        if not viscous:
+            raise UnsupportedByB200('mass source without viscous terms is not implemented')
+        cold.append(source_cold)
+        plan['mass_source'] = mass_source
     plan['cold'] = cold
     plan['q_names'] = q_names
 

@@ -30,6 +30,7 @@ struct BcSpec {
   int kind = BC_PERIODIC;
   double q[5] = {0, 0, 0, 0, 0};
   int order = 0;            // extrapolation order
+  int free_mask = 0;        // dirichlet_field: variables left free (bit m) / kinetic energy of the free momenta added to the energy (bit 8)
   bool closure = false;     // central derivatives use the one-sided closure next to this face
 };
 
@@ -52,6 +53,9 @@ struct Plan {
   bool teno_adaptive = false;
   bool forcing = false;
   int central_form = 0;      // 0 Blaisdell skew form, 1 Feiereisen quadratic split
+  bool mass_source = false;  // Residual_rho += BF_amp(x) sin(src_rate * iteration)
+  double src_rate = 0.0;
+  long long iteration0 = 0;
   Closures cl{};
 };
 
@@ -93,6 +97,7 @@ struct osb_ctx {
   cudaGraphExec_t step_graph = nullptr;
   long long graph_launches = 0;
   bool use_graph = true;
+  long long iteration = 0;                      // loop counter of algorithm.py:440-474 (argument of the mass source)
   int swap_parity = 0;                          // fused central path: q and Residual buffers exchange roles every stage
 };
 
@@ -148,7 +153,12 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
       else if (kind == "symmetry") b.kind = BC_SYMMETRY;
       else { err = "unsupported boundary condition '" + kind + "'"; return false; }
       std::string tok;
-      if (ls >> tok) { if (tok == "closure") b.closure = true; else { err = "bad bc line: " + line; return false; } }
+      while (ls >> tok) {
+        if (tok == "closure") b.closure = true;
+        else if (tok == "free") { int m; if (!(ls >> m) || m < 0 || m > 4) { err = "bad bc line: " + line; return false; } b.free_mask |= 1 << m; }
+        else if (tok == "ke_free") b.free_mask |= 256;
+        else { err = "bad bc line: " + line; return false; }
+      }
     }
     else if (key == "viscosity") {
       std::string v; ls >> v;
@@ -158,6 +168,7 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
     else if (key == "metric") { int d2, on; ls >> d2 >> on; if (d2 < 0 || d2 > 2) { err = "bad metric line"; return false; } P.metric[d2] = on != 0; }
     else if (key == "teno_adaptive") { int v; ls >> v; P.teno_adaptive = v != 0; }
     else if (key == "forcing") { int v; ls >> v; P.forcing = v != 0; }
+    else if (key == "mass_source") { ls >> P.src_rate >> P.iteration0; P.mass_source = true; }
     else if (key == "central_form") { std::string v; ls >> v; P.central_form = v == "blaisdell" ? 0 : v == "feiereisen" ? 1 : -1; if (P.central_form < 0) { err = "unknown central_form " + v; return false; } }
     else if (key == "closure_d1" || key == "closure_d2") {
       int nr, np; ls >> nr >> np;
@@ -207,6 +218,7 @@ void refresh_constants(osb_ctx *c) {
   c->pc.visc_law = P.visc_law; c->pc.mu_exp = P.mu_exp;
   c->pc.SuthT = get("SuthT", 0.0); c->pc.RefT = get("RefT", 1.0); c->pc.Twall = get("Twall", 1.0);
   c->pc.sensor_eps = get("epsilon", 1e-12);
+  c->pc.src_factor = P.mass_source ? sin(P.src_rate * (double)c->iteration) : 0.0;
   for (int d = 0; d < 3; d++) c->pc.force[d] = P.forcing ? get(("c" + std::to_string(d)).c_str(), 0.0) : 0.0;
 }
 
@@ -439,7 +451,7 @@ void launch_bcs(osb_ctx *c) {
         const unsigned nb = (unsigned)((cnt + 127) / 128);
         Launcher L(c, OSB_FAM_BC);
         switch (b.kind) {
-          case BC_DIRICHLET_FIELD: k_bc_dirichlet_field<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps, c->face_table[d][s], c->face_size[d]); break;
+          case BC_DIRICHLET_FIELD: k_bc_dirichlet_field<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps, c->face_table[d][s], c->face_size[d], b.free_mask); break;
           case BC_EXTRAPOLATION: k_bc_extrapolation<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps, b.order); break;
           case BC_SYMMETRY: k_bc_symmetry<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps); break;
           case BC_INLET_PRESSURE:
@@ -527,6 +539,8 @@ void launch_central_fused(osb_ctx *c, int stage) {
 template <int ND>
 int stage_nd(osb_ctx *c, int s) {
   const bool ex = has_exchange(c);
+  if (c->plan.mass_source && s <= 0) c->pc.src_factor = sin(c->plan.src_rate * (double)c->iteration);
+  struct StepCounter { osb_ctx *c; int s; ~StepCounter() { if (s == (int)c->plan.rk_a.size() - 1) c->iteration++; } } counter{c, s};
   if (ND == 3 && fused_central_ok(c)) {
     if (s >= 0) launch_central_fused(c, s);
     launch_bcs(c);
@@ -589,7 +603,7 @@ void drop_graph(osb_ctx *c) {
 // kernels carry a new epoch number every stage).
 int do_step(osb_ctx *c, int nsteps) {
   const long long pts = (long long)c->grid.np[0] * c->grid.np[1] * c->grid.np[2];
-  if (!c->use_graph || c->profiling || has_exchange(c) || pts > (1LL << 22) || nsteps < 2) return step_dispatch(c, nsteps);
+  if (!c->use_graph || c->profiling || c->plan.mass_source || has_exchange(c) || pts > (1LL << 22) || nsteps < 2) return step_dispatch(c, nsteps);
   // the fused central path exchanges buffer roles every stage: the captured unit must bring them back (two steps if the
   // number of stages is odd) and may only be replayed from the parity it was captured at (0)
   const int unit = (fused_central_ok(c) && (c->plan.rk_a.size() % 2)) ? 2 : 1;
@@ -671,7 +685,9 @@ int osb_create(const char *plan_text, int device, osb_ctx **out) {
   for (int m = 0; m < nv && ok; m++) ok = add("Residual" + std::to_string(m), &c->fp.R[m]);
   for (int m = 0; m < nv && ok; m++) ok = add(P.rk == RK_LS ? "tempRK_" + qn[m] : qn[m] + "_RKold", &c->fp.rk[m]);
   // general path: metric fields (uploaded by the caller), viscosity, sensor
-  c->general = P.visc_law != 0 || P.forcing;
+  c->general = P.visc_law != 0 || P.forcing || P.mass_source;
+  c->iteration = P.iteration0;
+  if (P.mass_source && !P.viscous) { g_create_error = "mass_source is implemented on the viscous general path only"; osb_destroy(c); return 1; }
   for (int d = 0; d < P.nd; d++) {
     if (P.metric[d] || P.bc[d][0].closure || P.bc[d][1].closure) c->general = true;
     if (P.metric[d] && ok) {
@@ -682,6 +698,7 @@ int osb_create(const char *plan_text, int device, osb_ctx **out) {
     }
   }
   if (ok && (c->general || P.visc_law != 0)) ok = add("mu", &c->gp.mu);
+  if (ok && P.mass_source) { double *ps = nullptr; ok = add("BF_amp", &ps); c->gp.src = ps; }
   if (ok && P.teno_adaptive) ok = add("theta", &c->gp.theta) && add("TENO", &c->gp.teno_store);
   if (P.teno_adaptive && P.nd < 2) { g_create_error = "adaptive TENO needs at least 2 dimensions (vorticity)"; osb_destroy(c); return 1; }
   for (int d = 0; d < P.nd && ok; d++) {
@@ -727,6 +744,13 @@ int osb_set_const_f64(osb_ctx *c, const char *name, double v) {
   drop_graph(c);          // constants are baked into the captured kernel arguments
   return 0;
 }
+int osb_set_iteration(osb_ctx *c, long long iteration) {
+  if (!c || iteration < 0) return 1;
+  c->iteration = iteration;
+  refresh_constants(c);
+  return 0;
+}
+long long osb_get_iteration(const osb_ctx *c) { return c ? c->iteration : -1; }
 int osb_get_const_f64(const osb_ctx *c, const char *name, double *v) {
   if (!c || !name || !v) return 1;
   auto it = c->plan.consts.find(name);

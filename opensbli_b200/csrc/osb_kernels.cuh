@@ -39,6 +39,7 @@ struct PhysConst {
   int visc_law;             // 0 constant, 1 Sutherland, 2 power law
   double SuthT, RefT, mu_exp, Twall, sensor_eps;
   double force[3];          // constant body force c_j (channel apps): momentum_i -= c_i, energy -= c_j u_j
+  double src_factor;        // sin(src_rate * iteration) of the mass source, refreshed by the host every step
 };
 
 // one-sided closure tables (reduced_access_scheme.py:36-83, Carpenter_scheme.py:38-102): rows idx = 0..nr-1 next to
@@ -53,6 +54,7 @@ struct GeneralPtrs {
   const double *D[3];       // D_dd metric (nullptr: direction not stretched)
   const double *SD[3];      // SD_ddd
   double *mu, *theta, *teno_store;
+  const double *src;        // mass-source amplitude (nullptr: none)
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -1028,6 +1030,7 @@ __global__ void __launch_bounds__(256) k_viscous_general(GridDev g, FieldPtrs f,
   double old[ND + 1];
 #pragma unroll
   for (int a = 0; a < ND + 1; a++) old[a] = f.R[1 + a][x];
+  if (gp.src) f.R[0][x] += gp.src[x] * c.src_factor;      // time-periodic mass source (transitional_SBLI.py:77-89)
 #pragma unroll
   for (int a = 0; a < ND; a++) f.R[1 + a][x] = old[a] + vis[a];
   f.R[ND + 1][x] = old[ND] + (kq * hT + e);
@@ -1162,13 +1165,24 @@ __device__ __forceinline__ bool plane_point(const GridDev &g, const PlaneSpec &p
 }
 
 // dirichlet.py:28-41 with a state that varies along the face: table[m * tsize + tlin]
-__global__ void __launch_bounds__(128) k_bc_dirichlet_field(GridDev g, FieldPtrs f, int nv, PlaneSpec ps, const double *table, long long tsize) {
+// free: bit m = variable m keeps its value; bit 8 = imposed energy is table + 1/2 sum(free momentum^2)/rho (transitional_SBLI.py:134-139)
+__global__ void __launch_bounds__(128) k_bc_dirichlet_field(GridDev g, FieldPtrs f, int nv, PlaneSpec ps, const double *table, long long tsize, int free_mask) {
   long long x, t;
   if (!plane_point(g, ps, x, t)) return;
   const long long out = (ps.side == 0 ? -1 : 1) * g.s[ps.dir];
   for (int m = 0; m < nv; m++) {
+    if (free_mask >> m & 1) continue;
     const double v = table[m * tsize + t];
     for (int h = 0; h <= ps.nh; h++) f.q[m][x + h * out] = v;
+  }
+  if (free_mask >> 8 & 1) {
+    const double e = table[(nv - 1) * tsize + t];
+    for (int h = 0; h <= ps.nh; h++) {
+      const long long xo = x + h * out;
+      double ke = 0.0;
+      for (int m = 1; m < nv - 1; m++) if (free_mask >> m & 1) { const double v = f.q[m][xo]; ke += v * v; }
+      f.q[nv - 1][xo] = e + 0.5 * ke / f.q[0][xo];
+    }
   }
 }
 // extrapolation.py:29-58

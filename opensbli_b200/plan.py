@@ -26,6 +26,10 @@ JSON-able dict; `to_text` serialises it to the line format parsed by the C ABI (
                     (constant: an optional constant 'mu' scales 1/Re, e.g. viscous_shock_tube.py:14-16)
     metric_fields   per direction None | 'D11'...: stretched direction; fields['D11'], fields['SD111'] hold the metric arrays
     teno_adaptive   bool: C_T from the Ducros sensor (constants teno_a1, teno_a2, epsilon)
+    mass_source     {'field': name, 'rate': w}: Residual_rho += fields[name] * sin(w * iteration)  (transitional_SBLI.py:77-89);
+                    iteration0: iteration number of the first step (restart)
+                    dirichlet_field faces may carry 'free': [m, ...] (variables left untouched) and 'ke_free': True (imposed
+                    energy = table + 1/2 sum(free momentum^2)/rho)
     forcing         bool: constant body force c0, c1, c2 (constants): momentum_i -= c_i, energy -= c_j u_j
     central_form    'blaisdell' (default; Skew() split of taylor_green_vortex / laminar_2D) | 'feiereisen' (quadratic split of
                     compressible_TCF_Central / turbulent_3D): how Central(4) writes the convective terms
@@ -116,6 +120,9 @@ def to_text(plan):
                 L.append('bc %d %d dirichlet %s%s' % (d, s, ' '.join(_f(v) for v in b['q']), cl))
             elif b['type'] == 'extrapolation':
                 L.append('bc %d %d extrapolation %d%s' % (d, s, int(b.get('order', 0)), cl))
+            elif b['type'] == 'dirichlet_field':
+                fr = ''.join(' free %d' % m for m in b.get('free', [])) + (' ke_free' if b.get('ke_free') else '')
+                L.append('bc %d %d dirichlet_field%s%s' % (d, s, cl, fr))
             else:
                 L.append('bc %d %d %s%s' % (d, s, b['type'], cl))
     if len(closures) > 1:
@@ -136,6 +143,8 @@ def to_text(plan):
         L.append('teno_adaptive 1')
     if plan.get('forcing'):
         L.append('forcing 1')
+    if plan.get('mass_source'):
+        L.append('mass_source %s %d' % (_f(plan['mass_source']['rate']), int(plan.get('iteration0', 0))))
     if plan.get('central_form', 'blaisdell') != 'blaisdell':
         if plan['central_form'] != 'feiereisen':
             raise PlanError("central_form must be 'blaisdell' or 'feiereisen'")

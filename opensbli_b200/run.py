@@ -118,7 +118,7 @@ def resolve(plan_sym, env):
     metric fields, tabulated Dirichlet states); returns (plan, ColdRunner holding every cold dataset)."""
     nd = plan_sym['ndim']
     p = {k: plan_sym[k] for k in ('ndim', 'conv', 'order', 'weno_formulation', 'averaging', 'viscous', 'rk', 'rk_a', 'rk_b')}
-    for k in ('viscosity', 'metric_fields', 'teno_adaptive', 'closures', 'forcing', 'central_form'):
+    for k in ('viscosity', 'metric_fields', 'teno_adaptive', 'closures', 'forcing', 'central_form'):   # copied verbatim
         if k in plan_sym:
             p[k] = plan_sym[k]
     p['np'] = [int(env['block0np%d' % d]) for d in range(nd)]
@@ -133,6 +133,10 @@ def resolve(plan_sym, env):
         if name:
             for f in (name, 'S' + name + str(d)):
                 p['fields'][f] = cold.array(f).copy()
+    if plan_sym.get('mass_source'):
+        ms = plan_sym['mass_source']
+        p['mass_source'] = {'field': ms['field'], 'rate': float(c_eval(ms['rate'], env))}
+        p['fields'][ms['field']] = cold.array(ms['field']).copy()
     bc = []
     for d in range(nd):
         pair = []
@@ -142,6 +146,8 @@ def resolve(plan_sym, env):
                 # evaluate the BC equations on a scratch copy of the datasets, read the imposed state off the boundary plane
                 scratch = ColdRunner(nd, p['np'], env)
                 scratch.arrays = {k: v.copy() for k, v in cold.arrays.items()}
+                for m in b.get('free', []):                   # the kinetic energy of the free momenta is added at run time
+                    scratch.array(plan_sym['q_names'][m])[...] = 0.0
                 scratch.run(b.pop('kernel'))
                 plane = p['np'][d] - 1 + scratch.h if s == 1 else scratch.h
                 tabs = []

@@ -14,7 +14,7 @@ _lib = None
 
 FAMILIES = ('prim', 'flux', 'central', 'viscous', 'rk', 'bc', 'sync')
 
-SYMBOLS = ('osb_create', 'osb_destroy', 'osb_last_error', 'osb_set_const_f64', 'osb_get_const_f64',
+SYMBOLS = ('osb_create', 'osb_destroy', 'osb_last_error', 'osb_set_const_f64', 'osb_get_const_f64', 'osb_set_iteration', 'osb_get_iteration',
            'osb_num_fields', 'osb_field_name', 'osb_field_info', 'osb_upload', 'osb_download', 'osb_device_ptr', 'osb_upload_face',
            'osb_step', 'osb_step_begin', 'osb_stage', 'osb_sync', 'osb_apply_bcs', 'osb_residual', 'osb_step_timed', 'osb_timer_start', 'osb_timer_stop', 'osb_advance_host',
            'osb_launch_count', 'osb_profile_step', 'osb_ipc_export', 'osb_ipc_import', 'osb_halo_push',
@@ -43,6 +43,9 @@ def load_library(path=None):
     lib.osb_destroy.argtypes = [ctypes.c_void_p]
     lib.osb_set_const_f64.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_double]
     lib.osb_get_const_f64.argtypes = [ctypes.c_void_p, ctypes.c_char_p, _P]
+    lib.osb_set_iteration.argtypes = [ctypes.c_void_p, ctypes.c_longlong]
+    lib.osb_get_iteration.argtypes = [ctypes.c_void_p]
+    lib.osb_get_iteration.restype = ctypes.c_longlong
     lib.osb_num_fields.argtypes = [ctypes.c_void_p]
     lib.osb_field_info.argtypes = [ctypes.c_void_p, ctypes.c_char_p] + [ctypes.POINTER(ctypes.c_int)] * 3
     lib.osb_upload.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
@@ -161,6 +164,13 @@ class Simulation(object):
 
     def set_const(self, name, value):
         self._check(self.lib.osb_set_const_f64(self.ctx, name.encode(), float(value)), 'osb_set_const_f64')
+
+    def set_iteration(self, iteration):
+        """iteration number seen by time-dependent source terms (restart)"""
+        self._check(self.lib.osb_set_iteration(self.ctx, int(iteration)), 'osb_set_iteration')
+
+    def get_iteration(self):
+        return int(self.lib.osb_get_iteration(self.ctx))
 
     # -- the time loop
     def step(self, nsteps=1, sync=True):

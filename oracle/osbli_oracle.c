@@ -102,8 +102,16 @@ static void bc_dirichlet_field(const osbo_cfg *c, const grid_t *g, double *const
     int id[3] = {i, j, k};
     long t = 0;
     for (int d = 0; d < g->ndim; d++) if (d != dir) t += ts[d] * (id[d] + g->h);
-    for (int m = 0; m < g->nv; m++)
-      for (int h = 0; h <= n; h++) q[m][x + (side == 0 ? -h : h) * sd] = tab[m * acc + t];
+    const int fr = c->bc_free[dir][side];
+    for (int h = 0; h <= n; h++) {
+      const long xo = x + (side == 0 ? -h : h) * sd;
+      for (int m = 0; m < g->nv; m++) if (!(fr >> m & 1)) q[m][xo] = tab[m * acc + t];
+      if (fr >> 8 & 1) {
+        double ke = 0.0;
+        for (int m = 1; m <= g->ndim; m++) if (fr >> m & 1) ke += q[m][xo] * q[m][xo];
+        q[g->nv - 1][xo] = tab[(g->nv - 1) * acc + t] + 0.5 * ke / q[0][xo];
+      }
+    }
   })
 }
 /* extrapolation.py:29-58 */
@@ -678,6 +686,7 @@ static void central_general(const osbo_cfg *c, const grid_t *g, double *const *q
 /* ---------------------------------------------------------------------------------------------
  * Spatial residual = what the stage's "spatial kernels" leave in Residual_m
  * ------------------------------------------------------------------------------------------- */
+static int g_src_iter = -1;   /* iteration number seen by the mass source; -1: use c->src_iter0 */
 void osbo_residual(const osbo_cfg *c, double *const *q, double *const *R) {
   grid_t g; grid_init(c, &g);
   const int nd = g.ndim, nv = g.nv;
@@ -755,6 +764,13 @@ void osbo_residual(const osbo_cfg *c, double *const *q, double *const *R) {
     }
   }
 
+  if (c->src_amp) {
+    const double fac = sin(c->src_rate * (g_src_iter < 0 ? c->src_iter0 : g_src_iter));
+    for (int k = 0; k < g.np[2]; k++) for (int j = 0; j < g.np[1]; j++) for (int i = 0; i < g.np[0]; i++) {
+      long x = gidx(&g, i, j, k);
+      R[0][x] += c->src_amp[x] * fac;
+    }
+  }
   if (c->viscous && general) viscous_general(c, &g, &P, R, dv, inv, inv2);
   if (c->viscous && !general) {
     /* Stored first derivatives d(u_v)/dx_d, d(T)/dx_d over ranges widened by +-2 in the other directions
@@ -858,6 +874,7 @@ int osbo_advance(const osbo_cfg *c, double *const *q, double *const *rk_reg, int
   if (!Rbuf) return 1;
   double *R[5]; for (int m = 0; m < nv; m++) R[m] = Rbuf + (size_t)m * g.n;
   for (int it = 0; it < nsteps; it++) {
+    g_src_iter = c->src_iter0 + it;
     osbo_apply_bcs(c, q);
     if (c->rk == OSBO_RK_SBLI)
       for (int m = 0; m < nv; m++)
@@ -880,6 +897,7 @@ int osbo_advance(const osbo_cfg *c, double *const *q, double *const *rk_reg, int
       osbo_apply_bcs(c, q);
     }
   }
+  g_src_iter = -1;
   free(Rbuf);
   return 0;
 }

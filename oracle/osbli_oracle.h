@@ -74,6 +74,13 @@ typedef struct {
   int extrap_order[3][2];
   const double *bc_face[3][2];/* OSBO_BC_DIRICHLET_FIELD: [nv][padded tangential extent] */
   double force[3];            /* constant body force c_j: momentum_i -= c_i, energy -= c_j u_j (turbulent_channel.py:15-16) */
+  int bc_free[3][2];          /* OSBO_BC_DIRICHLET_FIELD: bit m set = conserved variable m is NOT imposed on this face; bit 8 set = the
+                               * imposed energy is the table value + 1/2 sum(free momentum^2)/rho (transitional_SBLI.py:134-139) */
+  /* time-periodic mass source of apps/transitional_SBLI (transitional_SBLI.py:77-89): Residual_rho += src_amp(x) sin(src_rate * iter),
+   * iter = src_iter0 + number of completed steps (the loop counter of algorithm.py:440-474) */
+  const double *src_amp;      /* padded array or NULL */
+  double src_rate;
+  int src_iter0;
   int central_form;           /* Central(4) convective split: 0 Blaisdell skew form (taylor_green_vortex.py:8-11, laminar_channel.py:7-9),
                                * 1 Feiereisen quadratic split (compressible_TCF_Central/turbulent_channel.py:12-20) */
 } osbo_cfg;

@@ -164,7 +164,41 @@ def vst_plan(N0, N1):
                 bc=[[wall(), wall()], [wall(), dict(type='symmetry')]], **LS3)     # SymmetryBC does not modify the derivatives
 
 
+def trans_plan(N0, N1, N2):
+    """apps/transitional_SBLI/transitional_SBLI.py (statistics off): Katzer's set-up in 3-D -- TENO6 adaptive, wall-normal
+    stretching, Sutherland viscosity, ReducedAccess closures, inlet / outlet / isothermal wall / shock-generator Dirichlet
+    top (spanwise momentum left free, its kinetic energy added to the imposed energy) / periodic span -- plus the
+    time-periodic mass source A exp(-(x-xF)^2-(y-yF)^2) cos(bta z) sin(omega dt iter) in the continuity equation."""
+    ra = 'reduced_access'
+    return dict(ndim=3, np=[N0, N1, N2], delta=[375.0 / (N0 - 1), 140.0 / (N1 - 1), 27.32 / N2], conv='teno', order=6, averaging='roe',
+                viscous=True, viscosity=dict(type='sutherland'), teno_adaptive=True, metric_fields=[None, 'D11', None],
+                mass_source=dict(field='BF_amp', rate=0.025 * 0.1011),
+                constants=dict(gama=1.4, Minf=1.5, Pr=0.72, Re=750.0, Twall=1.3809973268575328, dt=0.025, SuthT=110.4, RefT=202.17,
+                               eps=1e-30, TENO_CT=1e-5, teno_a1=9.5, teno_a2=3.5, epsilon=1e-12),
+                bc=[[dict(type='inlet_pressure_extrapolate', closure=ra), dict(type='extrapolation', order=0, closure=ra)],
+                    [dict(type='isothermal_wall', closure=ra), dict(type='dirichlet_field', closure=ra, free=[3], ke_free=True)],
+                    [dict(type='periodic'), dict(type='periodic')]], **LS3)
+
+
+def trans_dirichlet_table(x0_padded):
+    """transitional_SBLI.py:127-139: pre / post oblique-shock states switched at x0 = 20, printed with %.15f by the app."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), 'oracle'))
+    import refshim
+    refshim.install()
+    from opensbli.utilities.oblique_shock import ShockConditions
+    g, M = 1.4, 1.5
+    pre = (1.0, 1.0, 0.00466654053208844, (1.0 / (g * M ** 2)) / (g - 1.0) + 0.5 * (1.0 * 1.0 ** 2 + 0.00466654053208844 ** 2))
+    post = ShockConditions(44.6607551, M, g).conservative_post_shock_conditions(1.0)
+    r = lambda v: float('%.15f' % float(v))
+    x = np.moveaxis(x0_padded, 1, 0)[5].reshape(-1)        # tangential plane (z, x) at an interior j, x fastest (x0 does not depend on j)
+    rows = [np.where(x > 20.0, r(post[m]), r(pre[m])) for m in range(3)]
+    rows.append(np.zeros_like(x))                           # rhou2 is not imposed
+    rows.append(np.where(x > 20.0, r(post[3]), r(pre[3])))
+    return np.stack(rows)
+
+
 if os.path.isdir('/root/reference'):
+    FIXTURES['trans_40x30x8'] = ('trans', trans_plan(40, 30, 8), [1, 5, 20])
     FIXTURES['vst_60x30'] = ('vst', vst_plan(60, 30), [1, 10, 200])
     FIXTURES['lam2d_16x64'] = ('lam2d', lam2d_plan(16, 64), [1, 10])
     FIXTURES['tcf_central_16x24x12'] = ('tcf_central', tcf_central_plan(16, 24, 12), [1, 5])
@@ -203,6 +237,10 @@ def main():
                 out['field_' + n] = r[n]
             if config.startswith('katzer'):
                 out['bc_table_1_1'] = katzer_dirichlet_table(plan['np'][0])
+            if config == 'trans':
+                rx = run_ref(config, dict(env_params(plan), niter=0), ['x0', 'x1', 'x2'], dump_all=True)
+                out['bc_table_1_1'] = trans_dirichlet_table(rx['x0'])
+                out['field_BF_amp'] = 2.5e-3 * np.exp(-(rx['x0'] - 20.0) ** 2 - (rx['x1'] - 4.0) ** 2) * np.cos(0.23 * rx['x2'])
         out['q0'] = np.stack([r[f][inner] for f in fields])
         for n in steps:
             r = run_ref(config, dict(env_params(plan), niter=n), fields)

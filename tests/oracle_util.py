@@ -41,7 +41,8 @@ class OsboCfg(ctypes.Structure):
                 ('sensor_eps', ctypes.c_double), ('theta', ctypes.POINTER(ctypes.c_double)),
                 ('teno_store', ctypes.POINTER(ctypes.c_double)), ('Twall', ctypes.c_double),
                 ('extrap_order', (ctypes.c_int * 2) * 3), ('bc_face', (ctypes.POINTER(ctypes.c_double) * 2) * 3),
-                ('force', ctypes.c_double * 3), ('central_form', ctypes.c_int)]
+                ('force', ctypes.c_double * 3), ('bc_free', (ctypes.c_int * 2) * 3), ('src_amp', ctypes.POINTER(ctypes.c_double)), ('src_rate', ctypes.c_double),
+                ('src_iter0', ctypes.c_int), ('central_form', ctypes.c_int)]
 
 
 _lib = None
@@ -100,6 +101,7 @@ def make_cfg(plan):
                 a = np.ascontiguousarray(b['table'], dtype=np.float64)
                 keep.append(a)
                 c.bc_face[d][s] = a.ctypes.data_as(P)
+                c.bc_free[d][s] = sum(1 << m for m in b.get('free', [])) | (256 if b.get('ke_free') else 0)
             if b['type'] == 'extrapolation':
                 c.extrap_order[d][s] = int(b.get('order', 0))
             if b.get('closure'):
@@ -128,6 +130,12 @@ def make_cfg(plan):
                 assert a.shape == shape
                 keep.append(a)
                 arr[d] = a.ctypes.data_as(P)
+    ms = plan.get('mass_source')
+    if ms:
+        a = np.ascontiguousarray(plan['fields'][ms['field']], dtype=np.float64)
+        assert a.shape == shape
+        keep.append(a)
+        c.src_amp, c.src_rate, c.src_iter0 = a.ctypes.data_as(P), ms['rate'], int(plan.get('iteration0', 0))
     ad = plan.get('teno_adaptive')
     if ad:
         c.teno_adaptive = 1

@@ -26,12 +26,14 @@ APPS = {
                      ("print_iteration_ops()", "")], 'tcf_central_16x24x12'),
     'vst': (REF + '/apps/viscous_shock_tube/viscous_shock_tube.py',
             [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)"), ("print_iteration_ops(NaN_check='rho_B0')", "")], 'vst_60x30'),
+    'trans': (REF + '/apps/transitional_SBLI/transitional_SBLI.py',
+              [("stats = True", "stats = False"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'trans_40x30x8'),
     'sod_teno5': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'sod_teno5_n200'),
 }
 
 DRIVER = r'''
 import sys, os
-sys.path.insert(0, %(oracle)r); sys.path.insert(0, %(repo)r)
+sys.path.insert(0, %(oracle)r); sys.path.insert(0, %(repo)r); sys.path.insert(0, os.path.dirname(%(app)r))   # apps import their neighbours
 import refshim; refshim.install(%(ref)r)
 os.environ['OSBLI_BACKEND'] = 'b200'
 src = open(%(app)r).read()
@@ -69,6 +71,7 @@ def comparable(plan):
     p['teno_adaptive'] = bool(plan.get('teno_adaptive'))
     p['metric_fields'] = plan.get('metric_fields') or [None] * plan['ndim']
     p['forcing'] = bool(plan.get('forcing'))
+    p['mass_source'] = plan.get('mass_source')
     p['central_form'] = plan.get('central_form', 'blaisdell') if plan['conv'] == 'central' else None
     if plan['conv'] == 'weno':
         p['weno_formulation'] = plan.get('weno_formulation', 'JS')
@@ -149,6 +152,31 @@ def test_channel_cold_kernels_match_reference(name, fixture, sizes):
     # copies them into the periodic halos, which nothing reads)
     for f, a in want.get('fields', {}).items():
         assert np.abs(plan_num['fields'][f][s] - a[s]).max() <= 1e-11 * np.abs(a).max(), f
+
+
+def test_transitional_sbli_cold_data_match_reference():
+    """apps/transitional_SBLI: mass-source amplitude, metrics, shock-generator table (imposed variables, used range) and the
+    polynomial boundary-layer initial condition evaluated by the runner == the reference's own cold kernels (golden)."""
+    import numpy as np
+    from opensbli_b200 import run as R
+    workdir = os.path.join(PLANS, 'trans')
+    if not os.path.exists(os.path.join(workdir, 'opensbli.cpp')):
+        pytest.skip('plan fixture missing')
+    plan_sym, env, plan, cold = R.load_case(workdir, overrides={'block0np0': 40, 'block0np1': 30, 'block0np2': 8})
+    want, states = load_fixture('trans_40x30x8')
+    s = (slice(5, -5),) * 3
+    assert plan['mass_source'] == want['mass_source']
+    for f in ('BF_amp', 'D11', 'SD111'):
+        assert np.abs(plan['fields'][f][s] - want['fields'][f][s]).max() <= 1e-12 * np.abs(want['fields'][f]).max(), f
+    top = plan['bc'][1][1]
+    assert top['free'] == [3] and top['ke_free'] and top['closure'] == 'reduced_access'
+    used = np.zeros((8 + 10, 40 + 10), bool)
+    used[2:-1, 2:-1] = True                                   # the BC kernel's tangential range [-3, np + 4)
+    for m in (0, 1, 2, 4):
+        assert np.abs(top['table'][m].reshape(18, 50)[used] - want['bc'][1][1]['table'][m].reshape(18, 50)[used]).max() <= 1e-15
+    q0 = R.initial_state(plan_sym, cold)
+    for m in range(5):
+        assert np.abs(q0[m][s] - states[0][m]).max() <= 1e-9      # degree-50 polynomial fit: ill-conditioned (see Katzer)
 
 
 def test_sod_initial_state_and_dirichlet_states():

@@ -100,3 +100,20 @@ def test_channel_apps_from_plan_fixture(name, fixture, sizes, nsteps):
         q = sim.get_state()
     err = field_errors(plan, inner(plan, q), states[nsteps])
     assert max(err) < 1e-12 * min(nsteps, 20), err
+
+
+def test_transitional_sbli_app_from_plan_fixture():
+    """apps/transitional_SBLI/transitional_SBLI.py through `B200(alg)` (statistics off): 3-D adaptive TENO6, stretched grid,
+    Sutherland viscosity, inlet / outlet / isothermal wall / partial Dirichlet top, time-periodic mass source; cold kernels by
+    the runner, 20 steps on a 40x30x8 grid on the GPU against the oracle started from the same cold data."""
+    from opensbli_b200 import run as R, Simulation
+    plan_sym, env, plan, cold = R.load_case(os.path.join(PLANS, 'trans'), overrides={'block0np0': 40, 'block0np1': 30, 'block0np2': 8})
+    q0 = R.initial_state(plan_sym, cold)
+    with Simulation(plan) as sim:
+        sim.set_state(q0)
+        sim.step(20)
+        assert sim.get_iteration() == 20
+        q = sim.get_state()
+    qo, _ = ou.oracle_advance(plan, [a.copy() for a in q0], 20)
+    err = field_errors(plan, inner(plan, q), inner(plan, qo))
+    assert max(err) < 1e-11, err
