@@ -35,7 +35,7 @@ class UnsupportedByB200(NotImplementedError):
 
 def _walk(components, out, path=()):
     for c in components:
-        if hasattr(c, 'components'):
+        if hasattr(c, 'components') and type(c).__name__ not in ('SimulationMonitor',):
             _walk(c.components, out, path + (c,))
         else:
             out.append((path, c))
@@ -607,6 +607,10 @@ def extract_plan(algorithm):
         if nloops == 0 and 'Timers' in loops:
             after.append(c)
     plan = {'ndim': ndim, 'viscous': False, 'averaging': 'roe', 'weno_formulation': 'JS'}
+    # components of the program that are not part of the per-step hot path (file output, monitors, timers): not executed
+    # by the B200 run-time; listed in the plan and printed so that nothing is dropped silently
+    plan['not_executed'] = sorted(set(type(c).__name__ for c in in_iter + after + before
+                                      if type(c).__name__ not in ('Kernel', 'ExchangeSelf', 'DoLoop', 'Timers')))
     q_names = ['rho'] + ['rhou%d' % d for d in range(ndim)] + ['rhoE']
 
     # ---- stage loop: classify every kernel
@@ -774,4 +778,6 @@ class B200(object):
         with open(os.path.join(workdir, PLAN_FILE), 'w') as f:
             json.dump(self.plan, f, indent=1)
         write_stub(self.plan, os.path.join(workdir, STUB_FILE))
+        if self.plan.get('not_executed'):
+            print("B200: components outside the accelerated time loop are not executed: %s" % ', '.join(self.plan['not_executed']))
         print("Successfully generated the B200 execution plan.")

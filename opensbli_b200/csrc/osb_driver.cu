@@ -346,10 +346,10 @@ void neighbour_wait(osb_ctx *c, int kind) {
 
 int push_planes_memcpy(osb_ctx *c);
 
-template <int RK>
+template <int RK, bool FROMQ = false>
 void launch_viscous_tiled(osb_ctx *c, double a, double b) {
   const GridDev &g = c->grid;
-  auto kern = k_viscous3d_tiled<RK>;
+  auto kern = k_viscous3d_tiled<RK, FROMQ>;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vt_smem_bytes()); attr_set = true; }
   dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + VT_ZC - 1) / VT_ZC);
@@ -357,11 +357,32 @@ void launch_viscous_tiled(osb_ctx *c, double a, double b) {
   kern<<<gr, bl, vt_smem_bytes(), c->stream>>>(g, c->fp, c->pc, a, b, RK == 0 ? PeerPush{} : peer_push(c));
 }
 
+// Stage kernels that write the new state out of place into the Residual buffers: the buffers then exchange roles with
+// the q buffers (the field table follows, so "rho" always names the current density).
+void swap_q_and_residual(osb_ctx *c) {
+  for (int m = 0; m < 5; m++) {
+    if (!c->fp.q[m] || !c->fp.R[m]) continue;
+    for (auto &f : c->fields) { if (f.dev == c->fp.q[m]) f.dev = c->fp.R[m]; else if (f.dev == c->fp.R[m]) f.dev = c->fp.q[m]; }
+    std::swap(c->fp.q[m], c->fp.R[m]);
+  }
+  c->swap_parity ^= 1;
+}
+
+// Shock-capturing 3-D stages on one GPU: the viscous + RK kernel derives (u, T) from q itself, so the constituent-relation
+// kernel is not launched at all (the flux sweeps stage their own primitives too).
+bool viscous_from_q_ok(const osb_ctx *c) {
+  static const bool on = getenv("OSB_NO_VISCOUS_FROM_Q") == nullptr;
+  const Plan &P = c->plan;
+  if (!on || P.nd != 3 || P.conv == CONV_CENTRAL || !P.viscous || c->general || P.teno_adaptive) return false;
+  for (int s = 0; s < 2; s++) if (P.bc[2][s].kind == BC_EXCHANGE) return false;
+  return true;
+}
+
 // phase A of a stage: everything that reads the halos of q (constituent relations, sensor, convective terms)
 template <int ND>
-void launch_phase_a(osb_ctx *c) {
+void launch_phase_a(osb_ctx *c, int stage = -1) {
   const GridDev &g = c->grid;
-  launch_prim<ND>(c);
+  if (!(ND == 3 && stage >= 0 && viscous_from_q_ok(c))) launch_prim<ND>(c);
   if (c->plan.teno_adaptive) {
     dim3 b(64, 2, 2);
     Launcher L(c, OSB_FAM_PRIM);
@@ -392,6 +413,11 @@ bool launch_phase_b(osb_ctx *c, int stage) {
   if (c->plan.viscous) {
     if (ND == 3 && !c->general) {
       if (stage < 0) launch_viscous_tiled<0>(c, 0.0, 0.0);
+      else if (viscous_from_q_ok(c)) {
+        if (c->plan.rk == RK_LS) launch_viscous_tiled<1, true>(c, c->plan.rk_a[stage], c->plan.rk_b[stage]);
+        else launch_viscous_tiled<2, true>(c, c->plan.rk_a[stage], c->plan.rk_b[stage]);
+        swap_q_and_residual(c);
+      }
       else if (c->plan.rk == RK_LS) launch_viscous_tiled<1>(c, c->plan.rk_a[stage], c->plan.rk_b[stage]);
       else launch_viscous_tiled<2>(c, c->plan.rk_a[stage], c->plan.rk_b[stage]);
       return stage >= 0;
@@ -526,11 +552,7 @@ void launch_central_fused(osb_ctx *c, int stage) {
     if (c->plan.rk == RK_LS) k_central3d_fused<1><<<gr, bl, ct_smem_bytes(), c->stream>>>(g, qi, qo, rk, c->pc, c->plan.rk_a[stage], c->plan.rk_b[stage], 0);
     else k_central3d_fused<2><<<gr, bl, ct_smem_bytes(), c->stream>>>(g, qi, qo, rk, c->pc, c->plan.rk_a[stage], c->plan.rk_b[stage], stage == 0);
   }
-  for (int m = 0; m < 5; m++) {
-    for (auto &f : c->fields) { if (f.dev == c->fp.q[m]) f.dev = c->fp.R[m]; else if (f.dev == c->fp.R[m]) f.dev = c->fp.q[m]; }
-    std::swap(c->fp.q[m], c->fp.R[m]);
-  }
-  c->swap_parity ^= 1;
+  swap_q_and_residual(c);
 }
 
 // One stage of the loop (s < 0: iteration start).  In a decomposed run the neighbour exchange is part of the stage and is
@@ -552,7 +574,7 @@ int stage_nd(osb_ctx *c, int s) {
     if (ex) { if (push_planes_memcpy(c)) return 1; neighbour_signal(c, 1); neighbour_wait(c, 1); }
     if (c->plan.rk == RK_SBLI) launch_save<ND>(c);
   } else {
-    launch_phase_a<ND>(c);        // sends the "read done" notification as soon as the halo-reading kernels are enqueued
+    launch_phase_a<ND>(c, s);     // sends the "read done" notification as soon as the halo-reading kernels are enqueued
     neighbour_wait(c, 0);
     const bool fused = launch_phase_b<ND>(c, s);
     if (!fused) launch_rk<ND>(c, s);
@@ -606,7 +628,7 @@ int do_step(osb_ctx *c, int nsteps) {
   if (!c->use_graph || c->profiling || c->plan.mass_source || has_exchange(c) || pts > (1LL << 22) || nsteps < 2) return step_dispatch(c, nsteps);
   // the fused central path exchanges buffer roles every stage: the captured unit must bring them back (two steps if the
   // number of stages is odd) and may only be replayed from the parity it was captured at (0)
-  const int unit = (fused_central_ok(c) && (c->plan.rk_a.size() % 2)) ? 2 : 1;
+  const int unit = ((fused_central_ok(c) || viscous_from_q_ok(c)) && (c->plan.rk_a.size() % 2)) ? 2 : 1;
   if (c->swap_parity) { if (step_dispatch(c, 1)) return 1; nsteps--; }
   if (nsteps < unit) return step_dispatch(c, nsteps);
   if (!c->step_graph) {

@@ -523,7 +523,18 @@ __global__ void k_wait(const unsigned long long *a, const unsigned long long *b,
 constexpr int VT_X = 32, VT_Y = 8, VT_HX = VT_X + 4, VT_HY = VT_Y + 4, VT_PLANE = VT_HX * VT_HY, VT_ZC = 32;
 constexpr size_t vt_smem_bytes() { return sizeof(double) * 5 * 4 * VT_PLANE; }
 
-template <int RK>   // RK: 0 = residual only, 1 = low-storage update (rk_LS.py:139-166), 2 = SBLI update (rk_sbli.py:102-133)
+// u0, u1, u2, T of one point from its conserved state (constituent relations of the canonical system)
+__device__ __forceinline__ void prim_uT(const double *q, const PhysConst &c, double *w) {
+  const double irho = 1.0 / q[0];
+  w[0] = q[1] * irho; w[1] = q[2] * irho; w[2] = q[3] * irho;
+  const double p = (c.gama - 1.0) * (q[4] - 0.5 * q[0] * (w[0] * w[0] + w[1] * w[1] + w[2] * w[2]));
+  w[3] = c.Minf * c.Minf * c.gama * p * irho;
+}
+
+// FROMQ: the planes of (u, T) are computed from q while staging (no constituent-relation kernel, four array reads fewer);
+// the new state is then written OUT OF PLACE into the Residual buffers (neighbouring blocks still stage the old q), which
+// exchange roles with the q buffers after the launch.
+template <int RK, bool FROMQ = false>   // RK: 0 = residual only, 1 = low-storage update (rk_LS.py:139-166), 2 = SBLI update (rk_sbli.py:102-133)
 __global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled(GridDev g, FieldPtrs f, PhysConst c, double rkA, double rkB, PeerPush pp) {
   extern __shared__ double vt_smem[];
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * VT_X + tx;
@@ -542,8 +553,17 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled(GridDev g, F
       const int gi = i0 + xx - 2, gj = j0 + yy - 2;
       if (gi < g.np[0] + 2 && gj < g.np[1] + 2) {
         const long long x = g.off + gi + gj * g.s[1] + (long long)kk * g.s[2];
+        if (FROMQ) {
+          double q[5], w[4];
 #pragma unroll
-        for (int v = 0; v < 4; v++) S(slot, v)[e] = __ldg(src[v] + x);
+          for (int m = 0; m < 5; m++) q[m] = __ldg(f.q[m] + x);
+          prim_uT(q, c, w);
+#pragma unroll
+          for (int v = 0; v < 4; v++) S(slot, v)[e] = w[v];
+        } else {
+#pragma unroll
+          for (int v = 0; v < 4; v++) S(slot, v)[e] = __ldg(src[v] + x);
+        }
       }
     }
   };
@@ -556,7 +576,7 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled(GridDev g, F
   __syncthreads();
   for (int k = k0; k < kend; k++) {
     // software pipeline: fetch plane k+3 and this point's Residual / RK register / q while plane k is computed
-    double pf[NPF][4];
+    double pf[NPF][FROMQ ? 5 : 4];
     const bool more = k + 1 < kend;
     if (more) {
 #pragma unroll
@@ -566,8 +586,13 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled(GridDev g, F
         const int gi = i0 + xx - 2, gj = j0 + yy - 2;
         if (e < VT_PLANE && gi < g.np[0] + 2 && gj < g.np[1] + 2) {
           const long long xg = g.off + gi + gj * g.s[1] + (long long)(k + 3) * g.s[2];
+          if (FROMQ) {
 #pragma unroll
-          for (int v = 0; v < 4; v++) pf[it][v] = __ldg(src[v] + xg);
+            for (int m = 0; m < 5; m++) pf[it][m] = __ldg(f.q[m] + xg);
+          } else {
+#pragma unroll
+            for (int v = 0; v < 4; v++) pf[it][v] = __ldg(src[v] + xg);
+          }
         }
       }
     }
@@ -646,7 +671,7 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled(GridDev g, F
           double qn;
           if (RK == 1) { const double t = c.dt * R[m] + rkA * o[m]; f.rk[m][x] = t; qn = rkB * t + q[m]; }
           else { qn = c.dt * rkB * R[m] + o[m]; f.rk[m][x] = c.dt * rkA * R[m] + o[m]; }
-          f.q[m][x] = qn;
+          if (FROMQ) f.R[m][x] = qn; else f.q[m][x] = qn;
           // fused halo exchange: peer stores of the new boundary planes
           if (pp.hi[m] && k >= g.np[2] - pp.hm) pp.hi[m][x - (long long)g.np[2] * g.s[2]] = qn;
           if (pp.lo[m] && k < pp.hp) pp.lo[m][x + (long long)g.np[2] * g.s[2]] = qn;
@@ -662,8 +687,15 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled(GridDev g, F
         const int yy = e / VT_HX, xx = e % VT_HX;
         const int gi = i0 + xx - 2, gj = j0 + yy - 2;
         if (e < VT_PLANE && gi < g.np[0] + 2 && gj < g.np[1] + 2) {
+          if (FROMQ) {
+            double w[4];
+            prim_uT(pf[it], c, w);
 #pragma unroll
-          for (int v = 0; v < 4; v++) S(slot, v)[e] = pf[it][v];
+            for (int v = 0; v < 4; v++) S(slot, v)[e] = w[v];
+          } else {
+#pragma unroll
+            for (int v = 0; v < 4; v++) S(slot, v)[e] = pf[it][v];
+          }
         }
       }
     }
