@@ -511,6 +511,147 @@ def _central_form(kernels, ndim, q_names):
     return 'blaisdell' if 'blaisdell' in common else 'feiereisen'
 
 
+def _check_viscous_form(kernels, ndim):
+    """The viscous loops (Derivative evaluation / Viscous CD / Viscous terms / Viscous residual, in program order;
+    StoreSome.py:71-161, scheme.py:256-271) are interpreted numerically on random data, like the central convective loops:
+    every derivative loop must be a 4th-order first, second or mixed central difference of u_a, T or mu, and what the
+    residual equations ADD must equal the Navier-Stokes terms the kernels implement (k_viscous*, osb_kernels.cuh):
+        tau_ij = mu/Re (d_j u_i + d_i u_j - 2/3 delta_ij d_k u_k) ,  q_j = mu/((gama-1) Minf^2 Pr Re) d_j T
+        momentum_i += d_j tau_ij (- c_i) ,  energy += d_j q_j + d_j (u_i tau_ij) (- c_j u_j)
+    with diagonal metrics  d_j f = D_jj delta_j f ,  d_jj f = D_jj^2 delta_jj f + D_jj SD_jjj delta_j f."""
+    import random
+    from sympy import Piecewise
+    from opensbli.core.opensbliobjects import DataSet
+    rnd = random.Random(4711)
+    W1 = {-2: 1.0 / 12, -1: -8.0 / 12, 1: 8.0 / 12, 2: -1.0 / 12}
+    W2 = {-2: -1.0 / 12, -1: 16.0 / 12, 0: -30.0 / 12, 1: 16.0 / 12, 2: -1.0 / 12}
+    fields = ['u0', 'u1', 'u2', 'T', 'mu']
+    vals, Dv, SDv, cst = {}, {}, {}, {}
+
+    def v(key, s):
+        return vals.setdefault((key, s), rnd.uniform(1.0, 2.0))
+
+    def default_branch(ex):
+        for _ in range(4):
+            pws = list(ex.atoms(Piecewise))
+            if not pws:
+                break
+            ex = ex.xreplace({pw: pw.args[-1][0] for pw in pws})
+        return ex
+
+    def constant(name):
+        return cst.setdefault(name, rnd.uniform(1.2, 1.8))
+
+    def numeric(ex, mapping, derivative):
+        ex = ex.xreplace(mapping)
+        # derivative loops: strip the 1/Delta factors; residual equations: physical constants get random values
+        return float(ex.subs({s: (1.0 if derivative else constant(str(s))) for s in ex.free_symbols}))
+
+    terms, checked = {}, 0
+    for k in kernels:
+        for e in k.equations:
+            if not hasattr(e, 'rhs'):
+                continue
+            lname = _strip(e.lhs.base) if hasattr(e.lhs, 'base') else str(e.lhs)
+            ex = default_branch(e.rhs)
+            dss = list(ex.atoms(DataSet))
+            m = re.match(r'Residual(\d)$', lname)
+            if m:
+                eq = int(m.group(1))
+                mapping, r0 = {}, rnd.uniform(1.0, 2.0)
+                for ds in dss:
+                    n = _strip(ds.base)
+                    if any(int(i) != 0 for i in ds.indices[:ndim]):
+                        raise UnsupportedByB200('stencil access inside the viscous residual equation of %s' % _name(k))
+                    if n == lname:
+                        mapping[ds] = r0
+                    elif n in terms:
+                        mapping[ds] = v(terms[n], 0)
+                    elif re.match(r'D(\d)\1$', n):
+                        mapping[ds] = Dv.setdefault(int(n[1]), rnd.uniform(1.0, 2.0))
+                    elif re.match(r'SD(\d)\1\1$', n):
+                        mapping[ds] = SDv.setdefault(int(n[2]), rnd.uniform(1.0, 2.0))
+                    elif n in fields:
+                        mapping[ds] = v(n, 0)
+                    else:
+                        raise UnsupportedByB200('viscous residual equation reads %s, which the B200 kernels do not implement' % n)
+                for s in ex.free_symbols:
+                    if str(s) in terms:
+                        mapping[s] = v(terms[str(s)], 0)
+                got = numeric(ex, mapping, False) - r0
+                # ---- the terms the kernels implement, from the same random values
+                has_mu_field = any(_strip(ds.base) == 'mu' for kk in kernels for ee in kk.equations if hasattr(ee, 'rhs') for ds in ee.rhs.atoms(DataSet))
+                mu = v('mu', 0) if has_mu_field else (cst['mu'] if 'mu' in cst else 1.0)
+                Re, gama, Minf, Pr = (constant(n) for n in ('Re', 'gama', 'Minf', 'Pr'))
+                D = lambda d: Dv.get(d, 1.0)
+                SD = lambda d: SDv.get(d, 0.0)
+                # a derivative the loops do not evaluate can only be one whose coefficient vanishes (e.g. d T without metrics and
+                # with constant viscosity); if it does not, the comparison below fails
+                T = lambda *key: v(key, 0) if key in terms.values() else 0.0
+                try:
+                    du = [[D(b) * T('d1', 'u%d' % a, b) for b in range(ndim)] for a in range(ndim)]
+                    dT = [D(b) * T('d1', 'T', b) for b in range(ndim)]
+                    dmu = [D(b) * T('d1', 'mu', b) for b in range(ndim)]
+                    div = sum(du[a][a] for a in range(ndim))
+                    lap = lambda f, b: D(b) ** 2 * T('d2', f, b) + D(b) * SD(b) * T('d1', f, b)
+                    S = lambda a, b: du[a][b] + du[b][a] - ((2.0 / 3.0) * div if a == b else 0.0)
+                    vis = []
+                    for a in range(ndim):
+                        s1 = sum(dmu[b] * S(a, b) for b in range(ndim))
+                        s2 = 0.0
+                        for b in range(ndim):
+                            if a == b:
+                                s2 += (4.0 / 3.0) * lap('u%d' % a, a)
+                            else:
+                                s2 += lap('u%d' % a, b) + (1.0 / 3.0) * D(a) * D(b) * T('mix', 'u%d' % b, min(a, b), max(a, b))
+                        vis.append((s1 + mu * s2) / Re)
+                    forced = [cst.get('c%d' % a) for a in range(ndim)]
+                    if 1 <= eq <= ndim:
+                        want = vis[eq - 1] - (forced[eq - 1] or 0.0)
+                    elif eq == ndim + 1:
+                        kq = 1.0 / ((gama - 1.0) * Minf ** 2 * Pr * Re)
+                        want = kq * (sum(dmu[d] * dT[d] for d in range(ndim)) + mu * sum(lap('T', d) for d in range(ndim)))
+                        want += sum(vis[a] * v('u%d' % a, 0) for a in range(ndim))
+                        want += (mu / Re) * sum(S(a, b) * du[a][b] for a in range(ndim) for b in range(ndim))
+                        want -= sum((forced[a] or 0.0) * v('u%d' % a, 0) for a in range(ndim))
+                    else:
+                        want = 0.0
+                except KeyError as err:
+                    raise UnsupportedByB200('viscous terms: derivative %s needed by the implemented Navier-Stokes terms is not evaluated by the loops' % (err.args[0],))
+                if abs(got - want) > 1e-10 * max(1.0, abs(want)):
+                    raise UnsupportedByB200('viscous terms added to %s differ from the Navier-Stokes terms the B200 kernels implement '
+                                            '(loops give %.12g, kernels %.12g on the same random data)' % (lname, got, want))
+                checked += 1
+                continue
+            dirs = set(d for ds in dss for d in range(ndim) if int(ds.indices[d]) != 0)
+            if len(dirs) != 1:
+                raise UnsupportedByB200('viscous derivative loop %s does not differentiate along exactly one direction' % _name(k))
+            d = dirs.pop()
+            mapping = {}
+            for ds in dss:
+                n, s = _strip(ds.base), int(ds.indices[d])
+                if n in terms:
+                    mapping[ds] = v(terms[n], s)
+                elif n in fields:
+                    mapping[ds] = v(n, s)
+                else:
+                    raise UnsupportedByB200('viscous derivative loop %s reads %s' % (_name(k), n))
+            got = numeric(ex, mapping, True)
+            cands = {}
+            for f in fields:
+                cands[('d1', f, d)] = sum(W1[s] * v(f, s) for s in W1)
+                cands[('d2', f, d)] = sum(W2[s] * v(f, s) for s in W2)
+            for key in set(terms.values()):
+                if key[0] == 'd1' and key[2] != d:
+                    cands[('mix', key[1], min(key[2], d), max(key[2], d))] = sum(W1[s] * v(key, s) for s in W1)
+            match = [key for key, val in cands.items() if abs(val - got) < 1e-11]
+            if len(match) != 1:
+                raise UnsupportedByB200('viscous derivative loop %s (%s) is not a 4th-order central difference the B200 kernels implement' % (_name(k), lname))
+            terms[lname] = match[0]
+    if not checked:
+        raise UnsupportedByB200('no viscous residual equations found in the viscous loops')
+
+
 def _metric_directions(kernels, ndim):
     """Stretched directions from the metric arrays the residual / viscous loops read: only diagonal metrics D_dd
     (+ SD_ddd) are implemented, i.e. grids stretched along their own coordinate (metric.py:137-147)."""
@@ -661,6 +802,8 @@ def extract_plan(algorithm):
     else:
         raise UnsupportedByB200('no convective discretisation found in the stage loop')
     plan['viscous'] = bool(viscous)
+    if viscous:
+        _check_viscous_form([k for k in in_stage if k in viscous], ndim)
     plan['forcing'] = _check_forcing(resid + viscous + central_conv, ndim)
     if plan['viscosity']['type'] != 'constant' and not viscous:
         plan['viscosity'] = {'type': 'constant'}
