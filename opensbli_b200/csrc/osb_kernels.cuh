@@ -223,6 +223,10 @@ __device__ __forceinline__ void stage_values(const double *q, double gama, doubl
   sv[V::A * VS] = sqrt(gama * p * irho);
 }
 
+// Loads whose values are needed only at the end of a block / plane iteration (old Residual, RK register) would expose their
+// DRAM latency to every warp at once where they are used: the lines are requested into L2 up front (a few lanes per warp).
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int ND>
 __device__ __forceinline__ void stage_point(const FieldPtrs &f, long long x, double gama, double *sv, int VS) {
   double q[ND + 2];
@@ -597,6 +601,14 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled(GridDev g, F
       }
     }
     const long long x = g.off + i + j * g.s[1] + (long long)k * g.s[2];
+    if (more && active && (tx & 15) == 0) {
+#pragma unroll
+      for (int m = 0; m < 5; m++) {
+        prefetch_l2(f.R[m] + x + g.s[2]);
+        if (RK != 0) prefetch_l2(f.rk[m] + x + g.s[2]);
+        if (RK != 0 && !FROMQ) prefetch_l2(f.q[m] + x + g.s[2]);
+      }
+    }
     double R[5], q[5], o[5];
     if (active) {
 #pragma unroll
@@ -769,6 +781,10 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 1) k_central3d_fused(GridDev g, Q
       }
     }
     const long long x = g.off + i + j * g.s[1] + (long long)k * g.s[2];
+    if (more && active && (tx & 15) == 0 && !(RK == 2 && first_stage)) {
+#pragma unroll
+      for (int m = 0; m < 5; m++) prefetch_l2(rkreg.q[m] + x + g.s[2]);
+    }
     double o[5];
     if (active && !(RK == 2 && first_stage)) {
 #pragma unroll
