@@ -245,7 +245,7 @@ def main():
     q_in = [t.numpy() for t in hin]
     q_out = [t.numpy() for t in hout]
     tgv_state_into(q_in, lplan, k0, nk)
-    sim.set_state(q_in)
+    dsim.set_state(q_in)           # collective: the upload also writes the halo planes the neighbours store into
 
     def barrier():
         sim.sync()
@@ -330,7 +330,7 @@ def main():
             barrier()
             sim.timer_start()
             for _ in range(Ke):
-                sim.set_state(q_in)
+                dsim.set_state(q_in)
                 dsim.step(1)
                 for m, nme in enumerate(sim.q_names):
                     sim.download_into(nme, q_out[m])

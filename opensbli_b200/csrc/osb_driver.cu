@@ -87,7 +87,10 @@ struct osb_ctx {
   bool general = false;
   double *face_table[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   long long face_size[3] = {0, 0, 0};
-  double *peer_q[2][5] = {{nullptr}};
+  // neighbours' arrays: [side][set][m], set 0 = the buffers that held q at creation, set 1 = those that held Residual (the
+  // two sets exchange roles every stage on the out-of-place paths; all ranks step in lockstep, so parities agree)
+  double *peer_buf[2][2][5] = {{{nullptr}}};
+  double *own_buf[2][5] = {{nullptr}};
   bool peer_open[2] = {false, false};
   // stream-ordered neighbour synchronisation (flag words written by the neighbours through peer pointers)
   unsigned long long *flags = nullptr;          // [0] low nbr read-done, [1] low nbr pushed, [2] high nbr read-done, [3] high nbr pushed, [7] error
@@ -311,15 +314,18 @@ bool fused_push_enabled() {
   return on;
 }
 
-PeerPush peer_push(const osb_ctx *c) {
+// out_of_place: the launching kernel writes the new state into the Residual-role buffers, so the neighbours' copies go into
+// THEIR Residual-role buffers (which become their q after the stage)
+PeerPush peer_push(const osb_ctx *c, bool out_of_place = false) {
   PeerPush pp;
+  const int set = out_of_place ? 1 - c->swap_parity : c->swap_parity;
   if (!fused_push_enabled()) return PeerPush{};
   const int d = c->plan.nd - 1;
   int hm, hp; scheme_halos(c->plan, hm, hp);
   pp.hm = hm; pp.hp = hp;
   for (int m = 0; m < 5; m++) {
-    pp.lo[m] = (c->plan.bc[d][0].kind == BC_EXCHANGE && c->peer_open[0]) ? c->peer_q[0][m] : nullptr;
-    pp.hi[m] = (c->plan.bc[d][1].kind == BC_EXCHANGE && c->peer_open[1]) ? c->peer_q[1][m] : nullptr;
+    pp.lo[m] = (c->plan.bc[d][0].kind == BC_EXCHANGE && c->peer_open[0]) ? c->peer_buf[0][set][m] : nullptr;
+    pp.hi[m] = (c->plan.bc[d][1].kind == BC_EXCHANGE && c->peer_open[1]) ? c->peer_buf[1][set][m] : nullptr;
   }
   return pp;
 }
@@ -354,7 +360,7 @@ void launch_viscous_tiled(osb_ctx *c, double a, double b) {
   if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vt_smem_bytes()); attr_set = true; }
   dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + VT_ZC - 1) / VT_ZC);
   Launcher L(c, OSB_FAM_VISCOUS);
-  kern<<<gr, bl, vt_smem_bytes(), c->stream>>>(g, c->fp, c->pc, a, b, RK == 0 ? PeerPush{} : peer_push(c));
+  kern<<<gr, bl, vt_smem_bytes(), c->stream>>>(g, c->fp, c->pc, a, b, RK == 0 ? PeerPush{} : peer_push(c, FROMQ));
 }
 
 // Stage kernels that write the new state out of place into the Residual buffers: the buffers then exchange roles with
@@ -374,7 +380,7 @@ bool viscous_from_q_ok(const osb_ctx *c) {
   static const bool on = getenv("OSB_NO_VISCOUS_FROM_Q") == nullptr;
   const Plan &P = c->plan;
   if (!on || P.nd != 3 || P.conv == CONV_CENTRAL || !P.viscous || c->general || P.teno_adaptive) return false;
-  for (int s = 0; s < 2; s++) if (P.bc[2][s].kind == BC_EXCHANGE) return false;
+  for (int s = 0; s < 2; s++) if (P.bc[2][s].kind == BC_EXCHANGE && !(c->peer_open[s] && fused_push_enabled())) return false;
   return true;
 }
 
@@ -706,6 +712,7 @@ int osb_create(const char *plan_text, int device, osb_ctx **out) {
   ok = ok && add("p", &c->fp.p) && add("a", &c->fp.a) && add("T", &c->fp.T);
   for (int m = 0; m < nv && ok; m++) ok = add("Residual" + std::to_string(m), &c->fp.R[m]);
   for (int m = 0; m < nv && ok; m++) ok = add(P.rk == RK_LS ? "tempRK_" + qn[m] : qn[m] + "_RKold", &c->fp.rk[m]);
+  for (int m = 0; m < nv; m++) { c->own_buf[0][m] = c->fp.q[m]; c->own_buf[1][m] = c->fp.R[m]; }
   // general path: metric fields (uploaded by the caller), viscosity, sensor
   c->general = P.visc_law != 0 || P.forcing || P.mass_source;
   c->iteration = P.iteration0;
@@ -746,7 +753,7 @@ int osb_destroy(osb_ctx *c) {
   cudaSetDevice(c->device);
   for (int s = 0; s < 2; s++)
     if (c->peer_open[s]) {
-      for (int m = 0; m < 5; m++) if (c->peer_q[s][m]) cudaIpcCloseMemHandle(c->peer_q[s][m]);
+      for (int t = 0; t < 2; t++) for (int m = 0; m < 5; m++) if (c->peer_buf[s][t][m]) cudaIpcCloseMemHandle(c->peer_buf[s][t][m]);
       if (c->peer_flags[s]) cudaIpcCloseMemHandle(c->peer_flags[s]);
     }
   drop_graph(c);
@@ -945,34 +952,36 @@ int osb_ipc_export(osb_ctx *c, void *handles, int *nbytes) {
   if (!c || !handles || !nbytes) return 1;
   cudaSetDevice(c->device);
   const int nv = c->plan.nd + 2;
-  for (int m = 0; m < nv; m++) {
-    cudaIpcMemHandle_t h;
-    OSB_CUDA(c, cudaIpcGetMemHandle(&h, c->fp.q[m]));
-    memcpy((char *)handles + m * sizeof(h), &h, sizeof(h));
-  }
+  for (int t = 0; t < 2; t++)
+    for (int m = 0; m < nv; m++) {
+      cudaIpcMemHandle_t h;
+      OSB_CUDA(c, cudaIpcGetMemHandle(&h, c->own_buf[t][m]));
+      memcpy((char *)handles + (t * nv + m) * sizeof(h), &h, sizeof(h));
+    }
   {
     cudaIpcMemHandle_t h;
     OSB_CUDA(c, cudaIpcGetMemHandle(&h, c->flags));
-    memcpy((char *)handles + nv * sizeof(h), &h, sizeof(h));
+    memcpy((char *)handles + 2 * nv * sizeof(h), &h, sizeof(h));
   }
-  *nbytes = (nv + 1) * (int)sizeof(cudaIpcMemHandle_t);
+  *nbytes = (2 * nv + 1) * (int)sizeof(cudaIpcMemHandle_t);
   return 0;
 }
 int osb_ipc_import(osb_ctx *c, int side, const void *handles, int nbytes) {
   if (!c || !handles || side < 0 || side > 1) return 1;
   cudaSetDevice(c->device);
   const int nv = c->plan.nd + 2;
-  if (nbytes != (nv + 1) * (int)sizeof(cudaIpcMemHandle_t)) return fail(c, "osb_ipc_import: wrong handle size");
-  for (int m = 0; m < nv; m++) {
-    cudaIpcMemHandle_t h;
-    memcpy(&h, (const char *)handles + m * sizeof(h), sizeof(h));
-    void *p = nullptr;
-    OSB_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-    c->peer_q[side][m] = (double *)p;
-  }
+  if (nbytes != (2 * nv + 1) * (int)sizeof(cudaIpcMemHandle_t)) return fail(c, "osb_ipc_import: wrong handle size");
+  for (int t = 0; t < 2; t++)
+    for (int m = 0; m < nv; m++) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char *)handles + (t * nv + m) * sizeof(h), sizeof(h));
+      void *p = nullptr;
+      OSB_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      c->peer_buf[side][t][m] = (double *)p;
+    }
   {
     cudaIpcMemHandle_t h;
-    memcpy(&h, (const char *)handles + nv * sizeof(h), sizeof(h));
+    memcpy(&h, (const char *)handles + 2 * nv * sizeof(h), sizeof(h));
     void *p = nullptr;
     OSB_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     c->peer_flags[side] = (unsigned long long *)p;
@@ -999,11 +1008,11 @@ int push_planes_memcpy(osb_ctx *c) {
   for (int m = 0; m < nv; m++) {
     if (P.bc[d][1].kind == BC_EXCHANGE && c->peer_open[1]) {
       // my top hm planes [np-hm, np) -> high neighbour's low halo [-hm, 0)
-      OSB_CUDA(c, cudaMemcpyAsync(c->peer_q[1][m] + (g.h - hm) * g.s[d], c->fp.q[m] + (g.h + g.np[d] - hm) * g.s[d], plane * hm, cudaMemcpyDeviceToDevice, c->stream));
+      OSB_CUDA(c, cudaMemcpyAsync(c->peer_buf[1][c->swap_parity][m] + (g.h - hm) * g.s[d], c->fp.q[m] + (g.h + g.np[d] - hm) * g.s[d], plane * hm, cudaMemcpyDeviceToDevice, c->stream));
     }
     if (P.bc[d][0].kind == BC_EXCHANGE && c->peer_open[0]) {
       // my bottom hp planes [0, hp) -> low neighbour's high halo [np, np+hp); neighbour has the same np
-      OSB_CUDA(c, cudaMemcpyAsync(c->peer_q[0][m] + (g.h + g.np[d]) * g.s[d], c->fp.q[m] + g.h * g.s[d], plane * hp, cudaMemcpyDeviceToDevice, c->stream));
+      OSB_CUDA(c, cudaMemcpyAsync(c->peer_buf[0][c->swap_parity][m] + (g.h + g.np[d]) * g.s[d], c->fp.q[m] + g.h * g.s[d], plane * hp, cudaMemcpyDeviceToDevice, c->stream));
     }
   }
   return 0;

@@ -109,6 +109,15 @@ class DistributedSimulation(object):
             else:
                 self.dist.barrier()
 
+    def set_state(self, q):
+        """Upload this rank's slab (padded arrays).  Collective: no rank may start stepping -- and storing boundary planes
+        into its neighbours' halos -- before every rank's upload, which also writes those halos, has landed."""
+        self.sim.set_state(q)
+        self.barrier()
+
+    def get_state(self):
+        return self.sim.get_state()
+
     def step(self, nsteps=1, sync=True):
         """Enqueue nsteps iterations; the neighbour exchange is part of the stream-ordered stage sequence."""
         self.sim.step(nsteps, sync=sync)

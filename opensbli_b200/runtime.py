@@ -188,7 +188,7 @@ class Simulation(object):
         self._check(self.lib.osb_halo_push(self.ctx), 'osb_halo_push')
 
     def ipc_export(self):
-        buf = ctypes.create_string_buffer(64 * 8)
+        buf = ctypes.create_string_buffer(64 * 16)
         n = ctypes.c_int()
         self._check(self.lib.osb_ipc_export(self.ctx, buf, ctypes.byref(n)), 'osb_ipc_export')
         return buf.raw[:n.value]
