@@ -538,7 +538,7 @@ bool fused_central_ok(const osb_ctx *c) {
   static const bool on = getenv("OSB_NO_FUSED_CENTRAL") == nullptr;
   const Plan &P = c->plan;
   if (!on || P.nd != 3 || P.conv != CONV_CENTRAL || !P.viscous || c->general || P.central_form != 0) return false;
-  for (int s = 0; s < 2; s++) if (P.bc[2][s].kind == BC_EXCHANGE) return false;
+  for (int s = 0; s < 2; s++) if (P.bc[2][s].kind == BC_EXCHANGE && !(c->peer_open[s] && fused_push_enabled())) return false;
   return true;
 }
 
@@ -555,8 +555,8 @@ void launch_central_fused(osb_ctx *c, int stage) {
   dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + VT_ZC - 1) / VT_ZC);
   {
     Launcher L(c, OSB_FAM_CENTRAL);
-    if (c->plan.rk == RK_LS) k_central3d_fused<1><<<gr, bl, ct_smem_bytes(), c->stream>>>(g, qi, qo, rk, c->pc, c->plan.rk_a[stage], c->plan.rk_b[stage], 0);
-    else k_central3d_fused<2><<<gr, bl, ct_smem_bytes(), c->stream>>>(g, qi, qo, rk, c->pc, c->plan.rk_a[stage], c->plan.rk_b[stage], stage == 0);
+    if (c->plan.rk == RK_LS) k_central3d_fused<1><<<gr, bl, ct_smem_bytes(), c->stream>>>(g, qi, qo, rk, c->pc, c->plan.rk_a[stage], c->plan.rk_b[stage], 0, peer_push(c, true));
+    else k_central3d_fused<2><<<gr, bl, ct_smem_bytes(), c->stream>>>(g, qi, qo, rk, c->pc, c->plan.rk_a[stage], c->plan.rk_b[stage], stage == 0, peer_push(c, true));
   }
   swap_q_and_residual(c);
 }
@@ -570,8 +570,14 @@ int stage_nd(osb_ctx *c, int s) {
   if (c->plan.mass_source && s <= 0) c->pc.src_factor = sin(c->plan.src_rate * (double)c->iteration);
   struct StepCounter { osb_ctx *c; int s; ~StepCounter() { if (s == (int)c->plan.rk_a.size() - 1) c->iteration++; } } counter{c, s};
   if (ND == 3 && fused_central_ok(c)) {
-    if (s >= 0) launch_central_fused(c, s);
-    launch_bcs(c);
+    if (s >= 0) {
+      launch_central_fused(c, s);                       // the kernel also stores the boundary planes into the neighbours' buffers
+      if (ex) { neighbour_signal(c, 1); neighbour_wait(c, 1); }
+      launch_bcs(c);
+    } else {
+      launch_bcs(c);
+      if (ex) { if (push_planes_memcpy(c)) return 1; neighbour_signal(c, 1); neighbour_wait(c, 1); }
+    }
     OSB_CUDA(c, cudaGetLastError());
     return 0;
   }

@@ -728,7 +728,7 @@ struct QPtrs { double *q[5]; };
 
 template <int RK>   // 1 = low-storage update, 2 = SBLI update (first_stage folds the "Save equations" loop: old = q)
 __global__ void __launch_bounds__(VT_X * VT_Y, 1) k_central3d_fused(GridDev g, QPtrs qin, QPtrs qout, QPtrs rkreg, PhysConst c,
-                                                                   double rkA, double rkB, int first_stage) {
+                                                                   double rkA, double rkB, int first_stage, PeerPush pp) {
   extern __shared__ double ct_smem[];
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * VT_X + tx;
   const int i0 = blockIdx.x * VT_X, j0 = blockIdx.y * VT_Y, k0 = blockIdx.z * VT_ZC;
@@ -881,8 +881,13 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 1) k_central3d_fused(GridDev g, Q
       // ---- RK update, out of place
 #pragma unroll
       for (int m = 0; m < 5; m++) {
-        if (RK == 1) { const double t = c.dt * R[m] + rkA * o[m]; rkreg.q[m][x] = t; qout.q[m][x] = rkB * t + qc[m]; }
-        else { const double old = first_stage ? qc[m] : o[m]; qout.q[m][x] = c.dt * rkB * R[m] + old; rkreg.q[m][x] = c.dt * rkA * R[m] + old; }
+        double qn;
+        if (RK == 1) { const double t = c.dt * R[m] + rkA * o[m]; rkreg.q[m][x] = t; qn = rkB * t + qc[m]; }
+        else { const double old = first_stage ? qc[m] : o[m]; qn = c.dt * rkB * R[m] + old; rkreg.q[m][x] = c.dt * rkA * R[m] + old; }
+        qout.q[m][x] = qn;
+        // slab decomposition: new boundary planes go straight into the neighbours' (next) q buffers
+        if (pp.hi[m] && k >= g.np[2] - pp.hm) pp.hi[m][x - (long long)g.np[2] * g.s[2]] = qn;
+        if (pp.lo[m] && k < pp.hp) pp.lo[m][x + (long long)g.np[2] * g.s[2]] = qn;
       }
     }
     __syncthreads();
