@@ -35,6 +35,7 @@ ALG_FLOP_PER_UPDATE = 27.1e3          # 3 x 9038 (reference's own operation coun
 # profiles/r01_final_ncu_top_kernels_512.md: z 15.55 GB, x 16.32 GB, y 22.50 GB -> mean of the three launches of a stage
 # (algorithmic: 5 q read + 5 residual read + 5 residual write = 16.1 GB for the accumulating sweeps, 10.7 GB for the first)
 NCU_DRAM_BYTES_PER_FLUX_LAUNCH_512 = 18.12e9
+NCU_DRAM_BYTES_PER_CENTRAL_LAUNCH_512 = 22.6e9      # 8 x the 256^3 capture (2.83 GB); refreshed from the 512^3 capture below
 LS3 = dict(rk='ls', rk_a=[0.0, -5.0 / 9.0, -153.0 / 128.0], rk_b=[1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0])
 
 
@@ -288,10 +289,19 @@ def main():
         pass
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     if prof and args.workload == 'central4':
+        # dominant kernel: the fused central stage kernel (decomposed runs without peers: k_central + k_viscous3d_tiled)
         tot = sum(v['ms'] for v in prof.values())
-        roofline = {'bound': 'hbm', 'kernel': 'whole step (k_prim, k_central, k_viscous3d_tiled+RK)', 'achieved': ALG_BYTES_PER_UPDATE * value / world / 1e9,
-                    'peak': hbm_peak, 'unit': 'GB/s', 'frac': ALG_BYTES_PER_UPDATE * value / world / 1e9 / hbm_peak, 'traffic': None,
-                    'families_ms': {k: v['ms'] for k, v in prof.items()}, 'share_of_step': 1.0,
+        ce = prof['central']
+        launch_ms = (ce['ms'] + prof['viscous']['ms'] + prof['prim']['ms']) / max(ce['launches'], 1)
+        pts_local = float(np.prod(lplan['np']))
+        ach = (ALG_BYTES_PER_UPDATE / 3.0) * pts_local / (launch_ms * 1e-3) / 1e9
+        roofline = {'bound': 'hbm', 'kernel': 'k_central3d_fused (constituent relations + Central(4) convective + viscous terms + RK stage update)',
+                    'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
+                    'traffic': NCU_DRAM_BYTES_PER_CENTRAL_LAUNCH_512 if (world == 1 and args.size == 512) else None,
+                    'traffic_source': 'profiles/r01_final_ncu_central_fused_512.md (bytes per launch, ncu --set full)',
+                    'launch_ms': launch_ms, 'share_of_step': (ce['ms'] + prof['viscous']['ms'] + prof['prim']['ms']) / tot if tot else None,
+                    'bytes_model': 'algorithmic 160 B per point per stage: q read once, q and RK register written once, RK register read once',
+                    'families_ms': {k: v['ms'] for k, v in prof.items()},
                     'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'}
     elif prof:
         fl = prof['flux']
@@ -354,7 +364,7 @@ def main():
             cpu = {'value': None, 'unit': UNIT, 'cores': cores, 'kind': 'reference', 'sample': 'oracle/_ref/tgv_teno5/ref_omp missing'}
 
     if rank == 0:
-        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+        line = {'metric': METRIC if args.workload == 'teno5' else 'grid-point updates/s (fp64, Central-4 TGV)', 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
                 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
                 'data': 'synthetic',
                 'config': {'workload': ('TGV Re=1600 TENO5(Roe,LLF)+StoreSome(4) viscous+RK-LS3, %s grid fp64 (BASELINE configs[%d]), %d^3 points per GPU'
@@ -367,6 +377,8 @@ def main():
                 'gpu_launches': int(launches), 'fp64_peak_tflops_measured': fp64_peak,
                 'families_ms_rank0': {k: v['ms'] for k, v in prof.items()} if prof else None,
                 'alg_flop_per_update': ALG_FLOP_PER_UPDATE, 'achieved_alg_tflops': ALG_FLOP_PER_UPDATE * value / world / 1e12}
+        if args.workload != 'teno5':      # the reference operation count quoted above is the TENO5 one
+            line.pop('alg_flop_per_update'); line.pop('achieved_alg_tflops')
         print(json.dumps(line))
     dsim.close()
     if world > 1:

@@ -546,18 +546,15 @@ void launch_central_fused(osb_ctx *c, int stage) {
   const GridDev &g = c->grid;
   QPtrs qi, qo, rk;
   for (int m = 0; m < 5; m++) { qi.q[m] = c->fp.q[m]; qo.q[m] = c->fp.R[m]; rk.q[m] = c->fp.rk[m]; }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_central3d_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_smem_bytes());
-    cudaFuncSetAttribute(k_central3d_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_smem_bytes());
-    attr_set = true;
-  }
-  dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + VT_ZC - 1) / VT_ZC);
-  {
+  const bool push = has_exchange(c);
+  auto launch = [&](auto kern, int first) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_smem_bytes());
+    dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + VT_ZC - 1) / VT_ZC);
     Launcher L(c, OSB_FAM_CENTRAL);
-    if (c->plan.rk == RK_LS) k_central3d_fused<1><<<gr, bl, ct_smem_bytes(), c->stream>>>(g, qi, qo, rk, c->pc, c->plan.rk_a[stage], c->plan.rk_b[stage], 0, peer_push(c, true));
-    else k_central3d_fused<2><<<gr, bl, ct_smem_bytes(), c->stream>>>(g, qi, qo, rk, c->pc, c->plan.rk_a[stage], c->plan.rk_b[stage], stage == 0, peer_push(c, true));
-  }
+    kern<<<gr, bl, ct_smem_bytes(), c->stream>>>(g, qi, qo, rk, c->pc, c->plan.rk_a[stage], c->plan.rk_b[stage], first, push ? peer_push(c, true) : PeerPush{});
+  };
+  if (c->plan.rk == RK_LS) { if (push) launch(k_central3d_fused<1, true>, 0); else launch(k_central3d_fused<1, false>, 0); }
+  else { if (push) launch(k_central3d_fused<2, true>, stage == 0); else launch(k_central3d_fused<2, false>, stage == 0); }
   swap_q_and_residual(c);
 }
 

@@ -726,7 +726,7 @@ constexpr int CT_NV = 7, CT_RHO = 0, CT_E = 1, CT_U = 2, CT_P = 5, CT_T = 6;
 constexpr size_t ct_smem_bytes() { return sizeof(double) * 5 * CT_NV * VT_PLANE; }
 struct QPtrs { double *q[5]; };
 
-template <int RK>   // 1 = low-storage update, 2 = SBLI update (first_stage folds the "Save equations" loop: old = q)
+template <int RK, bool PUSH>   // RK 1 = low-storage update, 2 = SBLI update (first_stage folds the "Save equations" loop: old = q); PUSH: slab run
 __global__ void __launch_bounds__(VT_X * VT_Y, 1) k_central3d_fused(GridDev g, QPtrs qin, QPtrs qout, QPtrs rkreg, PhysConst c,
                                                                    double rkA, double rkB, int first_stage, PeerPush pp) {
   extern __shared__ double ct_smem[];
@@ -886,8 +886,10 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 1) k_central3d_fused(GridDev g, Q
         else { const double old = first_stage ? qc[m] : o[m]; qn = c.dt * rkB * R[m] + old; rkreg.q[m][x] = c.dt * rkA * R[m] + old; }
         qout.q[m][x] = qn;
         // slab decomposition: new boundary planes go straight into the neighbours' (next) q buffers
-        if (pp.hi[m] && k >= g.np[2] - pp.hm) pp.hi[m][x - (long long)g.np[2] * g.s[2]] = qn;
-        if (pp.lo[m] && k < pp.hp) pp.lo[m][x + (long long)g.np[2] * g.s[2]] = qn;
+        if (PUSH) {
+          if (pp.hi[m] && k >= g.np[2] - pp.hm) pp.hi[m][x - (long long)g.np[2] * g.s[2]] = qn;
+          if (pp.lo[m] && k < pp.hp) pp.lo[m][x + (long long)g.np[2] * g.s[2]] = qn;
+        }
       }
     }
     __syncthreads();
