@@ -35,7 +35,7 @@ ALG_FLOP_PER_UPDATE = 27.1e3          # 3 x 9038 (reference's own operation coun
 # profiles/r01_final_ncu_top_kernels_512.md: z 15.55 GB, x 16.32 GB, y 22.50 GB -> mean of the three launches of a stage
 # (algorithmic: 5 q read + 5 residual read + 5 residual write = 16.1 GB for the accumulating sweeps, 10.7 GB for the first)
 NCU_DRAM_BYTES_PER_FLUX_LAUNCH_512 = 18.12e9
-NCU_DRAM_BYTES_PER_CENTRAL_LAUNCH_512 = 22.6e9      # 8 x the 256^3 capture (2.83 GB); refreshed from the 512^3 capture below
+NCU_DRAM_BYTES_PER_CENTRAL_LAUNCH_512 = 22.80e9     # k_central3d_fused at 512^3: 12.02 GB read + 10.78 GB written (algorithmic 21.5 GB)
 LS3 = dict(rk='ls', rk_a=[0.0, -5.0 / 9.0, -153.0 / 128.0], rk_b=[1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0])
 
 
