@@ -101,6 +101,7 @@ struct osb_ctx {
   long long graph_launches = 0;
   bool use_graph = true;
   long long iteration = 0;                      // loop counter of algorithm.py:440-474 (argument of the mass source)
+  bool prim_stale = false;                      // u, p, a, T arrays lag the state (stage kernels that derive them on the fly)
   int swap_parity = 0;                          // fused central path: q and Residual buffers exchange roles every stage
 };
 
@@ -256,6 +257,7 @@ void launch_prim(osb_ctx *c) {
   dim3 b(128, 2, 1);
   Launcher L(c, OSB_FAM_PRIM);
   k_prim<ND><<<grid3(n[0], n[1], n[2], b), b, 0, c->stream>>>(c->grid, c->fp, c->pc, c->gp.mu, lo[0], lo[1], lo[2], n[0], n[1], n[2]);
+  c->prim_stale = false;
 }
 
 void neighbour_signal(osb_ctx *c, int kind);
@@ -372,6 +374,7 @@ void swap_q_and_residual(osb_ctx *c) {
     std::swap(c->fp.q[m], c->fp.R[m]);
   }
   c->swap_parity ^= 1;
+  c->prim_stale = true;
 }
 
 // Shock-capturing 3-D stages on one GPU: the viscous + RK kernel derives (u, T) from q itself, so the constituent-relation
@@ -813,10 +816,22 @@ int osb_upload(osb_ctx *c, const char *name, const double *host) {
   OSB_CUDA(c, cudaStreamSynchronize(c->stream));
   return 0;
 }
+// u_i, p, a, T are not kept up to date by the stage kernels that derive them on the fly: evaluate the constituent relations
+// of the current state before handing such an array out
+static void refresh_primitives_for(osb_ctx *c, const Field *f) {
+  if (!c->prim_stale) return;
+  bool prim = f->dev == c->fp.p || f->dev == c->fp.a || f->dev == c->fp.T;
+  for (int d = 0; d < c->plan.nd; d++) prim = prim || f->dev == c->fp.u[d];
+  if (!prim) return;
+  cudaSetDevice(c->device);
+  switch (c->plan.nd) { case 1: launch_prim<1>(c); break; case 2: launch_prim<2>(c); break; default: launch_prim<3>(c); }
+}
+
 int osb_download(osb_ctx *c, const char *name, double *host) {
   if (!c || !name || !host) return 1;
   Field *f = find_field(c, name);
   if (!f) return fail(c, std::string("unknown field ") + name);
+  refresh_primitives_for(c, f);
   OSB_CUDA(c, cudaMemcpyAsync(host, f->dev, sizeof(double) * c->grid.n, cudaMemcpyDeviceToHost, c->stream));
   OSB_CUDA(c, cudaStreamSynchronize(c->stream));
   return 0;
@@ -833,6 +848,7 @@ int osb_device_ptr(osb_ctx *c, const char *name, double **p) {
   if (!c || !name || !p) return 1;
   Field *f = find_field(c, name);
   if (!f) return fail(c, std::string("unknown field ") + name);
+  refresh_primitives_for(c, f);
   *p = f->dev;
   return 0;
 }

@@ -93,6 +93,22 @@ def test_boundary_conditions_on_perturbed_state(osb, name):
         assert np.allclose(a, b, rtol=1e-13, atol=1e-15), name
 
 
+@pytest.mark.parametrize('name', ['tgv_teno5_16', 'tgv_central4_16'])
+def test_primitive_fields_follow_the_state(osb, name):
+    """u_i, p, T handed out after a run are the constituent relations of the CURRENT state, also on the paths whose stage
+    kernels derive them on the fly and never write the arrays."""
+    plan, states = load_fixture(name)
+    g, M = plan['constants']['gama'], plan['constants']['Minf']
+    with osb.Simulation(plan) as sim:
+        sim.set_state(initial_padded(plan, states))
+        sim.step(3)
+        q = inner(plan, sim.get_state())
+        u0, p, T = (inner(plan, [sim.download(n)])[0] for n in ('u0', 'p', 'T'))
+    pw = (g - 1.0) * (q[4] - 0.5 * (q[1] ** 2 + q[2] ** 2 + q[3] ** 2) / q[0])
+    assert np.allclose(u0, q[1] / q[0], rtol=1e-14, atol=1e-16)
+    assert np.allclose(p, pw, rtol=1e-12) and np.allclose(T, g * M * M * pw / q[0], rtol=1e-12)
+
+
 CASES = [
     # nd, N, conv, order, formulation, averaging, viscous, rk
     (1, 64, 'teno', 6, 'JS', 'roe', False, 'ls'),
