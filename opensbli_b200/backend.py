@@ -183,6 +183,8 @@ def _check_constituent(kernels, ndim):
     }
     for d in range(ndim):
         canon['u%d' % d] = (lambda d: (lambda v: v['rhou%d' % d] / v['rho']))(d)
+        # contravariant velocity of the curvilinear form (euler_wave.py:29)
+        canon['U%d' % d] = (lambda d: (lambda v: sum(v['D%d%d' % (d, j)] * v['u%d' % j] for j in range(ndim))))(d)
     info = {'viscosity': {'type': 'constant'}, 'sensor': False}
     for k in kernels:
         lhs_names = [(_strip(e.lhs.base) if hasattr(e.lhs, 'base') else str(e.lhs)) for e in k.equations if hasattr(e, 'lhs')]
@@ -247,10 +249,52 @@ def _recon_info(k):
     info['averaging'] = 'roe' if ('AVG_%d_inv_rho' % d) in names else 'simple'
     used = _datasets_used([k])
     extra = [u for u in used if re.match(r'(D\d\d|detJ|SD\d+)$', u)]
-    if extra:   # full curvilinear eigensystems (metric direction cosines, euler_eigensystem.py:18-54) are not implemented
-        raise UnsupportedByB200('curvilinear metric terms %s in %s are not implemented yet' % (sorted(extra), _name(k)))
+    info['curvilinear'] = bool(extra)
+    if extra:   # metric direction cosines in the eigensystem (euler_eigensystem.py:18-54): the 2-D strong-conservation form
+        want = sorted(['D%d0' % d, 'D%d1' % d, 'detJ'])
+        if sorted(extra) != want or 'U%d' % d not in used:
+            raise UnsupportedByB200('curvilinear metric terms %s in %s: only the 2-D strong-conservation form (D_%d0, D_%d1, detJ, '
+                                    'contravariant velocity U%d) is implemented' % (sorted(extra), _name(k), d, d, d))
     info.setdefault('teno_adaptive', False)
     return info
+
+
+def _check_curvilinear_residual(recon, resid, ndim):
+    """Strong-conservation form: Residual_m = - sum_d (F^d_m[i] - F^d_m[i-1]) / Delta_d / detJ, with F^d_m the m-th array
+    written by the reconstruction loop of direction d (shock_capturing.py:21-34; euler_wave.py:12-18).  Checked numerically
+    with every constant (the 1/Delta factors) set to one."""
+    import random
+    from opensbli.core.opensbliobjects import DataSet
+    rnd = random.Random(99)
+    flux = {}
+    for k in recon:
+        d = _recon_info(k)['direction']
+        outs = [_strip(e.lhs.base) for e in k.equations if hasattr(e, 'lhs') and hasattr(e.lhs, 'base')]
+        flux[d] = outs
+    vals = {}
+    for k in resid:
+        for e in k.equations:
+            m = re.match(r'Residual(\d)$', _strip(e.lhs.base) if hasattr(e.lhs, 'base') else '')
+            if not m:
+                continue
+            eq = int(m.group(1))
+            mapping = {}
+            for ds in e.rhs.atoms(DataSet):
+                key = (_strip(ds.base), tuple(int(i) for i in ds.indices[:ndim]))
+                mapping[ds] = vals.setdefault(key, rnd.uniform(1.0, 2.0))
+            ex = e.rhs.xreplace(mapping)
+            got = float(ex.subs({s: 1.0 for s in ex.free_symbols}))
+            zero = (0,) * ndim
+            want = 0.0
+            try:
+                for d in range(ndim):
+                    back = tuple(-1 if e_ == d else 0 for e_ in range(ndim))
+                    want -= vals[(flux[d][eq], zero)] - vals[(flux[d][eq], back)]
+                want /= vals[('detJ', zero)]
+            except (KeyError, IndexError):
+                raise UnsupportedByB200('curvilinear residual equation of Residual%d does not difference the reconstructed fluxes' % eq)
+            if abs(got - want) > 1e-11 * max(1.0, abs(want)):
+                raise UnsupportedByB200('curvilinear residual equation of Residual%d is not -(dF/dxi)/detJ' % eq)
 
 
 KNOWN_CONSTANTS = re.compile(r'^(gama|gamma_m1|Minf|Re|Pr|mu|dt|eps|TENO_CT|teno_a1|teno_a2|epsilon|SuthT|RefT|Twall|niter|c[0-2]|'
@@ -790,7 +834,7 @@ def extract_plan(algorithm):
         infos = [_recon_info(k) for k in recon]
         if sorted(i['direction'] for i in infos) != list(range(ndim)):
             raise UnsupportedByB200('reconstruction kernels do not cover every direction once')
-        for key in ('conv', 'order', 'weno_formulation', 'averaging', 'teno_adaptive'):
+        for key in ('conv', 'order', 'weno_formulation', 'averaging', 'teno_adaptive', 'curvilinear'):
             if len(set(i[key] for i in infos)) != 1:
                 raise UnsupportedByB200('direction-dependent %s is not implemented' % key)
             plan[key] = infos[0][key]
@@ -802,12 +846,17 @@ def extract_plan(algorithm):
     else:
         raise UnsupportedByB200('no convective discretisation found in the stage loop')
     plan['viscous'] = bool(viscous)
+    plan['curvilinear'] = bool(plan.get('curvilinear'))
+    if plan['curvilinear']:
+        if ndim != 2 or viscous or plan.get('teno_adaptive'):
+            raise UnsupportedByB200('curvilinear grids are implemented for 2-D inviscid shock-capturing schemes only')
+        _check_curvilinear_residual(recon, resid, ndim)
     if viscous:
         _check_viscous_form([k for k in in_stage if k in viscous], ndim)
     plan['forcing'] = _check_forcing(resid + viscous + central_conv, ndim)
     if plan['viscosity']['type'] != 'constant' and not viscous:
         plan['viscosity'] = {'type': 'constant'}
-    plan['metric_fields'] = _metric_directions(resid + viscous + central_conv + [k for k in cr if _name(k) == 'ConstituentRelations evaluation'], ndim)
+    plan['metric_fields'] = [None] * ndim if plan['curvilinear'] else _metric_directions(resid + viscous + central_conv + [k for k in cr if _name(k) == 'ConstituentRelations evaluation'], ndim)
     faces, d1tab = _closure_tables([k for k in viscous + cr + central_conv if _name(k).startswith(('Derivative evaluation', 'Viscous CD', 'Convective CD'))
                                     or _name(k) == 'ConstituentRelations evaluation'], ndim)
     closure_name = None
@@ -881,6 +930,11 @@ def extract_plan(algorithm):
     # ---- cold kernels before the time loop (initialisation, metric evaluation, metric boundaries), in program order
     cold = []
     for c in before:
+        if type(c).__name__ == 'ExchangeSelf':
+            from sympy.printing.c import ccode
+            cold.append({'name': 'exchange', 'exchange': True, 'arrays': [_strip(a) for a in c.transfer_arrays],
+                         'size': [ccode(s) for s in c.transfer_size], 'from': [ccode(s) for s in c.transfer_from],
+                         'to': [ccode(s) for s in c.transfer_to]})
         if type(c).__name__ == 'Kernel':
             n = _name(c)
             if not (n.startswith('Grid_based_initialisation') or n.startswith('MetricsEquation') or n.startswith('Metric boundary')):

@@ -53,6 +53,7 @@ struct Plan {
   bool teno_adaptive = false;
   bool forcing = false;
   int central_form = 0;      // 0 Blaisdell skew form, 1 Feiereisen quadratic split
+  bool curvilinear = false;  // full metric tensor D_ij + detJ (2-D strong-conservation form)
   bool mass_source = false;  // Residual_rho += BF_amp(x) sin(src_rate * iteration)
   double src_rate = 0.0;
   long long iteration0 = 0;
@@ -84,6 +85,7 @@ struct osb_ctx {
   cudaEvent_t timer0 = nullptr, timer1 = nullptr;
   GeneralPtrs gp{};
   AdaptiveCT ad{};
+  CurvPtrs cp{};
   bool general = false;
   double *face_table[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   long long face_size[3] = {0, 0, 0};
@@ -172,6 +174,7 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
     else if (key == "metric") { int d2, on; ls >> d2 >> on; if (d2 < 0 || d2 > 2) { err = "bad metric line"; return false; } P.metric[d2] = on != 0; }
     else if (key == "teno_adaptive") { int v; ls >> v; P.teno_adaptive = v != 0; }
     else if (key == "forcing") { int v; ls >> v; P.forcing = v != 0; }
+    else if (key == "curvilinear") { int v; ls >> v; P.curvilinear = v != 0; }
     else if (key == "mass_source") { ls >> P.src_rate >> P.iteration0; P.mass_source = true; }
     else if (key == "central_form") { std::string v; ls >> v; P.central_form = v == "blaisdell" ? 0 : v == "feiereisen" ? 1 : -1; if (P.central_form < 0) { err = "unknown central_form " + v; return false; } }
     else if (key == "closure_d1" || key == "closure_d2") {
@@ -296,8 +299,34 @@ void launch_flux(osb_ctx *c) {
   if (ND < 3) neighbour_signal(c, 0);
 }
 
+template <int RECON, int AVG>
+void launch_flux_curv2d(osb_ctx *c) {
+  const GridDev &g = c->grid;
+  dim3 bf(128, 1, 1), br(64, 4, 1);
+  {
+    Launcher L(c, OSB_FAM_FLUX);
+    k_flux_curv2d<0, RECON, AVG><<<dim3((g.np[0] + 1 + 127) / 128, g.np[1], 1), bf, 0, c->stream>>>(g, c->fp, c->pc, c->sp, c->cp);
+  }
+  { Launcher L(c, OSB_FAM_FLUX); k_resid_curv2d<0, false><<<grid3(g.np[0], g.np[1], 1, br), br, 0, c->stream>>>(g, c->fp, c->pc, c->cp); }
+  {
+    Launcher L(c, OSB_FAM_FLUX);
+    k_flux_curv2d<1, RECON, AVG><<<dim3((g.np[1] + 1 + 127) / 128, g.np[0], 1), bf, 0, c->stream>>>(g, c->fp, c->pc, c->sp, c->cp);
+  }
+  { Launcher L(c, OSB_FAM_FLUX); k_resid_curv2d<1, true><<<grid3(g.np[0], g.np[1], 1, br), br, 0, c->stream>>>(g, c->fp, c->pc, c->cp); }
+}
+
 template <int ND>
 void launch_flux_scheme(osb_ctx *c) {
+  if (ND == 2 && c->plan.curvilinear) {
+    const Plan &Pc = c->plan;
+    const bool roe_ = Pc.averaging == AVG_ROE;
+    if (Pc.conv == CONV_TENO && Pc.order == 5) { roe_ ? launch_flux_curv2d<RECON_TENO5, AVG_ROE>(c) : launch_flux_curv2d<RECON_TENO5, AVG_SIMPLE>(c); }
+    else if (Pc.conv == CONV_TENO) { roe_ ? launch_flux_curv2d<RECON_TENO6, AVG_ROE>(c) : launch_flux_curv2d<RECON_TENO6, AVG_SIMPLE>(c); }
+    else if (Pc.weno_z) { roe_ ? launch_flux_curv2d<RECON_WENO5_Z, AVG_ROE>(c) : launch_flux_curv2d<RECON_WENO5_Z, AVG_SIMPLE>(c); }
+    else { roe_ ? launch_flux_curv2d<RECON_WENO5_JS, AVG_ROE>(c) : launch_flux_curv2d<RECON_WENO5_JS, AVG_SIMPLE>(c); }
+    neighbour_signal(c, 0);
+    return;
+  }
   const Plan &P = c->plan;
   const bool roe = P.averaging == AVG_ROE;
   if (P.conv == CONV_TENO && P.order == 5) { roe ? launch_flux<ND, RECON_TENO5, AVG_ROE>(c) : launch_flux<ND, RECON_TENO5, AVG_SIMPLE>(c); }
@@ -733,6 +762,15 @@ int osb_create(const char *plan_text, int device, osb_ctx **out) {
     }
   }
   if (ok && (c->general || P.visc_law != 0)) ok = add("mu", &c->gp.mu);
+  if (P.curvilinear) {
+    if (P.nd != 2 || P.viscous || P.conv == CONV_CENTRAL || P.teno_adaptive) {
+      g_create_error = "curvilinear grids are implemented for 2-D inviscid shock-capturing schemes"; osb_destroy(c); return 1;
+    }
+    for (int i = 0; i < 2 && ok; i++)
+      for (int j = 0; j < 2 && ok; j++) { double *pd = nullptr; ok = add("D" + std::to_string(i) + std::to_string(j), &pd); c->cp.D[i][j] = pd; }
+    if (ok) { double *pd = nullptr; ok = add("detJ", &pd); c->cp.detJ = pd; }
+    for (int m = 0; m < 4 && ok; m++) ok = add("wk_flux" + std::to_string(m), &c->cp.wk[m]);
+  }
   if (ok && P.mass_source) { double *ps = nullptr; ok = add("BF_amp", &ps); c->gp.src = ps; }
   if (ok && P.teno_adaptive) ok = add("theta", &c->gp.theta) && add("TENO", &c->gp.teno_store);
   if (P.teno_adaptive && P.nd < 2) { g_create_error = "adaptive TENO needs at least 2 dimensions (vorticity)"; osb_destroy(c); return 1; }

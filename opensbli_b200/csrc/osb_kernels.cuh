@@ -1166,6 +1166,106 @@ __global__ void __launch_bounds__(256) k_central_general(GridDev g, FieldPtrs f,
 }
 
 // -------------------------------------------------------------------------------------------------
+// Fully curvilinear 2-D grids in strong-conservation form (apps/euler_wave_curvilinear/euler_wave.py:12-18):
+//   d q / dt = - (1/detJ) sum_i  d/dxi_i [ detJ ( U_i q + p (0, D_i0, D_i1, U_i) ) ] ,   U_i = D_ij u_j
+// Characteristic LLF flux with the metric-aware eigensystem (euler_eigensystem.py:18-105): direction cosines
+// k~ = avg(D_i.)/|avg(D_i.)| of the two interface points, wave speeds U, U +- a |D_i.| at every stencil point
+// (shock_capturing.py:357-536).  One thread per interface; the fluxes go through a work array and a difference kernel.
+// -------------------------------------------------------------------------------------------------
+struct CurvPtrs {
+  const double *D[2][2];    // D_ij = d xi_i / d x_j
+  const double *detJ;
+  double *wk[4];            // interface fluxes of the direction being swept
+};
+
+template <int DIR, int RECON, int AVG>
+__global__ void __launch_bounds__(128) k_flux_curv2d(GridDev g, FieldPtrs f, PhysConst c, SchemeParams sp, CurvPtrs cp) {
+  // interfaces i+1/2 for i = -1 .. np[DIR]-1 along DIR, all interior points of the other direction
+  const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  const int na = g.np[DIR] + 1;
+  if (a >= na || b >= g.np[1 - DIR]) return;
+  const int i = DIR == 0 ? a - 1 : b, j = DIR == 0 ? b : a - 1;
+  const long long x = g.off + i + j * g.s[1], sd = g.s[DIR];
+  const double gm1 = c.gama - 1.0;
+  double rho_[6], m0[6], m1[6], E_[6], pr[6], u0[6], u1[6], as[6], D0[6], D1[6], J[6];
+#pragma unroll
+  for (int p = 0; p < 6; p++) {
+    const long long xp = x + (p - 2) * sd;
+    rho_[p] = __ldg(f.q[0] + xp); m0[p] = __ldg(f.q[1] + xp); m1[p] = __ldg(f.q[2] + xp); E_[p] = __ldg(f.q[3] + xp);
+    D0[p] = __ldg(cp.D[DIR][0] + xp); D1[p] = __ldg(cp.D[DIR][1] + xp); J[p] = __ldg(cp.detJ + xp);
+    u0[p] = m0[p] / rho_[p]; u1[p] = m1[p] / rho_[p];
+    pr[p] = gm1 * (E_[p] - 0.5 * rho_[p] * (u0[p] * u0[p] + u1[p] * u1[p]));
+    as[p] = sqrt(c.gama * pr[p] / rho_[p]);
+  }
+  // interface state (averaging.py:31-114)
+  double rho, v0, v1, av;
+  if (AVG == AVG_ROE) {
+    const double sl = sqrt(rho_[2]), sr = sqrt(rho_[3]), w = 1.0 / (sr + sl);
+    rho = sqrt(rho_[2] * rho_[3]);
+    v0 = w * (sr * u0[3] + sl * u0[2]); v1 = w * (sr * u1[3] + sl * u1[2]);
+    const double H = w * ((pr[2] + E_[2]) / sl + (pr[3] + E_[3]) / sr);
+    av = sqrt(gm1 * (H - 0.5 * (v0 * v0 + v1 * v1)));
+  } else {
+    rho = 0.5 * (rho_[2] + rho_[3]); v0 = 0.5 * (u0[2] + u0[3]); v1 = 0.5 * (u1[2] + u1[3]); av = 0.5 * (as[2] + as[3]);
+  }
+  double k0 = 0.5 * (D0[2] + D0[3]), k1 = 0.5 * (D1[2] + D1[3]);
+  const double inm = 1.0 / sqrt(k0 * k0 + k1 * k1);
+  k0 *= inm; k1 *= inm;
+  const double phi = 0.5 * gm1 * (v0 * v0 + v1 * v1), ia2 = 1.0 / (av * av), irho = 1.0 / rho;
+  const double bt = 0.70710678118654752440 * irho / av;
+  double cf[4][6], cs[4][6], lam0 = 0.0, lamp = 0.0, lamm = 0.0;
+#pragma unroll
+  for (int p = 0; p < 6; p++) {
+    const double U = D0[p] * u0[p] + D1[p] * u1[p];
+    const double am = sqrt(D0[p] * D0[p] + D1[p] * D1[p]) * as[p];
+    lam0 = fmax(lam0, fabs(U)); lamp = fmax(lamp, fabs(U + am)); lamm = fmax(lamm, fabs(U - am));
+    double v[2][4];
+    v[0][0] = rho_[p]; v[0][1] = m0[p]; v[0][2] = m1[p]; v[0][3] = E_[p];
+    v[1][0] = J[p] * (rho_[p] * U); v[1][1] = J[p] * (m0[p] * U + D0[p] * pr[p]); v[1][2] = J[p] * (m1[p] * U + D1[p] * pr[p]);
+    v[1][3] = J[p] * ((pr[p] + E_[p]) * U);
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      const double *xv = v[t];
+      const double um = v0 * xv[1] + v1 * xv[2], w0 = xv[1] - v0 * xv[0], w1 = xv[2] - v1 * xv[0];
+      const double S = phi * xv[0] - gm1 * um + gm1 * xv[3];
+      const double aw = av * (k0 * w0 + k1 * w1);
+      double ch[4];
+      ch[0] = xv[0] - S * ia2;
+      ch[1] = (k1 * w0 - k0 * w1) * irho;
+      ch[2] = bt * (S + aw);
+      ch[3] = bt * (S - aw);
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) { if (t == 0) cs[jj][p] = ch[jj]; else cf[jj][p] = ch[jj]; }
+    }
+  }
+  double rec[4];
+  rec[0] = reconstruct<RECON>(cf[0], cs[0], lam0, sp);
+  rec[1] = reconstruct<RECON>(cf[1], cs[1], lam0, sp);
+  rec[2] = reconstruct<RECON>(cf[2], cs[2], lamp, sp);
+  rec[3] = reconstruct<RECON>(cf[3], cs[3], lamm, sp);
+  const double al = 0.70710678118654752440 * rho / av;
+  const double th = k0 * v0 + k1 * v1, Hp = (phi + av * av) / gm1;
+  cp.wk[0][x] = rec[0] + al * (rec[2] + rec[3]);
+  cp.wk[1][x] = v0 * rec[0] + k1 * rho * rec[1] + al * ((v0 + k0 * av) * rec[2] + (v0 - k0 * av) * rec[3]);
+  cp.wk[2][x] = v1 * rec[0] - k0 * rho * rec[1] + al * ((v1 + k1 * av) * rec[2] + (v1 - k1 * av) * rec[3]);
+  cp.wk[3][x] = (phi / gm1) * rec[0] + rho * (k1 * v0 - k0 * v1) * rec[1] + al * ((Hp + av * th) * rec[2] + (Hp - av * th) * rec[3]);
+}
+
+// Residual (+)= -(F_{i+1/2} - F_{i-1/2}) / Delta_DIR / detJ   (shock_capturing.py:21-34 with the 1/detJ of the app's equations)
+template <int DIR, bool ACCUM>
+__global__ void __launch_bounds__(256) k_resid_curv2d(GridDev g, FieldPtrs f, PhysConst c, CurvPtrs cp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= g.np[0] || j >= g.np[1]) return;
+  const long long x = g.off + i + j * g.s[1];
+  const double sc = -c.inv[DIR] / __ldg(cp.detJ + x);
+  double r[4];
+#pragma unroll
+  for (int m = 0; m < 4; m++) r[m] = sc * (cp.wk[m][x] - cp.wk[m][x - g.s[DIR]]) + (ACCUM ? f.R[m][x] : 0.0);
+#pragma unroll
+  for (int m = 0; m < 4; m++) f.R[m][x] = r[m];
+}
+
+// -------------------------------------------------------------------------------------------------
 // Boundary conditions
 // -------------------------------------------------------------------------------------------------
 struct Box { int lo[3], n[3]; };   // start index and extent per dimension (inactive dims: lo 0, n 1)

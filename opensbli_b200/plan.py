@@ -26,6 +26,8 @@ JSON-able dict; `to_text` serialises it to the line format parsed by the C ABI (
                     (constant: an optional constant 'mu' scales 1/Re, e.g. viscous_shock_tube.py:14-16)
     metric_fields   per direction None | 'D11'...: stretched direction; fields['D11'], fields['SD111'] hold the metric arrays
     teno_adaptive   bool: C_T from the Ducros sensor (constants teno_a1, teno_a2, epsilon)
+    curvilinear     bool: full metric tensor; fields D00, D01, D10, D11, detJ (2-D, inviscid shock-capturing schemes;
+                    strong-conservation form of apps/euler_wave_curvilinear)
     mass_source     {'field': name, 'rate': w}: Residual_rho += fields[name] * sin(w * iteration)  (transitional_SBLI.py:77-89);
                     iteration0: iteration number of the first step (restart)
                     dirichlet_field faces may carry 'free': [m, ...] (variables left untouched) and 'ke_free': True (imposed
@@ -143,6 +145,8 @@ def to_text(plan):
         L.append('teno_adaptive 1')
     if plan.get('forcing'):
         L.append('forcing 1')
+    if plan.get('curvilinear'):
+        L.append('curvilinear 1')
     if plan.get('mass_source'):
         L.append('mass_source %s %d' % (_f(plan['mass_source']['rate']), int(plan.get('iteration0', 0))))
     if plan.get('central_form', 'blaisdell') != 'blaisdell':

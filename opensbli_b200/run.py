@@ -92,7 +92,21 @@ class ColdRunner(object):
     def _slices(self, lo, hi, off):
         return tuple(slice(lo[d] + off[d] + self.h, hi[d] + off[d] + self.h) for d in reversed(range(self.nd)))
 
+    def exchange(self, op):
+        """Periodic copy of a cold phase (ExchangeSelf, periodic.py:42-56; e.g. the metric arrays of a curvilinear grid):
+        size / from / to are the reference's own transfer description (C expressions in block0np{d})."""
+        size = [int(c_eval(s, self.env)) for s in op['size']]
+        src = [int(c_eval(s, self.env)) for s in op['from']]
+        dst = [int(c_eval(s, self.env)) for s in op['to']]
+        s_from = tuple(slice(src[d] + self.h, src[d] + size[d] + self.h) for d in reversed(range(self.nd)))
+        s_to = tuple(slice(dst[d] + self.h, dst[d] + size[d] + self.h) for d in reversed(range(self.nd)))
+        for name in op['arrays']:
+            a = self.array(name)
+            a[s_to] = a[s_from].copy()
+
     def run(self, kernel):
+        if kernel.get('exchange'):
+            return self.exchange(kernel)
         rng = [int(c_eval(r, self.env)) for r in kernel['range']]
         lo, hi = rng[0::2], rng[1::2]
         ax = [np.arange(lo[d], hi[d]) for d in range(self.nd)]
@@ -118,7 +132,7 @@ def resolve(plan_sym, env):
     metric fields, tabulated Dirichlet states); returns (plan, ColdRunner holding every cold dataset)."""
     nd = plan_sym['ndim']
     p = {k: plan_sym[k] for k in ('ndim', 'conv', 'order', 'weno_formulation', 'averaging', 'viscous', 'rk', 'rk_a', 'rk_b')}
-    for k in ('viscosity', 'metric_fields', 'teno_adaptive', 'closures', 'forcing', 'central_form'):   # copied verbatim
+    for k in ('viscosity', 'metric_fields', 'teno_adaptive', 'closures', 'forcing', 'central_form', 'curvilinear'):   # copied verbatim
         if k in plan_sym:
             p[k] = plan_sym[k]
     p['np'] = [int(env['block0np%d' % d]) for d in range(nd)]
@@ -133,6 +147,9 @@ def resolve(plan_sym, env):
         if name:
             for f in (name, 'S' + name + str(d)):
                 p['fields'][f] = cold.array(f).copy()
+    if plan_sym.get('curvilinear'):
+        for f in ['D%d%d' % (i, j) for i in range(nd) for j in range(nd)] + ['detJ']:
+            p['fields'][f] = cold.array(f).copy()
     if plan_sym.get('mass_source'):
         ms = plan_sym['mass_source']
         p['mass_source'] = {'field': ms['field'], 'rate': float(c_eval(ms['rate'], env))}

@@ -353,7 +353,7 @@ double osbo_recon_weno5(const double *fp, const double *fm, int z) {
  * the FD metric matrix is diagonal, euler_eigensystem.py:50-54).
  * 1-D: :57-75   2-D: :77-105   3-D: :107-135.   L = LEV, Rm = REV (nv x nv, row major, stride 5).
  * ------------------------------------------------------------------------------------------- */
-static void eigensystem(int nd, int d, double gama, double rho, const double *u, double a,
+static void eigensystem(int nd, int d, const double *kk, double gama, double rho, const double *u, double a,
                         double L[5][5], double Rm[5][5]) {
   const double gm1 = gama - 1.0;
   memset(L, 0, sizeof(double) * 25); memset(Rm, 0, sizeof(double) * 25);
@@ -370,7 +370,7 @@ static void eigensystem(int nd, int d, double gama, double rho, const double *u,
   const double s2 = sqrt(2.0);
   double al = rho / (a * s2), bt = 1.0 / (rho * a * s2);
   if (nd == 2) {
-    double k0 = d == 0, k1 = d == 1, u0 = u[0], u1 = u[1];
+    double k0 = kk ? kk[0] : (d == 0), k1 = kk ? kk[1] : (d == 1), u0 = u[0], u1 = u[1];
     double th = k0 * u0 + k1 * u1, ph = gm1 * 0.5 * (u0 * u0 + u1 * u1), a2 = a * a;
     L[0][0] = 1.0 - ph / a2; L[0][1] = gm1 * u0 / a2; L[0][2] = gm1 * u1 / a2; L[0][3] = -gm1 / a2;
     L[1][0] = -(k1 * u0 - k0 * u1) / rho; L[1][1] = k1 / rho; L[1][2] = -k0 / rho; L[1][3] = 0.0;
@@ -383,7 +383,7 @@ static void eigensystem(int nd, int d, double gama, double rho, const double *u,
     Rm[3][2] = al * ((ph + a2) / gm1 + a * th); Rm[3][3] = al * ((ph + a2) / gm1 - a * th);
     return;
   }
-  double k0 = d == 0, k1 = d == 1, k2 = d == 2, u0 = u[0], u1 = u[1], u2 = u[2];
+  double k0 = kk ? kk[0] : (d == 0), k1 = kk ? kk[1] : (d == 1), k2 = kk ? kk[2] : (d == 2), u0 = u[0], u1 = u[1], u2 = u[2];
   double th = k0 * u0 + k1 * u1 + k2 * u2, ph = gm1 * 0.5 * (u0 * u0 + u1 * u1 + u2 * u2), a2 = a * a;
   L[0][0] = k0 * (1.0 - ph / a2) - (k2 * u1 - k1 * u2) / rho; L[0][1] = k0 * gm1 * u0 / a2;
   L[0][2] = k0 * gm1 * u1 / a2 + k2 / rho; L[0][3] = k0 * gm1 * u2 / a2 - k1 / rho; L[0][4] = -k0 * gm1 / a2;
@@ -424,8 +424,12 @@ static double adaptive_ct(const osbo_cfg *c, double th) {
 }
 
 /* one interface: stencil data for the 6 points p = 0..5 <-> offsets -2..3 */
+/* met != NULL (curvilinear): met[p][0..nd-1] = D_dir,j and met[p][3] = detJ at the stencil points.  Then (euler_wave.py:12-18,
+ * shock_capturing.py:357-536 with the metric-aware eigensystem) the direction cosines are the simple average of D_dir. over
+ * the two interface points, normalised; the flux vector is detJ (U q + p (0, D_dir., U)) with U = D_dir,j u_j; the wave speeds
+ * are U, U +- a |D_dir.| at each stencil point. */
 static void interface_flux(const osbo_cfg *c, int nd, int dir, double qs[6][5], double us[6][3],
-                           const double *ps, const double *as, double teno_ct, double *flux) {
+                           const double *ps, const double *as, double teno_ct, double *flux, double (*met)[4]) {
   const int nv = nd + 2;
   const double gm1 = c->gama - 1.0;
   /* interface state between points 2 and 3 (averaging.py:31-59 simple, :62-114 Roe) */
@@ -442,21 +446,37 @@ static void interface_flux(const osbo_cfg *c, int nd, int dir, double qs[6][5], 
     for (int d = 0; d < nd; d++) u[d] = 0.5 * (us[2][d] + us[3][d]);
     a = 0.5 * (as[2] + as[3]);
   }
-  double L[5][5], Rm[5][5];
-  eigensystem(nd, dir, c->gama, rho, u, a, L, Rm);
+  double L[5][5], Rm[5][5], kk[3] = {0, 0, 0};
+  if (met) {
+    double n2 = 0.0;
+    for (int d = 0; d < nd; d++) { kk[d] = 0.5 * (met[2][d] + met[3][d]); n2 += kk[d] * kk[d]; }
+    const double inv = pow(n2, -0.5);
+    for (int d = 0; d < nd; d++) kk[d] *= inv;
+  }
+  eigensystem(nd, dir, met ? kk : NULL, c->gama, rho, u, a, L, Rm);
   /* characteristic flux / solution over the 6 stencil points and max |lambda| */
   double CF[5][6], CS[5][6], lam[5] = {0, 0, 0, 0, 0};
   for (int p = 0; p < 6; p++) {
-    double F[5], ud = us[p][dir], pr = ps[p];
+    double F[5], ud = us[p][dir], pr = ps[p], am = as[p];
     const double *qv = qs[p];
-    F[0] = qv[1 + dir];
-    for (int d = 0; d < nd; d++) F[1 + d] = qv[1 + d] * ud + (d == dir ? pr : 0.0);
-    F[nd + 1] = (pr + qv[nd + 1]) * ud;
+    if (met) {
+      double n2 = 0.0;
+      ud = 0.0;
+      for (int d = 0; d < nd; d++) { ud += met[p][d] * us[p][d]; n2 += met[p][d] * met[p][d]; }
+      am = sqrt(n2) * as[p];
+      F[0] = met[p][3] * (qv[0] * ud);
+      for (int d = 0; d < nd; d++) F[1 + d] = met[p][3] * (qv[1 + d] * ud + met[p][d] * pr);
+      F[nd + 1] = met[p][3] * ((pr + qv[nd + 1]) * ud);
+    } else {
+      F[0] = qv[1 + dir];
+      for (int d = 0; d < nd; d++) F[1 + d] = qv[1 + d] * ud + (d == dir ? pr : 0.0);
+      F[nd + 1] = (pr + qv[nd + 1]) * ud;
+    }
     for (int jj = 0; jj < nv; jj++) {
       double cf = 0.0, cs = 0.0;
       for (int m = 0; m < nv; m++) { cf += L[jj][m] * F[m]; cs += L[jj][m] * qv[m]; }
       CF[jj][p] = cf; CS[jj][p] = cs;
-      double l = fabs(eigenvalue(nd, jj, ud, as[p]));
+      double l = fabs(eigenvalue(nd, jj, ud, am));
       if (l > lam[jj]) lam[jj] = l;
     }
   }
@@ -485,7 +505,7 @@ void osbo_interface_flux(const osbo_cfg *c, int dir, const double *q6, double *f
     ps[p] = (c->gama - 1.0) * (qs[p][nd + 1] - ke);
     as[p] = sqrt(c->gama * ps[p] / qs[p][0]);
   }
-  interface_flux(c, nd, dir, qs, us, ps, as, c->teno_ct, flux);
+  interface_flux(c, nd, dir, qs, us, ps, as, c->teno_ct, flux, NULL);
 }
 
 static void llf_flux(const osbo_cfg *c, const grid_t *g, int dir, double *const *q, const prim_t *P, double **wk) {
@@ -508,7 +528,14 @@ static void llf_flux(const osbo_cfg *c, const grid_t *g, int dir, double *const 
       ct = adaptive_ct(c, c->theta[x]);
       if (dir == 0 && c->teno_store) c->teno_store[x] = ct;
     }
-    interface_flux(c, nd, dir, qs, us, ps, as, ct, fl);
+    double met[6][4];
+    if (c->curv_detJ)
+      for (int p = 0; p < 6; p++) {
+        const long xp = x + (p - 2) * sd;
+        for (int d = 0; d < nd; d++) met[p][d] = c->curv_D[dir][d][xp];
+        met[p][3] = c->curv_detJ[xp];
+      }
+    interface_flux(c, nd, dir, qs, us, ps, as, ct, fl, c->curv_detJ ? met : NULL);
     for (int m = 0; m < nv; m++) wk[m][x] = fl[m];
   }
 }
@@ -727,7 +754,7 @@ void osbo_residual(const osbo_cfg *c, double *const *q, double *const *R) {
       for (int m = 0; m < nv; m++) {
         double r = 0.0;
         for (int d = 0; d < nd; d++) r -= inv[d] * (wk[d][m][x] - wk[d][m][x - g.s[d]]) * (c->D[d] ? c->D[d][x] : 1.0);
-        R[m][x] = r;
+        R[m][x] = c->curv_detJ ? r / c->curv_detJ[x] : r;
       }
     }
   } else if (general || c->central_form != 0) {

@@ -81,6 +81,11 @@ typedef struct {
   const double *src_amp;      /* padded array or NULL */
   double src_rate;
   int src_iter0;
+  /* fully curvilinear grid (strong-conservation form of apps/euler_wave_curvilinear/euler_wave.py:12-18): metric arrays
+   * curv_D[i][j] = D_ij = d xi_i / d x_j and the Jacobian determinant detJ (padded, valid in the scheme halos); NULL: Cartesian
+   * or diagonal metrics.  Eigensystems then carry the direction cosines k~ = D_i. / |D_i.| (euler_eigensystem.py:18-54). */
+  const double *curv_D[3][3];
+  const double *curv_detJ;
   int central_form;           /* Central(4) convective split: 0 Blaisdell skew form (taylor_green_vortex.py:8-11, laminar_channel.py:7-9),
                                * 1 Feiereisen quadratic split (compressible_TCF_Central/turbulent_channel.py:12-20) */
 } osbo_cfg;

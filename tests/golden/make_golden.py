@@ -197,7 +197,21 @@ def trans_dirichlet_table(x0_padded):
     return np.stack(rows)
 
 
+def ewc_plan(N, conv='weno'):
+    """apps/euler_wave_curvilinear/euler_wave.py: 2-D Euler density wave on a wavy, fully curvilinear periodic grid in
+    strong-conservation form (metric arrays D_ij, detJ from the reference's own metric kernels), WENO5-Z (shipped) or TENO5."""
+    p = dict(ndim=2, np=[N, N], delta=[2.0 / N, 2.0 / N], conv=conv, order=5, averaging='roe', viscous=False, curvilinear=True,
+             constants=dict(gama=1.4, dt=0.0005), bc=[[dict(type='periodic'), dict(type='periodic')] for _ in range(2)], **LS3)
+    if conv == 'weno':
+        p['weno_formulation'] = 'Z'
+    else:
+        p['constants'].update(eps=1e-15, TENO_CT=1e-6)
+    return p
+
+
 if os.path.isdir('/root/reference'):
+    FIXTURES['ewc_wenoz5_32'] = ('ewc', ewc_plan(32), [1, 10])
+    FIXTURES['ewc_teno5_32'] = ('ewc_teno5', ewc_plan(32, 'teno'), [1, 10])
     FIXTURES['trans_40x30x8'] = ('trans', trans_plan(40, 30, 8), [1, 5, 20])
     FIXTURES['vst_60x30'] = ('vst', vst_plan(60, 30), [1, 10, 200])
     FIXTURES['lam2d_16x64'] = ('lam2d', lam2d_plan(16, 64), [1, 10])
@@ -209,7 +223,7 @@ FIXTURES['tgv_sym_17'] = ('tgv_sym', tgv_sym_plan(17), [1, 3])
 
 def env_params(plan):
     P = {'dt': plan['constants']['dt']}
-    if 'metric_fields' in plan or plan['bc'][0][0]['type'] == 'symmetry':
+    if 'metric_fields' in plan or plan.get('curvilinear') or plan['bc'][0][0]['type'] == 'symmetry':
         P = {}                        # grid spacings follow from the sizes inside the generated program
     for d in range(plan['ndim']):
         P['block0np%d' % d] = plan['np'][d]
@@ -228,6 +242,8 @@ def main():
         extra = []
         if 'metric_fields' in plan:
             extra = [n for d, name in enumerate(plan['metric_fields']) if name for n in ('D%d%d' % (d, d), 'SD%d%d%d' % (d, d, d))]
+        if plan.get('curvilinear'):
+            extra = ['D%d%d' % (i, j) for i in range(nd) for j in range(nd)] + ['detJ']
         r = run_ref(config, dict(env_params(plan), niter=0), fields + extra, dump_all=bool(extra))
         if extra:
             # full padded arrays: the halo values of the initial state and of the metrics are part of the problem

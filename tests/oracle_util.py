@@ -42,7 +42,8 @@ class OsboCfg(ctypes.Structure):
                 ('teno_store', ctypes.POINTER(ctypes.c_double)), ('Twall', ctypes.c_double),
                 ('extrap_order', (ctypes.c_int * 2) * 3), ('bc_face', (ctypes.POINTER(ctypes.c_double) * 2) * 3),
                 ('force', ctypes.c_double * 3), ('bc_free', (ctypes.c_int * 2) * 3), ('src_amp', ctypes.POINTER(ctypes.c_double)), ('src_rate', ctypes.c_double),
-                ('src_iter0', ctypes.c_int), ('central_form', ctypes.c_int)]
+                ('src_iter0', ctypes.c_int), ('curv_D', (ctypes.POINTER(ctypes.c_double) * 3) * 3),
+                ('curv_detJ', ctypes.POINTER(ctypes.c_double)), ('central_form', ctypes.c_int)]
 
 
 _lib = None
@@ -130,6 +131,16 @@ def make_cfg(plan):
                 assert a.shape == shape
                 keep.append(a)
                 arr[d] = a.ctypes.data_as(P)
+    if plan.get('curvilinear'):
+        for i in range(plan['ndim']):
+            for j in range(plan['ndim']):
+                a = np.ascontiguousarray(plan['fields']['D%d%d' % (i, j)], dtype=np.float64)
+                assert a.shape == shape
+                keep.append(a)
+                c.curv_D[i][j] = a.ctypes.data_as(P)
+        a = np.ascontiguousarray(plan['fields']['detJ'], dtype=np.float64)
+        keep.append(a)
+        c.curv_detJ = a.ctypes.data_as(P)
     ms = plan.get('mass_source')
     if ms:
         a = np.ascontiguousarray(plan['fields'][ms['field']], dtype=np.float64)

@@ -28,6 +28,8 @@ APPS = {
             [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)"), ("print_iteration_ops(NaN_check='rho_B0')", "")], 'vst_60x30'),
     'trans': (REF + '/apps/transitional_SBLI/transitional_SBLI.py',
               [("stats = True", "stats = False"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'trans_40x30x8'),
+    'ewc': (REF + '/apps/euler_wave_curvilinear/euler_wave.py',
+            [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)"), ("print_iteration_ops(NaN_check='rho_B0', every=100)", "")], 'ewc_wenoz5_32'),
     'sod_teno5': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'sod_teno5_n200'),
 }
 
@@ -72,6 +74,7 @@ def comparable(plan):
     p['metric_fields'] = plan.get('metric_fields') or [None] * plan['ndim']
     p['forcing'] = bool(plan.get('forcing'))
     p['mass_source'] = plan.get('mass_source')
+    p['curvilinear'] = bool(plan.get('curvilinear'))
     p['central_form'] = plan.get('central_form', 'blaisdell') if plan['conv'] == 'central' else None
     if plan['conv'] == 'weno':
         p['weno_formulation'] = plan.get('weno_formulation', 'JS')
@@ -154,6 +157,24 @@ def test_channel_cold_kernels_match_reference(name, fixture, sizes):
         assert np.abs(plan_num['fields'][f][s] - a[s]).max() <= 1e-11 * np.abs(a).max(), f
 
 
+def test_curvilinear_cold_data_match_reference():
+    """apps/euler_wave_curvilinear: the full metric tensor and detJ -- metric kernels plus the periodic exchanges of the cold
+    phase -- evaluated by the runner from the plan fixture equal the reference's arrays in every point incl. the halos."""
+    import numpy as np
+    from opensbli_b200 import run as R
+    workdir = os.path.join(PLANS, 'ewc')
+    if not os.path.exists(os.path.join(workdir, 'opensbli.cpp')):
+        pytest.skip('plan fixture missing')
+    plan_sym, env, plan, cold = R.load_case(workdir, overrides={'block0np0': 32, 'block0np1': 32})
+    want, states = load_fixture('ewc_wenoz5_32')
+    assert plan['curvilinear'] and plan['conv'] == 'weno' and plan['weno_formulation'] == 'Z'
+    for f in ('D00', 'D01', 'D10', 'D11', 'detJ'):
+        assert np.abs(plan['fields'][f] - want['fields'][f]).max() <= 1e-14, f
+    q0 = R.initial_state(plan_sym, cold)
+    for m in range(4):
+        assert np.abs(q0[m][5:-5, 5:-5] - states[0][m]).max() <= 1e-15
+
+
 def test_transitional_sbli_cold_data_match_reference():
     """apps/transitional_SBLI: mass-source amplitude, metrics, shock-generator table (imposed variables, used range) and the
     polynomial boundary-layer initial condition evaluated by the runner == the reference's own cold kernels (golden)."""
@@ -207,8 +228,8 @@ def test_c_expression_semantics():
 TGV = REF + '/apps/taylor_green_vortex/taylor_green_vortex.py'
 B200_LINE = ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")
 UNSUPPORTED = {
-    # full curvilinear eigensystems are not implemented
-    'curvilinear': (REF + '/apps/euler_wave_curvilinear/euler_wave.py', [B200_LINE], 'UnsupportedByB200'),
+    # another equation of state (isothermal variant of the TGV app)
+    'other_eos': (REF + '/apps/taylor_green_vortex/TGsym/TG_IsoT.py', [B200_LINE], 'constituent relation'),
     # a stress tensor with another bulk-viscosity factor: the viscous loops no longer equal the implemented terms
     'other_stress_tensor': (TGV, [B200_LINE, ("- (2/3)* KD(_i,_j)* Der(u_k,x_k)", "- (1/3)* KD(_i,_j)* Der(u_k,x_k)")], 'viscous terms added to'),
     # plain conservative central convective terms instead of the skew-symmetric split
