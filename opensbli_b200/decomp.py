@@ -7,8 +7,13 @@ recomputed in the halos, as the reference does (constituent-relation kernels run
 
 Exchange protocol per RK stage (the place where the reference has its `ops_halo_transfer`s, algorithm.py:440-442), all
 ordered on each rank's CUDA stream by flag words the neighbours write through peer pointers -- no host synchronisation:
-    kernels that read the halos -> "read done" handshake -> viscous + RK kernel, which also stores the new boundary
-    planes straight into the neighbours' halos over NVLink (CUDA IPC peer pointers) -> "pushed" handshake -> rank-local BCs
+    out-of-place stage kernels (3-D periodic-box paths): the kernel that finishes the stage also stores the new boundary
+    planes into the neighbours' Residual-role buffers over NVLink (CUDA IPC peer pointers) -> "pushed" handshake -> the
+    buffers exchange roles -> rank-local BCs;
+    in-place paths (2-D, general path with walls / metrics): kernels that read the halos -> "read done" handshake -> RK
+    update -> plane copies into the neighbours' halos -> "pushed" handshake.
+Per-point arrays of the general path (metrics, source amplitudes) and tabulated Dirichlet states are cut with the slab;
+physical boundary conditions and their one-sided closures stay with the ranks that own the face.
 The pure functions in this module (extents, neighbours, plane indices) are shared by the GPU driver and by the
 CPU (gloo) tests of the N>1 path.
 """
@@ -62,6 +67,21 @@ def local_plan(plan, rank, world):
         p['bc'][ax][0] = {'type': 'exchange'}
     if high is not None:
         p['bc'][ax][1] = {'type': 'exchange'}
+    # general path: per-point arrays (metrics, mass-source amplitude) and tabulated Dirichlet states follow the slab
+    import numpy as np
+    nd, h = plan['ndim'], 5
+    k0, _ = local_extent(plan, rank, world)
+    if plan.get('teno_adaptive'):
+        raise _plan.PlanError('slab decomposition of adaptive-TENO runs needs a halo exchange of the shock sensor: not implemented')
+    if plan.get('fields'):
+        p['fields'] = {n: np.ascontiguousarray(np.asarray(a)[k0:k0 + loc + 2 * h]) for n, a in plan['fields'].items()}
+    for d in range(nd):
+        for s in range(2):
+            b = plan['bc'][d][s]
+            if b.get('table') is not None and d != ax:
+                pd = [plan['np'][e] + 2 * h for e in range(nd) if e != d]          # tangential padded extents, x fastest
+                t = np.asarray(b['table']).reshape((-1,) + tuple(reversed(pd)))
+                p['bc'][d][s]['table'] = np.ascontiguousarray(t[:, k0:k0 + loc + 2 * h]).reshape(t.shape[0], -1)
     return _plan.validate(p)
 
 

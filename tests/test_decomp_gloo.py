@@ -63,7 +63,10 @@ def _worker(rank, world, port, fixture, nsteps, out):
     lp = local_plan(plan, rank, world)
     k0, nk = local_extent(plan, rank, world)
     low, high = neighbours(plan, rank, world)
-    q = [np.ascontiguousarray(a) for a in pad(lp, states[0][:, k0:k0 + nk])]
+    if 'q0_padded' in plan:      # general path: padded initial state, slab incl. its halo planes
+        q = [np.ascontiguousarray(a[k0:k0 + nk + 10]) for a in plan['q0_padded']]
+    else:
+        q = [np.ascontiguousarray(a) for a in pad(lp, states[0][:, k0:k0 + nk])]
     rk = [np.zeros_like(a) for a in q]
     for _ in range(nsteps):
         ou.oracle_stage(lp, q, rk, -1)
@@ -76,16 +79,22 @@ def _worker(rank, world, port, fixture, nsteps, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('fixture,world', [('tgv_teno5_16', 2), ('tgv_teno5_16', 4), ('tgv_central4_16', 2)])
+@pytest.mark.parametrize('fixture,world', [('tgv_teno5_16', 2), ('tgv_teno5_16', 4), ('tgv_central4_16', 2),
+                                           # general path: metric fields follow the slab (3-D channel, periodic slab axis) ...
+                                           ('tcf_central_16x24x12', 2), ('tcf_teno6_16x24x12', 2),
+                                           # ... and physical walls / closures stay with the ranks that own them (2-D, slabs along y)
+                                           ('lam2d_16x64', 4), ('vst_60x30', 2)])
 def test_slab_decomposition_reproduces_single_domain(fixture, world, tmp_path):
     import oracle_util as ou
     from common import load_fixture, pad, inner
     nsteps = 2
     mp.spawn(_worker, args=(world, _free_port(), fixture, nsteps, str(tmp_path)), nprocs=world, join=True)
     plan, states = load_fixture(fixture)
-    q, _ = ou.oracle_advance(plan, pad(plan, states[0]), nsteps)
+    from common import initial_padded
+    q, _ = ou.oracle_advance(plan, initial_padded(plan, states), nsteps)
     ref = inner(plan, q)
-    got = np.concatenate([np.load(os.path.join(str(tmp_path), 'q_%d.npy' % r))[:, :, 5:-5, 5:-5] for r in range(world)], axis=1)
+    cut = (slice(None), slice(None)) + (slice(5, -5),) * (plan['ndim'] - 1)
+    got = np.concatenate([np.load(os.path.join(str(tmp_path), 'q_%d.npy' % r))[cut] for r in range(world)], axis=1)
     assert got.shape == ref.shape
     assert np.array_equal(got, ref)        # same arithmetic on every point: bit-exact
 

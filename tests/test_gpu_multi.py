@@ -28,12 +28,16 @@ def _worker(rank, world, port, fixture, nsteps, out):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
-    from common import load_fixture, pad
+    from common import load_fixture, pad, initial_padded
     from opensbli_b200.decomp import DistributedSimulation
     plan, states = load_fixture(fixture)
     ds = DistributedSimulation(plan, dist, device=rank)
     k0, nk = ds.offset, ds.nloc
-    ds.set_state(pad(ds.plan, states[0][:, k0:k0 + nk]))       # collective: uploads also write the halos the neighbours push into
+    if 'q0_padded' in plan:      # general path: the padded initial state (halo values of the walls' directions matter)
+        q0 = [np.ascontiguousarray(a[k0:k0 + nk + 10]) for a in initial_padded(plan, states)]
+    else:
+        q0 = pad(ds.plan, states[0][:, k0:k0 + nk])
+    ds.set_state(q0)       # collective: uploads also write the halos the neighbours push into
     ds.step(nsteps)
     ds.barrier()
     q = ds.sim.get_state()
@@ -43,7 +47,7 @@ def _worker(rank, world, port, fixture, nsteps, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('fixture', ['tgv_teno5_16', 'tgv_central4_16'])
+@pytest.mark.parametrize('fixture', ['tgv_teno5_16', 'tgv_central4_16', 'tcf_teno6_16x24x12', 'tcf_central_16x24x12'])
 def test_two_gpu_slabs_match_single_gpu(fixture, tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
@@ -53,8 +57,9 @@ def test_two_gpu_slabs_match_single_gpu(fixture, tmp_path):
     from common import load_fixture, pad, inner
     nsteps = 3
     plan, states = load_fixture(fixture)
+    from common import initial_padded
     with opensbli_b200.Simulation(plan, device=0) as sim:
-        sim.set_state(pad(plan, states[0]))
+        sim.set_state(initial_padded(plan, states))
         sim.step(nsteps)
         ref = inner(plan, sim.get_state())
     mp.spawn(_worker, args=(2, _free_port(), fixture, nsteps, str(tmp_path)), nprocs=2, join=True)
