@@ -89,7 +89,7 @@ int osb_profile_step(osb_ctx *ctx, double *family_ms /* [OSB_NFAM] */, long long
 
 /* Multi-GPU (slab decomposition along the slowest axis): direct peer access to a neighbour's
  * arrays through CUDA IPC.  See INTEGRATION.md. */
-int osb_ipc_export(osb_ctx *ctx, void *handles /* room for (2 nq + 1) * 64 bytes: q buffers, Residual buffers, flag words */, int *nbytes);
+int osb_ipc_export(osb_ctx *ctx, void *handles /* room for (2 nq + 2) * 64 bytes: q buffers, Residual buffers, flag words, shock sensor (adaptive TENO) */, int *nbytes);
 int osb_ipc_import(osb_ctx *ctx, int side /* 0 = low neighbour, 1 = high neighbour */, const void *handles, int nbytes);
 /* push this rank's boundary planes of q into the neighbours' halo planes (peer stores over NVLink) */
 int osb_halo_push(osb_ctx *ctx);

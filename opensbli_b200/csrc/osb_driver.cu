@@ -98,6 +98,9 @@ struct osb_ctx {
   unsigned long long *flags = nullptr;          // [0] low nbr read-done, [1] low nbr pushed, [2] high nbr read-done, [3] high nbr pushed, [7] error
   unsigned long long *peer_flags[2] = {nullptr, nullptr};
   unsigned long long epoch_sig[2] = {0, 0}, epoch_wait[2] = {0, 0};
+  // adaptive TENO in a decomposed run: the sweep along the slab axis reads the shock sensor one plane below the slab
+  double *peer_theta[2] = {nullptr, nullptr};   // neighbours' theta arrays
+  unsigned long long epoch_theta = 0;           // flag slot [4]: "low neighbour has stored its top sensor plane"
   // one time step captured as a CUDA graph (launch-bound small grids): invalidated when a constant changes
   cudaGraphExec_t step_graph = nullptr;
   long long graph_launches = 0;
@@ -425,6 +428,20 @@ void launch_phase_a(osb_ctx *c, int stage = -1) {
     dim3 b(64, 2, 2);
     Launcher L(c, OSB_FAM_PRIM);
     k_theta<(ND > 1 ? ND : 2)><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc, c->plan.cl, c->gp);
+    if (has_exchange(c)) {
+      // the interface between the slab's first point and the plane below it takes C_T from the sensor of that plane
+      // (the left point of the interface): it belongs to the low neighbour, which stores it here
+      const int d = ND - 1;
+      const bool lo = c->plan.bc[d][0].kind == BC_EXCHANGE && c->peer_open[0], hi = c->plan.bc[d][1].kind == BC_EXCHANGE && c->peer_open[1];
+      const unsigned long long e = ++c->epoch_theta;
+      if (hi && c->peer_theta[1])
+        cudaMemcpyAsync(c->peer_theta[1] + (long long)(g.h - 1) * g.s[d], c->gp.theta + (long long)(g.h + g.np[d] - 1) * g.s[d],
+                        sizeof(double) * g.s[d], cudaMemcpyDeviceToDevice, c->stream);
+      k_signal<<<1, 1, 0, c->stream>>>(nullptr, hi ? c->peer_flags[1] + 4 : nullptr, e);
+      c->launches++;
+      Launcher L2(c, OSB_FAM_SYNC);
+      k_wait<<<1, 1, 0, c->stream>>>(lo ? c->flags + 4 : nullptr, nullptr, e, c->flags + 7);
+    }
   }
   if (c->plan.conv == CONV_CENTRAL) {
     dim3 b(64, 2, 2);
@@ -799,6 +816,7 @@ int osb_destroy(osb_ctx *c) {
     if (c->peer_open[s]) {
       for (int t = 0; t < 2; t++) for (int m = 0; m < 5; m++) if (c->peer_buf[s][t][m]) cudaIpcCloseMemHandle(c->peer_buf[s][t][m]);
       if (c->peer_flags[s]) cudaIpcCloseMemHandle(c->peer_flags[s]);
+      if (c->peer_theta[s]) cudaIpcCloseMemHandle(c->peer_theta[s]);
     }
   drop_graph(c);
   if (c->flags) cudaFree(c->flags);
@@ -1021,13 +1039,27 @@ int osb_ipc_export(osb_ctx *c, void *handles, int *nbytes) {
     memcpy((char *)handles + 2 * nv * sizeof(h), &h, sizeof(h));
   }
   *nbytes = (2 * nv + 1) * (int)sizeof(cudaIpcMemHandle_t);
+  if (c->gp.theta) {       // adaptive TENO: the sensor array too
+    cudaIpcMemHandle_t h;
+    OSB_CUDA(c, cudaIpcGetMemHandle(&h, c->gp.theta));
+    memcpy((char *)handles + *nbytes, &h, sizeof(h));
+    *nbytes += (int)sizeof(h);
+  }
   return 0;
 }
 int osb_ipc_import(osb_ctx *c, int side, const void *handles, int nbytes) {
   if (!c || !handles || side < 0 || side > 1) return 1;
   cudaSetDevice(c->device);
   const int nv = c->plan.nd + 2;
-  if (nbytes != (2 * nv + 1) * (int)sizeof(cudaIpcMemHandle_t)) return fail(c, "osb_ipc_import: wrong handle size");
+  const int nh = 2 * nv + 1 + (c->gp.theta ? 1 : 0);
+  if (nbytes != nh * (int)sizeof(cudaIpcMemHandle_t)) return fail(c, "osb_ipc_import: wrong handle size");
+  if (c->gp.theta) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + (2 * nv + 1) * sizeof(h), sizeof(h));
+    void *p = nullptr;
+    OSB_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_theta[side] = (double *)p;
+  }
   for (int t = 0; t < 2; t++)
     for (int m = 0; m < nv; m++) {
       cudaIpcMemHandle_t h;

@@ -71,8 +71,6 @@ def local_plan(plan, rank, world):
     import numpy as np
     nd, h = plan['ndim'], 5
     k0, _ = local_extent(plan, rank, world)
-    if plan.get('teno_adaptive'):
-        raise _plan.PlanError('slab decomposition of adaptive-TENO runs needs a halo exchange of the shock sensor: not implemented')
     if plan.get('fields'):
         p['fields'] = {n: np.ascontiguousarray(np.asarray(a)[k0:k0 + loc + 2 * h]) for n, a in plan['fields'].items()}
     for d in range(nd):

@@ -22,6 +22,28 @@ def _free_port():
     return p
 
 
+def _load(fixture):
+    """fixture, optionally repeated along z ('name*2': the slab of each of two ranks must keep >= 6 planes)"""
+    from common import load_fixture
+    name, _, rep = fixture.partition('*')
+    plan, states = load_fixture(name)
+    if rep:
+        r = int(rep)
+        tile = lambda a: np.concatenate([a[:5]] + [a[5:-5]] * r + [a[-5:]], axis=0)
+        nz, h = plan['np'][2], 5
+        plan['np'][2] = nz * r
+        plan['q0_padded'] = np.stack([tile(a) for a in plan['q0_padded']])
+        plan['fields'] = {n: tile(a) for n, a in plan['fields'].items()}
+        for pair in plan['bc'][:2]:
+            for b in pair:
+                if b.get('table') is not None:
+                    tb = np.asarray(b['table'])
+                    tb = tb.reshape(tb.shape[0], nz + 2 * h, -1)
+                    b['table'] = np.stack([tile(x) for x in tb]).reshape(tb.shape[0], -1)
+        states = {0: np.stack([a[5:-5, 5:-5, 5:-5] for a in plan['q0_padded']])}
+    return plan, states
+
+
 def _worker(rank, world, port, fixture, nsteps, out):
     import torch
     import torch.distributed as dist
@@ -30,7 +52,7 @@ def _worker(rank, world, port, fixture, nsteps, out):
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     from common import load_fixture, pad, initial_padded
     from opensbli_b200.decomp import DistributedSimulation
-    plan, states = load_fixture(fixture)
+    plan, states = _load(fixture)
     ds = DistributedSimulation(plan, dist, device=rank)
     k0, nk = ds.offset, ds.nloc
     if 'q0_padded' in plan:      # general path: the padded initial state (halo values of the walls' directions matter)
@@ -41,13 +63,14 @@ def _worker(rank, world, port, fixture, nsteps, out):
     ds.step(nsteps)
     ds.barrier()
     q = ds.sim.get_state()
-    np.save(os.path.join(out, 'q_%d.npy' % rank), np.stack([a[5:-5, 5:-5, 5:-5] for a in q]))
+    np.save(os.path.join(out, 'q_%d.npy' % rank), np.stack([a[(slice(5, -5),) * a.ndim] for a in q]))
     ds.barrier()
     ds.close()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('fixture', ['tgv_teno5_16', 'tgv_central4_16', 'tcf_teno6_16x24x12', 'tcf_central_16x24x12'])
+@pytest.mark.parametrize('fixture', ['tgv_teno5_16', 'tgv_central4_16', 'tcf_teno6_16x24x12', 'tcf_central_16x24x12',
+                                     'trans_40x30x8*2', 'katzer_60x40', 'vst_60x30'])
 def test_two_gpu_slabs_match_single_gpu(fixture, tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
@@ -56,7 +79,7 @@ def test_two_gpu_slabs_match_single_gpu(fixture, tmp_path):
     import opensbli_b200
     from common import load_fixture, pad, inner
     nsteps = 3
-    plan, states = load_fixture(fixture)
+    plan, states = _load(fixture)
     from common import initial_padded
     with opensbli_b200.Simulation(plan, device=0) as sim:
         sim.set_state(initial_padded(plan, states))
