@@ -392,7 +392,7 @@ void launch_viscous_tiled(osb_ctx *c, double a, double b) {
   auto kern = k_viscous3d_tiled<RK, FROMQ>;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vt_smem_bytes()); attr_set = true; }
-  dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + VT_ZC - 1) / VT_ZC);
+  dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + g.zlen - 1) / g.zlen);
   Launcher L(c, OSB_FAM_VISCOUS);
   kern<<<gr, bl, vt_smem_bytes(), c->stream>>>(g, c->fp, c->pc, a, b, RK == 0 ? PeerPush{} : peer_push(c, FROMQ));
 }
@@ -479,7 +479,14 @@ bool launch_phase_b(osb_ctx *c, int stage) {
     }
     dim3 b(64, 2, 2);
     Launcher L(c, OSB_FAM_VISCOUS);
-    if (c->general) k_viscous_general<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc, c->plan.cl, c->gp);
+    static const bool tiled_general = getenv("OSB_NO_TILED_GENERAL") == nullptr;
+    if (c->general && ND == 3 && tiled_general) {
+      static bool attr_set = false;
+      if (!attr_set) { cudaFuncSetAttribute(k_viscous3d_tiled_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vtg_smem_bytes()); attr_set = true; }
+      dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + g.zlen - 1) / g.zlen);
+      k_viscous3d_tiled_general<<<gr, bl, vtg_smem_bytes(), c->stream>>>(g, c->fp, c->pc, c->plan.cl, c->gp);
+    }
+    else if (c->general) k_viscous_general<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc, c->plan.cl, c->gp);
     else k_viscous<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc);
   }
   return false;
@@ -598,7 +605,7 @@ void launch_central_fused(osb_ctx *c, int stage) {
   const bool push = has_exchange(c);
   auto launch = [&](auto kern, int first) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_smem_bytes());
-    dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + VT_ZC - 1) / VT_ZC);
+    dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + g.zlen - 1) / g.zlen);
     Launcher L(c, OSB_FAM_CENTRAL);
     kern<<<gr, bl, ct_smem_bytes(), c->stream>>>(g, qi, qo, rk, c->pc, c->plan.rk_a[stage], c->plan.rk_b[stage], first, push ? peer_push(c, true) : PeerPush{});
   };
@@ -744,6 +751,12 @@ int osb_create(const char *plan_text, int device, osb_ctx **out) {
     n *= g.pd[d];
   }
   g.n = n;
+  // z-marching kernels: the longest column chunk that still gives every SM a few blocks
+  {
+    const long long columns = (long long)((g.np[0] + VT_X - 1) / VT_X) * ((g.np[1] + VT_Y - 1) / VT_Y);
+    g.zlen = 8;
+    for (int z : {32, 16}) if (columns * ((g.np[2] + z - 1) / z) >= 148 * 4) { g.zlen = z; break; }
+  }
   refresh_constants(c);
   // fields (names = reference dataset names without the _B0 suffix)
   const int nv = P.nd + 2;

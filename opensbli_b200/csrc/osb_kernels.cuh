@@ -21,6 +21,7 @@ struct GridDev {
   long long s[3];     // strides
   long long off;      // linear index of point (0,0,0)
   int h;              // storage halo
+  int zlen;           // planes per block of the z-marching kernels (32 on large grids, shorter when that leaves SMs idle)
   long long n;        // padded size
 };
 
@@ -545,9 +546,9 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled(GridDev g, F
   // z-chunks are scheduled with the two boundary chunks first: they also perform the peer stores of a decomposed run,
   // which are slower than local stores and would otherwise form the tail of the launch
   const int nzc = gridDim.z, zc = blockIdx.z == 0 ? 0 : (blockIdx.z == 1 ? nzc - 1 : (int)blockIdx.z - 1);
-  const int i0 = blockIdx.x * VT_X, j0 = blockIdx.y * VT_Y, k0 = zc * VT_ZC;
+  const int i0 = blockIdx.x * VT_X, j0 = blockIdx.y * VT_Y, k0 = zc * g.zlen;
   const int i = i0 + tx, j = j0 + ty;
-  const int kend = min(k0 + VT_ZC, g.np[2]);
+  const int kend = min(k0 + g.zlen, g.np[2]);
   const double *src[4] = {f.u[0], f.u[1], f.u[2], f.T};
   auto S = [&](int slot, int v) -> double * { return vt_smem + (size_t)(slot * 4 + v) * VT_PLANE; };
   auto load_plane = [&](int kk) {
@@ -731,9 +732,9 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 1) k_central3d_fused(GridDev g, Q
                                                                    double rkA, double rkB, int first_stage, PeerPush pp) {
   extern __shared__ double ct_smem[];
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * VT_X + tx;
-  const int i0 = blockIdx.x * VT_X, j0 = blockIdx.y * VT_Y, k0 = blockIdx.z * VT_ZC;
+  const int i0 = blockIdx.x * VT_X, j0 = blockIdx.y * VT_Y, k0 = blockIdx.z * g.zlen;
   const int i = i0 + tx, j = j0 + ty;
-  const int kend = min(k0 + VT_ZC, g.np[2]);
+  const int kend = min(k0 + g.zlen, g.np[2]);
   constexpr int NPF = (VT_PLANE + VT_X * VT_Y - 1) / (VT_X * VT_Y);
   auto S = [&](int slot, int v) -> double * { return ct_smem + (size_t)(slot * CT_NV + v) * VT_PLANE; };
   auto in_tile = [&](int e, long long &xg, int kk) -> bool {
@@ -1031,14 +1032,11 @@ __global__ void __launch_bounds__(256) k_theta(GridDev g, FieldPtrs f, PhysConst
 // katzer_SBLI.py:10-14, expanded by StoreSome.py:71-161):
 //   momentum_i += 1/Re [ sum_j d_j mu S_ij + mu ( sum_j d_jj u_i + 1/3 sum_j d_ij u_j ) ]
 //   energy     += kq [ sum_j d_j mu d_j T + mu sum_j d_jj T ] + sum_i u_i (momentum_i term) + mu/Re sum_ij S_ij d_j u_i
+// viscous terms of one point from global memory (any stencil: central or one-sided closure rows): vis[a] = momentum terms
+// (body force included), *en = energy term
 template <int ND>
-__global__ void __launch_bounds__(256) k_viscous_general(GridDev g, FieldPtrs f, PhysConst c, Closures cl, GeneralPtrs gp) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int k = blockIdx.z * blockDim.z + threadIdx.z;
-  if (i >= g.np[0] || j >= g.np[1] || k >= g.np[2]) return;
-  const long long x = g.off + i + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
-  const int id[3] = {i, j, k};
+__device__ __forceinline__ void viscous_general_point(const GridDev &g, const FieldPtrs &f, const PhysConst &c, const Closures &cl,
+                                                      const GeneralPtrs &gp, long long x, const int *id, double *vis, double *en) {
   const double iRe = 1.0 / c.Re;
   const double kq = iRe * (1.0 / (c.gama - 1.0)) * (1.0 / (c.Minf * c.Minf)) * (1.0 / c.Pr);
   double Dm[ND], SDm[ND], dmu[ND], dT[ND], dxi[ND + 1][ND], du[ND][ND];
@@ -1056,7 +1054,7 @@ __global__ void __launch_bounds__(256) k_viscous_general(GridDev g, FieldPtrs f,
 #pragma unroll
   for (int a = 0; a < ND; a++) div += du[a][a];
   const double mu = gp.mu[x];
-  double vis[ND], e = 0.0;
+  double e = 0.0;
 #pragma unroll
   for (int a = 0; a < ND; a++) {
     double s1 = 0.0, s2 = 0.0;
@@ -1082,13 +1080,155 @@ __global__ void __launch_bounds__(256) k_viscous_general(GridDev g, FieldPtrs f,
 #pragma unroll
   for (int d = 0; d < ND; d++)
     hT += dmu[d] * dT[d] + mu * (Dm[d] * Dm[d] * gd2(cl, f.T, x, g.s[d], c.inv2[d], d, id[d], g.np[d]) + Dm[d] * SDm[d] * dxi[ND][d]);
+  *en = kq * hT + e;
+}
+
+template <int ND>
+__global__ void __launch_bounds__(256) k_viscous_general(GridDev g, FieldPtrs f, PhysConst c, Closures cl, GeneralPtrs gp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = blockIdx.z * blockDim.z + threadIdx.z;
+  if (i >= g.np[0] || j >= g.np[1] || k >= g.np[2]) return;
+  const long long x = g.off + i + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
+  const int id[3] = {i, j, k};
+  double vis[ND], en;
+  viscous_general_point<ND>(g, f, c, cl, gp, x, id, vis, &en);
   double old[ND + 1];
 #pragma unroll
   for (int a = 0; a < ND + 1; a++) old[a] = f.R[1 + a][x];
   if (gp.src) f.R[0][x] += gp.src[x] * c.src_factor;      // time-periodic mass source (transitional_SBLI.py:77-89)
 #pragma unroll
   for (int a = 0; a < ND; a++) f.R[1 + a][x] = old[a] + vis[a];
-  f.R[ND + 1][x] = old[ND] + (kq * hT + e);
+  f.R[ND + 1][x] = old[ND] + en;
+}
+
+// 3-D general viscous terms, tiled: a block marches along z over a 32 x 8 column with planes k-2..k+2 of (u0, u1, u2, T, mu)
+// in shared memory.  Points whose stencils are all central (not within the closure rows of a flagged face) take every
+// derivative from shared memory; the few rows next to walls evaluate the generic per-point formulas from global memory.
+constexpr size_t vtg_smem_bytes() { return sizeof(double) * 5 * 5 * VT_PLANE; }
+__global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled_general(GridDev g, FieldPtrs f, PhysConst c, Closures cl, GeneralPtrs gp) {
+  extern __shared__ double vtg_smem[];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * VT_X + tx;
+  const int i0 = blockIdx.x * VT_X, j0 = blockIdx.y * VT_Y, k0 = blockIdx.z * g.zlen;
+  const int i = i0 + tx, j = j0 + ty;
+  const int kend = min(k0 + g.zlen, g.np[2]);
+  const double *src[5] = {f.u[0], f.u[1], f.u[2], f.T, gp.mu};
+  auto S = [&](int slot, int v) -> double * { return vtg_smem + (size_t)(slot * 5 + v) * VT_PLANE; };
+  auto load_plane = [&](int kk) {
+    const int slot = (kk + 10) % 5;
+    for (int e = tid; e < VT_PLANE; e += VT_X * VT_Y) {
+      const int yy = e / VT_HX, xx = e % VT_HX;
+      const int gi = i0 + xx - 2, gj = j0 + yy - 2;
+      if (gi < g.np[0] + 2 && gj < g.np[1] + 2) {
+        const long long x = g.off + gi + gj * g.s[1] + (long long)kk * g.s[2];
+#pragma unroll
+        for (int v = 0; v < 5; v++) S(slot, v)[e] = __ldg(src[v] + x);
+      }
+    }
+  };
+  for (int kk = k0 - 2; kk <= k0 + 2; kk++) load_plane(kk);
+  const double iRe = 1.0 / c.Re;
+  const double kq = iRe * (1.0 / (c.gama - 1.0)) * (1.0 / (c.Minf * c.Minf)) * (1.0 / c.Pr);
+  const int ce = (ty + 2) * VT_HX + tx + 2;
+  const bool active = i < g.np[0] && j < g.np[1];
+  auto near_face = [&](int d, int idx) { return (cl.on[d][0] && idx < cl.nr1) || (cl.on[d][1] && g.np[d] - 1 - idx < cl.nr1); };
+  const bool slow_xy = near_face(0, i) || near_face(1, j);
+  __syncthreads();
+  for (int k = k0; k < kend; k++) {
+    const long long x = g.off + i + j * g.s[1] + (long long)k * g.s[2];
+    if (active) {
+      double vis[3], en;
+      if (slow_xy || near_face(2, k)) {
+        const int id[3] = {i, j, k};
+        viscous_general_point<3>(g, f, c, cl, gp, x, id, vis, &en);
+      } else {
+        const double *P[5][5];
+#pragma unroll
+        for (int dz = 0; dz < 5; dz++)
+#pragma unroll
+          for (int v = 0; v < 5; v++) P[dz][v] = S((k + dz - 2 + 10) % 5, v) + ce;
+        double Dm[3], SDm[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) { Dm[d] = gp.D[d] ? gp.D[d][x] : 1.0; SDm[d] = gp.SD[d] ? gp.SD[d][x] : 0.0; }
+        double dxi[5][3], d2[4][3];
+#pragma unroll
+        for (int v = 0; v < 5; v++) {
+          const double *p = P[2][v];
+          dxi[v][0] = d1c(p[-2], p[-1], p[1], p[2], c.inv[0]);
+          dxi[v][1] = d1c(p[-2 * VT_HX], p[-VT_HX], p[VT_HX], p[2 * VT_HX], c.inv[1]);
+          dxi[v][2] = d1c(P[0][v][0], P[1][v][0], P[3][v][0], P[4][v][0], c.inv[2]);
+          if (v < 4) {
+            d2[v][0] = d2c(p[-2], p[-1], p[0], p[1], p[2], c.inv2[0]);
+            d2[v][1] = d2c(p[-2 * VT_HX], p[-VT_HX], p[0], p[VT_HX], p[2 * VT_HX], c.inv2[1]);
+            d2[v][2] = d2c(P[0][v][0], P[1][v][0], p[0], P[3][v][0], P[4][v][0], c.inv2[2]);
+          }
+        }
+        // mixed xi-derivatives: outer (higher direction) central difference of the inner (lower direction) one
+        auto mix = [&](int v, int in, int out) {
+          double r[4];
+          if (out == 1) {            // d/dy ( d/dx )
+            const double *p = P[2][v];
+            const int oy[4] = {-2 * VT_HX, -VT_HX, VT_HX, 2 * VT_HX};
+#pragma unroll
+            for (int q = 0; q < 4; q++) r[q] = d1c(p[oy[q] - 2], p[oy[q] - 1], p[oy[q] + 1], p[oy[q] + 2], c.inv[0]);
+            return d1c(r[0], r[1], r[2], r[3], c.inv[1]);
+          }
+          const int pz[4] = {0, 1, 3, 4};
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const double *p = P[pz[q]][v];
+            r[q] = in == 0 ? d1c(p[-2], p[-1], p[1], p[2], c.inv[0]) : d1c(p[-2 * VT_HX], p[-VT_HX], p[VT_HX], p[2 * VT_HX], c.inv[1]);
+          }
+          return d1c(r[0], r[1], r[2], r[3], c.inv[2]);
+        };
+        double du[3][3], dT[3], dmu[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+#pragma unroll
+          for (int a = 0; a < 3; a++) du[a][d] = Dm[d] * dxi[a][d];
+          dT[d] = Dm[d] * dxi[3][d];
+          dmu[d] = c.visc_law == 0 ? 0.0 : Dm[d] * dxi[4][d];
+        }
+        const double div = du[0][0] + du[1][1] + du[2][2];
+        const double mu = P[2][4][0];
+        double e = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+          for (int b = 0; b < 3; b++) {
+            const double Sab = du[a][b] + du[b][a] - (a == b ? (2.0 / 3.0) * div : 0.0);
+            s1 += dmu[b] * Sab;
+            const double lap = Dm[b] * Dm[b] * d2[a][b] + Dm[b] * SDm[b] * dxi[a][b];
+            if (b == a) s2 += (4.0 / 3.0) * lap;
+            else {
+              s2 += lap;
+              s2 += (1.0 / 3.0) * Dm[a] * Dm[b] * mix(b, a < b ? a : b, a < b ? b : a);
+            }
+            e += iRe * mu * Sab * du[a][b];
+          }
+          vis[a] = iRe * (s1 + mu * s2);
+          const double ua = P[2][a][0];
+          e += vis[a] * ua - c.force[a] * ua;
+          vis[a] -= c.force[a];
+        }
+        double hT = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) hT += dmu[d] * dT[d] + mu * (Dm[d] * Dm[d] * d2[3][d] + Dm[d] * SDm[d] * dxi[3][d]);
+        en = kq * hT + e;
+      }
+      double old[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) old[a] = f.R[1 + a][x];
+      if (gp.src) f.R[0][x] += gp.src[x] * c.src_factor;
+#pragma unroll
+      for (int a = 0; a < 3; a++) f.R[1 + a][x] = old[a] + vis[a];
+      f.R[4][x] = old[3] + en;
+    }
+    __syncthreads();
+    if (k + 1 < kend) load_plane(k + 3);
+    __syncthreads();
+  }
 }
 
 // General Central(4) convective terms: one-sided closures by grid index (opensblifunctions.py:523-534), diagonal
