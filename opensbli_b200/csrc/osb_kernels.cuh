@@ -2,12 +2,18 @@
 //
 // Kernel families (OSB_FAM_* in include/osbli_b200.h) and the reference loops they replace
 // (SURVEY.md section 2b / appendix A):
-//   k_prim      CRu_i, CRp, CRa, CRT                       (constituent relations, one fused pass)
-//   k_flux      LLF{Weno,Teno}_reconstruction_d + Residual (flux sweep + flux difference, fused)
-//   k_central   Convective terms group / CD / residual     (4th-order skew-symmetric, fused)
-//   k_viscous   Derivative evaluation CD + Viscous terms   (fused, mixed derivatives on the fly)
-//   k_rk_*      Save equations / Sub stage / Temporal solution advancement
-//   k_periodic  exchange{n}_block0 ; k_dirichlet  Dirichlet boundary dir d side s
+//   k_prim                     CRu_i, CRp, CRa, CRT, CRmu            (constituent relations, one fused pass)
+//   k_theta                    modified Ducros sensor (adaptive TENO)
+//   k_flux2_x / k_flux2_yz     LLF{Weno,Teno}_reconstruction_d + Residual (staged flux sweep + flux difference, fused)
+//   k_flux_curv2d / k_resid_curv2d   the same on fully curvilinear 2-D grids (metric-aware eigensystem)
+//   k_central / k_central_general    Convective terms group / CD / residual (Blaisdell / Feiereisen splits, closures, metrics)
+//   k_viscous / k_viscous_general    Derivative evaluation CD + Viscous terms (fused, mixed derivatives on the fly)
+//   k_viscous3d_tiled          3-D viscous terms + RK update (+ constituent relations from q, + peer stores of a slab run)
+//   k_viscous3d_tiled_general  3-D viscous terms with variable viscosity / metrics / closures
+//   k_central3d_fused          whole Central(4) stage in one kernel
+//   k_rk_*                     Save equations / Sub stage / Temporal solution advancement
+//   k_copy_box, k_fill_box, k_bc_*   exchange{n}_block0 and the boundary-condition kernels
+//   k_signal / k_wait          stream-ordered handshakes between the ranks of a slab decomposition
 #pragma once
 #include "osb_math.cuh"
 #include "osb_flux.cuh"
@@ -94,113 +100,7 @@ __global__ void __launch_bounds__(256) k_prim(GridDev g, FieldPtrs f, PhysConst 
 }
 
 // -------------------------------------------------------------------------------------------------
-// characteristic flux sweep, direction DIR, fused with the flux difference.
-// Interfaces of one pencil are numbered e = 0..np_DIR (interface e sits between points e-1 and e);
-// pencils are concatenated, so neighbours e-1, e are adjacent unless e % (np_DIR+1) == 0.
-// A block evaluates BT consecutive interfaces (x-sweep) or 32 lanes x RB consecutive interface rows
-// (y/z sweeps), parks the fluxes in shared memory and differences them; consecutive blocks overlap by one.
-// -------------------------------------------------------------------------------------------------
-template <int ND>
-__device__ __forceinline__ void load_point(const FieldPtrs &f, long long x, Point<ND> &P) {
-  P.rho = __ldg(f.q[0] + x);
-#pragma unroll
-  for (int d = 0; d < ND; d++) { P.m[d] = __ldg(f.q[1 + d] + x); P.u[d] = __ldg(f.u[d] + x); }
-  P.E = __ldg(f.q[ND + 1] + x);
-  P.pr = __ldg(f.p + x);
-  P.a = __ldg(f.a + x);
-}
-
-constexpr int FLUX_BT = 256;   // x-sweep: interfaces per block
-constexpr int FLUX_RB = 32;    // y/z sweeps: interface rows per block
-constexpr int FLUX_TY = 8;     // y/z sweeps: thread rows
-
-template <int ND, int RECON, int AVG, bool ACCUM>
-__global__ void __launch_bounds__(FLUX_BT) k_flux_x(GridDev g, FieldPtrs f, PhysConst c, SchemeParams sp) {
-  constexpr int NV = ND + 2;
-  __shared__ double sF[NV][FLUX_BT];
-  const int t = threadIdx.x;
-  const long long NI = g.np[0] + 1;
-  const long long E = NI * g.np[1] * g.np[2];
-  const long long e = (long long)blockIdx.x * (FLUX_BT - 1) + t;
-  const bool valid = e < E;
-  long long x = 0;
-  int ie = 0;
-  if (valid) {
-    ie = (int)(e % NI);
-    const long long row = e / NI;
-    const int j = (int)(row % g.np[1]), k = (int)(row / g.np[1]);
-    x = g.off + (ie - 1) + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
-    Point<ND> pt[6];
-#pragma unroll
-    for (int p = 0; p < 6; p++) load_point<ND>(f, x + (p - 2), pt[p]);
-    double fl[NV];
-    interface_flux<ND, 0, RECON, AVG>(pt, c.gama, sp, fl);
-#pragma unroll
-    for (int m = 0; m < NV; m++) sF[m][t] = fl[m];
-  }
-  __syncthreads();
-  if (valid && t > 0 && ie != 0) {
-    // interface ie lies between points ie-1 and ie, interface ie-1 between ie-2 and ie-1: together they
-    // bound point ie-1, which is the left point x of this thread's interface.
-#pragma unroll
-    for (int m = 0; m < NV; m++) {
-      const double r = -c.inv[0] * (sF[m][t] - sF[m][t - 1]);
-      if (ACCUM) f.R[m][x] += r; else f.R[m][x] = r;
-    }
-  }
-}
-
-template <int ND, int DIR, int RECON, int AVG, bool ACCUM>
-__global__ void __launch_bounds__(32 * FLUX_TY) k_flux_yz(GridDev g, FieldPtrs f, PhysConst c, SchemeParams sp) {
-  constexpr int NV = ND + 2;
-  constexpr int OTH = (DIR == 1) ? 2 : 1;            // the other non-x direction
-  __shared__ double sF[FLUX_RB][NV][32];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int i = blockIdx.y * 32 + tx;
-  const long long NJ = g.np[DIR] + 1;
-  const long long nother = (ND > 2) ? g.np[OTH] : 1;
-  const long long ER = NJ * nother;
-  const long long r0 = (long long)blockIdx.x * (FLUX_RB - 1);
-  const bool xin = i < g.np[0];
-#pragma unroll 1
-  for (int it = 0; it < FLUX_RB / FLUX_TY; it++) {
-    const int r = ty + FLUX_TY * it;
-    const long long er = r0 + r;
-    if (xin && er < ER) {
-      const int je = (int)(er % NJ);
-      const int o = (int)(er / NJ);
-      const long long x = g.off + i + (long long)(je - 1) * g.s[DIR] + (ND > 2 ? o * g.s[OTH] : 0);
-      Point<ND> pt[6];
-#pragma unroll
-      for (int p = 0; p < 6; p++) load_point<ND>(f, x + (p - 2) * g.s[DIR], pt[p]);
-      double fl[NV];
-      interface_flux<ND, DIR, RECON, AVG>(pt, c.gama, sp, fl);
-#pragma unroll
-      for (int m = 0; m < NV; m++) sF[r][m][tx] = fl[m];
-    }
-  }
-  __syncthreads();
-#pragma unroll 1
-  for (int it = 0; it < FLUX_RB / FLUX_TY; it++) {
-    const int r = ty + FLUX_TY * it;
-    const long long er = r0 + r;
-    if (xin && r > 0 && er < ER) {
-      const int je = (int)(er % NJ);
-      if (je != 0) {
-        const int o = (int)(er / NJ);
-        const long long x = g.off + i + (long long)(je - 1) * g.s[DIR] + (ND > 2 ? o * g.s[OTH] : 0);
-#pragma unroll
-        for (int m = 0; m < NV; m++) {
-          const double rr = -c.inv[DIR] * (sF[r][m][tx] - sF[r - 1][m][tx]);
-          if (ACCUM) f.R[m][x] += rr; else f.R[m][x] = rr;
-        }
-      }
-    }
-  }
-}
-
-// -------------------------------------------------------------------------------------------------
-// v2 flux sweeps: the block first stages its points (conserved variables + constituent relations evaluated once
+// Flux sweeps: the block first stages its points (conserved variables + constituent relations evaluated once
 // per point: 1/rho, p, a) in shared memory, then every thread evaluates interface fluxes from the staged window,
 // parks them in shared memory and differences them.  Points are numbered along the sweep direction including 3
 // halo points on both sides (-3 .. np+2) and pencils are concatenated, so a block is simply a run of consecutive
