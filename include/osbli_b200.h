@@ -83,9 +83,21 @@ int osb_advance_host(osb_ctx *ctx, const double *const *q_in, double *const *q_o
 /* Instrumentation: number of kernels launched by this context so far; per-family device time of
  * one profiled step (events around each launch).  Families: see OSB_FAM_*. */
 enum { OSB_FAM_PRIM = 0, OSB_FAM_FLUX = 1, OSB_FAM_CENTRAL = 2, OSB_FAM_VISCOUS = 3, OSB_FAM_RK = 4, OSB_FAM_BC = 5,
-       OSB_FAM_SYNC = 6 /* waiting for neighbour ranks */, OSB_NFAM = 7 };
+       OSB_FAM_SYNC = 6 /* waiting for neighbour ranks */, OSB_FAM_USER = 7 /* run-time compiled user kernels */, OSB_NFAM = 8 };
 int osb_launch_count(const osb_ctx *ctx, long long *count);
 int osb_profile_step(osb_ctx *ctx, double *family_ms /* [OSB_NFAM] */, long long *family_launches /* [OSB_NFAM] */);
+
+/* Point-wise user kernels (the reference's `User kernel` loops, e.g. the statistics accumulation of
+ * apps/channel_flow/*: stats.py, opsc.py kernel emission): app-specific arithmetic outside the solver's hot loops, given as
+ * CUDA C source of one `extern "C" __global__` entry with the signature
+ *     entry(long long off, int n0, int n1, int n2, int lo0, int lo1, int lo2, long long s1, long long s2, UserFields f)
+ * where `struct UserFields { double *p[OSB_MAX_USER_FIELDS]; }` holds the arrays named in `fields` (comma separated; unknown
+ * names are created zero-initialised, as OPS declares datasets).  Compiled once with NVRTC for sm_100a.
+ * when = 0: launched at the end of every iteration of osb_step (after the last stage's boundary conditions);
+ * when = 1: launched by osb_run_user_kernels(ctx, 1) (loops after the time loop). */
+enum { OSB_MAX_USER_FIELDS = 48 };
+int osb_add_user_kernel(osb_ctx *ctx, const char *cuda_source, const char *entry, const char *fields, const int range[6], int when);
+int osb_run_user_kernels(osb_ctx *ctx, int when);
 
 /* Multi-GPU (slab decomposition along the slowest axis): direct peer access to a neighbour's
  * arrays through CUDA IPC.  See INTEGRATION.md. */

@@ -98,6 +98,52 @@ class _Printer(object):
         return self.p.doprint(expr)
 
 
+def _user_kernel(kernel, when):
+    """A point-wise user kernel (statistics accumulation, e.g. channel_flow/*/stats.py; `User kernel` in the algorithm): an
+    ordered list of assignments [lhs, is_dataset, rhs in C] over the kernel's range.  It is compiled at run time (NVRTC) --
+    app-specific arithmetic outside the solver's hot loops cannot be hand-written.  Only accesses at the point itself."""
+    from sympy.printing.c import C99CodePrinter, ccode
+    from opensbli.core.opensbliobjects import DataSet
+
+    class P(C99CodePrinter):
+        def _print_DataSet(s, e):
+            if any(int(i) != 0 for i in e.indices):
+                raise UnsupportedByB200('user kernel %s reads %s at an offset: only point-wise user kernels are implemented' % (_name(kernel), e))
+            return '%s[X]' % _strip(e.base)
+
+        def _print_Indexed(s, e):
+            if type(e).__name__ == 'DataSet':
+                return s._print_DataSet(e)
+            return C99CodePrinter._print_Indexed(s, e)
+
+        def _print_Rational(s, e):
+            return '(%d.0/%d.0)' % (e.p, e.q)
+
+    pr = P({'precision': 17})
+    out, reads, writes, local = [], [], [], []
+    for e in kernel.equations:
+        if not hasattr(e, 'lhs'):
+            raise UnsupportedByB200('user kernel %s: unsupported equation %r' % (_name(kernel), e))
+        for ds in e.rhs.atoms(DataSet):
+            n = _strip(ds.base)
+            if n not in reads:
+                reads.append(n)
+        if type(e.lhs).__name__ == 'DataSet':
+            if any(int(i) != 0 for i in e.lhs.indices):
+                raise UnsupportedByB200('user kernel %s writes at an offset' % _name(kernel))
+            n = _strip(e.lhs.base)
+            if n not in writes:
+                writes.append(n)
+            out.append([n, True, pr.doprint(e.rhs)])
+        else:
+            local.append(str(e.lhs))
+            out.append([str(e.lhs), False, pr.doprint(e.rhs)])
+    consts = sorted(set(str(s) for e in kernel.equations for s in e.rhs.free_symbols
+                        if type(s).__name__ == 'ConstantObject'))
+    return {'name': _name(kernel), 'when': when, 'range': [ccode(r) for r in kernel.total_range()], 'reads': reads,
+            'writes': writes, 'locals': local, 'constants': consts, 'statements': out}
+
+
 def _cold_kernel(kernel):
     """A cold (one-off or boundary-value) kernel as data: its iteration range (C expressions in block0np{d}) and an
     ordered list of assignments  [lhs name, lhs offset or None for a kernel-local variable, rhs in numpy syntax]."""
@@ -785,13 +831,27 @@ def extract_plan(algorithm):
     flat = []
     _walk(algorithm.prg.components, flat)
     before, in_iter, in_stage, after = [], [], [], []
+    seen_loop = False
     for path, c in flat:
         loops = [type(p).__name__ for p in path]
         nloops = loops.count('DoLoop')
-        (before if nloops == 0 and 'Timers' not in loops else in_iter if nloops == 1 else in_stage if nloops == 2 else after).append(c)
-        if nloops == 0 and 'Timers' in loops:
+        seen_loop = seen_loop or 'Timers' in loops or nloops > 0
+        if nloops == 0 and 'Timers' not in loops:
+            (after if seen_loop else before).append(c)          # top level: before / after the timed time loop
+        elif nloops == 1:
+            in_iter.append(c)
+        elif nloops == 2:
+            in_stage.append(c)
+        else:
             after.append(c)
     plan = {'ndim': ndim, 'viscous': False, 'averaging': 'roe', 'weno_formulation': 'JS'}
+    user = []
+    for c in in_iter:
+        if type(c).__name__ == 'Kernel' and _name(c).startswith('User kernel'):
+            user.append(_user_kernel(c, 'iteration_end'))
+    for c in after:
+        if type(c).__name__ == 'Kernel' and _name(c).startswith('User kernel'):
+            user.append(_user_kernel(c, 'after_loop'))
     # components of the program that are not part of the per-step hot path (file output, monitors, timers): not executed
     # by the B200 run-time; listed in the plan and printed so that nothing is dropped silently
     plan['not_executed'] = sorted(set(type(c).__name__ for c in in_iter + after + before
@@ -946,6 +1006,7 @@ def extract_plan(algorithm):
         cold.append(source_cold)
         plan['mass_source'] = mass_source
     plan['cold'] = cold
+    plan['user_kernels'] = user
     plan['q_names'] = q_names
 
     # ---- constants, in declaration order (opsc.py:625-654)

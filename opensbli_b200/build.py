@@ -8,7 +8,7 @@ DEPS = [SRC, os.path.join(HERE, 'csrc', 'osb_kernels.cuh'), os.path.join(HERE, '
         os.path.join(os.path.dirname(HERE), 'include', 'osbli_b200.h')]
 LIB = os.path.join(HERE, 'libosbli_b200.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-shared']
+              '-Xcompiler', '-fPIC', '-shared', '-ldl']
 
 
 def up_to_date():

@@ -5,6 +5,7 @@
 //   per iteration: BC kernels/exchanges (dir0 side0, dir0 side1, dir1 side0, ...) ; [rk_sbli: save]
 //   per stage:     constituent relations ; spatial kernels ; RK update ; BC kernels/exchanges
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -106,6 +107,8 @@ struct osb_ctx {
   long long graph_launches = 0;
   bool use_graph = true;
   long long iteration = 0;                      // loop counter of algorithm.py:440-474 (argument of the mass source)
+  struct UserKernel { cudaLibrary_t lib = nullptr; cudaKernel_t kern = nullptr; std::vector<std::string> fields; int range[6]; int when = 0; };
+  std::vector<UserKernel> user_kernels;
   bool prim_stale = false;                      // u, p, a, T arrays lag the state (stage kernels that derive them on the fly)
   int swap_parity = 0;                          // fused central path: q and Residual buffers exchange roles every stage
 };
@@ -614,6 +617,30 @@ void launch_central_fused(osb_ctx *c, int stage) {
   swap_q_and_residual(c);
 }
 
+// ---- run-time compiled point-wise user kernels ---------------------------------------------------
+struct UserFields { double *p[OSB_MAX_USER_FIELDS]; };
+
+int run_user_kernels(osb_ctx *c, int when) {
+  const GridDev &g = c->grid;
+  for (auto &k : c->user_kernels) {
+    if (k.when != when) continue;
+    UserFields uf{};
+    for (size_t i = 0; i < k.fields.size(); i++) {
+      Field *f = find_field(c, k.fields[i].c_str());
+      if (!f) return fail(c, "user kernel field vanished: " + k.fields[i]);
+      uf.p[i] = f->dev;                      // looked up per launch: the q / Residual buffers exchange roles
+    }
+    int lo[3] = {0, 0, 0}, n[3] = {1, 1, 1};
+    for (int d = 0; d < g.nd; d++) { lo[d] = k.range[2 * d]; n[d] = k.range[2 * d + 1] - k.range[2 * d]; }
+    long long off = g.off, s1 = g.nd > 1 ? g.s[1] : 0, s2 = g.nd > 2 ? g.s[2] : 0;
+    void *args[] = {&off, &n[0], &n[1], &n[2], &lo[0], &lo[1], &lo[2], &s1, &s2, &uf};
+    dim3 bl(128, 1, 1), gr((n[0] + 127) / 128, n[1], n[2]);
+    Launcher L(c, OSB_FAM_USER);
+    OSB_CUDA(c, cudaLaunchKernel((const void *)k.kern, gr, bl, args, 0, c->stream));
+  }
+  return 0;
+}
+
 // One stage of the loop (s < 0: iteration start).  In a decomposed run the neighbour exchange is part of the stage and is
 // ordered on the stream by flag words, so a whole run can be enqueued without host synchronisation:
 //   phase A (reads halos) -> "read done" handshake -> phase B + RK (+ fused peer push) -> "pushed" handshake -> local BCs
@@ -631,6 +658,7 @@ int stage_nd(osb_ctx *c, int s) {
       launch_bcs(c);
       if (ex) { if (push_planes_memcpy(c)) return 1; neighbour_signal(c, 1); neighbour_wait(c, 1); }
     }
+    if (s == (int)c->plan.rk_a.size() - 1 && run_user_kernels(c, 0)) return 1;
     OSB_CUDA(c, cudaGetLastError());
     return 0;
   }
@@ -651,6 +679,7 @@ int stage_nd(osb_ctx *c, int s) {
       if (ex) { if (push_planes_memcpy(c)) return 1; neighbour_signal(c, 1); neighbour_wait(c, 1); }
     }
   }
+  if (s == (int)c->plan.rk_a.size() - 1 && run_user_kernels(c, 0)) return 1;
   OSB_CUDA(c, cudaGetLastError());
   return 0;
 }
@@ -832,6 +861,7 @@ int osb_destroy(osb_ctx *c) {
       if (c->peer_theta[s]) cudaIpcCloseMemHandle(c->peer_theta[s]);
     }
   drop_graph(c);
+  for (auto &k : c->user_kernels) if (k.lib) cudaLibraryUnload(k.lib);
   if (c->flags) cudaFree(c->flags);
   for (auto &f : c->fields) cudaFree(f.dev);
   for (int d = 0; d < 3; d++) for (int s = 0; s < 2; s++) if (c->face_table[d][s]) cudaFree(c->face_table[d][s]);
@@ -848,6 +878,70 @@ int osb_set_const_f64(osb_ctx *c, const char *name, double v) {
   drop_graph(c);          // constants are baked into the captured kernel arguments
   return 0;
 }
+int osb_add_user_kernel(osb_ctx *c, const char *source, const char *entry, const char *fields, const int range[6], int when) {
+  if (!c || !source || !entry || !fields || !range) return 1;
+  cudaSetDevice(c->device);
+  osb_ctx::UserKernel k;
+  k.when = when;
+  for (int i = 0; i < 6; i++) k.range[i] = range[i];
+  {
+    std::stringstream ss(fields);
+    std::string n;
+    while (std::getline(ss, n, ',')) if (!n.empty()) k.fields.push_back(n);
+  }
+  if (k.fields.size() > OSB_MAX_USER_FIELDS) return fail(c, "user kernel uses too many arrays");
+  for (auto &n : k.fields)
+    if (!find_field(c, n.c_str())) {          // a dataset of the user kernel only (e.g. a running mean): zero-initialised
+      Field f; f.name = n;
+      OSB_CUDA(c, cudaMalloc(&f.dev, sizeof(double) * c->grid.n));
+      OSB_CUDA(c, cudaMemsetAsync(f.dev, 0, sizeof(double) * c->grid.n, c->stream));
+      c->fields.push_back(f);
+    }
+  // NVRTC is loaded on demand: the library itself must not depend on it (it also loads on hosts without a driver)
+  typedef int (*create_t)(void **, const char *, const char *, int, const char *const *, const char *const *);
+  typedef int (*compile_t)(void *, int, const char *const *);
+  typedef int (*size_t_fn)(void *, size_t *);
+  typedef int (*get_t)(void *, char *);
+  typedef int (*destroy_t)(void **);
+  void *h = dlopen("libnvrtc.so.12", RTLD_NOW);
+  if (!h) h = dlopen("libnvrtc.so", RTLD_NOW);
+  if (!h) h = dlopen("/usr/local/cuda/lib64/libnvrtc.so", RTLD_NOW);
+  if (!h) return fail(c, std::string("osb_add_user_kernel: cannot load NVRTC: ") + dlerror());
+  auto create = (create_t)dlsym(h, "nvrtcCreateProgram");
+  auto compile = (compile_t)dlsym(h, "nvrtcCompileProgram");
+  auto log_size = (size_t_fn)dlsym(h, "nvrtcGetProgramLogSize");
+  auto get_log = (get_t)dlsym(h, "nvrtcGetProgramLog");
+  auto bin_size = (size_t_fn)dlsym(h, "nvrtcGetCUBINSize");
+  auto get_bin = (get_t)dlsym(h, "nvrtcGetCUBIN");
+  auto destroy = (destroy_t)dlsym(h, "nvrtcDestroyProgram");
+  if (!create || !compile || !log_size || !get_log || !bin_size || !get_bin || !destroy) return fail(c, "osb_add_user_kernel: NVRTC symbols missing");
+  void *prog = nullptr;
+  if (create(&prog, source, "osb_user_kernel.cu", 0, nullptr, nullptr)) return fail(c, "nvrtcCreateProgram failed");
+  const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false"};
+  const int rc = compile(prog, 3, opts);
+  if (rc) {
+    size_t ls = 0; log_size(prog, &ls);
+    std::string log(ls, ' ');
+    if (ls) get_log(prog, &log[0]);
+    destroy(&prog);
+    return fail(c, "user kernel does not compile:\n" + log);
+  }
+  size_t bs = 0; bin_size(prog, &bs);
+  std::vector<char> bin(bs);
+  get_bin(prog, bin.data());
+  destroy(&prog);
+  OSB_CUDA(c, cudaLibraryLoadData(&k.lib, bin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  OSB_CUDA(c, cudaLibraryGetKernel(&k.kern, k.lib, entry));
+  c->user_kernels.push_back(k);
+  drop_graph(c);
+  return 0;
+}
+int osb_run_user_kernels(osb_ctx *c, int when) {
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  return run_user_kernels(c, when);
+}
+
 int osb_set_iteration(osb_ctx *c, long long iteration) {
   if (!c || iteration < 0) return 1;
   c->iteration = iteration;

@@ -7,6 +7,7 @@ cold initialisation kernel with numpy on the host, runs `niter` steps on the GPU
 opensbli_output.npz (conserved fields, reference layout incl. halos)."""
 import ast
 import json
+import re
 import math
 import os
 import sys
@@ -127,6 +128,31 @@ class ColdRunner(object):
         return lo, hi
 
 
+def user_kernel_source(k, index, env, nd):
+    """CUDA C of one point-wise user kernel (entry signature: include/osbli_b200.h, osb_add_user_kernel)."""
+    fields = list(k['reads']) + [w for w in k['writes'] if w not in k['reads']]
+    entry = 'osb_user_kernel_%d' % index
+    text = ' '.join(s[2] for s in k['statements'])
+    L = ['struct UserFields { double *p[48]; };']
+    for name, val in env.items():                       # the constants the statements mention, as the reference's C globals
+        if re.search(r'\b%s\b' % re.escape(name), text):
+            L.append('#define %s (%s)' % (name, repr(float(val))))
+    L += ['extern "C" __global__ void %s(long long off, int n0, int n1, int n2, int lo0, int lo1, int lo2, long long s1, long long s2, UserFields f) {' % entry,
+          '  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;',
+          '  if (i >= n0 || j >= n1 || k >= n2) return;',
+          '  const long long X = off + (lo0 + i) + (lo1 + j) * s1 + (lo2 + k) * s2;']
+    for n, name in enumerate(fields):
+        L.append('  double *%s = f.p[%d];' % (name, n))
+    for name in dict.fromkeys(k['locals']):
+        L.append('  double %s;' % name)
+    for lhs, is_field, rhs in k['statements']:
+        L.append('  %s%s = %s;' % (lhs, '[X]' if is_field else '', rhs))
+    L.append('}')
+    rng = [int(c_eval(r, env)) for r in k['range']]
+    return {'name': k['name'], 'entry': entry, 'source': '\n'.join(L) + '\n', 'fields': fields, 'range': rng, 'when': k['when'],
+            'writes': list(k['writes'])}
+
+
 def resolve(plan_sym, env):
     """symbolic plan + parameter values -> numeric plan accepted by opensbli_b200.Simulation (cold kernels evaluated:
     metric fields, tabulated Dirichlet states); returns (plan, ColdRunner holding every cold dataset)."""
@@ -147,6 +173,7 @@ def resolve(plan_sym, env):
         if name:
             for f in (name, 'S' + name + str(d)):
                 p['fields'][f] = cold.array(f).copy()
+    p['user_kernels'] = [user_kernel_source(k, n, env, nd) for n, k in enumerate(plan_sym.get('user_kernels', []))]
     if plan_sym.get('curvilinear'):
         for f in ['D%d%d' % (i, j) for i in range(nd) for j in range(nd)] + ['detJ']:
             p['fields'][f] = cold.array(f).copy()
@@ -203,9 +230,12 @@ def main(argv=None):
     with Simulation(plan_num) as sim:
         sim.set_state(q0)
         ms = sim.step_timed(niter) if niter > 0 else 0.0
+        if any(k['when'] == 'after_loop' for k in plan_num.get('user_kernels', [])):
+            sim.run_user_kernels('after_loop')                  # loops after the time loop (e.g. statistics / niter)
         q = sim.get_state()
+        extra = {w: sim.download(w) for k in plan_num.get('user_kernels', []) for w in k['writes']}
     print('Total Wall time %f' % (ms * 1e-3))      # same span as the reference's Timers (algorithm.py:301-327)
-    np.savez(os.path.join(workdir, 'opensbli_output.npz'), **{n: a for n, a in zip(plan_sym['q_names'], q)})
+    np.savez(os.path.join(workdir, 'opensbli_output.npz'), **{n: a for n, a in zip(plan_sym['q_names'], q)}, **extra)
     return 0
 
 

@@ -63,6 +63,8 @@ CONFIGS = {
         ("LLFWeno(weno_order, formulation='Z', averaging=Avg)", "LLFTeno(5, averaging=Avg)"),
         ("'Delta0block0', 'Delta1block0']", "'Delta0block0', 'Delta1block0', 'eps', 'TENO_CT']"),
         ("'2.0/(block0np0)', '2.0/(block0np1)']", "'2.0/(block0np0)', '2.0/(block0np1)', '1e-15', '1e-6']")]),
+    # the same channel app exactly as shipped, i.e. with its statistics-gathering user kernels (stats.py) switched on
+    'tcf_teno6_stats': (REF + '/apps/channel_flow/compressible_TCF_TENO/turbulent_channel.py', []),
     # symmetry boundaries: shipped 1/8-domain TGV (central-4 + RK3, SymmetryBC on all six faces)
     'tgv_sym': (REF + '/apps/taylor_green_vortex/TGsym/TGsym.py', []),
 }
@@ -112,7 +114,11 @@ def generate(name):
     import refshim
     refshim.install(REF)
     import opensbli.utilities.helperfunctions as H
+    original = H.substitute_simulation_parameters
     H.substitute_simulation_parameters = env_substitute
+    for mod in list(sys.modules.values()):      # star-imports (e.g. `from opensbli import *` in an app's stats.py) re-export the original
+        if getattr(mod, 'substitute_simulation_parameters', None) is original:
+            mod.substitute_simulation_parameters = env_substitute
     src = open(app).read()
     for old, new in edits:
         assert old in src, (name, old)

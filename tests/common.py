@@ -38,6 +38,9 @@ def load_fixture(name):
             plan['bc'][d][s]['table'] = z[k]
     if 'q0_padded' in z.files:
         plan['q0_padded'] = z['q0_padded']
+    stats = {k[5:]: z[k] for k in z.files if k.startswith('stat_')}
+    if stats:
+        plan['stats_golden'] = stats
     return plan, states
 
 

@@ -209,7 +209,12 @@ def ewc_plan(N, conv='weno'):
     return p
 
 
+STATS = ['rhomean', 'E_mean', 'u0mean', 'u1u0mean', 'u2u2mean', 'p_mean', 'pp_mean', 'a_mean', 'T_mean', 'TT_mean', 'mu_mean', 'M_mean',
+         'rhou1u0mean', 'rhou2u2mean']
+
 if os.path.isdir('/root/reference'):
+    # the channel app as shipped (statistics on): the running sums after 5 steps, divided by niter by the loop after the time loop
+    FIXTURES['tcf_teno6_stats_16x24x12'] = ('tcf_teno6_stats', tcf_teno6_plan(16, 24, 12), [5])
     FIXTURES['ewc_wenoz5_32'] = ('ewc', ewc_plan(32), [1, 10])
     FIXTURES['ewc_teno5_32'] = ('ewc_teno5', ewc_plan(32, 'teno'), [1, 10])
     FIXTURES['trans_40x30x8'] = ('trans', trans_plan(40, 30, 8), [1, 5, 20])
@@ -259,8 +264,11 @@ def main():
                 out['field_BF_amp'] = 2.5e-3 * np.exp(-(rx['x0'] - 20.0) ** 2 - (rx['x1'] - 4.0) ** 2) * np.cos(0.23 * rx['x2'])
         out['q0'] = np.stack([r[f][inner] for f in fields])
         for n in steps:
-            r = run_ref(config, dict(env_params(plan), niter=n), fields)
+            stats = STATS if config.endswith('_stats') else []
+            r = run_ref(config, dict(env_params(plan), niter=n), fields + stats, dump_all=bool(stats))
             out['q%d' % n] = np.stack([r[f][inner] for f in fields])
+            for s in stats:
+                out['stat_' + s] = r[s][inner]
         path = os.path.join(HERE, name + '.npz')
         np.savez_compressed(path, **out)
         print(name, {k: v.shape for k, v in out.items() if k.startswith('q')}, '%.1f kB' % (os.path.getsize(path) / 1e3))

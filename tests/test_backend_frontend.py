@@ -30,6 +30,9 @@ APPS = {
               [("stats = True", "stats = False"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'trans_40x30x8'),
     'ewc': (REF + '/apps/euler_wave_curvilinear/euler_wave.py',
             [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)"), ("print_iteration_ops(NaN_check='rho_B0', every=100)", "")], 'ewc_wenoz5_32'),
+    # the channel app exactly as shipped: statistics gathering (`User kernel` loops of stats.py) switched on
+    'tcf_teno6_stats': (REF + '/apps/channel_flow/compressible_TCF_TENO/turbulent_channel.py',
+                        [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)"), ("print_iteration_ops()", "")], 'tcf_teno6_stats_16x24x12'),
     'sod_teno5': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'sod_teno5_n200'),
 }
 
@@ -155,6 +158,21 @@ def test_channel_cold_kernels_match_reference(name, fixture, sizes):
     # copies them into the periodic halos, which nothing reads)
     for f, a in want.get('fields', {}).items():
         assert np.abs(plan_num['fields'][f][s] - a[s]).max() <= 1e-11 * np.abs(a).max(), f
+
+
+def test_user_kernels_become_cuda_source():
+    """Statistics loops of the shipped channel app: distilled as point-wise user kernels and printed as CUDA C by the runner."""
+    from opensbli_b200 import run as R
+    workdir = os.path.join(PLANS, 'tcf_teno6_stats')
+    if not os.path.exists(os.path.join(workdir, 'opensbli.cpp')):
+        pytest.skip('plan fixture missing')
+    plan_sym, env, plan, cold = R.load_case(workdir, overrides={'block0np0': 16, 'block0np1': 24, 'block0np2': 12, 'niter': 5})
+    uk = plan['user_kernels']
+    assert [k['when'] for k in uk] == ['iteration_end', 'after_loop']
+    acc, norm = uk
+    assert acc['range'] == [0, 16, 0, 24, 0, 12] and 'u0u0mean' in acc['writes'] and 'rho' in acc['fields']
+    assert 'extern "C" __global__ void osb_user_kernel_0(' in acc['source'] and 'u0u0mean[X] = ' in acc['source']
+    assert '#define niter (5.0)' in norm['source'] and 'rhomean[X] = rhomean[X]/niter;' in norm['source']
 
 
 def test_curvilinear_cold_data_match_reference():

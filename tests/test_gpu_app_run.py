@@ -118,3 +118,26 @@ def test_transitional_sbli_app_from_plan_fixture():
     qo, _ = ou.oracle_advance(plan, [a.copy() for a in q0], 20)
     err = field_errors(plan, inner(plan, q), inner(plan, qo))
     assert max(err) < 1e-11, err
+
+
+def test_channel_app_with_statistics_as_shipped():
+    """apps/channel_flow/compressible_TCF_TENO/turbulent_channel.py with its statistics gathering on (the app as shipped): the
+    `User kernel` loops are compiled at run time (NVRTC) and run at the end of every iteration / after the time loop; the
+    running means after 5 steps equal the reference's own."""
+    from opensbli_b200 import run as R, Simulation
+    over = {'block0np0': 16, 'block0np1': 24, 'block0np2': 12, 'niter': 5}
+    plan_sym, env, plan, cold = R.load_case(os.path.join(PLANS, 'tcf_teno6_stats'), overrides=over)
+    want, states = load_fixture('tcf_teno6_stats_16x24x12')
+    q0 = R.initial_state(plan_sym, cold)
+    with Simulation(plan) as sim:
+        sim.set_state(q0)
+        sim.step(5)
+        sim.run_user_kernels('after_loop')
+        q = sim.get_state()
+        stats = {n: sim.download(n)[5:-5, 5:-5, 5:-5] for n in want['stats_golden']}
+        prof = sim.profile_step()
+    assert prof['user']['launches'] == 1
+    err = field_errors(plan, inner(plan, q), states[5])
+    assert max(err) < 1e-11, err
+    for n, ref in want['stats_golden'].items():
+        assert np.abs(stats[n] - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), n
