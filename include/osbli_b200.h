@@ -49,6 +49,9 @@ const char *osb_field_name(const osb_ctx *ctx, int index);
 int osb_field_info(const osb_ctx *ctx, const char *name, int *dims, int *halo_m, int *halo_p);
 int osb_upload(osb_ctx *ctx, const char *name, const double *host_padded);
 int osb_download(osb_ctx *ctx, const char *name, double *host_padded);
+/* One value of a dataset at grid index (i, j, k) (unused indices 0): what the reference's SimulationMonitor reads with a
+ * one-point reduction loop (simulation_monitors.py:17-160).  Synchronises the stream. */
+int osb_read_point(osb_ctx *ctx, const char *name, int i, int j, int k, double *value);
 int osb_device_ptr(osb_ctx *ctx, const char *name, double **device_ptr);
 /* State imposed by a `dirichlet_field` boundary (equations of a DirichletBC that depend on the position along the face,
  * dirichlet.py:28-41): table[m][t], m < ndim+2, t = padded tangential index (the field index with dimension dir removed). */

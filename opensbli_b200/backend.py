@@ -845,6 +845,13 @@ def extract_plan(algorithm):
         else:
             after.append(c)
     plan = {'ndim': ndim, 'viscous': False, 'averaging': 'roe', 'weno_formulation': 'JS'}
+    monitor = None
+    for c in in_iter:
+        if type(c).__name__ == 'SimulationMonitor':
+            # probes of dataset values printed every `frequency` iterations (simulation_monitors.py:17-160, algorithm.py:433-437)
+            monitor = {'arrays': [_strip(m.flow_var) for m in c.monitors],
+                       'probes': [[str(x) for x in (m.probe_loc if isinstance(m.probe_loc, (tuple, list)) else (m.probe_loc,))] for m in c.monitors],
+                       'frequency': int(c.frequency), 'precision': int(c.fp_precision), 'output_file': c.output_file}
     user = []
     for c in in_iter:
         if type(c).__name__ == 'Kernel' and _name(c).startswith('User kernel'):
@@ -855,7 +862,7 @@ def extract_plan(algorithm):
     # components of the program that are not part of the per-step hot path (file output, monitors, timers): not executed
     # by the B200 run-time; listed in the plan and printed so that nothing is dropped silently
     plan['not_executed'] = sorted(set(type(c).__name__ for c in in_iter + after + before
-                                      if type(c).__name__ not in ('Kernel', 'ExchangeSelf', 'DoLoop', 'Timers')))
+                                      if type(c).__name__ not in ('Kernel', 'ExchangeSelf', 'DoLoop', 'Timers', 'SimulationMonitor')))
     q_names = ['rho'] + ['rhou%d' % d for d in range(ndim)] + ['rhoE']
 
     # ---- stage loop: classify every kernel
@@ -1007,6 +1014,8 @@ def extract_plan(algorithm):
         plan['mass_source'] = mass_source
     plan['cold'] = cold
     plan['user_kernels'] = user
+    if monitor:
+        plan['monitor'] = monitor
     plan['q_names'] = q_names
 
     # ---- constants, in declaration order (opsc.py:625-654)

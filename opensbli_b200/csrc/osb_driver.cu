@@ -999,6 +999,19 @@ int osb_download(osb_ctx *c, const char *name, double *host) {
   OSB_CUDA(c, cudaStreamSynchronize(c->stream));
   return 0;
 }
+int osb_read_point(osb_ctx *c, const char *name, int i, int j, int k, double *value) {
+  if (!c || !name || !value) return 1;
+  Field *f = find_field(c, name);
+  if (!f) return fail(c, std::string("unknown field ") + name);
+  const GridDev &g = c->grid;
+  const int id[3] = {i, j, k};
+  for (int d = 0; d < g.nd; d++) if (id[d] < -g.h || id[d] >= g.np[d] + g.h) return fail(c, "osb_read_point: index outside the padded array");
+  refresh_primitives_for(c, f);
+  const long long x = g.off + i + (g.nd > 1 ? j * g.s[1] : 0) + (g.nd > 2 ? k * g.s[2] : 0);
+  OSB_CUDA(c, cudaMemcpyAsync(value, f->dev + x, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  OSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
 int osb_upload_face(osb_ctx *c, int dir, int side, const double *table) {
   if (!c || !table || dir < 0 || dir >= c->plan.nd || side < 0 || side > 1) return 1;
   if (!c->face_table[dir][side]) return fail(c, "osb_upload_face: this face has no dirichlet_field boundary condition");

@@ -174,6 +174,10 @@ def resolve(plan_sym, env):
             for f in (name, 'S' + name + str(d)):
                 p['fields'][f] = cold.array(f).copy()
     p['user_kernels'] = [user_kernel_source(k, n, env, nd) for n, k in enumerate(plan_sym.get('user_kernels', []))]
+    if plan_sym.get('monitor'):
+        m = dict(plan_sym['monitor'])
+        m['probes'] = [[int(c_eval(x, env)) for x in pr] for pr in m['probes']]
+        p['monitor'] = m
     if plan_sym.get('curvilinear'):
         for f in ['D%d%d' % (i, j) for i in range(nd) for j in range(nd)] + ['detJ']:
             p['fields'][f] = cold.array(f).copy()
@@ -213,6 +217,37 @@ def initial_state(plan_sym, cold):
     return [np.ascontiguousarray(cold.array(n)) for n in plan_sym['q_names']]
 
 
+def time_loop(sim, plan, niter, workdir='.'):
+    """The reference's time loop as the runner drives it: niter steps on the GPU; with a SimulationMonitor the run is cut at
+    the iterations that print (iter == 0 or (iter+1) %% frequency == 0, algorithm.py:433-437) and the probe values are written
+    in the reference's format (simulation_monitors.py:128-160).  Returns the device time of the steps in ms."""
+    mon = plan.get('monitor')
+    if not mon or niter <= 0:
+        return sim.step_timed(niter) if niter > 0 else 0.0
+    dt = plan['constants']['dt']
+    fmt = '%%.%df' % mon['precision']
+    out = open(os.path.join(workdir, mon['output_file']), 'w') if mon.get('output_file') else sys.stdout
+    ms, done = 0.0, 0
+    stops = sorted(set([1] + list(range(mon['frequency'], niter + 1, mon['frequency']))))
+    try:
+        for stop in stops:
+            ms += sim.step_timed(stop - done)
+            done = stop
+            if stop == 1:
+                out.write(', '.join(['Iteration', 'Time'] + ['%s_B0(%s)' % (a, ', '.join(str(x) for x in pr)) for a, pr in zip(mon['arrays'], mon['probes'])]) + '\n')
+            vals = []
+            for a, pr in zip(mon['arrays'], mon['probes']):
+                v = sim.read_point(a, *pr)
+                vals.append(v / stop if 'mean' in a else v)      # running sums are reported as means
+            out.write(', '.join(['%d' % stop, fmt % (stop * dt)] + [fmt % v for v in vals]) + '\n')
+        if done < niter:
+            ms += sim.step_timed(niter - done)
+    finally:
+        if out is not sys.stdout:
+            out.close()
+    return ms
+
+
 def load_case(workdir='.', overrides=None):
     plan_sym = json.load(open(os.path.join(workdir, PLAN_FILE)))
     env = read_stub(open(os.path.join(workdir, STUB_FILE)).read(), plan_sym['constant_decls'], overrides)
@@ -229,7 +264,7 @@ def main(argv=None):
     niter = plan_num.get('niter', 0)
     with Simulation(plan_num) as sim:
         sim.set_state(q0)
-        ms = sim.step_timed(niter) if niter > 0 else 0.0
+        ms = time_loop(sim, plan_num, niter, workdir)
         if any(k['when'] == 'after_loop' for k in plan_num.get('user_kernels', [])):
             sim.run_user_kernels('after_loop')                  # loops after the time loop (e.g. statistics / niter)
         q = sim.get_state()

@@ -14,7 +14,7 @@ _lib = None
 
 FAMILIES = ('prim', 'flux', 'central', 'viscous', 'rk', 'bc', 'sync', 'user')
 
-SYMBOLS = ('osb_create', 'osb_destroy', 'osb_last_error', 'osb_set_const_f64', 'osb_get_const_f64', 'osb_set_iteration', 'osb_get_iteration', 'osb_add_user_kernel', 'osb_run_user_kernels',
+SYMBOLS = ('osb_create', 'osb_destroy', 'osb_last_error', 'osb_set_const_f64', 'osb_get_const_f64', 'osb_set_iteration', 'osb_get_iteration', 'osb_add_user_kernel', 'osb_run_user_kernels', 'osb_read_point',
            'osb_num_fields', 'osb_field_name', 'osb_field_info', 'osb_upload', 'osb_download', 'osb_device_ptr', 'osb_upload_face',
            'osb_step', 'osb_step_begin', 'osb_stage', 'osb_sync', 'osb_apply_bcs', 'osb_residual', 'osb_step_timed', 'osb_timer_start', 'osb_timer_stop', 'osb_advance_host',
            'osb_launch_count', 'osb_profile_step', 'osb_ipc_export', 'osb_ipc_import', 'osb_halo_push',
@@ -48,6 +48,7 @@ def load_library(path=None):
     lib.osb_get_iteration.restype = ctypes.c_longlong
     lib.osb_add_user_kernel.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
     lib.osb_run_user_kernels.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.osb_read_point.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]
     lib.osb_num_fields.argtypes = [ctypes.c_void_p]
     lib.osb_field_info.argtypes = [ctypes.c_void_p, ctypes.c_char_p] + [ctypes.POINTER(ctypes.c_int)] * 3
     lib.osb_upload.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
@@ -179,6 +180,11 @@ class Simulation(object):
     def run_user_kernels(self, when='after_loop'):
         self._check(self.lib.osb_run_user_kernels(self.ctx, {'iteration_end': 0, 'after_loop': 1}[when]), 'osb_run_user_kernels')
         self.sync()
+
+    def read_point(self, name, i, j=0, k=0):
+        v = ctypes.c_double()
+        self._check(self.lib.osb_read_point(self.ctx, name.encode(), int(i), int(j), int(k), ctypes.byref(v)), 'osb_read_point')
+        return v.value
 
     def set_iteration(self, iteration):
         """iteration number seen by time-dependent source terms (restart)"""

@@ -33,6 +33,8 @@ APPS = {
     # the channel app exactly as shipped: statistics gathering (`User kernel` loops of stats.py) switched on
     'tcf_teno6_stats': (REF + '/apps/channel_flow/compressible_TCF_TENO/turbulent_channel.py',
                         [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)"), ("print_iteration_ops()", "")], 'tcf_teno6_stats_16x24x12'),
+    # 3-D channel in the Feiereisen split on a uniform grid, as shipped: statistics user kernels and a SimulationMonitor
+    't3d': (REF + '/apps/channel_flow/turbulent_3D/turbulent_channel.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),
     'sod_teno5': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'sod_teno5_n200'),
 }
 
@@ -97,6 +99,9 @@ def test_b200_backend_distils_expected_plan(name, app_runs):
         workdir = os.path.join(PLANS, name)
         if not os.path.exists(os.path.join(workdir, 'opensbli.cpp')):
             pytest.skip('no committed plan fixture for %s' % name)
+    if APPS[name][2] is None:          # no golden run of this app: the plan fixture is refreshed, dedicated tests below read it
+        assert json.load(open(os.path.join(workdir, 'opensbli_b200.plan.json')))['ndim'] in (1, 2, 3)
+        return
     plan_sym, env, plan_num, _cold = R.load_case(workdir)
     want, _ = load_fixture(APPS[name][2])
     got = comparable(plan_num)
@@ -158,6 +163,36 @@ def test_channel_cold_kernels_match_reference(name, fixture, sizes):
     # copies them into the periodic halos, which nothing reads)
     for f, a in want.get('fields', {}).items():
         assert np.abs(plan_num['fields'][f][s] - a[s]).max() <= 1e-11 * np.abs(a).max(), f
+
+
+def test_simulation_monitor_is_driven_by_the_runner(tmp_path):
+    """turbulent_3D as shipped: the SimulationMonitor (probes of rho, u0, p, T, u1 every 250 iterations into output.log) is
+    distilled into the plan; the runner cuts the time loop at the printing iterations and writes the reference's format."""
+    from opensbli_b200 import run as R
+    workdir = os.path.join(PLANS, 't3d')
+    if not os.path.exists(os.path.join(workdir, 'opensbli.cpp')):
+        pytest.skip('plan fixture missing')
+    plan_sym, env, plan, cold = R.load_case(workdir, overrides={'block0np0': 16, 'block0np1': 130, 'block0np2': 16, 'niter': 600})
+    mon = plan['monitor']
+    assert mon['arrays'] == ['rho', 'u0', 'p', 'T', 'u1'] and mon['frequency'] == 250 and mon['output_file'] == 'output.log'
+    assert mon['probes'][3] == [64, 15, 64] and plan['central_form'] == 'feiereisen' and len(plan['user_kernels']) == 2
+
+    class FakeSim(object):
+        calls, it = [], 0
+
+        def step_timed(self, n):
+            self.calls.append(n); self.it += n
+            return 1.0 * n
+
+        def read_point(self, name, i, j=0, k=0):
+            return self.it + 0.5
+    sim = FakeSim()
+    ms = R.time_loop(sim, plan, 600, str(tmp_path))
+    assert sim.calls == [1, 249, 250, 100] and ms == 600.0
+    lines = open(os.path.join(str(tmp_path), 'output.log')).read().splitlines()
+    assert lines[0].startswith('Iteration, Time, rho_B0(0, 10, 20)') and len(lines) == 4
+    assert lines[1].split(', ')[0] == '1' and lines[3].split(', ')[0] == '500'
+    assert lines[2].split(', ')[2] == '250.500000000000'          # fp_precision = 12
 
 
 def test_user_kernels_become_cuda_source():

@@ -141,3 +141,24 @@ def test_channel_app_with_statistics_as_shipped():
     assert max(err) < 1e-11, err
     for n, ref in want['stats_golden'].items():
         assert np.abs(stats[n] - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), n
+
+
+def test_turbulent_3d_app_as_shipped_with_monitor(tmp_path):
+    """apps/channel_flow/turbulent_3D/turbulent_channel.py as shipped (uniform grid, Feiereisen split, statistics user kernels,
+    SimulationMonitor): 500 iterations on a small grid, probe lines written at iterations 1, 250, 500; the last line equals the
+    values read from the final state, the state stays finite and the running sum of rho equals 500 x mean."""
+    from opensbli_b200 import run as R, Simulation
+    over = {'block0np0': 16, 'block0np1': 130, 'block0np2': 16, 'niter': 500}
+    plan_sym, env, plan, cold = R.load_case(os.path.join(PLANS, 't3d'), overrides=over)
+    plan['monitor']['probes'] = [[0, 10, 12], [3, 40, 5], [5, 129, 5], [6, 15, 6], [6, 96, 6]]      # inside the small grid
+    with Simulation(plan) as sim:
+        sim.set_state(R.initial_state(plan_sym, cold))
+        R.time_loop(sim, plan, 500, str(tmp_path))
+        last = [sim.read_point(a, *p) for a, p in zip(plan['monitor']['arrays'], plan['monitor']['probes'])]
+        rho = sim.download('rho')[5:-5, 5:-5, 5:-5]
+        rhomean = sim.download('rhomean')[5:-5, 5:-5, 5:-5]
+    lines = open(os.path.join(str(tmp_path), 'output.log')).read().splitlines()
+    assert [l.split(', ')[0] for l in lines[1:]] == ['1', '250', '500']
+    got = [float(x) for x in lines[-1].split(', ')[2:]]
+    assert np.allclose(got, last, rtol=0, atol=1e-11)
+    assert np.isfinite(rho).all() and abs(rhomean.mean() / 500 - 1.0) < 0.05       # mass is conserved around rho = 1
