@@ -312,7 +312,7 @@ def main():
         roofline = {'bound': 'fp64', 'kernel': 'k_flux_{x,yz} (TENO5 characteristic flux sweep + flux difference)',
                     'achieved': ach, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': ach / fp64_peak if fp64_peak else None,
                     'traffic': NCU_DRAM_BYTES_PER_FLUX_LAUNCH_512 if (world == 1 and args.size == 512) else None,
-                    'traffic_source': 'profiles/r01_final_ncu_top_kernels_512.md (bytes per launch, ncu --set full)', 'launch_ms': per_launch_ms, 'share_of_step': fl['ms'] / tot if tot else None,
+                    'traffic_source': 'profiles/r01_final2_ncu_top_kernels_512.md (bytes per launch, ncu --set full)', 'launch_ms': per_launch_ms, 'share_of_step': fl['ms'] / tot if tot else None,
                     'peak_source': 'measured in this run: DFMA micro-benchmark osb_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)',
                     'flop_model': "reference's own count_ops: 2836 per point per LLFTeno_reconstruction loop + 50/3 Residual",
                     'families_ms': {k: v['ms'] for k, v in prof.items()}}
