@@ -655,16 +655,18 @@ int stage_nd(osb_ctx *c, int s) {
       if (ex) { neighbour_signal(c, 1); neighbour_wait(c, 1); }
       launch_bcs(c);
     } else {
-      launch_bcs(c);
+      // planes first, rank-local BCs after the neighbours' planes have landed: the BC kernels also rewrite the x/y-halo
+      // parts of the received planes, which must neither race with nor precede the neighbour's stores
       if (ex) { if (push_planes_memcpy(c)) return 1; neighbour_signal(c, 1); neighbour_wait(c, 1); }
+      launch_bcs(c);
     }
     if (s == (int)c->plan.rk_a.size() - 1 && run_user_kernels(c, 0)) return 1;
     OSB_CUDA(c, cudaGetLastError());
     return 0;
   }
   if (s < 0) {
-    launch_bcs(c);
     if (ex) { if (push_planes_memcpy(c)) return 1; neighbour_signal(c, 1); neighbour_wait(c, 1); }
+    launch_bcs(c);
     if (c->plan.rk == RK_SBLI) launch_save<ND>(c);
   } else {
     launch_phase_a<ND>(c, s);     // sends the "read done" notification as soon as the halo-reading kernels are enqueued
@@ -675,8 +677,8 @@ int stage_nd(osb_ctx *c, int s) {
       neighbour_signal(c, 1); neighbour_wait(c, 1);
       launch_bcs(c);
     } else {
-      launch_bcs(c);
       if (ex) { if (push_planes_memcpy(c)) return 1; neighbour_signal(c, 1); neighbour_wait(c, 1); }
+      launch_bcs(c);
     }
   }
   if (s == (int)c->plan.rk_a.size() - 1 && run_user_kernels(c, 0)) return 1;
