@@ -11,7 +11,8 @@ ordered on each rank's CUDA stream by flag words the neighbours write through pe
     planes into the neighbours' Residual-role buffers over NVLink (CUDA IPC peer pointers) -> "pushed" handshake -> the
     buffers exchange roles -> rank-local BCs;
     in-place paths (2-D, general path with walls / metrics): kernels that read the halos -> "read done" handshake -> RK
-    update -> plane copies into the neighbours' halos -> "pushed" handshake.
+    update -> plane copies into the neighbours' halos -> "pushed" handshake -> rank-local BCs (they also rewrite the x/y-halo
+    parts of the received planes, so they must come after the neighbours' copies).
 Per-point arrays of the general path (metrics, source amplitudes) and tabulated Dirichlet states are cut with the slab;
 physical boundary conditions and their one-sided closures stay with the ranks that own the face.
 The pure functions in this module (extents, neighbours, plane indices) are shared by the GPU driver and by the
