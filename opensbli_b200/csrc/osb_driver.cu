@@ -466,7 +466,8 @@ void launch_phase_a(osb_ctx *c, int stage = -1) {
 // phase B: viscous terms (stencils on u, T only).  stage >= 0: fuse the RK update (and the halo push of a decomposed run)
 // of that stage into the kernel where possible; returns true if the RK update was fused.
 template <int ND>
-bool launch_phase_b(osb_ctx *c, int stage) {
+// returns 0: Residual complete, RK update still to do; 1: RK update fused; 2: RK update and peer stores of the boundary planes fused
+int launch_phase_b(osb_ctx *c, int stage) {
   const GridDev &g = c->grid;
   if (c->plan.viscous) {
     if (ND == 3 && !c->general) {
@@ -478,21 +479,30 @@ bool launch_phase_b(osb_ctx *c, int stage) {
       }
       else if (c->plan.rk == RK_LS) launch_viscous_tiled<1>(c, c->plan.rk_a[stage], c->plan.rk_b[stage]);
       else launch_viscous_tiled<2>(c, c->plan.rk_a[stage], c->plan.rk_b[stage]);
-      return stage >= 0;
+      return stage >= 0 ? 2 : 0;
     }
     dim3 b(64, 2, 2);
     Launcher L(c, OSB_FAM_VISCOUS);
     static const bool tiled_general = getenv("OSB_NO_TILED_GENERAL") == nullptr;
     if (c->general && ND == 3 && tiled_general) {
       static bool attr_set = false;
-      if (!attr_set) { cudaFuncSetAttribute(k_viscous3d_tiled_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vtg_smem_bytes()); attr_set = true; }
+      if (!attr_set) {
+        cudaFuncSetAttribute(k_viscous3d_tiled_general<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vtg_smem_bytes());
+        cudaFuncSetAttribute(k_viscous3d_tiled_general<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vtg_smem_bytes());
+        cudaFuncSetAttribute(k_viscous3d_tiled_general<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vtg_smem_bytes());
+        attr_set = true;
+      }
       dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + g.zlen - 1) / g.zlen);
-      k_viscous3d_tiled_general<<<gr, bl, vtg_smem_bytes(), c->stream>>>(g, c->fp, c->pc, c->plan.cl, c->gp);
+      const double ra = stage >= 0 ? c->plan.rk_a[stage] : 0.0, rb = stage >= 0 ? c->plan.rk_b[stage] : 0.0;
+      if (stage < 0) k_viscous3d_tiled_general<0><<<gr, bl, vtg_smem_bytes(), c->stream>>>(g, c->fp, c->pc, c->plan.cl, c->gp, ra, rb);
+      else if (c->plan.rk == RK_LS) k_viscous3d_tiled_general<1><<<gr, bl, vtg_smem_bytes(), c->stream>>>(g, c->fp, c->pc, c->plan.cl, c->gp, ra, rb);
+      else k_viscous3d_tiled_general<2><<<gr, bl, vtg_smem_bytes(), c->stream>>>(g, c->fp, c->pc, c->plan.cl, c->gp, ra, rb);
+      return stage >= 0 ? 1 : 0;
     }
     else if (c->general) k_viscous_general<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc, c->plan.cl, c->gp);
     else k_viscous<ND><<<grid3(g.np[0], g.np[1], g.np[2], b), b, 0, c->stream>>>(g, c->fp, c->pc);
   }
-  return false;
+  return 0;
 }
 
 void box_launch_cfg(const Box &b, int nv, unsigned &blocks) {
@@ -671,9 +681,9 @@ int stage_nd(osb_ctx *c, int s) {
   } else {
     launch_phase_a<ND>(c, s);     // sends the "read done" notification as soon as the halo-reading kernels are enqueued
     neighbour_wait(c, 0);
-    const bool fused = launch_phase_b<ND>(c, s);
+    const int fused = launch_phase_b<ND>(c, s);
     if (!fused) launch_rk<ND>(c, s);
-    if (ex && fused && fused_push_enabled()) {            // planes were pushed by the kernel: interior part; the receiver's own BCs complete the halos
+    if (ex && fused == 2 && fused_push_enabled()) {            // planes were pushed by the kernel: interior part; the receiver's own BCs complete the halos
       neighbour_signal(c, 1); neighbour_wait(c, 1);
       launch_bcs(c);
     } else {

@@ -1006,7 +1006,8 @@ __global__ void __launch_bounds__(256) k_viscous_general(GridDev g, FieldPtrs f,
 // in shared memory.  Points whose stencils are all central (not within the closure rows of a flagged face) take every
 // derivative from shared memory; the few rows next to walls evaluate the generic per-point formulas from global memory.
 constexpr size_t vtg_smem_bytes() { return sizeof(double) * 5 * 5 * VT_PLANE; }
-__global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled_general(GridDev g, FieldPtrs f, PhysConst c, Closures cl, GeneralPtrs gp) {
+template <int RK>   // 0 = Residual += viscous terms, 1 / 2 = also the low-storage / SBLI RK update of the stage (in place: q is not read by stencils here)
+__global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled_general(GridDev g, FieldPtrs f, PhysConst c, Closures cl, GeneralPtrs gp, double rkA, double rkB) {
   extern __shared__ double vtg_smem[];
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * VT_X + tx;
   const int i0 = blockIdx.x * VT_X, j0 = blockIdx.y * VT_Y, k0 = blockIdx.z * g.zlen;
@@ -1117,13 +1118,27 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled_general(Grid
         for (int d = 0; d < 3; d++) hT += dmu[d] * dT[d] + mu * (Dm[d] * Dm[d] * d2[3][d] + Dm[d] * SDm[d] * dxi[3][d]);
         en = kq * hT + e;
       }
-      double old[4];
+      double Rm[5];
 #pragma unroll
-      for (int a = 0; a < 4; a++) old[a] = f.R[1 + a][x];
-      if (gp.src) f.R[0][x] += gp.src[x] * c.src_factor;
+      for (int m = 0; m < 5; m++) Rm[m] = f.R[m][x];
+      if (gp.src) Rm[0] += gp.src[x] * c.src_factor;
 #pragma unroll
-      for (int a = 0; a < 3; a++) f.R[1 + a][x] = old[a] + vis[a];
-      f.R[4][x] = old[3] + en;
+      for (int a = 0; a < 3; a++) Rm[1 + a] += vis[a];
+      Rm[4] += en;
+      if (RK == 0) {
+        if (gp.src) f.R[0][x] = Rm[0];
+#pragma unroll
+        for (int m = 1; m < 5; m++) f.R[m][x] = Rm[m];
+      } else {
+        double o[5], q[5];
+#pragma unroll
+        for (int m = 0; m < 5; m++) { o[m] = f.rk[m][x]; q[m] = f.q[m][x]; }
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+          if (RK == 1) { const double t = c.dt * Rm[m] + rkA * o[m]; f.rk[m][x] = t; f.q[m][x] = rkB * t + q[m]; }
+          else { f.q[m][x] = c.dt * rkB * Rm[m] + o[m]; f.rk[m][x] = c.dt * rkA * Rm[m] + o[m]; }
+        }
+      }
     }
     __syncthreads();
     if (k + 1 < kend) load_plane(k + 3);
