@@ -81,6 +81,13 @@ def local_plan(plan, rank, world):
                 pd = [plan['np'][e] + 2 * h for e in range(nd) if e != d]          # tangential padded extents, x fastest
                 t = np.asarray(b['table']).reshape((-1,) + tuple(reversed(pd)))
                 p['bc'][d][s]['table'] = np.ascontiguousarray(t[:, k0:k0 + loc + 2 * h]).reshape(t.shape[0], -1)
+    # point-wise user kernels cover the rank's own slab
+    for uk in p.get('user_kernels', []):
+        r = list(uk['range']) + [0, 1] * (3 - nd)
+        if r[2 * ax] != 0 or r[2 * ax + 1] != plan['np'][ax]:
+            raise _plan.PlanError('user kernel %s does not cover the whole slab axis: cannot be decomposed' % uk.get('name'))
+        r[2 * ax + 1] = loc
+        uk['range'] = r[:2 * nd]
     return _plan.validate(p)
 
 

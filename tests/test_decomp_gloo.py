@@ -111,6 +111,10 @@ def test_decomp_helpers():
     assert pp['up'] == ((5 + 8 - 3, 5 + 8), (2, 5)) and pp['down'] == ((5, 9), (13, 17))
     with pytest.raises(Exception):
         decomp.local_plan(plan, 0, 3)
+    # point-wise user kernels (statistics) follow the slab
+    withuk = dict(plan, user_kernels=[{'name': 'stats', 'range': [0, 16, 0, 16, 0, 16], 'when': 'iteration_end'}])
+    assert decomp.local_plan(withuk, 1, 4)['user_kernels'][0]['range'] == [0, 16, 0, 16, 0, 4]
+    assert withuk['user_kernels'][0]['range'] == [0, 16, 0, 16, 0, 16]
     sod, _ = load_fixture('sod_teno5_n200')
     assert decomp.neighbours(sod, 0, 2) == (None, 1) and decomp.neighbours(sod, 1, 2) == (0, None)
     lp = decomp.local_plan(sod, 0, 2)
