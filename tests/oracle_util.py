@@ -192,6 +192,15 @@ def oracle_stage(plan, q, rk_reg, stage):
     assert lib.osbo_stage(ctypes.byref(cfg), qa, ra, ctypes.c_int(stage)) == 0
 
 
+def oracle_apply_bcs(plan, q):
+    """In-place boundary conditions of the rank-local faces ('exchange' faces are left alone)."""
+    lib = oracle_lib()
+    cfg = make_cfg(plan)
+    nv = plan['ndim'] + 2
+    P = ctypes.POINTER(ctypes.c_double)
+    lib.osbo_apply_bcs(ctypes.byref(cfg), (P * nv)(*[a.ctypes.data_as(P) for a in q]))
+
+
 def oracle_residual(plan, q):
     lib = oracle_lib()
     cfg = make_cfg(plan)

@@ -53,7 +53,7 @@ def host_exchange(q, plan_local, low, high, halo=5):
         a[d0:d1] = t.numpy()
 
 
-def _worker(rank, world, port, fixture, nsteps, out):
+def _worker(rank, world, port, fixture, nsteps, out, order='bcs_first'):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     import oracle_util as ou
@@ -68,6 +68,30 @@ def _worker(rank, world, port, fixture, nsteps, out):
     else:
         q = [np.ascontiguousarray(a) for a in pad(lp, states[0][:, k0:k0 + nk])]
     rk = [np.zeros_like(a) for a in q]
+    if order == 'exchange_first':
+        # the order of the GPU protocol: planes first, rank-local BCs after the neighbours' planes have landed (they also
+        # rewrite the halo parts of the received planes).  A copy of the plan with every face an 'exchange' face makes the
+        # oracle's stage call skip the BCs, which are then applied separately.
+        import copy
+        nobc = copy.deepcopy(lp)
+        nobc['bc'] = [[{'type': 'exchange'}, {'type': 'exchange'}] for _ in range(lp['ndim'])]
+        nobc_cl = [[b.get('closure') for b in pair] for pair in lp['bc']]
+        for d, pair in enumerate(nobc['bc']):
+            for s_, b in enumerate(pair):
+                if nobc_cl[d][s_]:
+                    b['closure'] = nobc_cl[d][s_]          # one-sided derivative rows belong to the face, not to its BC kernel
+        for _ in range(nsteps):
+            host_exchange(q, lp, low, high)
+            ou.oracle_apply_bcs(lp, q)
+            ou.oracle_stage(nobc, q, rk, -1)
+            for s in range(len(lp['rk_a'])):
+                ou.oracle_stage(nobc, q, rk, s)
+                host_exchange(q, lp, low, high)
+                ou.oracle_apply_bcs(lp, q)
+        np.save(os.path.join(out, 'q_%d.npy' % rank), np.stack([a[5:-5] for a in q]))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     for _ in range(nsteps):
         ou.oracle_stage(lp, q, rk, -1)
         host_exchange(q, lp, low, high)
@@ -97,6 +121,21 @@ def test_slab_decomposition_reproduces_single_domain(fixture, world, tmp_path):
     got = np.concatenate([np.load(os.path.join(str(tmp_path), 'q_%d.npy' % r))[cut] for r in range(world)], axis=1)
     assert got.shape == ref.shape
     assert np.array_equal(got, ref)        # same arithmetic on every point: bit-exact
+
+
+@pytest.mark.parametrize('fixture,world', [('tcf_central_16x24x12', 2), ('vst_60x30', 2), ('tgv_teno5_16', 2)])
+def test_exchange_before_rank_local_bcs_reproduces_single_domain(fixture, world, tmp_path):
+    """The order the GPU driver uses on every path (exchange, then the rank-local BCs) gives the single-domain result bit for bit."""
+    import oracle_util as ou
+    from common import load_fixture, inner, initial_padded
+    nsteps = 2
+    mp.spawn(_worker, args=(world, _free_port(), fixture, nsteps, str(tmp_path), 'exchange_first'), nprocs=world, join=True)
+    plan, states = load_fixture(fixture)
+    q, _ = ou.oracle_advance(plan, initial_padded(plan, states), nsteps)
+    ref = inner(plan, q)
+    cut = (slice(None), slice(None)) + (slice(5, -5),) * (plan['ndim'] - 1)
+    got = np.concatenate([np.load(os.path.join(str(tmp_path), 'q_%d.npy' % r))[cut] for r in range(world)], axis=1)
+    assert np.array_equal(got, ref)
 
 
 def test_decomp_helpers():
