@@ -191,6 +191,71 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------ parity beside the number
+def parity_check(args, world, rank, local_rank, dist):
+    """Correctness carried by the bench line itself (same library, same context type, right after the timed region):
+    a small TGV block (64^3, the workload's scheme) is advanced
+      (a) on this rank's GPU alone and compared with the reference's own generated C (oracle/_ref/<config>/ref_seq, run on
+          the host for the same grid and steps; the plain-C oracle port when the executable is absent) -> max_rel_err;
+      (b) for N > 1, slab-decomposed over all N ranks with the peer-store halo exchange and compared BIT FOR BIT with (a).
+    The reference / oracle is the checker here, never the thing measured."""
+    import numpy as np
+    import opensbli_b200
+    from opensbli_b200.decomp import DistributedSimulation, local_extent
+    sys.path.insert(0, os.path.join(REPO, 'tests'))
+    n, nsteps = 64, 2
+    plan = tgv_plan([n, n, n], args.workload)
+    plan['delta'] = [2 * math.pi / n] * 3
+    plan['constants']['dt'] = 0.003385 * 64 / n
+    names = ['rho', 'rhou0', 'rhou1', 'rhou2', 'rhoE']
+    inner = (slice(5, -5),) * 3
+    out = {'grid': [n, n, n], 'steps': nsteps, 'max_rel_err': None, 'vs': None, 'multi_gpu_bit_identical': None}
+    single = None
+    if rank == 0:
+        q0 = [np.zeros((n + 10,) * 3) for _ in range(5)]
+        tgv_state_into(q0, plan, 0, n)
+        with opensbli_b200.Simulation(plan, device=local_rank) as sim:
+            sim.set_state(q0)
+            sim.step(nsteps)
+            single = np.stack([a[inner] for a in sim.get_state()])
+        config = 'tgv_teno5' if args.workload == 'teno5' else 'tgv_central4'
+        try:
+            import oracle_util as ou
+            if ou.have_ref(config):
+                r = ou.run_ref(config, dict(block0np0=n, block0np1=n, block0np2=n, niter=nsteps, dt=plan['constants']['dt']), names, exe='ref_seq')
+                ref = np.stack([r[f][inner] for f in names])
+                out['vs'] = "reference's generated C oracle/_ref/%s/ref_seq (g++ -O2 -ffp-contract=off, OPS stand-in), %d^3, %d steps" % (config, n, nsteps)
+            else:
+                qo, _ = ou.oracle_advance(plan, [a.copy() for a in q0], nsteps)
+                ref = np.stack([a[inner] for a in qo])
+                out['vs'] = 'oracle/osbli_oracle.c port (oracle/_ref absent), %d^3, %d steps' % (n, nsteps)
+            norms = [np.abs(ref[0]).max(), np.abs(ref[1:4]).max(), np.abs(ref[1:4]).max(), np.abs(ref[1:4]).max(), np.abs(ref[4]).max()]
+            out['max_rel_err'] = float(max(np.abs(single[m] - ref[m]).max() / norms[m] for m in range(5)))
+            out['tolerance'] = 1e-12 * nsteps
+            out['ok'] = bool(out['max_rel_err'] <= out['tolerance'])
+        except Exception as e:       # the checker must never take the measurement down with it
+            out['vs'] = 'checker failed: %r' % (e,)
+    if world > 1:
+        import torch
+        ds = DistributedSimulation(plan, dist, device=local_rank)
+        k0, nk = local_extent(plan, rank, world)
+        q0 = [np.zeros((nk + 10, n + 10, n + 10)) for _ in range(5)]
+        tgv_state_into(q0, ds.plan, k0, nk)
+        ds.set_state(q0)
+        ds.step(nsteps)
+        ds.barrier()
+        mine = np.stack([a[inner] for a in ds.sim.get_state()])
+        ds.close()
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        if rank == 0:
+            got = np.concatenate(parts, axis=1)
+            out['multi_gpu_bit_identical'] = bool(np.array_equal(got, single))
+            out['multi_gpu_max_abs_diff'] = float(np.abs(got - single).max())
+            out['multi_gpu'] = '%d slabs of %d planes, peer-store halo exchange, vs the single-GPU run of the same block' % (world, nk)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -203,6 +268,7 @@ def main():
     ap.add_argument('--cpu-size', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-parity', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         reference_arm(args)
@@ -351,6 +417,12 @@ def main():
                    'd2h_bytes_per_step': nbytes_state * world, 'steps': Ke,
                    'call': 'per step: osb_upload x5 + stage loop with halo pushes + osb_download x5 on every rank'}
 
+    # ---- parity beside the number (small block: vs the reference executable; N>1: decomposed vs single GPU, bit for bit)
+    parity = None
+    if not args.no_parity:
+        barrier()
+        parity = parity_check(args, world, rank, local_rank, dist)
+
     # ---- CPU baseline beside it (rank 0, N=1): the reference's generated C on this box's host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -373,7 +445,7 @@ def main():
                            'grid': plan['np'], 'parallelism': 'slab%d' % world,
                            'l2_policy': 'working set %.1f GB per GPU >> 126 MB L2 (no flush needed)' % (19 * np.prod(shape) * 8 / 1e9),
                            'finite': finite},
-                'roofline': roofline, 'roofline_hbm': roofline_hbm, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e,
+                'roofline': roofline, 'roofline_hbm': roofline_hbm, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e, 'parity': parity,
                 'gpu_launches': int(launches), 'fp64_peak_tflops_measured': fp64_peak,
                 'families_ms_rank0': {k: v['ms'] for k, v in prof.items()} if prof else None,
                 'alg_flop_per_update': ALG_FLOP_PER_UPDATE, 'achieved_alg_tflops': ALG_FLOP_PER_UPDATE * value / world / 1e12}

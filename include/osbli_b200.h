@@ -94,11 +94,18 @@ int osb_profile_step(osb_ctx *ctx, double *family_ms /* [OSB_NFAM] */, long long
  * apps/channel_flow/*: stats.py, opsc.py kernel emission): app-specific arithmetic outside the solver's hot loops, given as
  * CUDA C source of one `extern "C" __global__` entry with the signature
  *     entry(long long off, int n0, int n1, int n2, int lo0, int lo1, int lo2, long long s1, long long s2, UserFields f)
- * where `struct UserFields { double *p[OSB_MAX_USER_FIELDS]; }` holds the arrays named in `fields` (comma separated; unknown
- * names are created zero-initialised, as OPS declares datasets).  Compiled once with NVRTC for sm_100a.
+ * where `struct UserFields { double *p[OSB_MAX_USER_FIELDS]; }` holds the arrays named in `fields` (comma separated).  A name
+ * prefixed with '+' is written by the kernel: if it does not exist yet it is created zero-initialised, as OPS declares
+ * datasets (opsc.py:693-722).  A name the kernel only reads must exist (solver field, or osb_create_field + osb_upload):
+ * otherwise the call fails -- reading zeros in place of a dataset nobody provided would be a silent wrong answer.
+ * u_i, p, a, T read by a user kernel are the constituent relations of the state at the time of the launch.
+ * Compiled once with NVRTC for sm_100a.
  * when = 0: launched at the end of every iteration of osb_step (after the last stage's boundary conditions);
  * when = 1: launched by osb_run_user_kernels(ctx, 1) (loops after the time loop). */
 enum { OSB_MAX_USER_FIELDS = 48 };
+/* Declare an additional dataset (zero-initialised; no-op if it exists): what ops_decl_dat does for a dataset that only user
+ * kernels touch, e.g. a coordinate array x0 evaluated by the cold path and uploaded with osb_upload (opsc.py:693-722). */
+int osb_create_field(osb_ctx *ctx, const char *name);
 int osb_add_user_kernel(osb_ctx *ctx, const char *cuda_source, const char *entry, const char *fields, const int range[6], int when);
 int osb_run_user_kernels(osb_ctx *ctx, int when);
 

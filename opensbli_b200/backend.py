@@ -825,8 +825,15 @@ def extract_plan(algorithm):
     from opensbli.core.kernel import ConstantsToDeclare
     if getattr(algorithm, 'MultiBlock', False) or len(algorithm.block_descriptions) != 1:
         raise UnsupportedByB200('multi-block algorithms are not implemented')
-    if str(algorithm.dtype).lower() not in ('double', 'dtype.double'):
-        pass
+    # the kernels are fp64 only (the reference's `SimulationDataType.set_datatype(Double)`, datatypes.py:2-30)
+    try:
+        from opensbli.core.datatypes import SimulationDataType
+        ctype = SimulationDataType.opsc()
+    except Exception:
+        ctype = 'double'
+    dt = algorithm.dtype if isinstance(algorithm.dtype, str) else getattr(algorithm.dtype, 'opsc', lambda: 'double')()
+    if ctype != 'double' or str(dt).lower() != 'double':
+        raise UnsupportedByB200('datatype %s/%s: the B200 back end computes in double precision only' % (ctype, dt))
     ndim = algorithm.block_descriptions[0].ndim
     flat = []
     _walk(algorithm.prg.components, flat)

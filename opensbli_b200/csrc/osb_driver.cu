@@ -280,8 +280,7 @@ void launch_flux(osb_ctx *c) {
     const long long TR = (long long)(g.np[2] + 6) * g.np[1];
     dim3 b(32, F2_TY, 1), gr((unsigned)((TR + F2_RT - 7) / (F2_RT - 6)), (g.np[0] + 31) / 32, 1);
     auto kern = k_flux2_yz<3, 2, RECON, AVG, false>;
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_yz_smem_bytes<3>()); attr_set = true; }
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_yz_smem_bytes<3>());   // per device: set on every launch
     { Launcher L(c, OSB_FAM_FLUX); kern<<<gr, b, f2_yz_smem_bytes<3>(), c->stream>>>(g, c->fp, c->pc, c->sp, c->ad, c->gp); }
     neighbour_signal(c, 0);
   }
@@ -297,8 +296,7 @@ void launch_flux(osb_ctx *c) {
     dim3 b(32, F2_TY, 1), gr((unsigned)((TR + F2_RT - 7) / (F2_RT - 6)), (g.np[0] + 31) / 32, 1);
     constexpr int N2 = (ND >= 2 ? ND : 2);
     auto kern = k_flux2_yz<N2, 1, RECON, AVG, true>;
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_yz_smem_bytes<N2>()); attr_set = true; }
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_yz_smem_bytes<N2>());
     Launcher L(c, OSB_FAM_FLUX);
     kern<<<gr, b, f2_yz_smem_bytes<N2>(), c->stream>>>(g, c->fp, c->pc, c->sp, c->ad, c->gp);
   }
@@ -393,8 +391,7 @@ template <int RK, bool FROMQ = false>
 void launch_viscous_tiled(osb_ctx *c, double a, double b) {
   const GridDev &g = c->grid;
   auto kern = k_viscous3d_tiled<RK, FROMQ>;
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vt_smem_bytes()); attr_set = true; }
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vt_smem_bytes());
   dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + g.zlen - 1) / g.zlen);
   Launcher L(c, OSB_FAM_VISCOUS);
   kern<<<gr, bl, vt_smem_bytes(), c->stream>>>(g, c->fp, c->pc, a, b, RK == 0 ? PeerPush{} : peer_push(c, FROMQ));
@@ -485,13 +482,9 @@ int launch_phase_b(osb_ctx *c, int stage) {
     Launcher L(c, OSB_FAM_VISCOUS);
     static const bool tiled_general = getenv("OSB_NO_TILED_GENERAL") == nullptr;
     if (c->general && ND == 3 && tiled_general) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        cudaFuncSetAttribute(k_viscous3d_tiled_general<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vtg_smem_bytes());
-        cudaFuncSetAttribute(k_viscous3d_tiled_general<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vtg_smem_bytes());
-        cudaFuncSetAttribute(k_viscous3d_tiled_general<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vtg_smem_bytes());
-        attr_set = true;
-      }
+      cudaFuncSetAttribute(k_viscous3d_tiled_general<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vtg_smem_bytes());
+      cudaFuncSetAttribute(k_viscous3d_tiled_general<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vtg_smem_bytes());
+      cudaFuncSetAttribute(k_viscous3d_tiled_general<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vtg_smem_bytes());
       dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + g.zlen - 1) / g.zlen);
       const double ra = stage >= 0 ? c->plan.rk_a[stage] : 0.0, rb = stage >= 0 ? c->plan.rk_b[stage] : 0.0;
       if (stage < 0) k_viscous3d_tiled_general<0><<<gr, bl, vtg_smem_bytes(), c->stream>>>(g, c->fp, c->pc, c->plan.cl, c->gp, ra, rb);
@@ -630,10 +623,23 @@ void launch_central_fused(osb_ctx *c, int stage) {
 // ---- run-time compiled point-wise user kernels ---------------------------------------------------
 struct UserFields { double *p[OSB_MAX_USER_FIELDS]; };
 
+bool is_primitive(const osb_ctx *c, const double *dev) {
+  bool prim = dev == c->fp.p || dev == c->fp.a || dev == c->fp.T;
+  for (int d = 0; d < c->plan.nd; d++) prim = prim || dev == c->fp.u[d];
+  return prim;
+}
+void launch_prim_nd(osb_ctx *c) {
+  switch (c->plan.nd) { case 1: launch_prim<1>(c); break; case 2: launch_prim<2>(c); break; default: launch_prim<3>(c); }
+}
+
 int run_user_kernels(osb_ctx *c, int when) {
   const GridDev &g = c->grid;
   for (auto &k : c->user_kernels) {
     if (k.when != when) continue;
+    // u_i, p, a, T are not written by the stage kernels that derive them on the fly: a user kernel that reads one of them
+    // sees the constituent relations of the current state (what the reference's loop reads after its last stage)
+    if (c->prim_stale)
+      for (auto &n : k.fields) { Field *f = find_field(c, n.c_str()); if (f && is_primitive(c, f->dev)) { launch_prim_nd(c); break; } }
     UserFields uf{};
     for (size_t i = 0; i < k.fields.size(); i++) {
       Field *f = find_field(c, k.fields[i].c_str());
@@ -739,12 +745,13 @@ int do_step(osb_ctx *c, int nsteps) {
   if (nsteps < unit) return step_dispatch(c, nsteps);
   if (!c->step_graph) {
     cudaGraph_t graph = nullptr;
-    const long long l0 = c->launches;
+    const long long l0 = c->launches, it0 = c->iteration;
     if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return step_dispatch(c, nsteps); }
     const int rc = step_dispatch(c, unit);
     const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
     c->graph_launches = c->launches - l0;
     c->launches = l0;
+    c->iteration = it0;              // nothing has run yet: the capture only recorded the launches
     if (rc || e != cudaSuccess || !graph) { cudaGetLastError(); if (graph) cudaGraphDestroy(graph); c->use_graph = false; return step_dispatch(c, nsteps); }
     if (cudaGraphInstantiate(&c->step_graph, graph, 0) != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(graph); c->use_graph = false; return step_dispatch(c, nsteps); }
     cudaGraphDestroy(graph);
@@ -752,6 +759,10 @@ int do_step(osb_ctx *c, int nsteps) {
   for (int it = 0; it + unit <= nsteps; it += unit) {
     OSB_CUDA(c, cudaGraphLaunch(c->step_graph, c->stream));
     c->launches += c->graph_launches;
+    // host-side effects of the replayed unit: the loop counter advances, and on the paths whose stage kernels derive the
+    // primitives on the fly the u/p/a/T arrays now lag the state again
+    c->iteration += unit;
+    if (fused_central_ok(c) || viscous_from_q_ok(c)) c->prim_stale = true;
   }
   return step_dispatch(c, nsteps % unit);
 }
@@ -890,24 +901,40 @@ int osb_set_const_f64(osb_ctx *c, const char *name, double v) {
   drop_graph(c);          // constants are baked into the captured kernel arguments
   return 0;
 }
+int osb_create_field(osb_ctx *c, const char *name) {
+  if (!c || !name || !*name) return 1;
+  if (find_field(c, name)) return 0;
+  cudaSetDevice(c->device);
+  Field f; f.name = name;
+  if (f.name.size() > 3 && f.name.compare(f.name.size() - 3, 3, "_B0") == 0) f.name.resize(f.name.size() - 3);
+  OSB_CUDA(c, cudaMalloc(&f.dev, sizeof(double) * c->grid.n));
+  OSB_CUDA(c, cudaMemsetAsync(f.dev, 0, sizeof(double) * c->grid.n, c->stream));
+  c->fields.push_back(f);
+  return 0;
+}
 int osb_add_user_kernel(osb_ctx *c, const char *source, const char *entry, const char *fields, const int range[6], int when) {
   if (!c || !source || !entry || !fields || !range) return 1;
   cudaSetDevice(c->device);
   osb_ctx::UserKernel k;
   k.when = when;
   for (int i = 0; i < 6; i++) k.range[i] = range[i];
+  std::vector<bool> written;
   {
     std::stringstream ss(fields);
     std::string n;
-    while (std::getline(ss, n, ',')) if (!n.empty()) k.fields.push_back(n);
+    while (std::getline(ss, n, ',')) if (!n.empty()) {
+      const bool w = n[0] == '+';
+      k.fields.push_back(w ? n.substr(1) : n);
+      written.push_back(w);
+    }
   }
   if (k.fields.size() > OSB_MAX_USER_FIELDS) return fail(c, "user kernel uses too many arrays");
-  for (auto &n : k.fields)
-    if (!find_field(c, n.c_str())) {          // a dataset of the user kernel only (e.g. a running mean): zero-initialised
-      Field f; f.name = n;
-      OSB_CUDA(c, cudaMalloc(&f.dev, sizeof(double) * c->grid.n));
-      OSB_CUDA(c, cudaMemsetAsync(f.dev, 0, sizeof(double) * c->grid.n, c->stream));
-      c->fields.push_back(f);
+  for (size_t i = 0; i < k.fields.size(); i++)
+    if (!find_field(c, k.fields[i].c_str())) {
+      // a dataset the kernel writes (e.g. a running mean) is created zero-initialised, as OPS declares datasets; one it only
+      // reads must exist: reading zeros in place of a dataset nobody uploaded would be a silent wrong answer
+      if (!written[i]) return fail(c, "user kernel reads dataset '" + k.fields[i] + "' which does not exist on the device: create it with osb_create_field and upload it first");
+      if (osb_create_field(c, k.fields[i].c_str())) return 1;
     }
   // NVRTC is loaded on demand: the library itself must not depend on it (it also loads on hosts without a driver)
   typedef int (*create_t)(void **, const char *, const char *, int, const char *const *, const char *const *);
@@ -994,12 +1021,9 @@ int osb_upload(osb_ctx *c, const char *name, const double *host) {
 // u_i, p, a, T are not kept up to date by the stage kernels that derive them on the fly: evaluate the constituent relations
 // of the current state before handing such an array out
 static void refresh_primitives_for(osb_ctx *c, const Field *f) {
-  if (!c->prim_stale) return;
-  bool prim = f->dev == c->fp.p || f->dev == c->fp.a || f->dev == c->fp.T;
-  for (int d = 0; d < c->plan.nd; d++) prim = prim || f->dev == c->fp.u[d];
-  if (!prim) return;
+  if (!c->prim_stale || !is_primitive(c, f->dev)) return;
   cudaSetDevice(c->device);
-  switch (c->plan.nd) { case 1: launch_prim<1>(c); break; case 2: launch_prim<2>(c); break; default: launch_prim<3>(c); }
+  launch_prim_nd(c);
 }
 
 int osb_download(osb_ctx *c, const char *name, double *host) {

@@ -417,6 +417,7 @@ __global__ void k_signal(unsigned long long *a, unsigned long long *b, unsigned 
   __threadfence_system();
 }
 __global__ void k_wait(const unsigned long long *a, const unsigned long long *b, unsigned long long e, unsigned long long *err) {
+  if (*(const volatile unsigned long long *)err) return;      // an earlier wait timed out: do not stall every later stage for 10 s more
   const long long t0 = clock64();
   while ((a && *(const volatile unsigned long long *)a < e) || (b && *(const volatile unsigned long long *)b < e)) {
     __nanosleep(500);

@@ -74,6 +74,8 @@ def local_plan(plan, rank, world):
     k0, _ = local_extent(plan, rank, world)
     if plan.get('fields'):
         p['fields'] = {n: np.ascontiguousarray(np.asarray(a)[k0:k0 + loc + 2 * h]) for n, a in plan['fields'].items()}
+    if plan.get('user_fields'):
+        p['user_fields'] = {n: np.ascontiguousarray(np.asarray(a)[k0:k0 + loc + 2 * h]) for n, a in plan['user_fields'].items()}
     for d in range(nd):
         for s in range(2):
             b = plan['bc'][d][s]

@@ -174,6 +174,11 @@ def resolve(plan_sym, env):
             for f in (name, 'S' + name + str(d)):
                 p['fields'][f] = cold.array(f).copy()
     p['user_kernels'] = [user_kernel_source(k, n, env, nd) for n, k in enumerate(plan_sym.get('user_kernels', []))]
+    # datasets the user kernels only read and the cold path has evaluated (coordinates, metric terms ...): shipped with the
+    # plan; the runtime declares and uploads those the solver does not hold itself
+    written = set(w for k in p['user_kernels'] for w in k['writes'])
+    p['user_fields'] = {f: cold.array(f).copy() for k in p['user_kernels'] for f in k['fields']
+                        if f not in written and f in cold.arrays and f not in plan_sym['q_names']}
     if plan_sym.get('monitor'):
         m = dict(plan_sym['monitor'])
         m['probes'] = [[int(c_eval(x, env)) for x in pr] for pr in m['probes']]

@@ -14,7 +14,7 @@ _lib = None
 
 FAMILIES = ('prim', 'flux', 'central', 'viscous', 'rk', 'bc', 'sync', 'user')
 
-SYMBOLS = ('osb_create', 'osb_destroy', 'osb_last_error', 'osb_set_const_f64', 'osb_get_const_f64', 'osb_set_iteration', 'osb_get_iteration', 'osb_add_user_kernel', 'osb_run_user_kernels', 'osb_read_point',
+SYMBOLS = ('osb_create', 'osb_destroy', 'osb_last_error', 'osb_set_const_f64', 'osb_get_const_f64', 'osb_set_iteration', 'osb_get_iteration', 'osb_create_field', 'osb_add_user_kernel', 'osb_run_user_kernels', 'osb_read_point',
            'osb_num_fields', 'osb_field_name', 'osb_field_info', 'osb_upload', 'osb_download', 'osb_device_ptr', 'osb_upload_face',
            'osb_step', 'osb_step_begin', 'osb_stage', 'osb_sync', 'osb_apply_bcs', 'osb_residual', 'osb_step_timed', 'osb_timer_start', 'osb_timer_stop', 'osb_advance_host',
            'osb_launch_count', 'osb_profile_step', 'osb_ipc_export', 'osb_ipc_import', 'osb_halo_push',
@@ -48,6 +48,7 @@ def load_library(path=None):
     lib.osb_get_iteration.restype = ctypes.c_longlong
     lib.osb_add_user_kernel.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
     lib.osb_run_user_kernels.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.osb_create_field.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
     lib.osb_read_point.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]
     lib.osb_num_fields.argtypes = [ctypes.c_void_p]
     lib.osb_field_info.argtypes = [ctypes.c_void_p, ctypes.c_char_p] + [ctypes.POINTER(ctypes.c_int)] * 3
@@ -110,8 +111,14 @@ class Simulation(object):
                     t = np.ascontiguousarray(b['table'], dtype=np.float64)
                     self._check(self.lib.osb_upload_face(self.ctx, d, s, t.ctypes.data), 'osb_upload_face')
         # point-wise user kernels (statistics): CUDA source written by opensbli_b200.run.resolve, compiled by NVRTC
+        # datasets that only user kernels read (e.g. coordinates evaluated by the cold path): declared and uploaded first
+        known = set(self.field_names())
+        for name, arr in plan.get('user_fields', {}).items():
+            if name not in known:
+                self._check(self.lib.osb_create_field(self.ctx, name.encode()), 'osb_create_field')
+                self.upload(name, arr)
         for k in plan.get('user_kernels', []):
-            self.add_user_kernel(k['source'], k['entry'], k['fields'], k['range'], k['when'])
+            self.add_user_kernel(k['source'], k['entry'], k['fields'], k['range'], k['when'], k.get('writes'))
 
     # -- plumbing
     def _check(self, rc, what):
@@ -171,11 +178,14 @@ class Simulation(object):
     def set_const(self, name, value):
         self._check(self.lib.osb_set_const_f64(self.ctx, name.encode(), float(value)), 'osb_set_const_f64')
 
-    def add_user_kernel(self, source, entry, fields, rng, when):
-        """when: 'iteration_end' (launched at the end of every time step) | 'after_loop' (run_user_kernels('after_loop'))"""
+    def add_user_kernel(self, source, entry, fields, rng, when, writes=None):
+        """when: 'iteration_end' (launched at the end of every time step) | 'after_loop' (run_user_kernels('after_loop')).
+        `writes`: the names among `fields` the kernel assigns (created zero-initialised when new); a name it only reads
+        must already exist on the device.  writes=None treats every name as written (the pre-existing call shape)."""
         r = (ctypes.c_int * 6)(*(list(rng) + [0, 1] * 3)[:6])
         w = {'iteration_end': 0, 'after_loop': 1}[when]
-        self._check(self.lib.osb_add_user_kernel(self.ctx, source.encode(), entry.encode(), ','.join(fields).encode(), r, w), 'osb_add_user_kernel')
+        names = [('+' + f) if (writes is None or f in writes) else f for f in fields]
+        self._check(self.lib.osb_add_user_kernel(self.ctx, source.encode(), entry.encode(), ','.join(names).encode(), r, w), 'osb_add_user_kernel')
 
     def run_user_kernels(self, when='after_loop'):
         self._check(self.lib.osb_run_user_kernels(self.ctx, {'iteration_end': 0, 'after_loop': 1}[when]), 'osb_run_user_kernels')

@@ -44,6 +44,13 @@ CONFIGS = {
     # config 4: shipped Katzer SBLI app (ReducedAccess closures) and a variant with the default Carpenter closures
     'katzer': (REF + '/apps/katzer_SBLI/katzer_SBLI.py', []),
     'katzer_carpenter': (REF + '/apps/katzer_SBLI/katzer_SBLI.py', [(", scheme=ReducedAccess())", ")")]),
+    # config 4 as BASELINE.json words it: the same app with WENO-Z instead of adaptive TENO (no shock sensor)
+    'katzer_wenoz': (REF + '/apps/katzer_SBLI/katzer_SBLI.py', [
+        ("sc1 = \"**{\\'scheme\\':\\'Teno\\'}\"", "sc1 = \"**{\\'scheme\\':\\'Weno\\'}\""),
+        ("constituent.add_equations(shock_sensor)", "pass"),
+        ("LLF = LLFTeno(teno_order, formulation='adaptive', averaging=Avg, sensor=sensor_array, store_sensor=True)",
+         "LLF = LLFWeno(5, formulation='Z', averaging=Avg)"),
+        (", DataObject('D11'), DataObject('TENO')])", ", DataObject('D11')])")]),
     # 3-D turbulent channel (TENO6, Carpenter closures, stretched wall-normal grid, isothermal walls, power-law viscosity,
     # body force, SSP-RK3), statistics gathering switched off (it is outside the hot path)
     'tcf_teno6': (REF + '/apps/channel_flow/compressible_TCF_TENO/turbulent_channel.py', [("stats = True", "stats = False")]),

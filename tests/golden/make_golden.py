@@ -92,6 +92,18 @@ def katzer_dirichlet_table(N0, halo=5):
 FIXTURES['katzer_60x40'] = ('katzer', katzer_plan(60, 40), [1, 10])
 
 
+def katzer_wenoz_plan(N0, N1):
+    """BASELINE.json configs[3] as worded: the Katzer app with LLFWeno(5, formulation='Z') in place of adaptive TENO."""
+    p = katzer_plan(N0, N1)
+    p.update(conv='weno', order=5, weno_formulation='Z', teno_adaptive=False)
+    for k in ('eps', 'TENO_CT', 'teno_a1', 'teno_a2', 'epsilon'):
+        p['constants'].pop(k)
+    return p
+
+
+FIXTURES['katzer_wenoz_60x40'] = ('katzer_wenoz', katzer_wenoz_plan(60, 40), [1, 10])
+
+
 def carpenter_tables():
     """First-derivative rows of the reference's Carpenter closure, taken from the scheme object itself
     (Carpenter_scheme.py:78-102, a 4x6 matrix al4^-1 ar4 evaluated by SymPy); second-derivative rows :69-76."""

@@ -278,3 +278,46 @@ def test_cuda_graph_replay_with_buffer_role_exchange(osb, name):
             ra, rb = a.residual(), b.residual()          # the parity entry point works on whichever buffers hold the roles now
             for x, y in zip(ra, rb):
                 assert np.array_equal(x, y), (name, done, 'residual')
+
+
+@pytest.mark.parametrize('name', ['tgv_teno5_16', 'tgv_central4_16'])
+def test_graph_replay_refreshes_primitives_and_iteration(osb, name):
+    """A replayed CUDA graph re-applies the host-side effects of the captured steps: primitives handed out after a replay are
+    those of the current state (the fused stage kernels never write u/p/T), and the iteration counter advances."""
+    plan, states = load_fixture(name)
+    q0 = initial_padded(plan, states)
+    with osb.Simulation(plan) as a, osb.Simulation(plan) as b:
+        a.set_state(q0)
+        b.set_state(q0)
+        for n in (4, 4, 6):
+            a.step(n)                       # graph replays (two-step units)
+            for _ in range(n):
+                b.step(1)                   # direct launches
+            pa, pb = a.download('p'), b.download('p')
+            assert np.array_equal(pa, pb), name
+            assert a.get_iteration() == b.get_iteration()
+        assert a.get_iteration() == 14
+
+
+def test_user_kernel_reads_current_primitives_and_rejects_unknown_inputs(osb):
+    """Point-wise user kernels on the fused 3-D paths: a kernel reading a primitive sees the constituent relations of the
+    current state (the stage kernels never write those arrays); a kernel reading a dataset nobody provided is refused."""
+    plan, states = load_fixture('tgv_teno5_16')
+    src = ('struct UserFields { double *p[48]; };\n'
+           'extern "C" __global__ void k(long long off, int n0, int n1, int n2, int lo0, int lo1, int lo2, long long s1, long long s2, UserFields f) {\n'
+           '  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, kk = blockIdx.z;\n'
+           '  if (i >= n0 || j >= n1 || kk >= n2) return;\n'
+           '  const long long X = off + (lo0 + i) + (lo1 + j) * s1 + (lo2 + kk) * s2;\n'
+           '  f.p[1][X] = f.p[1][X] + f.p[0][X];\n}\n')
+    with osb.Simulation(plan) as sim:
+        sim.add_user_kernel(src, 'k', ['p', 'psum'], [0, 16, 0, 16, 0, 16], 'iteration_end', writes=['psum'])
+        sim.set_state(initial_padded(plan, states))
+        acc = np.zeros((16, 16, 16))
+        for _ in range(3):
+            sim.step(1)
+            q = inner(plan, sim.get_state())
+            acc += 0.4 * (q[4] - 0.5 * (q[1] ** 2 + q[2] ** 2 + q[3] ** 2) / q[0])
+        got = sim.download('psum')[5:-5, 5:-5, 5:-5]
+        assert np.allclose(got, acc, rtol=1e-13, atol=0), float(np.abs(got - acc).max())
+        with pytest.raises(osb.BackendError, match='does not exist'):
+            sim.add_user_kernel(src, 'k', ['x0', 'psum2'], [0, 16, 0, 16, 0, 16], 'iteration_end', writes=['psum2'])

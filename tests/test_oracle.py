@@ -99,3 +99,23 @@ def test_oracle_matches_reference_executable(config, fixture):
     q, _ = ou.oracle_advance(plan, [r0[f].copy() for f in fields], 2)
     err = field_errors(plan, inner(plan, q), inner(plan, [r2[f] for f in fields]))
     assert max(err) < tol_for(plan, 2), err
+
+
+def test_reference_noise_floor_weno_z():
+    """Why WENO-Z parity is asserted at 1e-9 and not at 1e-12 (tests/common.py): the reference's OWN generated C, built twice
+    (ref_seq: g++ -O2 -ffp-contract=off; ref_omp: g++ -O3 -march=x86-64-v3, FMA contraction on), disagrees with itself by
+    ~5e-11 after ONE step of the Sod WENO-Z case, because with eps = 1e-14 its Horner-form smoothness indicators lose all
+    digits where beta <~ 1e-12.  No independent implementation can sit closer to "the reference" than its two builds sit to
+    each other.  The same two builds of the WENO-JS and TENO cases agree to round-off."""
+    if not (ou.have_ref('sod_wenoz5') and ou.have_ref('sod_wenojs5')):
+        pytest.skip('oracle/_ref not built (python oracle/gen_ref.py)')
+    names = ['rho', 'rhou0', 'rhoE']
+
+    def two_builds(config, n):
+        a = ou.run_ref(config, dict(block0np0=n, niter=1), names, exe='ref_seq')
+        b = ou.run_ref(config, dict(block0np0=n, niter=1), names, exe='ref_omp', threads=1)
+        return max(float(np.abs(a[f] - b[f]).max() / np.abs(a[f]).max()) for f in names)
+    z, js = two_builds('sod_wenoz5', 200), two_builds('sod_wenojs5', 800)
+    print('two builds of the reference, one step: WENO-Z %.2e  WENO-JS %.2e' % (z, js))
+    assert 1e-12 < z < 1e-9, z          # the noise floor itself: above the north-star 1e-12, below the asserted 1e-9
+    assert js < 1e-13, js
