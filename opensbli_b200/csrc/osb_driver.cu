@@ -15,6 +15,7 @@
 #include <vector>
 #include "../../include/osbli_b200.h"
 #include "osb_kernels.cuh"
+#include "osb_flux_api.h"
 
 using namespace osb;
 
@@ -273,33 +274,16 @@ void neighbour_signal(osb_ctx *c, int kind);
 
 // Sweep order: in 3-D the z sweep (the only one that reads the halos owned by neighbour ranks of a slab decomposition)
 // goes first, so that the "read done" notification overlaps with the x and y sweeps.
+// third-generation sweeps (osb_flux3.cuh, one translation unit per ndim x reconstruction)
 template <int ND, int RECON, int AVG>
 void launch_flux(osb_ctx *c) {
-  const GridDev &g = c->grid;
+  FluxArgs a{c->grid, c->fp, c->pc, c->sp, c->ad, c->gp};
   if (ND >= 3) {
-    const long long TR = (long long)(g.np[2] + 6) * g.np[1];
-    dim3 b(32, F2_TY, 1), gr((unsigned)((TR + F2_RT - 7) / (F2_RT - 6)), (g.np[0] + 31) / 32, 1);
-    auto kern = k_flux2_yz<3, 2, RECON, AVG, false>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_yz_smem_bytes<3>());   // per device: set on every launch
-    { Launcher L(c, OSB_FAM_FLUX); kern<<<gr, b, f2_yz_smem_bytes<3>(), c->stream>>>(g, c->fp, c->pc, c->sp, c->ad, c->gp); }
+    { Launcher L(c, OSB_FAM_FLUX); flux3_sweep(ND, RECON, 2, AVG, false, a, c->stream); }
     neighbour_signal(c, 0);
   }
-  {
-    const long long T = (long long)(g.np[0] + 6) * g.np[1] * g.np[2];
-    const long long nb = (T + F2_BT - 7) / (F2_BT - 6);
-    Launcher L(c, OSB_FAM_FLUX);
-    if (ND >= 3) k_flux2_x<ND, RECON, AVG, true><<<(unsigned)nb, F2_BT, 0, c->stream>>>(g, c->fp, c->pc, c->sp, c->ad, c->gp);
-    else k_flux2_x<ND, RECON, AVG, false><<<(unsigned)nb, F2_BT, 0, c->stream>>>(g, c->fp, c->pc, c->sp, c->ad, c->gp);
-  }
-  if (ND >= 2) {
-    const long long TR = (long long)(g.np[1] + 6) * (ND > 2 ? g.np[2] : 1);
-    dim3 b(32, F2_TY, 1), gr((unsigned)((TR + F2_RT - 7) / (F2_RT - 6)), (g.np[0] + 31) / 32, 1);
-    constexpr int N2 = (ND >= 2 ? ND : 2);
-    auto kern = k_flux2_yz<N2, 1, RECON, AVG, true>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2_yz_smem_bytes<N2>());
-    Launcher L(c, OSB_FAM_FLUX);
-    kern<<<gr, b, f2_yz_smem_bytes<N2>(), c->stream>>>(g, c->fp, c->pc, c->sp, c->ad, c->gp);
-  }
+  { Launcher L(c, OSB_FAM_FLUX); flux3_sweep(ND, RECON, 0, AVG, ND >= 3, a, c->stream); }
+  if (ND >= 2) { Launcher L(c, OSB_FAM_FLUX); flux3_sweep(ND, RECON, 1, AVG, true, a, c->stream); }
   if (ND < 3) neighbour_signal(c, 0);
 }
 

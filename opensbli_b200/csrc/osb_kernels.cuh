@@ -4,7 +4,7 @@
 // (SURVEY.md section 2b / appendix A):
 //   k_prim                     CRu_i, CRp, CRa, CRT, CRmu            (constituent relations, one fused pass)
 //   k_theta                    modified Ducros sensor (adaptive TENO)
-//   k_flux2_x / k_flux2_yz     LLF{Weno,Teno}_reconstruction_d + Residual (staged flux sweep + flux difference, fused)
+//   k_flux3_x / k_flux3_yz     LLF{Weno,Teno}_reconstruction_d + Residual (staged flux sweep + flux difference, fused): osb_flux3.cuh
 //   k_flux_curv2d / k_resid_curv2d   the same on fully curvilinear 2-D grids (metric-aware eigensystem)
 //   k_central / k_central_general    Convective terms group / CD / residual (Blaisdell / Feiereisen splits, closures, metrics)
 //   k_viscous / k_viscous_general    Derivative evaluation CD + Viscous terms (fused, mixed derivatives on the fly)
@@ -17,52 +17,9 @@
 #pragma once
 #include "osb_math.cuh"
 #include "osb_flux.cuh"
+#include "osb_types.cuh"
 
 namespace osb {
-
-struct GridDev {
-  int nd;
-  int np[3];          // interior points
-  int pd[3];          // padded dims (np + 2h in active dims)
-  long long s[3];     // strides
-  long long off;      // linear index of point (0,0,0)
-  int h;              // storage halo
-  int zlen;           // planes per block of the z-marching kernels (32 on large grids, shorter when that leaves SMs idle)
-  long long n;        // padded size
-};
-
-struct FieldPtrs {
-  double *q[5];       // rho, rhou0.., rhoE
-  double *u[3];       // velocities
-  double *p, *a, *T;
-  double *R[5];       // Residual
-  double *rk[5];      // RK register (tempRK_* or *_RKold)
-};
-
-struct PhysConst {
-  double gama, Minf, Re, Pr, dt;
-  double inv[3], inv2[3];   // 1/Delta_d, 1/Delta_d^2
-  // general path
-  int visc_law;             // 0 constant, 1 Sutherland, 2 power law
-  double SuthT, RefT, mu_exp, Twall, sensor_eps;
-  double force[3];          // constant body force c_j (channel apps): momentum_i -= c_i, energy -= c_j u_j
-  double src_factor;        // sin(src_rate * iteration) of the mass source, refreshed by the host every step
-};
-
-// one-sided closure tables (reduced_access_scheme.py:36-83, Carpenter_scheme.py:38-102): rows idx = 0..nr-1 next to
-// side 0 x weights of the boundary-absolute points 0..np-1; side 1 mirrors them (sign -1 for first derivatives)
-struct Closures {
-  int on[3][2];
-  int nr1, np1, nr2, np2;
-  double d1[4 * 6], d2[2 * 6];
-};
-
-struct GeneralPtrs {
-  const double *D[3];       // D_dd metric (nullptr: direction not stretched)
-  const double *SD[3];      // SD_ddd
-  double *mu, *theta, *teno_store;
-  const double *src;        // mass-source amplitude (nullptr: none)
-};
 
 // -------------------------------------------------------------------------------------------------
 // constituent relations over [lo, hi) (grid + scheme halos)
@@ -96,197 +53,6 @@ __global__ void __launch_bounds__(256) k_prim(GridDev g, FieldPtrs f, PhysConst 
     if (c.visc_law == 1) mu[x] = (c.SuthT / c.RefT + 1.0) * (T * sqrt(T)) / (c.SuthT / c.RefT + T);
     else if (c.visc_law == 2) mu[x] = pow(T, c.mu_exp);
     else mu[x] = 1.0;
-  }
-}
-
-// -------------------------------------------------------------------------------------------------
-// Flux sweeps: the block first stages its points (conserved variables + constituent relations evaluated once
-// per point: 1/rho, p, a) in shared memory, then every thread evaluates interface fluxes from the staged window,
-// parks them in shared memory and differences them.  Points are numbered along the sweep direction including 3
-// halo points on both sides (-3 .. np+2) and pencils are concatenated, so a block is simply a run of consecutive
-// staged points (x) or staged rows (y/z); consecutive blocks overlap by 6.
-// -------------------------------------------------------------------------------------------------
-template <int ND>
-__device__ __forceinline__ void stage_values(const double *q, double gama, double *sv, int VS) {
-  typedef SV<ND> V;
-  const double rho = q[0], E = q[ND + 1];
-  const double irho = 1.0 / rho;
-  double ke = 0.0;
-#pragma unroll
-  for (int d = 0; d < ND; d++) {
-    const double m = q[1 + d];
-    sv[(V::M0 + d) * VS] = m;
-    const double u = m * irho;
-    ke += 0.5 * rho * u * u;
-  }
-  const double p = (gama - 1.0) * (E - ke);
-  sv[V::RHO * VS] = rho; sv[V::IRHO * VS] = irho; sv[V::E * VS] = E; sv[V::P * VS] = p;
-  sv[V::A * VS] = sqrt(gama * p * irho);
-}
-
-// Loads whose values are needed only at the end of a block / plane iteration (old Residual, RK register) would expose their
-// DRAM latency to every warp at once where they are used: the lines are requested into L2 up front (a few lanes per warp).
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-template <int ND>
-__device__ __forceinline__ void stage_point(const FieldPtrs &f, long long x, double gama, double *sv, int VS) {
-  double q[ND + 2];
-#pragma unroll
-  for (int m = 0; m < ND + 2; m++) q[m] = __ldg(f.q[m] + x);
-  stage_values<ND>(q, gama, sv, VS);
-}
-
-constexpr int F2_BT = 128;            // x-sweep: staged points per block (BT-6 residual points)
-constexpr int F2_TY = 4;              // y/z sweeps: thread rows
-constexpr int F2_RT = 21;             // y/z sweeps: staged rows per block (RT-5 = 16 interface rows, RT-6 = 15 point rows)
-template <int ND> constexpr size_t f2_yz_smem_bytes() { return sizeof(double) * (SV<ND>::N + ND + 2) * F2_RT * 32; }
-
-template <int ND, int RECON, int AVG, bool ACCUM>
-__global__ void __launch_bounds__(F2_BT, 3) k_flux2_x(GridDev g, FieldPtrs f, PhysConst c, SchemeParams sp, AdaptiveCT ad, GeneralPtrs gp) {
-  constexpr int NV = ND + 2, NVAL = SV<ND>::N;
-  __shared__ double sP[NVAL][F2_BT];
-  __shared__ double sF[NV][F2_BT];
-  const int t = threadIdx.x;
-  const long long NPR = g.np[0] + 6;
-  const long long T = NPR * g.np[1] * g.np[2];
-  const long long fidx = (long long)blockIdx.x * (F2_BT - 6) + t;
-  const bool inside = fidx < T;
-  int ip = 0;
-  long long x = 0;
-  if (inside) {
-    ip = (int)(fidx % NPR) - 3;
-    const long long row = fidx / NPR;
-    const int j = (int)(row % g.np[1]), k = (int)(row / g.np[1]);
-    x = g.off + ip + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
-    stage_point<ND>(f, x, c.gama, &sP[0][t], F2_BT);
-  }
-  __syncthreads();
-  const bool iface = inside && t >= 2 && t <= F2_BT - 4 && ip >= -1 && ip <= g.np[0] - 1;
-  if (iface) {
-    double fl[NV];
-    if (ad.on) {                      // sensor value of the interface's left point (0 in the halos)
-      const int e = adaptive_exponent(ad, gp.theta[x]);
-      sp.teno_ct = ad.ct[e]; sp.kfast5 = ad.k5[e]; sp.kfast6 = ad.k6[e];
-      if (gp.teno_store) gp.teno_store[x] = sp.teno_ct;
-    }
-    interface_flux_staged<ND, 0, RECON, AVG>(&sP[0][t - 2], 1, F2_BT, c.gama, sp, fl);
-#pragma unroll
-    for (int m = 0; m < NV; m++) sF[m][t] = fl[m];
-  }
-  __syncthreads();
-  if (iface && t >= 3 && ip >= 0) {
-    double old[NV];
-    if (ACCUM) {
-#pragma unroll
-      for (int m = 0; m < NV; m++) old[m] = f.R[m][x];
-    }
-    const double met = gp.D[0] ? -c.inv[0] * gp.D[0][x] : -c.inv[0];
-#pragma unroll
-    for (int m = 0; m < NV; m++) {
-      const double r = met * (sF[m][t] - sF[m][t - 1]);
-      f.R[m][x] = ACCUM ? old[m] + r : r;
-    }
-  }
-}
-
-template <int ND, int DIR, int RECON, int AVG, bool ACCUM>
-__global__ void __launch_bounds__(32 * F2_TY, 3) k_flux2_yz(GridDev g, FieldPtrs f, PhysConst c, SchemeParams sp, AdaptiveCT ad, GeneralPtrs gp) {
-  constexpr int NV = ND + 2, NVAL = SV<ND>::N;
-  constexpr int OTH = (DIR == 1) ? 2 : 1;
-  extern __shared__ double f2_smem[];                       // dynamic: more than the 48 KB static limit
-  double (*sP)[F2_RT][32] = reinterpret_cast<double (*)[F2_RT][32]>(f2_smem);
-  double (*sF)[F2_RT][32] = reinterpret_cast<double (*)[F2_RT][32]>(f2_smem + NVAL * F2_RT * 32);
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int i = blockIdx.y * 32 + tx;
-  const bool xin = i < g.np[0];
-  const long long NJR = g.np[DIR] + 6;
-  const long long nother = (ND > 2) ? g.np[OTH] : 1;
-  const long long TR = NJR * nother;
-  const long long r0 = (long long)blockIdx.x * (F2_RT - 6);
-  // stage RT rows: all loads are issued before the first use so their latencies overlap
-  {
-    constexpr int NIT = (F2_RT + F2_TY - 1) / F2_TY;
-    double raw[NIT][NV];
-    bool ok[NIT];
-#pragma unroll
-    for (int it = 0; it < NIT; it++) {
-      const int r = ty + it * F2_TY;
-      const long long fr = r0 + r;
-      ok[it] = xin && r < F2_RT && fr < TR;
-      if (ok[it]) {
-        const int jp = (int)(fr % NJR) - 3;
-        const int o = (int)(fr / NJR);
-        const long long x = g.off + i + (long long)jp * g.s[DIR] + (ND > 2 ? o * g.s[OTH] : 0);
-#pragma unroll
-        for (int m = 0; m < NV; m++) raw[it][m] = __ldg(f.q[m] + x);
-      }
-    }
-#pragma unroll
-    for (int it = 0; it < NIT; it++) {
-      const int r = ty + it * F2_TY;
-      if (ok[it]) stage_values<ND>(raw[it], c.gama, &sP[0][r][tx], F2_RT * 32);
-    }
-  }
-  __syncthreads();
-  // interface rows r = 2 .. RT-4
-#pragma unroll 1
-  for (int r = 2 + ty; r <= F2_RT - 4; r += F2_TY) {
-    const long long fr = r0 + r;
-    if (xin && fr < TR) {
-      const int jp = (int)(fr % NJR) - 3;
-      if (jp >= -1 && jp <= g.np[DIR] - 1) {
-        double fl[NV];
-        if (ad.on) {
-          const int o = (int)(fr / NJR);
-          const long long x = g.off + i + (long long)jp * g.s[DIR] + (ND > 2 ? o * g.s[OTH] : 0);
-          const int e = adaptive_exponent(ad, gp.theta[x]);
-          sp.teno_ct = ad.ct[e]; sp.kfast5 = ad.k5[e]; sp.kfast6 = ad.k6[e];
-        }
-        interface_flux_staged<ND, DIR, RECON, AVG>(&sP[0][r - 2][tx], 32, F2_RT * 32, c.gama, sp, fl);
-#pragma unroll
-        for (int m = 0; m < NV; m++) sF[m][r][tx] = fl[m];
-      }
-    }
-  }
-  __syncthreads();
-  // flux differences; when accumulating, all old residual values are fetched before the first store
-  // (the compiler must assume the Residual arrays alias and would otherwise serialise load-add-store chains)
-  {
-    constexpr int NIT = (F2_RT - 6 + F2_TY - 1) / F2_TY;
-    double old[NIT][NV];
-    long long xs[NIT];
-    bool ok[NIT];
-#pragma unroll
-    for (int it = 0; it < NIT; it++) {
-      const int r = 3 + ty + it * F2_TY;
-      const long long fr = r0 + r;
-      ok[it] = false;
-      xs[it] = 0;
-      if (xin && r <= F2_RT - 4 && fr < TR) {
-        const int jp = (int)(fr % NJR) - 3;
-        if (jp >= 0 && jp <= g.np[DIR] - 1) {
-          const int o = (int)(fr / NJR);
-          xs[it] = g.off + i + (long long)jp * g.s[DIR] + (ND > 2 ? o * g.s[OTH] : 0);
-          ok[it] = true;
-          if (ACCUM) {
-#pragma unroll
-            for (int m = 0; m < NV; m++) old[it][m] = f.R[m][xs[it]];
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int it = 0; it < NIT; it++) {
-      const int r = 3 + ty + it * F2_TY;
-      if (ok[it]) {
-        const double met = gp.D[DIR] ? -c.inv[DIR] * gp.D[DIR][xs[it]] : -c.inv[DIR];
-#pragma unroll
-        for (int m = 0; m < NV; m++) {
-          const double rr = met * (sF[m][r][tx] - sF[m][r - 1][tx]);
-          f.R[m][xs[it]] = ACCUM ? old[it][m] + rr : rr;
-        }
-      }
-    }
   }
 }
 

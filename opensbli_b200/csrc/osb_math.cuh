@@ -35,6 +35,7 @@ struct SchemeParams {
   // derived on the host by make_scheme_params():
   double eps16;    // 16*eps: TENO5 works on g = 2f with beta'' = 16 beta(f)
   double kfast5;   // 0.98 (3 C_T)^(-1/6): if 1 + tau/D_min <= kfast every TENO5 stencil passes the cut-off
+  double kpass5;   // kfast5 - 1: the same test as  tau <= kpass5 D_r  for every r  (three compares, no minimum)
   double kfast6;   // 0.98 (4 C_T)^(-1/6): same for the 4 stencils of TENO6
 };
 
@@ -67,10 +68,45 @@ inline SchemeParams make_scheme_params(double eps, double ct) {
   s.eps = eps; s.teno_ct = ct; s.eps16 = 16.0 * eps;
   s.kfast5 = 0.98 * pow(3.0 * ct, -1.0 / 6.0);
   s.kfast6 = 0.98 * pow(4.0 * ct, -1.0 / 6.0);
+  s.kpass5 = s.kfast5 - 1.0;
   return s;
 }
 
 OSB_HD double sq(double x) { return x * x; }
+
+// max / min of two ordinary numbers as one compare + select.  fmax()/fmin() carry IEEE NaN semantics, which sm_100a has no
+// FP64 instruction for: each call compiles to DSETP + ~8 integer/select instructions (cuobjdump, r02), and the sweeps are
+// issue-bound.  The operands here are wave speeds / smoothness sums of a finite state.
+OSB_HD double dmax2(double a, double b) { return a > b ? a : b; }
+OSB_HD double dmin2(double a, double b) { return a < b ? a : b; }
+
+// 1/x and 1/sqrt(x) for ordinary positive x: hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~23 bits) + two Newton steps, no
+// special-case branches (the library routines guard denormals / infinities with a call to a slow path).  Relative error of the
+// result <~ 2 ulp.
+OSB_HD double rcp_nr(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+#else
+  return 1.0 / x;
+#endif
+}
+OSB_HD double rsqrt_nr(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-(x * y), y, 1.0);
+  y = fma(0.5 * y, e, y);
+  e = fma(-(x * y), y, 1.0);
+  return fma(0.5 * y, e, y);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
 OSB_HD double pow6(double x) { double x2 = x * x; return x2 * x2 * x2; }
 
 // 2^-e for m = 1.x * 2^e (m > 0, finite, normal): an exact power-of-two rescale that keeps the
@@ -115,8 +151,8 @@ OSB_HD Teno5Side teno5_front(double gm2, double gm1, double g0, double g1, doubl
   t.Q0 = 5.0 * g0 + (2.0 * g1 - gm1);
   t.Q1 = 5.0 * g1 + (2.0 * g0 - g2);
   t.Q2 = 11.0 * g0 + (2.0 * gm2 - 7.0 * gm1);
-  const double Dmin = fmin(t.D0, fmin(t.D1, t.D2));
-  t.all_pass = (Dmin + t.tau <= sp.kfast5 * Dmin);
+  // sufficient test for "every stencil passes": 1 + tau/D_min <= kfast5  <=>  tau <= (kfast5 - 1) D_r for r = 0, 1, 2
+  t.all_pass = (t.tau <= sp.kpass5 * t.D0) & (t.tau <= sp.kpass5 * t.D1) & (t.tau <= sp.kpass5 * t.D2);
   return t;
 }
 namespace teno5c {
@@ -134,7 +170,7 @@ OSB_HD double teno5_resolve(const Teno5Side &t, const SchemeParams &sp) {
   using namespace teno5c;
   // P_r = (D_r + tau) * prod_{s != r} D_s ; alpha_r = (P_r / (D0 D1 D2))^6   (teno.py:207-212, C=1, q=6)
   const double P0 = (t.D0 + t.tau) * (t.D1 * t.D2), P1 = (t.D1 + t.tau) * (t.D0 * t.D2), P2 = (t.D2 + t.tau) * (t.D0 * t.D1);
-  const double sc = inv_pow2(fmax(P0, fmax(P1, P2)));
+  const double sc = inv_pow2(dmax2(P0, dmax2(P1, P2)));
   const double a0 = pow6(P0 * sc), a1 = pow6(P1 * sc), a2 = pow6(P2 * sc);
   const double thr = sp.teno_ct * (a0 + a1 + a2);                                 // teno.py:445-465
   const bool k0 = !(thr > a0), k1 = !(thr > a1), k2 = !(thr > a2);
@@ -166,7 +202,7 @@ OSB_HD double teno6_side(double fm2, double fm1, double f0, double f1, double f2
   const double D01 = D0 * D1, D23 = D2 * D3;
   const double P0 = (D0 + tau) * (D1 * D23), P1 = (D1 + tau) * (D0 * D23);
   const double P2 = (D2 + tau) * (D01 * D3), P3 = (D3 + tau) * (D01 * D2);
-  const double sc = inv_pow2(fmax(fmax(P0, P1), fmax(P2, P3)));
+  const double sc = inv_pow2(dmax2(dmax2(P0, P1), dmax2(P2, P3)));
   const double A0 = pow6(P0 * sc), A1 = pow6(P1 * sc), A2 = pow6(P2 * sc), A3 = pow6(P3 * sc);
   const double thr = sp.teno_ct * (A0 + A1 + A2 + A3);
   const double w0 = !(thr > A0) ? (231.0 / 500.0) : 0.0, w1 = !(thr > A1) ? (3.0 / 10.0) : 0.0;

@@ -30,7 +30,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB
+    path = path or os.environ.get('OSB_B200_LIB') or LIB
     if not os.path.exists(path):
         raise BackendError('%s not found: build it with `python -m opensbli_b200.build` '
                            '(the B200 back end has no CPU fallback)' % path)

@@ -68,8 +68,8 @@ def test_product_never_imports_oracle():
 def hostcheck():
     src = os.path.join(REPO, 'tests', 'csrc', 'host_math_check.cpp')
     so = os.path.join(REPO, 'tests', 'csrc', 'libhostcheck.so')
-    hdr = os.path.join(REPO, 'opensbli_b200', 'csrc', 'osb_math.cuh')
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(REPO, 'opensbli_b200', 'csrc', h) for h in ('osb_math.cuh', 'osb_flux.cuh', 'osb_flux3.cuh')]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in [src] + hdrs):
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared', src, '-o', so])
     return ctypes.CDLL(so)
 
@@ -114,6 +114,12 @@ def test_device_math_matches_oracle(hostcheck, nd, recon, avg):
                                                     ctypes.c_double(1e-16), ctypes.c_double(1e-5), f2.ctypes.data_as(P))
             assert rc == 0
             worst = max(worst, np.abs(f1 - f2).max() / np.abs(f1).max())
+            # the pass-split form on the staged layout (what the sweep kernels inline)
+            for fn in (hostcheck.hostcheck_interface_flux_split,):
+                f3 = np.zeros(nv)
+                assert fn(nd, d, recon, avg, q.ctypes.data_as(P), ctypes.c_double(1.4), ctypes.c_double(1e-16), ctypes.c_double(1e-5),
+                          f3.ctypes.data_as(P)) == 0
+                worst = max(worst, np.abs(f1 - f3).max() / np.abs(f1).max())
         assert worst < 1e-13, (nd, d, recon, avg, worst)
 
 
