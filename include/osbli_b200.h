@@ -90,6 +90,18 @@ enum { OSB_FAM_PRIM = 0, OSB_FAM_FLUX = 1, OSB_FAM_CENTRAL = 2, OSB_FAM_VISCOUS 
 int osb_launch_count(const osb_ctx *ctx, long long *count);
 int osb_profile_step(osb_ctx *ctx, double *family_ms /* [OSB_NFAM] */, long long *family_launches /* [OSB_NFAM] */);
 
+/* In-loop diagnostics (device reductions, deterministic summation order; synchronise the stream):
+ * osb_nan_check counts the non-finite values of a dataset over the interior points -- what `ops_NaNcheck(rho_B0)` tests in the
+ * reference's time loop (core/diagnostics/simulation_monitors.py:112-113,180-181; utilities/helperfunctions.py:172-190,
+ * print_iteration_ops(NaN_check=...)).
+ * osb_diagnostics returns interior sums of this context's block: [0] sum rho, [1] sum 1/2 rho |u|^2 (kinetic energy),
+ * [2] sum 1/2 rho |curl u|^2 (enstrophy; 4th-order central differences, metric-scaled on stretched grids), [3] sum rhoE,
+ * [4] max Mach number, [5] number of points with non-finite rho or rhoE.  Ranks of a decomposed run add / max their values.
+ * (The reference computes the Taylor-Green kinetic energy and enstrophy offline from its dumps.) */
+enum { OSB_NDIAG = 6 };
+int osb_nan_check(osb_ctx *ctx, const char *name, long long *n_nonfinite);
+int osb_diagnostics(osb_ctx *ctx, double *sums /* [OSB_NDIAG] */);
+
 /* Point-wise user kernels (the reference's `User kernel` loops, e.g. the statistics accumulation of
  * apps/channel_flow/*: stats.py, opsc.py kernel emission): app-specific arithmetic outside the solver's hot loops, given as
  * CUDA C source of one `extern "C" __global__` entry with the signature

@@ -110,6 +110,7 @@ struct osb_ctx {
   long long iteration = 0;                      // loop counter of algorithm.py:440-474 (argument of the mass source)
   struct UserKernel { cudaLibrary_t lib = nullptr; cudaKernel_t kern = nullptr; std::vector<std::string> fields; int range[6]; int when = 0; };
   std::vector<UserKernel> user_kernels;
+  double *diag_buf = nullptr;                   // partial sums of the diagnostics kernels
   bool prim_stale = false;                      // u, p, a, T arrays lag the state (stage kernels that derive them on the fly)
   int swap_parity = 0;                          // fused central path: q and Residual buffers exchange roles every stage
 };
@@ -870,6 +871,7 @@ int osb_destroy(osb_ctx *c) {
   drop_graph(c);
   for (auto &k : c->user_kernels) if (k.lib) cudaLibraryUnload(k.lib);
   if (c->flags) cudaFree(c->flags);
+  if (c->diag_buf) cudaFree(c->diag_buf);
   for (auto &f : c->fields) cudaFree(f.dev);
   for (int d = 0; d < 3; d++) for (int s = 0; s < 2; s++) if (c->face_table[d][s]) cudaFree(c->face_table[d][s]);
   if (c->timer0) { cudaEventDestroy(c->timer0); cudaEventDestroy(c->timer1); }
@@ -1142,6 +1144,40 @@ int osb_advance_host(osb_ctx *c, const double *const *q_in, double *const *q_out
   return rc;
 }
 
+// ---- in-loop diagnostics ---------------------------------------------------------------------------
+static int run_diag(osb_ctx *c, const double *field, double *out) {
+  cudaSetDevice(c->device);
+  const int nblocks = 148 * 4;
+  if (!c->diag_buf) OSB_CUDA(c, cudaMalloc(&c->diag_buf, sizeof(double) * DIAG_N * (nblocks + 1)));
+  double *partial = c->diag_buf + DIAG_N, *res = c->diag_buf;
+  {
+    Launcher L(c, OSB_FAM_USER);
+    switch (c->plan.nd) {
+      case 1: k_diag_partial<1><<<nblocks, 256, 0, c->stream>>>(c->grid, c->fp, c->pc, c->gp, field, partial); break;
+      case 2: k_diag_partial<2><<<nblocks, 256, 0, c->stream>>>(c->grid, c->fp, c->pc, c->gp, field, partial); break;
+      default: k_diag_partial<3><<<nblocks, 256, 0, c->stream>>>(c->grid, c->fp, c->pc, c->gp, field, partial); break;
+    }
+  }
+  { Launcher L(c, OSB_FAM_USER); k_diag_final<<<1, 32, 0, c->stream>>>(partial, nblocks, res); }
+  OSB_CUDA(c, cudaMemcpyAsync(out, res, sizeof(double) * DIAG_N, cudaMemcpyDeviceToHost, c->stream));
+  OSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int osb_nan_check(osb_ctx *c, const char *name, long long *n_bad) {
+  if (!c || !name || !n_bad) return 1;
+  Field *f = find_field(c, name);
+  if (!f) return fail(c, std::string("unknown field ") + name);
+  refresh_primitives_for(c, f);
+  double out[DIAG_N];
+  if (run_diag(c, f->dev, out)) return 1;
+  *n_bad = (long long)out[5];
+  return 0;
+}
+int osb_diagnostics(osb_ctx *c, double *sums) {
+  if (!c || !sums) return 1;
+  return run_diag(c, nullptr, sums);
+}
+
 int osb_launch_count(const osb_ctx *c, long long *n) { if (!c || !n) return 1; *n = c->launches; return 0; }
 
 int osb_profile_step(osb_ctx *c, double *fam_ms, long long *fam_n) {
@@ -1153,8 +1189,12 @@ int osb_profile_step(osb_ctx *c, double *fam_ms, long long *fam_n) {
   c->profiling = false;
   OSB_CUDA(c, cudaStreamSynchronize(c->stream));
   for (int i = 0; i < OSB_NFAM; i++) { fam_ms[i] = 0.0; if (fam_n) fam_n[i] = 0; }
+  const bool list = getenv("OSB_PROFILE_LIST") != nullptr;       // per-launch times in launch order (kernel experiments)
+  int idx = 0;
   for (auto &pe : c->prof_events) {
     float t = 0; cudaEventElapsedTime(&t, pe.second.first, pe.second.second);
+    if (list && t > 0.2f) fprintf(stderr, "osb_profile launch %d family %d %.3f ms\n", idx, pe.first, t);
+    idx++;
     fam_ms[pe.first] += t; if (fam_n) fam_n[pe.first]++;
     cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second);
   }

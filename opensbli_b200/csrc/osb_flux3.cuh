@@ -5,31 +5,30 @@
 // interface per thread from the staged window to the flux in registers (168 registers, 12 warps per SM, FP64 pipe 50 %
 // busy, top stall "wait" on dependent DFMA chains, ncu r01).  Here the work of an interface is cut into short passes that
 // hand their results over through a THREAD-PRIVATE column of shared memory (no barrier: the same thread writes and reads):
-//     pass 0   interface state (Roe / simple average), u_d and the three max wave speeds over the 6-point stencil
-//     pass 1a  S, w_d per stencil point -> doubled split fluxes g+ / g- of the entropy and the two acoustic waves -> column G
-//     pass 2a  rolled loop over those 3 waves: reconstruction of both sides from G (TENO5: 10 values per wave)
-//     pass 1b  shear waves (need neither S nor w_d) -> G ;  pass 2b  rolled loop over them
-//     pass 3   flux = R . rec ; parked in the thread's own column for the flux difference
-// so that at most ~45 doubles are live at any point.  The kernels are compiled for 5 blocks x 128 threads (x) and
-// 2 blocks x 320 threads (y/z) per SM = 20 warps, and the rolled wave loops shrink the code (instruction-cache misses were
-// the "no_instruction" stalls of the unrolled 5-wave body).
+//     pass 0   interface state (Roe / simple average), the three max wave speeds over the 6-point stencil
+//     pass 1   S and w_d per stencil point -> doubled split fluxes g+ / g- of the two acoustic waves and S itself -> column
+//     pass 2   rolled loop over the acoustic waves: reconstruction of both sides from the column (TENO5: 10 values per wave)
+//     pass 3   rolled loop over the entropy wave (from S) and the shear waves (need neither S nor w_d): split fluxes formed
+//              in registers from the staged window, reconstructed at once
+//     pass 4   flux = R . rec ; parked in the thread's own column for the flux difference
+// so that at most ~45 doubles are live at any point, and the rolled wave loops shrink the code (instruction-cache misses were
+// the "no_instruction" stalls of the unrolled 5-wave body).  Round-2 ncu: the first cut of this design (all five waves through
+// the column) ran into the shared-memory pipe (wavefronts 77 % of peak); only the waves that share S and w_d go through it now.
 #pragma once
 #include "osb_math.cuh"
 #include "osb_flux.cuh"
 
 namespace osb {
 
-// values per wave in the column G: TENO5 / WENO5 use f(-2..2) of each side, TENO6 all six
-template <int RECON> struct F3 { static constexpr int NG = (RECON == RECON_TENO6) ? 12 : 10, NW = 3; };
+// values per wave handed to the reconstruction: TENO5 / WENO5 use f(-2..2) of each side, TENO6 all six.
+// Column of a thread: two acoustic waves x NG split fluxes, then S of the 6 stencil points.
+template <int RECON> struct F3 { static constexpr int NG = (RECON == RECON_TENO6) ? 12 : 10, NCOL = 2 * NG + 6; };
 
-// one side pair of a wave from the column: G[k * GS], k < NG;  right-biased values first (points 0..), then the
-// left-biased ones already mirrored (points 5, 4, ..)
+// both sides of one characteristic wave: a[] right-biased values (points 0..), b[] left-biased ones already mirrored
+// (points 5, 4, ..); returns recon+(f+) + recon-(f-) with f+- = g+-/2  (shock_capturing.py:479-495)
 template <int RECON>
-OSB_HD double f3_wave(const double *G, const int GS, const SchemeParams &sp) {
+OSB_HD double f3_recon(const double *a, const double *b, const SchemeParams &sp) {
   constexpr int NS = F3<RECON>::NG / 2;
-  double a[NS], b[NS];
-#pragma unroll
-  for (int k = 0; k < NS; k++) { a[k] = G[k * GS]; b[k] = G[(NS + k) * GS]; }
   if (RECON == RECON_TENO5) {
     const Teno5Side tp = teno5_front(a[0], a[1], a[2], a[3], a[4], sp);
     const Teno5Side tm = teno5_front(b[0], b[1], b[2], b[3], b[4], sp);
@@ -60,7 +59,7 @@ template <int ND, int DIR, int RECON, int AVG>
 OSB_HD void interface_flux_split(const double *sb, const int PS, const int VS, double *G, const int GS,
                                                      const double gama, const SchemeParams &sp, double *flux) {
   typedef SV<ND> V;
-  constexpr int NG = F3<RECON>::NG;
+  constexpr int NG = F3<RECON>::NG, NS = NG / 2;
   const double gm1 = gama - 1.0;
 #define SVAL(v, p) sb[(v) * VS + (p) * PS]
   // ---- pass 0: interface state between points 2 and 3 (averaging.py:31-59 simple, 62-114 Roe)
@@ -101,86 +100,90 @@ OSB_HD void interface_flux_split(const double *sb, const int PS, const int VS, d
   const double rsc = (ND == 1) ? 1.0 : 0.70710678118654752440 * rho * ia;
 
   // local wave speeds: max over the stencil of |u_d|, |u_d + a|, |u_d - a|  (shock_capturing.py:512-536)
-  double ud[6];
   double lam0 = 0.0, lamp = 0.0, lamm = 0.0;
 #pragma unroll
   for (int p = 0; p < 6; p++) {
-    const double ap = SVAL(V::A, p);
-    ud[p] = SVAL(V::UD, p);
-    lam0 = dmax2(lam0, fabs(ud[p]));
-    lamp = dmax2(lamp, fabs(ud[p] + ap));
-    lamm = dmax2(lamm, fabs(ud[p] - ap));
+    const double ap = SVAL(V::A, p), udp = SVAL(V::UD, p);
+    lam0 = dmax2(lam0, fabs(udp));
+    lamp = dmax2(lamp, fabs(udp + ap));
+    lamm = dmax2(lamm, fabs(udp - ap));
   }
-  // ---- pass 1a: entropy (wave 0) and acoustic (waves 1, 2) split fluxes -> G
+  // ---- pass 1: acoustic split fluxes and S -> column
   // split fluxes g+- = CF +- lam CS (shock_capturing.py:479-495; doubled, the 1/2 is in the reconstruction) with
   //   entropy   CS = rho - S/a^2          CF = u_d CS + e/a^2          e = (g-1)(u^_d - u_d) p
+  //   shear     CS = +-(m_t - u^_t rho)/rho^    CF = u_d CS
   //   acoustic  CS = lsc (S +- a w_d)     CF = u_d CS + lsc (+-a p - e)
   const double la = lsc * a;
+  double *const colS = G + 2 * NG * GS;
 #pragma unroll
   for (int p = 0; p < 6; p++) {
-    const double r = SVAL(V::RHO, p), pr = SVAL(V::P, p);
+    const double r = SVAL(V::RHO, p), pr = SVAL(V::P, p), udp = SVAL(V::UD, p);
     double um = 0.0;
 #pragma unroll
     for (int d = 0; d < ND; d++) um = fma(u[d], SVAL(V::M0 + d, p), um);
     const double S = fma(phi, r, gm1 * (SVAL(V::E, p) - um));
     const double wd = fma(-u[DIR], r, SVAL(V::M0 + DIR, p));
-    const double e = (gm1 * (u[DIR] - ud[p])) * pr;
-    {
-      const double cs = fma(-S, ia2, r);
-      const double cf = fma(ud[p], cs, e * ia2);
-      f3_put<RECON>(G, GS, p, fma(lam0, cs, cf), fma(-lam0, cs, cf));
-    }
+    const double e = (gm1 * (u[DIR] - udp)) * pr;
+    colS[p * GS] = S;
     const double lS = lsc * S, lw = la * wd, lp = la * pr, le = lsc * e;
     {
       const double cs = lS + lw;
-      const double cf = fma(ud[p], cs, lp - le);
-      f3_put<RECON>(G + NG * GS, GS, p, fma(lamp, cs, cf), fma(-lamp, cs, cf));
+      const double cf = fma(udp, cs, lp - le);
+      f3_put<RECON>(G, GS, p, fma(lamp, cs, cf), fma(-lamp, cs, cf));
     }
     {
       const double cs = lS - lw;
-      const double cf = fma(ud[p], cs, -(lp + le));
-      f3_put<RECON>(G + 2 * NG * GS, GS, p, fma(lamm, cs, cf), fma(-lamm, cs, cf));
+      const double cf = fma(udp, cs, -(lp + le));
+      f3_put<RECON>(G + NG * GS, GS, p, fma(lamm, cs, cf), fma(-lamm, cs, cf));
     }
   }
-  // ---- pass 2a: the three reconstructions, one wave at a time (rolled: one copy of the reconstruction code)
+  // ---- pass 2: the acoustic reconstructions, one wave at a time (rolled: one copy of the reconstruction code)
 #pragma unroll 1
-  for (int w = 0; w < 3; w++) {
-    const double r = f3_wave<RECON>(G + w * NG * GS, GS, sp);
-    G[w * NG * GS] = r;
-  }
-  const double recE = G[0], recP = G[NG * GS], recM = G[2 * NG * GS];
-  // ---- pass 1b / 2b: shear waves (tangential directions)
-  double recT[ND > 1 ? ND : 1];
-  if (ND > 1) {
-    int nw = 0;
+  for (int w = 0; w < 2; w++) {
+    double ga[NS], gb[NS];
 #pragma unroll
-    for (int t = 0; t < ND; t++) {
-      if (t == DIR) continue;
-      // reference sign convention -(e_DIR x w)_r / rho^ (matters for TENO6, whose beta_3 is not even in f)
+    for (int k = 0; k < NS; k++) { ga[k] = G[(w * NG + k) * GS]; gb[k] = G[(w * NG + NS + k) * GS]; }
+    G[w * NG * GS] = f3_recon<RECON>(ga, gb, sp);
+  }
+  // ---- pass 3: entropy wave (k = 0) and shear waves (k = 1 .. ND-1: the tangential directions in ascending order), split
+  // fluxes formed in registers
+#pragma unroll 1
+  for (int k = 0; k < ND; k++) {
+    double ga[NS], gb[NS];
+    if (k == 0) {
+#pragma unroll
+      for (int p = 0; p < 6; p++) {
+        const double udp = SVAL(V::UD, p);
+        const double e = (gm1 * (u[DIR] - udp)) * SVAL(V::P, p);
+        const double cs = fma(-colS[p * GS], ia2, SVAL(V::RHO, p));
+        const double cf = fma(udp, cs, e * ia2);
+        if (p < NS) ga[p] = fma(lam0, cs, cf);
+        if (5 - p < NS) gb[5 - p] = fma(-lam0, cs, cf);
+      }
+    } else {
+      // tangential direction t of wave k; reference sign convention -(e_DIR x w)_t / rho^ (matters for TENO6, whose beta_3
+      // is not even in f)
+      const int t = (k - 1 < DIR) ? k - 1 : k;
+      const double ut = (ND > 1 && t == 0) ? u[0] : ((ND > 2 && t == 2) ? u[ND > 2 ? 2 : 0] : u[ND > 1 ? 1 : 0]);
       const double sg = (t == (DIR + 2) % 3) ? irho : -irho;
 #pragma unroll
       for (int p = 0; p < 6; p++) {
-        const double cs = (SVAL(V::M0 + t, p) - u[t] * SVAL(V::RHO, p)) * sg;
-        const double cf = SVAL(V::UD, p) * cs;                           // u_d re-read: cheaper than 12 registers held across pass 2a
-        f3_put<RECON>(G + nw * NG * GS, GS, p, fma(lam0, cs, cf), fma(-lam0, cs, cf));
+        const double cs = (SVAL(V::M0 + t, p) - ut * SVAL(V::RHO, p)) * sg;
+        const double cf = SVAL(V::UD, p) * cs;
+        if (p < NS) ga[p] = fma(lam0, cs, cf);
+        if (5 - p < NS) gb[5 - p] = fma(-lam0, cs, cf);
       }
-      nw++;
     }
-#pragma unroll 1
-    for (int w = 0; w < ND - 1; w++) {
-      const double r = f3_wave<RECON>(G + w * NG * GS, GS, sp);
-      G[w * NG * GS] = r;
-    }
-    nw = 0;
+    colS[k * GS] = f3_recon<RECON>(ga, gb, sp);           // S is not needed any more after k = 0 has read it
+  }
+  const double recP = G[0], recM = G[NG * GS], recE = colS[0];
+  double recT[ND > 1 ? ND : 1];
+  if (ND > 1) {
 #pragma unroll
-    for (int t = 0; t < ND; t++) {
-      if (t == DIR) { recT[t] = 0.0; continue; }
-      recT[t] = G[nw * NG * GS];
-      nw++;
-    }
+    for (int t = 0; t < ND; t++) recT[t] = (t == DIR) ? 0.0 : colS[(t < DIR ? t + 1 : t) * GS];
   }
 #undef SVAL
-  // ---- pass 3: flux = REV . rec
+  // ---- pass 4: flux = REV . rec
   const double sp_ = rsc * (recP + recM), sm = rsc * a * (recP - recM);
   const double Hp = 0.5 * ke + hst;
   flux[0] = recE + sp_;
@@ -218,9 +221,9 @@ constexpr int F3_BT = 128;                 // x sweep: staged points (= threads)
 #endif
 template <int RECON> struct F3TY { static constexpr int v = RECON == RECON_TENO6 ? 7 : OSB_F3_TY; };
 template <int RECON> constexpr int f3_ty() { return F3TY<RECON>::v; }     // y/z sweeps: interface rows (= thread rows) per block
-template <int ND, int RECON> constexpr size_t f3_x_smem_bytes() { return sizeof(double) * F3_BT * (SV<ND>::N + F3<RECON>::NW * F3<RECON>::NG); }
+template <int ND, int RECON> constexpr size_t f3_x_smem_bytes() { return sizeof(double) * F3_BT * (SV<ND>::N + F3<RECON>::NCOL); }
 template <int ND, int RECON> constexpr size_t f3_yz_smem_bytes() {
-  return sizeof(double) * 32 * ((f3_ty<RECON>() + 5) * SV<ND>::N + f3_ty<RECON>() * F3<RECON>::NW * F3<RECON>::NG);
+  return sizeof(double) * 32 * ((f3_ty<RECON>() + 5) * SV<ND>::N + f3_ty<RECON>() * F3<RECON>::NCOL);
 }
 
 #ifndef OSB_F3_XBLOCKS

@@ -1272,6 +1272,84 @@ __global__ void __launch_bounds__(128) k_bc_symmetry(GridDev g, FieldPtrs f, int
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// In-loop diagnostics: NaN check of a dataset (what ops_NaNcheck does, simulation_monitors.py:112-113,
+// helperfunctions.py:172-190) and volume sums for the Taylor-Green diagnostics (kinetic energy, enstrophy -- computed offline
+// from the dumps in the reference workflow).  Deterministic: one partial per block (warp shuffles, then one value per warp
+// through shared memory), summed in block order by a second single-block kernel.
+// -------------------------------------------------------------------------------------------------
+constexpr int DIAG_N = 6;     // sum rho, sum 1/2 rho |u|^2, sum 1/2 rho |omega|^2, sum rhoE, max |u|/a (Mach), non-finite count
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = dmax2(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int ND>
+__global__ void __launch_bounds__(256) k_diag_partial(GridDev g, FieldPtrs f, PhysConst c, GeneralPtrs gp, const double *field, double *partial) {
+  __shared__ double sh[DIAG_N][8];
+  const long long cnt = (long long)g.np[0] * g.np[1] * g.np[2];
+  double acc[DIAG_N] = {0, 0, 0, 0, 0, 0};
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % g.np[0]);
+    const long long r = e / g.np[0];
+    const int j = (int)(r % g.np[1]), k = (int)(r / g.np[1]);
+    const long long x = g.off + i + (ND > 1 ? j * g.s[1] : 0) + (ND > 2 ? k * g.s[2] : 0);
+    if (field) {                     // NaN / Inf count of one dataset
+      const double v = field[x];
+      if (!(fabs(v) <= 1.79769313486231570e308)) acc[5] += 1.0;
+      continue;
+    }
+    const double rho = f.q[0][x], irho = 1.0 / rho;
+    double u2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < ND; d++) { const double u = f.q[1 + d][x] * irho; u2 += u * u; }
+    const double E = f.q[ND + 1][x];
+    const double p = (c.gama - 1.0) * (E - 0.5 * rho * u2);
+    // vorticity from 4th-order central differences of u = m / rho (halos valid after the boundary conditions)
+    double du[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+    for (int a = 0; a < ND; a++)
+#pragma unroll
+      for (int b = 0; b < ND; b++) {
+        if (a == b) continue;
+        const long long s = g.s[b];
+        const double um2 = f.q[1 + a][x - 2 * s] / f.q[0][x - 2 * s], um1 = f.q[1 + a][x - s] / f.q[0][x - s];
+        const double up1 = f.q[1 + a][x + s] / f.q[0][x + s], up2 = f.q[1 + a][x + 2 * s] / f.q[0][x + 2 * s];
+        du[a][b] = d1c(um2, um1, up1, up2, c.inv[b]) * (gp.D[b] ? gp.D[b][x] : 1.0);
+      }
+    double w2 = 0.0;
+    if (ND == 2) w2 = sq(du[1][0] - du[0][1]);
+    if (ND == 3) w2 = sq(du[2][1] - du[1][2]) + sq(du[0][2] - du[2][0]) + sq(du[1][0] - du[0][1]);
+    acc[0] += rho; acc[1] += 0.5 * rho * u2; acc[2] += 0.5 * rho * w2; acc[3] += E;
+    acc[4] = dmax2(acc[4], sqrt(u2 * rho / (c.gama * p)));
+    if (!(fabs(rho) <= 1.79769313486231570e308) || !(fabs(E) <= 1.79769313486231570e308)) acc[5] += 1.0;
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int n = 0; n < DIAG_N; n++) {
+    const double v = n == 4 ? warp_max(acc[n]) : warp_sum(acc[n]);
+    if (lane == 0) sh[n][w] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < DIAG_N) {
+    double v = sh[threadIdx.x][0];
+    for (int q = 1; q < 8; q++) v = threadIdx.x == 4 ? dmax2(v, sh[threadIdx.x][q]) : v + sh[threadIdx.x][q];
+    partial[(long long)blockIdx.x * DIAG_N + threadIdx.x] = v;
+  }
+}
+__global__ void k_diag_final(const double *partial, int nblocks, double *out) {
+  const int n = threadIdx.x;
+  if (n >= DIAG_N) return;
+  double v = partial[n];
+  for (int b = 1; b < nblocks; b++) v = n == 4 ? dmax2(v, partial[(long long)b * DIAG_N + n]) : v + partial[(long long)b * DIAG_N + n];
+  out[n] = v;
+}
+
 // FP64 pipe micro-benchmark: 8 independent DFMA chains per thread
 __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;

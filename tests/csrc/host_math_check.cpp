@@ -64,7 +64,7 @@ static void run_split(const double *q6, double gama, const SchemeParams &sp, dou
     st[V::RHO * 6 + p] = q[0]; st[V::Y * 6 + p] = y; st[V::E * 6 + p] = q[ND + 1];
     st[V::P * 6 + p] = pr; st[V::A * 6 + p] = sqrt(gama * pr * irho);
   }
-  double G[F3<RECON>::NW * F3<RECON>::NG];
+  double G[F3<RECON>::NCOL];
   interface_flux_split<ND, DIR, RECON, AVG>(st, 1, 6, G, 1, gama, sp, flux);
 }
 
