@@ -55,13 +55,18 @@ OSB_HD void f3_put(double *G, const int GS, const int p, const double gp, const 
 
 // sb: staged value 0 of stencil point 0 (offset -2); value v of point p at sb[v*VS + p*PS].
 // G: this thread's column (element k at G[k*GS]), NW*NG doubles.  flux: ND+2 values out.
-template <int ND, int DIR, int RECON, int AVG>
-OSB_HD void interface_flux_split(const double *sb, const int PS, const int VS, double *G, const int GS,
-                                                     const double gama, const SchemeParams &sp, double *flux) {
+// where the 6 stencil points of an interface sit in the staged array: equally spaced (tiles), or rows of a ring buffer of
+// 2^k rows of 32 lanes (marching kernel: the window may straddle the wrap)
+struct WinAffine { int PS; OSB_HD int off(int p) const { return p * PS; } };
+struct WinRing { int row0, mask; OSB_HD int off(int p) const { return ((row0 + p) & mask) * 32; } };
+
+template <int ND, int DIR, int RECON, int AVG, typename WIN>
+OSB_HD void interface_flux_split(const double *sb, const WIN win, const int VS, double *G, const int GS,
+                                 const double gama, const SchemeParams &sp, double *flux) {
   typedef SV<ND> V;
   constexpr int NG = F3<RECON>::NG, NS = NG / 2;
   const double gm1 = gama - 1.0;
-#define SVAL(v, p) sb[(v) * VS + (p) * PS]
+#define SVAL(v, p) sb[(v) * VS + win.off(p)]
   // ---- pass 0: interface state between points 2 and 3 (averaging.py:31-59 simple, 62-114 Roe)
   double rho, irho, u[ND], a, ia, hst;               // hst = a^2/(gama-1)
   {
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(F3_BT, OSB_F3_XBLOCKS) k_flux3_x(GridDev g, Fi
       sp.teno_ct = ad.ct[e]; sp.kfast5 = ad.k5[e]; sp.kpass5 = ad.k5[e] - 1.0; sp.kfast6 = ad.k6[e];
       if (gp.teno_store) gp.teno_store[x] = sp.teno_ct;
     }
-    interface_flux_split<ND, 0, RECON, AVG>(sP + t - 2, 1, F3_BT, sG + t, F3_BT, c.gama, sp, fl);
+    interface_flux_split<ND, 0, RECON, AVG>(sP + t - 2, WinAffine{1}, F3_BT, sG + t, F3_BT, c.gama, sp, fl);
 #pragma unroll
     for (int m = 0; m < NV; m++) sG[m * F3_BT + t] = fl[m];
   }
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(32 * F3TY<RECON>::v, OSB_F3_YZBLOCKS) k_flux3_
       const int e = adaptive_exponent(ad, gp.theta[x]);
       sp.teno_ct = ad.ct[e]; sp.kfast5 = ad.k5[e]; sp.kpass5 = ad.k5[e] - 1.0; sp.kfast6 = ad.k6[e];
     }
-    interface_flux_split<ND, DIR, RECON, AVG>(sP + (r - 2) * 32 + tx, 32, RT * 32, sG + tid, NTH, c.gama, sp, fl);
+    interface_flux_split<ND, DIR, RECON, AVG>(sP + (r - 2) * 32 + tx, WinAffine{32}, RT * 32, sG + tid, NTH, c.gama, sp, fl);
 #pragma unroll
     for (int m = 0; m < NV; m++) sG[m * NTH + tid] = fl[m];
   }
@@ -359,6 +364,144 @@ __global__ void __launch_bounds__(32 * F3TY<RECON>::v, OSB_F3_YZBLOCKS) k_flux3_
     for (int m = 0; m < NV; m++) {
       const double rr = met * (sG[m * NTH + tid] - sG[m * NTH + tid - 32]);
       f.R[m][x] = ACCUM ? old[m] + rr : rr;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// y / z sweeps of 3-D boxes as a MARCH along the sweep direction with a TMA + mbarrier pipeline.
+// A block owns 32 x-lanes of one pencil (fixed index in the other direction) and a chunk of rows along DIR; it advances
+// MTY interface rows per step.  Rows are staged once: a ring of 2 groups x MTY staged rows stays in shared memory, so the
+// tile kernel's re-staging (15 staged rows per 9 point rows) and its recomputed interface row disappear, and the loads of
+// the next row group are in flight while the current one is reconstructed:
+//     one elected thread:  mbarrier.arrive.expect_tx + 5 x cp.async.bulk.tensor.3d (box 32 x MTY rows of rho .. rhoE) -> raw
+//     all threads:         reconstruct the MTY interface rows of group n from the ring ; flux difference -> Residual
+//                          mbarrier.try_wait (group n+2 has landed) ; constituent relations raw -> ring slot of group n
+// Needs an even padded x-extent (TMA global strides are multiples of 16 bytes) and enough pencils to fill the GPU; the
+// tile kernel k_flux3_yz covers everything else.
+// -------------------------------------------------------------------------------------------------
+#ifndef OSB_F3_MTY
+#define OSB_F3_MTY 8
+#endif
+constexpr int F3_MTY = OSB_F3_MTY;                 // interface rows (= thread rows) per step; ring = 2 * MTY rows (power of two)
+static_assert((F3_MTY & (F3_MTY - 1)) == 0, "ring addressing needs a power-of-two row group");
+// The box starts one element left of the block's first lane: TMA wants the start of a box 16-byte aligned along x (probed on
+// the B200: an odd start coordinate of 8-byte elements raises "illegal instruction"), and the interior starts at the odd
+// padded index 5.  34 doubles per row = 272 bytes (a multiple of 16), rows of the landed box are 4 banks apart.
+constexpr int F3_MBOX = 34;
+struct alignas(64) TmaMaps5 { unsigned char m[5][128]; };     // five CUtensorMap objects (rho, rhou0, rhou1, rhou2, rhoE)
+template <int RECON> constexpr size_t f3_march_smem_bytes() {
+  return sizeof(double) * (5 * F3_MTY * F3_MBOX + 32 * (2 * F3_MTY * SV<3>::N + F3_MTY * F3<RECON>::NCOL + 2 * 5)) + 128;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase) {
+  unsigned ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const void *map, unsigned long long *bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+template <int DIR, int RECON, int AVG, bool ACCUM>
+__global__ void __launch_bounds__(32 * F3_MTY, 2) k_flux3_march(GridDev g, FieldPtrs f, PhysConst c, SchemeParams sp,
+                                                                 const __grid_constant__ TmaMaps5 maps, int chunk) {
+  constexpr int ND = 3, NV = 5, NVAL = SV<3>::N, TY = F3_MTY, RING = 2 * TY, NTH = 32 * TY;
+  constexpr int OTH = (DIR == 1) ? 2 : 1;
+  extern __shared__ __align__(128) double f3m_smem[];
+  double *raw = f3m_smem;                          // [NV][TY][34]   TMA destination (one row group, lanes -1 .. 32)
+  double *ring = raw + NV * TY * F3_MBOX;          // [NVAL][RING][32]
+  double *sG = ring + NVAL * RING * 32;            // [NCOL][TY][32] thread-private columns, then the fluxes
+  double *prevF = sG + F3<RECON>::NCOL * NTH;      // [2][NV][32]    flux of the last interface row of the previous step
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(prevF + 2 * NV * 32);
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+  const int i0 = blockIdx.x * 32, i = i0 + tx, o = blockIdx.y;
+  const bool xin = i < g.np[0];
+  // rows of this chunk: points [p0, p1) along DIR, interfaces jp = p0-1 .. p1-1; local staged row ls <-> grid index p0 + ls - 3
+  const int p0 = blockIdx.z * chunk, p1 = min(p0 + chunk, g.np[DIR]);
+  const int nsteps = (p1 - p0 + 1 + TY - 1) / TY;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int group) {                    // thread 0: row group `group` (staged rows group*TY ..) -> raw
+    mbar_expect_tx(bar, NV * TY * F3_MBOX * (unsigned)sizeof(double));
+    const int row = p0 + group * TY - 3 + g.h;     // padded index of the group's first row
+#pragma unroll
+    for (int m = 0; m < NV; m++) {
+      if (DIR == 1) tma_load_3d(raw + m * TY * F3_MBOX, maps.m[m], bar, i0 + g.h - 1, row, o + g.h);
+      else tma_load_3d(raw + m * TY * F3_MBOX, maps.m[m], bar, i0 + g.h - 1, o + g.h, row);
+    }
+  };
+  auto convert = [&](int group) {                  // constituent relations of this thread's point of the landed group
+    double q[NV];
+#pragma unroll
+    for (int m = 0; m < NV; m++) q[m] = raw[(m * TY + ty) * F3_MBOX + 1 + tx];
+    stage_values<ND, DIR>(q, c.gama, ring + ((group & 1) * TY + ty) * 32 + tx, RING * 32);
+  };
+  unsigned phase = 0;
+  if (tid == 0) issue(0);
+  mbar_wait(bar, phase); phase ^= 1;
+  convert(0);
+  __syncthreads();
+  if (tid == 0) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(1); }
+  mbar_wait(bar, phase); phase ^= 1;
+  convert(1);
+  __syncthreads();
+  if (tid == 0) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(2); }
+  const long long xbase = g.off + i + (long long)o * g.s[OTH];
+#pragma unroll 1
+  for (int n = 0; n < nsteps; n++) {
+    const int ls = 2 + n * TY + ty;                // local staged row left of this thread's interface
+    const int jp = p0 + ls - 3;
+    const bool iface = xin && jp <= p1 - 1;        // jp >= p0 - 1 >= -1 always
+    const bool point = iface && ls >= 3;           // lower interface ls-1 belongs to this chunk too
+    const long long x = xbase + (long long)jp * g.s[DIR];
+    if (ACCUM && point && (tx & 3) == 0) {
+#pragma unroll
+      for (int m = 0; m < NV; m++) prefetch_l2(f.R[m] + x);
+    }
+    if (iface) {
+      double fl[NV];
+      interface_flux_split<ND, DIR, RECON, AVG>(ring + tx, WinRing{ls - 2, RING - 1}, RING * 32, sG + tid, NTH, c.gama, sp, fl);
+#pragma unroll
+      for (int m = 0; m < NV; m++) sG[m * NTH + tid] = fl[m];
+      if (ty == TY - 1) {
+#pragma unroll
+        for (int m = 0; m < NV; m++) prevF[((n & 1) * NV + m) * 32 + tx] = fl[m];
+      }
+    }
+    __syncthreads();                               // fluxes of the step are in the columns; ring group n is no longer read
+    if (point) {
+      const double met = -c.inv[DIR];
+      double old[NV];
+      if (ACCUM) {
+#pragma unroll
+        for (int m = 0; m < NV; m++) old[m] = f.R[m][x];
+      }
+#pragma unroll
+      for (int m = 0; m < NV; m++) {
+        const double lower = ty > 0 ? sG[m * NTH + tid - 32] : prevF[(((n + 1) & 1) * NV + m) * 32 + tx];
+        const double rr = met * (sG[m * NTH + tid] - lower);
+        f.R[m][x] = ACCUM ? old[m] + rr : rr;
+      }
+    }
+    if (n + 1 < nsteps) {                          // group n+2 replaces group n in the ring; group n+3 starts travelling
+      mbar_wait(bar, phase); phase ^= 1;
+      convert(n + 2);
+      __syncthreads();
+      if (tid == 0 && n + 2 < nsteps) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(n + 3); }
     }
   }
 }

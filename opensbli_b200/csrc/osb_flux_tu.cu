@@ -1,5 +1,11 @@
 // osb_flux_tu.cu -- instantiations of the flux-sweep kernels for ONE (ndim, reconstruction) pair:
 //   nvcc -DOSB_FLUX_ND=3 -DOSB_FLUX_RECON=2 -c osb_flux_tu.cu     (RECON: 0 WENO5-JS, 1 WENO5-Z, 2 TENO5, 3 TENO6)
+#include <cuda.h>
+#include <array>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <tuple>
 #include "osb_flux_api.h"
 #include "osb_flux3.cuh"
 
@@ -27,9 +33,84 @@ cudaError_t sweep_x(const FluxArgs &a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+#if OSB_FLUX_ND == 3
+// ---- TMA descriptors of the conserved arrays for the marching kernel (driver API entry point fetched through the runtime:
+// the library does not link libcuda)
+typedef CUresult (*encode_tiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_tiled_t encode_tiled() {
+  static encode_tiled_t fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (encode_tiled_t)p;
+  }();
+  return fn;
+}
+
+// box of 34 x-lanes (see F3_MBOX) x F3_MTY rows along DIR of one padded array (x fastest); false if TMA cannot address it
+template <int DIR>
+bool make_map(const GridDev &g, double *base, unsigned char *out) {
+  static std::map<std::tuple<const void *, int, int, int, int>, std::array<unsigned char, 128>> cache;
+  const auto key = std::make_tuple((const void *)base, DIR, g.pd[0], g.pd[1], g.pd[2]);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    encode_tiled_t enc = encode_tiled();
+    if (!enc) return false;
+    alignas(64) CUtensorMap m;
+    const cuuint64_t dims[3] = {(cuuint64_t)g.pd[0], (cuuint64_t)g.pd[1], (cuuint64_t)g.pd[2]};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.s[1] * sizeof(double), (cuuint64_t)g.s[2] * sizeof(double)};
+    const cuuint32_t box[3] = {(cuuint32_t)F3_MBOX, DIR == 1 ? (cuuint32_t)F3_MTY : 1u, DIR == 2 ? (cuuint32_t)F3_MTY : 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+    std::array<unsigned char, 128> raw;
+    memcpy(raw.data(), &m, 128);
+    it = cache.emplace(key, raw).first;
+  }
+  memcpy(out, it->second.data(), 128);
+  return true;
+}
+
+bool march_enabled() {
+  static const bool on = getenv("OSB_NO_FLUX_MARCH") == nullptr;
+  return on;
+}
+
+// marching TMA kernel when the layout allows it and there is enough work to fill the GPU; returns cudaErrorNotSupported otherwise
+template <int DIR, int AVG, bool ACCUM>
+cudaError_t sweep_march(const FluxArgs &a, cudaStream_t s) {
+  const GridDev &g = a.g;
+  constexpr int OTH = (DIR == 1) ? 2 : 1;
+  if (!march_enabled() || a.ad.on || a.gp.D[DIR] || (g.s[1] & 1) || (g.s[2] & 1) || ((g.h - 1) & 1)) return cudaErrorNotSupported;
+  const int nx = (g.np[0] + 31) / 32;
+  // rows per chunk: whole pencils when they alone fill the GPU (2 blocks x 148 SMs x a few waves), else pieces of >= 64 rows
+  int chunk = g.np[DIR];
+  while ((long long)nx * g.np[OTH] * ((g.np[DIR] + chunk - 1) / chunk) < 148 * 2 * 4 && chunk > 64) chunk = (chunk + 1) / 2;
+  if ((long long)nx * g.np[OTH] * ((g.np[DIR] + chunk - 1) / chunk) < 148 * 2) return cudaErrorNotSupported;
+  TmaMaps5 maps;
+  for (int m = 0; m < 5; m++) if (!make_map<DIR>(g, a.f.q[m], maps.m[m])) return cudaErrorNotSupported;
+  auto kern = k_flux3_march<DIR, RECON, AVG, ACCUM>;
+  constexpr size_t smem = f3_march_smem_bytes<RECON>();
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 b(32, F3_MTY, 1), gr(nx, g.np[OTH], (g.np[DIR] + chunk - 1) / chunk);
+  if (gr.y > 65535u || gr.z > 65535u) return cudaErrorNotSupported;
+  kern<<<gr, b, smem, s>>>(g, a.f, a.c, a.sp, maps, chunk);
+  return cudaGetLastError();
+}
+#endif
+
 template <int DIR, int AVG, bool ACCUM>
 cudaError_t sweep_yz(const FluxArgs &a, cudaStream_t s) {
   const GridDev &g = a.g;
+#if OSB_FLUX_ND == 3
+  if (RECON != RECON_TENO6) {          // (TENO6 columns do not leave room for two marching blocks per SM)
+    const cudaError_t e = sweep_march<DIR, AVG, ACCUM>(a, s);
+    if (e != cudaErrorNotSupported) return e;
+  }
+#endif
   constexpr int TY = f3_ty<RECON>();
   constexpr int OTH = (DIR == 1) ? 2 : 1;
   const long long TR = (long long)(g.np[DIR] + 6) * (ND > 2 ? g.np[OTH] : 1);

@@ -65,7 +65,7 @@ static void run_split(const double *q6, double gama, const SchemeParams &sp, dou
     st[V::P * 6 + p] = pr; st[V::A * 6 + p] = sqrt(gama * pr * irho);
   }
   double G[F3<RECON>::NCOL];
-  interface_flux_split<ND, DIR, RECON, AVG>(st, 1, 6, G, 1, gama, sp, flux);
+  interface_flux_split<ND, DIR, RECON, AVG>(st, WinAffine{1}, 6, G, 1, gama, sp, flux);
 }
 
 template <int ND, int DIR>
