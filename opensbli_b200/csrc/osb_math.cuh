@@ -135,7 +135,8 @@ OSB_HD double inv_pow2(double m) {
 //   fast test: alpha_r >= 1 and sum(alpha) <= 3 alpha_max with alpha_max = (1 + tau/D_min)^6, hence
 //   alpha_r/sum >= 1/(3 alpha_max) >= C_T whenever 1 + tau/D_min <= (3 C_T)^(-1/6)  (2 % margin in kfast5).
 struct Teno5Side {
-  double D0, D1, D2, tau, Q0, Q1, Q2;
+  double b0, b1, b2, tau;          // 16 beta_r(f) and tau_5 (before eps is added)
+  double gm2, gm1, g0, g1, g2;
   bool all_pass;
 };
 OSB_HD Teno5Side teno5_front(double gm2, double gm1, double g0, double g1, double g2, const SchemeParams &sp) {
@@ -144,15 +145,12 @@ OSB_HD Teno5Side teno5_front(double gm2, double gm1, double g0, double g1, doubl
   const double A0 = e1 + e2, A1 = e3 - 3.0 * e2, A2 = 3.0 * e1 - e0;             // 2x first-derivative terms
   const double B0 = e2 - e1, B1 = e3 - e2, B2 = e1 - e0;                          // second differences
   const double c = 13.0 / 3.0;
-  const double b0 = (c * B0) * B0 + A0 * A0, b1 = (c * B1) * B1 + A1 * A1, b2 = (c * B2) * B2 + A2 * A2;
-  t.tau = fabs(b0 - b2);                                                          // teno.py:209
-  t.D0 = sp.eps16 + b0; t.D1 = sp.eps16 + b1; t.D2 = sp.eps16 + b2;
-  // 12 x candidate reconstructions (teno.py:113-114 times 6, times 2 for g = 2f)
-  t.Q0 = 5.0 * g0 + (2.0 * g1 - gm1);
-  t.Q1 = 5.0 * g1 + (2.0 * g0 - g2);
-  t.Q2 = 11.0 * g0 + (2.0 * gm2 - 7.0 * gm1);
-  // sufficient test for "every stencil passes": 1 + tau/D_min <= kfast5  <=>  tau <= (kfast5 - 1) D_r for r = 0, 1, 2
-  t.all_pass = (t.tau <= sp.kpass5 * t.D0) & (t.tau <= sp.kpass5 * t.D1) & (t.tau <= sp.kpass5 * t.D2);
+  t.b0 = (c * B0) * B0 + A0 * A0; t.b1 = (c * B1) * B1 + A1 * A1; t.b2 = (c * B2) * B2 + A2 * A2;
+  t.tau = fabs(t.b0 - t.b2);                                                      // teno.py:209
+  t.gm2 = gm2; t.gm1 = gm1; t.g0 = g0; t.g1 = g1; t.g2 = g2;
+  // sufficient test for "every stencil passes": 1 + tau/D_min <= kfast5  <=>  tau <= (kfast5 - 1)(eps + beta_r) for r = 0, 1, 2
+  const double ke = sp.kpass5 * sp.eps16;
+  t.all_pass = (t.tau <= fma(sp.kpass5, t.b0, ke)) & (t.tau <= fma(sp.kpass5, t.b1, ke)) & (t.tau <= fma(sp.kpass5, t.b2, ke));
   return t;
 }
 namespace teno5c {
@@ -162,21 +160,27 @@ constexpr double d0 = 11.0 / 20.0, d1 = 2.0 / 5.0, d2 = 1.0 / 20.0;             
 constexpr double i111 = 1.0 / ((d0 + d1) + d2), i110 = 1.0 / ((d0 + d1) + 0.0), i101 = 1.0 / ((d0 + 0.0) + d2), i100 = 1.0 / ((d0 + 0.0) + 0.0);
 constexpr double i011 = 1.0 / ((0.0 + d1) + d2), i010 = 1.0 / ((0.0 + d1) + 0.0), i001 = 1.0 / ((0.0 + 0.0) + d2);
 }
+// every stencil kept: the optimal weights give the 5-point linear upwind reconstruction of f = g/2
+//   sum_r d_r q_r(g)/2 = (2 g(-2) - 18 g(-1) + 82 g(0) + 62 g(1) - 8 g(2)) / 240      (teno.py:113-133)
 OSB_HD double teno5_linear(const Teno5Side &t) {
-  using namespace teno5c;
-  return i111 * ((d0 / 12.0) * t.Q0 + (d1 / 12.0) * t.Q1 + (d2 / 12.0) * t.Q2);
+  return (1.0 / 120.0) * t.gm2 + ((-3.0 / 40.0) * t.gm1 + ((41.0 / 120.0) * t.g0 + ((31.0 / 120.0) * t.g1 + (-1.0 / 30.0) * t.g2)));
 }
 OSB_HD double teno5_resolve(const Teno5Side &t, const SchemeParams &sp) {
   using namespace teno5c;
+  const double D0 = sp.eps16 + t.b0, D1 = sp.eps16 + t.b1, D2 = sp.eps16 + t.b2;
+  // 12 x candidate reconstructions (teno.py:113-114 times 6, times 2 for g = 2f)
+  const double Q0 = 5.0 * t.g0 + (2.0 * t.g1 - t.gm1);
+  const double Q1 = 5.0 * t.g1 + (2.0 * t.g0 - t.g2);
+  const double Q2 = 11.0 * t.g0 + (2.0 * t.gm2 - 7.0 * t.gm1);
   // P_r = (D_r + tau) * prod_{s != r} D_s ; alpha_r = (P_r / (D0 D1 D2))^6   (teno.py:207-212, C=1, q=6)
-  const double P0 = (t.D0 + t.tau) * (t.D1 * t.D2), P1 = (t.D1 + t.tau) * (t.D0 * t.D2), P2 = (t.D2 + t.tau) * (t.D0 * t.D1);
+  const double P0 = (D0 + t.tau) * (D1 * D2), P1 = (D1 + t.tau) * (D0 * D2), P2 = (D2 + t.tau) * (D0 * D1);
   const double sc = inv_pow2(dmax2(P0, dmax2(P1, P2)));
   const double a0 = pow6(P0 * sc), a1 = pow6(P1 * sc), a2 = pow6(P2 * sc);
   const double thr = sp.teno_ct * (a0 + a1 + a2);                                 // teno.py:445-465
   const bool k0 = !(thr > a0), k1 = !(thr > a1), k2 = !(thr > a2);
   const double w0 = k0 ? (d0 / 12.0) : 0.0, w1 = k1 ? (d1 / 12.0) : 0.0, w2 = k2 ? (d2 / 12.0) : 0.0;
   const double inv = k0 ? (k1 ? (k2 ? i111 : i110) : (k2 ? i101 : i100)) : (k1 ? (k2 ? i011 : i010) : i001);
-  return inv * (w0 * t.Q0 + w1 * t.Q1 + w2 * t.Q2);
+  return inv * (w0 * Q0 + w1 * Q1 + w2 * Q2);
 }
 // both sides of one characteristic wave: gp = CF + lam CS (right-biased), gm = CF - lam CS (left-biased, mirrored)
 OSB_HD double teno5_wave(const double *gp, const double *gm, const SchemeParams &sp) {
