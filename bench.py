@@ -256,6 +256,30 @@ def parity_check(args, world, rank, local_rank, dist):
     return out
 
 
+def central4_secondary(size, device, hbm_peak, steps=5):
+    """BASELINE configs[1]'s scheme (shipped taylor_green_vortex app: Central(4) skew-symmetric + RungeKutta(3)) at the headline
+    size on the same GPU, carried in the one JSON line: the bandwidth-bound stage kernel against the measured HBM copy bandwidth."""
+    import numpy as np
+    import opensbli_b200
+    n = size
+    plan = tgv_plan([n, n, n], 'central4')
+    q = [np.zeros((n + 10,) * 3) for _ in range(5)]
+    tgv_state_into(q, plan, 0, n)
+    with opensbli_b200.Simulation(plan, device=device) as sim:
+        sim.set_state(q)
+        del q
+        sim.step(3)
+        ms = sim.step_timed(steps)
+        prof = sim.profile_step()
+        finite = bool(np.isfinite(sim.download('rho')).all())
+    launch_ms = (prof['central']['ms'] + prof['viscous']['ms'] + prof['prim']['ms']) / max(prof['central']['launches'], 1)
+    ach = (ALG_BYTES_PER_UPDATE / 3.0) * n ** 3 / (launch_ms * 1e-3) / 1e9
+    return {'workload': 'TGV Re=1600 Central(4) skew-symmetric + RungeKutta(3), %d^3 fp64 (BASELINE configs[1] scheme at the headline size)' % n,
+            'value': n ** 3 * steps / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / steps, 'steps': steps, 'finite': finite,
+            'roofline': {'bound': 'hbm', 'kernel': 'k_central3d_fused', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
+                         'launch_ms': launch_ms, 'bytes_model': 'algorithmic 160 B per point per stage'}}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -269,6 +293,13 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-parity', action='store_true')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: --size^3 points per GPU (default); strong: one --grid^3 block cut over all GPUs (BASELINE configs[4])')
+    ap.add_argument('--grid', type=int, default=1024, help='strong scaling: points per direction of the whole block')
+    ap.add_argument('--state', default='smooth', choices=['smooth', 'perturbed'],
+                    help='smooth: analytic TGV field (every TENO stencil passes the cut-off: the best case of the all-pass shortcut); '
+                         'perturbed: the same field with 5 %% random noise (nearly every wave takes the full cut-off path: the worst case)')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the Central-4 (BASELINE configs[1] scheme) line carried as `secondary`')
     args = ap.parse_args()
     if args.impl == 'reference':
         reference_arm(args)
@@ -294,7 +325,12 @@ def main():
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
 
-    plan = tgv_plan(global_grid(world, args.size), args.workload)
+    if args.scaling == 'strong':
+        plan = tgv_plan([args.grid] * 3, args.workload)
+        plan['delta'] = [2 * math.pi / args.grid] * 3
+        plan['constants']['dt'] = 0.003385 * 64 / args.grid
+    else:
+        plan = tgv_plan(global_grid(world, args.size), args.workload)
 
     class _Solo(object):
         def get_rank(self): return 0
@@ -307,11 +343,18 @@ def main():
     nbytes_state = 5 * int(np.prod(shape)) * 8
 
     # pinned host buffers (torch only provides the pinned allocation)
-    hin = [torch.empty(shape, dtype=torch.float64, pin_memory=True) for _ in range(5)]
-    hout = [torch.empty(shape, dtype=torch.float64, pin_memory=True) for _ in range(5)]
+    pin = not args.no_e2e                      # the end-to-end leg copies from / to pinned host memory
+    hin = [torch.empty(shape, dtype=torch.float64, pin_memory=pin) for _ in range(5)]
+    hout = [torch.empty(shape, dtype=torch.float64, pin_memory=True) for _ in range(5)] if pin else []
     q_in = [t.numpy() for t in hin]
     q_out = [t.numpy() for t in hout]
-    tgv_state_into(q_in, lplan, k0, nk)
+    def fill_state(bufs):
+        tgv_state_into(bufs, lplan, k0, nk)
+        if args.state == 'perturbed':           # 5 % multiplicative noise on every conserved variable, seeded per rank
+            rng = np.random.default_rng(1234 + rank)
+            for b in bufs:
+                b *= 1.0 + 0.05 * rng.standard_normal(b.shape)
+    fill_state(q_in)
     dsim.set_state(q_in)           # collective: the upload also writes the halo planes the neighbours store into
 
     def barrier():
@@ -348,6 +391,16 @@ def main():
     prof = sim.profile_step()          # every rank takes part (the stage sequence contains the neighbour handshakes)
     roofline = roofline_hbm = None
     fp64_peak = opensbli_b200.measure_fp64_peak(local_rank)
+    # share of TENO5 characteristic waves that left the all-pass shortcut during one more step (instrumented: not timed)
+    slow_fraction = None
+    if args.workload == 'teno5':
+        sim.slow_path_count(True)
+        dsim.step(1)
+        barrier()
+        nslow = sim.slow_path_count(False)
+        pl = lplan['np']
+        waves = 3 * 5 * float((pl[0] + 1) * pl[1] * pl[2] + pl[0] * (pl[1] + 1) * pl[2] + pl[0] * pl[1] * (pl[2] + 1))
+        slow_fraction = nslow / waves
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
@@ -391,7 +444,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         Ke = min(K, 5)
-        tgv_state_into(q_in, lplan, k0, nk)
+        fill_state(q_in)
         if world == 1:
             sim.advance_host(q_in, q_out, 1)      # warm-up of the path
             tot_ms = 0.0
@@ -435,18 +488,32 @@ def main():
         else:
             cpu = {'value': None, 'unit': UNIT, 'cores': cores, 'kind': 'reference', 'sample': 'oracle/_ref/tgv_teno5/ref_omp missing'}
 
+    secondary = None
+    if rank == 0 and world == 1 and args.workload == 'teno5' and not args.no_secondary:
+        try:
+            secondary = central4_secondary(args.size, local_rank, hbm_peak)
+        except Exception as e:
+            secondary = {'error': repr(e)}
+
     if rank == 0:
         line = {'metric': METRIC if args.workload == 'teno5' else 'grid-point updates/s (fp64, Central-4 TGV)', 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
-                'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+                'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64',
                 'data': 'synthetic',
-                'config': {'workload': ('TGV Re=1600 TENO5(Roe,LLF)+StoreSome(4) viscous+RK-LS3, %s grid fp64 (BASELINE configs[%d]), %d^3 points per GPU'
-                                        % ('x'.join(str(n) for n in plan['np']), 2 if world == 1 else 4, args.size)) if args.workload == 'teno5' else
+                'config': {'workload': ('TGV Re=1600 TENO5(Roe,LLF)+StoreSome(4) viscous+RK-LS3, %s grid fp64 (BASELINE configs[%d]), %s'
+                                        % ('x'.join(str(n) for n in plan['np']), 2 if world == 1 else 4,
+                                           ('%d^3 points per GPU' % args.size) if args.scaling == 'weak' else 'strong scaling: the block is cut into %d slabs' % world)) if args.workload == 'teno5' else
                                        'TGV Re=1600 Central(4) skew-symmetric + RungeKutta(3), %s grid fp64 (BASELINE configs[1] at this size)' % 'x'.join(str(n) for n in plan['np']),
                            'grid': plan['np'], 'parallelism': 'slab%d' % world,
+                           'state': args.state,
                            'l2_policy': 'working set %.1f GB per GPU >> 126 MB L2 (no flush needed)' % (19 * np.prod(shape) * 8 / 1e9),
                            'finite': finite},
-                'roofline': roofline, 'roofline_hbm': roofline_hbm, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e, 'parity': parity,
+                'roofline': roofline, 'roofline_hbm': roofline_hbm, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e, 'parity': parity, 'secondary': secondary,
                 'gpu_launches': int(launches), 'fp64_peak_tflops_measured': fp64_peak,
+                'fp64_peak': {'measured_tflops': fp64_peak, 'how': 'osb_measure_fp64_peak: 8 independent DFMA chains per thread, 148 x 8 blocks x 256 threads, 16384 iterations, best of 4',
+                              'sm_mhz_during_run': clocks.get('sm_mhz'), 'theoretical_tflops_at_max_clock': 148 * 64 * 2 * (clocks.get('sm_max_mhz') or 1965.0) * 1e6 / 1e12,
+                              'note': '64 FP64 FMA lanes per SM; MEASURED_PEAKS.json carries no FP64 entry'},
+                'state': {'kind': args.state, 'waves_on_full_cutoff_path': slow_fraction,
+                          'note': 'share of TENO5 characteristic waves (5 per interface per sweep) that needed the full cut-off evaluation in one step after the timed region'},
                 'families_ms_rank0': {k: v['ms'] for k, v in prof.items()} if prof else None,
                 'alg_flop_per_update': ALG_FLOP_PER_UPDATE, 'achieved_alg_tflops': ALG_FLOP_PER_UPDATE * value / world / 1e12}
         if args.workload != 'teno5':      # the reference operation count quoted above is the TENO5 one

@@ -88,6 +88,9 @@ int osb_advance_host(osb_ctx *ctx, const double *const *q_in, double *const *q_o
 enum { OSB_FAM_PRIM = 0, OSB_FAM_FLUX = 1, OSB_FAM_CENTRAL = 2, OSB_FAM_VISCOUS = 3, OSB_FAM_RK = 4, OSB_FAM_BC = 5,
        OSB_FAM_SYNC = 6 /* waiting for neighbour ranks */, OSB_FAM_USER = 7 /* run-time compiled user kernels */, OSB_NFAM = 8 };
 int osb_launch_count(const osb_ctx *ctx, long long *count);
+/* Bench instrumentation: number of TENO5 characteristic waves (5 per interface per sweep) that needed the full cut-off
+ * evaluation instead of the all-stencils-pass shortcut since the counter was armed.  enable != 0 arms and clears it. */
+int osb_slow_path_count(osb_ctx *ctx, int enable, long long *count);
 int osb_profile_step(osb_ctx *ctx, double *family_ms /* [OSB_NFAM] */, long long *family_launches /* [OSB_NFAM] */);
 
 /* In-loop diagnostics (device reductions, deterministic summation order; synchronise the stream):
@@ -123,7 +126,7 @@ int osb_run_user_kernels(osb_ctx *ctx, int when);
 
 /* Multi-GPU (slab decomposition along the slowest axis): direct peer access to a neighbour's
  * arrays through CUDA IPC.  See INTEGRATION.md. */
-int osb_ipc_export(osb_ctx *ctx, void *handles /* room for (2 nq + 2) * 64 bytes: q buffers, Residual buffers, flag words, shock sensor (adaptive TENO) */, int *nbytes);
+int osb_ipc_export(osb_ctx *ctx, void *handles /* room for (2 nq + 2) * 64 + 8 bytes: q buffers, Residual buffers, flag words, shock sensor (adaptive TENO), slab thickness */, int *nbytes);
 int osb_ipc_import(osb_ctx *ctx, int side /* 0 = low neighbour, 1 = high neighbour */, const void *handles, int nbytes);
 /* push this rank's boundary planes of q into the neighbours' halo planes (peer stores over NVLink) */
 int osb_halo_push(osb_ctx *ctx);

@@ -839,8 +839,25 @@ def extract_plan(algorithm):
     _walk(algorithm.prg.components, flat)
     before, in_iter, in_stage, after = [], [], [], []
     seen_loop = False
+    io_specs = []
     for path, c in flat:
         loops = [type(p).__name__ for p in path]
+        if type(c).__name__ == 'iohdf5':
+            # dataset files (core/io_hdf5.py:18-127): written after the time loop, every N iterations inside it
+            # (`iohdf5(save_every=N)`: Condition((iter + 1) %% N == 0), algorithm.py:456-463), or read before it
+            spec = {'arrays': [_strip(a) for a in c.arrays], 'iotype': c.kwargs.get('iotype', 'write'), 'name': c.kwargs.get('name'),
+                    'filename': c.kwargs.get('filename')}
+            cond = [p for p in path if type(p).__name__ == 'Condition']
+            if cond:
+                m = re.search(r'Mod\([^,]+,\s*(\d+)\)', str(cond[-1].condition))
+                if not m:
+                    raise UnsupportedByB200('output condition %s' % cond[-1].condition)
+                spec.update(when='in_loop', every=int(m.group(1)))
+            else:
+                spec['when'] = 'before' if spec['iotype'] == 'read' else ('after' if (seen_loop or 'DoLoop' in loops) else 'before')
+            io_specs.append(spec)
+            seen_loop = seen_loop or 'Timers' in loops or loops.count('DoLoop') > 0
+            continue
         nloops = loops.count('DoLoop')
         seen_loop = seen_loop or 'Timers' in loops or nloops > 0
         if nloops == 0 and 'Timers' not in loops:
@@ -869,7 +886,11 @@ def extract_plan(algorithm):
     # components of the program that are not part of the per-step hot path (file output, monitors, timers): not executed
     # by the B200 run-time; listed in the plan and printed so that nothing is dropped silently
     plan['not_executed'] = sorted(set(type(c).__name__ for c in in_iter + after + before
-                                      if type(c).__name__ not in ('Kernel', 'ExchangeSelf', 'DoLoop', 'Timers', 'SimulationMonitor')))
+                                      if type(c).__name__ not in ('Kernel', 'ExchangeSelf', 'DoLoop', 'Timers', 'SimulationMonitor', 'Condition')))
+    if any(sp_['iotype'] == 'read' for sp_ in io_specs):
+        raise UnsupportedByB200('initial data read from an HDF5 file by ops_decl_dat_hdf5 (iohdf5(iotype="read")): pass the file to the '
+                                'runner with --restart instead')
+    plan['io'] = io_specs
     q_names = ['rho'] + ['rhou%d' % d for d in range(ndim)] + ['rhoE']
 
     # ---- stage loop: classify every kernel

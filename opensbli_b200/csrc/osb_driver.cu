@@ -96,6 +96,7 @@ struct osb_ctx {
   double *peer_buf[2][2][5] = {{{nullptr}}};
   double *own_buf[2][5] = {{nullptr}};
   bool peer_open[2] = {false, false};
+  long long peer_np[2] = {0, 0};                // neighbours' slab thickness along the slab axis
   // stream-ordered neighbour synchronisation (flag words written by the neighbours through peer pointers)
   unsigned long long *flags = nullptr;          // [0] low nbr read-done, [1] low nbr pushed, [2] high nbr read-done, [3] high nbr pushed, [7] error
   unsigned long long *peer_flags[2] = {nullptr, nullptr};
@@ -110,6 +111,8 @@ struct osb_ctx {
   long long iteration = 0;                      // loop counter of algorithm.py:440-474 (argument of the mass source)
   struct UserKernel { cudaLibrary_t lib = nullptr; cudaKernel_t kern = nullptr; std::vector<std::string> fields; int range[6]; int when = 0; };
   std::vector<UserKernel> user_kernels;
+  unsigned long long *slow_count = nullptr;     // bench instrumentation (osb_slow_path_count)
+  bool count_slow = false;
   double *diag_buf = nullptr;                   // partial sums of the diagnostics kernels
   bool prim_stale = false;                      // u, p, a, T arrays lag the state (stage kernels that derive them on the fly)
   int swap_parity = 0;                          // fused central path: q and Residual buffers exchange roles every stage
@@ -229,6 +232,7 @@ void refresh_constants(osb_ctx *c) {
   c->pc.dt = get("dt", 0.0);
   for (int d = 0; d < 3; d++) { c->pc.inv[d] = 1.0 / P.delta[d]; c->pc.inv2[d] = pow(P.delta[d], -2); }
   c->sp = make_scheme_params(get("eps", 1e-16), get("TENO_CT", 1e-6));
+  c->sp.slow_count = c->count_slow ? c->slow_count : nullptr;
   c->ad = make_adaptive_ct(P.teno_adaptive, get("teno_a1", 0.0), get("teno_a2", 0.0));
   c->pc.visc_law = P.visc_law; c->pc.mu_exp = P.mu_exp;
   c->pc.SuthT = get("SuthT", 0.0); c->pc.RefT = get("RefT", 1.0); c->pc.Twall = get("Twall", 1.0);
@@ -343,6 +347,7 @@ PeerPush peer_push(const osb_ctx *c, bool out_of_place = false) {
   const int d = c->plan.nd - 1;
   int hm, hp; scheme_halos(c->plan, hm, hp);
   pp.hm = hm; pp.hp = hp;
+  pp.np_lo = (int)c->peer_np[0];
   for (int m = 0; m < 5; m++) {
     pp.lo[m] = (c->plan.bc[d][0].kind == BC_EXCHANGE && c->peer_open[0]) ? c->peer_buf[0][set][m] : nullptr;
     pp.hi[m] = (c->plan.bc[d][1].kind == BC_EXCHANGE && c->peer_open[1]) ? c->peer_buf[1][set][m] : nullptr;
@@ -872,6 +877,7 @@ int osb_destroy(osb_ctx *c) {
   for (auto &k : c->user_kernels) if (k.lib) cudaLibraryUnload(k.lib);
   if (c->flags) cudaFree(c->flags);
   if (c->diag_buf) cudaFree(c->diag_buf);
+  if (c->slow_count) cudaFree(c->slow_count);
   for (auto &f : c->fields) cudaFree(f.dev);
   for (int d = 0; d < 3; d++) for (int s = 0; s < 2; s++) if (c->face_table[d][s]) cudaFree(c->face_table[d][s]);
   if (c->timer0) { cudaEventDestroy(c->timer0); cudaEventDestroy(c->timer1); }
@@ -1178,6 +1184,25 @@ int osb_diagnostics(osb_ctx *c, double *sums) {
   return run_diag(c, nullptr, sums);
 }
 
+// Instrumentation for the bench: count, over the next steps, the TENO5 characteristic waves that leave the all-pass shortcut
+// (osb_math.cuh teno5_front) for the full cut-off path.  enable != 0 arms the counter (and clears it); the count is returned.
+int osb_slow_path_count(osb_ctx *c, int enable, long long *count) {
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  if (!c->slow_count) OSB_CUDA(c, cudaMalloc(&c->slow_count, sizeof(unsigned long long)));
+  OSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (count) {
+    unsigned long long v = 0;
+    OSB_CUDA(c, cudaMemcpy(&v, c->slow_count, sizeof(v), cudaMemcpyDeviceToHost));
+    *count = (long long)v;
+  }
+  OSB_CUDA(c, cudaMemset(c->slow_count, 0, sizeof(unsigned long long)));
+  c->sp.slow_count = enable ? c->slow_count : nullptr;
+  c->count_slow = enable != 0;
+  drop_graph(c);
+  return 0;
+}
+
 int osb_launch_count(const osb_ctx *c, long long *n) { if (!c || !n) return 1; *n = c->launches; return 0; }
 
 int osb_profile_step(osb_ctx *c, double *fam_ms, long long *fam_n) {
@@ -1225,6 +1250,11 @@ int osb_ipc_export(osb_ctx *c, void *handles, int *nbytes) {
     memcpy((char *)handles + *nbytes, &h, sizeof(h));
     *nbytes += (int)sizeof(h);
   }
+  {                        // slab thickness (neighbours may differ by one plane when the block does not divide evenly)
+    const long long npd = c->grid.np[c->plan.nd - 1];
+    memcpy((char *)handles + *nbytes, &npd, sizeof(npd));
+    *nbytes += (int)sizeof(npd);
+  }
   return 0;
 }
 int osb_ipc_import(osb_ctx *c, int side, const void *handles, int nbytes) {
@@ -1232,7 +1262,8 @@ int osb_ipc_import(osb_ctx *c, int side, const void *handles, int nbytes) {
   cudaSetDevice(c->device);
   const int nv = c->plan.nd + 2;
   const int nh = 2 * nv + 1 + (c->gp.theta ? 1 : 0);
-  if (nbytes != nh * (int)sizeof(cudaIpcMemHandle_t)) return fail(c, "osb_ipc_import: wrong handle size");
+  if (nbytes != nh * (int)sizeof(cudaIpcMemHandle_t) + (int)sizeof(long long)) return fail(c, "osb_ipc_import: wrong handle size");
+  memcpy(&c->peer_np[side], (const char *)handles + nh * sizeof(cudaIpcMemHandle_t), sizeof(long long));
   if (c->gp.theta) {
     cudaIpcMemHandle_t h;
     memcpy(&h, (const char *)handles + (2 * nv + 1) * sizeof(h), sizeof(h));
@@ -1280,8 +1311,8 @@ int push_planes_memcpy(osb_ctx *c) {
       OSB_CUDA(c, cudaMemcpyAsync(c->peer_buf[1][c->swap_parity][m] + (g.h - hm) * g.s[d], c->fp.q[m] + (g.h + g.np[d] - hm) * g.s[d], plane * hm, cudaMemcpyDeviceToDevice, c->stream));
     }
     if (P.bc[d][0].kind == BC_EXCHANGE && c->peer_open[0]) {
-      // my bottom hp planes [0, hp) -> low neighbour's high halo [np, np+hp); neighbour has the same np
-      OSB_CUDA(c, cudaMemcpyAsync(c->peer_buf[0][c->swap_parity][m] + (g.h + g.np[d]) * g.s[d], c->fp.q[m] + g.h * g.s[d], plane * hp, cudaMemcpyDeviceToDevice, c->stream));
+      // my bottom hp planes [0, hp) -> low neighbour's high halo [np_lo, np_lo+hp) (the neighbour's own thickness)
+      OSB_CUDA(c, cudaMemcpyAsync(c->peer_buf[0][c->swap_parity][m] + (g.h + c->peer_np[0]) * g.s[d], c->fp.q[m] + g.h * g.s[d], plane * hp, cudaMemcpyDeviceToDevice, c->stream));
     }
   }
   return 0;

@@ -33,6 +33,9 @@ OSB_HD double f3_recon(const double *a, const double *b, const SchemeParams &sp)
     const Teno5Side tp = teno5_front(a[0], a[1], a[2], a[3], a[4], sp);
     const Teno5Side tm = teno5_front(b[0], b[1], b[2], b[3], b[4], sp);
     if (tp.all_pass && tm.all_pass) return teno5_linear(tp) + teno5_linear(tm);
+#if defined(__CUDA_ARCH__)
+    if (sp.slow_count) atomicAdd(sp.slow_count, 1ull);     // bench instrumentation: share of waves on the full cut-off path
+#endif
     return teno5_resolve(tp, sp) + teno5_resolve(tm, sp);
   } else if (RECON == RECON_TENO6) {
     // beta_3 of the right-biased side is not homogeneous (linear last term, teno.py:166-167): evaluate on f = g/2 itself

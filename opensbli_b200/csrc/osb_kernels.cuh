@@ -168,10 +168,11 @@ __global__ void __launch_bounds__(256, 2) k_viscous(GridDev g, FieldPtrs f, Phys
 // -------------------------------------------------------------------------------------------------
 // Slab decomposition: the kernel that finishes a stage also delivers the new boundary planes to the neighbour ranks by
 // peer stores over NVLink (pointers obtained through CUDA IPC): plane k >= np2-hm goes to the high neighbour's low halo,
-// plane k < hp to the low neighbour's high halo (same slab thickness on every rank).
+// plane k < hp to the low neighbour's high halo (which starts at that neighbour's own slab thickness).
 struct PeerPush {
   double *lo[5], *hi[5];     // neighbour's conserved arrays (nullptr: no neighbour on that side)
   int hm, hp;
+  int np_lo;                 // slab thickness of the low neighbour (its high halo starts at that plane; slabs may differ by one)
 };
 
 // Stream-ordered cross-GPU synchronisation without the host: a rank publishes an epoch number in its neighbours' flag
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled(GridDev g, F
           if (FROMQ) f.R[m][x] = qn; else f.q[m][x] = qn;
           // fused halo exchange: peer stores of the new boundary planes
           if (pp.hi[m] && k >= g.np[2] - pp.hm) pp.hi[m][x - (long long)g.np[2] * g.s[2]] = qn;
-          if (pp.lo[m] && k < pp.hp) pp.lo[m][x + (long long)g.np[2] * g.s[2]] = qn;
+          if (pp.lo[m] && k < pp.hp) pp.lo[m][x + (long long)pp.np_lo * g.s[2]] = qn;
         }
       }
     }
@@ -556,7 +557,7 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 1) k_central3d_fused(GridDev g, Q
         // slab decomposition: new boundary planes go straight into the neighbours' (next) q buffers
         if (PUSH) {
           if (pp.hi[m] && k >= g.np[2] - pp.hm) pp.hi[m][x - (long long)g.np[2] * g.s[2]] = qn;
-          if (pp.lo[m] && k < pp.hp) pp.lo[m][x + (long long)g.np[2] * g.s[2]] = qn;
+          if (pp.lo[m] && k < pp.hp) pp.lo[m][x + (long long)pp.np_lo * g.s[2]] = qn;
         }
       }
     }

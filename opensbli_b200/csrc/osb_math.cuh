@@ -36,6 +36,7 @@ struct SchemeParams {
   double eps16;    // 16*eps: TENO5 works on g = 2f with beta'' = 16 beta(f)
   double kfast5;   // 0.98 (3 C_T)^(-1/6): if 1 + tau/D_min <= kfast every TENO5 stencil passes the cut-off
   double kpass5;   // kfast5 - 1: the same test as  tau <= kpass5 D_r  for every r  (three compares, no minimum)
+  unsigned long long *slow_count;   // instrumentation (null in production): number of TENO5 waves that took the full cut-off path
   double kfast6;   // 0.98 (4 C_T)^(-1/6): same for the 4 stencils of TENO6
 };
 
@@ -69,6 +70,7 @@ inline SchemeParams make_scheme_params(double eps, double ct) {
   s.kfast5 = 0.98 * pow(3.0 * ct, -1.0 / 6.0);
   s.kfast6 = 0.98 * pow(4.0 * ct, -1.0 / 6.0);
   s.kpass5 = s.kfast5 - 1.0;
+  s.slow_count = nullptr;
   return s;
 }
 

@@ -33,12 +33,12 @@ def slab_axis(plan):
 
 
 def local_extent(plan, rank, world):
+    """(first plane, number of planes) of a rank's slab; when the block does not divide evenly the first n %% world ranks hold
+    one plane more"""
     ax = slab_axis(plan)
     n = plan['np'][ax]
-    if n % world:
-        raise _plan.PlanError('np[%d]=%d is not divisible by %d ranks' % (ax, n, world))
-    loc = n // world
-    return rank * loc, loc
+    base, rem = divmod(n, world)
+    return rank * base + min(rank, rem), base + (1 if rank < rem else 0)
 
 
 def neighbours(plan, rank, world):
@@ -59,7 +59,7 @@ def local_plan(plan, rank, world):
     ax = slab_axis(plan)
     _, loc = local_extent(plan, rank, world)
     hm, hp = scheme_halos(plan)
-    if loc < max(hm, hp):
+    if min(local_extent(plan, r, world)[1] for r in range(world)) < max(hm, hp):
         raise _plan.PlanError('slab of %d planes is thinner than the halo depth' % loc)
     p = copy.deepcopy(plan)
     p['np'][ax] = loc
@@ -96,7 +96,7 @@ def local_plan(plan, rank, world):
 def push_planes(plan_local, halo=5):
     """Plane index ranges (in the padded array, along the slab axis) of the two pushes of one rank:
     'up'   : my top hm planes    [np-hm, np) -> high neighbour's low halo  [-hm, 0)
-    'down' : my bottom hp planes [0, hp)     -> low neighbour's high halo  [np, np+hp)   (same np on every rank)"""
+    'down' : my bottom hp planes [0, hp)     -> low neighbour's high halo  [np_lo, np_lo+hp)   (np_lo: the low neighbour's thickness)"""
     ax = slab_axis(plan_local)
     n = plan_local['np'][ax]
     hm, hp = scheme_halos(plan_local)

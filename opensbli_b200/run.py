@@ -222,33 +222,195 @@ def initial_state(plan_sym, cold):
     return [np.ascontiguousarray(cold.array(n)) for n in plan_sym['q_names']]
 
 
-def time_loop(sim, plan, niter, workdir='.'):
-    """The reference's time loop as the runner drives it: niter steps on the GPU; with a SimulationMonitor the run is cut at
-    the iterations that print (iter == 0 or (iter+1) %% frequency == 0, algorithm.py:433-437) and the probe values are written
-    in the reference's format (simulation_monitors.py:128-160).  Returns the device time of the steps in ms."""
+def read_iteration_ops(stub_text):
+    """What `print_iteration_ops(every=N, NaN_check='rho_B0')` (utilities/helperfunctions.py:172-190) injected after the
+    `int iter=0;` line of the program text: -> (every or None, dataset to NaN-check or None)."""
+    m = re.search(r'if\(fmod\(iter\+1,\s*(\d+)\)\s*==\s*0\)', stub_text)
+    n = re.search(r'ops_NaNcheck\((\w+)\)', stub_text)
+    name = n.group(1) if n else None
+    if name and name.endswith('_B0'):
+        name = name[:-3]
+    return (int(m.group(1)) if m else None), name
+
+
+class Runner(object):
+    """One rank of a run: a Simulation (one GPU) or a DistributedSimulation (torchrun, one process per GPU; the block is cut
+    into slabs along its slowest axis).  Field access is by GLOBAL padded arrays on rank 0."""
+
+    def __init__(self, plan, dist=None, device=-1):
+        from .runtime import Simulation
+        from . import decomp
+        self.plan_global = plan
+        self.dist = dist
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        if self.world > 1:
+            self.dsim = decomp.DistributedSimulation(plan, dist, device)
+            self.sim = self.dsim.sim
+            self.k0, self.nk = self.dsim.offset, self.dsim.nloc
+        else:
+            self.dsim = None
+            self.sim = Simulation(plan, device=device)
+            self.k0, self.nk = 0, plan['np'][plan['ndim'] - 1]
+
+    def close(self):
+        self.sim.close()
+
+    def local_part(self, a):
+        """slab of a global padded array (slowest axis first in numpy order) incl. 5 halo planes on both sides"""
+        return np.ascontiguousarray(a[self.k0:self.k0 + self.nk + 10]) if self.world > 1 else a
+
+    def set_state(self, q_global):
+        q = [self.local_part(a) for a in q_global]
+        if self.dsim is not None:
+            self.dsim.set_state(q)
+        else:
+            self.sim.set_state(q)
+
+    def step_timed(self, n):
+        if n <= 0:
+            return 0.0
+        if self.dsim is None:
+            return self.sim.step_timed(n)
+        self.dsim.barrier()
+        self.sim.timer_start()
+        self.dsim.step(n)
+        ms = self.sim.timer_stop()
+        self.dsim.barrier()
+        return ms
+
+    def gather(self, name):
+        """global padded array of a dataset on rank 0 (None elsewhere): interior planes of every slab, outer halo planes of
+        the first and the last one"""
+        a = self.sim.download(name)
+        if self.world == 1:
+            return a
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, (self.k0, self.nk, a))
+        if self.rank != 0:
+            return None
+        parts.sort(key=lambda p: p[0])
+        pieces = [parts[0][2][:5]] + [p[2][5:5 + p[1]] for p in parts] + [parts[-1][2][-5:]]
+        return np.concatenate(pieces, axis=0)
+
+    def read_point(self, name, idx):
+        """value of a dataset at a GLOBAL grid index (every rank gets it)"""
+        idx = list(idx) + [0] * (3 - len(idx))
+        ax = self.plan_global['ndim'] - 1
+        if self.world == 1:
+            return self.sim.read_point(name, *idx)
+        mine = self.k0 <= idx[ax] < self.k0 + self.nk
+        loc = list(idx)
+        loc[ax] -= self.k0
+        v = self.sim.read_point(name, *loc) if mine else None
+        vals = [None] * self.world
+        self.dist.all_gather_object(vals, v)
+        return [x for x in vals if x is not None][0]
+
+    def nan_count(self, name):
+        n = self.sim.nan_check(name)
+        if self.world > 1:
+            vals = [None] * self.world
+            self.dist.all_gather_object(vals, n)
+            n = sum(vals)
+        return n
+
+    def diagnostics(self):
+        """volume averages over the whole block: kinetic energy, enstrophy, mass, total energy; max Mach number"""
+        d = self.sim.diagnostics()
+        if self.world > 1:
+            vals = [None] * self.world
+            self.dist.all_gather_object(vals, d)
+            d = {k: (max(v[k] for v in vals) if k == 'max_mach' else sum(v[k] for v in vals)) for k in d}
+        npts = float(np.prod(self.plan_global['np']))
+        return {'ke': d['sum_ke'] / npts, 'enstrophy': d['sum_enstrophy'] / npts, 'mass': d['sum_rho'] / npts,
+                'energy': d['sum_rhoE'] / npts, 'max_mach': d['max_mach'], 'nonfinite': d['nonfinite']}
+
+
+def write_output(runner, plan_sym, plan, cold, spec, workdir, iteration=None):
+    """One dataset file of an `iohdf5` component in the reference's layout (iodata.py): `opensbli_output.h5` after the loop,
+    `opensbli_output_%06d.h5` for the in-loop dumps of save_every (io_hdf5.py:99-127; npz stand-in without h5py)."""
+    from . import iodata
+    known = set(runner.sim.field_names())
+    arrays = {}
+    for name in spec['arrays']:
+        if name in known:
+            a = runner.gather(name)
+        elif name in cold.arrays:                    # coordinates, metric terms: evaluated once by the cold path
+            a = cold.arrays[name]
+        else:
+            raise KeyError("dataset '%s' requested by the output component exists neither on the device nor in the cold data" % name)
+        arrays[name] = a
+    if runner.rank != 0:
+        return None
+    base = spec.get('name') or 'opensbli_output'
+    base = base[:-3] if base.endswith('.h5') else base
+    if iteration is not None:
+        base = '%s_%06d' % (base, iteration)
+    return iodata.write_datasets(os.path.join(workdir, base), arrays, plan['np'])
+
+
+def time_loop(runner, plan, niter, workdir='.', plan_sym=None, cold=None, iteration_ops=(None, None), log=None):
+    """The reference's time loop as the runner drives it: niter steps on the GPU(s), cut at the iterations where the
+    generated program does something besides stepping (algorithm.py:433-463):
+      * SimulationMonitor: iter == 0 or (iter+1) %% frequency == 0 -> probe values in the reference's format (simulation_monitors.py:128-160)
+      * print_iteration_ops(every, NaN_check): (iter+1) %% every == 0 -> "Iteration is N" (+ NaN check of the dataset; a
+        non-finite value stops the run as ops_NaNcheck does)
+      * iohdf5(save_every=N): (iter+1) %% N == 0 -> opensbli_output_%%06d file
+    Accepts a Runner or a bare Simulation.  Returns the device time of the steps in ms."""
+    if not isinstance(runner, Runner):
+        sim = runner
+        runner = Runner.__new__(Runner)
+        runner.plan_global, runner.dist, runner.world, runner.rank, runner.dsim, runner.sim = plan, None, 1, 0, None, sim
+        runner.k0, runner.nk = 0, plan['np'][plan['ndim'] - 1]
     mon = plan.get('monitor')
-    if not mon or niter <= 0:
-        return sim.step_timed(niter) if niter > 0 else 0.0
+    every, nan_name = iteration_ops
+    dumps = [sp for sp in (plan_sym or {}).get('io', []) if sp.get('when') == 'in_loop']
+    log = log if log is not None else (lambda s: print(s, flush=True))
+    if niter <= 0:
+        return 0.0
+    stops = set()
+    if mon:
+        stops |= set([1] + list(range(mon['frequency'], niter + 1, mon['frequency'])))
+    if every:
+        stops |= set(range(every, niter + 1, every))
+    for sp in dumps:
+        stops |= set(range(sp['every'], niter + 1, sp['every']))
+    if not stops:
+        return runner.step_timed(niter)
     dt = plan['constants']['dt']
-    fmt = '%%.%df' % mon['precision']
-    out = open(os.path.join(workdir, mon['output_file']), 'w') if mon.get('output_file') else sys.stdout
+    out = None
+    if mon and runner.rank == 0:
+        out = open(os.path.join(workdir, mon['output_file']), 'w') if mon.get('output_file') else sys.stdout
+        fmt = '%%.%df' % mon['precision']
     ms, done = 0.0, 0
-    stops = sorted(set([1] + list(range(mon['frequency'], niter + 1, mon['frequency']))))
     try:
-        for stop in stops:
-            ms += sim.step_timed(stop - done)
+        for stop in sorted(stops):
+            ms += runner.step_timed(stop - done)
             done = stop
-            if stop == 1:
-                out.write(', '.join(['Iteration', 'Time'] + ['%s_B0(%s)' % (a, ', '.join(str(x) for x in pr)) for a, pr in zip(mon['arrays'], mon['probes'])]) + '\n')
-            vals = []
-            for a, pr in zip(mon['arrays'], mon['probes']):
-                v = sim.read_point(a, *pr)
-                vals.append(v / stop if 'mean' in a else v)      # running sums are reported as means
-            out.write(', '.join(['%d' % stop, fmt % (stop * dt)] + [fmt % v for v in vals]) + '\n')
+            if every and stop % every == 0:
+                if runner.rank == 0:
+                    log('Iteration is %d' % stop)
+                if nan_name:
+                    bad = runner.nan_count(nan_name)
+                    if bad:
+                        raise RuntimeError('NaN check: %d non-finite values in %s at iteration %d' % (bad, nan_name, stop))
+            if mon and (stop == 1 or stop % mon['frequency'] == 0):
+                vals = []
+                for a, pr in zip(mon['arrays'], mon['probes']):
+                    v = runner.read_point(a, pr)
+                    vals.append(v / stop if 'mean' in a else v)      # running sums are reported as means
+                if runner.rank == 0:
+                    if stop == 1:
+                        out.write(', '.join(['Iteration', 'Time'] + ['%s_B0(%s)' % (a, ', '.join(str(x) for x in pr)) for a, pr in zip(mon['arrays'], mon['probes'])]) + '\n')
+                    out.write(', '.join(['%d' % stop, fmt % (stop * dt)] + [fmt % v for v in vals]) + '\n')
+            for sp in dumps:
+                if stop % sp['every'] == 0:
+                    write_output(runner, plan_sym, plan, cold, sp, workdir, iteration=stop)
         if done < niter:
-            ms += sim.step_timed(niter - done)
+            ms += runner.step_timed(niter - done)
     finally:
-        if out is not sys.stdout:
+        if out is not None and out is not sys.stdout:
             out.close()
     return ms
 
@@ -261,21 +423,58 @@ def load_case(workdir='.', overrides=None):
 
 
 def main(argv=None):
-    argv = sys.argv[1:] if argv is None else argv
-    workdir = argv[0] if argv else '.'
-    from .runtime import Simulation
+    """python -m opensbli_b200.run [dir] [--restart FILE [--iteration N]] [--niter N]
+    Under `python -m torch.distributed.run --nproc-per-node N ...` the block is decomposed over N GPUs (one rank each)."""
+    import argparse
+    ap = argparse.ArgumentParser(prog='python -m opensbli_b200.run')
+    ap.add_argument('workdir', nargs='?', default='.')
+    ap.add_argument('--restart', default=None, help='dataset file (.h5 / .npz, reference layout) holding the conserved arrays to start from')
+    ap.add_argument('--iteration', type=int, default=0, help='iteration number the restart file was written at (time-dependent source terms)')
+    ap.add_argument('--niter', type=int, default=None, help='override the number of iterations of the program')
+    args = ap.parse_args(sys.argv[1:] if argv is None else argv)
+    workdir = args.workdir
     plan_sym, env, plan_num, cold = load_case(workdir)
+    stub = open(os.path.join(workdir, STUB_FILE)).read()
     q0 = initial_state(plan_sym, cold)
-    niter = plan_num.get('niter', 0)
-    with Simulation(plan_num) as sim:
-        sim.set_state(q0)
-        ms = time_loop(sim, plan_num, niter, workdir)
+    if args.restart:                                  # the reference's ops_decl_dat_hdf5 route (opsc.py:702-705, generate_restart.py)
+        from . import iodata
+        data, _ = iodata.read_datasets(args.restart if os.path.isabs(args.restart) else os.path.join(workdir, args.restart))
+        for m, n in enumerate(plan_sym['q_names']):
+            if n not in data or data[n].shape != q0[m].shape:
+                raise ValueError('restart file %s: dataset %s missing or of another shape' % (args.restart, n))
+            q0[m] = np.ascontiguousarray(data[n], dtype=np.float64)
+        plan_num['iteration0'] = args.iteration
+    niter = plan_num.get('niter', 0) if args.niter is None else args.niter
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    dist, device = None, -1
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        device = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(device)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', device))
+    runner = Runner(plan_num, dist, device)
+    try:
+        runner.set_state(q0)
+        if args.restart:
+            runner.sim.set_iteration(args.iteration)
+        ms = time_loop(runner, plan_num, niter, workdir, plan_sym=plan_sym, cold=cold, iteration_ops=read_iteration_ops(stub))
         if any(k['when'] == 'after_loop' for k in plan_num.get('user_kernels', [])):
-            sim.run_user_kernels('after_loop')                  # loops after the time loop (e.g. statistics / niter)
-        q = sim.get_state()
-        extra = {w: sim.download(w) for k in plan_num.get('user_kernels', []) for w in k['writes']}
-    print('Total Wall time %f' % (ms * 1e-3))      # same span as the reference's Timers (algorithm.py:301-327)
-    np.savez(os.path.join(workdir, 'opensbli_output.npz'), **{n: a for n, a in zip(plan_sym['q_names'], q)}, **extra)
+            runner.sim.run_user_kernels('after_loop')             # loops after the time loop (e.g. statistics / niter)
+        if runner.rank == 0:
+            print('Total Wall time %f' % (ms * 1e-3))             # same span as the reference's Timers (algorithm.py:301-327)
+        # dataset files the program writes after the loop; without an iohdf5 component the conserved arrays are still kept
+        specs = [sp for sp in plan_sym.get('io', []) if sp.get('when') == 'after'] or [{'arrays': list(plan_sym['q_names']), 'name': None}]
+        extra = [w for k in plan_num.get('user_kernels', []) for w in k['writes']]
+        for sp in specs:
+            sp = dict(sp, arrays=list(dict.fromkeys(list(sp['arrays']) + extra)))
+            path = write_output(runner, plan_sym, plan_num, cold, sp, workdir)
+            if runner.rank == 0:
+                print('wrote %s' % path)
+    finally:
+        runner.close()
+        if world > 1:
+            dist.destroy_process_group()
     return 0
 
 

@@ -17,7 +17,7 @@ FAMILIES = ('prim', 'flux', 'central', 'viscous', 'rk', 'bc', 'sync', 'user')
 SYMBOLS = ('osb_create', 'osb_destroy', 'osb_last_error', 'osb_set_const_f64', 'osb_get_const_f64', 'osb_set_iteration', 'osb_get_iteration', 'osb_create_field', 'osb_add_user_kernel', 'osb_run_user_kernels', 'osb_read_point',
            'osb_num_fields', 'osb_field_name', 'osb_field_info', 'osb_upload', 'osb_download', 'osb_device_ptr', 'osb_upload_face',
            'osb_step', 'osb_step_begin', 'osb_stage', 'osb_sync', 'osb_apply_bcs', 'osb_residual', 'osb_step_timed', 'osb_timer_start', 'osb_timer_stop', 'osb_advance_host',
-           'osb_launch_count', 'osb_profile_step', 'osb_nan_check', 'osb_diagnostics', 'osb_ipc_export', 'osb_ipc_import', 'osb_halo_push',
+           'osb_launch_count', 'osb_slow_path_count', 'osb_profile_step', 'osb_nan_check', 'osb_diagnostics', 'osb_ipc_export', 'osb_ipc_import', 'osb_halo_push',
            'osb_measure_fp64_peak')
 
 
@@ -72,6 +72,7 @@ def load_library(path=None):
     lib.osb_ipc_import.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
     lib.osb_halo_push.argtypes = [ctypes.c_void_p]
     lib.osb_measure_fp64_peak.argtypes = [ctypes.c_int, _P]
+    lib.osb_slow_path_count.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
     lib.osb_nan_check.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_longlong)]
     lib.osb_diagnostics.argtypes = [ctypes.c_void_p, _P]
     _lib = lib
@@ -277,6 +278,12 @@ class Simulation(object):
         v = (ctypes.c_double * len(self.DIAG))()
         self._check(self.lib.osb_diagnostics(self.ctx, v), 'osb_diagnostics')
         return dict(zip(self.DIAG, list(v)))
+
+    def slow_path_count(self, enable=True):
+        """arm (or disarm) the counter of TENO5 waves that take the full cut-off path; returns the count so far"""
+        n = ctypes.c_longlong()
+        self._check(self.lib.osb_slow_path_count(self.ctx, 1 if enable else 0, ctypes.byref(n)), 'osb_slow_path_count')
+        return n.value
 
     def launch_count(self):
         n = ctypes.c_longlong()

@@ -14,4 +14,8 @@ inv_0 = 1.0/Delta1block0;
 inv_1 = 1.0/Delta0block0;
 int iter=0;
 
+if(fmod(iter+1, 100) == 0){
+        ops_printf("Iteration is %d\n", iter+1); 
+        ops_NaNcheck(rho_B0);
+}
 }

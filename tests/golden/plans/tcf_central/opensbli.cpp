@@ -29,4 +29,7 @@ inv_4 = pow(Delta2block0, -2);
 inv_5 = pow(Delta0block0, -2);
 int iter=0;
 
+if(fmod(iter+1, 250) == 0){
+        ops_printf("Iteration is %d\n", iter+1); 
+}
 }

@@ -22,4 +22,8 @@ inv_2 = pow(Delta0block0, -2);
 inv_3 = pow(Delta1block0, -2);
 int iter=0;
 
+if(fmod(iter+1, 250) == 0){
+        ops_printf("Iteration is %d\n", iter+1); 
+        ops_NaNcheck(rho_B0);
+}
 }

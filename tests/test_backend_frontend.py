@@ -3,6 +3,7 @@
 fixtures.  The committed plan fixtures under tests/golden/plans/ make the same check possible without the reference."""
 import json
 import os
+import re
 import subprocess
 import sys
 
@@ -22,20 +23,26 @@ APPS = {
                   [("stats = True", "stats = False"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'tcf_teno6_16x24x12'),
     'lam2d': (REF + '/apps/channel_flow/laminar_2D/laminar_channel.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'lam2d_16x64'),
     'tcf_central': (REF + '/apps/channel_flow/compressible_TCF_Central/turbulent_channel.py',
-                    [("stats = True", "stats = False"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)"),
-                     ("print_iteration_ops()", "")], 'tcf_central_16x24x12'),
+                    [("stats = True", "stats = False"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'tcf_central_16x24x12'),
     'vst': (REF + '/apps/viscous_shock_tube/viscous_shock_tube.py',
-            [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)"), ("print_iteration_ops(NaN_check='rho_B0')", "")], 'vst_60x30'),
+            [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'vst_60x30'),
     'trans': (REF + '/apps/transitional_SBLI/transitional_SBLI.py',
               [("stats = True", "stats = False"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'trans_40x30x8'),
     'ewc': (REF + '/apps/euler_wave_curvilinear/euler_wave.py',
-            [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)"), ("print_iteration_ops(NaN_check='rho_B0', every=100)", "")], 'ewc_wenoz5_32'),
+            [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'ewc_wenoz5_32'),
     # the channel app exactly as shipped: statistics gathering (`User kernel` loops of stats.py) switched on
     'tcf_teno6_stats': (REF + '/apps/channel_flow/compressible_TCF_TENO/turbulent_channel.py',
-                        [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)"), ("print_iteration_ops()", "")], 'tcf_teno6_stats_16x24x12'),
+                        [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'tcf_teno6_stats_16x24x12'),
     # 3-D channel in the Feiereisen split on a uniform grid, as shipped: statistics user kernels and a SimulationMonitor
     't3d': (REF + '/apps/channel_flow/turbulent_3D/turbulent_channel.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),
     'sod_teno5': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'sod_teno5_n200'),
+    # BASELINE configs[3] as worded: the Katzer app with WENO-Z instead of adaptive TENO (same edits as oracle/gen_ref.py)
+    'katzer_wenoz': (REF + '/apps/katzer_SBLI/katzer_SBLI.py',
+                     [("sc1 = \"**{\\'scheme\\':\\'Teno\\'}\"", "sc1 = \"**{\\'scheme\\':\\'Weno\\'}\""), ("constituent.add_equations(shock_sensor)", "pass"),
+                      ("LLF = LLFTeno(teno_order, formulation='adaptive', averaging=Avg, sensor=sensor_array, store_sensor=True)",
+                       "LLF = LLFWeno(5, formulation='Z', averaging=Avg)"),
+                      (", DataObject('D11'), DataObject('TENO')])", ", DataObject('D11')])"),
+                      ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'katzer_wenoz_60x40'),
 }
 
 DRIVER = r'''
@@ -92,9 +99,17 @@ def test_b200_backend_distils_expected_plan(name, app_runs):
     if os.path.isdir(REF):
         workdir, rc = app_runs[name]
         assert rc == 0, 'B200(alg) failed on %s' % APPS[name][0]
-        os.makedirs(os.path.join(PLANS, name), exist_ok=True)      # refresh the committed fixtures
-        for f in ('opensbli_b200.plan.json', 'opensbli.cpp'):
-            open(os.path.join(PLANS, name, f), 'w').write(open(os.path.join(workdir, f)).read())
+        committed = os.path.join(PLANS, name)
+        if os.environ.get('OSB_REFRESH_PLAN_FIXTURES') or not os.path.exists(os.path.join(committed, 'opensbli.cpp')):
+            os.makedirs(committed, exist_ok=True)                  # opt-in: OSB_REFRESH_PLAN_FIXTURES=1 rewrites the committed fixtures
+            for f in ('opensbli_b200.plan.json', 'opensbli.cpp'):
+                open(os.path.join(committed, f), 'w').write(open(os.path.join(workdir, f)).read())
+        else:                                                      # otherwise they are the regression reference of the back end
+            fresh = json.load(open(os.path.join(workdir, 'opensbli_b200.plan.json')))
+            kept = json.load(open(os.path.join(committed, 'opensbli_b200.plan.json')))
+            assert fresh == kept, 'B200(alg) no longer distils the committed plan of %s: %s' % (
+                name, sorted(k for k in set(fresh) | set(kept) if fresh.get(k) != kept.get(k)))
+            assert open(os.path.join(workdir, 'opensbli.cpp')).read() == open(os.path.join(committed, 'opensbli.cpp')).read()
     else:
         workdir = os.path.join(PLANS, name)
         if not os.path.exists(os.path.join(workdir, 'opensbli.cpp')):
@@ -115,12 +130,21 @@ def test_b200_backend_distils_expected_plan(name, app_runs):
     assert 'gama' in plan_num['constants']
     # one-sided closure rows read off the IR equal the tables of the reference's scheme objects
     import numpy as np
-    for name, tab in want.get('closures', {}).items():
+    for cname, tab in want.get('closures', {}).items():
         for key in ('d1', 'd2'):
-            assert np.allclose(np.array(plan_num['closures'][name][key]), np.array(tab[key]), rtol=1e-12, atol=1e-14), (name, key)
+            assert np.allclose(np.array(plan_num['closures'][cname][key]), np.array(tab[key]), rtol=1e-12, atol=1e-14), (cname, key)
     # the stub keeps the reference's contract: every parameter was substituted, `int iter=0;` is present
     stub = open(os.path.join(workdir, 'opensbli.cpp')).read()
     assert '=Input;' not in stub and 'int iter=0;' in stub
+    # print_iteration_ops (helperfunctions.py:172-190) works unchanged on the stub and is honoured by the runner
+    calls = re.findall(r"^print_iteration_ops\((.*)\)", open(APPS[name][0]).read(), flags=re.M) if os.path.exists(APPS[name][0]) else []
+    every, nan_name = R.read_iteration_ops(stub)
+    if calls:
+        want_every = int(re.search(r'every\s*=\s*(\d+)', calls[-1]).group(1)) if 'every' in calls[-1] else 250
+        want_nan = re.search(r"NaN_check\s*=\s*'(\w+)'", calls[-1])
+        assert every == want_every and nan_name == (want_nan.group(1)[:-3] if want_nan else None), (calls, every, nan_name)
+    else:
+        assert every is None and nan_name is None
 
 
 def test_initial_state_from_cold_kernel_matches_reference_init():

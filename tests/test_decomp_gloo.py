@@ -107,7 +107,9 @@ def _worker(rank, world, port, fixture, nsteps, out, order='bcs_first'):
                                            # general path: metric fields follow the slab (3-D channel, periodic slab axis) ...
                                            ('tcf_central_16x24x12', 2), ('tcf_teno6_16x24x12', 2),
                                            # ... and physical walls / closures stay with the ranks that own them (2-D, slabs along y)
-                                           ('lam2d_16x64', 4), ('vst_60x30', 2)])
+                                           ('lam2d_16x64', 4), ('vst_60x30', 2),
+                                           # blocks that do not divide evenly: slabs of 9 + 8 and 22 + 21 + 21 planes
+                                           ('tgv_sym_17', 2), ('lam2d_16x64', 3)])
 def test_slab_decomposition_reproduces_single_domain(fixture, world, tmp_path):
     import oracle_util as ou
     from common import load_fixture, pad, inner
@@ -143,13 +145,14 @@ def test_decomp_helpers():
     from opensbli_b200 import decomp
     plan, _ = load_fixture('tgv_teno5_16')
     assert decomp.local_extent(plan, 3, 4) == (12, 4)
+    assert [decomp.local_extent({'ndim': 1, 'np': [250]}, r, 4) for r in range(4)] == [(0, 63), (63, 63), (126, 62), (188, 62)]
     assert decomp.neighbours(plan, 0, 4) == (3, 1) and decomp.neighbours(plan, 3, 4) == (2, 0)
     lp = decomp.local_plan(plan, 1, 2)
     assert lp['np'] == [16, 16, 8] and lp['bc'][2][0]['type'] == 'exchange' and lp['bc'][0][0]['type'] == 'periodic'
     pp = decomp.push_planes(lp)
     assert pp['up'] == ((5 + 8 - 3, 5 + 8), (2, 5)) and pp['down'] == ((5, 9), (13, 17))
     with pytest.raises(Exception):
-        decomp.local_plan(plan, 0, 3)
+        decomp.local_plan(plan, 0, 5)          # 16 planes over 5 ranks: slabs of 3 planes are thinner than the halo
     # point-wise user kernels (statistics) follow the slab
     withuk = dict(plan, user_kernels=[{'name': 'stats', 'range': [0, 16, 0, 16, 0, 16], 'when': 'iteration_end'}])
     assert decomp.local_plan(withuk, 1, 4)['user_kernels'][0]['range'] == [0, 16, 0, 16, 0, 4]
