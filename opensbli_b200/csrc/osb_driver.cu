@@ -16,6 +16,7 @@
 #include "../../include/osbli_b200.h"
 #include "osb_kernels.cuh"
 #include "osb_flux_api.h"
+#include "osb_tma_host.h"
 
 using namespace osb;
 
@@ -377,9 +378,27 @@ void neighbour_wait(osb_ctx *c, int kind) {
 
 int push_planes_memcpy(osb_ctx *c);
 
+bool stage_tma_enabled() {
+  static const bool on = getenv("OSB_NO_STAGE_TMA") == nullptr;
+  return on;
+}
+
 template <int RK, bool FROMQ = false>
 void launch_viscous_tiled(osb_ctx *c, double a, double b) {
   const GridDev &g = c->grid;
+  if (FROMQ && RK != 0 && stage_tma_enabled()) {          // TMA plane pipeline when the layout allows it (even padded x-extent)
+    TmaMaps5 maps;
+    bool ok = ((g.h - 3) & 1) == 0;
+    for (int m = 0; m < 5 && ok; m++) ok = tma_make_map(g, c->fp.q[m], VTM_BX, VT_HY, 1, maps.m[m]);
+    if (ok) {
+      auto kern = k_viscous3d_tma<(RK == 0 ? 1 : RK)>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vtm_smem_bytes());
+      dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + g.zlen - 1) / g.zlen);
+      Launcher L(c, OSB_FAM_VISCOUS);
+      kern<<<gr, bl, vtm_smem_bytes(), c->stream>>>(g, c->fp, c->pc, a, b, peer_push(c, true), maps);
+      return;
+    }
+  }
   auto kern = k_viscous3d_tiled<RK, FROMQ>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vt_smem_bytes());
   dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + g.zlen - 1) / g.zlen);

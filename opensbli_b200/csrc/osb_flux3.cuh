@@ -392,28 +392,8 @@ static_assert((F3_MTY & (F3_MTY - 1)) == 0, "ring addressing needs a power-of-tw
 // the B200: an odd start coordinate of 8-byte elements raises "illegal instruction"), and the interior starts at the odd
 // padded index 5.  34 doubles per row = 272 bytes (a multiple of 16), rows of the landed box are 4 banks apart.
 constexpr int F3_MBOX = 34;
-struct alignas(64) TmaMaps5 { unsigned char m[5][128]; };     // five CUtensorMap objects (rho, rhou0, rhou1, rhou2, rhoE)
 template <int RECON> constexpr size_t f3_march_smem_bytes() {
   return sizeof(double) * (5 * F3_MTY * F3_MBOX + 32 * (2 * F3_MTY * SV<3>::N + F3_MTY * F3<RECON>::NCOL + 2 * 5)) + 128;
-}
-
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase) {
-  unsigned ok;
-  do {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const void *map, unsigned long long *bar, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 template <int DIR, int RECON, int AVG, bool ACCUM>

@@ -8,6 +8,7 @@
 #include <tuple>
 #include "osb_flux_api.h"
 #include "osb_flux3.cuh"
+#include "osb_tma_host.h"
 
 #ifndef OSB_FLUX_ND
 #error "compile with -DOSB_FLUX_ND=1|2|3 -DOSB_FLUX_RECON=0|1|2|3"
@@ -34,44 +35,10 @@ cudaError_t sweep_x(const FluxArgs &a, cudaStream_t s) {
 }
 
 #if OSB_FLUX_ND == 3
-// ---- TMA descriptors of the conserved arrays for the marching kernel (driver API entry point fetched through the runtime:
-// the library does not link libcuda)
-typedef CUresult (*encode_tiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-encode_tiled_t encode_tiled() {
-  static encode_tiled_t fn = [] {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
-    return (encode_tiled_t)p;
-  }();
-  return fn;
-}
-
 // box of 34 x-lanes (see F3_MBOX) x F3_MTY rows along DIR of one padded array (x fastest); false if TMA cannot address it
 template <int DIR>
 bool make_map(const GridDev &g, double *base, unsigned char *out) {
-  static std::map<std::tuple<const void *, int, int, int, int>, std::array<unsigned char, 128>> cache;
-  const auto key = std::make_tuple((const void *)base, DIR, g.pd[0], g.pd[1], g.pd[2]);
-  auto it = cache.find(key);
-  if (it == cache.end()) {
-    encode_tiled_t enc = encode_tiled();
-    if (!enc) return false;
-    alignas(64) CUtensorMap m;
-    const cuuint64_t dims[3] = {(cuuint64_t)g.pd[0], (cuuint64_t)g.pd[1], (cuuint64_t)g.pd[2]};
-    const cuuint64_t strides[2] = {(cuuint64_t)g.s[1] * sizeof(double), (cuuint64_t)g.s[2] * sizeof(double)};
-    const cuuint32_t box[3] = {(cuuint32_t)F3_MBOX, DIR == 1 ? (cuuint32_t)F3_MTY : 1u, DIR == 2 ? (cuuint32_t)F3_MTY : 1u};
-    const cuuint32_t estr[3] = {1u, 1u, 1u};
-    if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return false;
-    std::array<unsigned char, 128> raw;
-    memcpy(raw.data(), &m, 128);
-    it = cache.emplace(key, raw).first;
-  }
-  memcpy(out, it->second.data(), 128);
-  return true;
+  return tma_make_map(g, base, F3_MBOX, DIR == 1 ? F3_MTY : 1, DIR == 2 ? F3_MTY : 1, out);
 }
 
 bool march_enabled() {

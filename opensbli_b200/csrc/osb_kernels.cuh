@@ -198,7 +198,7 @@ constexpr size_t vt_smem_bytes() { return sizeof(double) * 5 * 4 * VT_PLANE; }
 
 // u0, u1, u2, T of one point from its conserved state (constituent relations of the canonical system)
 __device__ __forceinline__ void prim_uT(const double *q, const PhysConst &c, double *w) {
-  const double irho = 1.0 / q[0];
+  const double irho = rcp_nr(q[0]);
   w[0] = q[1] * irho; w[1] = q[2] * irho; w[2] = q[3] * irho;
   const double p = (c.gama - 1.0) * (q[4] - 0.5 * q[0] * (w[0] * w[0] + w[1] * w[1] + w[2] * w[2]));
   w[3] = c.Minf * c.Minf * c.gama * p * irho;
@@ -381,6 +381,179 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tiled(GridDev g, F
       }
     }
     __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// The same stage kernel (constituent relations + viscous terms + RK update out of place + peer stores) with a TMA + mbarrier
+// plane pipeline: the raw conserved variables of plane k+3 / k+4 (tile + halo 2, one box of 38 x 12 per array) travel into a
+// two-stage ring by cp.async.bulk.tensor while plane k is computed; one elected thread issues, everybody waits on the
+// mbarrier of the stage, converts its share of the landed plane to (u0, u1, u2, T) and moves on.  The per-thread staging
+// loads, their address arithmetic and the 20 registers that carried them are gone; this point's Residual / RK register / q
+// lines of the NEXT plane are requested into L2 one iteration ahead.  Needs an even padded x-extent (TMA strides).
+// -------------------------------------------------------------------------------------------------
+constexpr int VTM_BX = 38, VTM_RAW = 464;          // box width (lanes -3 .. 34: 16-byte aligned start), doubles per landed array (3648 B padded to 29 x 128 B)
+constexpr size_t vtm_smem_bytes() { return sizeof(double) * (2 * 5 * VTM_RAW + 5 * 4 * VT_PLANE) + 64; }
+__device__ __forceinline__ double ldg_f64_volatile(const double *p) {      // not sunk to its use by the compiler
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
+template <int RK>   // 1 = low-storage update (rk_LS.py:139-166), 2 = SBLI update (rk_sbli.py:102-133)
+__global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tma(GridDev g, FieldPtrs f, PhysConst c, double rkA, double rkB, PeerPush pp,
+                                                                 const __grid_constant__ TmaMaps5 maps) {
+  extern __shared__ __align__(128) double vtm_smem[];
+  double *raw = vtm_smem;                                   // [2][5][VTM_RAW]
+  double *conv = raw + 2 * 5 * VTM_RAW;                     // [5 slots][4][VT_PLANE]
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(conv + 5 * 4 * VT_PLANE);   // [2]
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * VT_X + tx;
+  const int nzc = gridDim.z, zc = blockIdx.z == 0 ? 0 : (blockIdx.z == 1 ? nzc - 1 : (int)blockIdx.z - 1);   // boundary chunks first (peer stores)
+  const int i0 = blockIdx.x * VT_X, j0 = blockIdx.y * VT_Y, k0 = zc * g.zlen;
+  const int i = i0 + tx, j = j0 + ty;
+  const int kend = min(k0 + g.zlen, g.np[2]);
+  const int NP = (kend - k0) + 4;                           // planes k0-2 .. kend+1, numbered n = 0 .. NP-1
+  if (tid == 0) {
+    mbar_init(bar, 1); mbar_init(bar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int n) {                                 // thread 0: plane n -> raw stage n & 1
+    unsigned long long *b = bar + (n & 1);
+    mbar_expect_tx(b, 5 * VTM_BX * VT_HY * (unsigned)sizeof(double));
+#pragma unroll
+    for (int m = 0; m < 5; m++)
+      tma_load_3d(raw + ((n & 1) * 5 + m) * VTM_RAW, maps.m[m], b, i0 - 3 + g.h, j0 - 2 + g.h, k0 - 2 + n + g.h);
+  };
+  auto convert = [&](int n) {                               // landed plane n -> (u0, u1, u2, T) in ring slot n % 5
+    const double *rw = raw + (n & 1) * 5 * VTM_RAW;
+    double *cv = conv + (n % 5) * 4 * VT_PLANE;
+    for (int e = tid; e < VT_PLANE; e += VT_X * VT_Y) {
+      const int yy = e / VT_HX, xx = e - yy * VT_HX;
+      const int r = yy * VTM_BX + xx + 1;
+      double q[5], w[4];
+#pragma unroll
+      for (int m = 0; m < 5; m++) q[m] = rw[m * VTM_RAW + r];
+      prim_uT(q, c, w);
+#pragma unroll
+      for (int v = 0; v < 4; v++) cv[v * VT_PLANE + e] = w[v];
+    }
+  };
+  if (tid == 0) { issue(0); if (NP > 1) issue(1); }
+  for (int n = 0; n < 5; n++) {                             // prologue: planes k0-2 .. k0+2
+    mbar_wait(bar + (n & 1), (n >> 1) & 1);
+    convert(n);
+    __syncthreads();
+    if (tid == 0 && n + 2 < NP) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(n + 2); }
+  }
+  const double iRe = 1.0 / c.Re;
+  const double kq = iRe * (1.0 / (c.gama - 1.0)) * (1.0 / (c.Minf * c.Minf)) * (1.0 / c.Pr);
+  const int ce = (ty + 2) * VT_HX + tx + 2;
+  const bool active = i < g.np[0] && j < g.np[1];
+  const long long xcol = g.off + i + j * g.s[1];
+  if (active && (tx & 15) == 0) {                           // this point's Residual / RK register lines of the first plane into L2
+    const long long x = xcol + (long long)k0 * g.s[2];
+#pragma unroll
+    for (int m = 0; m < 5; m++) { prefetch_l2(f.R[m] + x); prefetch_l2(f.rk[m] + x); }
+  }
+  int s0 = 0;                                               // ring slot of plane k-2 (planes k-2 .. k+2 in slots s0, s0+1, .. mod 5)
+  // z-derivatives of x- and y-derivatives: this point's d/dx u0, d/dx u2, d/dy u1, d/dy u2 of the planes k-2 .. k+2 ride along in
+  // registers (one new plane per iteration), so that d/dz(d/dx .) and d/dz(d/dy .) cost no shared-memory loads (the kernel is
+  // bound by the shared-memory pipe: ncu r02, short_scoreboard 4.2 and mio_throttle 2.9 per issue, wavefronts 65 % of peak)
+  double gx0[5], gx2[5], gy1[5], gy2[5];
+  auto plane_grads = [&](int slot, double &ax0, double &ax2, double &ay1, double &ay2) {
+    const double *p0 = conv + (slot * 4 + 0) * VT_PLANE + ce, *p1 = p0 + VT_PLANE, *p2 = p1 + VT_PLANE;
+    ax0 = d1c(p0[-2], p0[-1], p0[1], p0[2], c.inv[0]);
+    ax2 = d1c(p2[-2], p2[-1], p2[1], p2[2], c.inv[0]);
+    ay1 = d1c(p1[-2 * VT_HX], p1[-VT_HX], p1[VT_HX], p1[2 * VT_HX], c.inv[1]);
+    ay2 = d1c(p2[-2 * VT_HX], p2[-VT_HX], p2[VT_HX], p2[2 * VT_HX], c.inv[1]);
+  };
+  if (active) {
+#pragma unroll
+    for (int n = 0; n < 4; n++) plane_grads(n, gx0[n + 1], gx2[n + 1], gy1[n + 1], gy2[n + 1]);   // shifted down at the top of the first iteration
+  }
+#pragma unroll 1
+  for (int k = k0; k < kend; k++) {
+    const long long x = xcol + (long long)k * g.s[2];
+    const bool more = k + 1 < kend;
+    // this point's Residual, RK register and q: requested at the top of the iteration (volatile: the compiler would sink the
+    // loads to their use at the end and expose the latency), the lines were brought into L2 one iteration earlier
+    if (active && more && (tx & 15) == 0) {
+#pragma unroll
+      for (int m = 0; m < 5; m++) { prefetch_l2(f.R[m] + x + g.s[2]); prefetch_l2(f.rk[m] + x + g.s[2]); }
+    }
+    if (active) {
+#pragma unroll
+      for (int n = 0; n < 4; n++) { gx0[n] = gx0[n + 1]; gx2[n] = gx2[n + 1]; gy1[n] = gy1[n + 1]; gy2[n] = gy2[n + 1]; }
+      { int sl = s0 + 4; sl = sl >= 5 ? sl - 5 : sl; plane_grads(sl, gx0[4], gx2[4], gy1[4], gy2[4]); }
+      const double *P[5][4];
+#pragma unroll
+      for (int dz = 0; dz < 5; dz++) {
+        int sl = s0 + dz; sl = sl >= 5 ? sl - 5 : sl;
+#pragma unroll
+        for (int v = 0; v < 4; v++) P[dz][v] = conv + (sl * 4 + v) * VT_PLANE + ce;
+      }
+      double dv[3][3], d2[4][3];
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        const double *p = P[2][v];
+        const double fx = d1c(p[-2], p[-1], p[1], p[2], c.inv[0]);
+        const double fy = d1c(p[-2 * VT_HX], p[-VT_HX], p[VT_HX], p[2 * VT_HX], c.inv[1]);
+        const double fz = d1c(P[0][v][0], P[1][v][0], P[3][v][0], P[4][v][0], c.inv[2]);
+        if (v < 3) { dv[v][0] = fx; dv[v][1] = fy; dv[v][2] = fz; }
+        d2[v][0] = d2c(p[-2], p[-1], p[0], p[1], p[2], c.inv2[0]);
+        d2[v][1] = d2c(p[-2 * VT_HX], p[-VT_HX], p[0], p[VT_HX], p[2 * VT_HX], c.inv2[1]);
+        d2[v][2] = d2c(P[0][v][0], P[1][v][0], p[0], P[3][v][0], P[4][v][0], c.inv2[2]);
+      }
+      auto dxy = [&](int v) {        // d/dy ( d/dx )
+        const double *p = P[2][v];
+        double r[4];
+        const int oy[4] = {-2 * VT_HX, -VT_HX, VT_HX, 2 * VT_HX};
+#pragma unroll
+        for (int q = 0; q < 4; q++) r[q] = d1c(p[oy[q] - 2], p[oy[q] - 1], p[oy[q] + 1], p[oy[q] + 2], c.inv[0]);
+        return d1c(r[0], r[1], r[2], r[3], c.inv[1]);
+      };
+      // d/dz(d/dx u2), d/dz(d/dx u0), d/dz(d/dy u2), d/dz(d/dy u1) from the register rings
+      const double dxz2 = d1c(gx2[0], gx2[1], gx2[3], gx2[4], c.inv[2]), dxz0 = d1c(gx0[0], gx0[1], gx0[3], gx0[4], c.inv[2]);
+      const double dyz2 = d1c(gy2[0], gy2[1], gy2[3], gy2[4], c.inv[2]), dyz1 = d1c(gy1[0], gy1[1], gy1[3], gy1[4], c.inv[2]);
+      double vis[3];
+      vis[0] = iRe * ((4.0 / 3.0) * d2[0][0] + d2[0][1] + d2[0][2] + (1.0 / 3.0) * (dxy(1) + dxz2));
+      vis[1] = iRe * (d2[1][0] + (4.0 / 3.0) * d2[1][1] + d2[1][2] + (1.0 / 3.0) * (dxy(0) + dyz2));
+      vis[2] = iRe * (d2[2][0] + d2[2][1] + (4.0 / 3.0) * d2[2][2] + (1.0 / 3.0) * (dxz0 + dyz1));
+      const double div = dv[0][0] + dv[1][1] + dv[2][2];
+      double e = kq * (d2[3][0] + d2[3][1] + d2[3][2]);
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int b = a + 1; b < 3; b++) { const double sab = dv[a][b] + dv[b][a]; e += iRe * sab * sab; }
+        e += iRe * (2.0 * dv[a][a] - (2.0 / 3.0) * div) * dv[a][a];
+        e += vis[a] * P[2][a][0];
+      }
+      // this point's Residual, RK register and q: the lines were brought into L2 one iteration earlier (q: by the plane's box);
+      // loaded only now -- held across the derivative evaluation they cost 30 registers and spill
+      double cR[5], cO[5], cQ[5];
+#pragma unroll
+      for (int m = 0; m < 5; m++) { cR[m] = ldg_f64_volatile(f.R[m] + x); cO[m] = ldg_f64_volatile(f.rk[m] + x); cQ[m] = ldg_f64_volatile(f.q[m] + x); }
+      cR[1] += vis[0]; cR[2] += vis[1]; cR[3] += vis[2]; cR[4] += e;
+#pragma unroll
+      for (int m = 0; m < 5; m++) {
+        double qn;
+        if (RK == 1) { const double t = c.dt * cR[m] + rkA * cO[m]; f.rk[m][x] = t; qn = rkB * t + cQ[m]; }
+        else { qn = c.dt * rkB * cR[m] + cO[m]; f.rk[m][x] = c.dt * rkA * cR[m] + cO[m]; }
+        f.R[m][x] = qn;                                      // out of place: the Residual buffers become the new q
+        if (pp.hi[m] && k >= g.np[2] - pp.hm) pp.hi[m][x - (long long)g.np[2] * g.s[2]] = qn;
+        if (pp.lo[m] && k < pp.hp) pp.lo[m][x + (long long)pp.np_lo * g.s[2]] = qn;
+      }
+    }
+    __syncthreads();                                        // every thread is done reading the slot of plane k-2
+    if (more) {
+      const int n = k - k0 + 5;                             // plane k+3
+      mbar_wait(bar + (n & 1), (n >> 1) & 1);
+      convert(n);
+      __syncthreads();
+      if (tid == 0 && n + 2 < NP) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(n + 2); }
+      s0 = s0 == 4 ? 0 : s0 + 1;
+    }
   }
 }
 
