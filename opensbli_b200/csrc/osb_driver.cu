@@ -618,14 +618,24 @@ void launch_central_fused(osb_ctx *c, int stage) {
   QPtrs qi, qo, rk;
   for (int m = 0; m < 5; m++) { qi.q[m] = c->fp.q[m]; qo.q[m] = c->fp.R[m]; rk.q[m] = c->fp.rk[m]; }
   const bool push = has_exchange(c);
+  TmaMaps5 maps;
+  bool tma = stage_tma_enabled() && ((g.h - 3) & 1) == 0;
+  for (int m = 0; m < 5 && tma; m++) tma = tma_make_map(g, c->fp.q[m], VTM_BX, VT_HY, 1, maps.m[m]);
+  if (!tma) memset(&maps, 0, sizeof(maps));
   auto launch = [&](auto kern, int first) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_smem_bytes());
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_smem_bytes(tma));
     dim3 bl(VT_X, VT_Y, 1), gr((g.np[0] + VT_X - 1) / VT_X, (g.np[1] + VT_Y - 1) / VT_Y, (g.np[2] + g.zlen - 1) / g.zlen);
     Launcher L(c, OSB_FAM_CENTRAL);
-    kern<<<gr, bl, ct_smem_bytes(), c->stream>>>(g, qi, qo, rk, c->pc, c->plan.rk_a[stage], c->plan.rk_b[stage], first, push ? peer_push(c, true) : PeerPush{});
+    kern<<<gr, bl, ct_smem_bytes(tma), c->stream>>>(g, qi, qo, rk, c->pc, c->plan.rk_a[stage], c->plan.rk_b[stage], first, push ? peer_push(c, true) : PeerPush{}, maps);
   };
-  if (c->plan.rk == RK_LS) { if (push) launch(k_central3d_fused<1, true>, 0); else launch(k_central3d_fused<1, false>, 0); }
-  else { if (push) launch(k_central3d_fused<2, true>, stage == 0); else launch(k_central3d_fused<2, false>, stage == 0); }
+  const int first = (c->plan.rk == RK_LS) ? 0 : (stage == 0);
+  if (c->plan.rk == RK_LS) {
+    if (push) { if (tma) launch(k_central3d_fused<1, true, true>, first); else launch(k_central3d_fused<1, true, false>, first); }
+    else { if (tma) launch(k_central3d_fused<1, false, true>, first); else launch(k_central3d_fused<1, false, false>, first); }
+  } else {
+    if (push) { if (tma) launch(k_central3d_fused<2, true, true>, first); else launch(k_central3d_fused<2, true, false>, first); }
+    else { if (tma) launch(k_central3d_fused<2, false, true>, first); else launch(k_central3d_fused<2, false, false>, first); }
+  }
   swap_q_and_residual(c);
 }
 

@@ -565,13 +565,20 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 2) k_viscous3d_tma(GridDev g, Fie
 // (q_in -> q_out): neighbouring blocks still read the old values of the points this block updates.
 // -------------------------------------------------------------------------------------------------
 constexpr int CT_NV = 7, CT_RHO = 0, CT_E = 1, CT_U = 2, CT_P = 5, CT_T = 6;
-constexpr size_t ct_smem_bytes() { return sizeof(double) * 5 * CT_NV * VT_PLANE; }
+constexpr size_t ct_smem_bytes(bool tma = false) { return sizeof(double) * (5 * CT_NV * VT_PLANE + (tma ? 2 * 5 * 464 : 0)) + 64; }
 struct QPtrs { double *q[5]; };
 
-template <int RK, bool PUSH>   // RK 1 = low-storage update, 2 = SBLI update (first_stage folds the "Save equations" loop: old = q); PUSH: slab run
+// TMA = true: the raw conserved planes arrive through the TMA + mbarrier pipeline of k_viscous3d_tma (two-stage ring of
+// 38 x 12 boxes per array) instead of per-thread loads, the RK register is loaded just before the update and the
+// z-derivatives of x/y-derivatives come from register rings; needs an even padded x-extent.
+template <int RK, bool PUSH, bool TMA>   // RK 1 = low-storage update, 2 = SBLI update (first_stage folds the "Save equations" loop: old = q); PUSH: slab run
 __global__ void __launch_bounds__(VT_X * VT_Y, 1) k_central3d_fused(GridDev g, QPtrs qin, QPtrs qout, QPtrs rkreg, PhysConst c,
-                                                                   double rkA, double rkB, int first_stage, PeerPush pp) {
-  extern __shared__ double ct_smem[];
+                                                                   double rkA, double rkB, int first_stage, PeerPush pp,
+                                                                   const __grid_constant__ TmaMaps5 maps) {
+  extern __shared__ __align__(128) double ct_smem_all[];
+  double *raw = ct_smem_all;                                              // TMA: [2][5][VTM_RAW] landing zone
+  double *ct_smem = ct_smem_all + (TMA ? 2 * 5 * VTM_RAW : 0);           // [5 slots][CT_NV][VT_PLANE]
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(ct_smem + 5 * CT_NV * VT_PLANE);
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * VT_X + tx;
   const int i0 = blockIdx.x * VT_X, j0 = blockIdx.y * VT_Y, k0 = blockIdx.z * g.zlen;
   const int i = i0 + tx, j = j0 + ty;
@@ -585,34 +592,81 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 1) k_central3d_fused(GridDev g, Q
     return e < VT_PLANE && gi < g.np[0] + 2 && gj < g.np[1] + 2;
   };
   auto stage = [&](int slot, int e, const double *q) {     // constituent relations of one staged point
-    const double rho = q[0], irho = 1.0 / rho;
+    const double rho = q[0], irho = TMA ? rcp_nr(rho) : 1.0 / rho;
     const double u0 = q[1] * irho, u1 = q[2] * irho, u2 = q[3] * irho;
     const double p = (c.gama - 1.0) * (q[4] - 0.5 * rho * (u0 * u0 + u1 * u1 + u2 * u2));
     S(slot, CT_RHO)[e] = rho; S(slot, CT_E)[e] = q[4];
     S(slot, CT_U)[e] = u0; S(slot, CT_U + 1)[e] = u1; S(slot, CT_U + 2)[e] = u2;
     S(slot, CT_P)[e] = p; S(slot, CT_T)[e] = c.Minf * c.Minf * c.gama * p * irho;
   };
-  for (int kk = k0 - 2; kk <= k0 + 2; kk++)
-    for (int it = 0; it < NPF; it++) {
-      long long xg;
-      const int e = tid + it * VT_X * VT_Y;
-      if (in_tile(e, xg, kk)) {
-        double q[5];
+  const int NP = (kend - k0) + 4;                           // TMA: planes k0-2 .. kend+1, numbered n = 0 .. NP-1
+  auto issue = [&](int n) {                                 // thread 0: plane n -> raw stage n & 1
+    unsigned long long *b = bar + (n & 1);
+    mbar_expect_tx(b, 5 * VTM_BX * VT_HY * (unsigned)sizeof(double));
 #pragma unroll
-        for (int m = 0; m < 5; m++) q[m] = __ldg(qin.q[m] + xg);
-        stage((kk + 10) % 5, e, q);
-      }
+    for (int m = 0; m < 5; m++)
+      tma_load_3d(raw + ((n & 1) * 5 + m) * VTM_RAW, maps.m[m], b, i0 - 3 + g.h, j0 - 2 + g.h, k0 - 2 + n + g.h);
+  };
+  auto convert = [&](int n) {                               // landed plane n -> staged values in ring slot of that plane
+    const double *rw = raw + (n & 1) * 5 * VTM_RAW;
+    for (int e = tid; e < VT_PLANE; e += VT_X * VT_Y) {
+      const int yy = e / VT_HX, xx = e - yy * VT_HX;
+      double q[5];
+#pragma unroll
+      for (int m = 0; m < 5; m++) q[m] = rw[m * VTM_RAW + yy * VTM_BX + xx + 1];
+      stage((k0 - 2 + n + 10) % 5, e, q);
     }
+  };
+  if (TMA) {
+    if (tid == 0) {
+      mbar_init(bar, 1); mbar_init(bar + 1, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) { issue(0); issue(1); }
+    for (int n = 0; n < 5; n++) {
+      mbar_wait(bar + (n & 1), (n >> 1) & 1);
+      convert(n);
+      __syncthreads();
+      if (tid == 0 && n + 2 < NP) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(n + 2); }
+    }
+  } else {
+    for (int kk = k0 - 2; kk <= k0 + 2; kk++)
+      for (int it = 0; it < NPF; it++) {
+        long long xg;
+        const int e = tid + it * VT_X * VT_Y;
+        if (in_tile(e, xg, kk)) {
+          double q[5];
+#pragma unroll
+          for (int m = 0; m < 5; m++) q[m] = __ldg(qin.q[m] + xg);
+          stage((kk + 10) % 5, e, q);
+        }
+      }
+  }
   const double iRe = 1.0 / c.Re;
   const double kq = iRe * (1.0 / (c.gama - 1.0)) * (1.0 / (c.Minf * c.Minf)) * (1.0 / c.Pr);
   const int ce = (ty + 2) * VT_HX + tx + 2;
   const bool active = i < g.np[0] && j < g.np[1];
   __syncthreads();
+  // TMA: this point's d/dx u0, d/dx u2, d/dy u1, d/dy u2 of the planes k-2 .. k+2 in registers (see k_viscous3d_tma)
+  double gx0[5], gx2[5], gy1[5], gy2[5];
+  auto plane_grads = [&](int kk, double &ax0, double &ax2, double &ay1, double &ay2) {
+    const double *p0 = S((kk + 10) % 5, CT_U) + ce, *p1 = p0 + VT_PLANE, *p2 = p1 + VT_PLANE;
+    ax0 = d1c(p0[-2], p0[-1], p0[1], p0[2], c.inv[0]);
+    ax2 = d1c(p2[-2], p2[-1], p2[1], p2[2], c.inv[0]);
+    ay1 = d1c(p1[-2 * VT_HX], p1[-VT_HX], p1[VT_HX], p1[2 * VT_HX], c.inv[1]);
+    ay2 = d1c(p2[-2 * VT_HX], p2[-VT_HX], p2[VT_HX], p2[2 * VT_HX], c.inv[1]);
+  };
+  if (TMA && active) {
+#pragma unroll
+    for (int n = 0; n < 4; n++) plane_grads(k0 - 2 + n, gx0[n + 1], gx2[n + 1], gy1[n + 1], gy2[n + 1]);
+  }
+#pragma unroll 1
   for (int k = k0; k < kend; k++) {
     // software pipeline: raw q of plane k+3 and this point's RK register travel while plane k is computed
     double pf[NPF][5];
     const bool more = k + 1 < kend;
-    if (more) {
+    if (!TMA && more) {
 #pragma unroll
       for (int it = 0; it < NPF; it++) {
         long long xg;
@@ -628,11 +682,16 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 1) k_central3d_fused(GridDev g, Q
       for (int m = 0; m < 5; m++) prefetch_l2(rkreg.q[m] + x + g.s[2]);
     }
     double o[5];
-    if (active && !(RK == 2 && first_stage)) {
+    if (!TMA && active && !(RK == 2 && first_stage)) {
 #pragma unroll
       for (int m = 0; m < 5; m++) o[m] = rkreg.q[m][x];
     }
     if (active) {
+      if (TMA) {
+#pragma unroll
+        for (int n = 0; n < 4; n++) { gx0[n] = gx0[n + 1]; gx2[n] = gx2[n + 1]; gy1[n] = gy1[n + 1]; gy2[n] = gy2[n + 1]; }
+        plane_grads(k + 2, gx0[4], gx2[4], gy1[4], gy2[4]);
+      }
       const double *P[5][CT_NV];
 #pragma unroll
       for (int dz = 0; dz < 5; dz++)
@@ -707,9 +766,17 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 1) k_central3d_fused(GridDev g, Q
         return d1c(r[0], r[1], r[2], r[3], c.inv[2]);
       };
       double vis[3];
-      vis[0] = iRe * ((4.0 / 3.0) * d2[0][0] + d2[0][1] + d2[0][2] + (1.0 / 3.0) * (dxy(1) + dxz(2)));
-      vis[1] = iRe * (d2[1][0] + (4.0 / 3.0) * d2[1][1] + d2[1][2] + (1.0 / 3.0) * (dxy(0) + dyz(2)));
-      vis[2] = iRe * (d2[2][0] + d2[2][1] + (4.0 / 3.0) * d2[2][2] + (1.0 / 3.0) * (dxz(0) + dyz(1)));
+      if (TMA) {     // d/dz(d/dx .), d/dz(d/dy .) from the register rings
+        const double dxz2 = d1c(gx2[0], gx2[1], gx2[3], gx2[4], c.inv[2]), dxz0 = d1c(gx0[0], gx0[1], gx0[3], gx0[4], c.inv[2]);
+        const double dyz2 = d1c(gy2[0], gy2[1], gy2[3], gy2[4], c.inv[2]), dyz1 = d1c(gy1[0], gy1[1], gy1[3], gy1[4], c.inv[2]);
+        vis[0] = iRe * ((4.0 / 3.0) * d2[0][0] + d2[0][1] + d2[0][2] + (1.0 / 3.0) * (dxy(1) + dxz2));
+        vis[1] = iRe * (d2[1][0] + (4.0 / 3.0) * d2[1][1] + d2[1][2] + (1.0 / 3.0) * (dxy(0) + dyz2));
+        vis[2] = iRe * (d2[2][0] + d2[2][1] + (4.0 / 3.0) * d2[2][2] + (1.0 / 3.0) * (dxz0 + dyz1));
+      } else {
+        vis[0] = iRe * ((4.0 / 3.0) * d2[0][0] + d2[0][1] + d2[0][2] + (1.0 / 3.0) * (dxy(1) + dxz(2)));
+        vis[1] = iRe * (d2[1][0] + (4.0 / 3.0) * d2[1][1] + d2[1][2] + (1.0 / 3.0) * (dxy(0) + dyz(2)));
+        vis[2] = iRe * (d2[2][0] + d2[2][1] + (4.0 / 3.0) * d2[2][2] + (1.0 / 3.0) * (dxz(0) + dyz(1)));
+      }
       const double dvg = dv[0][0] + dv[1][1] + dv[2][2];
       double e = kq * (d2[3][0] + d2[3][1] + d2[3][2]);
 #pragma unroll
@@ -721,6 +788,10 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 1) k_central3d_fused(GridDev g, Q
       }
       R[1] += vis[0]; R[2] += vis[1]; R[3] += vis[2]; R[4] += e;
       // ---- RK update, out of place
+      if (TMA && !(RK == 2 && first_stage)) {       // RK register: line prefetched into L2 one plane earlier, loaded only now
+#pragma unroll
+        for (int m = 0; m < 5; m++) o[m] = ldg_f64_volatile(rkreg.q[m] + x);
+      }
 #pragma unroll
       for (int m = 0; m < 5; m++) {
         double qn;
@@ -735,6 +806,16 @@ __global__ void __launch_bounds__(VT_X * VT_Y, 1) k_central3d_fused(GridDev g, Q
       }
     }
     __syncthreads();
+    if (TMA) {
+      if (more) {
+        const int n = k - k0 + 5;                           // plane k+3
+        mbar_wait(bar + (n & 1), (n >> 1) & 1);
+        convert(n);
+        __syncthreads();
+        if (tid == 0 && n + 2 < NP) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(n + 2); }
+      }
+      continue;
+    }
     if (more) {
 #pragma unroll
       for (int it = 0; it < NPF; it++) {

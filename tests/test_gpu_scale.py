@@ -134,3 +134,38 @@ def test_katzer_500x250_as_shipped(config):
     err = field_errors(plan, qg, inner(plan, qo))
     print(config, '500x250 vs oracle', describe(err))
     assert max(err) < tol_for(plan, nsteps), err
+
+
+def test_tgv_64_cubed_100_steps_norms_and_diagnostics():
+    """north_star: "final-time L2 norms and diagnostics within 1e-10".  TGV TENO5 64^3 advanced 100 steps (a non-chaotic
+    horizon) on the GPU and by the reference executable: L2 norms of the conserved fields, and the volume-averaged kinetic
+    energy / enstrophy -- from the device reductions (osb_diagnostics) on one side, computed offline with numpy from the
+    reference's dump (how the reference workflow obtains them) on the other."""
+    import opensbli_b200
+    from test_gpu_diag import numpy_diagnostics
+    if not ou.have_ref('tgv_teno5'):
+        pytest.skip('oracle/_ref/tgv_teno5 not built')
+    n, nsteps = 64, 100
+    plan, q0 = tgv_case((n, n, n), 'teno5')
+    with opensbli_b200.Simulation(plan) as sim:
+        sim.set_state([a.copy() for a in q0])
+        sim.step(nsteps)
+        d = sim.diagnostics()
+        qg = inner(plan, sim.get_state())
+    names = ['rho', 'rhou0', 'rhou1', 'rhou2', 'rhoE']
+    r = ou.run_ref('tgv_teno5', dict(block0np0=n, block0np1=n, block0np2=n, niter=nsteps, dt=plan['constants']['dt']), names,
+                   exe='ref_omp', threads=ref_threads())
+    # the reference's dump carries the halos its last exchange left: periodic images, enough for the 4th-order vorticity
+    want = numpy_diagnostics(plan, [r[f] for f in names])
+    npts = float(n ** 3)
+    for key in ('sum_ke', 'sum_enstrophy', 'sum_rho', 'sum_rhoE'):
+        rel = abs(d[key] - want[key]) / abs(want[key])
+        print(key, d[key] / npts, want[key] / npts, 'rel %.2e' % rel)
+        assert rel < 1e-10, (key, d[key], want[key])
+    ref = np.stack([r[f][5:-5, 5:-5, 5:-5] for f in names])
+    for m, f in enumerate(names):
+        l2g, l2r = np.sqrt(np.mean(qg[m] ** 2)), np.sqrt(np.mean(ref[m] ** 2))
+        assert abs(l2g - l2r) <= 1e-10 * max(l2r, 1e-30), (f, l2g, l2r)
+    err = field_errors(plan, qg, ref)
+    print('100 steps, fields', describe(err))
+    assert max(err) < 1e-10, err
