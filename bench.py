@@ -32,10 +32,13 @@ ALG_BYTES_PER_UPDATE = 480.0          # 3 stages x (5 q + 5 RK r
 ALG_FLOP_PER_POINT_FLUX_SWEEP = 2836.0 + 50.0 / 3.0   # reference count_ops: one LLFTeno_reconstruction_d loop + its share of the Residual loop
 ALG_FLOP_PER_UPDATE = 27.1e3          # 3 x 9038 (reference's own operation count, opsc.py:411-418)
 # dram__bytes_read.sum + dram__bytes_write.sum per flux-sweep launch at 512^3 from the `ncu --set full` capture
-# profiles/r01_final_ncu_top_kernels_512.md: z 15.55 GB, x 16.32 GB, y 22.50 GB -> mean of the three launches of a stage
+# profiles/r02_final_ncu_top_kernels_512.md: z 11.04 GB, x 16.34 GB, y 16.44 GB -> mean of the three launches of a stage
 # (algorithmic: 5 q read + 5 residual read + 5 residual write = 16.1 GB for the accumulating sweeps, 10.7 GB for the first)
-NCU_DRAM_BYTES_PER_FLUX_LAUNCH_512 = 18.12e9
-NCU_DRAM_BYTES_PER_CENTRAL_LAUNCH_512 = 22.80e9     # k_central3d_fused at 512^3: 12.02 GB read + 10.78 GB written (algorithmic 21.5 GB)
+NCU_DRAM_BYTES_PER_FLUX_LAUNCH_512 = 14.61e9
+NCU_DRAM_BYTES_PER_CENTRAL_LAUNCH_512 = 22.58e9     # k_central3d_fused<.., TMA> at 512^3: 11.81 GB read + 10.77 GB written (algorithmic 21.5 GB)
+# sm__pipe_fp64_cycles_active (fraction of peak) of the z, x, y sweep kernels in the same capture: what the hardware says beside
+# the algorithmic fraction (the kernels execute ~820 FP64 instructions per interface where the reference's count_ops has 2836)
+NCU_PIPE_FP64_BUSY_512 = {'z': 0.634, 'x': 0.642, 'y': 0.599}
 LS3 = dict(rk='ls', rk_a=[0.0, -5.0 / 9.0, -153.0 / 128.0], rk_b=[1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0])
 
 
@@ -417,7 +420,7 @@ def main():
         roofline = {'bound': 'hbm', 'kernel': 'k_central3d_fused (constituent relations + Central(4) convective + viscous terms + RK stage update)',
                     'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
                     'traffic': NCU_DRAM_BYTES_PER_CENTRAL_LAUNCH_512 if (world == 1 and args.size == 512) else None,
-                    'traffic_source': 'profiles/r01_final_ncu_central_fused_512.md (bytes per launch, ncu --set full)',
+                    'traffic_source': 'profiles/r02_final_ncu_central_fused_512.md (bytes per launch, ncu --set full)',
                     'launch_ms': launch_ms, 'share_of_step': (ce['ms'] + prof['viscous']['ms'] + prof['prim']['ms']) / tot if tot else None,
                     'bytes_model': 'algorithmic 160 B per point per stage: q read once, q and RK register written once, RK register read once',
                     'families_ms': {k: v['ms'] for k, v in prof.items()},
@@ -428,10 +431,13 @@ def main():
         pts_local = float(np.prod(lplan['np']))
         ach = ALG_FLOP_PER_POINT_FLUX_SWEEP * pts_local / (per_launch_ms * 1e-3) / 1e12
         tot = sum(v['ms'] for v in prof.values())
-        roofline = {'bound': 'fp64', 'kernel': 'k_flux_{x,yz} (TENO5 characteristic flux sweep + flux difference)',
+        roofline = {'bound': 'fp64', 'kernel': 'k_flux3_x / k_flux3_march<y|z> (TENO5 characteristic flux sweep + flux difference)',
                     'achieved': ach, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': ach / fp64_peak if fp64_peak else None,
                     'traffic': NCU_DRAM_BYTES_PER_FLUX_LAUNCH_512 if (world == 1 and args.size == 512) else None,
-                    'traffic_source': 'profiles/r01_final2_ncu_top_kernels_512.md (bytes per launch, ncu --set full)', 'launch_ms': per_launch_ms, 'share_of_step': fl['ms'] / tot if tot else None,
+                    'traffic_source': 'profiles/r02_final_ncu_top_kernels_512.md (bytes per launch, ncu --set full)', 'launch_ms': per_launch_ms,
+                    'pipe_fp64_busy': NCU_PIPE_FP64_BUSY_512 if (world == 1 and args.size == 512 and args.state == 'smooth') else None,
+                    'pipe_fp64_busy_source': 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active, profiles/r02_final_ncu_top_kernels_512.md',
+                    'frac_note': 'frac uses the ALGORITHMIC operation count of the reference (SURVEY 8d); it exceeds 1 because the kernels need ~3.4x fewer FP64 instructions than that count -- pipe_fp64_busy is the hardware-side fraction', 'share_of_step': fl['ms'] / tot if tot else None,
                     'peak_source': 'measured in this run: DFMA micro-benchmark osb_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)',
                     'flop_model': "reference's own count_ops: 2836 per point per LLFTeno_reconstruction loop + 50/3 Residual",
                     'families_ms': {k: v['ms'] for k, v in prof.items()}}
