@@ -61,6 +61,9 @@ int osb_upload_face(osb_ctx *ctx, int dir, int side, const double *table);
  *   per iteration: BCs ; [save] ; per stage: constituent relations, spatial kernels, RK update, BCs.
  * osb_step enqueues nsteps iterations on the context's stream and returns without synchronising. */
 int osb_step(osb_ctx *ctx, int nsteps);
+/* osb_sync also surfaces a neighbour time-out of a decomposed run: a device-side wait gives up after ~10 s, later waits
+ * return at once, and the kernels already enqueued keep stepping on halos that were not refreshed -- the state is invalid from
+ * the reported exchange epoch on. */
 int osb_sync(osb_ctx *ctx);
 /* Pieces of the loop, for parity tests: boundary conditions on q; residual of the current q
  * (constituent relations + all spatial kernels) left in Residual0.. */
