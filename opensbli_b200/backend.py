@@ -343,7 +343,7 @@ def _check_curvilinear_residual(recon, resid, ndim):
                 raise UnsupportedByB200('curvilinear residual equation of Residual%d is not -(dF/dxi)/detJ' % eq)
 
 
-KNOWN_CONSTANTS = re.compile(r'^(gama|gamma_m1|Minf|Re|Pr|mu|dt|eps|TENO_CT|teno_a1|teno_a2|epsilon|SuthT|RefT|Twall|niter|c[0-2]|'
+KNOWN_CONSTANTS = re.compile(r'^(gama|gamma_m1|Minf|Re|Pr|mu|dt|eps|TENO_CT|teno_a1|teno_a2|epsilon|SuthT|RefT|Twall|back_pressure|niter|c[0-2]|'
                              r'block0np\d|Delta\dblock0|inv_\d+|rc\d+|rcinv\d+|inv_rfact\d*_block0)$')
 
 
@@ -1001,7 +1001,16 @@ def extract_plan(algorithm):
         elif kind == 'InletPressureExtrapolate':
             entry = {'type': 'inlet_pressure_extrapolate'}
         elif kind == 'Symmetry':
-            entry = {'type': 'symmetry'}
+            # SymmetryBC (symmetry.py:23-50) and InviscidWallBC (inviscid_wall.py:24-52) both name their kernel 'Symmetry'; the
+            # inviscid wall additionally assigns the boundary point itself (state one point inside, normal momentum removed)
+            writes_boundary = any(hasattr(e.lhs, 'indices') and int(e.lhs.indices[d]) == 0 for e in c.equations if hasattr(e, 'lhs'))
+            if writes_boundary and (plan.get('curvilinear') or any(plan.get('metric_fields') or [])):
+                raise UnsupportedByB200('inviscid wall on a stretched / curvilinear block (metric-dependent normal) is not implemented')
+            entry = {'type': 'inviscid_wall' if writes_boundary else 'symmetry'}
+        elif kind == 'ZeroGradientOutlet':
+            entry = {'type': 'zero_gradient_outlet'}
+        elif kind == 'PressureOutlet':
+            entry = {'type': 'pressure_outlet'}
         elif kind == 'AdiabaticWall':
             if not _check_adiabatic_wall(c, d, sd, ndim):
                 raise UnsupportedByB200('adiabatic wall with a non-canonical wall-energy equation is not implemented')

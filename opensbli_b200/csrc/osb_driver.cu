@@ -27,7 +27,8 @@ thread_local std::string g_create_error;
 enum ConvKind { CONV_CENTRAL = 0, CONV_WENO = 1, CONV_TENO = 2 };
 enum RkKind { RK_SBLI = 0, RK_LS = 1 };
 enum BcKind { BC_PERIODIC = 0, BC_DIRICHLET = 1, BC_EXCHANGE = 2 /* neighbour rank owns the halo */, BC_ISOTHERMAL_WALL = 3,
-              BC_EXTRAPOLATION = 4, BC_INLET_PRESSURE = 5, BC_SYMMETRY = 6, BC_DIRICHLET_FIELD = 7, BC_ADIABATIC_WALL = 8 };
+              BC_EXTRAPOLATION = 4, BC_INLET_PRESSURE = 5, BC_SYMMETRY = 6, BC_DIRICHLET_FIELD = 7, BC_ADIABATIC_WALL = 8,
+              BC_ZERO_GRADIENT = 9, BC_PRESSURE_OUTLET = 10, BC_INVISCID_WALL = 11 };
 
 struct BcSpec {
   int kind = BC_PERIODIC;
@@ -169,6 +170,9 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
       else if (kind == "extrapolation") { b.kind = BC_EXTRAPOLATION; ls >> b.order; }
       else if (kind == "inlet_pressure_extrapolate") { b.kind = BC_INLET_PRESSURE; if (s != 0) { err = "inlet_pressure_extrapolate is defined for side 0 only"; return false; } }
       else if (kind == "symmetry") b.kind = BC_SYMMETRY;
+      else if (kind == "zero_gradient_outlet") b.kind = BC_ZERO_GRADIENT;
+      else if (kind == "inviscid_wall") b.kind = BC_INVISCID_WALL;
+      else if (kind == "pressure_outlet") { b.kind = BC_PRESSURE_OUTLET; if (s != 1) { err = "pressure_outlet is defined for side 1 only"; return false; } }
       else { err = "unsupported boundary condition '" + kind + "'"; return false; }
       std::string tok;
       while (ls >> tok) {
@@ -216,8 +220,10 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
   }
   if (P.forcing && !P.viscous) { err = "body forcing is implemented together with the viscous terms only"; return false; }
   if (P.visc_law == 1) for (const char *k : {"SuthT", "RefT"}) if (!P.consts.count(k)) { err = std::string("missing constant ") + k; return false; }
-  for (int d = 0; d < P.nd; d++) for (int s = 0; s < 2; s++)
+  for (int d = 0; d < P.nd; d++) for (int s = 0; s < 2; s++) {
     if (P.bc[d][s].kind == BC_ISOTHERMAL_WALL && !P.consts.count("Twall")) { err = "missing constant Twall"; return false; }
+    if (P.bc[d][s].kind == BC_PRESSURE_OUTLET && !P.consts.count("back_pressure")) { err = "missing constant back_pressure"; return false; }
+  }
   return true;
 }
 
@@ -557,6 +563,15 @@ void launch_bcs(osb_ctx *c) {
           case BC_DIRICHLET_FIELD: k_bc_dirichlet_field<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps, c->face_table[d][s], c->face_size[d], b.free_mask); break;
           case BC_EXTRAPOLATION: k_bc_extrapolation<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps, b.order); break;
           case BC_SYMMETRY: k_bc_symmetry<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps); break;
+          case BC_ZERO_GRADIENT: k_bc_zero_gradient<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps); break;
+          case BC_INVISCID_WALL: k_bc_inviscid_wall<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps); break;
+          case BC_PRESSURE_OUTLET: {
+            const double bp = P.consts.at("back_pressure");
+            if (P.nd == 1) k_bc_pressure_outlet<1><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps, bp);
+            else if (P.nd == 2) k_bc_pressure_outlet<2><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps, bp);
+            else k_bc_pressure_outlet<3><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps, bp);
+            break;
+          }
           case BC_INLET_PRESSURE:
             if (P.nd == 1) k_bc_inlet_pressure<1><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
             else if (P.nd == 2) k_bc_inlet_pressure<2><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);

@@ -1527,6 +1527,52 @@ __global__ void __launch_bounds__(128) k_bc_symmetry(GridDev g, FieldPtrs f, int
     }
 }
 
+// zero_gradient_outlet.py:12-23: boundary point <- one point inside, halos mirror the interior
+__global__ void __launch_bounds__(128) k_bc_zero_gradient(GridDev g, FieldPtrs f, int nv, PlaneSpec ps) {
+  long long x, t;
+  if (!plane_point(g, ps, x, t)) return;
+  const long long out = (ps.side == 0 ? -1 : 1) * g.s[ps.dir], in = -out;
+  for (int m = 0; m < nv; m++) {
+    f.q[m][x] = f.q[m][x + in];
+    for (int h = 1; h <= ps.nh; h++) f.q[m][x + h * out] = f.q[m][x + h * in];
+  }
+}
+// pressure_outlet.py:33-52: rho, momentum of the point one inside -> boundary point and halos; energy from the back pressure
+template <int ND>
+__global__ void __launch_bounds__(128) k_bc_pressure_outlet(GridDev g, FieldPtrs f, PhysConst c, PlaneSpec ps, double back_pressure) {
+  long long x, t;
+  if (!plane_point(g, ps, x, t)) return;
+  const long long out = (ps.side == 0 ? -1 : 1) * g.s[ps.dir], xi = x - out;
+  const double rho = f.q[0][xi];
+  double m[ND], mm = 0.0;
+#pragma unroll
+  for (int d = 0; d < ND; d++) { m[d] = f.q[1 + d][xi]; mm += m[d] * m[d]; }
+  const double E = back_pressure / (c.gama - 1.0) + 0.5 * mm / rho;
+  for (int h = 0; h <= ps.nh; h++) {
+    const long long xo = x + h * out;
+    f.q[0][xo] = rho;
+#pragma unroll
+    for (int d = 0; d < ND; d++) f.q[1 + d][xo] = m[d];
+    f.q[ND + 1][xo] = E;
+  }
+}
+// inviscid_wall.py:24-52 (Cartesian normal): mirrored halos with the normal momentum reversed; boundary point <- one point
+// inside with the normal momentum removed
+__global__ void __launch_bounds__(128) k_bc_inviscid_wall(GridDev g, FieldPtrs f, int nv, PlaneSpec ps) {
+  long long x, t;
+  if (!plane_point(g, ps, x, t)) return;
+  const long long out = (ps.side == 0 ? -1 : 1) * g.s[ps.dir], in = -out;
+  for (int m = 0; m < nv; m++) {
+    const bool normal = m == 1 + ps.dir;
+    for (int h = 1; h <= ps.nh; h++) {
+      const double v = f.q[m][x + h * in];
+      f.q[m][x + h * out] = normal ? v - 2.0 * v : v;
+    }
+    const double v = f.q[m][x + in];
+    f.q[m][x] = normal ? v - 1.0 * v : v;
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // In-loop diagnostics: NaN check of a dataset (what ops_NaNcheck does, simulation_monitors.py:112-113,
 // helperfunctions.py:172-190) and volume sums for the Taylor-Green diagnostics (kinetic energy, enstrophy -- computed offline

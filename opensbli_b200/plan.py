@@ -21,6 +21,7 @@ JSON-able dict; `to_text` serialises it to the line format parsed by the C ABI (
                     | {'type': 'exchange'} (halo owned by the neighbouring rank of a slab decomposition)
                     | {'type': 'isothermal_wall'} | {'type': 'adiabatic_wall'} | {'type': 'extrapolation', 'order': 0|1} | {'type': 'symmetry'}
                     | {'type': 'inlet_pressure_extrapolate'} | {'type': 'dirichlet_field', 'table': ndarray [nv, tangential]}
+                    | {'type': 'zero_gradient_outlet'} | {'type': 'pressure_outlet'} (side 1; constant back_pressure) | {'type': 'inviscid_wall'}
                     every non-periodic face may carry 'closure': 'reduced_access' | 'carpenter' (one-sided derivative rows)
     viscosity       {'type': 'constant'} | {'type': 'sutherland'} | {'type': 'power', 'exponent': e}
                     (constant: an optional constant 'mu' scales 1/Re, e.g. viscous_shock_tube.py:14-16)
@@ -43,7 +44,7 @@ import json
 
 CONV = ('central', 'weno', 'teno')
 BC_TYPES = ('periodic', 'dirichlet', 'exchange', 'isothermal_wall', 'extrapolation', 'inlet_pressure_extrapolate', 'symmetry',
-            'dirichlet_field', 'adiabatic_wall')
+            'dirichlet_field', 'adiabatic_wall', 'zero_gradient_outlet', 'pressure_outlet', 'inviscid_wall')
 
 # one-sided derivative closures: rows idx = 0.. next to the face x weights of the boundary-absolute points 0..np-1
 # (reduced_access_scheme.py:36-43,76-83; Carpenter's first-derivative rows are taken from the scheme object by the back end)
@@ -83,6 +84,8 @@ def validate(plan):
                 raise PlanError("boundary condition '%s' is not implemented by the B200 back end" % b['type'])
             if b['type'] == 'dirichlet' and len(b.get('q', ())) != nd + 2:
                 raise PlanError('dirichlet bc needs %d conservative values' % (nd + 2))
+            if b['type'] == 'pressure_outlet' and (s != 1 or 'back_pressure' not in plan.get('constants', {})):
+                raise PlanError('pressure_outlet is defined for side 1 and needs the constant back_pressure (pressure_outlet.py:22-31)')
     c = plan.get('constants', {})
     need = ['gama', 'dt'] + (['Re', 'Pr', 'Minf'] if plan.get('viscous') else [])
     for k in need:

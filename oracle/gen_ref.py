@@ -37,6 +37,13 @@ CONFIGS = {
     'sod_wenoz5': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [
         ("'scheme\\':\\'Teno\\'", "'scheme\\':\\'Weno\\'"),
         ("LLFTeno(teno_order, averaging=Avg)", "LLFWeno(5, formulation='Z', averaging=Avg)")]),
+    # boundary classes no shipped app uses: the Sod app with a zero-gradient / a pressure outlet on the right,
+    # the inviscid shock reflection with its bottom wall as InviscidWallBC instead of SymmetryBC
+    'sod_zgo': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("boundaries += [DirichletBC(direction, 1, right_eqns)]", "boundaries += [ZeroGradientOutletBC(direction, 1)]")]),
+    'sod_pout': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("boundaries += [DirichletBC(direction, 1, right_eqns)]", "boundaries += [PressureOutletBC(direction, 1, 0.1)]")]),
+    'isr_invwall': (REF + '/apps/inviscid_shock_reflection/inviscid_shock.py', [("boundaries[direction][side] = SymmetryBC(direction, side)",
+                     "from opensbli.core.boundary_conditions.inviscid_wall import InviscidWallBC\nboundaries[direction][side] = InviscidWallBC(direction, side)")]),
+    'isr': (REF + '/apps/inviscid_shock_reflection/inviscid_shock.py', []),
     # config 2: shipped TGV app (central-4 + RK3)
     'tgv_central4': (REF + '/apps/taylor_green_vortex/taylor_green_vortex.py', []),
     # config 3/5: TGV TENO5 + StoreSome + RK-LS (our app script, reference front end + OPSC back end)

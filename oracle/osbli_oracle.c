@@ -213,6 +213,54 @@ static void bc_symmetry(const osbo_cfg *c, const grid_t *g, double *const *q, in
       }
   })
 }
+/* zero_gradient_outlet.py:12-23: the boundary point takes the value one point inside, the halos mirror the interior */
+static void bc_zero_gradient_outlet(const osbo_cfg *c, const grid_t *g, double *const *q, int dir, int side) {
+  int hm, hp; scheme_halos(c, &hm, &hp);
+  const int n = side == 0 ? hm : hp;
+  const long out = (side == 0 ? -1 : 1) * g->s[dir], in = -out;
+  PLANE_LOOP(c, g, dir, side, {
+    for (int m = 0; m < g->nv; m++) q[m][x] = q[m][x + in];
+    for (int h = 1; h <= n; h++)
+      for (int m = 0; m < g->nv; m++) q[m][x + h * out] = q[m][x + h * in];
+  })
+}
+/* pressure_outlet.py:33-52 (side 1 only): density and momentum one point inside are copied to the boundary point and the
+ * halos; the energy there is back_pressure/(gama-1) + 1/2 m.m/rho of that inner point */
+static void bc_pressure_outlet(const osbo_cfg *c, const grid_t *g, double *const *q, int dir, int side) {
+  int hm, hp; scheme_halos(c, &hm, &hp);
+  const int nd = g->ndim, n = side == 0 ? hm : hp;
+  const long out = (side == 0 ? -1 : 1) * g->s[dir], in = -out;
+  PLANE_LOOP(c, g, dir, side, {
+    for (int h = 0; h <= n; h++) {
+      const long xo = x + h * out, xi = x + in;
+      double mm = 0.0;
+      for (int d = 0; d < nd; d++) mm += q[1 + d][xi] * q[1 + d][xi];
+      const double rho = q[0][xi];
+      const double E = c->back_pressure / (c->gama - 1.0) + 0.5 * mm / rho;
+      q[0][xo] = rho;
+      for (int d = 0; d < nd; d++) q[1 + d][xo] = q[1 + d][xi];
+      q[nd + 1][xo] = E;
+    }
+  })
+}
+/* inviscid_wall.py:24-52 on a Cartesian block (unit normal e_dir): halos mirror the interior with the normal momentum reversed,
+ * the boundary point takes the state one point inside with the normal momentum removed */
+static void bc_inviscid_wall(const osbo_cfg *c, const grid_t *g, double *const *q, int dir, int side) {
+  int hm, hp; scheme_halos(c, &hm, &hp);
+  const int n = side == 0 ? hm : hp;
+  const long out = (side == 0 ? -1 : 1) * g->s[dir], in = -out;
+  PLANE_LOOP(c, g, dir, side, {
+    for (int h = 1; h <= n; h++)
+      for (int m = 0; m < g->nv; m++) {
+        const double v = q[m][x + h * in];
+        q[m][x + h * out] = (m == 1 + dir) ? v - 2.0 * v : v;
+      }
+    for (int m = 0; m < g->nv; m++) {
+      const double v = q[m][x + in];
+      q[m][x] = (m == 1 + dir) ? v - 1.0 * v : v;
+    }
+  })
+}
 /* order: dir0 side0, dir0 side1, dir1 side0 ...  (block.py:199-210, algorithm.py:440-442) */
 void osbo_apply_bcs(const osbo_cfg *c, double *const *q) {
   grid_t g; grid_init(c, &g);
@@ -227,6 +275,9 @@ void osbo_apply_bcs(const osbo_cfg *c, double *const *q) {
         case OSBO_BC_ISOTHERMAL_WALL: bc_isothermal_wall(c, &g, q, d, s); break;
         case OSBO_BC_SYMMETRY: bc_symmetry(c, &g, q, d, s); break;
         case OSBO_BC_ADIABATIC_WALL: bc_adiabatic_wall(c, &g, q, d, s); break;
+        case OSBO_BC_ZERO_GRADIENT_OUTLET: bc_zero_gradient_outlet(c, &g, q, d, s); break;
+        case OSBO_BC_PRESSURE_OUTLET: bc_pressure_outlet(c, &g, q, d, s); break;
+        case OSBO_BC_INVISCID_WALL: bc_inviscid_wall(c, &g, q, d, s); break;
         default: break;
       }
     }

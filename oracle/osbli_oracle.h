@@ -37,7 +37,7 @@ enum { OSBO_RK_SBLI = 0, OSBO_RK_LS = 1 };
 enum { OSBO_BC_PERIODIC = 0, OSBO_BC_DIRICHLET = 1, OSBO_BC_EXCHANGE = 2 /* halo filled by the caller (decomposed run) */,
        OSBO_BC_ISOTHERMAL_WALL = 3, OSBO_BC_EXTRAPOLATION = 4, OSBO_BC_INLET_PRESSURE_EXTRAPOLATE = 5,
        OSBO_BC_SYMMETRY = 6, OSBO_BC_DIRICHLET_FIELD = 7 /* imposed state varies along the face */,
-       OSBO_BC_ADIABATIC_WALL = 8 };
+       OSBO_BC_ADIABATIC_WALL = 8, OSBO_BC_ZERO_GRADIENT_OUTLET = 9, OSBO_BC_PRESSURE_OUTLET = 10, OSBO_BC_INVISCID_WALL = 11 };
 enum { OSBO_MU_CONSTANT = 0, OSBO_MU_SUTHERLAND = 1, OSBO_MU_POWER = 2 };
 
 typedef struct {
@@ -86,6 +86,7 @@ typedef struct {
    * or diagonal metrics.  Eigensystems then carry the direction cosines k~ = D_i. / |D_i.| (euler_eigensystem.py:18-54). */
   const double *curv_D[3][3];
   const double *curv_detJ;
+  double back_pressure;       /* OSBO_BC_PRESSURE_OUTLET: imposed outlet pressure (pressure_outlet.py:22-47) */
   int central_form;           /* Central(4) convective split: 0 Blaisdell skew form (taylor_green_vortex.py:8-11, laminar_channel.py:7-9),
                                * 1 Feiereisen quadratic split (compressible_TCF_Central/turbulent_channel.py:12-20) */
 } osbo_cfg;

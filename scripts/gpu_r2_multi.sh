@@ -3,7 +3,7 @@
 # then weak- and strong-scaling bench lines exactly as the driver launches them
 N=${1:-4}; T=${2:-r2m$N}
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_multi.py -m gpu -q --no-header -p no:cacheprovider > gpurun_out/${T}_tests.log 2>&1; echo "pytest exit $?" >> gpurun_out/${T}_tests.log
+[ -n "$SKIP_TESTS" ] || timeout 1500 python -m pytest tests/test_gpu_multi.py -m gpu -q --no-header -p no:cacheprovider > gpurun_out/${T}_tests.log 2>&1; echo "pytest exit $?" >> gpurun_out/${T}_tests.log
 tail -6 gpurun_out/${T}_tests.log
 run() { # name, extra args
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3 --no-cpu-baseline $2 > gpurun_out/${T}_$1.json 2> gpurun_out/${T}_$1.err

@@ -92,6 +92,29 @@ def katzer_dirichlet_table(N0, halo=5):
 FIXTURES['katzer_60x40'] = ('katzer', katzer_plan(60, 40), [1, 10])
 
 
+def sod_outlet_plan(N, kind):
+    """Sod app with its right boundary replaced by ZeroGradientOutletBC / PressureOutletBC(back_pressure=0.1) (boundary classes
+    no shipped app uses: zero_gradient_outlet.py:12-23, pressure_outlet.py:33-52)."""
+    p = sod_plan(N, 'teno', 5)
+    p['bc'][0][1] = dict(type=kind)
+    if kind == 'pressure_outlet':
+        p['constants']['back_pressure'] = 0.1
+    return p
+
+
+def isr_plan(N0, N1, wall):
+    """apps/inviscid_shock_reflection/inviscid_shock.py: 2-D Euler, WENO5-Z with simple averaging, RungeKuttaLS(3); constant
+    Dirichlet inflow, order-0 extrapolation outflow, shock-generator Dirichlet state along the top (tabulated: main() reads both
+    imposed states off the reference's own dumps), bottom wall = SymmetryBC (shipped) or InviscidWallBC (inviscid_wall.py:24-52)."""
+    return dict(ndim=2, np=[N0, N1], delta=[350.0 / (N0 - 1), 115.0 / (N1 - 1)], conv='weno', order=5, weno_formulation='Z',
+                averaging='simple', viscous=False, constants=dict(gama=1.4, Minf=2.0, dt=0.1),
+                bc=[[dict(type='dirichlet', q=None), dict(type='extrapolation', order=0)], [dict(type=wall), dict(type='dirichlet_field')]], **LS3)
+
+
+FIXTURES['sod_zgo_n200'] = ('sod_zgo', sod_outlet_plan(200, 'zero_gradient_outlet'), [1, 50])
+FIXTURES['sod_pout_n200'] = ('sod_pout', sod_outlet_plan(200, 'pressure_outlet'), [1, 50])
+
+
 def katzer_wenoz_plan(N0, N1):
     """BASELINE.json configs[3] as worded: the Katzer app with LLFWeno(5, formulation='Z') in place of adaptive TENO."""
     p = katzer_plan(N0, N1)
@@ -227,6 +250,8 @@ STATS = ['rhomean', 'E_mean', 'u0mean', 'u1u0mean', 'u2u2mean', 'p_mean', 'pp_me
 if os.path.isdir('/root/reference'):
     # the channel app as shipped (statistics on): the running sums after 5 steps, divided by niter by the loop after the time loop
     FIXTURES['tcf_teno6_stats_16x24x12'] = ('tcf_teno6_stats', tcf_teno6_plan(16, 24, 12), [5])
+    FIXTURES['isr_invwall_48x32'] = ('isr_invwall', isr_plan(48, 32, 'inviscid_wall'), [1, 20])
+    FIXTURES['isr_48x32'] = ('isr', isr_plan(48, 32, 'symmetry'), [1, 20])
     FIXTURES['ewc_wenoz5_32'] = ('ewc', ewc_plan(32), [1, 10])
     FIXTURES['ewc_teno5_32'] = ('ewc_teno5', ewc_plan(32, 'teno'), [1, 10])
     FIXTURES['trans_40x30x8'] = ('trans', trans_plan(40, 30, 8), [1, 5, 20])
@@ -254,8 +279,17 @@ def main():
         nd = plan['ndim']
         fields = ['rho'] + ['rhou%d' % d for d in range(nd)] + ['rhoE']
         inner = (slice(5, -5),) * nd
+        bc_tables = {}
+        if config.startswith('isr'):
+            # imposed states read off the reference's own dumps: the uniform initial state is the inflow state; the top row
+            # after one step holds the shock-generator state along x (boundary plane j = np1 - 1, tangential range incl. halos)
+            r0 = run_ref(config, dict(env_params(plan), niter=0), fields)
+            plan['bc'][0][0]['q'] = [float(r0[f][5 + 3, 5 + 3]) for f in fields]
+            r1 = run_ref(config, dict(env_params(plan), niter=1), fields)
+            bc_tables['bc_table_1_1'] = np.stack([r1[f][5 + plan['np'][1] - 1, :] for f in fields])
         out = {'plan': np.array(json.dumps(plan, sort_keys=True)),
                'provenance': np.array(open(os.path.join(REF_DIR, config, 'provenance.json')).read())}
+        out.update(bc_tables)
         extra = []
         if 'metric_fields' in plan:
             extra = [n for d, name in enumerate(plan['metric_fields']) if name for n in ('D%d%d' % (d, d), 'SD%d%d%d' % (d, d, d))]

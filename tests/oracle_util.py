@@ -12,7 +12,8 @@ REF_DIR = os.path.join(ORACLE_DIR, '_ref')
 
 CONV = {'central': 0, 'weno': 1, 'teno': 2}
 BC = {'periodic': 0, 'dirichlet': 1, 'exchange': 2, 'isothermal_wall': 3, 'extrapolation': 4,
-      'inlet_pressure_extrapolate': 5, 'symmetry': 6, 'dirichlet_field': 7, 'adiabatic_wall': 8}
+      'inlet_pressure_extrapolate': 5, 'symmetry': 6, 'dirichlet_field': 7, 'adiabatic_wall': 8,
+      'zero_gradient_outlet': 9, 'pressure_outlet': 10, 'inviscid_wall': 11}
 MU = {'constant': 0, 'sutherland': 1, 'power': 2}
 CLOSURES = {
     # rows idx = 0.. next to the face x weights of the boundary-absolute points 0..np-1
@@ -43,7 +44,7 @@ class OsboCfg(ctypes.Structure):
                 ('extrap_order', (ctypes.c_int * 2) * 3), ('bc_face', (ctypes.POINTER(ctypes.c_double) * 2) * 3),
                 ('force', ctypes.c_double * 3), ('bc_free', (ctypes.c_int * 2) * 3), ('src_amp', ctypes.POINTER(ctypes.c_double)), ('src_rate', ctypes.c_double),
                 ('src_iter0', ctypes.c_int), ('curv_D', (ctypes.POINTER(ctypes.c_double) * 3) * 3),
-                ('curv_detJ', ctypes.POINTER(ctypes.c_double)), ('central_form', ctypes.c_int)]
+                ('curv_detJ', ctypes.POINTER(ctypes.c_double)), ('back_pressure', ctypes.c_double), ('central_form', ctypes.c_int)]
 
 
 _lib = None
@@ -119,6 +120,7 @@ def make_cfg(plan):
     c.visc_law = MU[visc['type']]
     c.SuthT, c.RefT, c.mu_exp = k.get('SuthT', 0.0), k.get('RefT', 1.0), visc.get('exponent', 0.0)
     c.Twall = k.get('Twall', 1.0)
+    c.back_pressure = k.get('back_pressure', 0.0)
     c.central_form = {'blaisdell': 0, 'feiereisen': 1}[plan.get('central_form', 'blaisdell')]
     if plan.get('forcing'):
         for d in range(plan['ndim']):

@@ -36,6 +36,15 @@ APPS = {
     # 3-D channel in the Feiereisen split on a uniform grid, as shipped: statistics user kernels and a SimulationMonitor
     't3d': (REF + '/apps/channel_flow/turbulent_3D/turbulent_channel.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),
     'sod_teno5': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'sod_teno5_n200'),
+    # boundary classes no shipped app uses: Sod with a zero-gradient / pressure outlet, shock reflection with an InviscidWallBC
+    'sod_zgo': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("boundaries += [DirichletBC(direction, 1, right_eqns)]", "boundaries += [ZeroGradientOutletBC(direction, 1)]"),
+                                                                 ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'sod_zgo_n200'),
+    'sod_pout': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("boundaries += [DirichletBC(direction, 1, right_eqns)]", "boundaries += [PressureOutletBC(direction, 1, 0.1)]"),
+                                                                  ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'sod_pout_n200'),
+    'isr_invwall': (REF + '/apps/inviscid_shock_reflection/inviscid_shock.py',
+                    [("boundaries[direction][side] = SymmetryBC(direction, side)",
+                      "from opensbli.core.boundary_conditions.inviscid_wall import InviscidWallBC\nboundaries[direction][side] = InviscidWallBC(direction, side)"),
+                     ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),
     # BASELINE configs[3] as worded: the Katzer app with WENO-Z instead of adaptive TENO (same edits as oracle/gen_ref.py)
     'katzer_wenoz': (REF + '/apps/katzer_SBLI/katzer_SBLI.py',
                      [("sc1 = \"**{\\'scheme\\':\\'Teno\\'}\"", "sc1 = \"**{\\'scheme\\':\\'Weno\\'}\""), ("constituent.add_equations(shock_sensor)", "pass"),
@@ -115,7 +124,10 @@ def test_b200_backend_distils_expected_plan(name, app_runs):
         if not os.path.exists(os.path.join(workdir, 'opensbli.cpp')):
             pytest.skip('no committed plan fixture for %s' % name)
     if APPS[name][2] is None:          # no golden run of this app: the plan fixture is refreshed, dedicated tests below read it
-        assert json.load(open(os.path.join(workdir, 'opensbli_b200.plan.json')))['ndim'] in (1, 2, 3)
+        sym = json.load(open(os.path.join(workdir, 'opensbli_b200.plan.json')))
+        assert sym['ndim'] in (1, 2, 3)
+        if name == 'isr_invwall':      # kernel named 'Symmetry' by the reference, recognised by what it assigns
+            assert sym['bc'][1][0]['type'] == 'inviscid_wall' and sym['bc'][0][1] == {'type': 'extrapolation', 'order': 0}
         return
     plan_sym, env, plan_num, _cold = R.load_case(workdir)
     want, _ = load_fixture(APPS[name][2])

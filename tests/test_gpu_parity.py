@@ -66,7 +66,7 @@ def test_residual_matches_oracle(osb, name):
     assert max(err) < lim, err
 
 
-@pytest.mark.parametrize('name', [n for n in fixtures() if n.startswith(('katzer', 'vst', 'trans', 'tcf', 'lam2d', 'tgv_sym'))])
+@pytest.mark.parametrize('name', [n for n in fixtures() if n.startswith(('katzer', 'vst', 'trans', 'tcf', 'lam2d', 'tgv_sym', 'sod_zgo', 'sod_pout', 'isr'))])
 def test_boundary_conditions_on_perturbed_state(osb, name):
     """Wall / inflow / outflow / symmetry / (partial) Dirichlet kernels on a randomly perturbed state -- every branch of the
     formulas carries signal (e.g. the free spanwise momentum at the transitional-SBLI top boundary) -- vs the oracle."""

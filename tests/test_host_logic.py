@@ -48,7 +48,7 @@ def test_plan_roundtrip_and_validation():
     bad = dict(plan, order=7)
     with pytest.raises(P.PlanError):
         P.to_text(bad)
-    bad = dict(plan, bc=[[dict(type='pressure_outlet')] * 2] * 3)
+    bad = dict(plan, bc=[[dict(type='forcing_strip_wall')] * 2] * 3)
     with pytest.raises(P.PlanError, match='not implemented'):
         P.to_text(bad)
     p2 = P.with_size(plan, [32, 32, 32], delta=[0.1] * 3, dt=1e-3)
