@@ -266,14 +266,24 @@ __global__ void __launch_bounds__(F3_BT, OSB_F3_XBLOCKS) k_flux3_x(GridDev g, Fi
 #pragma unroll
     for (int m = 0; m < NV; m++) prefetch_l2(f.R[m] + x);
   }
+  double fl[NV];
+#pragma unroll
+  for (int m = 0; m < NV; m++) fl[m] = 0.0;
   if (iface) {
-    double fl[NV];
     if (ad.on) {                                 // sensor value of the interface's left point (0 in the halos)
       const int e = adaptive_exponent(ad, gp.theta[x]);
       sp.teno_ct = ad.ct[e]; sp.kfast5 = ad.k5[e]; sp.kpass5 = ad.k5[e] - 1.0; sp.kfast6 = ad.k6[e];
       if (gp.teno_store) gp.teno_store[x] = sp.teno_ct;
     }
     interface_flux_split<ND, 0, RECON, AVG>(sP + t - 2, WinAffine{1}, F3_BT, sG + t, F3_BT, c.gama, sp, fl);
+  }
+  // flux difference along x, the fastest axis: the flux of the lower interface comes from the neighbouring lane by a warp
+  // shuffle; only the last lane of a warp parks its flux in shared memory for the first lane of the next warp
+  const int lane = t & 31;
+  double lower[NV];
+#pragma unroll
+  for (int m = 0; m < NV; m++) lower[m] = __shfl_up_sync(0xffffffffu, fl[m], 1);
+  if (lane == 31) {
 #pragma unroll
     for (int m = 0; m < NV; m++) sG[m * F3_BT + t] = fl[m];
   }
@@ -287,7 +297,8 @@ __global__ void __launch_bounds__(F3_BT, OSB_F3_XBLOCKS) k_flux3_x(GridDev g, Fi
     }
 #pragma unroll
     for (int m = 0; m < NV; m++) {
-      const double r = met * (sG[m * F3_BT + t] - sG[m * F3_BT + t - 1]);
+      const double lo = lane == 0 ? sG[m * F3_BT + t - 1] : lower[m];
+      const double r = met * (fl[m] - lo);
       f.R[m][x] = ACCUM ? old[m] + r : r;
     }
   }
