@@ -21,6 +21,7 @@ It writes, in the current directory (like OPSC writes opensbli.cpp & co, opsc.py
 Anything outside the recognised path raises NotImplementedError naming the offending loop -- there is no silent fallback.
 """
 import json
+import os
 import re
 
 import numpy as np
@@ -98,49 +99,76 @@ class _Printer(object):
         return self.p.doprint(expr)
 
 
-def _user_kernel(kernel, when):
-    """A point-wise user kernel (statistics accumulation, e.g. channel_flow/*/stats.py; `User kernel` in the algorithm): an
-    ordered list of assignments [lhs, is_dataset, rhs in C] over the kernel's range.  It is compiled at run time (NVRTC) --
-    app-specific arithmetic outside the solver's hot loops cannot be hand-written.  Only accesses at the point itself."""
+def _user_kernel(kernel, when, stencil=False):
+    """A user kernel compiled at run time (NVRTC): an ordered list of assignments [lhs, is_dataset, rhs in C, lhs index] over
+    the kernel's range -- app-specific arithmetic outside the solver's hot loops cannot be hand-written.
+    stencil=False: point-wise kernels (statistics accumulation, e.g. channel_flow/*/stats.py; `User kernel` in the algorithm).
+    stencil=True: datasets may be read and written at relative offsets (boundary-condition kernels of classes without a
+    hand-written kernel, `when` = 'bc_<dir>_<side>'); every point of the range runs in its own thread, so the kernel must not
+    write where another point of the range reads or writes -- checked here from the offsets and the range's unit extents."""
     from sympy.printing.c import C99CodePrinter, ccode
     from opensbli.core.opensbliobjects import DataSet
 
+    def index(e):
+        off = [int(i) for i in e.indices]
+        if any(off) and not stencil:
+            raise UnsupportedByB200('user kernel %s accesses %s at an offset: only point-wise user kernels are implemented' % (_name(kernel), e))
+        terms = ['X'] + ['(%d)%s' % (o, ('', '*s1', '*s2')[d]) for d, o in enumerate(off) if o]
+        return ' + '.join(terms), tuple(off + [0] * (3 - len(off)))
+
     class P(C99CodePrinter):
         def _print_DataSet(s, e):
-            if any(int(i) != 0 for i in e.indices):
-                raise UnsupportedByB200('user kernel %s reads %s at an offset: only point-wise user kernels are implemented' % (_name(kernel), e))
-            return '%s[X]' % _strip(e.base)
+            return '%s[%s]' % (_strip(e.base), index(e)[0])
 
         def _print_Indexed(s, e):
             if type(e).__name__ == 'DataSet':
                 return s._print_DataSet(e)
+            if type(e).__name__ == 'Grididx':
+                return 'idx%d' % int(e.indices[0])
             return C99CodePrinter._print_Indexed(s, e)
+
+        def _print_Grididx(s, e):
+            return 'idx%d' % int(e.indices[0])
 
         def _print_Rational(s, e):
             return '(%d.0/%d.0)' % (e.p, e.q)
 
     pr = P({'precision': 17})
     out, reads, writes, local = [], [], [], []
+    roff, woff = {}, {}
     for e in kernel.equations:
         if not hasattr(e, 'lhs'):
             raise UnsupportedByB200('user kernel %s: unsupported equation %r' % (_name(kernel), e))
         for ds in e.rhs.atoms(DataSet):
             n = _strip(ds.base)
+            roff.setdefault(n, set()).add(index(ds)[1])
             if n not in reads:
                 reads.append(n)
         if type(e.lhs).__name__ == 'DataSet':
-            if any(int(i) != 0 for i in e.lhs.indices):
-                raise UnsupportedByB200('user kernel %s writes at an offset' % _name(kernel))
             n = _strip(e.lhs.base)
+            idx, off = index(e.lhs)
+            woff.setdefault(n, set()).add(off)
             if n not in writes:
                 writes.append(n)
-            out.append([n, True, pr.doprint(e.rhs)])
+            out.append([n, True, pr.doprint(e.rhs), idx])
         else:
             local.append(str(e.lhs))
-            out.append([str(e.lhs), False, pr.doprint(e.rhs)])
+            out.append([str(e.lhs), False, pr.doprint(e.rhs), None])
+    rng = kernel.total_range()
+    if stencil:
+        # two different points p, p' of the range touch the same element iff p - p' = (read or write offset) - (write offset);
+        # that is impossible when the difference is non-zero along a direction in which the range is one point thick
+        thin = [str(rng[2 * d + 1] - rng[2 * d]) == '1' for d in range(len(rng) // 2)] + [True] * 3
+        for n, ws in woff.items():
+            for w in ws:
+                for o in ws | roff.get(n, set()):
+                    diff = [a - b for a, b in zip(o, w)]
+                    if any(diff) and not any(diff[d] and thin[d] for d in range(3)):
+                        raise UnsupportedByB200('kernel %s writes %s where a neighbouring point of its range reads or writes it (offsets %s / %s): '
+                                                'it cannot run one thread per point' % (_name(kernel), n, w, o))
     consts = sorted(set(str(s) for e in kernel.equations for s in e.rhs.free_symbols
                         if type(s).__name__ == 'ConstantObject'))
-    return {'name': _name(kernel), 'when': when, 'range': [ccode(r) for r in kernel.total_range()], 'reads': reads,
+    return {'name': _name(kernel), 'when': when, 'range': [ccode(r) for r in rng], 'reads': reads,
             'writes': writes, 'locals': local, 'constants': consts, 'statements': out}
 
 
@@ -342,6 +370,11 @@ def _check_curvilinear_residual(recon, resid, ndim):
             if abs(got - want) > 1e-11 * max(1.0, abs(want)):
                 raise UnsupportedByB200('curvilinear residual equation of Residual%d is not -(dF/dxi)/detJ' % eq)
 
+
+# boundary classes routed through the run-time compiled path although a hand-written kernel exists (tests of that path)
+GENERIC_BCS = set(k for k in os.environ.get('OSB_GENERIC_BC', '').split(',') if k)
+
+NATIVE_BCS = ('Dirichlet', 'Extrapolation', 'InletPressureExtrapolate', 'Symmetry', 'AdiabaticWall', 'IsothermalWall', 'ZeroGradientOutlet', 'PressureOutlet')
 
 KNOWN_CONSTANTS = re.compile(r'^(gama|gamma_m1|Minf|Re|Pr|mu|dt|eps|TENO_CT|teno_a1|teno_a2|epsilon|SuthT|RefT|Twall|back_pressure|niter|c[0-2]|'
                              r'block0np\d|Delta\dblock0|inv_\d+|rc\d+|rcinv\d+|inv_rfact\d*_block0)$')
@@ -920,7 +953,10 @@ def extract_plan(algorithm):
     mass_source, source_cold, source_kernel = _mass_source(cr, [c for c in in_stage if type(c).__name__ == 'Kernel' and c not in cr], ndim)
     if source_kernel is not None:
         cr.remove(source_kernel)
-    _check_constants_used([c for c in in_stage + in_iter if c is not source_kernel])
+    def _generic_bc(c):           # boundary kernels that will be compiled at run time carry their own constants
+        m = re.match(r'(\w+) boundary dir(\d) side(\d)', _name(c) or '')
+        return bool(m) and (m.group(1) not in NATIVE_BCS or m.group(1) in GENERIC_BCS)
+    _check_constants_used([c for c in in_stage + in_iter if c is not source_kernel and not _generic_bc(c)])
     crinfo = _check_constituent(cr, ndim)
     plan['viscosity'] = crinfo['viscosity']
     if recon and central_conv:
@@ -990,7 +1026,9 @@ def extract_plan(algorithm):
         m = re.match(r'(\w+) boundary dir(\d) side(\d)', _name(c))
         kind, d, sd = m.group(1), int(m.group(2)), int(m.group(3))
         entry = None
-        if kind == 'Dirichlet':
+        if kind in GENERIC_BCS:
+            pass
+        elif kind == 'Dirichlet':
             # imposed state = whatever the BC equations evaluate to on the face (constants or functions of the position)
             entry = {'type': 'dirichlet_field', 'kernel': _cold_kernel(c)}
             entry.update(_dirichlet_free(c, ndim, q_names))
@@ -1022,8 +1060,12 @@ def extract_plan(algorithm):
             if not walls or not _lambdify_check(walls[0], canon, None):
                 raise UnsupportedByB200('isothermal wall with a non-canonical wall-energy equation is not implemented')
             entry = {'type': 'isothermal_wall'}
-        else:
-            raise UnsupportedByB200("boundary condition '%s' is not implemented yet" % kind)
+        if entry is None or kind in GENERIC_BCS:
+            # no hand-written kernel for this boundary class (ForcingStripWall, InletLawal, InletTransfer, InviscidWall2D, ...
+            # or forced through OSB_GENERIC_BC for testing): its equations are printed as CUDA C and compiled at run time --
+            # boundary kernels touch a plane of points per application, nothing to gain from hand-writing them
+            entry = {'type': 'generic', 'class': kind}
+            user.append(_user_kernel(c, 'bc_%d_%d' % (d, sd), stencil=True))
         if (d, sd) in faces:
             entry['closure'] = closure_name
         bc[d][sd] = entry

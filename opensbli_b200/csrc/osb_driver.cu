@@ -28,7 +28,8 @@ enum ConvKind { CONV_CENTRAL = 0, CONV_WENO = 1, CONV_TENO = 2 };
 enum RkKind { RK_SBLI = 0, RK_LS = 1 };
 enum BcKind { BC_PERIODIC = 0, BC_DIRICHLET = 1, BC_EXCHANGE = 2 /* neighbour rank owns the halo */, BC_ISOTHERMAL_WALL = 3,
               BC_EXTRAPOLATION = 4, BC_INLET_PRESSURE = 5, BC_SYMMETRY = 6, BC_DIRICHLET_FIELD = 7, BC_ADIABATIC_WALL = 8,
-              BC_ZERO_GRADIENT = 9, BC_PRESSURE_OUTLET = 10, BC_INVISCID_WALL = 11 };
+              BC_ZERO_GRADIENT = 9, BC_PRESSURE_OUTLET = 10, BC_INVISCID_WALL = 11,
+              BC_GENERIC = 12 /* run-time compiled kernel registered with when = 100 + 2 dir + side */ };
 
 struct BcSpec {
   int kind = BC_PERIODIC;
@@ -171,6 +172,7 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
       else if (kind == "inlet_pressure_extrapolate") { b.kind = BC_INLET_PRESSURE; if (s != 0) { err = "inlet_pressure_extrapolate is defined for side 0 only"; return false; } }
       else if (kind == "symmetry") b.kind = BC_SYMMETRY;
       else if (kind == "zero_gradient_outlet") b.kind = BC_ZERO_GRADIENT;
+      else if (kind == "generic") b.kind = BC_GENERIC;
       else if (kind == "inviscid_wall") b.kind = BC_INVISCID_WALL;
       else if (kind == "pressure_outlet") { b.kind = BC_PRESSURE_OUTLET; if (s != 1) { err = "pressure_outlet is defined for side 1 only"; return false; } }
       else { err = "unsupported boundary condition '" + kind + "'"; return false; }
@@ -521,7 +523,9 @@ void box_launch_cfg(const Box &b, int nv, unsigned &blocks) {
   blocks = (unsigned)nb;
 }
 
-void launch_bcs(osb_ctx *c) {
+int run_user_kernels(osb_ctx *c, int when);
+
+int launch_bcs(osb_ctx *c) {
   const Plan &P = c->plan;
   const GridDev &g = c->grid;
   const int nv = P.nd + 2;
@@ -530,6 +534,13 @@ void launch_bcs(osb_ctx *c) {
     for (int s = 0; s < 2; s++) {
       const BcSpec &b = P.bc[d][s];
       if (b.kind == BC_EXCHANGE) continue;   // filled by the neighbour rank (osb_halo_push)
+      if (b.kind == BC_GENERIC) {            // boundary class without a hand-written kernel: its run-time compiled kernel
+        bool found = false;
+        for (auto &k : c->user_kernels) found = found || k.when == 100 + 2 * d + s;
+        if (!found) return fail(c, "face (" + std::to_string(d) + ", " + std::to_string(s) + ") has a 'generic' boundary condition but no kernel was registered for it");
+        if (run_user_kernels(c, 100 + 2 * d + s)) return 1;
+        continue;
+      }
       Box full;
       for (int e = 0; e < 3; e++) { full.lo[e] = e < P.nd ? -hm : 0; full.n[e] = e < P.nd ? g.np[e] + hm + hp : 1; }
       unsigned blocks;
@@ -591,6 +602,7 @@ void launch_bcs(osb_ctx *c) {
         }
       }
     }
+  return 0;
 }
 
 template <int ND>
@@ -703,12 +715,12 @@ int stage_nd(osb_ctx *c, int s) {
     if (s >= 0) {
       launch_central_fused(c, s);                       // the kernel also stores the boundary planes into the neighbours' buffers
       if (ex) { neighbour_signal(c, 1); neighbour_wait(c, 1); }
-      launch_bcs(c);
+      if (launch_bcs(c)) return 1;
     } else {
       // planes first, rank-local BCs after the neighbours' planes have landed: the BC kernels also rewrite the x/y-halo
       // parts of the received planes, which must neither race with nor precede the neighbour's stores
       if (ex) { if (push_planes_memcpy(c)) return 1; neighbour_signal(c, 1); neighbour_wait(c, 1); }
-      launch_bcs(c);
+      if (launch_bcs(c)) return 1;
     }
     if (s == (int)c->plan.rk_a.size() - 1 && run_user_kernels(c, 0)) return 1;
     OSB_CUDA(c, cudaGetLastError());
@@ -716,7 +728,7 @@ int stage_nd(osb_ctx *c, int s) {
   }
   if (s < 0) {
     if (ex) { if (push_planes_memcpy(c)) return 1; neighbour_signal(c, 1); neighbour_wait(c, 1); }
-    launch_bcs(c);
+    if (launch_bcs(c)) return 1;
     if (c->plan.rk == RK_SBLI) launch_save<ND>(c);
   } else {
     launch_phase_a<ND>(c, s);     // sends the "read done" notification as soon as the halo-reading kernels are enqueued
@@ -725,10 +737,10 @@ int stage_nd(osb_ctx *c, int s) {
     if (!fused) launch_rk<ND>(c, s);
     if (ex && fused == 2 && fused_push_enabled()) {            // planes were pushed by the kernel: interior part; the receiver's own BCs complete the halos
       neighbour_signal(c, 1); neighbour_wait(c, 1);
-      launch_bcs(c);
+      if (launch_bcs(c)) return 1;
     } else {
       if (ex) { if (push_planes_memcpy(c)) return 1; neighbour_signal(c, 1); neighbour_wait(c, 1); }
-      launch_bcs(c);
+      if (launch_bcs(c)) return 1;
     }
   }
   if (s == (int)c->plan.rk_a.size() - 1 && run_user_kernels(c, 0)) return 1;
@@ -1129,7 +1141,7 @@ int osb_sync(osb_ctx *c) {
 int osb_apply_bcs(osb_ctx *c) {
   if (!c) return 1;
   cudaSetDevice(c->device);
-  launch_bcs(c);
+  if (launch_bcs(c)) return 1;
   OSB_CUDA(c, cudaGetLastError());
   return 0;
 }

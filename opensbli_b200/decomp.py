@@ -83,13 +83,33 @@ def local_plan(plan, rank, world):
                 pd = [plan['np'][e] + 2 * h for e in range(nd) if e != d]          # tangential padded extents, x fastest
                 t = np.asarray(b['table']).reshape((-1,) + tuple(reversed(pd)))
                 p['bc'][d][s]['table'] = np.ascontiguousarray(t[:, k0:k0 + loc + 2 * h]).reshape(t.shape[0], -1)
-    # point-wise user kernels cover the rank's own slab
+    # point-wise user kernels cover the rank's own slab; run-time compiled boundary kernels ('bc_<dir>_<side>') follow their face
+    kept = []
+    n_ax = plan['np'][ax]
     for uk in p.get('user_kernels', []):
         r = list(uk['range']) + [0, 1] * (3 - nd)
-        if r[2 * ax] != 0 or r[2 * ax + 1] != plan['np'][ax]:
-            raise _plan.PlanError('user kernel %s does not cover the whole slab axis: cannot be decomposed' % uk.get('name'))
-        r[2 * ax + 1] = loc
+        if uk['when'].startswith('bc_'):
+            _, d, sd = uk['when'].split('_')
+            d, sd = int(d), int(sd)
+            if d == ax:
+                if p['bc'][ax][sd]['type'] == 'exchange':        # an interior cut: the neighbour's planes take the face's place
+                    continue
+                if sd == 1:
+                    r[2 * ax] += loc - n_ax
+                    r[2 * ax + 1] += loc - n_ax
+            else:                                                # tangential range [-halo, np + halo) -> [-halo, nloc + halo)
+                if r[2 * ax] > 0 or r[2 * ax + 1] < n_ax:
+                    raise _plan.PlanError('boundary kernel %s does not cover the whole slab axis: cannot be decomposed' % uk.get('name'))
+                r[2 * ax + 1] += loc - n_ax
+            uk['source'] = '#define OSB_GOFF%d %d\n' % (ax, k0) + uk['source']
+        else:
+            if r[2 * ax] != 0 or r[2 * ax + 1] != n_ax:
+                raise _plan.PlanError('user kernel %s does not cover the whole slab axis: cannot be decomposed' % uk.get('name'))
+            r[2 * ax + 1] = loc
         uk['range'] = r[:2 * nd]
+        kept.append(uk)
+    if 'user_kernels' in p:
+        p['user_kernels'] = kept
     return _plan.validate(p)
 
 

@@ -22,6 +22,7 @@ JSON-able dict; `to_text` serialises it to the line format parsed by the C ABI (
                     | {'type': 'isothermal_wall'} | {'type': 'adiabatic_wall'} | {'type': 'extrapolation', 'order': 0|1} | {'type': 'symmetry'}
                     | {'type': 'inlet_pressure_extrapolate'} | {'type': 'dirichlet_field', 'table': ndarray [nv, tangential]}
                     | {'type': 'zero_gradient_outlet'} | {'type': 'pressure_outlet'} (side 1; constant back_pressure) | {'type': 'inviscid_wall'}
+                    | {'type': 'generic'}: the face's kernel is a run-time compiled user kernel with when = 'bc_<dir>_<side>' (user_kernels)
                     every non-periodic face may carry 'closure': 'reduced_access' | 'carpenter' (one-sided derivative rows)
     viscosity       {'type': 'constant'} | {'type': 'sutherland'} | {'type': 'power', 'exponent': e}
                     (constant: an optional constant 'mu' scales 1/Re, e.g. viscous_shock_tube.py:14-16)
@@ -44,7 +45,7 @@ import json
 
 CONV = ('central', 'weno', 'teno')
 BC_TYPES = ('periodic', 'dirichlet', 'exchange', 'isothermal_wall', 'extrapolation', 'inlet_pressure_extrapolate', 'symmetry',
-            'dirichlet_field', 'adiabatic_wall', 'zero_gradient_outlet', 'pressure_outlet', 'inviscid_wall')
+            'dirichlet_field', 'adiabatic_wall', 'zero_gradient_outlet', 'pressure_outlet', 'inviscid_wall', 'generic')
 
 # one-sided derivative closures: rows idx = 0.. next to the face x weights of the boundary-absolute points 0..np-1
 # (reduced_access_scheme.py:36-43,76-83; Carpenter's first-derivative rows are taken from the scheme object by the back end)

@@ -137,16 +137,22 @@ def user_kernel_source(k, index, env, nd):
     for name, val in env.items():                       # the constants the statements mention, as the reference's C globals
         if re.search(r'\b%s\b' % re.escape(name), text):
             L.append('#define %s (%s)' % (name, repr(float(val))))
+    # OSB_GOFF<d>: global index of the rank's first point along direction d (slab-decomposed runs; decomp.local_plan defines it)
+    L += ['#ifndef OSB_GOFF0', '#define OSB_GOFF0 0', '#endif', '#ifndef OSB_GOFF1', '#define OSB_GOFF1 0', '#endif', '#ifndef OSB_GOFF2', '#define OSB_GOFF2 0', '#endif']
     L += ['extern "C" __global__ void %s(long long off, int n0, int n1, int n2, int lo0, int lo1, int lo2, long long s1, long long s2, UserFields f) {' % entry,
           '  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;',
           '  if (i >= n0 || j >= n1 || k >= n2) return;',
-          '  const long long X = off + (lo0 + i) + (lo1 + j) * s1 + (lo2 + k) * s2;']
+          '  const long long X = off + (lo0 + i) + (lo1 + j) * s1 + (lo2 + k) * s2;',
+          '  const int idx0 = lo0 + i + OSB_GOFF0, idx1 = lo1 + j + OSB_GOFF1, idx2 = lo2 + k + OSB_GOFF2;   // grid indices (block.grid_indexes)',
+          '  (void)idx0; (void)idx1; (void)idx2;']
     for n, name in enumerate(fields):
         L.append('  double *%s = f.p[%d];' % (name, n))
     for name in dict.fromkeys(k['locals']):
         L.append('  double %s;' % name)
-    for lhs, is_field, rhs in k['statements']:
-        L.append('  %s%s = %s;' % (lhs, '[X]' if is_field else '', rhs))
+    for st in k['statements']:
+        lhs, is_field, rhs = st[0], st[1], st[2]
+        at = (st[3] if len(st) > 3 and st[3] else 'X')            # relative write (boundary kernels): index printed by the back end
+        L.append('  %s%s = %s;' % (lhs, '[%s]' % at if is_field else '', rhs))
     L.append('}')
     rng = [int(c_eval(r, env)) for r in k['range']]
     return {'name': k['name'], 'entry': entry, 'source': '\n'.join(L) + '\n', 'fields': fields, 'range': rng, 'when': k['when'],

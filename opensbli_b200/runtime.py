@@ -186,12 +186,20 @@ class Simulation(object):
         `writes`: the names among `fields` the kernel assigns (created zero-initialised when new); a name it only reads
         must already exist on the device.  writes=None treats every name as written (the pre-existing call shape)."""
         r = (ctypes.c_int * 6)(*(list(rng) + [0, 1] * 3)[:6])
-        w = {'iteration_end': 0, 'after_loop': 1}[when]
+        w = self._when_code(when)
         names = [('+' + f) if (writes is None or f in writes) else f for f in fields]
         self._check(self.lib.osb_add_user_kernel(self.ctx, source.encode(), entry.encode(), ','.join(names).encode(), r, w), 'osb_add_user_kernel')
 
+    @staticmethod
+    def _when_code(when):
+        """'iteration_end' | 'after_loop' | 'bc_<dir>_<side>' (the boundary kernel of a face whose plan entry is 'generic')"""
+        if when.startswith('bc_'):
+            _, d, s = when.split('_')
+            return 100 + 2 * int(d) + int(s)
+        return {'iteration_end': 0, 'after_loop': 1}[when]
+
     def run_user_kernels(self, when='after_loop'):
-        self._check(self.lib.osb_run_user_kernels(self.ctx, {'iteration_end': 0, 'after_loop': 1}[when]), 'osb_run_user_kernels')
+        self._check(self.lib.osb_run_user_kernels(self.ctx, self._when_code(when)), 'osb_run_user_kernels')
         self.sync()
 
     def read_point(self, name, i, j=0, k=0):

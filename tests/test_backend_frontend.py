@@ -45,6 +45,19 @@ APPS = {
                     [("boundaries[direction][side] = SymmetryBC(direction, side)",
                       "from opensbli.core.boundary_conditions.inviscid_wall import InviscidWallBC\nboundaries[direction][side] = InviscidWallBC(direction, side)"),
                      ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),
+    # the same three through the run-time compiled boundary-kernel path (OSB_GENERIC_BC forces it for classes that have a hand-written
+    # kernel): what classes without one (ForcingStripWall, InletLawal, InletTransfer, InviscidWall2D) go through
+    'sod_zgo_generic': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("boundaries += [DirichletBC(direction, 1, right_eqns)]", "boundaries += [ZeroGradientOutletBC(direction, 1)]"),
+                                                                         ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None, {'OSB_GENERIC_BC': 'ZeroGradientOutlet,Dirichlet'}),
+    'sod_pout_generic': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("boundaries += [DirichletBC(direction, 1, right_eqns)]", "boundaries += [PressureOutletBC(direction, 1, 0.1)]"),
+                                                                          ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None, {'OSB_GENERIC_BC': 'PressureOutlet'}),
+    'isr_invwall_generic': (REF + '/apps/inviscid_shock_reflection/inviscid_shock.py',
+                            [("boundaries[direction][side] = SymmetryBC(direction, side)",
+                              "from opensbli.core.boundary_conditions.inviscid_wall import InviscidWallBC\nboundaries[direction][side] = InviscidWallBC(direction, side)"),
+                             ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None, {'OSB_GENERIC_BC': 'Symmetry,Extrapolation,Dirichlet'}),
+    # InletTransferBC has no hand-written kernel: generic by itself (Sod with the left boundary copied from its first halo point)
+    'sod_inlet_transfer': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("boundaries += [DirichletBC(direction, 0, left_eqns)]", "boundaries += [InletTransferBC(direction, 0)]"),
+                                                                            ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),
     # BASELINE configs[3] as worded: the Katzer app with WENO-Z instead of adaptive TENO (same edits as oracle/gen_ref.py)
     'katzer_wenoz': (REF + '/apps/katzer_SBLI/katzer_SBLI.py',
                      [("sc1 = \"**{\\'scheme\\':\\'Teno\\'}\"", "sc1 = \"**{\\'scheme\\':\\'Weno\\'}\""), ("constituent.add_equations(shock_sensor)", "pass"),
@@ -68,9 +81,9 @@ exec(compile(src, %(app)r, 'exec'), {'__name__': '__main__'})
 
 
 def start_app(name, workdir):
-    app, edits, _ = APPS[name]
+    app, edits = APPS[name][0], APPS[name][1]
     code = DRIVER % dict(oracle=os.path.join(REPO, 'oracle'), repo=REPO, ref=REF, app=app, edits=edits)
-    env = dict(os.environ, PYTHONHASHSEED='0')
+    env = dict(os.environ, PYTHONHASHSEED='0', **(APPS[name][3] if len(APPS[name]) > 3 else {}))
     return subprocess.Popen([sys.executable, '-W', 'ignore', '-c', code], cwd=workdir, env=env, stdout=subprocess.DEVNULL)
 
 
@@ -128,6 +141,12 @@ def test_b200_backend_distils_expected_plan(name, app_runs):
         assert sym['ndim'] in (1, 2, 3)
         if name == 'isr_invwall':      # kernel named 'Symmetry' by the reference, recognised by what it assigns
             assert sym['bc'][1][0]['type'] == 'inviscid_wall' and sym['bc'][0][1] == {'type': 'extrapolation', 'order': 0}
+        if name.endswith('_generic') or name == 'sod_inlet_transfer':
+            gen = [(d, sd) for d, pair in enumerate(sym['bc']) for sd, b in enumerate(pair) if b['type'] == 'generic']
+            assert gen and sorted(k['when'] for k in sym['user_kernels']) == sorted('bc_%d_%d' % f for f in gen)
+            plan_sym, env, plan_num, _cold = R.load_case(workdir)
+            for k in plan_num['user_kernels']:
+                assert 'extern "C" __global__' in k['source'] and k['when'].startswith('bc_')
         return
     plan_sym, env, plan_num, _cold = R.load_case(workdir)
     want, _ = load_fixture(APPS[name][2])

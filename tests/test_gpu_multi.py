@@ -98,8 +98,10 @@ def test_slabs_match_single_gpu(fixture, world, tmp_path):
     assert np.array_equal(got, ref), (float(diff.max()), len(where), where[:5].tolist())       # identical arithmetic per point: bit-exact
 
 
-@pytest.mark.parametrize('world', [2, 4])
-def test_katzer_500x250_decomposed_matches_single_gpu(world, tmp_path):
+@pytest.mark.parametrize('case,world,names', [('katzer', 2, ('rho', 'rhou0', 'rhou1', 'rhoE', 'TENO')), ('katzer', 4, ('rho', 'rhou0', 'rhou1', 'rhoE', 'TENO')),
+                                              # run-time compiled boundary kernels on every face, slabs along y
+                                              ('isr_invwall_generic', 2, ('rho', 'rhou0', 'rhou1', 'rhoE'))])
+def test_apps_decomposed_by_the_runner_match_single_gpu(case, world, names, tmp_path):
     """BASELINE configs[3] at its shipped size through the app-level runner on 2 / 4 GPUs (slabs along y: 250 = 63 + 63 + 62 + 62,
     wall and shock-generator faces stay with the ranks that own them): the dataset file equals the single-GPU run's bit for bit."""
     import subprocess
@@ -113,12 +115,12 @@ def test_katzer_500x250_decomposed_matches_single_gpu(world, tmp_path):
     for n, d in ((1, tmp_path / 'one'), (world, tmp_path / 'many')):
         d.mkdir()
         for f in ('opensbli_b200.plan.json', 'opensbli.cpp'):
-            shutil.copy(os.path.join(HERE, 'golden', 'plans', 'katzer', f), str(d))
+            shutil.copy(os.path.join(HERE, 'golden', 'plans', case, f), str(d))
         cmd = [sys.executable, '-m', 'opensbli_b200.run', str(d), '--niter', '10']
         if n > 1:
             cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(n), '--master-addr', '127.0.0.1',
                    '--master-port', str(_free_port()), '-m', 'opensbli_b200.run', str(d), '--niter', '10']
         subprocess.check_call(cmd, cwd=repo, env=dict(os.environ, PYTHONPATH=repo))
         outs.append(iodata.read_datasets(str(d / 'opensbli_output'))[0])
-    for name in ('rho', 'rhou0', 'rhou1', 'rhoE', 'TENO'):
+    for name in names:
         assert np.array_equal(outs[0][name][5:-5, 5:-5], outs[1][name][5:-5, 5:-5]), name
