@@ -912,10 +912,10 @@ def extract_plan(algorithm):
     user = []
     for c in in_iter:
         if type(c).__name__ == 'Kernel' and _name(c).startswith('User kernel'):
-            user.append(_user_kernel(c, 'iteration_end'))
+            user.append(_user_kernel(c, 'iteration_end', stencil=True))
     for c in after:
         if type(c).__name__ == 'Kernel' and _name(c).startswith('User kernel'):
-            user.append(_user_kernel(c, 'after_loop'))
+            user.append(_user_kernel(c, 'after_loop', stencil=True))
     # components of the program that are not part of the per-step hot path (file output, monitors, timers): not executed
     # by the B200 run-time; listed in the plan and printed so that nothing is dropped silently
     plan['not_executed'] = sorted(set(type(c).__name__ for c in in_iter + after + before
