@@ -169,3 +169,21 @@ def test_tgv_64_cubed_100_steps_norms_and_diagnostics():
     err = field_errors(plan, qg, ref)
     print('100 steps, fields', describe(err))
     assert max(err) < 1e-10, err
+
+
+@pytest.mark.parametrize('conv,order,form,avg', [('weno', 5, 'Z', 'roe'), ('weno', 5, 'JS', 'simple'), ('teno', 5, 'JS', 'simple'), ('teno', 6, 'JS', 'roe')],
+                         ids=['wenoZ-roe', 'wenoJS-simple', 'teno5-simple', 'teno6-roe'])
+def test_other_reconstructions_on_the_marching_and_tile_sweeps_at_scale(conv, order, form, avg):
+    """The marching TMA sweeps are instantiated for WENO5-JS/Z and both averagings as well (TENO6 keeps the tile kernel): the
+    same 96 x 72 x 80 block, non-symmetric smooth state, 1 step against the oracle."""
+    from test_gpu_parity import synthetic_state
+    np3 = (96, 72, 80)
+    plan, _ = tgv_case(np3, 'teno5')
+    plan.update(conv=conv, order=order, weno_formulation=form, averaging=avg)
+    plan['constants'].update(Minf=0.5, Re=200.0, dt=2e-3, TENO_CT=1e-5)
+    q0 = pad(plan, synthetic_state(plan))
+    qg = inner(plan, run_gpu(plan, [a.copy() for a in q0], 1))
+    qo, _ = ou.oracle_advance(plan, [a.copy() for a in q0], 1)
+    err = field_errors(plan, qg, inner(plan, qo))
+    print(conv, order, form, avg, describe(err))
+    assert max(err) < tol_for(plan, 1), err
