@@ -85,6 +85,34 @@ int osb_timer_stop(osb_ctx *ctx, double *elapsed_ms);
 /* End-to-end: copy the conserved arrays from host (pinned or pageable, reference layout), advance
  * nsteps, copy them back.  q_in/q_out hold ndim+2 pointers.  elapsed_ms covers H2D + steps + D2H. */
 int osb_advance_host(osb_ctx *ctx, const double *const *q_in, double *const *q_out, int nsteps, double *elapsed_ms);
+/* Window pipeline over a host-resident block (opensbli_b200/hostpipe.py drives it; the reference reads and writes whole
+ * blocks through ops_fetch / HDF5, io_hdf5.py:99-127, so there is no counterpart to cite): the context holds one WINDOW of
+ * the block -- a run of planes along the slowest axis whose cut faces carry the 'open' boundary type -- and owns an upload
+ * and a download stream next to its compute stream.
+ *   osb_host_planes_upload    copy nplanes planes of each conserved array (src[m] points at the first plane in PINNED host
+ *                             memory) into padded local planes [plane0, plane0 + nplanes); asynchronous; waits for a pending
+ *                             download of this context first
+ *   osb_host_planes_ready     make the compute stream wait for the uploads enqueued so far
+ *   osb_host_planes_download  copy padded local planes [plane0, ...) of the state as it is after the work enqueued on the
+ *                             compute stream so far; asynchronous
+ *   osb_host_planes_sync      wait for all three streams */
+int osb_host_planes_upload(osb_ctx *ctx, const double *const *src, int plane0, int nplanes);
+int osb_host_planes_ready(osb_ctx *ctx);
+int osb_host_planes_download(osb_ctx *ctx, double *const *dst, int plane0, int nplanes);
+int osb_host_planes_sync(osb_ctx *ctx);
+/* Staging copy of the whole block on the device, so that the host arrays cross PCIe once although neighbouring windows
+ * share their guard and halo planes: osb_staging_upload copies planes host -> stage on the stage's own stream (pinned memory,
+ * asynchronous); osb_staging_feed makes the window's compute stream wait for the uploads enqueued so far (and for a pending
+ * download of that context) and copies stage planes [stage_plane0, +nplanes) into the window's padded local planes
+ * [plane0, +nplanes) device to device; osb_staging_fed is called once per window after its last feed. */
+typedef struct osb_staging osb_staging;
+int osb_staging_create(int device, int nv, long long plane_doubles, int nplanes, osb_staging **out);
+int osb_staging_destroy(osb_staging *stage);
+const char *osb_staging_last_error(const osb_staging *stage);
+int osb_staging_upload(osb_staging *stage, const double *const *src, int plane0, int nplanes);
+int osb_staging_feed(osb_staging *stage, osb_ctx *ctx, int stage_plane0, int plane0, int nplanes);
+int osb_staging_fed(osb_ctx *ctx);
+int osb_staging_sync(osb_staging *stage);
 
 /* Instrumentation: number of kernels launched by this context so far; per-family device time of
  * one profiled step (events around each launch).  Families: see OSB_FAM_*. */

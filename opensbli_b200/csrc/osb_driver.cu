@@ -29,7 +29,8 @@ enum RkKind { RK_SBLI = 0, RK_LS = 1 };
 enum BcKind { BC_PERIODIC = 0, BC_DIRICHLET = 1, BC_EXCHANGE = 2 /* neighbour rank owns the halo */, BC_ISOTHERMAL_WALL = 3,
               BC_EXTRAPOLATION = 4, BC_INLET_PRESSURE = 5, BC_SYMMETRY = 6, BC_DIRICHLET_FIELD = 7, BC_ADIABATIC_WALL = 8,
               BC_ZERO_GRADIENT = 9, BC_PRESSURE_OUTLET = 10, BC_INVISCID_WALL = 11,
-              BC_GENERIC = 12 /* run-time compiled kernel registered with when = 100 + 2 dir + side */ };
+              BC_GENERIC = 12 /* run-time compiled kernel registered with when = 100 + 2 dir + side */,
+              BC_OPEN = 13 /* halo left as uploaded: the face of a window cut out of a larger block (guard planes absorb the error) */ };
 
 struct BcSpec {
   int kind = BC_PERIODIC;
@@ -119,6 +120,10 @@ struct osb_ctx {
   double *diag_buf = nullptr;                   // partial sums of the diagnostics kernels
   bool prim_stale = false;                      // u, p, a, T arrays lag the state (stage kernels that derive them on the fly)
   int swap_parity = 0;                          // fused central path: q and Residual buffers exchange roles every stage
+  // window pipeline over a host-resident state (osb_host_planes_*): copy streams ordered against the compute stream by events
+  cudaStream_t s_up = nullptr, s_down = nullptr;
+  cudaEvent_t ev_up = nullptr, ev_comp = nullptr, ev_down = nullptr;
+  bool down_pending = false;
 };
 
 namespace {
@@ -164,6 +169,7 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
       BcSpec &b = P.bc[d][s];
       if (kind == "periodic") b.kind = BC_PERIODIC;
       else if (kind == "exchange") b.kind = BC_EXCHANGE;
+      else if (kind == "open") b.kind = BC_OPEN;
       else if (kind == "dirichlet") { b.kind = BC_DIRICHLET; for (int m = 0; m < P.nd + 2; m++) ls >> b.q[m]; }
       else if (kind == "dirichlet_field") b.kind = BC_DIRICHLET_FIELD;
       else if (kind == "isothermal_wall") b.kind = BC_ISOTHERMAL_WALL;
@@ -534,6 +540,7 @@ int launch_bcs(osb_ctx *c) {
     for (int s = 0; s < 2; s++) {
       const BcSpec &b = P.bc[d][s];
       if (b.kind == BC_EXCHANGE) continue;   // filled by the neighbour rank (osb_halo_push)
+      if (b.kind == BC_OPEN) continue;       // window face: nothing to fill
       if (b.kind == BC_GENERIC) {            // boundary class without a hand-written kernel: its run-time compiled kernel
         bool found = false;
         for (auto &k : c->user_kernels) found = found || k.when == 100 + 2 * d + s;
@@ -937,6 +944,9 @@ int osb_destroy(osb_ctx *c) {
   for (auto &f : c->fields) cudaFree(f.dev);
   for (int d = 0; d < 3; d++) for (int s = 0; s < 2; s++) if (c->face_table[d][s]) cudaFree(c->face_table[d][s]);
   if (c->timer0) { cudaEventDestroy(c->timer0); cudaEventDestroy(c->timer1); }
+  if (c->s_up) cudaStreamDestroy(c->s_up);
+  if (c->s_down) cudaStreamDestroy(c->s_down);
+  for (cudaEvent_t e : {c->ev_up, c->ev_comp, c->ev_down}) if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -1204,6 +1214,148 @@ int osb_advance_host(osb_ctx *c, const double *const *q_in, double *const *q_out
   if (ms) *ms = t;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return rc;
+}
+
+// ---- window pipeline over a host-resident state ------------------------------------------------------
+// A block that lives in host memory is advanced window by window (planes along the slowest axis, 'open' faces, guard planes
+// on both sides): while one context sweeps its window, the next one receives its planes and the previous one returns its
+// result, so the three engines (H2D, SMs, D2H) work at the same time.  Each context orders its own three streams by events.
+static int pipeline_init(osb_ctx *c) {
+  if (c->s_up) return 0;
+  OSB_CUDA(c, cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
+  OSB_CUDA(c, cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking));
+  OSB_CUDA(c, cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
+  OSB_CUDA(c, cudaEventCreateWithFlags(&c->ev_comp, cudaEventDisableTiming));
+  OSB_CUDA(c, cudaEventCreateWithFlags(&c->ev_down, cudaEventDisableTiming));
+  return 0;
+}
+static int plane_range_ok(osb_ctx *c, int plane0, int nplanes) {
+  const int d = c->plan.nd - 1;
+  if (plane0 < 0 || nplanes < 1 || plane0 + nplanes > c->grid.pd[d]) return fail(c, "plane range outside the padded array");
+  return 0;
+}
+int osb_host_planes_upload(osb_ctx *c, const double *const *src, int plane0, int nplanes) {
+  if (!c || !src) return 1;
+  cudaSetDevice(c->device);
+  if (pipeline_init(c) || plane_range_ok(c, plane0, nplanes)) return 1;
+  const int d = c->plan.nd - 1, nv = c->plan.nd + 2;
+  // the planes being overwritten may still be on their way back to the host from the previous window of this context
+  if (c->down_pending) OSB_CUDA(c, cudaStreamWaitEvent(c->s_up, c->ev_down, 0));
+  const size_t plane = sizeof(double) * c->grid.s[d];
+  for (int m = 0; m < nv; m++)
+    OSB_CUDA(c, cudaMemcpyAsync(c->fp.q[m] + (long long)plane0 * c->grid.s[d], src[m], plane * nplanes, cudaMemcpyHostToDevice, c->s_up));
+  OSB_CUDA(c, cudaEventRecord(c->ev_up, c->s_up));
+  return 0;
+}
+// The window is about to be advanced as a fresh block: the RK registers of the low-storage scheme enter the first stage multiplied
+// by A[0] = 0, which does not clear what an earlier window left in the guard planes if that is not finite (0 * NaN)
+static int window_reset_registers(osb_ctx *c) {
+  const int nv = c->plan.nd + 2;
+  for (int m = 0; m < nv; m++) OSB_CUDA(c, cudaMemsetAsync(c->fp.rk[m], 0, sizeof(double) * c->grid.n, c->stream));
+  return 0;
+}
+int osb_host_planes_ready(osb_ctx *c) {
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  if (pipeline_init(c)) return 1;
+  OSB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_up, 0));     // work enqueued on the compute stream from here on sees the uploads
+  return window_reset_registers(c);
+}
+int osb_host_planes_download(osb_ctx *c, double *const *dst, int plane0, int nplanes) {
+  if (!c || !dst) return 1;
+  cudaSetDevice(c->device);
+  if (pipeline_init(c) || plane_range_ok(c, plane0, nplanes)) return 1;
+  const int d = c->plan.nd - 1, nv = c->plan.nd + 2;
+  OSB_CUDA(c, cudaEventRecord(c->ev_comp, c->stream));
+  OSB_CUDA(c, cudaStreamWaitEvent(c->s_down, c->ev_comp, 0));
+  const size_t plane = sizeof(double) * c->grid.s[d];
+  for (int m = 0; m < nv; m++)
+    OSB_CUDA(c, cudaMemcpyAsync(dst[m], c->fp.q[m] + (long long)plane0 * c->grid.s[d], plane * nplanes, cudaMemcpyDeviceToHost, c->s_down));
+  OSB_CUDA(c, cudaEventRecord(c->ev_down, c->s_down));
+  c->down_pending = true;
+  return 0;
+}
+// Staging copy of the whole block on the device: the host arrays cross PCIe once, in plane order, and every window takes its
+// planes (guard and halo planes included, which neighbouring windows share) from here with device-to-device copies.
+struct osb_staging {
+  int device = 0, nv = 0, nplanes = 0;
+  long long plane = 0;                       // doubles per plane
+  double *buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t s_up = nullptr;
+  std::string error;
+};
+int osb_staging_create(int device, int nv, long long plane_doubles, int nplanes, osb_staging **out) {
+  if (!out || nv < 1 || nv > 5 || plane_doubles < 1 || nplanes < 1) return 1;
+  *out = nullptr;
+  if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return 2;
+  osb_staging *st = new osb_staging();
+  cudaGetDevice(&st->device);
+  st->nv = nv; st->nplanes = nplanes; st->plane = plane_doubles;
+  bool ok = cudaStreamCreateWithFlags(&st->s_up, cudaStreamNonBlocking) == cudaSuccess;
+  for (int m = 0; m < nv && ok; m++) ok = cudaMalloc(&st->buf[m], sizeof(double) * plane_doubles * nplanes) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); osb_staging_destroy(st); return 3; }
+  *out = st;
+  return 0;
+}
+int osb_staging_destroy(osb_staging *st) {
+  if (!st) return 0;
+  cudaSetDevice(st->device);
+  for (int m = 0; m < 5; m++) if (st->buf[m]) cudaFree(st->buf[m]);
+  if (st->s_up) cudaStreamDestroy(st->s_up);
+  delete st;
+  return 0;
+}
+const char *osb_staging_last_error(const osb_staging *st) { return st ? st->error.c_str() : "null stage"; }
+#define OSB_STAGE_CUDA(st, call)                                                                                     \
+  do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { (st)->error = std::string(#call) + ": " + cudaGetErrorString(e_); return 1; } } while (0)
+int osb_staging_upload(osb_staging *st, const double *const *src, int plane0, int nplanes) {
+  if (!st || !src) return 1;
+  cudaSetDevice(st->device);
+  if (plane0 < 0 || nplanes < 1 || plane0 + nplanes > st->nplanes) { st->error = "plane range outside the staged block"; return 1; }
+  for (int m = 0; m < st->nv; m++)
+    OSB_STAGE_CUDA(st, cudaMemcpyAsync(st->buf[m] + plane0 * st->plane, src[m], sizeof(double) * st->plane * nplanes, cudaMemcpyHostToDevice, st->s_up));
+  return 0;
+}
+int osb_staging_feed(osb_staging *st, osb_ctx *c, int stage_plane0, int plane0, int nplanes) {
+  if (!st || !c) return 1;
+  cudaSetDevice(c->device);
+  if (pipeline_init(c) || plane_range_ok(c, plane0, nplanes)) return 1;
+  const int d = c->plan.nd - 1, nv = c->plan.nd + 2;
+  if (nv != st->nv || c->grid.s[d] != st->plane) return fail(c, "osb_staging_feed: the staged planes do not have this context's layout");
+  if (stage_plane0 < 0 || stage_plane0 + nplanes > st->nplanes) return fail(c, "osb_staging_feed: plane range outside the staged block");
+  // everything enqueued on the stage's upload stream so far must have landed; the planes being overwritten may still be on
+  // their way to the host from the previous window of this context
+  cudaEvent_t e;
+  OSB_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  OSB_CUDA(c, cudaEventRecord(e, st->s_up));
+  OSB_CUDA(c, cudaStreamWaitEvent(c->stream, e, 0));
+  OSB_CUDA(c, cudaEventDestroy(e));            // released by the runtime once the wait has been satisfied
+  if (c->down_pending) OSB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_down, 0));
+  for (int m = 0; m < nv; m++)
+    OSB_CUDA(c, cudaMemcpyAsync(c->fp.q[m] + (long long)plane0 * st->plane, st->buf[m] + (long long)stage_plane0 * st->plane,
+                                sizeof(double) * st->plane * nplanes, cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+int osb_staging_fed(osb_ctx *c) {                // all planes of the window are in place: it starts as a fresh block
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  return window_reset_registers(c);
+}
+int osb_staging_sync(osb_staging *st) {
+  if (!st) return 1;
+  cudaSetDevice(st->device);
+  OSB_STAGE_CUDA(st, cudaStreamSynchronize(st->s_up));
+  return 0;
+}
+
+int osb_host_planes_sync(osb_ctx *c) {
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  if (c->s_up) OSB_CUDA(c, cudaStreamSynchronize(c->s_up));
+  OSB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->s_down) OSB_CUDA(c, cudaStreamSynchronize(c->s_down));
+  c->down_pending = false;
+  return 0;
 }
 
 // ---- in-loop diagnostics ---------------------------------------------------------------------------

@@ -1,0 +1,183 @@
+"""Window pipeline: advance a block that lives in HOST memory with the three engines of the GPU busy at the same time.
+
+The reference moves whole blocks between host and device (ops_fetch / HDF5, opensbli/core/io_hdf5.py:99-127) and has nothing
+to cite here; this module is how the end-to-end call of the B200 back end (`Simulation.advance_host`: upload, step, download,
+one after the other) is made to overlap its copies with the sweeps.
+
+The block is cut into WINDOWS along its slowest axis.  A window carries `guard` extra planes on each cut side, its cut faces
+have the 'open' boundary type (nothing is filled there), and it is advanced as an independent small block:
+
+    upload   the host arrays cross PCIe ONCE, in plane order, into a staging copy of the block on the device; the window takes
+             planes [z0 - guard - halo, z1 + guard + halo) (periodic wrap) from there with device-to-device copies, as soon as
+             the upload has got that far
+    step     nsteps iterations on its compute stream -- every RK stage invalidates `depth` more planes next to an open face
+             (depth = the reach of the scheme's stencil along the axis), so with guard = depth * (stages * nsteps - 1) the
+             planes [z0, z1) end up exactly as in a run of the whole block (same kernels, same arithmetic per point)
+    download planes [z0, z1) into the host arrays, on the context's download stream
+
+A few contexts take the windows in turn, so window k+1 is uploaded and window k-1 downloaded while window k is swept.  The
+price is the redundant sweep of the guard planes; the gain is that a step costs max(copy, sweep) instead of their sum.
+
+Scope: periodic along the slab axis, no per-point plan arrays (metrics, tables) and no user kernels -- the periodic-box
+configurations the bench line is quoted on.  Anything else raises PlanError; callers fall back to `advance_host`.
+"""
+import copy
+
+from . import plan as _plan
+from .decomp import scheme_halos, slab_axis
+
+HALO = 5
+
+
+def stencil_depth(plan):
+    """Planes next to an open face that one RK stage invalidates = the farthest plane a residual reads along the axis: 2 for
+    Central(4) (first, second and mixed derivatives), 3 for WENO5 / TENO5 / TENO6 (interfaces i -+ 1/2 read points i-3 .. i+3;
+    the fourth halo plane the reference exchanges on one side, weno.py:17-32, is not read by a residual)."""
+    return scheme_halos(plan)[0]
+
+
+def guard_planes(plan, nsteps=1):
+    return stencil_depth(plan) * (len(plan['rk_a']) * int(nsteps) - 1)
+
+
+def windows(n, chunk):
+    """[(z0, z1)] covering [0, n) with windows of exactly `chunk` planes; the last one is shifted back to end at n (its
+    overlap with the one before is computed twice, to the same values)."""
+    if chunk >= n:
+        return [(0, n)]
+    out = []
+    z = 0
+    while z + chunk < n:
+        out.append((z, z + chunk))
+        z += chunk
+    out.append((n - chunk, n))
+    return out
+
+
+def window_plan(plan, chunk, nsteps=1):
+    """Plan of one window (all windows share it): `chunk` + 2 guard planes along the slab axis, 'open' cut faces."""
+    plan = _plan.validate(copy.deepcopy(plan))
+    ax = slab_axis(plan)
+    n = plan['np'][ax]
+    if plan['bc'][ax][0]['type'] != 'periodic' or plan['bc'][ax][1]['type'] != 'periodic':
+        raise _plan.PlanError('window pipeline: the slab axis must be periodic')
+    if plan.get('fields') or plan.get('user_fields') or plan.get('user_kernels'):
+        raise _plan.PlanError('window pipeline: per-point plan arrays and user kernels are not windowed')
+    for d in range(plan['ndim']):
+        for s in range(2):
+            if plan['bc'][d][s].get('table') is not None:
+                raise _plan.PlanError('window pipeline: tabulated boundary states are not windowed')
+    g = guard_planes(plan, nsteps)
+    if chunk >= n:
+        raise _plan.PlanError('window pipeline: one window would hold the whole block (use advance_host)')
+    p = copy.deepcopy(plan)
+    p['np'][ax] = chunk + 2 * g
+    p['bc'][ax][0] = {'type': 'open'}
+    p['bc'][ax][1] = {'type': 'open'}
+    p.pop('io', None)
+    return _plan.validate(p), g
+
+
+def wrapped_runs(first, count, n):
+    """Split global interior planes [first, first + count) (may lie outside [0, n): periodic images) into runs of
+    consecutive planes inside [0, n): [(global plane of the run, offset within the request, length)]."""
+    runs = []
+    done = 0
+    while done < count:
+        g = (first + done) % n
+        length = min(count - done, n - g)
+        runs.append((g, done, length))
+        done += length
+    return runs
+
+
+class HostPipeline(object):
+    """advance(q_in, q_out): q_out <- nsteps iterations of q_in, both lists of padded host arrays (PINNED for the copies to
+    overlap; reference layout, slab axis first).  Same result, bit for bit, as Simulation.advance_host on the whole block in
+    every cell a kernel defines: the grid points and the halo cells within the scheme's halo depth (the last boundary-condition
+    pass).  Halo cells beyond that depth are read by nothing and are left unspecified, as they are by the whole-block call."""
+
+    def __init__(self, plan, chunk=64, nsteps=1, device=-1, contexts=3, factory=None, stage_factory=None):
+        """factory(window_plan) -> window solver, stage_factory(nv, plane_doubles, nplanes) -> staging copy; defaults: a
+        Simulation and a Stage on `device` (the CPU tests of the windowing drive the oracle through the same calls)."""
+        if factory is None:
+            from .runtime import Simulation, Stage
+            factory = lambda p: Simulation(p, device=device)
+            stage_factory = lambda nv, plane, n: Stage(nv, plane, n, device=device)
+        self.plan_global = _plan.validate(copy.deepcopy(plan))
+        self.ax = slab_axis(self.plan_global)
+        self.n = self.plan_global['np'][self.ax]
+        self.nsteps = int(nsteps)
+        self.chunk = int(chunk)
+        self.plan, self.guard = window_plan(self.plan_global, self.chunk, self.nsteps)
+        self.windows = windows(self.n, self.chunk)
+        self.sims = [factory(self.plan) for _ in range(min(int(contexts), len(self.windows)))]
+        self.hm, self.hp = scheme_halos(self.plan_global)
+        self.nv = self.plan_global['ndim'] + 2
+        self.plane = 1
+        for d in range(self.plan_global['ndim']):
+            if d != self.ax:
+                self.plane *= self.plan_global['np'][d] + 2 * HALO
+        self.stage = stage_factory(self.nv, self.plane, self.n)
+        self.launches = 0
+
+    def close(self):
+        for s in self.sims:
+            s.close()
+        self.sims = []
+        if self.stage is not None:
+            self.stage.close()
+            self.stage = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def bytes_per_call(self):
+        """(H2D, D2H) bytes of one advance() call, counted from the plane copies it enqueues."""
+        down = sum(z1 - z0 for z0, z1 in self.windows) + 2 * self.hm
+        return self.n * self.plane * 8 * self.nv, down * self.plane * 8 * self.nv
+
+    def advance(self, q_in, q_out):
+        n, g, h = self.n, self.guard, HALO
+        if any(a is b or a.ctypes.data == b.ctypes.data for a, b in zip(q_in, q_out)):
+            raise ValueError('window pipeline: q_out must not alias q_in (windows read guard planes other windows write)')
+        l0 = sum(s.launch_count() for s in self.sims)
+        staged = [False] * n                         # planes of the block already on their way to the staging copy
+        for w, (z0, z1) in enumerate(self.windows):
+            sim = self.sims[w % len(self.sims)]
+            # padded local plane j of the window holds plane z0 - g - h + j of the block (periodic image)
+            runs = wrapped_runs(z0 - g - h, self.chunk + 2 * g + 2 * h, n)
+            for gp, _, length in runs:
+                a = gp
+                while a < gp + length:               # upload the planes of this run that no earlier window asked for
+                    if staged[a]:
+                        a += 1
+                        continue
+                    b = a
+                    while b < gp + length and not staged[b]:
+                        staged[b] = True
+                        b += 1
+                    self.stage.upload(q_in, h + a, a, b - a)
+                    a = b
+            for gp, off, length in runs:
+                self.stage.feed(sim, gp, off, length)
+            sim.stage_fed()
+            sim.step(self.nsteps, sync=False)
+            sim.planes_download(q_out, h + z0, h + g, z1 - z0)
+            # halo planes of the whole block as its periodic BC leaves them after the last stage: [-hm, 0) <- [n-hm, n),
+            # [n, n+hm) <- [0, hm)  (periodic.py:42-56: side 0 copies hm planes up; side 1 copies hp planes starting at n-hm
+            # down to -hm, the last of which lands on plane 0 and is plane 0); they come from the windows that own those planes
+            lo, hi = max(z0, n - self.hm), min(z1, n)
+            if lo < hi:
+                sim.planes_download(q_out, h + lo - n, h + g + lo - z0, hi - lo)
+            lo, hi = max(z0, 0), min(z1, self.hm)
+            if lo < hi:
+                sim.planes_download(q_out, h + n + lo, h + g + lo - z0, hi - lo)
+        for sim in self.sims:
+            sim.planes_sync()
+        self.stage.sync()
+        self.launches = sum(s.launch_count() for s in self.sims) - l0
+        return self.launches

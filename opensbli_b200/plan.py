@@ -19,6 +19,7 @@ JSON-able dict; `to_text` serialises it to the line format parsed by the C ABI (
     constants       {name: float}                 gama, Minf, Re, Pr, dt, eps, TENO_CT, ...
     bc              [[side0, side1] per direction] each {'type': 'periodic'} | {'type': 'dirichlet', 'q': [...]}
                     | {'type': 'exchange'} (halo owned by the neighbouring rank of a slab decomposition)
+                    | {'type': 'open'} (cut face of a window of a larger block: the halo is left as uploaded, hostpipe.py)
                     | {'type': 'isothermal_wall'} | {'type': 'adiabatic_wall'} | {'type': 'extrapolation', 'order': 0|1} | {'type': 'symmetry'}
                     | {'type': 'inlet_pressure_extrapolate'} | {'type': 'dirichlet_field', 'table': ndarray [nv, tangential]}
                     | {'type': 'zero_gradient_outlet'} | {'type': 'pressure_outlet'} (side 1; constant back_pressure) | {'type': 'inviscid_wall'}
@@ -45,7 +46,7 @@ import json
 
 CONV = ('central', 'weno', 'teno')
 BC_TYPES = ('periodic', 'dirichlet', 'exchange', 'isothermal_wall', 'extrapolation', 'inlet_pressure_extrapolate', 'symmetry',
-            'dirichlet_field', 'adiabatic_wall', 'zero_gradient_outlet', 'pressure_outlet', 'inviscid_wall', 'generic')
+            'dirichlet_field', 'adiabatic_wall', 'zero_gradient_outlet', 'pressure_outlet', 'inviscid_wall', 'generic', 'open')
 
 # one-sided derivative closures: rows idx = 0.. next to the face x weights of the boundary-absolute points 0..np-1
 # (reduced_access_scheme.py:36-43,76-83; Carpenter's first-derivative rows are taken from the scheme object by the back end)

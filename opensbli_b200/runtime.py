@@ -18,6 +18,8 @@ SYMBOLS = ('osb_create', 'osb_destroy', 'osb_last_error', 'osb_set_const_f64', '
            'osb_num_fields', 'osb_field_name', 'osb_field_info', 'osb_upload', 'osb_download', 'osb_device_ptr', 'osb_upload_face',
            'osb_step', 'osb_step_begin', 'osb_stage', 'osb_sync', 'osb_apply_bcs', 'osb_residual', 'osb_step_timed', 'osb_timer_start', 'osb_timer_stop', 'osb_advance_host',
            'osb_launch_count', 'osb_slow_path_count', 'osb_profile_step', 'osb_nan_check', 'osb_diagnostics', 'osb_ipc_export', 'osb_ipc_import', 'osb_halo_push',
+           'osb_host_planes_upload', 'osb_host_planes_ready', 'osb_host_planes_download', 'osb_host_planes_sync',
+           'osb_staging_create', 'osb_staging_destroy', 'osb_staging_last_error', 'osb_staging_upload', 'osb_staging_feed', 'osb_staging_fed', 'osb_staging_sync',
            'osb_measure_fp64_peak')
 
 
@@ -75,8 +77,59 @@ def load_library(path=None):
     lib.osb_slow_path_count.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
     lib.osb_nan_check.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_longlong)]
     lib.osb_diagnostics.argtypes = [ctypes.c_void_p, _P]
+    lib.osb_host_planes_upload.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    lib.osb_host_planes_download.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    lib.osb_host_planes_ready.argtypes = [ctypes.c_void_p]
+    lib.osb_host_planes_sync.argtypes = [ctypes.c_void_p]
+    lib.osb_staging_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    lib.osb_staging_destroy.argtypes = [ctypes.c_void_p]
+    lib.osb_staging_last_error.restype = ctypes.c_char_p
+    lib.osb_staging_last_error.argtypes = [ctypes.c_void_p]
+    lib.osb_staging_upload.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    lib.osb_staging_feed.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.osb_staging_fed.argtypes = [ctypes.c_void_p]
+    lib.osb_staging_sync.argtypes = [ctypes.c_void_p]
     _lib = lib
     return lib
+
+
+class Stage(object):
+    """Device copy of a whole host-resident block (planes along the slowest axis) that windows are fed from (hostpipe.py)."""
+
+    def __init__(self, nv, plane_doubles, nplanes, device=-1):
+        self.lib = load_library()
+        self.nv = nv
+        h = ctypes.c_void_p()
+        rc = self.lib.osb_staging_create(int(device), int(nv), int(plane_doubles), int(nplanes), ctypes.byref(h))
+        if rc:
+            raise BackendError('osb_staging_create failed (%d): %s' % (rc, 'out of device memory' if rc == 3 else 'no CUDA device'))
+        self.h = h
+
+    def _check(self, rc, what):
+        if rc:
+            raise BackendError('%s: %s' % (what, self.lib.osb_staging_last_error(self.h).decode()))
+
+    def upload(self, arrays, host_plane0, plane0, nplanes):
+        stride = arrays[0].strides[0]
+        ptrs = (ctypes.c_void_p * self.nv)(*[a.ctypes.data + host_plane0 * stride for a in arrays])
+        self._check(self.lib.osb_staging_upload(self.h, ptrs, int(plane0), int(nplanes)), 'osb_staging_upload')
+
+    def feed(self, sim, stage_plane0, plane0, nplanes):
+        sim._check(self.lib.osb_staging_feed(self.h, sim.ctx, int(stage_plane0), int(plane0), int(nplanes)), 'osb_staging_feed')
+
+    def sync(self):
+        self._check(self.lib.osb_staging_sync(self.h), 'osb_staging_sync')
+
+    def close(self):
+        if self.h:
+            self.lib.osb_staging_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def measure_fp64_peak(device=-1):
@@ -270,6 +323,27 @@ class Simulation(object):
         ms = ctypes.c_double()
         self._check(self.lib.osb_advance_host(self.ctx, pin, pout, int(nsteps), ctypes.byref(ms)), 'osb_advance_host')
         return ms.value
+
+    # -- window pipeline over a host-resident block (hostpipe.py)
+    def planes_upload(self, arrays, host_plane0, plane0, nplanes):
+        """Asynchronous copy of planes [host_plane0, +nplanes) of the padded host arrays into local planes [plane0, +nplanes)."""
+        stride = arrays[0].strides[0]
+        ptrs = (ctypes.c_void_p * self.nv)(*[a.ctypes.data + host_plane0 * stride for a in arrays])
+        self._check(self.lib.osb_host_planes_upload(self.ctx, ptrs, int(plane0), int(nplanes)), 'osb_host_planes_upload')
+
+    def planes_ready(self):
+        self._check(self.lib.osb_host_planes_ready(self.ctx), 'osb_host_planes_ready')
+
+    def planes_download(self, arrays, host_plane0, plane0, nplanes):
+        stride = arrays[0].strides[0]
+        ptrs = (ctypes.c_void_p * self.nv)(*[a.ctypes.data + host_plane0 * stride for a in arrays])
+        self._check(self.lib.osb_host_planes_download(self.ctx, ptrs, int(plane0), int(nplanes)), 'osb_host_planes_download')
+
+    def planes_sync(self):
+        self._check(self.lib.osb_host_planes_sync(self.ctx), 'osb_host_planes_sync')
+
+    def stage_fed(self):
+        self._check(self.lib.osb_staging_fed(self.ctx), 'osb_staging_fed')
 
     # -- in-loop diagnostics
     def nan_check(self, name='rho'):

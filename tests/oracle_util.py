@@ -11,7 +11,7 @@ ORACLE_DIR = os.path.join(REPO, 'oracle')
 REF_DIR = os.path.join(ORACLE_DIR, '_ref')
 
 CONV = {'central': 0, 'weno': 1, 'teno': 2}
-BC = {'periodic': 0, 'dirichlet': 1, 'exchange': 2, 'isothermal_wall': 3, 'extrapolation': 4,
+BC = {'periodic': 0, 'dirichlet': 1, 'exchange': 2, 'open': 2, 'isothermal_wall': 3, 'extrapolation': 4,
       'inlet_pressure_extrapolate': 5, 'symmetry': 6, 'dirichlet_field': 7, 'adiabatic_wall': 8,
       'zero_gradient_outlet': 9, 'pressure_outlet': 10, 'inviscid_wall': 11}
 MU = {'constant': 0, 'sutherland': 1, 'power': 2}
