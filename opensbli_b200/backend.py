@@ -99,7 +99,7 @@ class _Printer(object):
         return self.p.doprint(expr)
 
 
-def _user_kernel(kernel, when, stencil=False):
+def _user_kernel(kernel, when, stencil=False, thin_direction=None):
     """A user kernel compiled at run time (NVRTC): an ordered list of assignments [lhs, is_dataset, rhs in C, lhs index] over
     the kernel's range -- app-specific arithmetic outside the solver's hot loops cannot be hand-written.
     stencil=False: point-wise kernels (statistics accumulation, e.g. channel_flow/*/stats.py; `User kernel` in the algorithm).
@@ -158,7 +158,10 @@ def _user_kernel(kernel, when, stencil=False):
     if stencil:
         # two different points p, p' of the range touch the same element iff p - p' = (read or write offset) - (write offset);
         # that is impossible when the difference is non-zero along a direction in which the range is one point thick
-        thin = [str(rng[2 * d + 1] - rng[2 * d]) == '1' for d in range(len(rng) // 2)] + [True] * 3
+        if thin_direction is None:
+            thin = [str(rng[2 * d + 1] - rng[2 * d]) == '1' for d in range(len(rng) // 2)] + [True] * 3
+        else:       # ranges given at run time (SplitBC): a boundary kernel covers ONE plane normal to its direction (checked when resolved)
+            thin = [d == thin_direction for d in range(len(rng) // 2)] + [True] * 3
         for n, ws in woff.items():
             for w in ws:
                 for o in ws | roff.get(n, set()):
@@ -168,8 +171,11 @@ def _user_kernel(kernel, when, stencil=False):
                                                 'it cannot run one thread per point' % (_name(kernel), n, w, o))
     consts = sorted(set(str(s) for e in kernel.equations for s in e.rhs.free_symbols
                         if type(s).__name__ == 'ConstantObject'))
-    return {'name': _name(kernel), 'when': when, 'range': [ccode(r) for r in rng], 'reads': reads,
-            'writes': writes, 'locals': local, 'constants': consts, 'statements': out}
+    out_k = {'name': _name(kernel), 'when': when, 'range': [r if isinstance(r, str) else ccode(r) for r in rng], 'reads': reads,
+             'writes': writes, 'locals': local, 'constants': consts, 'statements': out}
+    if thin_direction is not None:
+        out_k['one_plane_along'] = thin_direction
+    return out_k
 
 
 def _cold_kernel(kernel):
@@ -372,6 +378,7 @@ def _check_curvilinear_residual(recon, resid, ndim):
 
 
 # boundary classes routed through the run-time compiled path although a hand-written kernel exists (tests of that path)
+_SPLIT_BC = re.compile(r'(\w+) bc direction-(\d) side-(\d) split-(\d+)')
 GENERIC_BCS = set(k for k in os.environ.get('OSB_GENERIC_BC', '').split(',') if k)
 
 NATIVE_BCS = ('Dirichlet', 'Extrapolation', 'InletPressureExtrapolate', 'Symmetry', 'AdiabaticWall', 'IsothermalWall', 'ZeroGradientOutlet', 'PressureOutlet')
@@ -930,7 +937,7 @@ def extract_plan(algorithm):
     cr, recon, resid, central_conv, viscous, rk_kernels, stage_bcs, unknown = [], [], [], [], [], [], [], []
     for c in in_stage:
         t, n = type(c).__name__, _name(c)
-        if t == 'ExchangeSelf' or ' boundary dir' in n:
+        if t == 'ExchangeSelf' or ' boundary dir' in n or _SPLIT_BC.match(n or ''):
             stage_bcs.append(c)
         elif t != 'Kernel':
             unknown.append(c)
@@ -954,6 +961,8 @@ def extract_plan(algorithm):
     if source_kernel is not None:
         cr.remove(source_kernel)
     def _generic_bc(c):           # boundary kernels that will be compiled at run time carry their own constants
+        if _SPLIT_BC.match(_name(c) or '') or (_name(c) or '').startswith('User kernel'):
+            return True
         m = re.match(r'(\w+) boundary dir(\d) side(\d)', _name(c) or '')
         return bool(m) and (m.group(1) not in NATIVE_BCS or m.group(1) in GENERIC_BCS)
     _check_constants_used([c for c in in_stage + in_iter if c is not source_kernel and not _generic_bc(c)])
@@ -1015,7 +1024,20 @@ def extract_plan(algorithm):
 
     # ---- boundary conditions, from the iteration-start list (algorithm.py:442)
     bc = [[None, None] for _ in range(ndim)]
-    for c in [c for c in in_iter if type(c).__name__ == 'ExchangeSelf' or ' boundary dir' in _name(c)]:
+    for c in [c for c in in_iter if type(c).__name__ == 'ExchangeSelf' or ' boundary dir' in _name(c) or _SPLIT_BC.match(_name(c) or '')]:
+        ms = _SPLIT_BC.match(_name(c) or '')
+        if ms:
+            # SplitBC (bc_core.py:200-217): several boundary classes share a face, each over its own part of the plane.  The
+            # parts are run-time integer arrays (split_range_<d><s><n> + split_halo_range_<d><s><n>, bc_core.py:110-127) that
+            # the user fills in; every part becomes a run-time compiled kernel on the face, applied in the order given
+            d, sd = int(ms.group(2)), int(ms.group(3))
+            user.append(_user_kernel(c, 'bc_%d_%d' % (d, sd), stencil=True, thin_direction=d))
+            entry = bc[d][sd] or {'type': 'generic', 'class': 'Split', 'parts': []}
+            entry['parts'].append(ms.group(1))
+            if (d, sd) in faces:
+                entry['closure'] = closure_name
+            bc[d][sd] = entry
+            continue
         if type(c).__name__ == 'ExchangeSelf':
             arrays = [_strip(a) for a in c.transfer_arrays]
             if arrays != q_names:
@@ -1083,7 +1105,10 @@ def extract_plan(algorithm):
                          'to': [ccode(s) for s in c.transfer_to]})
         if type(c).__name__ == 'Kernel':
             n = _name(c)
-            if not (n.startswith('Grid_based_initialisation') or n.startswith('MetricsEquation') or n.startswith('Metric boundary')):
+            # 'User kernel: ...' placed BeforeSimulationStarts (e.g. the SFD filter's `Initialize the filter`, filters/SFD.py:50-62):
+            # evaluated once by the cold path like the initialisation, its datasets uploaded with the plan
+            if not (n.startswith('Grid_based_initialisation') or n.startswith('MetricsEquation') or n.startswith('Metric boundary')
+                    or n.startswith('User kernel')):
                 raise UnsupportedByB200('cold kernel %s is not implemented yet' % n)
             cold.append(_cold_kernel(c))
     if mass_source:
@@ -1102,6 +1127,11 @@ def extract_plan(algorithm):
     for c in ConstantsToDeclare.constants:
         if type(c).__name__ == 'ConstantObject':
             plan['constant_decls'].append([str(c), 'int' if 'int' in str(c.datatype.opsc()).lower() else 'double', _const_value(c)])
+    # run-time integer arrays of SplitBC: declared like OPSC does, `int name[] = {Input, ...};`, for the user to fill in
+    arrays = [[str(c.base), 'int', 2 * ndim] for c in ConstantsToDeclare.constants
+              if type(c).__name__ == 'ConstantIndexed' and str(c.base).startswith(('split_range_', 'split_halo_range_'))]
+    if arrays:
+        plan['constant_array_decls'] = arrays
     return plan
 
 
@@ -1111,6 +1141,8 @@ def write_stub(plan, path=STUB_FILE):
          '// run with:  python -m opensbli_b200.run', 'int main(int argc, char **argv)', '{']
     for name, dtype, value in plan['constant_decls']:
         L.append('%s=%s;' % (name, value) if value == 'Input' else '%s = %s;' % (name, value))
+    for name, dtype, count in plan.get('constant_array_decls', []):
+        L.append('%s %s[] = {%s};' % (dtype, name, ', '.join(['Input'] * count)))
     L += ['int iter=0;', '', '}']
     open(path, 'w').write('\n'.join(L) + '\n')
 

@@ -30,9 +30,17 @@ enum BcKind { BC_PERIODIC = 0, BC_DIRICHLET = 1, BC_EXCHANGE = 2 /* neighbour ra
               BC_EXTRAPOLATION = 4, BC_INLET_PRESSURE = 5, BC_SYMMETRY = 6, BC_DIRICHLET_FIELD = 7, BC_ADIABATIC_WALL = 8,
               BC_ZERO_GRADIENT = 9, BC_PRESSURE_OUTLET = 10, BC_INVISCID_WALL = 11,
               BC_GENERIC = 12 /* run-time compiled kernel registered with when = 100 + 2 dir + side */,
+              BC_SPLIT = 14 /* several boundary classes share the face, each over its own part of the plane (SplitBC, bc_core.py:200-217) */,
               BC_OPEN = 13 /* halo left as uploaded: the face of a window cut out of a larger block (guard planes absorb the error) */ };
 
+struct BcPart {              // one part of a split face: boundary class + evaluation range [lo, hi) per direction (halo extension included)
+  int kind = BC_SYMMETRY, order = 0;
+  int lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+  double q[5] = {0, 0, 0, 0, 0};
+};
+
 struct BcSpec {
+  std::vector<BcPart> parts; // BC_SPLIT
   int kind = BC_PERIODIC;
   double q[5] = {0, 0, 0, 0, 0};
   int order = 0;            // extrapolation order
@@ -170,6 +178,7 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
       if (kind == "periodic") b.kind = BC_PERIODIC;
       else if (kind == "exchange") b.kind = BC_EXCHANGE;
       else if (kind == "open") b.kind = BC_OPEN;
+      else if (kind == "split") b.kind = BC_SPLIT;
       else if (kind == "dirichlet") { b.kind = BC_DIRICHLET; for (int m = 0; m < P.nd + 2; m++) ls >> b.q[m]; }
       else if (kind == "dirichlet_field") b.kind = BC_DIRICHLET_FIELD;
       else if (kind == "isothermal_wall") b.kind = BC_ISOTHERMAL_WALL;
@@ -189,6 +198,23 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
         else if (tok == "ke_free") b.free_mask |= 256;
         else { err = "bad bc line: " + line; return false; }
       }
+    }
+    else if (key == "bc_part") {
+      int d, s; std::string kind; ls >> d >> s >> kind;
+      if (d < 0 || d >= P.nd || s < 0 || s > 1 || P.bc[d][s].kind != BC_SPLIT) { err = "bc_part without a 'split' face: " + line; return false; }
+      BcPart part;
+      static const std::map<std::string, int> kinds = {{"dirichlet", BC_DIRICHLET}, {"isothermal_wall", BC_ISOTHERMAL_WALL}, {"adiabatic_wall", BC_ADIABATIC_WALL},
+        {"extrapolation", BC_EXTRAPOLATION}, {"inlet_pressure_extrapolate", BC_INLET_PRESSURE}, {"symmetry", BC_SYMMETRY}, {"zero_gradient_outlet", BC_ZERO_GRADIENT},
+        {"pressure_outlet", BC_PRESSURE_OUTLET}, {"inviscid_wall", BC_INVISCID_WALL}};
+      auto it = kinds.find(kind);
+      if (it == kinds.end()) { err = "unsupported boundary condition '" + kind + "' in a split face"; return false; }
+      part.kind = it->second;
+      for (int e = 0; e < P.nd; e++) if (!(ls >> part.lo[e] >> part.hi[e]) || part.hi[e] <= part.lo[e]) { err = "bad bc_part range: " + line; return false; }
+      if (part.hi[d] - part.lo[d] != 1) { err = "a split part covers one plane along its face normal: " + line; return false; }
+      if (part.kind == BC_DIRICHLET) { for (int m = 0; m < P.nd + 2; m++) if (!(ls >> part.q[m])) { err = "bad bc_part line: " + line; return false; } }
+      else ls >> part.order;
+      if ((part.kind == BC_PRESSURE_OUTLET && s != 1) || (part.kind == BC_INLET_PRESSURE && s != 0)) { err = "boundary class on the wrong side: " + line; return false; }
+      P.bc[d][s].parts.push_back(part);
     }
     else if (key == "viscosity") {
       std::string v; ls >> v;
@@ -231,6 +257,12 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
   for (int d = 0; d < P.nd; d++) for (int s = 0; s < 2; s++) {
     if (P.bc[d][s].kind == BC_ISOTHERMAL_WALL && !P.consts.count("Twall")) { err = "missing constant Twall"; return false; }
     if (P.bc[d][s].kind == BC_PRESSURE_OUTLET && !P.consts.count("back_pressure")) { err = "missing constant back_pressure"; return false; }
+    if (P.bc[d][s].kind == BC_SPLIT && P.bc[d][s].parts.empty()) { err = "split face without parts"; return false; }
+    for (const BcPart &part : P.bc[d][s].parts) {
+      if (part.kind == BC_ISOTHERMAL_WALL && !P.consts.count("Twall")) { err = "missing constant Twall"; return false; }
+      if (part.kind == BC_PRESSURE_OUTLET && !P.consts.count("back_pressure")) { err = "missing constant back_pressure"; return false; }
+      for (int e = 0; e < P.nd; e++) if (part.lo[e] < -5 || part.hi[e] > P.np[e] + 5) { err = "split part outside the padded block"; return false; }
+    }
   }
   return true;
 }
@@ -531,6 +563,46 @@ void box_launch_cfg(const Box &b, int nv, unsigned &blocks) {
 
 int run_user_kernels(osb_ctx *c, int when);
 
+// plane kernels: one thread per point of the boundary plane (or of a part of it), each filling its column of halo points
+void launch_plane_bc(osb_ctx *c, int kind, int order, int free_mask, int d, int s, const PlaneSpec &ps) {
+  const Plan &P = c->plan;
+  const GridDev &g = c->grid;
+  const int nv = P.nd + 2;
+  const long long cnt = (long long)ps.n[0] * ps.n[1] * ps.n[2];
+  const unsigned nb = (unsigned)((cnt + 127) / 128);
+  Launcher L(c, OSB_FAM_BC);
+  switch (kind) {
+    case BC_DIRICHLET_FIELD: k_bc_dirichlet_field<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps, c->face_table[d][s], c->face_size[d], free_mask); break;
+    case BC_EXTRAPOLATION: k_bc_extrapolation<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps, order); break;
+    case BC_SYMMETRY: k_bc_symmetry<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps); break;
+    case BC_ZERO_GRADIENT: k_bc_zero_gradient<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps); break;
+    case BC_INVISCID_WALL: k_bc_inviscid_wall<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps); break;
+    case BC_PRESSURE_OUTLET: {
+      const double bp = P.consts.at("back_pressure");
+      if (P.nd == 1) k_bc_pressure_outlet<1><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps, bp);
+      else if (P.nd == 2) k_bc_pressure_outlet<2><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps, bp);
+      else k_bc_pressure_outlet<3><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps, bp);
+      break;
+    }
+    case BC_INLET_PRESSURE:
+      if (P.nd == 1) k_bc_inlet_pressure<1><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+      else if (P.nd == 2) k_bc_inlet_pressure<2><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+      else k_bc_inlet_pressure<3><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+      break;
+    case BC_ISOTHERMAL_WALL:
+      if (P.nd == 1) k_bc_isothermal_wall<1><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+      else if (P.nd == 2) k_bc_isothermal_wall<2><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+      else k_bc_isothermal_wall<3><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+      break;
+    case BC_ADIABATIC_WALL:
+      if (P.nd == 1) k_bc_adiabatic_wall<1><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+      else if (P.nd == 2) k_bc_adiabatic_wall<2><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+      else k_bc_adiabatic_wall<3><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
+      break;
+    default: break;
+  }
+}
+
 int launch_bcs(osb_ctx *c) {
   const Plan &P = c->plan;
   const GridDev &g = c->grid;
@@ -568,45 +640,33 @@ int launch_bcs(osb_ctx *c) {
         box_launch_cfg(dst, nv, blocks);
         Launcher L(c, OSB_FAM_BC);
         k_fill_box<<<blocks, 256, 0, c->stream>>>(g, c->fp, nv, dst, st);
+      } else if (b.kind == BC_SPLIT) {
+        // SplitBC (bc_core.py:200-217): the parts in the order given, each over its own range of the boundary plane
+        for (const BcPart &part : b.parts) {
+          if (part.kind == BC_DIRICHLET) {
+            Box dst;
+            for (int e = 0; e < 3; e++) { dst.lo[e] = e < P.nd ? part.lo[e] : 0; dst.n[e] = e < P.nd ? part.hi[e] - part.lo[e] : 1; }
+            if (s == 0) { dst.lo[d] = -hm; dst.n[d] = hm + 1; } else { dst.lo[d] = g.np[d] - 1; dst.n[d] = hp + 1; }
+            DirichletState st;
+            for (int m = 0; m < 5; m++) st.q[m] = part.q[m];
+            box_launch_cfg(dst, nv, blocks);
+            Launcher L(c, OSB_FAM_BC);
+            k_fill_box<<<blocks, 256, 0, c->stream>>>(g, c->fp, nv, dst, st);
+            continue;
+          }
+          PlaneSpec ps;
+          ps.dir = d; ps.side = s; ps.nh = s == 0 ? hm : hp;
+          for (int e = 0; e < 3; e++) { ps.lo[e] = e < P.nd ? part.lo[e] : 0; ps.n[e] = e < P.nd ? part.hi[e] - part.lo[e] : 1; }
+          ps.lo[d] = s == 0 ? 0 : g.np[d] - 1; ps.n[d] = 1;
+          launch_plane_bc(c, part.kind, part.order, 0, d, s, ps);
+        }
       } else {
         // plane kernels: boundary plane of (d, s), tangential range incl. the scheme halos
         PlaneSpec ps;
         ps.dir = d; ps.side = s; ps.nh = s == 0 ? hm : hp;
         for (int e = 0; e < 3; e++) { ps.lo[e] = full.lo[e]; ps.n[e] = full.n[e]; }
         ps.lo[d] = s == 0 ? 0 : g.np[d] - 1; ps.n[d] = 1;
-        const long long cnt = (long long)ps.n[0] * ps.n[1] * ps.n[2];
-        const unsigned nb = (unsigned)((cnt + 127) / 128);
-        Launcher L(c, OSB_FAM_BC);
-        switch (b.kind) {
-          case BC_DIRICHLET_FIELD: k_bc_dirichlet_field<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps, c->face_table[d][s], c->face_size[d], b.free_mask); break;
-          case BC_EXTRAPOLATION: k_bc_extrapolation<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps, b.order); break;
-          case BC_SYMMETRY: k_bc_symmetry<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps); break;
-          case BC_ZERO_GRADIENT: k_bc_zero_gradient<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps); break;
-          case BC_INVISCID_WALL: k_bc_inviscid_wall<<<nb, 128, 0, c->stream>>>(g, c->fp, nv, ps); break;
-          case BC_PRESSURE_OUTLET: {
-            const double bp = P.consts.at("back_pressure");
-            if (P.nd == 1) k_bc_pressure_outlet<1><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps, bp);
-            else if (P.nd == 2) k_bc_pressure_outlet<2><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps, bp);
-            else k_bc_pressure_outlet<3><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps, bp);
-            break;
-          }
-          case BC_INLET_PRESSURE:
-            if (P.nd == 1) k_bc_inlet_pressure<1><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
-            else if (P.nd == 2) k_bc_inlet_pressure<2><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
-            else k_bc_inlet_pressure<3><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
-            break;
-          case BC_ISOTHERMAL_WALL:
-            if (P.nd == 1) k_bc_isothermal_wall<1><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
-            else if (P.nd == 2) k_bc_isothermal_wall<2><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
-            else k_bc_isothermal_wall<3><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
-            break;
-          case BC_ADIABATIC_WALL:
-            if (P.nd == 1) k_bc_adiabatic_wall<1><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
-            else if (P.nd == 2) k_bc_adiabatic_wall<2><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
-            else k_bc_adiabatic_wall<3><<<nb, 128, 0, c->stream>>>(g, c->fp, c->pc, ps);
-            break;
-          default: break;
-        }
+        launch_plane_bc(c, b.kind, b.order, b.free_mask, d, s, ps);
       }
     }
   return 0;

@@ -23,6 +23,9 @@ JSON-able dict; `to_text` serialises it to the line format parsed by the C ABI (
                     | {'type': 'isothermal_wall'} | {'type': 'adiabatic_wall'} | {'type': 'extrapolation', 'order': 0|1} | {'type': 'symmetry'}
                     | {'type': 'inlet_pressure_extrapolate'} | {'type': 'dirichlet_field', 'table': ndarray [nv, tangential]}
                     | {'type': 'zero_gradient_outlet'} | {'type': 'pressure_outlet'} (side 1; constant back_pressure) | {'type': 'inviscid_wall'}
+                    | {'type': 'split', 'parts': [{'type': t, 'range': [lo0, hi0, lo1, hi1, ...], ('order': n)}, ...]}: SplitBC
+                      (bc_core.py:200-217) -- several boundary classes share the face, each over its own part of the plane; `range`
+                      is the part's evaluation range per direction (halo extension included), one plane thick along the face normal
                     | {'type': 'generic'}: the face's kernel is a run-time compiled user kernel with when = 'bc_<dir>_<side>' (user_kernels)
                     every non-periodic face may carry 'closure': 'reduced_access' | 'carpenter' (one-sided derivative rows)
     viscosity       {'type': 'constant'} | {'type': 'sutherland'} | {'type': 'power', 'exponent': e}
@@ -46,7 +49,9 @@ import json
 
 CONV = ('central', 'weno', 'teno')
 BC_TYPES = ('periodic', 'dirichlet', 'exchange', 'isothermal_wall', 'extrapolation', 'inlet_pressure_extrapolate', 'symmetry',
-            'dirichlet_field', 'adiabatic_wall', 'zero_gradient_outlet', 'pressure_outlet', 'inviscid_wall', 'generic', 'open')
+            'dirichlet_field', 'adiabatic_wall', 'zero_gradient_outlet', 'pressure_outlet', 'inviscid_wall', 'generic', 'open', 'split')
+SPLIT_PART_TYPES = ('dirichlet', 'isothermal_wall', 'adiabatic_wall', 'extrapolation', 'inlet_pressure_extrapolate', 'symmetry',
+                    'zero_gradient_outlet', 'pressure_outlet', 'inviscid_wall')
 
 # one-sided derivative closures: rows idx = 0.. next to the face x weights of the boundary-absolute points 0..np-1
 # (reduced_access_scheme.py:36-43,76-83; Carpenter's first-derivative rows are taken from the scheme object by the back end)
@@ -88,6 +93,24 @@ def validate(plan):
                 raise PlanError('dirichlet bc needs %d conservative values' % (nd + 2))
             if b['type'] == 'pressure_outlet' and (s != 1 or 'back_pressure' not in plan.get('constants', {})):
                 raise PlanError('pressure_outlet is defined for side 1 and needs the constant back_pressure (pressure_outlet.py:22-31)')
+            if b['type'] == 'split':
+                if not b.get('parts') or len(b['parts']) > 8:
+                    raise PlanError('split bc needs 1..8 parts')
+                plane = 0 if s == 0 else plan['np'][d] - 1
+                for part in b['parts']:
+                    if part.get('type') not in SPLIT_PART_TYPES:
+                        raise PlanError("split bc: part type '%s' is not implemented (supported: %s)" % (part.get('type'), SPLIT_PART_TYPES))
+                    r = part.get('range', ())
+                    if len(r) != 2 * nd or any(r[2 * e] >= r[2 * e + 1] for e in range(nd)):
+                        raise PlanError('split bc: every part needs a non-empty range [lo, hi) per direction')
+                    if r[2 * d] != plane or r[2 * d + 1] != plane + 1:
+                        raise PlanError('split bc: a part must cover the boundary plane of its face only (direction %d: [%d, %d))' % (d, plane, plane + 1))
+                    if any(r[2 * e] < -5 or r[2 * e + 1] > plan['np'][e] + 5 for e in range(nd)):
+                        raise PlanError('split bc: part range outside the padded block')
+                    if part['type'] == 'dirichlet' and len(part.get('q', ())) != nd + 2:
+                        raise PlanError('dirichlet bc needs %d conservative values' % (nd + 2))
+                    if part['type'] == 'pressure_outlet' and (s != 1 or 'back_pressure' not in plan.get('constants', {})):
+                        raise PlanError('pressure_outlet is defined for side 1 and needs the constant back_pressure (pressure_outlet.py:22-31)')
     c = plan.get('constants', {})
     need = ['gama', 'dt'] + (['Re', 'Pr', 'Minf'] if plan.get('viscous') else [])
     for k in need:
@@ -127,6 +150,11 @@ def to_text(plan):
                 L.append('bc %d %d dirichlet %s%s' % (d, s, ' '.join(_f(v) for v in b['q']), cl))
             elif b['type'] == 'extrapolation':
                 L.append('bc %d %d extrapolation %d%s' % (d, s, int(b.get('order', 0)), cl))
+            elif b['type'] == 'split':
+                L.append('bc %d %d split%s' % (d, s, cl))
+                for part in b['parts']:
+                    extra = ' '.join(_f(v) for v in part['q']) if part['type'] == 'dirichlet' else str(int(part.get('order', 0)))
+                    L.append('bc_part %d %d %s %s %s' % (d, s, part['type'], ' '.join(str(int(v)) for v in part['range']), extra))
             elif b['type'] == 'dirichlet_field':
                 fr = ''.join(' free %d' % m for m in b.get('free', [])) + (' ke_free' if b.get('ke_free') else '')
                 L.append('bc %d %d dirichlet_field%s%s' % (d, s, cl, fr))

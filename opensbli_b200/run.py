@@ -31,6 +31,8 @@ def c_eval(expr, env):
             if n.id == 'M_PI':
                 return math.pi
             return env[n.id]
+        if isinstance(n, ast.Subscript):        # element of a run-time integer array (SplitBC ranges)
+            return ev(n.value)[int(ev(n.slice))]
         if isinstance(n, ast.UnaryOp):
             v = ev(n.operand)
             return -v if isinstance(n.op, ast.USub) else +v
@@ -53,14 +55,27 @@ def c_eval(expr, env):
     return ev(ast.parse(expr.strip(), mode='eval'))
 
 
-def read_stub(text, decls, overrides=None):
+def read_stub(text, decls, overrides=None, array_decls=()):
     """-> ordered {name: value} from the stub's `name = expr;` lines (declared types from the plan).  `overrides` replaces
-    the value of a parameter (e.g. block0np0) before the expressions that depend on it are evaluated."""
+    the value of a parameter (e.g. block0np0) before the expressions that depend on it are evaluated.  Integer arrays
+    (`int name[] = {a, b, ...};`, the SplitBC ranges the user edits by hand as in the reference's opensbli.cpp) become lists."""
     types = {n: t for n, t, _ in decls}
+    arrays = {n: int(cnt) for n, _, cnt in array_decls}
     env = {}
     overrides = overrides or {}
     for line in text.splitlines():
         line = line.strip()
+        m = re.match(r'int\s+(\w+)\[\]\s*=\s*\{(.*)\};$', line)
+        if m and m.group(1) in arrays:
+            if m.group(1) in overrides:
+                env[m.group(1)] = [int(v) for v in overrides[m.group(1)]]
+                continue
+            items = [x.strip() for x in m.group(2).split(',')]
+            if 'Input' in items or len(items) != arrays[m.group(1)]:
+                raise ValueError("range array '%s' needs %d integer values in the parameter file (opensbli.cpp): {first, last+1} per direction "
+                                 "for split_range_*, {extension below, extension above} for split_halo_range_*" % (m.group(1), arrays[m.group(1)]))
+            env[m.group(1)] = [int(c_eval(x, env)) for x in items]
+            continue
         if not line.endswith(';') or '=' not in line or line.startswith(('//', 'int iter')):
             continue
         name, expr = line[:-1].split('=', 1)
@@ -135,7 +150,7 @@ def user_kernel_source(k, index, env, nd):
     text = ' '.join(s[2] for s in k['statements'])
     L = ['struct UserFields { double *p[48]; };']
     for name, val in env.items():                       # the constants the statements mention, as the reference's C globals
-        if re.search(r'\b%s\b' % re.escape(name), text):
+        if not isinstance(val, list) and re.search(r'\b%s\b' % re.escape(name), text):
             L.append('#define %s (%s)' % (name, repr(float(val))))
     # OSB_GOFF<d>: global index of the rank's first point along direction d (slab-decomposed runs; decomp.local_plan defines it)
     L += ['#ifndef OSB_GOFF0', '#define OSB_GOFF0 0', '#endif', '#ifndef OSB_GOFF1', '#define OSB_GOFF1 0', '#endif', '#ifndef OSB_GOFF2', '#define OSB_GOFF2 0', '#endif']
@@ -155,6 +170,10 @@ def user_kernel_source(k, index, env, nd):
         L.append('  %s%s = %s;' % (lhs, '[%s]' % at if is_field else '', rhs))
     L.append('}')
     rng = [int(c_eval(r, env)) for r in k['range']]
+    if 'one_plane_along' in k:              # SplitBC part: the race check of the back end relied on it
+        d = k['one_plane_along']
+        if rng[2 * d + 1] - rng[2 * d] != 1:
+            raise ValueError('boundary kernel %s: its range must be ONE plane along direction %d, got [%d, %d)' % (k['name'], d, rng[2 * d], rng[2 * d + 1]))
     return {'name': k['name'], 'entry': entry, 'source': '\n'.join(L) + '\n', 'fields': fields, 'range': rng, 'when': k['when'],
             'writes': list(k['writes'])}
 
@@ -169,7 +188,7 @@ def resolve(plan_sym, env):
             p[k] = plan_sym[k]
     p['np'] = [int(env['block0np%d' % d]) for d in range(nd)]
     p['delta'] = [float(env['Delta%dblock0' % d]) for d in range(nd)]
-    p['constants'] = {k: float(v) for k, v in env.items() if not k.startswith(('block0np', 'Delta', 'niter'))}
+    p['constants'] = {k: float(v) for k, v in env.items() if not k.startswith(('block0np', 'Delta', 'niter')) and not isinstance(v, list)}
     p['niter'] = int(env.get('niter', 0))
     cold = ColdRunner(nd, p['np'], env)
     for k in plan_sym.get('cold', []):
@@ -184,7 +203,7 @@ def resolve(plan_sym, env):
     # plan; the runtime declares and uploads those the solver does not hold itself
     written = set(w for k in p['user_kernels'] for w in k['writes'])
     p['user_fields'] = {f: cold.array(f).copy() for k in p['user_kernels'] for f in k['fields']
-                        if f not in written and f in cold.arrays and f not in plan_sym['q_names']}
+                        if f in cold.arrays and f not in plan_sym['q_names']}
     if plan_sym.get('monitor'):
         m = dict(plan_sym['monitor'])
         m['probes'] = [[int(c_eval(x, env)) for x in pr] for pr in m['probes']]
@@ -423,7 +442,7 @@ def time_loop(runner, plan, niter, workdir='.', plan_sym=None, cold=None, iterat
 
 def load_case(workdir='.', overrides=None):
     plan_sym = json.load(open(os.path.join(workdir, PLAN_FILE)))
-    env = read_stub(open(os.path.join(workdir, STUB_FILE)).read(), plan_sym['constant_decls'], overrides)
+    env = read_stub(open(os.path.join(workdir, STUB_FILE)).read(), plan_sym['constant_decls'], overrides, plan_sym.get('constant_array_decls', ()))
     plan_num, cold = resolve(plan_sym, env)
     return plan_sym, env, plan_num, cold
 

@@ -44,6 +44,11 @@ CONFIGS = {
     'isr_invwall': (REF + '/apps/inviscid_shock_reflection/inviscid_shock.py', [("boundaries[direction][side] = SymmetryBC(direction, side)",
                      "from opensbli.core.boundary_conditions.inviscid_wall import InviscidWallBC\nboundaries[direction][side] = InviscidWallBC(direction, side)")]),
     'isr': (REF + '/apps/inviscid_shock_reflection/inviscid_shock.py', []),
+    # the same with its bottom wall split in two (SplitBC, bc_core.py:200-217): SymmetryBC over x-points [0, 20), InviscidWallBC
+    # over the rest; the part ranges are run-time arrays the reference leaves as `Input` for the user to edit (CPP_EDITS below)
+    'isr_split': (REF + '/apps/inviscid_shock_reflection/inviscid_shock.py', [("boundaries[direction][side] = SymmetryBC(direction, side)",
+                  "from opensbli.core.boundary_conditions.inviscid_wall import InviscidWallBC\nfrom opensbli.core.boundary_conditions.bc_core import SplitBC\n"
+                  "boundaries[direction][side] = SplitBC(direction, side, [SymmetryBC(direction, side), InviscidWallBC(direction, side)])")]),
     # config 2: shipped TGV app (central-4 + RK3)
     'tgv_central4': (REF + '/apps/taylor_green_vortex/taylor_green_vortex.py', []),
     # config 3/5: TGV TENO5 + StoreSome + RK-LS (our app script, reference front end + OPSC back end)
@@ -51,6 +56,11 @@ CONFIGS = {
     # config 4: shipped Katzer SBLI app (ReducedAccess closures) and a variant with the default Carpenter closures
     'katzer': (REF + '/apps/katzer_SBLI/katzer_SBLI.py', []),
     'katzer_carpenter': (REF + '/apps/katzer_SBLI/katzer_SBLI.py', [(", scheme=ReducedAccess())", ")")]),
+    # config 4 with the selective-frequency-damping filter (filters/SFD.py): a `User kernel` before the loop (filtered state <- state)
+    # and one at the end of every iteration that relaxes the state towards its filtered copy
+    'katzer_sfd': (REF + '/apps/katzer_SBLI/katzer_SBLI.py', [("block.set_equations([constituent, simulation_eq, initial, metriceq])",
+                   "from opensbli.filters.SFD import SFD\nsfd = SFD(block, chifilt=0.1, omegafilt=1.0/0.75)\n"
+                   "block.set_equations([constituent, simulation_eq, initial, metriceq] + sfd.equation_classes)")]),
     # config 4 as BASELINE.json words it: the same app with WENO-Z instead of adaptive TENO (no shock sensor)
     'katzer_wenoz': (REF + '/apps/katzer_SBLI/katzer_SBLI.py', [
         ("sc1 = \"**{\\'scheme\\':\\'Teno\\'}\"", "sc1 = \"**{\\'scheme\\':\\'Weno\\'}\""),
@@ -81,6 +91,16 @@ CONFIGS = {
     'tcf_teno6_stats': (REF + '/apps/channel_flow/compressible_TCF_TENO/turbulent_channel.py', []),
     # symmetry boundaries: shipped 1/8-domain TGV (central-4 + RK3, SymmetryBC on all six faces)
     'tgv_sym': (REF + '/apps/taylor_green_vortex/TGsym/TGsym.py', []),
+}
+
+# hand edits of the generated opensbli.cpp that the reference expects from its user (values it prints as `Input` and
+# substitute_simulation_parameters does not reach): the SplitBC part ranges; the tangential extensions (-3, +4) are those of
+# the full-plane kernel ({-3, block0np0 + 4, 0, 1} in oracle/_ref/isr/opensbli.cpp)
+CPP_EDITS = {
+    'isr_split': [("int split_range_100[] = {Input, Input, Input, Input};", "int split_range_100[] = {0, 20, 0, 1};"),
+                  ("int split_halo_range_100[] = {Input, Input, Input, Input};", "int split_halo_range_100[] = {-3, 0, 0, 0};"),
+                  ("int split_range_101[] = {Input, Input, Input, Input};", "int split_range_101[] = {20, block0np0, 0, 1};"),
+                  ("int split_halo_range_101[] = {Input, Input, Input, Input};", "int split_halo_range_101[] = {0, 4, 0, 0};")],
 }
 
 INT_PARAMS = ('niter',)
@@ -140,6 +160,12 @@ def generate(name):
     os.environ['OSBLI_BACKEND'] = 'opsc'
     g = {'__name__': '__main__', '__file__': app}
     exec(compile(src, app, 'exec'), g)
+    if name in CPP_EDITS:
+        cpp = open('opensbli.cpp').read()
+        for old, new in CPP_EDITS[name]:
+            assert old in cpp, (name, old)
+            cpp = cpp.replace(old, new)
+        open('opensbli.cpp', 'w').write(cpp)
     sha = {}
     for f in sorted(os.listdir('.')):
         if f.endswith(('.cpp', '.h')):

@@ -65,16 +65,22 @@ static void bc_periodic(const osbo_cfg *c, const grid_t *g, double *const *q, in
   }
   free(tmp);
 }
+/* part of a split face being applied (bc_core.py:110-127: arbitrary_bc_plane_kernel takes its range from run-time arrays
+ * instead of the whole plane); NULL: whole plane.  The oracle is single-threaded test infrastructure. */
+static const int *g_part_lo = NULL, *g_part_hi = NULL;
+static const double *g_part_state = NULL;
 /* dirichlet.py:28-41 + bc_core.py:158-198: boundary plane and the halo planes of that side get the
  * imposed state; tangential range = block range + scheme halos. */
 static void bc_dirichlet(const osbo_cfg *c, const grid_t *g, double *const *q, int dir, int side) {
   int hm, hp; scheme_halos(c, &hm, &hp);
   int lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
   for (int d = 0; d < g->ndim; d++) { lo[d] = -hm; hi[d] = g->np[d] + hp; }
+  if (g_part_lo) for (int d = 0; d < g->ndim; d++) { lo[d] = g_part_lo[d]; hi[d] = g_part_hi[d]; }
   if (side == 0) { lo[dir] = -hm; hi[dir] = 1; } else { lo[dir] = g->np[dir] - 1; hi[dir] = g->np[dir] + hp; }
+  const double *state = g_part_state ? g_part_state : c->bc_q[dir][side];
   for (int m = 0; m < g->nv; m++)
     for (int k = lo[2]; k < hi[2]; k++) for (int j = lo[1]; j < hi[1]; j++) for (int i = lo[0]; i < hi[0]; i++)
-      q[m][gidx(g, i, j, k)] = c->bc_q[dir][side][m];
+      q[m][gidx(g, i, j, k)] = state[m];
 }
 /* plane loop helper: boundary plane of (dir, side), tangential range = block + scheme halos (bc_core.py:158-198) */
 #define PLANE_LOOP(c, g, dir, side, ...)                                                               \
@@ -82,6 +88,7 @@ static void bc_dirichlet(const osbo_cfg *c, const grid_t *g, double *const *q, i
     int hm_, hp_; scheme_halos(c, &hm_, &hp_);                                                         \
     int lo_[3] = {0, 0, 0}, hi_[3] = {1, 1, 1};                                                        \
     for (int d_ = 0; d_ < (g)->ndim; d_++) { lo_[d_] = -hm_; hi_[d_] = (g)->np[d_] + hp_; }            \
+    if (g_part_lo) for (int d_ = 0; d_ < (g)->ndim; d_++) { lo_[d_] = g_part_lo[d_]; hi_[d_] = g_part_hi[d_]; } \
     lo_[dir] = (side) == 0 ? 0 : (g)->np[dir] - 1; hi_[dir] = lo_[dir] + 1;                            \
     for (int k = lo_[2]; k < hi_[2]; k++) for (int j = lo_[1]; j < hi_[1]; j++) for (int i = lo_[0]; i < hi_[0]; i++) { \
       const long x = gidx(g, i, j, k); (void)x; __VA_ARGS__                                                   \
@@ -262,23 +269,37 @@ static void bc_inviscid_wall(const osbo_cfg *c, const grid_t *g, double *const *
   })
 }
 /* order: dir0 side0, dir0 side1, dir1 side0 ...  (block.py:199-210, algorithm.py:440-442) */
+static void bc_apply_kind(const osbo_cfg *c, const grid_t *g, double *const *q, int kind, int d, int s) {
+  switch (kind) {
+    case OSBO_BC_PERIODIC: bc_periodic(c, g, q, d, s); break;
+    case OSBO_BC_DIRICHLET: bc_dirichlet(c, g, q, d, s); break;
+    case OSBO_BC_DIRICHLET_FIELD: bc_dirichlet_field(c, g, q, d, s); break;
+    case OSBO_BC_EXTRAPOLATION: bc_extrapolation(c, g, q, d, s); break;
+    case OSBO_BC_INLET_PRESSURE_EXTRAPOLATE: bc_inlet_pressure(c, g, q, d, s); break;
+    case OSBO_BC_ISOTHERMAL_WALL: bc_isothermal_wall(c, g, q, d, s); break;
+    case OSBO_BC_SYMMETRY: bc_symmetry(c, g, q, d, s); break;
+    case OSBO_BC_ADIABATIC_WALL: bc_adiabatic_wall(c, g, q, d, s); break;
+    case OSBO_BC_ZERO_GRADIENT_OUTLET: bc_zero_gradient_outlet(c, g, q, d, s); break;
+    case OSBO_BC_PRESSURE_OUTLET: bc_pressure_outlet(c, g, q, d, s); break;
+    case OSBO_BC_INVISCID_WALL: bc_inviscid_wall(c, g, q, d, s); break;
+    default: break;
+  }
+}
 void osbo_apply_bcs(const osbo_cfg *c, double *const *q) {
   grid_t g; grid_init(c, &g);
   for (int d = 0; d < c->ndim; d++)
     for (int s = 0; s < 2; s++) {
-      switch (c->bc[d][s]) {
-        case OSBO_BC_PERIODIC: bc_periodic(c, &g, q, d, s); break;
-        case OSBO_BC_DIRICHLET: bc_dirichlet(c, &g, q, d, s); break;
-        case OSBO_BC_DIRICHLET_FIELD: bc_dirichlet_field(c, &g, q, d, s); break;
-        case OSBO_BC_EXTRAPOLATION: bc_extrapolation(c, &g, q, d, s); break;
-        case OSBO_BC_INLET_PRESSURE_EXTRAPOLATE: bc_inlet_pressure(c, &g, q, d, s); break;
-        case OSBO_BC_ISOTHERMAL_WALL: bc_isothermal_wall(c, &g, q, d, s); break;
-        case OSBO_BC_SYMMETRY: bc_symmetry(c, &g, q, d, s); break;
-        case OSBO_BC_ADIABATIC_WALL: bc_adiabatic_wall(c, &g, q, d, s); break;
-        case OSBO_BC_ZERO_GRADIENT_OUTLET: bc_zero_gradient_outlet(c, &g, q, d, s); break;
-        case OSBO_BC_PRESSURE_OUTLET: bc_pressure_outlet(c, &g, q, d, s); break;
-        case OSBO_BC_INVISCID_WALL: bc_inviscid_wall(c, &g, q, d, s); break;
-        default: break;
+      if (c->bc[d][s] == OSBO_BC_SPLIT) {
+        /* bc_core.py:200-217: every part is the boundary class's own kernel over the part's range, in the order given */
+        for (int n = 0; n < c->split_n[d][s]; n++) {
+          osbo_cfg part = *c;                       /* the part's parameters where the class reads them from the face */
+          part.extrap_order[d][s] = c->split_order[d][s][n];
+          g_part_lo = c->split_lo[d][s][n]; g_part_hi = c->split_hi[d][s][n]; g_part_state = c->split_q[d][s][n];
+          bc_apply_kind(&part, &g, q, c->split_kind[d][s][n], d, s);
+          g_part_lo = g_part_hi = NULL; g_part_state = NULL;
+        }
+      } else {
+        bc_apply_kind(c, &g, q, c->bc[d][s], d, s);
       }
     }
 }

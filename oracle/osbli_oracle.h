@@ -37,7 +37,8 @@ enum { OSBO_RK_SBLI = 0, OSBO_RK_LS = 1 };
 enum { OSBO_BC_PERIODIC = 0, OSBO_BC_DIRICHLET = 1, OSBO_BC_EXCHANGE = 2 /* halo filled by the caller (decomposed run) */,
        OSBO_BC_ISOTHERMAL_WALL = 3, OSBO_BC_EXTRAPOLATION = 4, OSBO_BC_INLET_PRESSURE_EXTRAPOLATE = 5,
        OSBO_BC_SYMMETRY = 6, OSBO_BC_DIRICHLET_FIELD = 7 /* imposed state varies along the face */,
-       OSBO_BC_ADIABATIC_WALL = 8, OSBO_BC_ZERO_GRADIENT_OUTLET = 9, OSBO_BC_PRESSURE_OUTLET = 10, OSBO_BC_INVISCID_WALL = 11 };
+       OSBO_BC_ADIABATIC_WALL = 8, OSBO_BC_ZERO_GRADIENT_OUTLET = 9, OSBO_BC_PRESSURE_OUTLET = 10, OSBO_BC_INVISCID_WALL = 11,
+       OSBO_BC_SPLIT = 14 /* SplitBC (bc_core.py:200-217): several boundary classes on one face, each over its own part of the plane */ };
 enum { OSBO_MU_CONSTANT = 0, OSBO_MU_SUTHERLAND = 1, OSBO_MU_POWER = 2 };
 
 typedef struct {
@@ -87,6 +88,13 @@ typedef struct {
   const double *curv_D[3][3];
   const double *curv_detJ;
   double back_pressure;       /* OSBO_BC_PRESSURE_OUTLET: imposed outlet pressure (pressure_outlet.py:22-47) */
+  /* OSBO_BC_SPLIT faces: parts in the order applied; each has a boundary kind and the evaluation range [lo, hi) per direction that
+   * the reference takes from its run-time arrays split_range_<d><s><n> + split_halo_range_<d><s><n> (bc_core.py:110-127) */
+  int split_n[3][2];
+  int split_kind[3][2][8];
+  int split_lo[3][2][8][3], split_hi[3][2][8][3];
+  int split_order[3][2][8];   /* extrapolation order of a part */
+  double split_q[3][2][8][5]; /* Dirichlet state of a part */
   int central_form;           /* Central(4) convective split: 0 Blaisdell skew form (taylor_green_vortex.py:8-11, laminar_channel.py:7-9),
                                * 1 Feiereisen quadratic split (compressible_TCF_Central/turbulent_channel.py:12-20) */
 } osbo_cfg;

@@ -106,9 +106,12 @@ def isr_plan(N0, N1, wall):
     """apps/inviscid_shock_reflection/inviscid_shock.py: 2-D Euler, WENO5-Z with simple averaging, RungeKuttaLS(3); constant
     Dirichlet inflow, order-0 extrapolation outflow, shock-generator Dirichlet state along the top (tabulated: main() reads both
     imposed states off the reference's own dumps), bottom wall = SymmetryBC (shipped) or InviscidWallBC (inviscid_wall.py:24-52)."""
+    bottom = dict(type=wall)
+    if wall == 'split':      # SplitBC (bc_core.py:200-217) as set up by oracle/gen_ref.py CPP_EDITS: SymmetryBC over x-points [-3, 20), InviscidWallBC beyond
+        bottom = dict(type='split', parts=[dict(type='symmetry', range=[-3, 20, 0, 1]), dict(type='inviscid_wall', range=[20, N0 + 4, 0, 1])])
     return dict(ndim=2, np=[N0, N1], delta=[350.0 / (N0 - 1), 115.0 / (N1 - 1)], conv='weno', order=5, weno_formulation='Z',
                 averaging='simple', viscous=False, constants=dict(gama=1.4, Minf=2.0, dt=0.1),
-                bc=[[dict(type='dirichlet', q=None), dict(type='extrapolation', order=0)], [dict(type=wall), dict(type='dirichlet_field')]], **LS3)
+                bc=[[dict(type='dirichlet', q=None), dict(type='extrapolation', order=0)], [bottom, dict(type='dirichlet_field')]], **LS3)
 
 
 FIXTURES['sod_zgo_n200'] = ('sod_zgo', sod_outlet_plan(200, 'zero_gradient_outlet'), [1, 50])
@@ -124,6 +127,9 @@ def katzer_wenoz_plan(N0, N1):
     return p
 
 
+# the Katzer app with the SFD filter (filters/SFD.py) switched on: golden states of an APP run (its user kernels change the state, which
+# the oracle does not model), kept under golden/apps/ so that the fixture-driven oracle tests do not pick it up
+FIXTURES['apps/katzer_sfd_60x40'] = ('katzer_sfd', katzer_plan(60, 40), [10])
 FIXTURES['katzer_wenoz_60x40'] = ('katzer_wenoz', katzer_wenoz_plan(60, 40), [1, 10])
 
 
@@ -252,6 +258,7 @@ if os.path.isdir('/root/reference'):
     FIXTURES['tcf_teno6_stats_16x24x12'] = ('tcf_teno6_stats', tcf_teno6_plan(16, 24, 12), [5])
     FIXTURES['isr_invwall_48x32'] = ('isr_invwall', isr_plan(48, 32, 'inviscid_wall'), [1, 20])
     FIXTURES['isr_48x32'] = ('isr', isr_plan(48, 32, 'symmetry'), [1, 20])
+    FIXTURES['isr_split_48x32'] = ('isr_split', isr_plan(48, 32, 'split'), [1, 20])
     FIXTURES['ewc_wenoz5_32'] = ('ewc', ewc_plan(32), [1, 10])
     FIXTURES['ewc_teno5_32'] = ('ewc_teno5', ewc_plan(32, 'teno'), [1, 10])
     FIXTURES['trans_40x30x8'] = ('trans', trans_plan(40, 30, 8), [1, 5, 20])
@@ -310,7 +317,7 @@ def main():
                 out['field_BF_amp'] = 2.5e-3 * np.exp(-(rx['x0'] - 20.0) ** 2 - (rx['x1'] - 4.0) ** 2) * np.cos(0.23 * rx['x2'])
         out['q0'] = np.stack([r[f][inner] for f in fields])
         for n in steps:
-            stats = STATS if config.endswith('_stats') else []
+            stats = STATS if config.endswith('_stats') else ['rho_filt', 'rhou0_filt', 'rhou1_filt', 'rhoE_filt'] if config.endswith('_sfd') else []
             r = run_ref(config, dict(env_params(plan), niter=n), fields + stats, dump_all=bool(stats))
             out['q%d' % n] = np.stack([r[f][inner] for f in fields])
             for s in stats:

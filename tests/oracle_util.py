@@ -11,7 +11,7 @@ ORACLE_DIR = os.path.join(REPO, 'oracle')
 REF_DIR = os.path.join(ORACLE_DIR, '_ref')
 
 CONV = {'central': 0, 'weno': 1, 'teno': 2}
-BC = {'periodic': 0, 'dirichlet': 1, 'exchange': 2, 'open': 2, 'isothermal_wall': 3, 'extrapolation': 4,
+BC = {'periodic': 0, 'dirichlet': 1, 'exchange': 2, 'open': 2, 'split': 14, 'isothermal_wall': 3, 'extrapolation': 4,
       'inlet_pressure_extrapolate': 5, 'symmetry': 6, 'dirichlet_field': 7, 'adiabatic_wall': 8,
       'zero_gradient_outlet': 9, 'pressure_outlet': 10, 'inviscid_wall': 11}
 MU = {'constant': 0, 'sutherland': 1, 'power': 2}
@@ -44,7 +44,10 @@ class OsboCfg(ctypes.Structure):
                 ('extrap_order', (ctypes.c_int * 2) * 3), ('bc_face', (ctypes.POINTER(ctypes.c_double) * 2) * 3),
                 ('force', ctypes.c_double * 3), ('bc_free', (ctypes.c_int * 2) * 3), ('src_amp', ctypes.POINTER(ctypes.c_double)), ('src_rate', ctypes.c_double),
                 ('src_iter0', ctypes.c_int), ('curv_D', (ctypes.POINTER(ctypes.c_double) * 3) * 3),
-                ('curv_detJ', ctypes.POINTER(ctypes.c_double)), ('back_pressure', ctypes.c_double), ('central_form', ctypes.c_int)]
+                ('curv_detJ', ctypes.POINTER(ctypes.c_double)), ('back_pressure', ctypes.c_double),
+                ('split_n', (ctypes.c_int * 2) * 3), ('split_kind', ((ctypes.c_int * 8) * 2) * 3), ('split_lo', (((ctypes.c_int * 3) * 8) * 2) * 3),
+                ('split_hi', (((ctypes.c_int * 3) * 8) * 2) * 3), ('split_order', ((ctypes.c_int * 8) * 2) * 3), ('split_q', (((ctypes.c_double * 5) * 8) * 2) * 3),
+                ('central_form', ctypes.c_int)]
 
 
 _lib = None
@@ -106,6 +109,16 @@ def make_cfg(plan):
                 c.bc_free[d][s] = sum(1 << m for m in b.get('free', [])) | (256 if b.get('ke_free') else 0)
             if b['type'] == 'extrapolation':
                 c.extrap_order[d][s] = int(b.get('order', 0))
+            if b['type'] == 'split':
+                c.split_n[d][s] = len(b['parts'])
+                for n, part in enumerate(b['parts']):
+                    c.split_kind[d][s][n] = BC[part['type']]
+                    c.split_order[d][s][n] = int(part.get('order', 0))
+                    for e in range(3):
+                        c.split_lo[d][s][n][e] = part['range'][2 * e] if e < plan['ndim'] else 0
+                        c.split_hi[d][s][n][e] = part['range'][2 * e + 1] if e < plan['ndim'] else 1
+                    for m, v in enumerate(part.get('q', ())):
+                        c.split_q[d][s][n][m] = v
             if b.get('closure'):
                 c.closure[d][s] = 1
                 cl = plan['closures'][b['closure']] if 'closures' in plan else CLOSURES[b['closure']]

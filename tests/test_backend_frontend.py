@@ -55,6 +55,19 @@ APPS = {
                             [("boundaries[direction][side] = SymmetryBC(direction, side)",
                               "from opensbli.core.boundary_conditions.inviscid_wall import InviscidWallBC\nboundaries[direction][side] = InviscidWallBC(direction, side)"),
                              ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None, {'OSB_GENERIC_BC': 'Symmetry,Extrapolation,Dirichlet'}),
+    # SplitBC (bc_core.py:200-217): the bottom wall of the shock reflection shared by a SymmetryBC and an InviscidWallBC; each part
+    # becomes a run-time compiled kernel whose range comes from the integer arrays the user fills in in opensbli.cpp
+    'isr_split': (REF + '/apps/inviscid_shock_reflection/inviscid_shock.py',
+                  [("boundaries[direction][side] = SymmetryBC(direction, side)",
+                    "from opensbli.core.boundary_conditions.inviscid_wall import InviscidWallBC\nfrom opensbli.core.boundary_conditions.bc_core import SplitBC\n"
+                    "boundaries[direction][side] = SplitBC(direction, side, [SymmetryBC(direction, side), InviscidWallBC(direction, side)])"),
+                   ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),
+    # selective frequency damping (filters/SFD.py) on the Katzer app: a cold user kernel + an in-loop user kernel that writes the state
+    'katzer_sfd': (REF + '/apps/katzer_SBLI/katzer_SBLI.py',
+                   [("block.set_equations([constituent, simulation_eq, initial, metriceq])",
+                     "from opensbli.filters.SFD import SFD\nsfd = SFD(block, chifilt=0.1, omegafilt=1.0/0.75)\n"
+                     "block.set_equations([constituent, simulation_eq, initial, metriceq] + sfd.equation_classes)"),
+                    ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'katzer_60x40'),
     # InletTransferBC has no hand-written kernel: generic by itself (Sod with the left boundary copied from its first halo point)
     'sod_inlet_transfer': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("boundaries += [DirichletBC(direction, 0, left_eqns)]", "boundaries += [InletTransferBC(direction, 0)]"),
                                                                             ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),

@@ -146,6 +146,31 @@ def test_channel_app_with_statistics_as_shipped():
         assert np.abs(stats[n] - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), n
 
 
+def test_katzer_app_with_sfd_filter():
+    """Selective frequency damping (filters/SFD.py) on the Katzer app: `User kernel: Initialize the filter` runs once on the cold
+    path (filtered state <- state, uploaded with the plan), `User kernel: Apply the filter` at the end of every iteration
+    relaxes the conserved arrays towards the filtered copy -- a run-time compiled kernel that WRITES the state.  10 steps
+    against the reference's own run of the same program (state and filtered state)."""
+    from opensbli_b200 import run as R, Simulation
+    over = {'block0np0': 60, 'block0np1': 40, 'niter': 10}
+    plan_sym, env, plan, cold = R.load_case(os.path.join(PLANS, 'katzer_sfd'), overrides=over)
+    assert [k['name'] for k in plan_sym['user_kernels']] == ['User kernel: Apply the filter'] and 'rho_filt' in plan['user_fields']
+    z = np.load(os.path.join(os.path.dirname(PLANS), 'apps', 'katzer_sfd_60x40.npz'))
+    plain = load_fixture('katzer_60x40')[1][10]
+    q0 = R.initial_state(plan_sym, cold)
+    with Simulation(plan) as sim:
+        sim.set_state(q0)
+        sim.step(10)
+        q = inner(plan, sim.get_state())
+        filt = {n: sim.download(n)[5:-5, 5:-5] for n in ('rho_filt', 'rhou0_filt', 'rhou1_filt', 'rhoE_filt')}
+    err = field_errors(plan, q, z['q10'])
+    print('katzer + SFD', err)
+    assert max(err) < 1e-11, err
+    for n, a in filt.items():
+        assert np.abs(a - z['stat_' + n]).max() <= 1e-11 * max(1.0, np.abs(z['stat_' + n]).max()), n
+    assert max(field_errors(plan, z['q10'], plain)) > 1e-5          # and the filter is visible in the state
+
+
 def test_turbulent_3d_app_as_shipped_with_monitor(tmp_path):
     """apps/channel_flow/turbulent_3D/turbulent_channel.py as shipped (uniform grid, Feiereisen split, statistics user kernels,
     SimulationMonitor): 500 iterations on a small grid, probe lines written at iterations 1, 250, 500; the last line equals the
@@ -247,6 +272,68 @@ def test_run_time_compiled_boundary_kernels_match_reference(name, fixture, sizes
     err = field_errors(plan, inner(plan, q), states[nsteps])
     print(name, nsteps, err)
     assert max(err) < max(tol_for(plan, nsteps), 1e-12 * nsteps), err
+
+
+def test_split_boundary_from_the_front_end_matches_reference():
+    """SplitBC (bc_core.py:200-217): the shock reflection's bottom wall shared by SymmetryBC (x-points below 20) and InviscidWallBC.
+    The plan the back end distils carries one run-time compiled kernel per part; their ranges are the integer arrays the user
+    fills in in opensbli.cpp (here: the values oracle/gen_ref.py CPP_EDITS gives the reference's own program) -- 20 steps against
+    the reference's golden states; a parameter file with the arrays left as `Input` is refused."""
+    from opensbli_b200 import run as R, Simulation
+    from common import tol_for
+    over = {'block0np0': 48, 'block0np1': 32}
+    with pytest.raises(ValueError, match='split_range_100'):
+        R.load_case(os.path.join(PLANS, 'isr_split'), overrides=over)
+    over.update(split_range_100=[0, 20, 0, 1], split_halo_range_100=[-3, 0, 0, 0], split_range_101=[20, 48, 0, 1], split_halo_range_101=[0, 4, 0, 0])
+    plan_sym, env, plan, cold = R.load_case(os.path.join(PLANS, 'isr_split'), overrides=over)
+    assert plan['bc'][1][0]['type'] == 'generic' and [k['range'] for k in plan['user_kernels']] == [[-3, 20, 0, 1], [20, 52, 0, 1]]
+    want, states = load_fixture('isr_split_48x32')
+    q0 = R.initial_state(plan_sym, cold)
+    with Simulation(plan) as sim:
+        sim.set_state(q0)
+        sim.step(20)
+        q = sim.get_state()
+    err = field_errors(plan, inner(plan, q), states[20])
+    print('isr_split', err)
+    assert max(err) < max(tol_for(plan, 20), 2e-11), err
+
+
+GENERIC_CASES = [('sod_zgo_generic', 'sod_zgo_n200', {'block0np0': 200}), ('sod_pout_generic', 'sod_pout_n200', {'block0np0': 200}),
+                 ('isr_invwall_generic', 'isr_invwall_48x32', {'block0np0': 48, 'block0np1': 32}),
+                 ('isr_split', 'isr_split_48x32', dict(block0np0=48, block0np1=32, split_range_100=[0, 20, 0, 1], split_halo_range_100=[-3, 0, 0, 0],
+                                                       split_range_101=[20, 48, 0, 1], split_halo_range_101=[0, 4, 0, 0]))]
+
+
+@pytest.mark.parametrize('name,fixture,over', GENERIC_CASES, ids=[c[0] for c in GENERIC_CASES])
+def test_run_time_compiled_boundary_kernels_on_perturbed_state(name, fixture, over):
+    """The short runs above leave most boundary formulas without signal (uniform flow along the wall: an inviscid wall and a
+    symmetry plane give the same state).  Here one boundary-condition pass of the plan the front end distilled -- run-time
+    compiled kernels -- is applied to a randomly perturbed state and compared with the oracle's pass over the same state under
+    the hand-written plan of the fixture (hand-written boundary functions, SplitBC parts included)."""
+    import ctypes
+    import oracle_util as ou
+    from opensbli_b200 import run as R, Simulation
+    plan_sym, env, plan, cold = R.load_case(os.path.join(PLANS, name), overrides=over)
+    assert any(b['type'] == 'generic' for pair in plan['bc'] for b in pair)
+    want, _ = load_fixture(fixture)
+    rng = np.random.default_rng(11)
+    q0 = R.initial_state(plan_sym, cold)
+    nd = plan['ndim']
+    for m, a in enumerate(q0):
+        a *= 1.0 + 0.05 * rng.standard_normal(a.shape)
+        if 1 <= m <= nd:
+            a += 0.05 * rng.standard_normal(a.shape)
+    cfg = ou.make_cfg(want)
+    P = ctypes.POINTER(ctypes.c_double)
+    qo = [a.copy() for a in q0]
+    ou.oracle_lib().osbo_apply_bcs(ctypes.byref(cfg), (P * len(qo))(*[a.ctypes.data_as(P) for a in qo]))
+    with Simulation(plan) as sim:
+        sim.set_state(q0)
+        sim.apply_bcs()
+        qb = sim.get_state()
+    assert sum(int(np.count_nonzero(b != a)) for a, b in zip(q0, qo)) > 0
+    for a, b in zip(qb, qo):
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-14), name
 
 
 def test_inlet_transfer_boundary_kernel():

@@ -55,6 +55,26 @@ def test_plan_roundtrip_and_validation():
     assert p2['np'] == [32, 32, 32] and p2['constants']['dt'] == 1e-3 and plan['np'] == [16, 16, 16]
 
 
+def test_split_face_plan_text_and_validation():
+    """SplitBC faces (bc_core.py:200-217): parts serialised in order; a part must be one plane thick at its face, inside the
+    padded block, of a boundary class with a plane kernel"""
+    import copy
+    from opensbli_b200 import plan as P
+    plan, _ = load_fixture('isr_split_48x32')
+    plan = {k: v for k, v in plan.items() if k not in ('q0_padded', 'fields')}
+    txt = P.to_text(plan)
+    assert 'bc 1 0 split\nbc_part 1 0 symmetry -3 20 0 1 0\nbc_part 1 0 inviscid_wall 20 52 0 1 0\n' in txt
+    for edit in (lambda b: b['parts'][0].update(range=[-3, 20, 0, 2]),            # two planes along the normal
+                 lambda b: b['parts'][0].update(range=[-3, 20, 1, 2]),            # not the boundary plane
+                 lambda b: b['parts'][1].update(range=[20, 60, 0, 1]),            # outside the padded block
+                 lambda b: b['parts'][1].update(type='periodic'),
+                 lambda b: b.update(parts=[])):
+        bad = copy.deepcopy(plan)
+        edit(bad['bc'][1][0])
+        with pytest.raises(P.PlanError, match='split bc'):
+            P.to_text(bad)
+
+
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure: nothing under opensbli_b200/ may reference it."""
     for root, _, files in os.walk(os.path.join(REPO, 'opensbli_b200')):
