@@ -916,13 +916,21 @@ def extract_plan(algorithm):
             monitor = {'arrays': [_strip(m.flow_var) for m in c.monitors],
                        'probes': [[str(x) for x in (m.probe_loc if isinstance(m.probe_loc, (tuple, list)) else (m.probe_loc,))] for m in c.monitors],
                        'frequency': int(c.frequency), 'precision': int(c.fp_precision), 'output_file': c.output_file}
+    # loops of UserDefinedEquations (utilities/user_defined_kernels.py): `User kernel: <name>` and, when their equations hold
+    # derivatives, the `UserDefinedEquations CD ...` / `UserDefinedEquations evaluation` loops that evaluate those first
+    # (statistics, SFD, the WENO filter's sensor): compiled at run time, launched in program order at the end of the iteration
     user = []
+    is_user = lambda c: type(c).__name__ == 'Kernel' and _name(c).startswith(('User kernel', 'UserDefinedEquations'))
     for c in in_iter:
-        if type(c).__name__ == 'Kernel' and _name(c).startswith('User kernel'):
+        if is_user(c):
             user.append(_user_kernel(c, 'iteration_end', stencil=True))
+        elif type(c).__name__ == 'Kernel' and not (' boundary dir' in _name(c) or _SPLIT_BC.match(_name(c)) or _name(c) == 'Save equations'):
+            raise UnsupportedByB200('loop outside the accelerated hot path at iteration level: %s' % _name(c))
     for c in after:
-        if type(c).__name__ == 'Kernel' and _name(c).startswith('User kernel'):
+        if is_user(c):
             user.append(_user_kernel(c, 'after_loop', stencil=True))
+        elif type(c).__name__ == 'Kernel':
+            raise UnsupportedByB200('loop after the time loop is not implemented: %s' % _name(c))
     # components of the program that are not part of the per-step hot path (file output, monitors, timers): not executed
     # by the B200 run-time; listed in the plan and printed so that nothing is dropped silently
     plan['not_executed'] = sorted(set(type(c).__name__ for c in in_iter + after + before
@@ -961,7 +969,7 @@ def extract_plan(algorithm):
     if source_kernel is not None:
         cr.remove(source_kernel)
     def _generic_bc(c):           # boundary kernels that will be compiled at run time carry their own constants
-        if _SPLIT_BC.match(_name(c) or '') or (_name(c) or '').startswith('User kernel'):
+        if _SPLIT_BC.match(_name(c) or '') or (_name(c) or '').startswith(('User kernel', 'UserDefinedEquations')):
             return True
         m = re.match(r'(\w+) boundary dir(\d) side(\d)', _name(c) or '')
         return bool(m) and (m.group(1) not in NATIVE_BCS or m.group(1) in GENERIC_BCS)
@@ -1024,6 +1032,7 @@ def extract_plan(algorithm):
 
     # ---- boundary conditions, from the iteration-start list (algorithm.py:442)
     bc = [[None, None] for _ in range(ndim)]
+    halo_depths = {}
     for c in [c for c in in_iter if type(c).__name__ == 'ExchangeSelf' or ' boundary dir' in _name(c) or _SPLIT_BC.match(_name(c) or '')]:
         ms = _SPLIT_BC.match(_name(c) or '')
         if ms:
@@ -1044,6 +1053,7 @@ def extract_plan(algorithm):
                 raise UnsupportedByB200('periodic exchange of %s (expected the conserved arrays)' % arrays)
             side = {'left': 0, 'right': 1}.get(c.side, c.side)
             bc[int(c.direction)][int(side)] = {'type': 'periodic'}
+            halo_depths.setdefault(int(side), set()).add(int(c.transfer_size[int(c.direction)]))   # periodic.py:42-56: hm planes go up, hp down
             continue
         m = re.match(r'(\w+) boundary dir(\d) side(\d)', _name(c))
         kind, d, sd = m.group(1), int(m.group(2)), int(m.group(3))
@@ -1094,6 +1104,16 @@ def extract_plan(algorithm):
     if any(b is None for pair in bc for b in pair):
         raise UnsupportedByB200('a block face has no recognised boundary condition')
     plan['bc'] = bc
+    # depth of the halos the boundary conditions fill: the scheme's own (2/2 central, 3/4 WENO/TENO) unless the block has further
+    # consumers (block.shock_filter: a WENO filter on a central scheme makes the exchanges 3/4 deep)
+    if halo_depths:
+        if any(len(v) != 1 for v in halo_depths.values()) or set(halo_depths) != {0, 1}:
+            raise UnsupportedByB200('periodic exchanges of different depths: %s' % halo_depths)
+        depth = (halo_depths[0].pop(), halo_depths[1].pop())
+        if depth != ((2, 2) if plan['conv'] == 'central' else (3, 4)):
+            if not (2 <= depth[0] <= 5 and 2 <= depth[1] <= 5):
+                raise UnsupportedByB200('halo depth %s' % (depth,))
+            plan['halos'] = list(depth)
 
     # ---- cold kernels before the time loop (initialisation, metric evaluation, metric boundaries), in program order
     cold = []

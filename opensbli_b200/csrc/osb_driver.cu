@@ -66,6 +66,7 @@ struct Plan {
   bool metric[3] = {false, false, false};
   bool teno_adaptive = false;
   bool forcing = false;
+  int halo_m = 0, halo_p = 0; // depth of the boundary / exchange halos when it is not the scheme's own (0: 2/2 central, 3/4 WENO / TENO)
   int central_form = 0;      // 0 Blaisdell skew form, 1 Feiereisen quadratic split
   bool curvilinear = false;  // full metric tensor D_ij + detJ (2-D strong-conservation form)
   bool mass_source = false;  // Residual_rho += BF_amp(x) sin(src_rate * iteration)
@@ -121,7 +122,7 @@ struct osb_ctx {
   long long graph_launches = 0;
   bool use_graph = true;
   long long iteration = 0;                      // loop counter of algorithm.py:440-474 (argument of the mass source)
-  struct UserKernel { cudaLibrary_t lib = nullptr; cudaKernel_t kern = nullptr; std::vector<std::string> fields; int range[6]; int when = 0; };
+  struct UserKernel { cudaLibrary_t lib = nullptr; cudaKernel_t kern = nullptr; std::vector<std::string> fields; int range[6]; int when = 0; bool writes_state = false; };
   std::vector<UserKernel> user_kernels;
   unsigned long long *slow_count = nullptr;     // bench instrumentation (osb_slow_path_count)
   bool count_slow = false;
@@ -167,6 +168,7 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
     else if (key == "weno_formulation") { std::string v; ls >> v; P.weno_z = (v == "Z"); }
     else if (key == "averaging") { std::string v; ls >> v; P.averaging = v == "roe" ? AVG_ROE : AVG_SIMPLE; }
     else if (key == "viscous") { int v; ls >> v; P.viscous = v != 0; }
+    else if (key == "halos") { ls >> P.halo_m >> P.halo_p; if (P.halo_m < 2 || P.halo_p < 2 || P.halo_m > 5 || P.halo_p > 5) { err = "halos must lie in 2..5"; return false; } }
     else if (key == "rk") { std::string v; ls >> v; P.rk = v == "sbli" ? RK_SBLI : RK_LS; }
     else if (key == "rk_a") { double v; while (ls >> v) P.rk_a.push_back(v); }
     else if (key == "rk_b") { double v; while (ls >> v) P.rk_b.push_back(v); }
@@ -268,6 +270,7 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
 }
 
 void scheme_halos(const Plan &P, int &hm, int &hp) {
+  if (P.halo_m > 0) { hm = P.halo_m; hp = P.halo_p; return; }     // set by the plan: a block with further consumers of the halos (filters)
   if (P.conv == CONV_CENTRAL) { hm = 2; hp = 2; } else { hm = 3; hp = 4; }
 }
 
@@ -766,6 +769,7 @@ int run_user_kernels(osb_ctx *c, int when) {
     dim3 bl(128, 1, 1), gr((n[0] + 127) / 128, n[1], n[2]);
     Launcher L(c, OSB_FAM_USER);
     OSB_CUDA(c, cudaLaunchKernel((const void *)k.kern, gr, bl, args, 0, c->stream));
+    if (k.writes_state) c->prim_stale = true;
   }
   return 0;
 }
@@ -1046,6 +1050,9 @@ int osb_add_user_kernel(osb_ctx *c, const char *source, const char *entry, const
       written.push_back(w);
     }
   }
+  // a kernel that writes a conserved array (filters: SFD, the WENO filter) leaves the primitive arrays behind the state
+  for (size_t i = 0; i < k.fields.size(); i++)
+    if (written[i]) { Field *f = find_field(c, k.fields[i].c_str()); for (int m = 0; f && m < c->plan.nd + 2; m++) k.writes_state = k.writes_state || f->dev == c->fp.q[m] || f->dev == c->fp.R[m]; }
   if (k.fields.size() > OSB_MAX_USER_FIELDS) return fail(c, "user kernel uses too many arrays");
   for (size_t i = 0; i < k.fields.size(); i++)
     if (!find_field(c, k.fields[i].c_str())) {

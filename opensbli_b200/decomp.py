@@ -25,6 +25,8 @@ from . import plan as _plan
 
 def scheme_halos(plan):
     """(halo_m, halo_p) of the spatial scheme: WENO/TENO 3/4 (weno.py:17-32, teno.py:18-36), central 2/2."""
+    if plan.get('halos'):
+        return tuple(plan['halos'])
     return (2, 2) if plan['conv'] == 'central' else (3, 4)
 
 

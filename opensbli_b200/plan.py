@@ -14,6 +14,8 @@ JSON-able dict; `to_text` serialises it to the line format parsed by the C ABI (
     weno_formulation 'JS' | 'Z'
     averaging       'roe' | 'simple'              RoeAverage / SimpleAverage
     viscous         bool                          constant-viscosity Navier-Stokes terms (Central / StoreSome)
+    halos           optional [hm, hp]             depth of the boundary / periodic halos when the block has consumers beyond the
+                                                  scheme itself (a WENO filter on a central scheme: 3, 4); default 2/2 central, 3/4 WENO/TENO
     rk              'ls' | 'sbli'                 RungeKuttaLS / RungeKutta
     rk_a, rk_b      stage coefficients            LS: A, B ; SBLI: rkold, rknew
     constants       {name: float}                 gama, Minf, Re, Pr, dt, eps, TENO_CT, ...
@@ -133,7 +135,7 @@ def to_text(plan):
          'conv %s' % plan['conv'], 'order %d' % plan['order'],
          'weno_formulation %s' % plan.get('weno_formulation', 'JS'),
          'averaging %s' % plan.get('averaging', 'roe'),
-         'viscous %d' % (1 if plan.get('viscous') else 0),
+         'viscous %d' % (1 if plan.get('viscous') else 0)] + (['halos %d %d' % tuple(plan['halos'])] if plan.get('halos') else []) + [
          'rk %s' % plan['rk'],
          'rk_a ' + ' '.join(_f(v) for v in plan['rk_a']),
          'rk_b ' + ' '.join(_f(v) for v in plan['rk_b'])]

@@ -163,7 +163,7 @@ def user_kernel_source(k, index, env, nd):
     for n, name in enumerate(fields):
         L.append('  double *%s = f.p[%d];' % (name, n))
     for name in dict.fromkeys(k['locals']):
-        L.append('  double %s;' % name)
+        L.append('  double %s = 0.0;' % name)       # kernel locals start at zero, as in the reference's generated C (opsc.py:340-343)
     for st in k['statements']:
         lhs, is_field, rhs = st[0], st[1], st[2]
         at = (st[3] if len(st) > 3 and st[3] else 'X')            # relative write (boundary kernels): index printed by the back end
@@ -183,7 +183,7 @@ def resolve(plan_sym, env):
     metric fields, tabulated Dirichlet states); returns (plan, ColdRunner holding every cold dataset)."""
     nd = plan_sym['ndim']
     p = {k: plan_sym[k] for k in ('ndim', 'conv', 'order', 'weno_formulation', 'averaging', 'viscous', 'rk', 'rk_a', 'rk_b')}
-    for k in ('viscosity', 'metric_fields', 'teno_adaptive', 'closures', 'forcing', 'central_form', 'curvilinear'):   # copied verbatim
+    for k in ('viscosity', 'metric_fields', 'teno_adaptive', 'closures', 'forcing', 'central_form', 'curvilinear', 'halos'):   # copied verbatim
         if k in plan_sym:
             p[k] = plan_sym[k]
     p['np'] = [int(env['block0np%d' % d]) for d in range(nd)]

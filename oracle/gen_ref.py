@@ -51,6 +51,12 @@ CONFIGS = {
                   "boundaries[direction][side] = SplitBC(direction, side, [SymmetryBC(direction, side), InviscidWallBC(direction, side)])")]),
     # config 2: shipped TGV app (central-4 + RK3)
     'tgv_central4': (REF + '/apps/taylor_green_vortex/taylor_green_vortex.py', []),
+    # the same with the non-linear WENO filter (filters/WENO_filter.py) applied after every step of the central scheme: characteristic
+    # WENO5 reconstruction of the dissipative flux part in the three directions, Ducros sensor, filter application -- all
+    # UserDefinedEquations loops at the end of the iteration; the exchanges become 3/4 planes deep
+    'tgv_wf': (REF + '/apps/taylor_green_vortex/taylor_green_vortex.py', [("block.set_equations([copy.deepcopy(constituent), copy.deepcopy(simulation_eq), initial])",
+               "from opensbli.filters.WENO_filter import WENOFilter\nwf = WENOFilter(block, order=5)\n"
+               "block.set_equations([copy.deepcopy(constituent), copy.deepcopy(simulation_eq), initial] + wf.equation_classes)")]),
     # config 3/5: TGV TENO5 + StoreSome + RK-LS (our app script, reference front end + OPSC back end)
     'tgv_teno5': (REPO + '/apps/tgv_teno5.py', []),
     # config 4: shipped Katzer SBLI app (ReducedAccess closures) and a variant with the default Carpenter closures

@@ -37,6 +37,7 @@ long osbo_padded_size(const osbo_cfg *c) { grid_t g; grid_init(c, &g); return g.
 
 /* scheme halos: WENO/TENO [-3,4] (weno.py:17-32, teno.py:18-36), central +-2 (scheme.py:32-44) */
 static void scheme_halos(const osbo_cfg *c, int *hm, int *hp) {
+  if (c->halo_m > 0) { *hm = c->halo_m; *hp = c->halo_p; return; }   /* block with further consumers of the halos (block.shock_filter: 3/4 on a central scheme) */
   if (c->conv == OSBO_CONV_CENTRAL) { *hm = 2; *hp = 2; } else { *hm = 3; *hp = 4; }
 }
 

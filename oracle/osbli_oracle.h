@@ -95,6 +95,7 @@ typedef struct {
   int split_lo[3][2][8][3], split_hi[3][2][8][3];
   int split_order[3][2][8];   /* extrapolation order of a part */
   double split_q[3][2][8][5]; /* Dirichlet state of a part */
+  int halo_m, halo_p;         /* depth of the boundary / periodic halos when not the scheme's own (0: default) */
   int central_form;           /* Central(4) convective split: 0 Blaisdell skew form (taylor_green_vortex.py:8-11, laminar_channel.py:7-9),
                                * 1 Feiereisen quadratic split (compressible_TCF_Central/turbulent_channel.py:12-20) */
 } osbo_cfg;

@@ -130,6 +130,8 @@ def katzer_wenoz_plan(N0, N1):
 # the Katzer app with the SFD filter (filters/SFD.py) switched on: golden states of an APP run (its user kernels change the state, which
 # the oracle does not model), kept under golden/apps/ so that the fixture-driven oracle tests do not pick it up
 FIXTURES['apps/katzer_sfd_60x40'] = ('katzer_sfd', katzer_plan(60, 40), [10])
+# the central-4 TGV with the non-linear WENO filter (filters/WENO_filter.py) after every step: an APP run as well
+FIXTURES['apps/tgv_wf_16'] = ('tgv_wf', tgv_plan(16, 'central', 4, SBLI3), [1, 3])
 FIXTURES['katzer_wenoz_60x40'] = ('katzer_wenoz', katzer_wenoz_plan(60, 40), [1, 10])
 
 
@@ -317,7 +319,7 @@ def main():
                 out['field_BF_amp'] = 2.5e-3 * np.exp(-(rx['x0'] - 20.0) ** 2 - (rx['x1'] - 4.0) ** 2) * np.cos(0.23 * rx['x2'])
         out['q0'] = np.stack([r[f][inner] for f in fields])
         for n in steps:
-            stats = STATS if config.endswith('_stats') else ['rho_filt', 'rhou0_filt', 'rhou1_filt', 'rhoE_filt'] if config.endswith('_sfd') else []
+            stats = STATS if config.endswith('_stats') else ['rho_filt', 'rhou0_filt', 'rhou1_filt', 'rhoE_filt'] if config.endswith('_sfd') else ['kappa'] if config.endswith('_wf') else []
             r = run_ref(config, dict(env_params(plan), niter=n), fields + stats, dump_all=bool(stats))
             out['q%d' % n] = np.stack([r[f][inner] for f in fields])
             for s in stats:

@@ -47,7 +47,7 @@ class OsboCfg(ctypes.Structure):
                 ('curv_detJ', ctypes.POINTER(ctypes.c_double)), ('back_pressure', ctypes.c_double),
                 ('split_n', (ctypes.c_int * 2) * 3), ('split_kind', ((ctypes.c_int * 8) * 2) * 3), ('split_lo', (((ctypes.c_int * 3) * 8) * 2) * 3),
                 ('split_hi', (((ctypes.c_int * 3) * 8) * 2) * 3), ('split_order', ((ctypes.c_int * 8) * 2) * 3), ('split_q', (((ctypes.c_double * 5) * 8) * 2) * 3),
-                ('central_form', ctypes.c_int)]
+                ('halo_m', ctypes.c_int), ('halo_p', ctypes.c_int), ('central_form', ctypes.c_int)]
 
 
 _lib = None
@@ -135,6 +135,8 @@ def make_cfg(plan):
     c.Twall = k.get('Twall', 1.0)
     c.back_pressure = k.get('back_pressure', 0.0)
     c.central_form = {'blaisdell': 0, 'feiereisen': 1}[plan.get('central_form', 'blaisdell')]
+    if plan.get('halos'):
+        c.halo_m, c.halo_p = plan['halos']
     if plan.get('forcing'):
         for d in range(plan['ndim']):
             c.force[d] = k.get('c%d' % d, 0.0)

@@ -68,6 +68,12 @@ APPS = {
                      "from opensbli.filters.SFD import SFD\nsfd = SFD(block, chifilt=0.1, omegafilt=1.0/0.75)\n"
                      "block.set_equations([constituent, simulation_eq, initial, metriceq] + sfd.equation_classes)"),
                     ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], 'katzer_60x40'),
+    # the non-linear WENO filter (filters/WENO_filter.py) after every step of the central-4 TGV: 15 UserDefinedEquations loops
+    'tgv_wf': (REF + '/apps/taylor_green_vortex/taylor_green_vortex.py',
+               [("block.set_equations([copy.deepcopy(constituent), copy.deepcopy(simulation_eq), initial])",
+                 "from opensbli.filters.WENO_filter import WENOFilter\nwf = WENOFilter(block, order=5)\n"
+                 "block.set_equations([copy.deepcopy(constituent), copy.deepcopy(simulation_eq), initial] + wf.equation_classes)"),
+                ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),
     # InletTransferBC has no hand-written kernel: generic by itself (Sod with the left boundary copied from its first halo point)
     'sod_inlet_transfer': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("boundaries += [DirichletBC(direction, 0, left_eqns)]", "boundaries += [InletTransferBC(direction, 0)]"),
                                                                             ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),
