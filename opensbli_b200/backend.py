@@ -136,7 +136,9 @@ def _user_kernel(kernel, when, stencil=False, thin_direction=None):
     pr = P({'precision': 17})
     out, reads, writes, local = [], [], [], []
     roff, woff = {}, {}
-    for e in kernel.equations:
+    indexed = {}                  # IndexedConstants of the kernel (rkA[stage], ...): name -> values
+
+    def one(e):
         if not hasattr(e, 'lhs'):
             raise UnsupportedByB200('user kernel %s: unsupported equation %r' % (_name(kernel), e))
         for ds in e.rhs.atoms(DataSet):
@@ -154,6 +156,30 @@ def _user_kernel(kernel, when, stencil=False, thin_direction=None):
         else:
             local.append(str(e.lhs))
             out.append([str(e.lhs), False, pr.doprint(e.rhs), None])
+
+    def condition(c):
+        for ds in c.atoms(DataSet):
+            n = _strip(ds.base)
+            roff.setdefault(n, set()).add(index(ds)[1])
+            if n not in reads:
+                reads.append(n)
+        return pr.doprint(c)
+
+    for e in kernel.equations:
+        if type(e).__name__ == 'GroupedPiecewise':
+            # groups of equations under if / else if / else, printed as opsc.py:372-397 does
+            for i, (eqs, cond) in enumerate(e.args):
+                out.append(['#if' if i == 0 else '#else' if cond == True else '#elif', None, None if (i and cond == True) else condition(cond), None])   # noqa: E712
+                for q in (eqs if isinstance(eqs, (list, tuple)) or type(eqs).__name__ == 'Tuple' else [eqs]):
+                    one(q)
+            out.append(['#end', None, None, None])
+        else:
+            one(e)
+    for ic in getattr(kernel, 'IndexedConstants', []):
+        try:
+            indexed[str(ic.base.label)] = [float(v) for v in ic.value]
+        except Exception:
+            raise UnsupportedByB200('kernel %s: indexed constant %s has no values' % (_name(kernel), ic))
     rng = kernel.total_range()
     if stencil:
         # two different points p, p' of the range touch the same element iff p - p' = (read or write offset) - (write offset);
@@ -169,12 +195,14 @@ def _user_kernel(kernel, when, stencil=False, thin_direction=None):
                     if any(diff) and not any(diff[d] and thin[d] for d in range(3)):
                         raise UnsupportedByB200('kernel %s writes %s where a neighbouring point of its range reads or writes it (offsets %s / %s): '
                                                 'it cannot run one thread per point' % (_name(kernel), n, w, o))
-    consts = sorted(set(str(s) for e in kernel.equations for s in e.rhs.free_symbols
+    consts = sorted(set(str(s) for e in kernel.equations for s in (e.rhs if hasattr(e, 'rhs') else e).free_symbols
                         if type(s).__name__ == 'ConstantObject'))
     out_k = {'name': _name(kernel), 'when': when, 'range': [r if isinstance(r, str) else ccode(r) for r in rng], 'reads': reads,
              'writes': writes, 'locals': local, 'constants': consts, 'statements': out}
     if thin_direction is not None:
         out_k['one_plane_along'] = thin_direction
+    if indexed:
+        out_k['indexed_constants'] = indexed
     return out_k
 
 
@@ -860,11 +888,154 @@ def _const_value(c):
     return ccode(v)
 
 
+class _NotForGenericPath(UnsupportedByB200):
+    """Raised for programs neither path can run (precision, multi-block, input files): not retried on the generic path."""
+
+
 def extract_plan(algorithm):
-    """Distil the plan from an OpenSBLI algorithm object (see module docstring)."""
+    """Distil the plan from an OpenSBLI algorithm object (see module docstring).  Programs the hand-written kernels do not cover
+    (other scheme orders, fully curvilinear 3-D / viscous terms, loops of classes unknown here ...) fall back to the GENERIC
+    path: every loop of the time step is printed from its equations as CUDA C and compiled at run time, launched in program
+    order -- one thread per point, the reference's own arithmetic, at the speed of a plain loop-per-kernel code."""
+    import os
+    try:
+        return _extract_specialised(algorithm)
+    except _NotForGenericPath:
+        raise
+    except UnsupportedByB200 as e:
+        if os.environ.get('OSB_NO_GENERIC_PATH'):
+            raise
+        try:
+            plan = _extract_generic(algorithm, str(e))
+        except UnsupportedByB200 as e2:
+            raise UnsupportedByB200('%s -- and the generic path cannot run the program either: %s' % (e, e2))
+        print('B200: %s' % e)
+        print('B200: the program runs on the GENERIC path (every loop compiled at run time from its equations); expect the speed of '
+              'a loop-per-kernel code, not of the hand-written kernels')
+        return plan
+
+
+def _generic_exchange(c, when):
+    """A periodic self-exchange (exchange.py:9-57) as a printed copy kernel: over the destination box, a[X] = a[X + from - to]"""
+    from sympy.printing.c import ccode
+    arrays = [_strip(a) for a in c.transfer_arrays]
+    size, frm, to = [ccode(v) for v in c.transfer_size], [ccode(v) for v in c.transfer_from], [ccode(v) for v in c.transfer_to]
+    nd = len(size)
+    shift = ' + '.join('((%s) - (%s))%s' % (frm[d], to[d], ('', '*s1', '*s2')[d]) for d in range(nd))
+    rng = []
+    for d in range(nd):
+        rng += [to[d], '(%s) + (%s)' % (to[d], size[d])]
+    return {'name': 'exchange %s %s' % (getattr(c, 'direction', ''), getattr(c, 'side', '')), 'when': when, 'range': rng, 'reads': list(arrays),
+            'writes': list(arrays), 'locals': [], 'constants': [], 'statements': [[a, True, '%s[X + %s]' % (a, shift), 'X'] for a in arrays]}
+
+
+def _extract_generic(algorithm, reason):
+    from opensbli.core.kernel import ConstantsToDeclare
+    ndim = algorithm.block_descriptions[0].ndim
+    flat = []
+    _walk(algorithm.prg.components, flat)
+    plan = {'ndim': ndim, 'generic': {'reason': reason}, 'conv': 'generic', 'order': 0, 'viscous': False, 'averaging': 'roe', 'weno_formulation': 'JS'}
+    q_names = ['rho'] + ['rhou%d' % d for d in range(ndim)] + ['rhoE']
+    cold, user, io_specs, monitor = [], [], [], None
+    seen_loop = seen_stage = False
+    nstages = 0
+    halo_depths = {}
+    not_executed = set()
+    for path, c in flat:
+        loops = [type(p).__name__ for p in path]
+        t, n = type(c).__name__, _name(c)
+        nloops = loops.count('DoLoop')
+        if t == 'iohdf5':
+            spec = {'arrays': [_strip(a) for a in c.arrays], 'iotype': c.kwargs.get('iotype', 'write'), 'name': c.kwargs.get('name'),
+                    'filename': c.kwargs.get('filename')}
+            if spec['iotype'] == 'read':
+                raise UnsupportedByB200('initial data read from an HDF5 file: pass the file to the runner with --restart instead')
+            cond = [p_ for p_ in path if type(p_).__name__ == 'Condition']
+            if cond:
+                m = re.search(r'Mod\([^,]+,\s*(\d+)\)', str(cond[-1].condition))
+                if not m:
+                    raise UnsupportedByB200('output condition %s' % cond[-1].condition)
+                spec.update(when='in_loop', every=int(m.group(1)))
+            else:
+                spec['when'] = 'after' if (seen_loop or 'DoLoop' in loops) else 'before'
+            io_specs.append(spec)
+            seen_loop = seen_loop or 'Timers' in loops or nloops > 0
+            continue
+        seen_loop = seen_loop or 'Timers' in loops or nloops > 0
+        if t == 'SimulationMonitor':
+            monitor = {'arrays': [_strip(m.flow_var) for m in c.monitors],
+                       'probes': [[str(x) for x in (m.probe_loc if isinstance(m.probe_loc, (tuple, list)) else (m.probe_loc,))] for m in c.monitors],
+                       'frequency': int(c.frequency), 'precision': int(c.fp_precision), 'output_file': c.output_file}
+            continue
+        if t not in ('Kernel', 'ExchangeSelf'):
+            if t not in ('DoLoop', 'Timers', 'Condition'):
+                not_executed.add(t)
+            continue
+        if nloops == 0 and 'Timers' not in loops:
+            if seen_loop:                                           # after the time loop
+                if t != 'Kernel':
+                    raise UnsupportedByB200('exchange after the time loop')
+                user.append(_user_kernel(c, 'after_loop', stencil=True))
+            elif t == 'ExchangeSelf':
+                from sympy.printing.c import ccode
+                cold.append({'name': 'exchange', 'exchange': True, 'arrays': [_strip(a) for a in c.transfer_arrays],
+                             'size': [ccode(v) for v in c.transfer_size], 'from': [ccode(v) for v in c.transfer_from],
+                             'to': [ccode(v) for v in c.transfer_to]})
+            else:
+                cold.append(_cold_kernel(c))
+            continue
+        if nloops == 2:
+            seen_stage = True
+            stage_loop = [p_ for p_ in path if type(p_).__name__ == 'DoLoop'][-1]
+            nstages = int(stage_loop.loop.upper) - int(stage_loop.loop.lower) + 1
+            when = 'stage'
+        elif nloops == 1:
+            when = 'iteration_end' if seen_stage else 'iteration_start'
+        else:
+            raise UnsupportedByB200('loop nest deeper than iteration / stage: %s' % n)
+        if t == 'ExchangeSelf':
+            side = {'left': 0, 'right': 1}.get(c.side, c.side)
+            halo_depths.setdefault(int(side), set()).add(int(c.transfer_size[int(c.direction)]))
+            user.append(_generic_exchange(c, when))
+        else:
+            user.append(_user_kernel(c, when, stencil=True))
+    if not nstages:
+        raise UnsupportedByB200('no Runge-Kutta stage loop found in the program')
+    plan['generic']['nstages'] = nstages
+    plan.update(rk='ls', rk_a=[0.0] * nstages, rk_b=[0.0] * nstages)          # placeholders: the printed RK kernels carry their own coefficients
+    for k in user:
+        ic = k.get('indexed_constants', {})
+        if 'rkold' in ic:
+            plan['rk'] = 'sbli'
+    # halos the boundary kernels / exchanges fill (the specialised driver code is not used; the depth only sizes nothing here but is
+    # kept for the runner's dataset files)
+    depth = (3, 4)
+    if halo_depths and all(len(v) == 1 for v in halo_depths.values()) and set(halo_depths) == {0, 1}:
+        depth = (min(5, max(2, next(iter(halo_depths[0])))), min(5, max(2, next(iter(halo_depths[1])))))
+    plan['halos'] = list(depth)
+    plan['bc'] = [[{'type': 'open'}, {'type': 'open'}] for _ in range(ndim)]   # the boundary kernels are in the kernel lists
+    plan['cold'] = cold
+    plan['user_kernels'] = user
+    plan['io'] = io_specs
+    if monitor:
+        plan['monitor'] = monitor
+    plan['q_names'] = q_names
+    plan['not_executed'] = sorted(not_executed)
+    plan['constant_decls'] = []
+    for c in ConstantsToDeclare.constants:
+        if type(c).__name__ == 'ConstantObject':
+            plan['constant_decls'].append([str(c), 'int' if 'int' in str(c.datatype.opsc()).lower() else 'double', _const_value(c)])
+    arrays = [[str(c.base), 'int', 2 * ndim] for c in ConstantsToDeclare.constants
+              if type(c).__name__ == 'ConstantIndexed' and str(c.base).startswith(('split_range_', 'split_halo_range_'))]
+    if arrays:
+        plan['constant_array_decls'] = arrays
+    return plan
+
+
+def _extract_specialised(algorithm):
     from opensbli.core.kernel import ConstantsToDeclare
     if getattr(algorithm, 'MultiBlock', False) or len(algorithm.block_descriptions) != 1:
-        raise UnsupportedByB200('multi-block algorithms are not implemented')
+        raise _NotForGenericPath('multi-block algorithms are not implemented')
     # the kernels are fp64 only (the reference's `SimulationDataType.set_datatype(Double)`, datatypes.py:2-30)
     try:
         from opensbli.core.datatypes import SimulationDataType
@@ -873,7 +1044,7 @@ def extract_plan(algorithm):
         ctype = 'double'
     dt = algorithm.dtype if isinstance(algorithm.dtype, str) else getattr(algorithm.dtype, 'opsc', lambda: 'double')()
     if ctype != 'double' or str(dt).lower() != 'double':
-        raise UnsupportedByB200('datatype %s/%s: the B200 back end computes in double precision only' % (ctype, dt))
+        raise _NotForGenericPath('datatype %s/%s: the B200 back end computes in double precision only' % (ctype, dt))
     ndim = algorithm.block_descriptions[0].ndim
     flat = []
     _walk(algorithm.prg.components, flat)
@@ -936,8 +1107,8 @@ def extract_plan(algorithm):
     plan['not_executed'] = sorted(set(type(c).__name__ for c in in_iter + after + before
                                       if type(c).__name__ not in ('Kernel', 'ExchangeSelf', 'DoLoop', 'Timers', 'SimulationMonitor', 'Condition')))
     if any(sp_['iotype'] == 'read' for sp_ in io_specs):
-        raise UnsupportedByB200('initial data read from an HDF5 file by ops_decl_dat_hdf5 (iohdf5(iotype="read")): pass the file to the '
-                                'runner with --restart instead')
+        raise _NotForGenericPath('initial data read from an HDF5 file by ops_decl_dat_hdf5 (iohdf5(iotype="read")): pass the file to the '
+                                 'runner with --restart instead')
     plan['io'] = io_specs
     q_names = ['rho'] + ['rhou%d' % d for d in range(ndim)] + ['rhoE']
 

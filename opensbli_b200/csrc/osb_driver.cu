@@ -24,7 +24,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-enum ConvKind { CONV_CENTRAL = 0, CONV_WENO = 1, CONV_TENO = 2 };
+enum ConvKind { CONV_CENTRAL = 0, CONV_WENO = 1, CONV_TENO = 2, CONV_GENERIC = 3 /* every loop of the step is a run-time compiled kernel */ };
 enum RkKind { RK_SBLI = 0, RK_LS = 1 };
 enum BcKind { BC_PERIODIC = 0, BC_DIRICHLET = 1, BC_EXCHANGE = 2 /* neighbour rank owns the halo */, BC_ISOTHERMAL_WALL = 3,
               BC_EXTRAPOLATION = 4, BC_INLET_PRESSURE = 5, BC_SYMMETRY = 6, BC_DIRICHLET_FIELD = 7, BC_ADIABATIC_WALL = 8,
@@ -66,6 +66,7 @@ struct Plan {
   bool metric[3] = {false, false, false};
   bool teno_adaptive = false;
   bool forcing = false;
+  int generic_stages = 0;     // CONV_GENERIC: number of RK stages; the step is user kernels with when = 200 (iteration start), 209 (every stage), 210 + s
   int halo_m = 0, halo_p = 0; // depth of the boundary / exchange halos when it is not the scheme's own (0: 2/2 central, 3/4 WENO / TENO)
   int central_form = 0;      // 0 Blaisdell skew form, 1 Feiereisen quadratic split
   bool curvilinear = false;  // full metric tensor D_ij + detJ (2-D strong-conservation form)
@@ -163,11 +164,12 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
     else if (key == "ndim") ls >> P.nd;
     else if (key == "np") { for (int d = 0; d < P.nd; d++) ls >> P.np[d]; }
     else if (key == "delta") { for (int d = 0; d < P.nd; d++) ls >> P.delta[d]; }
-    else if (key == "conv") { std::string v; ls >> v; P.conv = v == "central" ? CONV_CENTRAL : v == "weno" ? CONV_WENO : v == "teno" ? CONV_TENO : -1; if (P.conv < 0) { err = "unknown conv scheme " + v; return false; } }
+    else if (key == "conv") { std::string v; ls >> v; P.conv = v == "central" ? CONV_CENTRAL : v == "weno" ? CONV_WENO : v == "teno" ? CONV_TENO : v == "generic" ? CONV_GENERIC : -1; if (P.conv < 0) { err = "unknown conv scheme " + v; return false; } }
     else if (key == "order") ls >> P.order;
     else if (key == "weno_formulation") { std::string v; ls >> v; P.weno_z = (v == "Z"); }
     else if (key == "averaging") { std::string v; ls >> v; P.averaging = v == "roe" ? AVG_ROE : AVG_SIMPLE; }
     else if (key == "viscous") { int v; ls >> v; P.viscous = v != 0; }
+    else if (key == "generic_stages") { ls >> P.generic_stages; if (P.generic_stages < 1 || P.generic_stages > 8) { err = "generic_stages must lie in 1..8"; return false; } }
     else if (key == "halos") { ls >> P.halo_m >> P.halo_p; if (P.halo_m < 2 || P.halo_p < 2 || P.halo_m > 5 || P.halo_p > 5) { err = "halos must lie in 2..5"; return false; } }
     else if (key == "rk") { std::string v; ls >> v; P.rk = v == "sbli" ? RK_SBLI : RK_LS; }
     else if (key == "rk_a") { double v; while (ls >> v) P.rk_a.push_back(v); }
@@ -245,6 +247,11 @@ bool parse_plan(const std::string &text, Plan &P, std::string &err) {
   if (P.conv == CONV_CENTRAL && P.order != 4) { err = "central scheme: only order 4 is implemented"; return false; }
   if (P.conv == CONV_WENO && P.order != 5) { err = "WENO: only order 5 (k=3) is implemented"; return false; }
   if (P.conv == CONV_TENO && P.order != 5 && P.order != 6) { err = "TENO: only orders 5 and 6 are implemented"; return false; }
+  if (P.conv == CONV_GENERIC) {
+    if (!P.generic_stages) { err = "conv generic needs generic_stages"; return false; }
+    if (P.halo_m <= 0) { err = "conv generic needs halos"; return false; }
+    P.consts.emplace("gama", 1.4); P.consts.emplace("dt", 0.0);       // unused: the printed kernels carry their own constants
+  } else if (P.generic_stages) { err = "generic_stages needs conv generic"; return false; }
   for (const char *k : {"gama", "dt"}) if (!P.consts.count(k)) { err = std::string("missing constant ") + k; return false; }
   if (P.viscous) for (const char *k : {"Re", "Pr", "Minf"}) if (!P.consts.count(k)) { err = std::string("missing constant ") + k; return false; }
   bool any_closure = false;
@@ -751,10 +758,10 @@ void launch_prim_nd(osb_ctx *c) {
 int run_user_kernels(osb_ctx *c, int when) {
   const GridDev &g = c->grid;
   for (auto &k : c->user_kernels) {
-    if (k.when != when) continue;
+    if (k.when != when && !(when >= 210 && when < 220 && k.when == 209)) continue;      // 209: every stage
     // u_i, p, a, T are not written by the stage kernels that derive them on the fly: a user kernel that reads one of them
     // sees the constituent relations of the current state (what the reference's loop reads after its last stage)
-    if (c->prim_stale)
+    if (c->prim_stale && c->plan.conv != CONV_GENERIC)
       for (auto &n : k.fields) { Field *f = find_field(c, n.c_str()); if (f && is_primitive(c, f->dev)) { launch_prim_nd(c); break; } }
     UserFields uf{};
     for (size_t i = 0; i < k.fields.size(); i++) {
@@ -769,7 +776,7 @@ int run_user_kernels(osb_ctx *c, int when) {
     dim3 bl(128, 1, 1), gr((n[0] + 127) / 128, n[1], n[2]);
     Launcher L(c, OSB_FAM_USER);
     OSB_CUDA(c, cudaLaunchKernel((const void *)k.kern, gr, bl, args, 0, c->stream));
-    if (k.writes_state) c->prim_stale = true;
+    if (k.writes_state && c->plan.conv != CONV_GENERIC) c->prim_stale = true;
   }
   return 0;
 }
@@ -777,8 +784,20 @@ int run_user_kernels(osb_ctx *c, int when) {
 // One stage of the loop (s < 0: iteration start).  In a decomposed run the neighbour exchange is part of the stage and is
 // ordered on the stream by flag words, so a whole run can be enqueued without host synchronisation:
 //   phase A (reads halos) -> "read done" handshake -> phase B + RK (+ fused peer push) -> "pushed" handshake -> local BCs
+// CONV_GENERIC: a stage is the list of run-time compiled kernels the back end printed for it, boundary kernels and periodic copies
+// included, in program order (algorithm.py:440-474)
+int generic_stage(osb_ctx *c, int s) {
+  const int last = c->plan.generic_stages - 1;
+  if (s < 0) return run_user_kernels(c, 200);
+  if (run_user_kernels(c, 210 + s)) return 1;
+  if (s == last) { if (run_user_kernels(c, 0)) return 1; c->iteration++; }
+  OSB_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
 template <int ND>
 int stage_nd(osb_ctx *c, int s) {
+  if (c->plan.conv == CONV_GENERIC) return generic_stage(c, s);
   const bool ex = has_exchange(c);
   if (c->plan.mass_source && s <= 0) c->pc.src_factor = sin(c->plan.src_rate * (double)c->iteration);
   struct StepCounter { osb_ctx *c; int s; ~StepCounter() { if (s == (int)c->plan.rk_a.size() - 1) c->iteration++; } } counter{c, s};
@@ -1146,7 +1165,7 @@ int osb_upload(osb_ctx *c, const char *name, const double *host) {
 // u_i, p, a, T are not kept up to date by the stage kernels that derive them on the fly: evaluate the constituent relations
 // of the current state before handing such an array out
 static void refresh_primitives_for(osb_ctx *c, const Field *f) {
-  if (!c->prim_stale || !is_primitive(c, f->dev)) return;
+  if (!c->prim_stale || c->plan.conv == CONV_GENERIC || !is_primitive(c, f->dev)) return;
   cudaSetDevice(c->device);
   launch_prim_nd(c);
 }

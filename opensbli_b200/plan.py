@@ -49,7 +49,7 @@ JSON-able dict; `to_text` serialises it to the line format parsed by the C ABI (
 import copy
 import json
 
-CONV = ('central', 'weno', 'teno')
+CONV = ('central', 'weno', 'teno', 'generic')
 BC_TYPES = ('periodic', 'dirichlet', 'exchange', 'isothermal_wall', 'extrapolation', 'inlet_pressure_extrapolate', 'symmetry',
             'dirichlet_field', 'adiabatic_wall', 'zero_gradient_outlet', 'pressure_outlet', 'inviscid_wall', 'generic', 'open', 'split')
 SPLIT_PART_TYPES = ('dirichlet', 'isothermal_wall', 'adiabatic_wall', 'extrapolation', 'inlet_pressure_extrapolate', 'symmetry',
@@ -77,7 +77,9 @@ def validate(plan):
     if plan.get('conv') not in CONV:
         raise PlanError('conv must be one of %s' % (CONV,))
     order = plan.get('order')
-    ok = {'central': (4,), 'weno': (5,), 'teno': (5, 6)}[plan['conv']]
+    ok = {'central': (4,), 'weno': (5,), 'teno': (5, 6), 'generic': (order,)}[plan['conv']]
+    if plan['conv'] == 'generic' and not (plan.get('generic') or {}).get('nstages'):
+        raise PlanError("conv 'generic' needs generic.nstages (every loop of the step is a run-time compiled kernel, see backend.extract_plan)")
     if order not in ok:
         raise PlanError('%s scheme: order %r is not implemented by the B200 back end (supported: %s)' % (plan['conv'], order, ok))
     if plan.get('rk') not in ('ls', 'sbli'):
@@ -114,7 +116,7 @@ def validate(plan):
                     if part['type'] == 'pressure_outlet' and (s != 1 or 'back_pressure' not in plan.get('constants', {})):
                         raise PlanError('pressure_outlet is defined for side 1 and needs the constant back_pressure (pressure_outlet.py:22-31)')
     c = plan.get('constants', {})
-    need = ['gama', 'dt'] + (['Re', 'Pr', 'Minf'] if plan.get('viscous') else [])
+    need = [] if plan['conv'] == 'generic' else ['gama', 'dt'] + (['Re', 'Pr', 'Minf'] if plan.get('viscous') else [])
     for k in need:
         if k not in c:
             raise PlanError('missing constant %s' % k)
@@ -136,7 +138,7 @@ def to_text(plan):
          'weno_formulation %s' % plan.get('weno_formulation', 'JS'),
          'averaging %s' % plan.get('averaging', 'roe'),
          'viscous %d' % (1 if plan.get('viscous') else 0)] + (['halos %d %d' % tuple(plan['halos'])] if plan.get('halos') else []) + [
-         'rk %s' % plan['rk'],
+         'rk %s' % plan['rk']] + (['generic_stages %d' % int(plan['generic']['nstages'])] if plan['conv'] == 'generic' else []) + [
          'rk_a ' + ' '.join(_f(v) for v in plan['rk_a']),
          'rk_b ' + ' '.join(_f(v) for v in plan['rk_b'])]
     for k, v in sorted(plan['constants'].items()):

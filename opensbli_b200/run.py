@@ -143,11 +143,12 @@ class ColdRunner(object):
         return lo, hi
 
 
-def user_kernel_source(k, index, env, nd):
-    """CUDA C of one point-wise user kernel (entry signature: include/osbli_b200.h, osb_add_user_kernel)."""
+def user_kernel_source(k, index, env, nd, stage=None):
+    """CUDA C of one run-time compiled kernel (entry signature: include/osbli_b200.h, osb_add_user_kernel).  `stage`: the RK stage
+    the copy is compiled for when its statements index constants by the stage counter (rkA[stage], generic path)."""
     fields = list(k['reads']) + [w for w in k['writes'] if w not in k['reads']]
     entry = 'osb_user_kernel_%d' % index
-    text = ' '.join(s[2] for s in k['statements'])
+    text = ' '.join(s[2] for s in k['statements'] if s[2])
     L = ['struct UserFields { double *p[48]; };']
     for name, val in env.items():                       # the constants the statements mention, as the reference's C globals
         if not isinstance(val, list) and re.search(r'\b%s\b' % re.escape(name), text):
@@ -160,12 +161,19 @@ def user_kernel_source(k, index, env, nd):
           '  const long long X = off + (lo0 + i) + (lo1 + j) * s1 + (lo2 + k) * s2;',
           '  const int idx0 = lo0 + i + OSB_GOFF0, idx1 = lo1 + j + OSB_GOFF1, idx2 = lo2 + k + OSB_GOFF2;   // grid indices (block.grid_indexes)',
           '  (void)idx0; (void)idx1; (void)idx2;']
+    for name, vals in sorted(k.get('indexed_constants', {}).items()):      # rkA[stage] ...: the table and the stage this copy runs in
+        L.append('  const double %s[%d] = {%s};' % (name, len(vals), ', '.join(repr(float(v)) for v in vals)))
+    if stage is not None:
+        L.append('  const int stage = %d; (void)stage;' % stage)
     for n, name in enumerate(fields):
         L.append('  double *%s = f.p[%d];' % (name, n))
     for name in dict.fromkeys(k['locals']):
         L.append('  double %s = 0.0;' % name)       # kernel locals start at zero, as in the reference's generated C (opsc.py:340-343)
     for st in k['statements']:
         lhs, is_field, rhs = st[0], st[1], st[2]
+        if lhs in ('#if', '#elif', '#else', '#end'):              # GroupedPiecewise: equations under if / else if / else (opsc.py:372-397)
+            L.append({'#if': '  if (%s) {' % rhs, '#elif': '  } else if (%s) {' % rhs, '#else': '  } else {', '#end': '  }'}[lhs])
+            continue
         at = (st[3] if len(st) > 3 and st[3] else 'X')            # relative write (boundary kernels): index printed by the back end
         L.append('  %s%s = %s;' % (lhs, '[%s]' % at if is_field else '', rhs))
     L.append('}')
@@ -174,8 +182,24 @@ def user_kernel_source(k, index, env, nd):
         d = k['one_plane_along']
         if rng[2 * d + 1] - rng[2 * d] != 1:
             raise ValueError('boundary kernel %s: its range must be ONE plane along direction %d, got [%d, %d)' % (k['name'], d, rng[2 * d], rng[2 * d + 1]))
-    return {'name': k['name'], 'entry': entry, 'source': '\n'.join(L) + '\n', 'fields': fields, 'range': rng, 'when': k['when'],
+    when = k['when'] if stage is None else 'stage_%d' % stage
+    return {'name': k['name'], 'entry': entry, 'source': '\n'.join(L) + '\n', 'fields': fields, 'range': rng, 'when': when,
             'writes': list(k['writes'])}
+
+
+def user_kernel_sources(plan_sym, env, nd):
+    """All run-time compiled kernels of a plan, in program order.  On the generic path a kernel of the stage loop that reads the
+    stage counter is compiled once per stage; registration order = launch order within each list."""
+    out = []
+    nstages = (plan_sym.get('generic') or {}).get('nstages', 0)
+    for k in plan_sym.get('user_kernels', []):
+        uses_stage = k['when'] == 'stage' and any(s[2] and re.search(r'\bstage\b', s[2]) for s in k['statements'])
+        if uses_stage:
+            for s in range(nstages):
+                out.append(user_kernel_source(k, len(out), env, nd, stage=s))
+        else:
+            out.append(user_kernel_source(k, len(out), env, nd))
+    return out
 
 
 def resolve(plan_sym, env):
@@ -183,7 +207,7 @@ def resolve(plan_sym, env):
     metric fields, tabulated Dirichlet states); returns (plan, ColdRunner holding every cold dataset)."""
     nd = plan_sym['ndim']
     p = {k: plan_sym[k] for k in ('ndim', 'conv', 'order', 'weno_formulation', 'averaging', 'viscous', 'rk', 'rk_a', 'rk_b')}
-    for k in ('viscosity', 'metric_fields', 'teno_adaptive', 'closures', 'forcing', 'central_form', 'curvilinear', 'halos'):   # copied verbatim
+    for k in ('viscosity', 'metric_fields', 'teno_adaptive', 'closures', 'forcing', 'central_form', 'curvilinear', 'halos', 'generic'):   # copied verbatim
         if k in plan_sym:
             p[k] = plan_sym[k]
     p['np'] = [int(env['block0np%d' % d]) for d in range(nd)]
@@ -198,7 +222,7 @@ def resolve(plan_sym, env):
         if name:
             for f in (name, 'S' + name + str(d)):
                 p['fields'][f] = cold.array(f).copy()
-    p['user_kernels'] = [user_kernel_source(k, n, env, nd) for n, k in enumerate(plan_sym.get('user_kernels', []))]
+    p['user_kernels'] = user_kernel_sources(plan_sym, env, nd)
     # datasets the user kernels only read and the cold path has evaluated (coordinates, metric terms ...): shipped with the
     # plan; the runtime declares and uploads those the solver does not hold itself
     written = set(w for k in p['user_kernels'] for w in k['writes'])

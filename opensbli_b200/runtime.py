@@ -245,11 +245,14 @@ class Simulation(object):
 
     @staticmethod
     def _when_code(when):
-        """'iteration_end' | 'after_loop' | 'bc_<dir>_<side>' (the boundary kernel of a face whose plan entry is 'generic')"""
+        """'iteration_end' | 'after_loop' | 'bc_<dir>_<side>' (the boundary kernel of a face whose plan entry is 'generic') |
+        generic path: 'iteration_start' | 'stage' (every RK stage) | 'stage_<s>' (stage s only)"""
         if when.startswith('bc_'):
             _, d, s = when.split('_')
             return 100 + 2 * int(d) + int(s)
-        return {'iteration_end': 0, 'after_loop': 1}[when]
+        if when.startswith('stage_'):
+            return 210 + int(when.split('_')[1])
+        return {'iteration_end': 0, 'after_loop': 1, 'iteration_start': 200, 'stage': 209}[when]
 
     def run_user_kernels(self, when='after_loop'):
         self._check(self.lib.osb_run_user_kernels(self.ctx, self._when_code(when)), 'osb_run_user_kernels')

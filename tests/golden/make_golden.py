@@ -130,6 +130,9 @@ def katzer_wenoz_plan(N0, N1):
 # the Katzer app with the SFD filter (filters/SFD.py) switched on: golden states of an APP run (its user kernels change the state, which
 # the oracle does not model), kept under golden/apps/ so that the fixture-driven oracle tests do not pick it up
 FIXTURES['apps/katzer_sfd_60x40'] = ('katzer_sfd', katzer_plan(60, 40), [10])
+# WENO orders 7 and 3 (the hand-written sweeps cover 5): programs of the GENERIC path -- APP goldens, the oracle does not model them
+FIXTURES['apps/sod_weno7_n200'] = ('sod_weno7', sod_plan(200, 'weno', 5, 'JS'), [1, 50])
+FIXTURES['apps/sod_weno3_n200'] = ('sod_weno3', sod_plan(200, 'weno', 5, 'Z'), [1, 50])
 # the central-4 TGV with the non-linear WENO filter (filters/WENO_filter.py) after every step: an APP run as well
 FIXTURES['apps/tgv_wf_16'] = ('tgv_wf', tgv_plan(16, 'central', 4, SBLI3), [1, 3])
 FIXTURES['katzer_wenoz_60x40'] = ('katzer_wenoz', katzer_wenoz_plan(60, 40), [1, 10])
@@ -270,6 +273,8 @@ if os.path.isdir('/root/reference'):
     FIXTURES['tcf_teno6_16x24x12'] = ('tcf_teno6', tcf_teno6_plan(16, 24, 12), [1, 5])
     FIXTURES['katzer_carpenter_60x40'] = ('katzer_carpenter', katzer_carpenter_plan(60, 40), [1, 10])
 FIXTURES['tgv_sym_17'] = ('tgv_sym', tgv_sym_plan(17), [1, 3])
+# the isothermal-EOS Taylor-Green app (TGsym/TG_IsoT.py: four conserved variables, no energy equation): generic path, APP golden
+FIXTURES['apps/tg_isot_17'] = ('tg_isot', tgv_sym_plan(17), [1, 3])
 
 
 def env_params(plan):
@@ -286,7 +291,7 @@ def main():
         if sys.argv[1:] and name not in sys.argv[1:]:
             continue
         nd = plan['ndim']
-        fields = ['rho'] + ['rhou%d' % d for d in range(nd)] + ['rhoE']
+        fields = ['rho'] + ['rhou%d' % d for d in range(nd)] + ([] if config == 'tg_isot' else ['rhoE'])
         inner = (slice(5, -5),) * nd
         bc_tables = {}
         if config.startswith('isr'):

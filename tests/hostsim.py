@@ -60,7 +60,7 @@ class HostKernels(object):
         s2 = pd[0] * pd[1] if nd > 2 else 0
         off = h * (1 + (s1 if nd > 1 else 0) + (s2 if nd > 2 else 0))
         for n, k in enumerate(self.kernels):
-            if k['when'] != when:
+            if k['when'] != when and not (when.startswith('stage_') and k['when'] == 'stage'):      # 'stage': every RK stage
                 continue
             arrs = [self.field(f) for f in k['fields']]
             assert all(a.flags['C_CONTIGUOUS'] and a.dtype == np.float64 for a in arrs)

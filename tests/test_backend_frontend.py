@@ -74,6 +74,13 @@ APPS = {
                  "from opensbli.filters.WENO_filter import WENOFilter\nwf = WENOFilter(block, order=5)\n"
                  "block.set_equations([copy.deepcopy(constituent), copy.deepcopy(simulation_eq), initial] + wf.equation_classes)"),
                 ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),
+    # programs outside the hand-written kernels run on the GENERIC path (every loop printed and compiled at run time): WENO orders 7 and 3
+    'sod_weno7': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("'scheme\\':\\'Teno\\'", "'scheme\\':\\'Weno\\'"),
+                  ("LLFTeno(teno_order, averaging=Avg)", "LLFWeno(7, formulation='JS', averaging=Avg)"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),
+    'sod_weno3': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("'scheme\\':\\'Teno\\'", "'scheme\\':\\'Weno\\'"),
+                  ("LLFTeno(teno_order, averaging=Avg)", "LLFWeno(3, formulation='Z', averaging=Avg)"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),
+    # isothermal-EOS Taylor-Green as shipped (no energy equation): generic path, 3-D central scheme with ~90 loops per stage
+    'tg_isot': (REF + '/apps/taylor_green_vortex/TGsym/TG_IsoT.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),
     # InletTransferBC has no hand-written kernel: generic by itself (Sod with the left boundary copied from its first halo point)
     'sod_inlet_transfer': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("boundaries += [DirichletBC(direction, 0, left_eqns)]", "boundaries += [InletTransferBC(direction, 0)]"),
                                                                             ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),
@@ -366,21 +373,32 @@ UNSUPPORTED = {
 
 @pytest.fixture(scope='module')
 def unsupported_runs(tmp_path_factory):
+    """every case twice: as a user runs it (falls back to the generic path) and with OSB_NO_GENERIC_PATH=1 (must raise)"""
     if not os.path.isdir(REF):
         return {}
     procs = {}
     for name, (app, edits, _) in UNSUPPORTED.items():
         code = DRIVER % dict(oracle=os.path.join(REPO, 'oracle'), repo=REPO, ref=REF, app=app, edits=edits)
-        procs[name] = subprocess.Popen([sys.executable, '-W', 'ignore', '-c', code], cwd=str(tmp_path_factory.mktemp(name)),
-                                       env=dict(os.environ, PYTHONHASHSEED='0'), stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
-    return {name: (p.communicate()[1], p.returncode) for name, p in procs.items()}
+        for strict in (False, True):
+            d = str(tmp_path_factory.mktemp(name + ('_strict' if strict else '')))
+            env = dict(os.environ, PYTHONHASHSEED='0', **({'OSB_NO_GENERIC_PATH': '1'} if strict else {}))
+            procs[name, strict] = (d, subprocess.Popen([sys.executable, '-W', 'ignore', '-c', code], cwd=d, env=env, stdout=subprocess.PIPE,
+                                                       stderr=subprocess.PIPE, text=True))
+    return {key: (d,) + p.communicate() + (p.returncode,) for key, (d, p) in procs.items()}
 
 
 @pytest.mark.parametrize('name', sorted(UNSUPPORTED))
-def test_unsupported_features_fail_loudly(name, unsupported_runs):
-    """An app outside the accelerated path -- or one whose equations differ from what the kernels compute -- must raise,
-    never silently fall back or silently compute something else."""
+def test_programs_outside_the_hand_written_kernels(name, unsupported_runs):
+    """An app whose equations differ from what the hand-written kernels compute must never silently compute something else:
+    it is recognised (the reason names what differs) and runs on the GENERIC path -- its own loops, printed and compiled at run
+    time -- or, with OSB_NO_GENERIC_PATH=1, raises."""
     if not os.path.isdir(REF):
         pytest.skip('needs the reference front end')
-    stderr, rc = unsupported_runs[name]
-    assert rc != 0 and 'UnsupportedByB200' in stderr and UNSUPPORTED[name][2] in stderr, stderr[-600:]
+    d, out, err, rc = unsupported_runs[name, True]
+    assert rc != 0 and 'UnsupportedByB200' in err and UNSUPPORTED[name][2] in err, err[-600:]
+    d, out, err, rc = unsupported_runs[name, False]
+    assert rc == 0 and 'GENERIC path' in out and UNSUPPORTED[name][2] in out, (out[-600:], err[-600:])
+    sym = json.load(open(os.path.join(d, 'opensbli_b200.plan.json')))
+    assert sym['conv'] == 'generic' and UNSUPPORTED[name][2] in sym['generic']['reason'] and sym['generic']['nstages'] == 3
+    whens = set(k['when'] for k in sym['user_kernels'])
+    assert 'stage' in whens and 'iteration_start' in whens

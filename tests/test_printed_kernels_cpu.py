@@ -110,3 +110,44 @@ def test_printed_boundary_kernels_on_perturbed_state(name, fixture, over):
                 ou.oracle_lib().osbo_apply_bcs(ctypes.byref(c1), (P * len(q0))(*[a.ctypes.data_as(P) for a in q0]))
     for a, b in zip(q0, qo):
         assert np.allclose(a, b, rtol=1e-12, atol=1e-14), name
+
+
+def run_generic_on_host(plan_sym, plan, cold, nsteps):
+    """the whole time loop of a GENERIC-path plan on the host: every loop of the step is a printed kernel, launched in program order"""
+    from opensbli_b200 import run as R
+    q = [a.copy() for a in R.initial_state(plan_sym, cold)]
+    hk = hostsim.HostKernels(plan['user_kernels'], q[0].shape)
+    for n, a in zip(plan_sym['q_names'], q):
+        hk.fields[n] = a
+    for n, a in plan.get('user_fields', {}).items():
+        hk.fields[n] = np.ascontiguousarray(a).copy()
+    for _ in range(nsteps):
+        hk.run('iteration_start')
+        for s in range(plan['generic']['nstages']):
+            hk.run('stage_%d' % s)
+        hk.run('iteration_end')
+    return hk
+
+
+@pytest.mark.parametrize('name,golden,over,steps', [('sod_weno7', 'sod_weno7_n200', {'block0np0': 200}, (1, 50)),
+                                                    ('sod_weno3', 'sod_weno3_n200', {'block0np0': 200}, (1, 50)),
+                                                    ('tg_isot', 'tg_isot_17', {'block0np0': 17, 'block0np1': 17, 'block0np2': 17}, (3,))])
+def test_generic_path_reproduces_the_reference(name, golden, over, steps):
+    """Programs the hand-written kernels do not cover fall back to the generic path (backend.extract_plan): here WENO7-JS and
+    WENO3-Z on the Sod tube.  Every loop of the time step -- boundary kernels, constituent relations, reconstruction, residual, RK
+    update with rkA[stage] / rkB[stage] -- is a printed kernel; run on the host in program order against the reference's own run."""
+    from opensbli_b200 import run as R
+    plan_sym, env, plan, cold = R.load_case(os.path.join(PLANS, name), overrides=over)
+    assert plan['conv'] == 'generic' and plan['generic']['nstages'] == 3 and 'not implemented' in plan['generic']['reason']
+    whens = [k['when'] for k in plan['user_kernels']]
+    assert {'stage_0', 'stage_1', 'stage_2'} <= set(whens) and 'iteration_start' in whens      # the RK update is compiled per stage
+    z = np.load(os.path.join(APPS, golden + '.npz'))
+    for n in steps:
+        hk = run_generic_on_host(plan_sym, plan, cold, n)
+        ref = z['q%d' % n]
+        inner_ = (slice(5, -5),) * plan['ndim']
+        got = np.stack([hk.fields[f][inner_] for f in plan_sym['q_names'][:len(ref)]])
+        ax = tuple(range(1, ref.ndim))
+        err = np.abs(got - ref).max(axis=ax) / np.abs(ref).max(axis=ax)
+        tol = 1e-9 if name == 'sod_weno3' else 1e-12          # WENO-Z: the reference's own build-to-build noise floor (common.TOL)
+        assert err.max() < tol * max(1, n / 10), (n, err)
