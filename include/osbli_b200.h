@@ -151,7 +151,7 @@ int osb_diagnostics(osb_ctx *ctx, double *sums /* [OSB_NDIAG] */);
  * when = 100 + 2 dir + side: the boundary kernel of that face, for plans whose `bc dir side generic` line hands the face to a
  *   run-time compiled kernel (boundary classes without a hand-written kernel: the reference's kernel equations printed with
  *   relative offsets, bc_core.py:104-198); launched wherever the face's boundary condition is applied, in the reference's order. */
-enum { OSB_MAX_USER_FIELDS = 48 };
+enum { OSB_MAX_USER_FIELDS = 96 };
 /* Declare an additional dataset (zero-initialised; no-op if it exists): what ops_decl_dat does for a dataset that only user
  * kernels touch, e.g. a coordinate array x0 evaluated by the cold path and uploaded with osb_upload (opsc.py:693-722). */
 int osb_create_field(osb_ctx *ctx, const char *name);

@@ -133,6 +133,9 @@ def _user_kernel(kernel, when, stencil=False, thin_direction=None):
         def _print_Rational(s, e):
             return '(%d.0/%d.0)' % (e.p, e.q)
 
+        def _print_GroupedPiecewise(s, e):      # used as an EXPRESSION (teno.py:456-459: delta_r = 0 if ... else 1): a plain Piecewise;
+            return s._print_Piecewise(e)        # SymPy >= 1.6 no longer finds the base class's printer for Function subclasses
+
     pr = P({'precision': 17})
     out, reads, writes, local = [], [], [], []
     roff, woff = {}, {}
@@ -898,6 +901,9 @@ def extract_plan(algorithm):
     path: every loop of the time step is printed from its equations as CUDA C and compiled at run time, launched in program
     order -- one thread per point, the reference's own arithmetic, at the speed of a plain loop-per-kernel code."""
     import os
+    if os.environ.get('OSB_FORCE_GENERIC_PATH'):          # testing / measuring: the same program through the printed kernels
+        _extract_specialised_checks_only(algorithm)
+        return _extract_generic(algorithm, 'forced by OSB_FORCE_GENERIC_PATH')
     try:
         return _extract_specialised(algorithm)
     except _NotForGenericPath:
@@ -913,6 +919,16 @@ def extract_plan(algorithm):
         print('B200: the program runs on the GENERIC path (every loop compiled at run time from its equations); expect the speed of '
               'a loop-per-kernel code, not of the hand-written kernels')
         return plan
+
+
+def _extract_specialised_checks_only(algorithm):
+    """the refusals that hold for both paths (multi-block, precision)"""
+    try:
+        _extract_specialised(algorithm)
+    except _NotForGenericPath:
+        raise
+    except UnsupportedByB200:
+        pass
 
 
 def _generic_exchange(c, when):

@@ -58,6 +58,9 @@ def local_plan(plan, rank, world):
     """Plan of one rank: its slab of the block; faces shared with a neighbour become 'exchange' BCs."""
     if world == 1:
         return copy.deepcopy(plan)
+    if plan.get('conv') == 'generic':
+        raise _plan.PlanError('programs on the generic path (every loop a run-time compiled kernel) run on one GPU: their boundary '
+                              'kernels and periodic copies are part of the kernel lists and are not cut into slabs')
     ax = slab_axis(plan)
     _, loc = local_extent(plan, rank, world)
     hm, hp = scheme_halos(plan)

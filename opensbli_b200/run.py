@@ -147,12 +147,16 @@ def user_kernel_source(k, index, env, nd, stage=None):
     """CUDA C of one run-time compiled kernel (entry signature: include/osbli_b200.h, osb_add_user_kernel).  `stage`: the RK stage
     the copy is compiled for when its statements index constants by the stage counter (rkA[stage], generic path)."""
     fields = list(k['reads']) + [w for w in k['writes'] if w not in k['reads']]
+    if len(fields) > 96:
+        raise ValueError('kernel %s touches %d datasets (limit 96, OSB_MAX_USER_FIELDS)' % (k['name'], len(fields)))
     entry = 'osb_user_kernel_%d' % index
     text = ' '.join(s[2] for s in k['statements'] if s[2])
-    L = ['struct UserFields { double *p[48]; };']
+    L = ['struct UserFields { double *p[96]; };']          # OSB_MAX_USER_FIELDS (include/osbli_b200.h)
     for name, val in env.items():                       # the constants the statements mention, as the reference's C globals
         if not isinstance(val, list) and re.search(r'\b%s\b' % re.escape(name), text):
-            L.append('#define %s (%s)' % (name, repr(float(val))))
+            # integer parameters (block0np<d>, niter) stay integers, as the reference's C globals are: index arithmetic and
+            # integer division behave as in its program
+            L.append('#define %s (%s)' % (name, str(val) if isinstance(val, int) and not isinstance(val, bool) else repr(float(val))))
     # OSB_GOFF<d>: global index of the rank's first point along direction d (slab-decomposed runs; decomp.local_plan defines it)
     L += ['#ifndef OSB_GOFF0', '#define OSB_GOFF0 0', '#endif', '#ifndef OSB_GOFF1', '#define OSB_GOFF1 0', '#endif', '#ifndef OSB_GOFF2', '#define OSB_GOFF2 0', '#endif']
     L += ['extern "C" __global__ void %s(long long off, int n0, int n1, int n2, int lo0, int lo1, int lo2, long long s1, long long s2, UserFields f) {' % entry,

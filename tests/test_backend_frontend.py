@@ -81,6 +81,10 @@ APPS = {
                   ("LLFTeno(teno_order, averaging=Avg)", "LLFWeno(3, formulation='Z', averaging=Avg)"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),
     # isothermal-EOS Taylor-Green as shipped (no energy equation): generic path, 3-D central scheme with ~90 loops per stage
     'tg_isot': (REF + '/apps/taylor_green_vortex/TGsym/TG_IsoT.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),
+    # the two bench workloads FORCED through the generic path: the printed loops must reproduce what the hand-written kernels compute
+    'tgv_teno5_allprinted': (os.path.join(REPO, 'apps', 'tgv_teno5.py'), [], None, {'OSB_FORCE_GENERIC_PATH': '1'}),
+    'tgv_central4_allprinted': (REF + '/apps/taylor_green_vortex/taylor_green_vortex.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None,
+                                    {'OSB_FORCE_GENERIC_PATH': '1'}),
     # InletTransferBC has no hand-written kernel: generic by itself (Sod with the left boundary copied from its first halo point)
     'sod_inlet_transfer': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("boundaries += [DirichletBC(direction, 0, left_eqns)]", "boundaries += [InletTransferBC(direction, 0)]"),
                                                                             ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),

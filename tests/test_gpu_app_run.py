@@ -412,3 +412,22 @@ def test_generic_path_programs_match_reference(name, golden, over, steps, tol):
         err = np.abs(got - ref).max(axis=ax) / np.abs(ref).max(axis=ax)
         print(name, n, err)
         assert err.max() < tol * max(1, n / 10), (n, err)
+
+
+@pytest.mark.parametrize('name,fixture', [('tgv_teno5_allprinted', 'tgv_teno5_16'), ('tgv_central4_allprinted', 'tgv_central4_16')])
+def test_bench_workloads_through_the_generic_path(name, fixture):
+    """The two bench workloads forced through the generic path on the GPU (plans distilled with OSB_FORCE_GENERIC_PATH=1): the
+    run-time compiled loops reproduce the goldens the hand-written kernels are held to."""
+    from opensbli_b200 import run as R, Simulation
+    want, states = load_fixture(fixture)
+    over = {'block0np%d' % d: 16 for d in range(3)}
+    over['dt'] = want['constants']['dt']
+    plan_sym, env, plan, cold = R.load_case(os.path.join(PLANS, name), overrides=over)
+    assert plan['conv'] == 'generic'
+    with Simulation(plan) as sim:
+        sim.set_state(R.initial_state(plan_sym, cold))
+        sim.step(3)
+        q = inner(plan, sim.get_state())
+    err = field_errors(want, q, states[3])
+    print(name, err)
+    assert max(err) < 1e-12, err

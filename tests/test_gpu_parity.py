@@ -306,7 +306,7 @@ def test_user_kernel_reads_current_primitives_and_rejects_unknown_inputs(osb):
     """Point-wise user kernels on the fused 3-D paths: a kernel reading a primitive sees the constituent relations of the
     current state (the stage kernels never write those arrays); a kernel reading a dataset nobody provided is refused."""
     plan, states = load_fixture('tgv_teno5_16')
-    src = ('struct UserFields { double *p[48]; };\n'
+    src = ('struct UserFields { double *p[96]; };\n'
            'extern "C" __global__ void k(long long off, int n0, int n1, int n2, int lo0, int lo1, int lo2, long long s1, long long s2, UserFields f) {\n'
            '  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, kk = blockIdx.z;\n'
            '  if (i >= n0 || j >= n1 || kk >= n2) return;\n'

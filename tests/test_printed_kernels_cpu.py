@@ -151,3 +151,20 @@ def test_generic_path_reproduces_the_reference(name, golden, over, steps):
         err = np.abs(got - ref).max(axis=ax) / np.abs(ref).max(axis=ax)
         tol = 1e-9 if name == 'sod_weno3' else 1e-12          # WENO-Z: the reference's own build-to-build noise floor (common.TOL)
         assert err.max() < tol * max(1, n / 10), (n, err)
+
+
+@pytest.mark.parametrize('name,fixture', [('tgv_teno5_allprinted', 'tgv_teno5_16'), ('tgv_central4_allprinted', 'tgv_central4_16')])
+def test_bench_workloads_through_the_generic_path(name, fixture):
+    """The two bench workloads (TENO5 + StoreSome + RK-LS, Central-4 + RK3 Taylor-Green) FORCED through the generic path
+    (OSB_FORCE_GENERIC_PATH=1 when the plan was distilled): the printed loops reproduce the goldens the hand-written kernels are
+    held to -- the two paths of the back end agree through the reference."""
+    from opensbli_b200 import run as R
+    want, states = load_fixture(fixture)
+    over = {'block0np%d' % d: 16 for d in range(3)}
+    over['dt'] = want['constants']['dt']
+    plan_sym, env, plan, cold = R.load_case(os.path.join(PLANS, name), overrides=over)
+    assert plan['conv'] == 'generic' and 'forced' in plan['generic']['reason']
+    hk = run_generic_on_host(plan_sym, plan, cold, 3)
+    got = np.stack([hk.fields[f][5:-5, 5:-5, 5:-5] for f in plan_sym['q_names']])
+    err = field_errors(want, got, states[3])
+    assert max(err) < 1e-12, err
