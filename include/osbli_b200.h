@@ -150,7 +150,11 @@ int osb_diagnostics(osb_ctx *ctx, double *sums /* [OSB_NDIAG] */);
  * when = 1: launched by osb_run_user_kernels(ctx, 1) (loops after the time loop);
  * when = 100 + 2 dir + side: the boundary kernel of that face, for plans whose `bc dir side generic` line hands the face to a
  *   run-time compiled kernel (boundary classes without a hand-written kernel: the reference's kernel equations printed with
- *   relative offsets, bc_core.py:104-198); launched wherever the face's boundary condition is applied, in the reference's order. */
+ *   relative offsets, bc_core.py:104-198); launched wherever the face's boundary condition is applied, in the reference's order;
+ * generic path (plan `conv generic`, `generic_stages N`: a program outside the hand-written kernels -- every loop of its time
+ * step is such a kernel, boundary kernels and periodic copies included, launched in registration order = program order,
+ * algorithm.py:440-474):  when = 200: at the start of every iteration;  when = 209: in every RK stage;  when = 210 + s: in
+ * stage s only (a loop that reads the stage counter, rkA[stage], is compiled once per stage);  when = 0: after the last stage. */
 enum { OSB_MAX_USER_FIELDS = 96 };
 /* Declare an additional dataset (zero-initialised; no-op if it exists): what ops_decl_dat does for a dataset that only user
  * kernels touch, e.g. a coordinate array x0 evaluated by the cold path and uploaded with osb_upload (opsc.py:693-722). */
