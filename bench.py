@@ -297,7 +297,8 @@ def main():
     ap.add_argument('--cpu-size', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--e2e-chunk', type=int, default=64, help='planes per window of the pipelined end-to-end leg')
+    ap.add_argument('--e2e-chunk', default='64', help="planes per window of the pipelined end-to-end leg, or 'ramp' (n/16, n/8, n/4, n/4, 3n/16, n/8; measured slower: 0.76 vs 0.83 G)")
+    ap.add_argument('--e2e-contexts', type=int, default=3, help='window contexts taking turns in the pipelined end-to-end leg')
     ap.add_argument('--no-parity', action='store_true')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak: --size^3 points per GPU (default); strong: one --grid^3 block cut over all GPUs (BASELINE configs[4])')
@@ -469,7 +470,7 @@ def main():
             # sweep of window k and the download of window k-1 overlap (hostpipe.py); host wall clock around the call
             try:
                 from opensbli_b200.hostpipe import HostPipeline
-                with HostPipeline(plan, chunk=args.e2e_chunk, nsteps=1, device=local_rank) as pipe:
+                with HostPipeline(plan, chunk=(args.e2e_chunk if args.e2e_chunk == 'ramp' else int(args.e2e_chunk)), nsteps=1, device=local_rank, contexts=args.e2e_contexts) as pipe:
                     pipe.advance(src, dst)        # warm-up (module load, first-touch of the window contexts)
                     src, dst = dst, src
                     torch.cuda.synchronize()
@@ -481,8 +482,8 @@ def main():
                     up, down = pipe.bytes_per_call()
                     e2e = {'value': points * Ke / wall, 'unit': UNIT, 'h2d_bytes_per_step': up, 'd2h_bytes_per_step': down, 'steps': Ke,
                            'call': 'HostPipeline.advance(q_in, q_out): osb_staging_upload (each plane once) + per window osb_staging_feed / osb_step / osb_host_planes_download, '
-                                   'pinned host buffers in the reference layout, %d windows of %d + 2 x %d guard planes on %d contexts'
-                                   % (len(pipe.windows), pipe.chunk, pipe.guard, len(pipe.sims)),
+                                   'pinned host buffers in the reference layout, windows of %s planes + 2 x %d guard planes on %d contexts'
+                                   % ([z1 - z0 for z0, z1 in pipe.windows], pipe.guard, len(pipe.sims)),
                            'timing': 'host wall clock around the calls (each call ends with a synchronisation of all its streams)',
                            'launches_per_step': pipe.launches, 'unpipelined': whole}
             except Exception as ex:               # a failure of the pipelined leg must not cost the bench line

@@ -40,9 +40,27 @@ def guard_planes(plan, nsteps=1):
     return stencil_depth(plan) * (len(plan['rk_a']) * int(nsteps) - 1)
 
 
+def ramp(n):
+    """Window sizes that ramp up and down: the pipeline cannot sweep before its first window is uploaded nor finish before its
+    last one is downloaded, so the ends are small (n/16, n/8 ... 3n/16, n/8) and the middle large (n/4: less guard-plane work)."""
+    if n % 16 or n < 256:
+        raise _plan.PlanError('ramp windows need a plane count that is a multiple of 16 and at least 256')
+    u = n // 16
+    return [u, 2 * u, 4 * u, 4 * u, 3 * u, 2 * u]
+
+
 def windows(n, chunk):
-    """[(z0, z1)] covering [0, n) with windows of exactly `chunk` planes; the last one is shifted back to end at n (its
-    overlap with the one before is computed twice, to the same values)."""
+    """[(z0, z1)] covering [0, n): `chunk` is a list of window sizes that add up to n, or one size -- then the windows have exactly
+    `chunk` planes and the last one is shifted back to end at n (its overlap with the one before is computed twice, to the same
+    values)."""
+    if isinstance(chunk, (list, tuple)):
+        if sum(chunk) != n or min(chunk) < 1:
+            raise _plan.PlanError('window sizes %s do not add up to %d planes' % (list(chunk), n))
+        out, z = [], 0
+        for c in chunk:
+            out.append((z, z + c))
+            z += c
+        return out
     if chunk >= n:
         return [(0, n)]
     out = []
@@ -70,6 +88,8 @@ def window_plan(plan, chunk, nsteps=1):
     g = guard_planes(plan, nsteps)
     if chunk >= n:
         raise _plan.PlanError('window pipeline: one window would hold the whole block (use advance_host)')
+    if chunk < 1:
+        raise _plan.PlanError('window pipeline: empty window')
     p = copy.deepcopy(plan)
     p['np'][ax] = chunk + 2 * g
     p['bc'][ax][0] = {'type': 'open'}
@@ -108,10 +128,24 @@ class HostPipeline(object):
         self.ax = slab_axis(self.plan_global)
         self.n = self.plan_global['np'][self.ax]
         self.nsteps = int(nsteps)
-        self.chunk = int(chunk)
-        self.plan, self.guard = window_plan(self.plan_global, self.chunk, self.nsteps)
+        if chunk == 'ramp':
+            chunk = ramp(self.n)
+        self.chunk = list(chunk) if isinstance(chunk, (list, tuple)) else int(chunk)
         self.windows = windows(self.n, self.chunk)
-        self.sims = [factory(self.plan) for _ in range(min(int(contexts), len(self.windows)))]
+        # one window plan per window size; windows of a size take turns on that size's contexts (at most `contexts` each)
+        self.plans, self.pools, self.guard = {}, {}, None
+        for z0, z1 in self.windows:
+            size = z1 - z0
+            if size not in self.plans:
+                self.plans[size], self.guard = window_plan(self.plan_global, size, self.nsteps)
+                self.pools[size] = []
+        count = {}
+        for z0, z1 in self.windows:
+            count[z1 - z0] = count.get(z1 - z0, 0) + 1
+        for size, cnt in count.items():
+            self.pools[size] = [factory(self.plans[size]) for _ in range(min(int(contexts), cnt))]
+        self.sims = [sim for pool in self.pools.values() for sim in pool]
+        self.plan = self.plans[self.windows[0][1] - self.windows[0][0]]
         self.hm, self.hp = scheme_halos(self.plan_global)
         self.nv = self.plan_global['ndim'] + 2
         self.plane = 1
@@ -146,10 +180,14 @@ class HostPipeline(object):
             raise ValueError('window pipeline: q_out must not alias q_in (windows read guard planes other windows write)')
         l0 = sum(s.launch_count() for s in self.sims)
         staged = [False] * n                         # planes of the block already on their way to the staging copy
+        turn = {}
         for w, (z0, z1) in enumerate(self.windows):
-            sim = self.sims[w % len(self.sims)]
+            size = z1 - z0
+            pool = self.pools[size]
+            sim = pool[turn.get(size, 0) % len(pool)]
+            turn[size] = turn.get(size, 0) + 1
             # padded local plane j of the window holds plane z0 - g - h + j of the block (periodic image)
-            runs = wrapped_runs(z0 - g - h, self.chunk + 2 * g + 2 * h, n)
+            runs = wrapped_runs(z0 - g - h, size + 2 * g + 2 * h, n)
             for gp, _, length in runs:
                 a = gp
                 while a < gp + length:               # upload the planes of this run that no earlier window asked for

@@ -26,7 +26,8 @@ def defined_cells(plan, a):
 
 
 @pytest.mark.parametrize('workload,np3,chunk,nsteps', [('teno5', (64, 48, 96), 32, 1), ('teno5', (64, 48, 90), 32, 1),
-                                                       ('central4', (64, 64, 64), 16, 1), ('teno5', (40, 40, 64), 24, 2)])
+                                                       ('central4', (64, 64, 64), 16, 1), ('teno5', (40, 40, 64), 24, 2),
+                                                       ('teno5', (64, 48, 96), [8, 16, 40, 20, 12], 1)])
 def test_window_pipeline_equals_whole_block_call(workload, np3, chunk, nsteps):
     import opensbli_b200
     plan, q0 = tgv_case(np3, workload)

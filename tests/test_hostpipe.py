@@ -76,7 +76,7 @@ def defined_cells(plan, a):
 
 
 @pytest.mark.parametrize('fixture,chunk,nsteps', [('tgv_teno5_16', 8, 1), ('tgv_teno5_16', 5, 1), ('tgv_central4_16', 4, 2),
-                                                  ('tgv_central4_16', 6, 1)])
+                                                  ('tgv_central4_16', 6, 1), ('tgv_teno5_16', [2, 3, 6, 5], 1)])
 def test_windowed_advance_reproduces_whole_block(fixture, chunk, nsteps):
     plan, states = load_fixture(fixture)
     q0 = pad(plan, states[0])
@@ -112,6 +112,12 @@ def test_window_helpers():
     assert hostpipe.windows(16, 8) == [(0, 8), (8, 16)]
     assert hostpipe.windows(16, 6) == [(0, 6), (6, 12), (10, 16)]
     assert hostpipe.windows(8, 8) == [(0, 8)]
+    assert hostpipe.windows(16, [2, 4, 6, 4]) == [(0, 2), (2, 6), (6, 12), (12, 16)]
+    assert hostpipe.ramp(512) == [32, 64, 128, 128, 96, 64] and sum(hostpipe.ramp(1024)) == 1024
+    with pytest.raises(PlanError):
+        hostpipe.windows(16, [4, 4])
+    with pytest.raises(PlanError):
+        hostpipe.ramp(100)
     assert hostpipe.wrapped_runs(-13, 30, 16) == [(3, 0, 13), (0, 13, 16), (0, 29, 1)]
     assert hostpipe.wrapped_runs(2, 5, 16) == [(2, 0, 5)]
     runs = hostpipe.wrapped_runs(500, 90, 512)
