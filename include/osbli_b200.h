@@ -113,6 +113,13 @@ int osb_staging_upload(osb_staging *stage, const double *const *src, int plane0,
 int osb_staging_feed(osb_staging *stage, osb_ctx *ctx, int stage_plane0, int plane0, int nplanes);
 int osb_staging_fed(osb_ctx *ctx);
 int osb_staging_sync(osb_staging *stage);
+/* Slab-decomposed blocks (one rank per GPU): a rank's staging copy carries guard + halo planes below and above its slab, which
+ * it pulls out of the neighbours' staging copies over NVLink (CUDA IPC, same exchange of handles as osb_ipc_export / _import);
+ * the caller orders the ranks (pull after every rank's boundary planes have landed).  With them in place the rank's windows
+ * need no per-stage halo exchange at all. */
+int osb_staging_ipc_export(osb_staging *stage, void *handles, int *nbytes);
+int osb_staging_ipc_import(osb_staging *stage, int side, const void *handles, int nbytes);
+int osb_staging_pull(osb_staging *stage, int side, int src_plane0, int dst_plane0, int nplanes);
 
 /* Instrumentation: number of kernels launched by this context so far; per-family device time of
  * one profiled step (events around each launch).  Families: see OSB_FAM_*. */

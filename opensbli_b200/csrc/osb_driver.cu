@@ -1367,6 +1367,7 @@ struct osb_staging {
   int device = 0, nv = 0, nplanes = 0;
   long long plane = 0;                       // doubles per plane
   double *buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  double *peer[2][5] = {{nullptr}};          // neighbour ranks' staging copies (slab-decomposed blocks), CUDA IPC
   cudaStream_t s_up = nullptr;
   std::string error;
 };
@@ -1386,6 +1387,7 @@ int osb_staging_create(int device, int nv, long long plane_doubles, int nplanes,
 int osb_staging_destroy(osb_staging *st) {
   if (!st) return 0;
   cudaSetDevice(st->device);
+  for (int side = 0; side < 2; side++) for (int m = 0; m < 5; m++) if (st->peer[side][m]) cudaIpcCloseMemHandle(st->peer[side][m]);
   for (int m = 0; m < 5; m++) if (st->buf[m]) cudaFree(st->buf[m]);
   if (st->s_up) cudaStreamDestroy(st->s_up);
   delete st;
@@ -1426,6 +1428,43 @@ int osb_staging_fed(osb_ctx *c) {                // all planes of the window are
   if (!c) return 1;
   cudaSetDevice(c->device);
   return window_reset_registers(c);
+}
+// slab-decomposed blocks: the planes a rank's first and last windows need from its neighbours are pulled out of the neighbours'
+// staging copies over NVLink (the caller orders the ranks: pull after every rank's boundary planes have landed, re-upload after
+// every rank's pulls have)
+int osb_staging_ipc_export(osb_staging *st, void *handles, int *nbytes) {
+  if (!st || !handles || !nbytes) return 1;
+  cudaSetDevice(st->device);
+  for (int m = 0; m < st->nv; m++) {
+    cudaIpcMemHandle_t h;
+    OSB_STAGE_CUDA(st, cudaIpcGetMemHandle(&h, st->buf[m]));
+    memcpy((char *)handles + m * sizeof(h), &h, sizeof(h));
+  }
+  *nbytes = st->nv * (int)sizeof(cudaIpcMemHandle_t);
+  return 0;
+}
+int osb_staging_ipc_import(osb_staging *st, int side, const void *handles, int nbytes) {
+  if (!st || !handles || side < 0 || side > 1) return 1;
+  cudaSetDevice(st->device);
+  if (nbytes != st->nv * (int)sizeof(cudaIpcMemHandle_t)) { st->error = "osb_staging_ipc_import: wrong handle size"; return 1; }
+  for (int m = 0; m < st->nv; m++) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + m * sizeof(h), sizeof(h));
+    void *p = nullptr;
+    OSB_STAGE_CUDA(st, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    st->peer[side][m] = (double *)p;
+  }
+  return 0;
+}
+int osb_staging_pull(osb_staging *st, int side, int src_plane0, int dst_plane0, int nplanes) {
+  if (!st || side < 0 || side > 1) return 1;
+  cudaSetDevice(st->device);
+  if (!st->peer[side][0]) { st->error = "osb_staging_pull: no neighbour imported on this side"; return 1; }
+  if (src_plane0 < 0 || dst_plane0 < 0 || nplanes < 1 || dst_plane0 + nplanes > st->nplanes) { st->error = "osb_staging_pull: plane range outside the staged block"; return 1; }
+  for (int m = 0; m < st->nv; m++)
+    OSB_STAGE_CUDA(st, cudaMemcpyAsync(st->buf[m] + dst_plane0 * st->plane, st->peer[side][m] + src_plane0 * st->plane,
+                                       sizeof(double) * st->plane * nplanes, cudaMemcpyDefault, st->s_up));
+  return 0;
 }
 int osb_staging_sync(osb_staging *st) {
   if (!st) return 1;

@@ -117,16 +117,21 @@ class HostPipeline(object):
     every cell a kernel defines: the grid points and the halo cells within the scheme's halo depth (the last boundary-condition
     pass).  Halo cells beyond that depth are read by nothing and are left unspecified, as they are by the whole-block call."""
 
-    def __init__(self, plan, chunk=64, nsteps=1, device=-1, contexts=3, factory=None, stage_factory=None):
+    def __init__(self, plan, chunk=64, nsteps=1, device=-1, contexts=3, factory=None, stage_factory=None, exchange=None, slab=None):
         """factory(window_plan) -> window solver, stage_factory(nv, plane_doubles, nplanes) -> staging copy; defaults: a
-        Simulation and a Stage on `device` (the CPU tests of the windowing drive the oracle through the same calls)."""
+        Simulation and a Stage on `device` (the CPU tests of the windowing drive the oracle through the same calls).
+        Slab-decomposed blocks (one rank per GPU): `slab` = (first plane, number of planes) of this rank and
+        `exchange(stage, G, n)` fills the staging copy's G = guard + halo planes below and above the slab with the neighbours'
+        planes (their staged bottom / top planes; see DistributedHostPipeline) -- after that the rank's windows are as
+        independent of the other ranks as they are of each other: no per-stage halo exchange at all."""
         if factory is None:
             from .runtime import Simulation, Stage
             factory = lambda p: Simulation(p, device=device)
-            stage_factory = lambda nv, plane, n: Stage(nv, plane, n, device=device)
+            stage_factory = stage_factory or (lambda nv, plane, n: Stage(nv, plane, n, device=device))
         self.plan_global = _plan.validate(copy.deepcopy(plan))
         self.ax = slab_axis(self.plan_global)
-        self.n = self.plan_global['np'][self.ax]
+        self.exchange = exchange
+        self.n = self.plan_global['np'][self.ax] if slab is None else int(slab[1])
         self.nsteps = int(nsteps)
         if chunk == 'ramp':
             chunk = ramp(self.n)
@@ -152,7 +157,12 @@ class HostPipeline(object):
         for d in range(self.plan_global['ndim']):
             if d != self.ax:
                 self.plane *= self.plan_global['np'][d] + 2 * HALO
-        self.stage = stage_factory(self.nv, self.plane, self.n)
+        # single block: the staging copy holds the n planes, guard planes are periodic images; slab of a decomposed block: it
+        # holds G more planes on either side, which the neighbours fill
+        self.G = 0 if exchange is None else self.guard + HALO
+        if exchange is not None and self.n < self.G:
+            raise _plan.PlanError('window pipeline: slab of %d planes is thinner than guard + halo' % self.n)
+        self.stage = stage_factory(self.nv, self.plane, self.n + 2 * self.G)
         self.launches = 0
 
     def close(self):
@@ -171,7 +181,7 @@ class HostPipeline(object):
 
     def bytes_per_call(self):
         """(H2D, D2H) bytes of one advance() call, counted from the plane copies it enqueues."""
-        down = sum(z1 - z0 for z0, z1 in self.windows) + 2 * self.hm
+        down = sum(z1 - z0 for z0, z1 in self.windows) + (2 * self.hm if self.exchange is None else 0)
         return self.n * self.plane * 8 * self.nv, down * self.plane * 8 * self.nv
 
     def advance(self, q_in, q_out):
@@ -180,6 +190,16 @@ class HostPipeline(object):
             raise ValueError('window pipeline: q_out must not alias q_in (windows read guard planes other windows write)')
         l0 = sum(s.launch_count() for s in self.sims)
         staged = [False] * n                         # planes of the block already on their way to the staging copy
+        G = self.G
+        if self.exchange is not None:
+            # the planes the neighbours need go first; once they have landed the ranks swap them device to device, then the
+            # rest of the slab follows in window order while the first windows are already swept
+            for a, b in ((0, min(G, n)), (max(n - G, min(G, n)), n)):
+                if b > a:
+                    self.stage.upload(q_in, h + a, G + a, b - a)
+                    staged[a:b] = [True] * (b - a)
+            self.stage.sync()
+            self.exchange(self.stage, G, n)
         turn = {}
         for w, (z0, z1) in enumerate(self.windows):
             size = z1 - z0
@@ -187,27 +207,33 @@ class HostPipeline(object):
             sim = pool[turn.get(size, 0) % len(pool)]
             turn[size] = turn.get(size, 0) + 1
             # padded local plane j of the window holds plane z0 - g - h + j of the block (periodic image)
-            runs = wrapped_runs(z0 - g - h, size + 2 * g + 2 * h, n)
+            if self.exchange is None:
+                runs = wrapped_runs(z0 - g - h, size + 2 * g + 2 * h, n)
+            else:                                    # planes below 0 / above n are the neighbours', already in the staging copy
+                lo_, hi_ = z0 - g - h, z1 + g + h
+                runs = [(p0, p0 - lo_, p1 - p0) for p0, p1 in ((lo_, min(hi_, 0)), (max(lo_, 0), min(hi_, n)), (max(lo_, n), hi_)) if p1 > p0]
             for gp, _, length in runs:
                 a = gp
-                while a < gp + length:               # upload the planes of this run that no earlier window asked for
+                while 0 <= a < min(gp + length, n):  # upload the planes of this run that no earlier window asked for
                     if staged[a]:
                         a += 1
                         continue
                     b = a
-                    while b < gp + length and not staged[b]:
+                    while b < min(gp + length, n) and not staged[b]:
                         staged[b] = True
                         b += 1
-                    self.stage.upload(q_in, h + a, a, b - a)
+                    self.stage.upload(q_in, h + a, G + a, b - a)
                     a = b
             for gp, off, length in runs:
-                self.stage.feed(sim, gp, off, length)
+                self.stage.feed(sim, G + gp, off, length)
             sim.stage_fed()
             sim.step(self.nsteps, sync=False)
             sim.planes_download(q_out, h + z0, h + g, z1 - z0)
             # halo planes of the whole block as its periodic BC leaves them after the last stage: [-hm, 0) <- [n-hm, n),
             # [n, n+hm) <- [0, hm)  (periodic.py:42-56: side 0 copies hm planes up; side 1 copies hp planes starting at n-hm
             # down to -hm, the last of which lands on plane 0 and is plane 0); they come from the windows that own those planes
+            if self.exchange is not None:
+                continue                             # slab of a decomposed block: its halo planes belong to the neighbours
             lo, hi = max(z0, n - self.hm), min(z1, n)
             if lo < hi:
                 sim.planes_download(q_out, h + lo - n, h + g + lo - z0, hi - lo)
@@ -219,3 +245,61 @@ class HostPipeline(object):
         self.stage.sync()
         self.launches = sum(s.launch_count() for s in self.sims) - l0
         return self.launches
+
+
+class DistributedHostPipeline(object):
+    """The window pipeline on a slab-decomposed block, one rank per GPU (`dist` = torch.distributed, initialised).  Every rank
+    advances ITS slab of the host-resident block window by window; the guard + halo planes its first and last windows need
+    from the neighbouring slabs are pulled out of the neighbours' staging copies over NVLink right after those planes were
+    uploaded.  The windows then run without any per-stage halo exchange -- the guard planes absorb it -- so the ranks do not
+    wait for each other during the sweeps.  q_in / q_out: this rank's padded slab arrays (decomp.local_extent); the grid points
+    of q_out equal those of the decomposed in-HBM run bit for bit; its halo planes along the slab axis are not written."""
+
+    def __init__(self, plan_global, dist, device, chunk=64, nsteps=1, contexts=3, factory=None, stage_factory=None, exchange=None):
+        from .decomp import local_extent, neighbours
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        plan_global = _plan.validate(copy.deepcopy(plan_global))
+        self.offset, self.nloc = local_extent(plan_global, self.rank, self.world)
+        self.low, self.high = neighbours(plan_global, self.rank, self.world)
+        if self.world > 1 and (self.low is None or self.high is None):
+            raise _plan.PlanError('window pipeline: the slab axis must be periodic')
+        self.n_low = local_extent(plan_global, self.low, self.world)[1] if self.world > 1 else 0
+        self.pipe = HostPipeline(plan_global, chunk=chunk, nsteps=nsteps, device=device, contexts=contexts, factory=factory,
+                                 stage_factory=stage_factory, slab=(self.offset, self.nloc) if self.world > 1 else None,
+                                 exchange=(exchange or self._exchange) if self.world > 1 else None)
+        if self.world > 1 and exchange is None:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.pipe.stage.ipc_export())
+            self.pipe.stage.ipc_import(0, handles[self.low])
+            self.pipe.stage.ipc_import(1, handles[self.high])
+            self._barrier()
+
+    def _barrier(self):
+        if self.dist.get_backend() == 'nccl':
+            import torch
+            self.dist.barrier(device_ids=[torch.cuda.current_device()])
+        else:
+            self.dist.barrier()
+
+    def _exchange(self, stage, G, n):
+        self._barrier()                                   # every rank's boundary planes are in its staging copy
+        stage.pull(0, self.n_low, 0, G)                   # low neighbour's top G planes (its staging planes [n_low, n_low + G))
+        stage.pull(1, G, G + n, G)                        # high neighbour's bottom G planes (its staging planes [G, 2G))
+        stage.sync()
+        self._barrier()                                   # nobody re-uploads while a neighbour is still reading
+
+    def advance(self, q_in, q_out):
+        return self.pipe.advance(q_in, q_out)
+
+    def bytes_per_call(self):
+        return self.pipe.bytes_per_call()
+
+    def close(self):
+        self.pipe.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

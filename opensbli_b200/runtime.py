@@ -20,6 +20,7 @@ SYMBOLS = ('osb_create', 'osb_destroy', 'osb_last_error', 'osb_set_const_f64', '
            'osb_launch_count', 'osb_slow_path_count', 'osb_profile_step', 'osb_nan_check', 'osb_diagnostics', 'osb_ipc_export', 'osb_ipc_import', 'osb_halo_push',
            'osb_host_planes_upload', 'osb_host_planes_ready', 'osb_host_planes_download', 'osb_host_planes_sync',
            'osb_staging_create', 'osb_staging_destroy', 'osb_staging_last_error', 'osb_staging_upload', 'osb_staging_feed', 'osb_staging_fed', 'osb_staging_sync',
+           'osb_staging_ipc_export', 'osb_staging_ipc_import', 'osb_staging_pull',
            'osb_measure_fp64_peak')
 
 
@@ -89,6 +90,9 @@ def load_library(path=None):
     lib.osb_staging_feed.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.osb_staging_fed.argtypes = [ctypes.c_void_p]
     lib.osb_staging_sync.argtypes = [ctypes.c_void_p]
+    lib.osb_staging_ipc_export.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
+    lib.osb_staging_ipc_import.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    lib.osb_staging_pull.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     _lib = lib
     return lib
 
@@ -119,6 +123,18 @@ class Stage(object):
 
     def sync(self):
         self._check(self.lib.osb_staging_sync(self.h), 'osb_staging_sync')
+
+    def ipc_export(self):
+        buf = ctypes.create_string_buffer(64 * 8)
+        n = ctypes.c_int()
+        self._check(self.lib.osb_staging_ipc_export(self.h, buf, ctypes.byref(n)), 'osb_staging_ipc_export')
+        return buf.raw[:n.value]
+
+    def ipc_import(self, side, handles):
+        self._check(self.lib.osb_staging_ipc_import(self.h, int(side), handles, len(handles)), 'osb_staging_ipc_import')
+
+    def pull(self, side, src_plane0, dst_plane0, nplanes):
+        self._check(self.lib.osb_staging_pull(self.h, int(side), int(src_plane0), int(dst_plane0), int(nplanes)), 'osb_staging_pull')
 
     def close(self):
         if self.h:
