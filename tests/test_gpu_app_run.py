@@ -431,3 +431,19 @@ def test_bench_workloads_through_the_generic_path(name, fixture):
     err = field_errors(want, q, states[3])
     print(name, err)
     assert max(err) < 1e-12, err
+
+
+def test_generic_path_app_full_run_with_the_runner(tmp_path):
+    """`python -m opensbli_b200.run` on a generic-path program as a user runs it: the Sod tube with WENO7 (1000 steps of the
+    app's own niter), dataset file written in the reference's layout, L1 error against the exact solution of the order the
+    fifth-order schemes reach on this grid."""
+    from opensbli_b200 import run as R, iodata
+    for f in ('opensbli_b200.plan.json', 'opensbli.cpp'):
+        shutil.copy(os.path.join(PLANS, 'sod_weno7', f), str(tmp_path))
+    assert R.main([str(tmp_path)]) == 0
+    out, attrs = iodata.read_datasets(os.path.join(str(tmp_path), 'opensbli_output'))
+    assert {'rho', 'rhou0', 'rhoE'} <= set(out)
+    rho = iodata.strip_halos(out['rho'], attrs['rho'])
+    x = np.arange(200) / 199.0
+    l1 = np.mean(np.abs(rho - sod_exact_density(x, 0.2)))
+    assert np.isfinite(rho).all() and l1 < 4e-3, l1
