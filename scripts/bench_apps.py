@@ -18,6 +18,12 @@ CASES = [
     ('trans', {'block0np0': 240, 'block0np1': 120, 'block0np2': 64}, 20, 'trans'),
     ('vst', {'block0np0': 500, 'block0np1': 250}, 400, 'vst'),
     ('ewc', {'block0np0': 512, 'block0np1': 512}, 200, 'ewc'),
+    # filters (run-time compiled UserDefinedEquations loops after every step of the hand-written kernels)
+    ('katzer_sfd', {'block0np0': 500, 'block0np1': 250}, 400, 'katzer_sfd'),
+    ('tgv_wf', {'block0np0': 128, 'block0np1': 128, 'block0np2': 128, 'dt': 0.003385 * 64 / 128}, 20, 'tgv_wf'),
+    # programs on the generic path (every loop of the step printed from its equations, NVRTC)
+    ('tg_isot', {'block0np0': 129, 'block0np1': 129, 'block0np2': 129, 'dt': 0.0015}, 20, 'tg_isot'),
+    ('sod_weno7', {'block0np0': 100000, 'dt': 4e-7}, 200, 'sod_weno7'),
 ]
 
 
@@ -34,7 +40,7 @@ def main():
             sim.step(3)
             ms = sim.step_timed(nsteps)
             finite = bool(np.isfinite(sim.download('rho')).all())
-        line = {'app': name, 'np': plan['np'], 'steps': nsteps, 'ms_per_step': ms / nsteps, 'updates_per_s': pts * nsteps / (ms * 1e-3), 'finite': finite}
+        line = {'app': name, 'path': 'generic' if plan['conv'] == 'generic' else 'hand-written', 'np': plan['np'], 'steps': nsteps, 'ms_per_step': ms / nsteps, 'updates_per_s': pts * nsteps / (ms * 1e-3), 'finite': finite}
         if ref and ou.have_ref(ref) and '--no-cpu' not in sys.argv:
             n = max(2, nsteps // 10)
             r = ou.run_ref(ref, dict(over, niter=n), [], exe='ref_omp', threads=os.cpu_count())
