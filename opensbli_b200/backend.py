@@ -1087,6 +1087,9 @@ def _extract_specialised(algorithm):
             continue
         nloops = loops.count('DoLoop')
         seen_loop = seen_loop or 'Timers' in loops or nloops > 0
+        if 'Condition' in loops and type(c).__name__ in ('Kernel', 'ExchangeSelf'):
+            # InTheSimulation(frequency=N) on a loop (algorithm.py:456-463): only dataset files are honoured every N iterations
+            raise _NotForGenericPath('loop %s runs under a condition (every N iterations): conditional loops are not implemented' % _name(c))
         if nloops == 0 and 'Timers' not in loops:
             (after if seen_loop else before).append(c)          # top level: before / after the timed time loop
         elif nloops == 1:
