@@ -1237,6 +1237,7 @@ int osb_sync(osb_ctx *c) {
 int osb_apply_bcs(osb_ctx *c) {
   if (!c) return 1;
   cudaSetDevice(c->device);
+  if (c->plan.conv == CONV_GENERIC) return run_user_kernels(c, 200);     // generic path: the iteration-start list IS the boundary pass
   if (launch_bcs(c)) return 1;
   OSB_CUDA(c, cudaGetLastError());
   return 0;
@@ -1244,6 +1245,7 @@ int osb_apply_bcs(osb_ctx *c) {
 int osb_residual(osb_ctx *c) {
   if (!c) return 1;
   cudaSetDevice(c->device);
+  if (c->plan.conv == CONV_GENERIC) return fail(c, "osb_residual: a program on the generic path has no separate residual evaluation (its stage lists include the RK update)");
   switch (c->plan.nd) { case 1: launch_residual<1>(c); break; case 2: launch_residual<2>(c); break; default: launch_residual<3>(c); }
   OSB_CUDA(c, cudaGetLastError());
   return 0;
