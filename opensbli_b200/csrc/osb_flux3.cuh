@@ -63,6 +63,10 @@ OSB_HD void f3_put(double *G, const int GS, const int p, const double gp, const 
 struct WinAffine { int PS; OSB_HD int off(int p) const { return p * PS; } };
 struct WinRing { int row0, mask; OSB_HD int off(int p) const { return ((row0 + p) & mask) * 32; } };
 
+#ifndef OSB_F3_UNROLL_ACOUSTIC
+#define OSB_F3_UNROLL_ACOUSTIC 1     // 2: both acoustic waves interleaved (more ILP, more registers)
+#endif
+constexpr int F3_UNROLL_ACOUSTIC = OSB_F3_UNROLL_ACOUSTIC;
 template <int ND, int DIR, int RECON, int AVG, typename WIN>
 OSB_HD void interface_flux_split(const double *sb, const WIN win, const int VS, double *G, const int GS,
                                  const double gama, const SchemeParams &sp, double *flux) {
@@ -146,7 +150,7 @@ OSB_HD void interface_flux_split(const double *sb, const WIN win, const int VS, 
     }
   }
   // ---- pass 2: the acoustic reconstructions, one wave at a time (rolled: one copy of the reconstruction code)
-#pragma unroll 1
+#pragma unroll F3_UNROLL_ACOUSTIC
   for (int w = 0; w < 2; w++) {
     double ga[NS], gb[NS];
 #pragma unroll
