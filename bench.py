@@ -303,7 +303,8 @@ def main():
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak: --size^3 points per GPU (default); strong: one --grid^3 block cut over all GPUs (BASELINE configs[4])')
     ap.add_argument('--grid', type=int, default=1024, help='strong scaling: points per direction of the whole block')
-    ap.add_argument('--state', default='smooth', choices=['smooth', 'perturbed'],
+    ap.add_argument('--develop-time', type=float, default=4.0, help='--state developed: time units the half-size box is advanced for')
+    ap.add_argument('--state', default='smooth', choices=['smooth', 'perturbed', 'developed'],
                     help='smooth: analytic TGV field (every TENO stencil passes the cut-off: the best case of the all-pass shortcut); '
                          'perturbed: the same field with 5 %% random noise (nearly every wave takes the full cut-off path: the worst case)')
     ap.add_argument('--no-secondary', action='store_true', help='skip the Central-4 (BASELINE configs[1] scheme) line carried as `secondary`')
@@ -355,8 +356,32 @@ def main():
     hout = [torch.empty(shape, dtype=torch.float64, pin_memory=True) for _ in range(5)] if pin else []
     q_in = [t.numpy() for t in hin]
     q_out = [t.numpy() for t in hout]
+    developed = None
+    if args.state == 'developed':
+        # a flow with small scales in it: the vortex on a box of half the size per direction (same Mach and Reynolds numbers)
+        # advanced to t = --develop-time on this GPU with the same kernels, then tiled 2 x 2 x 2 -- what TENO sees are the
+        # differences between neighbouring cells, which the tiling keeps.  Single GPU, cubic block.
+        if world != 1 or args.scaling != 'weak' or args.size % 2:
+            raise SystemExit('--state developed: one GPU, even --size')
+        h = args.size // 2
+        hp = tgv_plan([h] * 3, args.workload)
+        nst = int(math.ceil(args.develop_time / hp['constants']['dt']))
+        from opensbli_b200 import Simulation
+        with Simulation(hp, device=local_rank) as small:
+            b = [np.zeros((h + 10,) * 3) for _ in range(5)]
+            tgv_state_into(b, hp, 0, h)
+            small.set_state(b)
+            small.step(nst)
+            developed = [np.tile(a[5:-5, 5:-5, 5:-5], (2, 2, 2)) for a in small.get_state()]
+        if not all(np.isfinite(a).all() for a in developed):
+            raise SystemExit('--state developed: the precursor run is not finite')
+        developed_note = 'TGV on %d^3 advanced %d steps to t = %.2f with the same kernels, tiled 2 x 2 x 2' % (h, nst, nst * hp['constants']['dt'])
+
     def fill_state(bufs):
         tgv_state_into(bufs, lplan, k0, nk)
+        if developed is not None:
+            for b, a in zip(bufs, developed):
+                b[5:-5, 5:-5, 5:-5] = a
         if args.state == 'perturbed':           # 5 % multiplicative noise on every conserved variable, seeded per rank
             rng = np.random.default_rng(1234 + rank)
             for b in bufs:
@@ -571,7 +596,7 @@ def main():
                 'fp64_peak': {'measured_tflops': fp64_peak, 'how': 'osb_measure_fp64_peak: 8 independent DFMA chains per thread, 148 x 8 blocks x 256 threads, 16384 iterations, best of 4',
                               'sm_mhz_during_run': clocks.get('sm_mhz'), 'theoretical_tflops_at_max_clock': 148 * 64 * 2 * (clocks.get('sm_max_mhz') or 1965.0) * 1e6 / 1e12,
                               'note': '64 FP64 FMA lanes per SM; MEASURED_PEAKS.json carries no FP64 entry'},
-                'state': {'kind': args.state, 'waves_on_full_cutoff_path': slow_fraction,
+                'state': {'kind': args.state if developed is None else 'developed: ' + developed_note, 'waves_on_full_cutoff_path': slow_fraction,
                           'note': 'share of TENO5 characteristic waves (5 per interface per sweep) that needed the full cut-off evaluation in one step after the timed region'},
                 'families_ms_rank0': {k: v['ms'] for k, v in prof.items()} if prof else None,
                 'alg_flop_per_update': ALG_FLOP_PER_UPDATE, 'achieved_alg_tflops': ALG_FLOP_PER_UPDATE * value / world / 1e12}
