@@ -229,21 +229,46 @@ OSB_HD double weno5_side(double gm2, double gm1, double g0, double g1, double g2
   const double b0 = 0.25 * ((13.0 / 12.0) * sq(g0 - 2.0 * g1 + g2) + 0.25 * sq(3.0 * g0 - 4.0 * g1 + g2));
   const double b1 = 0.25 * ((13.0 / 12.0) * sq(gm1 - 2.0 * g0 + g1) + 0.25 * sq(gm1 - g1));
   const double b2 = 0.25 * ((13.0 / 12.0) * sq(gm2 - 2.0 * gm1 + g0) + 0.25 * sq(gm2 - 4.0 * gm1 + 3.0 * g0));
-  double a0, a1, a2;
+  // alpha_r = d_r / (beta_r + eps)^2 (JS, weno.py:354) or d_r (1 + tau^2 / (beta_r + eps)^2) (Z, weno.py:323), each a division in
+  // the reference.  Only the RATIOS alpha_r / sum(alpha) enter, so every alpha is taken over the common denominator
+  // D0 D1 D2, D_r = (beta_r + eps)^2: n_r = d_r (D_r [+ tau^2 for Z] ... ) prod_{s != r} D_s -- one division per side instead
+  // of four.  The D_r are rescaled by an exact power of two first, so the products stay inside the double range.
+#ifdef OSB_WENO_FOUR_DIVISIONS        // the reference's form, kept for A/B measurements (scripts/weno_speed.py)
+  {
+    double a0, a1, a2;
+    if (!Z) {
+      const double e = 1.0e-6;
+      a0 = (3.0 / 10.0) / sq(b0 + e); a1 = (3.0 / 5.0) / sq(b1 + e); a2 = (1.0 / 10.0) / sq(b2 + e);
+    } else {
+      const double e = 1.0e-14;
+      const double t2 = sq(b0 - b2);
+      a0 = (3.0 / 10.0) + (3.0 / 10.0) * t2 / sq(b0 + e);
+      a1 = (3.0 / 5.0) + (3.0 / 5.0) * t2 / sq(b1 + e);
+      a2 = (1.0 / 10.0) + (1.0 / 10.0) * t2 / sq(b2 + e);
+    }
+    const double q0 = (1.0 / 6.0) * (2.0 * g0 + 5.0 * g1 - g2);
+    const double q1 = (1.0 / 6.0) * (-gm1 + 5.0 * g0 + 2.0 * g1);
+    const double q2 = (1.0 / 6.0) * (2.0 * gm2 - 7.0 * gm1 + 11.0 * g0);
+    return (a0 * q0 + a1 * q1 + a2 * q2) / (a0 + a1 + a2);
+  }
+#endif
+  const double e = Z ? 1.0e-14 : 1.0e-6;
+  double D0 = sq(b0 + e), D1 = sq(b1 + e), D2 = sq(b2 + e);
+  const double sc = inv_pow2(dmax2(D0, dmax2(D1, D2)));
+  D0 *= sc; D1 *= sc; D2 *= sc;
+  double n0, n1, n2;
   if (!Z) {
-    const double e = 1.0e-6;
-    a0 = (3.0 / 10.0) / sq(b0 + e); a1 = (3.0 / 5.0) / sq(b1 + e); a2 = (1.0 / 10.0) / sq(b2 + e);
+    n0 = (3.0 / 10.0) * (D1 * D2); n1 = (3.0 / 5.0) * (D0 * D2); n2 = (1.0 / 10.0) * (D0 * D1);
   } else {
-    const double e = 1.0e-14;
-    const double t2 = sq(b0 - b2);
-    a0 = (3.0 / 10.0) + (3.0 / 10.0) * t2 / sq(b0 + e);
-    a1 = (3.0 / 5.0) + (3.0 / 5.0) * t2 / sq(b1 + e);
-    a2 = (1.0 / 10.0) + (1.0 / 10.0) * t2 / sq(b2 + e);
+    const double t2 = sq(b0 - b2) * sc;
+    n0 = (3.0 / 10.0) * ((D0 + t2) * (D1 * D2));
+    n1 = (3.0 / 5.0) * ((D1 + t2) * (D0 * D2));
+    n2 = (1.0 / 10.0) * ((D2 + t2) * (D0 * D1));
   }
   const double q0 = (1.0 / 6.0) * (2.0 * g0 + 5.0 * g1 - g2);
   const double q1 = (1.0 / 6.0) * (-gm1 + 5.0 * g0 + 2.0 * g1);
   const double q2 = (1.0 / 6.0) * (2.0 * gm2 - 7.0 * gm1 + 11.0 * g0);
-  return (a0 * q0 + a1 * q1 + a2 * q2) / (a0 + a1 + a2);
+  return (n0 * q0 + n1 * q1 + n2 * q2) / (n0 + n1 + n2);
 }
 
 // Both sides for one characteristic field.  cf[p], cs[p], p=0..5 <-> points -2..3; lam = max |lambda|.
