@@ -88,6 +88,17 @@ def tgv_state_into(bufs, plan, k0, nk, halo=5):
     bufs[4][s] = p / (g - 1.0) + 0.5 * r * (u0 * u0 + u1 * u1)
 
 
+def pipeline_fits(plan, nloc, chunk, contexts, torch):
+    """the window contexts (about 26 arrays each) and the staging copy of the pipelined end-to-end leg next to what is already
+    on the device: skip the leg rather than run the device out of memory (large strong-scaling slabs)"""
+    plane = 8.0
+    for n in plan['np'][:-1]:
+        plane *= n + 10
+    need = (contexts * (chunk + 2 * 8 + 10) * 26 + (nloc + 32) * 5) * plane
+    free, _ = torch.cuda.mem_get_info()
+    return need < 0.8 * free, need, free
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
@@ -495,6 +506,9 @@ def main():
             # sweep of window k and the download of window k-1 overlap (hostpipe.py); host wall clock around the call
             try:
                 from opensbli_b200.hostpipe import HostPipeline
+                ok_, need_, free_ = pipeline_fits(plan, plan['np'][2], 64 if args.e2e_chunk == 'ramp' else int(args.e2e_chunk), args.e2e_contexts, torch)
+                if not ok_:
+                    raise MemoryError('pipelined leg skipped: needs about %.0f GB, %.0f GB free on the device' % (need_ / 1e9, free_ / 1e9))
                 with HostPipeline(plan, chunk=(args.e2e_chunk if args.e2e_chunk == 'ramp' else int(args.e2e_chunk)), nsteps=1, device=local_rank, contexts=args.e2e_contexts) as pipe:
                     pipe.advance(src, dst)        # warm-up (module load, first-touch of the window contexts)
                     src, dst = dst, src
@@ -532,6 +546,11 @@ def main():
             # neighbours' staging copies over NVLink, so there is no per-stage halo exchange at all (hostpipe.DistributedHostPipeline)
             try:
                 from opensbli_b200.hostpipe import DistributedHostPipeline
+                ok_, need_, free_ = pipeline_fits(plan, nk, int(args.e2e_chunk), args.e2e_contexts, torch)
+                fits = torch.tensor([1.0 if ok_ else 0.0], dtype=torch.float64, device='cuda')
+                dist.all_reduce(fits, op=dist.ReduceOp.MIN)          # all ranks take the same branch
+                if float(fits.item()) < 1.0:
+                    raise MemoryError('pipelined leg skipped: needs about %.0f GB per rank, %.0f GB free on the device' % (need_ / 1e9, free_ / 1e9))
                 with DistributedHostPipeline(plan, dist, local_rank, chunk=int(args.e2e_chunk), nsteps=1, contexts=args.e2e_contexts) as dp:
                     src, dst = q_in, q_out
                     dp.advance(src, dst)          # warm-up
