@@ -171,15 +171,22 @@ def user_kernel_source(k, index, env, nd, stage=None):
         L.append('  const int stage = %d; (void)stage;' % stage)
     for n, name in enumerate(fields):
         L.append('  double *%s = f.p[%d];' % (name, n))
+    # a kernel-local variable may carry the name of a dataset the kernel also touches (the reference tells `x0` from `x0_B0[...]`;
+    # here datasets lost the suffix): such a local is renamed -- a dataset name is always followed by its index, a local never
+    clash = {name: re.compile(r'\b%s\b(?!\s*\[)' % re.escape(name)) for name in dict.fromkeys(k['locals']) if name in fields}
+    def loc(text):
+        for name, rx in clash.items():
+            text = rx.sub(name + '_local', text)
+        return text
     for name in dict.fromkeys(k['locals']):
-        L.append('  double %s = 0.0;' % name)       # kernel locals start at zero, as in the reference's generated C (opsc.py:340-343)
+        L.append('  double %s = 0.0;' % loc(name))       # kernel locals start at zero, as in the reference's generated C (opsc.py:340-343)
     for st in k['statements']:
         lhs, is_field, rhs = st[0], st[1], st[2]
         if lhs in ('#if', '#elif', '#else', '#end'):              # GroupedPiecewise: equations under if / else if / else (opsc.py:372-397)
-            L.append({'#if': '  if (%s) {' % rhs, '#elif': '  } else if (%s) {' % rhs, '#else': '  } else {', '#end': '  }'}[lhs])
+            L.append({'#if': '  if (%s) {' % loc(rhs or ''), '#elif': '  } else if (%s) {' % loc(rhs or ''), '#else': '  } else {', '#end': '  }'}[lhs])
             continue
         at = (st[3] if len(st) > 3 and st[3] else 'X')            # relative write (boundary kernels): index printed by the back end
-        L.append('  %s%s = %s;' % (lhs, '[%s]' % at if is_field else '', rhs))
+        L.append('  %s%s = %s;' % (lhs if is_field else loc(lhs), '[%s]' % at if is_field else '', loc(rhs)))
     L.append('}')
     rng = [int(c_eval(r, env)) for r in k['range']]
     if 'one_plane_along' in k:              # SplitBC part: the race check of the back end relied on it

@@ -85,6 +85,12 @@ APPS = {
     'tgv_teno5_allprinted': (os.path.join(REPO, 'apps', 'tgv_teno5.py'), [], None, {'OSB_FORCE_GENERIC_PATH': '1'}),
     'tgv_central4_allprinted': (REF + '/apps/taylor_green_vortex/taylor_green_vortex.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None,
                                     {'OSB_FORCE_GENERIC_PATH': '1'}),
+    # ... and three general-path apps forced through it: stretched grid + ReducedAccess closures + adaptive TENO + wall / inflow / outflow
+    # kernels (Katzer), 3-D channel with TENO6, Carpenter closures, power-law viscosity and body force, fully curvilinear WENO-Z
+    'katzer_allprinted': (REF + '/apps/katzer_SBLI/katzer_SBLI.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None, {'OSB_FORCE_GENERIC_PATH': '1'}),
+    'tcf_teno6_allprinted': (REF + '/apps/channel_flow/compressible_TCF_TENO/turbulent_channel.py',
+                             [("stats = True", "stats = False"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None, {'OSB_FORCE_GENERIC_PATH': '1'}),
+    'ewc_allprinted': (REF + '/apps/euler_wave_curvilinear/euler_wave.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None, {'OSB_FORCE_GENERIC_PATH': '1'}),
     # InletTransferBC has no hand-written kernel: generic by itself (Sod with the left boundary copied from its first halo point)
     'sod_inlet_transfer': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("boundaries += [DirichletBC(direction, 0, left_eqns)]", "boundaries += [InletTransferBC(direction, 0)]"),
                                                                             ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None),

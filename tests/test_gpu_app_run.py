@@ -447,3 +447,28 @@ def test_generic_path_app_full_run_with_the_runner(tmp_path):
     x = np.arange(200) / 199.0
     l1 = np.mean(np.abs(rho - sod_exact_density(x, 0.2)))
     assert np.isfinite(rho).all() and l1 < 4e-3, l1
+
+
+@pytest.mark.parametrize('name,fixture,over,nsteps', [('katzer_allprinted', 'katzer_60x40', {'block0np0': 60, 'block0np1': 40}, 10),
+                                                      ('ewc_allprinted', 'ewc_wenoz5_32', {'block0np0': 32, 'block0np1': 32}, 10),
+                                                      ('tcf_teno6_allprinted', 'tcf_teno6_16x24x12', {'block0np0': 16, 'block0np1': 24, 'block0np2': 12}, 5)])
+def test_general_path_apps_through_the_generic_path(name, fixture, over, nsteps):
+    """Katzer (stretched grid, closures, adaptive TENO, wall / inflow / outflow kernels), the 3-D TENO6 channel and the fully
+    curvilinear Euler wave forced through the generic path on the GPU (NVRTC): the goldens of the reference's generated C.  The same
+    sources run on the host in tests/test_printed_kernels_cpu.py."""
+    from opensbli_b200 import run as R, Simulation
+    want, states = load_fixture(fixture)
+    plan_sym, env, plan, cold = R.load_case(os.path.join(PLANS, name), overrides=over)
+    assert plan['conv'] == 'generic'
+    q0 = R.initial_state(plan_sym, cold)
+    with Simulation(plan) as sim:
+        if name.startswith('katzer'):             # the reference's own cold data (ill-conditioned polynomial initial profile)
+            q0 = [np.ascontiguousarray(a) for a in want['q0_padded']]
+            for f, a in want['fields'].items():
+                sim.upload(f, np.ascontiguousarray(a))
+        sim.set_state(q0)
+        sim.step(nsteps)
+        q = inner(plan, sim.get_state())
+    err = field_errors(want, q, states[nsteps])
+    print(name, err)
+    assert max(err) < 1e-12, err
