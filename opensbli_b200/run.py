@@ -239,6 +239,16 @@ def resolve(plan_sym, env):
     written = set(w for k in p['user_kernels'] for w in k['writes'])
     p['user_fields'] = {f: cold.array(f).copy() for k in p['user_kernels'] for f in k['fields']
                         if f in cold.arrays and f not in plan_sym['q_names']}
+    if plan_sym.get('generic'):
+        # generic path: a dataset some loop reads but no loop writes and the cold path never evaluated holds the zeros OPS declares
+        # it with (e.g. `u2` of StoreSome(4, 'u0 u1 u2 T') in a 2-D app, katzer_SBLI.py:60-75) -- declared explicitly, and listed
+        known = set(plan_sym['q_names']) | set('u%d' % d for d in range(nd)) | {'p', 'a', 'T'} | \
+            set('Residual%d' % m for m in range(nd + 2)) | set(pre + n for n in plan_sym['q_names'] for pre in ('tempRK_',)) | \
+            set(n + '_RKold' for n in plan_sym['q_names'])
+        zero = sorted(set(f for k in p['user_kernels'] for f in k['fields']) - written - set(p['user_fields']) - known)
+        for f in zero:
+            p['user_fields'][f] = np.zeros(cold.shape)
+        p['zero_datasets'] = zero
     if plan_sym.get('monitor'):
         m = dict(plan_sym['monitor'])
         m['probes'] = [[int(c_eval(x, env)) for x in pr] for pr in m['probes']]
@@ -496,6 +506,10 @@ def main(argv=None):
     plan_sym, env, plan_num, cold = load_case(workdir)
     stub = open(os.path.join(workdir, STUB_FILE)).read()
     q0 = initial_state(plan_sym, cold)
+    if plan_num.get('generic'):
+        print('B200: generic path (%s): %d run-time compiled loops per step' % (plan_num['generic'].get('reason'), len(plan_num['user_kernels'])))
+        if plan_num.get('zero_datasets'):
+            print('B200: datasets read but never written hold zeros, as OPS declares them: %s' % ', '.join(plan_num['zero_datasets']))
     if args.restart:                                  # the reference's ops_decl_dat_hdf5 route (opsc.py:702-705, generate_restart.py)
         from . import iodata
         data, _ = iodata.read_datasets(args.restart if os.path.isabs(args.restart) else os.path.join(workdir, args.restart))
