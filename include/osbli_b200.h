@@ -147,7 +147,9 @@ int osb_diagnostics(osb_ctx *ctx, double *sums /* [OSB_NDIAG] */);
  * apps/channel_flow/*: stats.py, opsc.py kernel emission): app-specific arithmetic outside the solver's hot loops, given as
  * CUDA C source of one `extern "C" __global__` entry with the signature
  *     entry(long long off, int n0, int n1, int n2, int lo0, int lo1, int lo2, long long s1, long long s2, UserFields f)
- * where `struct UserFields { double *p[OSB_MAX_USER_FIELDS]; }` holds the arrays named in `fields` (comma separated).  A name
+ * where `struct UserFields { double *p[OSB_MAX_USER_FIELDS]; long long iter; }` holds the arrays named in `fields` (comma separated)
+ * and the loop counter of the time loop (what the reference hands to a kernel as ops_arg_gbl `iter`; a kernel that reads `f.iter`
+ * keeps the step out of the CUDA-graph replay).  A name
  * prefixed with '+' is written by the kernel: if it does not exist yet it is created zero-initialised, as OPS declares
  * datasets (opsc.py:693-722).  A name the kernel only reads must exist (solver field, or osb_create_field + osb_upload):
  * otherwise the call fails -- reading zeros in place of a dataset nobody provided would be a silent wrong answer.

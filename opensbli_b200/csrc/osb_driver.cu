@@ -123,7 +123,7 @@ struct osb_ctx {
   long long graph_launches = 0;
   bool use_graph = true;
   long long iteration = 0;                      // loop counter of algorithm.py:440-474 (argument of the mass source)
-  struct UserKernel { cudaLibrary_t lib = nullptr; cudaKernel_t kern = nullptr; std::vector<std::string> fields; int range[6]; int when = 0; bool writes_state = false; };
+  struct UserKernel { cudaLibrary_t lib = nullptr; cudaKernel_t kern = nullptr; std::vector<std::string> fields; int range[6]; int when = 0; bool writes_state = false; bool uses_iter = false; };
   std::vector<UserKernel> user_kernels;
   unsigned long long *slow_count = nullptr;     // bench instrumentation (osb_slow_path_count)
   bool count_slow = false;
@@ -744,7 +744,7 @@ void launch_central_fused(osb_ctx *c, int stage) {
 }
 
 // ---- run-time compiled point-wise user kernels ---------------------------------------------------
-struct UserFields { double *p[OSB_MAX_USER_FIELDS]; };
+struct UserFields { double *p[OSB_MAX_USER_FIELDS]; long long iter; };     // iter: the loop counter the reference hands to kernels as ops_arg_gbl
 
 bool is_primitive(const osb_ctx *c, const double *dev) {
   bool prim = dev == c->fp.p || dev == c->fp.a || dev == c->fp.T;
@@ -764,6 +764,7 @@ int run_user_kernels(osb_ctx *c, int when) {
     if (c->prim_stale && c->plan.conv != CONV_GENERIC)
       for (auto &n : k.fields) { Field *f = find_field(c, n.c_str()); if (f && is_primitive(c, f->dev)) { launch_prim_nd(c); break; } }
     UserFields uf{};
+    uf.iter = c->iteration;
     for (size_t i = 0; i < k.fields.size(); i++) {
       Field *f = find_field(c, k.fields[i].c_str());
       if (!f) return fail(c, "user kernel field vanished: " + k.fields[i]);
@@ -873,7 +874,9 @@ void drop_graph(osb_ctx *c) {
 // kernels carry a new epoch number every stage).
 int do_step(osb_ctx *c, int nsteps) {
   const long long pts = (long long)c->grid.np[0] * c->grid.np[1] * c->grid.np[2];
-  if (!c->use_graph || c->profiling || c->plan.mass_source || has_exchange(c) || pts > (1LL << 22) || nsteps < 2) return step_dispatch(c, nsteps);
+  bool iter_kernels = false;
+  for (auto &k : c->user_kernels) iter_kernels = iter_kernels || k.uses_iter;
+  if (!c->use_graph || c->profiling || c->plan.mass_source || iter_kernels || has_exchange(c) || pts > (1LL << 22) || nsteps < 2) return step_dispatch(c, nsteps);
   // the fused central path exchanges buffer roles every stage: the captured unit must bring them back (two steps if the
   // number of stages is odd) and may only be replayed from the parity it was captured at (0)
   const int unit = ((fused_central_ok(c) || viscous_from_q_ok(c)) && (c->plan.rk_a.size() % 2)) ? 2 : 1;
@@ -1058,6 +1061,7 @@ int osb_add_user_kernel(osb_ctx *c, const char *source, const char *entry, const
   cudaSetDevice(c->device);
   osb_ctx::UserKernel k;
   k.when = when;
+  k.uses_iter = strstr(source, "f.iter") != nullptr;           // reads the loop counter: its launches cannot be replayed from a captured graph
   for (int i = 0; i < 6; i++) k.range[i] = range[i];
   std::vector<bool> written;
   {

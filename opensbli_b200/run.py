@@ -151,7 +151,7 @@ def user_kernel_source(k, index, env, nd, stage=None):
         raise ValueError('kernel %s touches %d datasets (limit 96, OSB_MAX_USER_FIELDS)' % (k['name'], len(fields)))
     entry = 'osb_user_kernel_%d' % index
     text = ' '.join(s[2] for s in k['statements'] if s[2])
-    L = ['struct UserFields { double *p[96]; };']          # OSB_MAX_USER_FIELDS (include/osbli_b200.h)
+    L = ['struct UserFields { double *p[96]; long long iter; };']          # OSB_MAX_USER_FIELDS (include/osbli_b200.h)
     for name, val in env.items():                       # the constants the statements mention, as the reference's C globals
         if not isinstance(val, list) and re.search(r'\b%s\b' % re.escape(name), text):
             # integer parameters (block0np<d>, niter) stay integers, as the reference's C globals are: index arithmetic and
@@ -169,6 +169,8 @@ def user_kernel_source(k, index, env, nd, stage=None):
         L.append('  const double %s[%d] = {%s};' % (name, len(vals), ', '.join(repr(float(v)) for v in vals)))
     if stage is not None:
         L.append('  const int stage = %d; (void)stage;' % stage)
+    if re.search(r'\biter\b', text):                      # the loop counter, an ops_arg_gbl in the reference (e.g. sin(omega dt iter))
+        L.append('  const int iter = (int)f.iter;')
     for n, name in enumerate(fields):
         L.append('  double *%s = f.p[%d];' % (name, n))
     # a kernel-local variable may carry the name of a dataset the kernel also touches (the reference tells `x0` from `x0_B0[...]`;

@@ -33,8 +33,8 @@ class HostKernels(object):
         for n, k in enumerate(kernels):
             body = k['source'].replace('extern "C" ', '')
             src.append('namespace hk%d {\n%s\n}' % (n, body))
-            src.append('extern "C" void hostrun_%d(long long off, int n0, int n1, int n2, int lo0, int lo1, int lo2, long long s1, long long s2, double **p, int nf) {\n'
-                       '  hk%d::UserFields f; for (int i = 0; i < nf; i++) f.p[i] = p[i];\n  blockDim = {1, 1, 1}; threadIdx = {0, 0, 0};\n'
+            src.append('extern "C" void hostrun_%d(long long off, int n0, int n1, int n2, int lo0, int lo1, int lo2, long long s1, long long s2, double **p, int nf, long long iter) {\n'
+                       '  hk%d::UserFields f; for (int i = 0; i < nf; i++) f.p[i] = p[i]; f.iter = iter;\n  blockDim = {1, 1, 1}; threadIdx = {0, 0, 0};\n'
                        '  for (int z = 0; z < n2; z++) for (int y = 0; y < n1; y++) for (int x = 0; x < n0; x++) { blockIdx = {x, y, z};\n'
                        '    hk%d::%s(off, n0, n1, n2, lo0, lo1, lo2, s1, s2, f); }\n}' % (n, n, n, k['entry']))
         text = '\n'.join(src)
@@ -53,7 +53,7 @@ class HostKernels(object):
             self.fields[name] = np.zeros(self.shape)          # datasets start zeroed (OPS semantics)
         return self.fields[name]
 
-    def run(self, when):
+    def run(self, when, iteration=0):
         h, nd = self.h, self.nd
         pd = list(reversed(self.shape))                         # padded extents, x first
         s1 = pd[0] if nd > 1 else 0
@@ -67,4 +67,4 @@ class HostKernels(object):
             ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
             r = list(k['range']) + [0, 1] * (3 - nd)
             getattr(self.lib, 'hostrun_%d' % n)(ctypes.c_longlong(off), r[1] - r[0], r[3] - r[2], r[5] - r[4], r[0], r[2], r[4],
-                                                ctypes.c_longlong(s1), ctypes.c_longlong(s2), ptrs, len(arrs))
+                                                ctypes.c_longlong(s1), ctypes.c_longlong(s2), ptrs, len(arrs), ctypes.c_longlong(iteration))

@@ -90,6 +90,11 @@ APPS = {
     'katzer_allprinted': (REF + '/apps/katzer_SBLI/katzer_SBLI.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None, {'OSB_FORCE_GENERIC_PATH': '1'}),
     'tcf_teno6_allprinted': (REF + '/apps/channel_flow/compressible_TCF_TENO/turbulent_channel.py',
                              [("stats = True", "stats = False"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None, {'OSB_FORCE_GENERIC_PATH': '1'}),
+    # the 3-D transitional SBLI app (TENO6-adaptive, time-periodic mass source sin(omega dt iter): the loop counter reaches the printed
+    # kernels) and the viscous shock tube (adiabatic walls, symmetry plane, a dataset that is read but never written)
+    'trans_allprinted': (REF + '/apps/transitional_SBLI/transitional_SBLI.py',
+                         [("stats = True", "stats = False"), ("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None, {'OSB_FORCE_GENERIC_PATH': '1'}),
+    'vst_allprinted': (REF + '/apps/viscous_shock_tube/viscous_shock_tube.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None, {'OSB_FORCE_GENERIC_PATH': '1'}),
     'ewc_allprinted': (REF + '/apps/euler_wave_curvilinear/euler_wave.py', [("OPSC(alg)", "from opensbli_b200 import B200\nB200(alg)")], None, {'OSB_FORCE_GENERIC_PATH': '1'}),
     # InletTransferBC has no hand-written kernel: generic by itself (Sod with the left boundary copied from its first halo point)
     'sod_inlet_transfer': (REF + '/apps/Sod_shock_tube/Sod_shock_tube.py', [("boundaries += [DirichletBC(direction, 0, left_eqns)]", "boundaries += [InletTransferBC(direction, 0)]"),

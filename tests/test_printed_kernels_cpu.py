@@ -125,11 +125,11 @@ def run_generic_on_host(plan_sym, plan, cold, nsteps, state=None, fields=None):
         hk.fields[n] = np.ascontiguousarray(a).copy()
     for n, a in (fields or {}).items():
         hk.fields[n] = np.ascontiguousarray(a).copy()
-    for _ in range(nsteps):
-        hk.run('iteration_start')
+    for it in range(nsteps):
+        hk.run('iteration_start', it)
         for s in range(plan['generic']['nstages']):
-            hk.run('stage_%d' % s)
-        hk.run('iteration_end')
+            hk.run('stage_%d' % s, it)
+        hk.run('iteration_end', it)
     return hk
 
 
@@ -176,7 +176,9 @@ def test_bench_workloads_through_the_generic_path(name, fixture):
 
 @pytest.mark.parametrize('name,fixture,over,nsteps', [('katzer_allprinted', 'katzer_60x40', {'block0np0': 60, 'block0np1': 40}, 10),
                                                       ('ewc_allprinted', 'ewc_wenoz5_32', {'block0np0': 32, 'block0np1': 32}, 10),
-                                                      ('tcf_teno6_allprinted', 'tcf_teno6_16x24x12', {'block0np0': 16, 'block0np1': 24, 'block0np2': 12}, 5)])
+                                                      ('tcf_teno6_allprinted', 'tcf_teno6_16x24x12', {'block0np0': 16, 'block0np1': 24, 'block0np2': 12}, 5),
+                                                      ('trans_allprinted', 'trans_40x30x8', {'block0np0': 40, 'block0np1': 30, 'block0np2': 8}, 5),
+                                                      ('vst_allprinted', 'vst_60x30', {'block0np0': 60, 'block0np1': 30}, 10)])
 def test_general_path_apps_through_the_generic_path(name, fixture, over, nsteps):
     """Three apps of the general path FORCED through the generic path: Katzer (stretched grid, ReducedAccess closures selected by
     grid index, adaptive TENO with the Ducros sensor, isothermal wall / inflow / outflow / tabulated Dirichlet kernels), the 3-D
@@ -188,8 +190,8 @@ def test_general_path_apps_through_the_generic_path(name, fixture, over, nsteps)
     want, states = load_fixture(fixture)
     plan_sym, env, plan, cold = R.load_case(os.path.join(PLANS, name), overrides=over)
     assert plan['conv'] == 'generic'
-    state = want.get('q0_padded') if name.startswith('katzer') else None
-    fields = {k: v for k, v in want.get('fields', {}).items()} if name.startswith('katzer') else None
+    state = want.get('q0_padded')            # general-path fixtures carry the reference's own cold data (initial state incl. halos, metrics)
+    fields = want.get('fields')
     hk = run_generic_on_host(plan_sym, plan, cold, nsteps, state=state, fields=fields)
     nd = plan['ndim']
     got = np.stack([hk.fields[f][(slice(5, -5),) * nd] for f in plan_sym['q_names']])
